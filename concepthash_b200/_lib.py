@@ -1,0 +1,107 @@
+"""ctypes binding of include/concepthash_b200.h.  Fails loudly: there is no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libconcepthash_b200.so")
+
+CH_F32, CH_F16, CH_BF16, CH_F64, CH_I64, CH_I32, CH_U8, CH_I16, CH_I8 = range(9)
+CH_MEM_DEVICE, CH_MEM_HOST = 0, 1
+CH_LAB_NONE, CH_LAB_ID, CH_LAB_MASK = 0, 1, 2
+CH_EMIT_NONE, CH_EMIT_RELEVANT, CH_EMIT_CANDIDATES = 0, 1, 2
+CH_QUERY_NOLABEL, CH_GALLERY_NOLABEL = 0xFFFFFFFF, 0xFFFFFFFE
+CH_MAX_NBIT, CH_MAX_R, CH_MAX_PR = 256, 8, 32
+
+P = C.c_void_p
+
+
+class HistArgs(C.Structure):
+    _fields_ = [(n, P) for n in ("q_bits", "q_nz", "g_bits", "g_nz", "q_lab", "g_lab", "slab_all", "slab_rel",
+                                 "thresh", "rec_off", "rec_cap", "rec_cnt", "recs", "err_flag")] + \
+               [(n, C.c_int64) for n in ("nq", "nq_pad", "ndb")] + \
+               [(n, C.c_int32) for n in ("nbit", "ternary", "label_mode", "mask_words", "emit_mode",
+                                         "nstripes", "threads", "rows_per_stripe")]
+
+
+class FinalArgs(C.Structure):
+    _fields_ = [(n, P) for n in ("recs", "rec_off", "rec_cnt", "base0_all", "base0_rel", "sbase_all", "sbase_rel",
+                                 "first_rel", "partial", "cols")] + \
+               [(n, C.c_int64) for n in ("nq", "nq_pad")] + \
+               [(n, C.c_int32) for n in ("nstripes", "nbins", "remove_first", "nR", "nPR")] + \
+               [("r_eff", C.c_int64 * CH_MAX_R), ("pr_k", C.c_int64 * CH_MAX_PR)]
+
+
+# name -> (restype, argtypes); the authoritative list of exported symbols (tests check it against the header)
+SIGNATURES = {
+    "ch_abi_version": (C.c_int, []),
+    "ch_last_error": (C.c_char_p, []),
+    "ch_workspace_create": (C.c_int, [C.c_int, C.POINTER(P)]),
+    "ch_workspace_destroy": (C.c_int, [P]),
+    "ch_device_info": (C.c_int, [P] + [C.POINTER(C.c_int)] * 4),
+    "ch_padded_rows": (C.c_int64, [C.c_int64]),
+    "ch_code_words": (C.c_int, [C.c_int]),
+    "ch_pack_sign": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_double,
+                               P, P, P, P]),
+    "ch_pack_labels": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_uint32,
+                                 P, P, P, P]),
+    "ch_hist_geometry": (C.c_int, [P, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int32),
+                                   C.POINTER(C.c_int32)]),
+    "ch_hamming_hist": (C.c_int, [P, C.POINTER(HistArgs), P]),
+    "ch_slab_totals": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int64, P, P]),
+    "ch_slab_exscan": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int64, P]),
+    "ch_scan_bases": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, P, P, P, P]),
+    "ch_record_caps": (C.c_int, [P, C.c_int, P, P, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, P, P]),
+    "ch_record_offsets": (C.c_int, [P, P, C.c_int, C.c_int64, C.c_int64, P, C.POINTER(C.c_uint64), P]),
+    "ch_class_counts": (C.c_int, [P, P, C.c_int64, C.c_int, C.c_int, P, P]),
+    "ch_finalize_records": (C.c_int, [P, C.POINTER(FinalArgs), P]),
+    "ch_first_relevant": (C.c_int, [P, C.POINTER(FinalArgs), P, P]),
+    "ch_reduce_means": (C.c_int, [P, P, P, P, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), P,
+                                  C.POINTER(C.c_double), P]),
+    "ch_scatter_ranked": (C.c_int, [P, C.POINTER(FinalArgs), C.c_int64, C.c_int64, P, P, P]),
+    "ch_ap_from_ranked": (C.c_int, [P, P, C.c_int64, C.c_int64, P, P, C.c_int, C.c_int, C.c_int,
+                                    C.POINTER(C.c_int64), P, P]),
+    "ch_hamming_matrix": (C.c_int, [P, P, P, P, P, C.c_int64, C.c_int64, C.c_int, C.c_int, P, P]),
+    "ch_popc_peak": (C.c_int, [P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "ch_launch_count": (C.c_int64, [P]),
+}
+
+_lib = None
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads libconcepthash_b200.so (built in-tree by ``python -m concepthash_b200.build``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError(
+            f"{LIB_PATH} is missing: build it with `python -m concepthash_b200.build` "
+            "(needs nvcc; sm_100a only).  There is no CPU fallback.")
+    try:
+        lib = C.CDLL(LIB_PATH)
+    except OSError as e:  # e.g. libcudart not found
+        raise NativeLibraryError(f"cannot load {LIB_PATH}: {e}") from e
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise NativeLibraryError(f"{LIB_PATH} does not export {name}") from e
+        fn.restype = res
+        fn.argtypes = args
+    if lib.ch_abi_version() != 1:
+        raise NativeLibraryError("ABI version mismatch: rebuild the library")
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().ch_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"concepthash_b200 {what} failed: {msg}")

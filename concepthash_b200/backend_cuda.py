@@ -1,0 +1,242 @@
+"""Thin torch-tensor wrappers over the C-ABI (one method per exported kernel entry point).
+
+torch is plumbing here: it owns device memory, the current stream and (in ``evaluator``) the NCCL
+collectives.  All arithmetic of the hot path runs in libconcepthash_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+_DTYPES = {
+    torch.float32: L.CH_F32, torch.float16: L.CH_F16, torch.bfloat16: L.CH_BF16, torch.float64: L.CH_F64,
+    torch.int64: L.CH_I64, torch.int32: L.CH_I32, torch.uint8: L.CH_U8, torch.int16: L.CH_I16,
+    torch.int8: L.CH_I8,
+}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class CudaBackend:
+    """One instance per process / GPU (owns a ``ch_ws`` workspace)."""
+
+    name = "cuda"
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("concepthash_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = L.load()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else
+                                   (device.index if isinstance(device, torch.device) else int(device)))
+        ws = C.c_void_p()
+        L.check(self.lib.ch_workspace_create(self.device.index, C.byref(ws)), "ch_workspace_create")
+        self.ws = ws
+        sm, smem, l2, khz = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        L.check(self.lib.ch_device_info(self.ws, C.byref(sm), C.byref(smem), C.byref(l2), C.byref(khz)))
+        self.sm_count, self.max_smem, self.l2_bytes, self.clock_khz = sm.value, smem.value, l2.value, khz.value
+
+    def __del__(self):
+        try:
+            if getattr(self, "ws", None):
+                self.lib.ch_workspace_destroy(self.ws)
+                self.ws = None
+        except Exception:
+            pass
+
+    # ---- plumbing ----
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def zeros(self, shape, dtype):
+        return torch.zeros(shape, dtype=dtype, device=self.device)
+
+    def empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def full(self, shape, value, dtype):
+        return torch.full(shape, value, dtype=dtype, device=self.device)
+
+    def to_host(self, t):
+        return t.cpu()
+
+    def padded_rows(self, n):
+        return int(self.lib.ch_padded_rows(int(n)))
+
+    def code_words(self, nbit):
+        return int(self.lib.ch_code_words(int(nbit)))
+
+    def launch_count(self):
+        return int(self.lib.ch_launch_count(self.ws))
+
+    # ---- K1 ----
+    def _src(self, t):
+        """(tensor kept alive, mem kind) for a caller tensor: CUDA tensors are used in place, CPU tensors
+        are handed to the library as host pointers (it stages them in pipelined chunks)."""
+        if t.dtype == torch.bool:
+            t = t.to(torch.uint8)
+        if t.dtype not in _DTYPES:
+            t = t.to(torch.float32)
+        if t.is_cuda:
+            if t.device != self.device:
+                t = t.to(self.device)
+            return t, L.CH_MEM_DEVICE
+        if t.dim() == 2 and t.stride(1) != 1 or (t.dim() == 2 and t.shape[0] > 1 and t.stride(0) < t.shape[1]):
+            t = t.contiguous()
+        return t, L.CH_MEM_HOST
+
+    def pack_sign(self, codes, threshold, flags):
+        """codes (n, nbit) real -> (bits, nz) u32 (rows_pad, words); ``flags`` u32[1] is OR-ed."""
+        n, nbit = codes.shape
+        words = self.code_words(nbit)
+        if words == 0:
+            raise ValueError(f"nbit={nbit} unsupported (1..{L.CH_MAX_NBIT})")
+        if not codes.dtype.is_floating_point:
+            codes = codes.to(torch.float32)
+        t, mem = self._src(codes)
+        rows = self.padded_rows(n)
+        bits = self.empty((rows, words), torch.int32)
+        nz = self.empty((rows, words), torch.int32)
+        thr = float(threshold)
+        if thr != 0.0:   # torch compares `codes.abs() < threshold` in the dtype of codes
+            thr = float(torch.tensor(thr, dtype=t.dtype))
+        rs = t.stride(0) if n > 1 else nbit
+        L.check(self.lib.ch_pack_sign(self.ws, _ptr(t), mem, _DTYPES[t.dtype], n, nbit, rs,
+                                      t.stride(1) if nbit > 1 else 1, thr, _ptr(bits), _ptr(nz), _ptr(flags),
+                                      self._stream()), "ch_pack_sign")
+        return bits, nz
+
+    def pack_labels(self, labels, nolabel):
+        """labels (n, C) one-/multi-hot or (n,) ids -> (ids u32 (rows_pad), masks (rows_pad, lw) | None, info u32[4])."""
+        t, mem = self._src(labels)
+        n = t.shape[0]
+        rows = self.padded_rows(n)
+        ids = self.empty((rows,), torch.int32)
+        info = self.zeros((4,), torch.int32)
+        if t.dim() == 2:
+            ncls = t.shape[1]
+            lw = (ncls + 31) // 32
+            masks = self.empty((rows, max(lw, 1)), torch.int32)
+            rs = t.stride(0) if n > 1 else ncls
+            L.check(self.lib.ch_pack_labels(self.ws, _ptr(t), mem, _DTYPES[t.dtype], n, ncls, rs,
+                                            t.stride(1) if ncls > 1 else 1, nolabel, _ptr(ids), _ptr(masks),
+                                            _ptr(info), self._stream()), "ch_pack_labels")
+            return ids, masks, info
+        if t.dtype in (torch.float16, torch.bfloat16):
+            t = t.to(torch.float32)
+        L.check(self.lib.ch_pack_labels(self.ws, _ptr(t), mem, _DTYPES[t.dtype], n, 0,
+                                        t.stride(0) if n > 1 else 1, 1, nolabel, _ptr(ids), None, _ptr(info),
+                                        self._stream()), "ch_pack_labels")
+        return ids, None, info
+
+    # ---- K2 ----
+    def geometry(self, nq, ndb, nbit, ternary, label_mode, lw):
+        th, st, rps = C.c_int32(), C.c_int32(), C.c_int32()
+        nqp = C.c_int64()
+        L.check(self.lib.ch_hist_geometry(self.ws, nq, ndb, nbit, int(ternary), label_mode, lw, C.byref(th),
+                                          C.byref(nqp), C.byref(st), C.byref(rps)), "ch_hist_geometry")
+        return th.value, nqp.value, st.value, rps.value
+
+    def hamming_hist(self, *, q_bits, q_nz, g_bits, g_nz, q_lab, g_lab, slab_all, slab_rel, thresh, rec_off,
+                     rec_cap, rec_cnt, recs, err_flag, nq, nq_pad, ndb, nbit, ternary, label_mode, mask_words,
+                     emit_mode, nstripes, threads, rows_per_stripe):
+        a = L.HistArgs()
+        for k, v in dict(q_bits=q_bits, q_nz=q_nz if ternary else None, g_bits=g_bits,
+                         g_nz=g_nz if ternary else None, q_lab=q_lab, g_lab=g_lab, slab_all=slab_all,
+                         slab_rel=slab_rel, thresh=thresh, rec_off=rec_off, rec_cap=rec_cap, rec_cnt=rec_cnt,
+                         recs=recs, err_flag=err_flag).items():
+            setattr(a, k, v.data_ptr() if v is not None else None)
+        a.nq, a.nq_pad, a.ndb = nq, nq_pad, ndb
+        a.nbit, a.ternary, a.label_mode, a.mask_words, a.emit_mode = nbit, int(ternary), label_mode, mask_words, emit_mode
+        a.nstripes, a.threads, a.rows_per_stripe = nstripes, threads, rows_per_stripe
+        L.check(self.lib.ch_hamming_hist(self.ws, C.byref(a), self._stream()), "ch_hamming_hist")
+
+    def slab_totals(self, slab, nstripes, nbins, nq_pad, out):
+        L.check(self.lib.ch_slab_totals(self.ws, _ptr(slab), nstripes, nbins, nq_pad, _ptr(out), self._stream()),
+                "ch_slab_totals")
+
+    def slab_exscan(self, slab, nstripes, nbins, nq_pad):
+        L.check(self.lib.ch_slab_exscan(self.ws, _ptr(slab), nstripes, nbins, nq_pad, self._stream()),
+                "ch_slab_exscan")
+
+    def class_counts(self, g_ids, ndb, rows_per_stripe, nclass, cls):
+        L.check(self.lib.ch_class_counts(self.ws, _ptr(g_ids), ndb, rows_per_stripe, nclass, _ptr(cls),
+                                         self._stream()), "ch_class_counts")
+
+    # ---- K3 ----
+    def scan_bases(self, tot_all, world, rank, nbins, nq, nq_pad, rmax, base0, thresh, total):
+        L.check(self.lib.ch_scan_bases(self.ws, _ptr(tot_all), world, rank, nbins, nq, nq_pad, rmax, _ptr(base0),
+                                       _ptr(thresh), _ptr(total), self._stream()), "ch_scan_bases")
+
+    def record_caps(self, source, a0, a1, nstripes, nb, nq, nq_pad, min_with_prev, cap):
+        L.check(self.lib.ch_record_caps(self.ws, source, _ptr(a0), _ptr(a1), nstripes, nb, nq, nq_pad,
+                                        int(min_with_prev), _ptr(cap), self._stream()), "ch_record_caps")
+
+    def record_offsets(self, cap, nstripes, nq, nq_pad, off):
+        total = C.c_uint64()
+        L.check(self.lib.ch_record_offsets(self.ws, _ptr(cap), nstripes, nq, nq_pad, _ptr(off), C.byref(total),
+                                           self._stream()), "ch_record_offsets")
+        return int(total.value)
+
+    # ---- K4 ----
+    def _final_args(self, f):
+        a = L.FinalArgs()
+        for k in ("recs", "rec_off", "rec_cnt", "base0_all", "base0_rel", "sbase_all", "sbase_rel", "first_rel",
+                  "partial", "cols"):
+            v = f.get(k)
+            setattr(a, k, v.data_ptr() if v is not None else None)
+        a.nq, a.nq_pad, a.nstripes, a.nbins = f["nq"], f["nq_pad"], f["nstripes"], f["nbins"]
+        a.remove_first = int(f.get("remove_first", False))
+        r_eff, pr_k = list(f.get("r_eff", [])), list(f.get("pr_k", []))
+        if len(r_eff) > L.CH_MAX_R or len(pr_k) > L.CH_MAX_PR:
+            raise ValueError(f"at most {L.CH_MAX_R} R values and {L.CH_MAX_PR} PRs cut-offs are supported")
+        a.nR, a.nPR = len(r_eff), len(pr_k)
+        for i, v in enumerate(r_eff):
+            a.r_eff[i] = int(v)
+        for i, v in enumerate(pr_k):
+            a.pr_k[i] = int(v)
+        return a
+
+    def finalize_records(self, f):
+        L.check(self.lib.ch_finalize_records(self.ws, C.byref(self._final_args(f)), self._stream()),
+                "ch_finalize_records")
+
+    def first_relevant(self, f, out):
+        L.check(self.lib.ch_first_relevant(self.ws, C.byref(self._final_args(f)), _ptr(out), self._stream()),
+                "ch_first_relevant")
+
+    def reduce_means(self, cols, total_rel, first_rel, nq, n_r, pr_k, ap_out=None):
+        n_pr = len(pr_k)
+        out = (C.c_double * max(1, n_r + 2 * n_pr))()
+        prk = (C.c_int64 * max(1, n_pr))(*[int(k) for k in pr_k])
+        L.check(self.lib.ch_reduce_means(self.ws, _ptr(cols), _ptr(total_rel), _ptr(first_rel), nq, n_r, n_pr, prk,
+                                         _ptr(ap_out), out, self._stream()), "ch_reduce_means")
+        vals = [float(out[i]) for i in range(n_r + 2 * n_pr)]
+        return vals[:n_r], vals[n_r:n_r + n_pr], vals[n_r + n_pr:]
+
+    def scatter_ranked(self, f, R, row_offset, ids, keys):
+        L.check(self.lib.ch_scatter_ranked(self.ws, C.byref(self._final_args(f)), R, row_offset, _ptr(ids),
+                                           _ptr(keys), self._stream()), "ch_scatter_ranked")
+
+    def ap_from_ranked(self, ids, nq, R, q_lab, g_lab, label_mode, mask_words, pr_k, cols):
+        prk = (C.c_int64 * max(1, len(pr_k)))(*[int(k) for k in pr_k])
+        L.check(self.lib.ch_ap_from_ranked(self.ws, _ptr(ids), nq, R, _ptr(q_lab), _ptr(g_lab), label_mode,
+                                           mask_words, len(pr_k), prk, _ptr(cols), self._stream()),
+                "ch_ap_from_ranked")
+
+    # ---- small ----
+    def hamming_matrix(self, q_bits, q_nz, g_bits, g_nz, nq, ndb, nbit, ternary):
+        out = self.empty((nq, ndb), torch.int16)
+        L.check(self.lib.ch_hamming_matrix(self.ws, _ptr(q_bits), _ptr(q_nz) if ternary else None, _ptr(g_bits),
+                                           _ptr(g_nz) if ternary else None, nq, ndb, nbit, int(ternary), _ptr(out),
+                                           self._stream()), "ch_hamming_matrix")
+        return out
+
+    def popc_peak(self):
+        rate, ms = C.c_double(), C.c_double()
+        L.check(self.lib.ch_popc_peak(self.ws, C.byref(rate), C.byref(ms)), "ch_popc_peak")
+        return rate.value, ms.value

@@ -1,0 +1,104 @@
+// Workspace, error reporting and device queries of the C-ABI (include/concepthash_b200.h).
+#include <stdarg.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void ch_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+struct ch_ws_priv {
+  ch_ws pub;
+  void* scratch;
+  size_t scratch_bytes;
+};
+
+// grow-only device scratch shared by the small helper kernels (all calls are stream-ordered by the caller)
+int ch_ws_scratch(ch_ws* ws, size_t bytes, void** out) {
+  ch_ws_priv* p = reinterpret_cast<ch_ws_priv*>(ws);
+  if (bytes > p->scratch_bytes) {
+    if (p->scratch) CH_CUDA(cudaFree(p->scratch));  // cudaFree waits for outstanding work
+    p->scratch = nullptr;
+    p->scratch_bytes = 0;
+    const size_t want = ch_round_up(static_cast<int64_t>(bytes), 1 << 20);
+    CH_CUDA(cudaMalloc(&p->scratch, want));
+    p->scratch_bytes = want;
+  }
+  *out = p->scratch;
+  return 0;
+}
+
+extern "C" int ch_abi_version(void) { return CH_ABI_VERSION; }
+extern "C" const char* ch_last_error(void) { return g_err; }
+
+extern "C" int ch_workspace_create(int device, ch_ws** out) {
+  if (out == nullptr) CH_FAIL("null out pointer");
+  *out = nullptr;
+  int count = 0;
+  CH_CUDA(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) CH_FAIL("device %d out of range (found %d CUDA devices)", device, count);
+  cudaDeviceProp prop;
+  CH_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    CH_FAIL("concepthash_b200 is built for sm_100a only; device %d is sm_%d%d (%s)", device, prop.major, prop.minor,
+            prop.name);
+  ChDeviceGuard guard(device);
+  ch_ws_priv* p = new ch_ws_priv();
+  memset(p, 0, sizeof(*p));
+  ch_ws* ws = &p->pub;
+  ws->device = device;
+  ws->sm_count = prop.multiProcessorCount;
+  ws->max_smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+  ws->l2_bytes = prop.l2CacheSize;
+  int khz = 0;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+  ws->clock_khz = khz;
+  ws->stage_bytes = static_cast<size_t>(64) << 20;
+  for (int i = 0; i < 2; ++i) {
+    ws->stage[i] = nullptr;
+    CH_CUDA(cudaEventCreateWithFlags(&ws->ev_copied[i], cudaEventDisableTiming));
+    CH_CUDA(cudaEventCreateWithFlags(&ws->ev_consumed[i], cudaEventDisableTiming));
+  }
+  CH_CUDA(cudaStreamCreateWithFlags(&ws->copy_stream, cudaStreamNonBlocking));
+  *out = ws;
+  return 0;
+}
+
+// staging buffers are allocated on first host-side use
+int ch_ws_ensure_stage(ch_ws* ws) {
+  for (int i = 0; i < 2; ++i)
+    if (ws->stage[i] == nullptr) CH_CUDA(cudaMalloc(&ws->stage[i], ws->stage_bytes));
+  return 0;
+}
+
+extern "C" int ch_workspace_destroy(ch_ws* ws) {
+  if (ws == nullptr) return 0;
+  ch_ws_priv* p = reinterpret_cast<ch_ws_priv*>(ws);
+  ChDeviceGuard guard(ws->device);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < 2; ++i) {
+    if (ws->stage[i]) cudaFree(ws->stage[i]);
+    cudaEventDestroy(ws->ev_copied[i]);
+    cudaEventDestroy(ws->ev_consumed[i]);
+  }
+  cudaStreamDestroy(ws->copy_stream);
+  if (p->scratch) cudaFree(p->scratch);
+  delete p;
+  return 0;
+}
+
+extern "C" int ch_device_info(ch_ws* ws, int* sm_count, int* max_smem_optin, int* l2_bytes, int* clock_khz) {
+  if (ws == nullptr) CH_FAIL("null workspace");
+  if (sm_count) *sm_count = ws->sm_count;
+  if (max_smem_optin) *max_smem_optin = ws->max_smem_optin;
+  if (l2_bytes) *l2_bytes = ws->l2_bytes;
+  if (clock_khz) *clock_khz = ws->clock_khz;
+  return 0;
+}
+
+extern "C" int64_t ch_launch_count(ch_ws* ws) { return ws ? ws->launches : 0; }

@@ -1,0 +1,528 @@
+// K2: Hamming distances (XOR + POPC on the integer pipes) fused with the per-query key histogram and
+// the stable in-bucket prefixes the exact top-R selection / AP need.  Nothing of size (nq, ndb) is
+// ever written.
+//
+// Mapping.  One THREAD owns one query (its packed code stays in registers); one CTA owns `threads`
+// queries x one gallery stripe (a contiguous block of gallery rows).  The stripe is streamed through
+// shared memory in tiles by 1-D bulk async copies (cp.async.bulk + mbarrier, the TMA engine; SASS
+// UBLKCP), double-buffered; every thread reads the same gallery word at the same time (shared-memory
+// broadcast) and walks the tile IN ROW ORDER.  The thread's private histogram lives in shared memory,
+// laid out [key][thread] so that lane l always hits bank l (conflict-free without atomics); one u32
+// per key holds {lo16: items seen, hi16: relevant items seen}.  Because the walk is in row order the
+// value read back BEFORE the increment is exactly the stable in-bucket prefix
+//     p(j) = #{k < j in this stripe : key_k == key_j}
+// which is what "ties by ascending gallery row index" needs.  For the rare relevant (or candidate)
+// pair the thread appends a 16-byte record {key, p_all, p_rel, row} to its own pre-sized slice of the
+// record buffer: no atomics and no divergence-heavy code in the loop.  Counters are flushed into the
+// (stripe, key, query) slabs in global memory before any u16 can overflow.
+//
+// Per pair (64-bit codes): 2 LOP3 + 2 POPC + 1 IADD3 (distance), 1 ISETP + 1 SEL (relevance), 1 IMAD
+// (address), LDS + IADD + STS (histogram) and 1/4 LDS.128 x2 (gallery code + label broadcast).
+// The limiter is the POPC pipe (16 lanes / clk / SM): algorithmic popc32 ops per pair = words.
+#include "common.cuh"
+
+namespace {
+
+struct HistDev {
+  const uint32_t* q_bits; const uint32_t* q_nz;
+  const uint32_t* g_bits; const uint32_t* g_nz;
+  const uint32_t* q_lab;  const uint32_t* g_lab;
+  uint32_t* slab_all; uint32_t* slab_rel;
+  const uint32_t* thresh;
+  const uint32_t* rec_off; const uint32_t* rec_cap; uint32_t* rec_cnt; uint4* recs;
+  uint32_t* err_flag;
+  long long nq, nq_pad, ndb;
+  int nbit, nbins, lw, emit_mode;
+  int nqtiles, rows_per_stripe, tile_rows, flush_tiles;
+};
+
+constexpr int kStages = 2;
+
+__host__ __device__ inline int tile_rows_for(int nw, bool tern, int label_mode, int lw) {
+  int t = nw <= 2 ? 256 : (nw == 4 ? 128 : 64);
+  if (tern) t /= 2;
+  if (label_mode == CH_LAB_MASK)
+    while (t > 32 && t * lw * 4 > 4096) t /= 2;
+  return t;
+}
+
+struct SmemPlan {
+  size_t hist, qmask, stage_bits, stage_nz, stage_lab, stage, bars, total;
+};
+
+inline SmemPlan smem_plan(int nbins, int threads, int nw, bool tern, int label_mode, int lw, int tile) {
+  SmemPlan p;
+  p.hist = static_cast<size_t>(nbins) * threads * 4;
+  p.hist = (p.hist + 15) / 16 * 16;
+  p.qmask = label_mode == CH_LAB_MASK ? static_cast<size_t>(lw) * threads * 4 : 0;
+  p.qmask = (p.qmask + 15) / 16 * 16;
+  p.stage_bits = static_cast<size_t>(tile) * nw * 4;
+  p.stage_nz = tern ? p.stage_bits : 0;
+  p.stage_lab = label_mode == CH_LAB_NONE ? 0 : static_cast<size_t>(tile) * (label_mode == CH_LAB_ID ? 1 : lw) * 4;
+  p.stage = p.stage_bits + p.stage_nz + p.stage_lab;
+  p.bars = 16 * kStages;
+  p.total = p.hist + p.qmask + kStages * p.stage + p.bars;
+  return p;
+}
+
+template <int NW, bool TERN>
+__device__ __forceinline__ uint32_t pair_key(const uint32_t (&qb)[NW], const uint32_t (&qz)[NW],
+                                             const uint32_t (&gb)[NW], const uint32_t (&gz)[NW], int nbit) {
+  if constexpr (!TERN) {
+    uint32_t d = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) d += __popc(qb[w] ^ gb[w]);
+    return d;
+  } else {
+    // sign(0) = 0: only positions non-zero on both sides contribute +-1 to the inner product
+    // key = 2 * dist = nbit - popc(M) + 2 * popc((sq ^ sg) & M),  M = nzq & nzg
+    uint32_t both = 0, dis = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const uint32_t m = qz[w] & gz[w];
+      both += __popc(m);
+      dis += __popc((qb[w] ^ gb[w]) & m);
+    }
+    return static_cast<uint32_t>(nbit) - both + 2u * dis;
+  }
+}
+
+template <int NW, bool TERN, int LAB, bool THRESH>
+__global__ void __launch_bounds__(256, (NW <= 2 && !TERN) ? 3 : 1) hamming_hist_kernel(const HistDev a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int T = blockDim.x;
+  const int tid = threadIdx.x;
+  const int TILE = a.tile_rows;
+  const int lws = LAB == CH_LAB_ID ? 1 : (LAB == CH_LAB_MASK ? a.lw : 0);
+
+  // ---- shared memory carve-up (must match smem_plan) ----
+  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw);
+  size_t off = (static_cast<size_t>(a.nbins) * T * 4 + 15) / 16 * 16;
+  uint32_t* qmask = reinterpret_cast<uint32_t*>(smem_raw + off);
+  if (LAB == CH_LAB_MASK) off += (static_cast<size_t>(a.lw) * T * 4 + 15) / 16 * 16;
+  const size_t stage_bits = static_cast<size_t>(TILE) * NW * 4;
+  const size_t stage_nz = TERN ? stage_bits : 0;
+  const size_t stage_lab = static_cast<size_t>(TILE) * lws * 4;
+  const size_t stage_bytes = stage_bits + stage_nz + stage_lab;
+  unsigned char* stage0 = smem_raw + off;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + kStages * stage_bytes);
+
+  const int qtile = blockIdx.x % a.nqtiles;
+  const int stripe = blockIdx.x / a.nqtiles;
+  const long long q = static_cast<long long>(qtile) * T + tid;
+  const bool active = q < a.nq;
+
+  // ---- this thread's query ----
+  uint32_t qb[NW], qz[NW];
+#pragma unroll
+  for (int w = 0; w < NW; ++w) {
+    qb[w] = active ? a.q_bits[q * NW + w] : 0u;
+    qz[w] = (TERN && active) ? a.q_nz[q * NW + w] : 0u;
+  }
+  uint32_t qid = CH_QUERY_NOLABEL;
+  if (LAB == CH_LAB_ID && active) qid = a.q_lab[q];
+  if (LAB == CH_LAB_MASK)
+    for (int w = 0; w < a.lw; ++w) qmask[w * T + tid] = active ? a.q_lab[q * a.lw + w] : 0u;
+  uint32_t thr = 0;
+  if (THRESH && active) thr = a.thresh[q];
+
+  for (int b = 0; b < a.nbins; ++b) hist[b * T + tid] = 0u;
+
+  const size_t sq = static_cast<size_t>(stripe) * a.nq_pad + q;  // (stripe, query) slot
+  uint32_t rptr = 0, rstart = 0, rend = 0;
+  if (a.emit_mode != CH_EMIT_NONE && active) {
+    rstart = a.rec_off[sq];
+    rend = rstart + a.rec_cap[sq];
+    rptr = rstart;
+  }
+  bool overflow = false;
+
+  // ---- stripe geometry ----
+  const long long row_begin = static_cast<long long>(stripe) * a.rows_per_stripe;
+  long long row_end = row_begin + a.rows_per_stripe;
+  if (row_end > a.ndb) row_end = a.ndb;
+  const int ntiles = row_end > row_begin ? static_cast<int>((row_end - row_begin + TILE - 1) / TILE) : 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int k) {
+    const long long r0 = row_begin + static_cast<long long>(k) * TILE;
+    long long rows = row_end - r0;
+    if (rows > TILE) rows = TILE;
+    const uint32_t rows4 = static_cast<uint32_t>((rows + 3) & ~3ll);  // pad rows exist (ch_padded_rows)
+    unsigned char* dst = stage0 + static_cast<size_t>(k % kStages) * stage_bytes;
+    uint64_t* bar = &bars[k % kStages];
+    const uint32_t bytes_bits = rows4 * NW * 4u;
+    const uint32_t bytes_lab = rows4 * static_cast<uint32_t>(lws) * 4u;
+    mbar_arrive_expect_tx(bar, bytes_bits * (TERN ? 2u : 1u) + bytes_lab);
+    bulk_g2s(dst, a.g_bits + r0 * NW, bytes_bits, bar);
+    if (TERN) bulk_g2s(dst + stage_bits, a.g_nz + r0 * NW, bytes_bits, bar);
+    if (LAB != CH_LAB_NONE) bulk_g2s(dst + stage_bits + stage_nz, a.g_lab + r0 * lws, bytes_lab, bar);
+  };
+
+  uint32_t epoch = 0;  // number of flushes so far (uniform over the CTA)
+  auto flush = [&]() {
+    for (int b = 0; b < a.nbins; ++b) {
+      const uint32_t v = hist[b * T + tid];
+      if (v != 0u) {
+        hist[b * T + tid] = 0u;
+        if (active) {
+          const size_t o = (static_cast<size_t>(stripe) * a.nbins + b) * a.nq_pad + q;
+          a.slab_all[o] += v & 0xffffu;
+          if (LAB != CH_LAB_NONE) a.slab_rel[o] += v >> 16;
+        }
+      }
+    }
+    ++epoch;
+  };
+
+  // one (query, gallery row) pair; `glab` = gallery id (CH_LAB_ID), `gmask` = gallery mask row (CH_LAB_MASK)
+  auto visit = [&](uint32_t key, uint32_t glab, const uint32_t* __restrict__ gmask, uint32_t shard_row) {
+    if (THRESH && key > thr) return;
+    bool rel = false;
+    if constexpr (LAB == CH_LAB_ID) rel = glab == qid;
+    if constexpr (LAB == CH_LAB_MASK) {
+      uint32_t any = 0;
+      for (int w = 0; w < a.lw; ++w) any |= qmask[w * T + tid] & gmask[w];
+      rel = any != 0u;
+    }
+    const uint32_t idx = key * T + tid;
+    const uint32_t old = hist[idx];
+    hist[idx] = old + (rel ? 0x10001u : 1u);
+    if (a.emit_mode == CH_EMIT_CANDIDATES || (a.emit_mode == CH_EMIT_RELEVANT && rel)) {
+      if (active) {
+        uint32_t base_all = 0, base_rel = 0;
+        if (epoch != 0u) {  // counts already flushed to the slab belong to the prefix as well
+          const size_t o = (static_cast<size_t>(stripe) * a.nbins + key) * a.nq_pad + q;
+          base_all = a.slab_all[o];
+          if (LAB != CH_LAB_NONE) base_rel = a.slab_rel[o];
+        }
+        if (rptr < rend)
+          a.recs[rptr] = make_uint4(key | (rel ? 0x80000000u : 0u), base_all + (old & 0xffffu),
+                                    base_rel + (old >> 16), shard_row);
+        else
+          overflow = true;
+        ++rptr;
+      }
+    }
+  };
+
+  if (ntiles > 0 && tid == 0) issue(0);
+  for (int k = 0; k < ntiles; ++k) {
+    if (tid == 0 && k + 1 < ntiles) issue(k + 1);  // slot (k+1)%2 was released by the barrier ending tile k-1
+    mbar_wait(&bars[k % kStages], static_cast<uint32_t>((k / kStages) & 1));
+
+    const unsigned char* st = stage0 + static_cast<size_t>(k % kStages) * stage_bytes;
+    const uint32_t* gb = reinterpret_cast<const uint32_t*>(st);
+    const uint32_t* gz = reinterpret_cast<const uint32_t*>(st + stage_bits);
+    const uint32_t* gl = reinterpret_cast<const uint32_t*>(st + stage_bits + stage_nz);
+    long long rows_ll = row_end - (row_begin + static_cast<long long>(k) * TILE);
+    const int rows = rows_ll > TILE ? TILE : static_cast<int>(rows_ll);
+
+    const uint32_t shard_row0 = static_cast<uint32_t>(row_begin) + static_cast<uint32_t>(k) * TILE;
+    int i = 0;
+    if constexpr (NW <= 2) {
+      // groups of 4 rows: 128-bit broadcast loads of codes (and ids)
+      for (; i + 4 <= rows; i += 4) {
+        uint32_t g[4][NW], z[4][NW];
+        if constexpr (NW == 1) {
+          const uint4 v = *reinterpret_cast<const uint4*>(gb + i);
+          g[0][0] = v.x; g[1][0] = v.y; g[2][0] = v.z; g[3][0] = v.w;
+          if constexpr (TERN) {
+            const uint4 u = *reinterpret_cast<const uint4*>(gz + i);
+            z[0][0] = u.x; z[1][0] = u.y; z[2][0] = u.z; z[3][0] = u.w;
+          }
+        } else {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint4 v = *reinterpret_cast<const uint4*>(gb + (i + 2 * h) * 2);
+            g[2 * h][0] = v.x; g[2 * h][1] = v.y; g[2 * h + 1][0] = v.z; g[2 * h + 1][1] = v.w;
+            if constexpr (TERN) {
+              const uint4 u = *reinterpret_cast<const uint4*>(gz + (i + 2 * h) * 2);
+              z[2 * h][0] = u.x; z[2 * h][1] = u.y; z[2 * h + 1][0] = u.z; z[2 * h + 1][1] = u.w;
+            }
+          }
+        }
+        uint32_t lab4[4] = {0u, 0u, 0u, 0u};
+        if constexpr (LAB == CH_LAB_ID) {
+          const uint4 v = *reinterpret_cast<const uint4*>(gl + i);
+          lab4[0] = v.x; lab4[1] = v.y; lab4[2] = v.z; lab4[3] = v.w;
+        }
+        uint32_t key[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if constexpr (TERN) key[j] = pair_key<NW, TERN>(qb, qz, g[j], z[j], a.nbit);
+          else key[j] = pair_key<NW, TERN>(qb, qz, g[j], g[j], a.nbit);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          visit(key[j], lab4[j], gl + static_cast<size_t>(i + j) * lws, shard_row0 + i + j);
+      }
+    }
+    // wide codes, and the tail rows of the last tile: one row at a time
+    for (; i < rows; ++i) {
+      uint32_t g1[NW], z1[NW];
+      if constexpr (NW >= 4) {
+#pragma unroll
+        for (int w4 = 0; w4 < NW / 4; ++w4) {
+          const uint4 v = *reinterpret_cast<const uint4*>(gb + i * NW + w4 * 4);
+          g1[w4 * 4 + 0] = v.x; g1[w4 * 4 + 1] = v.y; g1[w4 * 4 + 2] = v.z; g1[w4 * 4 + 3] = v.w;
+          if constexpr (TERN) {
+            const uint4 u = *reinterpret_cast<const uint4*>(gz + i * NW + w4 * 4);
+            z1[w4 * 4 + 0] = u.x; z1[w4 * 4 + 1] = u.y; z1[w4 * 4 + 2] = u.z; z1[w4 * 4 + 3] = u.w;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+          g1[w] = gb[i * NW + w];
+          if constexpr (TERN) z1[w] = gz[i * NW + w];
+        }
+      }
+      uint32_t key;
+      if constexpr (TERN) key = pair_key<NW, TERN>(qb, qz, g1, z1, a.nbit);
+      else key = pair_key<NW, TERN>(qb, qz, g1, g1, a.nbit);
+      uint32_t lab1 = 0u;
+      if constexpr (LAB == CH_LAB_ID) lab1 = gl[i];
+      visit(key, lab1, gl + static_cast<size_t>(i) * lws, shard_row0 + i);
+    }
+    __syncthreads();  // everyone is done with this stage before it is refilled
+    if ((k + 1) % a.flush_tiles == 0 && k + 1 < ntiles) flush();
+  }
+  flush();
+
+  if (a.emit_mode != CH_EMIT_NONE && active) {
+    a.rec_cnt[sq] = (rptr < rend ? rptr : rend) - rstart;
+    if (overflow) atomicOr(a.err_flag, 1u);
+  }
+}
+
+// ---- slab reductions --------------------------------------------------------------------------------
+__global__ void slab_totals_kernel(const uint32_t* __restrict__ slab, int nstripes, long long plane,
+                                   uint32_t* __restrict__ tot) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= plane) return;
+  uint32_t s = 0;
+  for (int k = 0; k < nstripes; ++k) s += slab[static_cast<size_t>(k) * plane + i];
+  tot[i] = s;
+}
+__global__ void slab_exscan_kernel(uint32_t* __restrict__ slab, int nstripes, long long plane) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= plane) return;
+  uint32_t run = 0;
+  for (int k = 0; k < nstripes; ++k) {
+    const size_t o = static_cast<size_t>(k) * plane + i;
+    const uint32_t v = slab[o];
+    slab[o] = run;
+    run += v;
+  }
+}
+
+// per-stripe class histogram of single-label gallery ids
+__global__ void class_counts_kernel(const uint32_t* __restrict__ ids, long long ndb, int rows_per_stripe,
+                                    int nclass, uint32_t* __restrict__ cls) {
+  const long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= ndb) return;
+  const uint32_t id = ids[r];
+  if (id < static_cast<uint32_t>(nclass)) atomicAdd(cls + static_cast<size_t>(r / rows_per_stripe) * nclass + id, 1u);
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+typedef void (*hist_fn_t)(const HistDev);
+
+template <int NW, bool TERN, int LAB>
+hist_fn_t pick_thresh(bool thresh) {
+  return thresh ? hamming_hist_kernel<NW, TERN, LAB, true> : hamming_hist_kernel<NW, TERN, LAB, false>;
+}
+template <int NW, bool TERN>
+hist_fn_t pick_lab(int lab, bool thresh) {
+  switch (lab) {
+    case CH_LAB_NONE: return pick_thresh<NW, TERN, CH_LAB_NONE>(thresh);
+    case CH_LAB_ID: return pick_thresh<NW, TERN, CH_LAB_ID>(thresh);
+    default: return pick_thresh<NW, TERN, CH_LAB_MASK>(thresh);
+  }
+}
+template <int NW>
+hist_fn_t pick_tern(bool tern, int lab, bool thresh) {
+  return tern ? pick_lab<NW, true>(lab, thresh) : pick_lab<NW, false>(lab, thresh);
+}
+hist_fn_t pick_kernel(int nw, bool tern, int lab, bool thresh) {
+  switch (nw) {
+    case 1: return pick_tern<1>(tern, lab, thresh);
+    case 2: return pick_tern<2>(tern, lab, thresh);
+    case 4: return pick_tern<4>(tern, lab, thresh);
+    case 8: return pick_tern<8>(tern, lab, thresh);
+    default: return nullptr;
+  }
+}
+
+int pick_threads(int nbins, long long nq) {
+  int t = 256;
+  while (t > 32 && static_cast<size_t>(nbins) * t * 4 > 68 * 1024) t /= 2;
+  while (t > 32 && nq <= t / 2) t /= 2;  // few queries: smaller CTAs, more stripes
+  return t;
+}
+
+struct Geometry {
+  int threads, nstripes, rows_per_stripe, tile, flush_tiles, nqtiles;
+  long long nq_pad;
+  size_t smem;
+};
+
+int make_geometry(ch_ws* ws, long long nq, long long ndb, int nbit, bool tern, int lab, int lw, int forced_threads,
+                  int forced_stripes, int forced_rows_per_stripe, Geometry* g) {
+  const int nw = ch_code_words(nbit);
+  if (nw == 0) CH_FAIL("nbit=%d unsupported (1..%d)", nbit, CH_MAX_NBIT);
+  const int nbins = (tern ? 2 * nbit : nbit) + 1;
+  g->threads = forced_threads > 0 ? forced_threads : pick_threads(nbins, nq);
+  g->tile = tile_rows_for(nw, tern, lab, lw);
+  const SmemPlan p = smem_plan(nbins, g->threads, nw, tern, lab, lw, g->tile);
+  g->smem = p.total;
+  if (p.total > static_cast<size_t>(ws->max_smem_optin))
+    CH_FAIL("histogram needs %zu bytes of shared memory per CTA (nbit=%d ternary=%d classes/32=%d), device has %d",
+            p.total, nbit, tern ? 1 : 0, lw, ws->max_smem_optin);
+  g->nq_pad = ch_round_up(nq > 0 ? nq : 1, g->threads);
+  g->nqtiles = static_cast<int>(g->nq_pad / g->threads);
+  g->flush_tiles = 65535 / g->tile;
+  if (forced_stripes > 0) {
+    if (forced_rows_per_stripe <= 0 || forced_rows_per_stripe % 256 != 0 ||
+        static_cast<long long>(forced_stripes) * forced_rows_per_stripe < ndb)
+      CH_FAIL("bad stripe geometry: %d stripes x %d rows for %lld gallery rows", forced_stripes,
+              forced_rows_per_stripe, ndb);
+    g->nstripes = forced_stripes;
+    g->rows_per_stripe = forced_rows_per_stripe;
+    return 0;
+  } else {
+    // resident CTAs per SM by shared memory (1 KB reserved per CTA) and threads
+    long long per_sm = (228ll * 1024) / static_cast<long long>(p.total + 1024);
+    if (per_sm > 2048 / g->threads) per_sm = 2048 / g->threads;
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 32) per_sm = 32;
+    const long long slots = per_sm * ws->sm_count;
+    const long long max_stripes = ndb > 0 ? (ndb + g->tile - 1) / g->tile : 1;
+    // smallest stripe count in [lo, hi] with the best wave efficiency (>= 2 waves when the gallery allows)
+    long long lo = (2 * slots + g->nqtiles - 1) / g->nqtiles;
+    if (lo < 1) lo = 1;
+    long long hi = (8 * slots + g->nqtiles - 1) / g->nqtiles;
+    if (lo > max_stripes) lo = max_stripes;
+    if (hi > max_stripes) hi = max_stripes;
+    if (hi > 4096) hi = 4096;
+    if (lo > hi) lo = hi;
+    long long best = lo;
+    double best_eff = -1.0;
+    for (long long s = lo; s <= hi; ++s) {
+      const long long ctas = s * g->nqtiles;
+      const long long waves = (ctas + slots - 1) / slots;
+      const double eff = static_cast<double>(ctas) / static_cast<double>(waves * slots);
+      if (eff > best_eff + 1e-9) {
+        best_eff = eff;
+        best = s;
+      }
+    }
+    g->nstripes = static_cast<int>(best);
+  }
+  // stripe boundaries are multiples of 256 rows (>= every tile size, so every pass of one evaluation --
+  // whatever its label mode -- sees the same stripes and every bulk copy starts 16-byte aligned)
+  long long rps = ndb > 0 ? (ndb + g->nstripes - 1) / g->nstripes : 256;
+  rps = ch_round_up(rps, 256);
+  if (rps > 0x7fffff00ll) CH_FAIL("gallery shard too large for one stripe");
+  g->rows_per_stripe = static_cast<int>(rps);
+  g->nstripes = ndb > 0 ? static_cast<int>((ndb + rps - 1) / rps) : 1;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int ch_hist_geometry(ch_ws* ws, int64_t nq, int64_t ndb, int nbit, int ternary, int label_mode,
+                                int mask_words, int32_t* threads, int64_t* nq_pad, int32_t* nstripes,
+                                int32_t* rows_per_stripe) {
+  if (ws == nullptr) CH_FAIL("null workspace");
+  Geometry g;
+  if (make_geometry(ws, nq, ndb, nbit, ternary != 0, label_mode, mask_words, 0, 0, 0, &g)) return 1;
+  // computed once per evaluation (with the richest label mode) and handed back to every
+  // ch_hamming_hist call, so all passes share the same (threads, stripes, rows per stripe)
+  if (threads) *threads = g.threads;
+  if (nq_pad) *nq_pad = g.nq_pad;
+  if (nstripes) *nstripes = g.nstripes;
+  if (rows_per_stripe) *rows_per_stripe = g.rows_per_stripe;
+  return 0;
+}
+
+extern "C" int ch_hamming_hist(ch_ws* ws, const ch_hist_args* a, void* stream) {
+  if (ws == nullptr || a == nullptr) CH_FAIL("null argument to ch_hamming_hist");
+  if (a->nq <= 0 || a->ndb < 0) CH_FAIL("bad sizes nq=%lld ndb=%lld", (long long)a->nq, (long long)a->ndb);
+  if (a->q_bits == nullptr || a->g_bits == nullptr || a->slab_all == nullptr) CH_FAIL("null packed input / slab");
+  if (a->ternary && (a->q_nz == nullptr || a->g_nz == nullptr)) CH_FAIL("ternary codes need the non-zero planes");
+  if (a->label_mode != CH_LAB_NONE && (a->q_lab == nullptr || a->g_lab == nullptr || a->slab_rel == nullptr))
+    CH_FAIL("label mode %d needs labels and the relevant slab", a->label_mode);
+  if (a->emit_mode != CH_EMIT_NONE &&
+      (a->rec_off == nullptr || a->rec_cap == nullptr || a->rec_cnt == nullptr || a->recs == nullptr ||
+       a->err_flag == nullptr))
+    CH_FAIL("record emission needs rec_off / rec_cap / rec_cnt / recs / err_flag");
+  if (a->emit_mode == CH_EMIT_RELEVANT && a->label_mode == CH_LAB_NONE) CH_FAIL("relevant records need labels");
+  if ((reinterpret_cast<uintptr_t>(a->g_bits) | reinterpret_cast<uintptr_t>(a->g_nz) |
+       reinterpret_cast<uintptr_t>(a->g_lab)) & 15)
+    CH_FAIL("gallery arrays must be 16-byte aligned");
+  ChDeviceGuard guard(ws->device);
+  Geometry g;
+  if (a->threads <= 0 || a->threads > 256 || (a->threads & 31) || a->nstripes <= 0)
+    CH_FAIL("bad geometry threads=%d nstripes=%d (use ch_hist_geometry)", a->threads, a->nstripes);
+  if (make_geometry(ws, a->nq, a->ndb, a->nbit, a->ternary != 0, a->label_mode, a->mask_words, a->threads,
+                    a->nstripes, a->rows_per_stripe, &g))
+    return 1;
+  if (g.nq_pad != a->nq_pad) CH_FAIL("nq_pad mismatch: got %lld, geometry says %lld", (long long)a->nq_pad, g.nq_pad);
+  const int nw = ch_code_words(a->nbit);
+  hist_fn_t fn = pick_kernel(nw, a->ternary != 0, a->label_mode, a->thresh != nullptr);
+  if (fn == nullptr) CH_FAIL("no kernel for words=%d", nw);
+  HistDev d;
+  d.q_bits = a->q_bits; d.q_nz = a->q_nz; d.g_bits = a->g_bits; d.g_nz = a->g_nz;
+  d.q_lab = a->q_lab; d.g_lab = a->g_lab; d.slab_all = a->slab_all; d.slab_rel = a->slab_rel;
+  d.thresh = a->thresh; d.rec_off = a->rec_off; d.rec_cap = a->rec_cap; d.rec_cnt = a->rec_cnt;
+  d.recs = static_cast<uint4*>(a->recs); d.err_flag = a->err_flag;
+  d.nq = a->nq; d.nq_pad = a->nq_pad; d.ndb = a->ndb;
+  d.nbit = a->nbit; d.nbins = (a->ternary ? 2 * a->nbit : a->nbit) + 1; d.lw = a->mask_words;
+  d.emit_mode = a->emit_mode;
+  d.nqtiles = g.nqtiles; d.rows_per_stripe = g.rows_per_stripe; d.tile_rows = g.tile; d.flush_tiles = g.flush_tiles;
+  CH_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(g.smem)));
+  const long long ctas = static_cast<long long>(g.nqtiles) * g.nstripes;
+  if (ctas > 0x7fffffffll) CH_FAIL("grid too large");
+  fn<<<static_cast<unsigned>(ctas), g.threads, g.smem, static_cast<cudaStream_t>(stream)>>>(d);
+  CH_LAUNCH_CHECK(ws);
+  return 0;
+}
+
+extern "C" int ch_slab_totals(ch_ws* ws, const uint32_t* slab, int nstripes, int nbins, int64_t nq_pad,
+                              uint32_t* tot_dev, void* stream) {
+  if (ws == nullptr || slab == nullptr || tot_dev == nullptr) CH_FAIL("null argument to ch_slab_totals");
+  ChDeviceGuard guard(ws->device);
+  const long long plane = static_cast<long long>(nbins) * nq_pad;
+  slab_totals_kernel<<<static_cast<unsigned>((plane + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      slab, nstripes, plane, tot_dev);
+  CH_LAUNCH_CHECK(ws);
+  return 0;
+}
+
+extern "C" int ch_slab_exscan(ch_ws* ws, uint32_t* slab, int nstripes, int nbins, int64_t nq_pad, void* stream) {
+  if (ws == nullptr || slab == nullptr) CH_FAIL("null argument to ch_slab_exscan");
+  ChDeviceGuard guard(ws->device);
+  const long long plane = static_cast<long long>(nbins) * nq_pad;
+  slab_exscan_kernel<<<static_cast<unsigned>((plane + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      slab, nstripes, plane);
+  CH_LAUNCH_CHECK(ws);
+  return 0;
+}
+
+extern "C" int ch_class_counts(ch_ws* ws, const uint32_t* g_ids, int64_t ndb, int rows_per_stripe, int nclass,
+                               uint32_t* cls_dev, void* stream) {
+  if (ws == nullptr || g_ids == nullptr || cls_dev == nullptr) CH_FAIL("null argument to ch_class_counts");
+  if (ndb <= 0) return 0;
+  ChDeviceGuard guard(ws->device);
+  class_counts_kernel<<<static_cast<unsigned>((ndb + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      g_ids, ndb, rows_per_stripe, nclass, cls_dev);
+  CH_LAUNCH_CHECK(ws);
+  return 0;
+}

@@ -1,0 +1,357 @@
+// K1: sign + bit-pack of real-valued codes, and the label packer (one-/multi-hot -> ids + bitmasks).
+// HBM-bound: algorithmic bytes per code row = elem_size * nbit read + nbit / 8 written.
+//
+// Work unit = one 32-bit output word (row r, word w).  A warp owns 32 consecutive units: for unit u
+// every lane loads element (r, 32 w + lane) -- a fully coalesced 128-byte request when the column
+// stride is 1 -- and one __ballot_sync turns the 32 predicates into the packed word; lane u keeps it.
+// After 32 units the warp stores its 32 words as one coalesced 128-byte line.  Loads are unrolled 8x
+// so every warp keeps 1 KB of HBM requests in flight.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+int ch_ws_ensure_stage(ch_ws* ws);  // api.cu
+
+namespace {
+
+template <typename T>
+struct Elem;
+template <>
+struct Elem<float> {
+  typedef float cmp_t;
+  static __device__ __forceinline__ float load(const float* p) { return __ldg(p); }
+};
+template <>
+struct Elem<double> {
+  typedef double cmp_t;
+  static __device__ __forceinline__ double load(const double* p) { return __ldg(p); }
+};
+template <>
+struct Elem<__half> {
+  typedef float cmp_t;
+  static __device__ __forceinline__ float load(const __half* p) {
+    return __half2float(__ushort_as_half(__ldg(reinterpret_cast<const unsigned short*>(p))));
+  }
+};
+template <>
+struct Elem<__nv_bfloat16> {
+  typedef float cmp_t;
+  static __device__ __forceinline__ float load(const __nv_bfloat16* p) {
+    return __uint_as_float(static_cast<uint32_t>(__ldg(reinterpret_cast<const unsigned short*>(p))) << 16);
+  }
+};
+template <>
+struct Elem<int64_t> {
+  typedef double cmp_t;
+  static __device__ __forceinline__ double load(const int64_t* p) { return static_cast<double>(__ldg(p)); }
+};
+template <>
+struct Elem<int32_t> {
+  typedef double cmp_t;
+  static __device__ __forceinline__ double load(const int32_t* p) { return static_cast<double>(__ldg(p)); }
+};
+template <>
+struct Elem<int16_t> {
+  typedef float cmp_t;
+  static __device__ __forceinline__ float load(const int16_t* p) { return static_cast<float>(__ldg(p)); }
+};
+template <>
+struct Elem<int8_t> {
+  typedef float cmp_t;
+  static __device__ __forceinline__ float load(const int8_t* p) {
+    return static_cast<float>(static_cast<int8_t>(__ldg(reinterpret_cast<const signed char*>(p))));
+  }
+};
+template <>
+struct Elem<uint8_t> {
+  typedef float cmp_t;
+  static __device__ __forceinline__ float load(const uint8_t* p) { return static_cast<float>(__ldg(p)); }
+};
+
+// rows [row0, row_end) of the output are produced; rows >= n are zero pad rows.
+// element (r, k) lives at src[(r - row0) * rs + k * cs].
+template <typename T>
+__global__ void __launch_bounds__(256) pack_bits_kernel(const T* __restrict__ src, int64_t row0, int64_t row_end,
+                                                        int64_t n, int ncols, int64_t rs, int64_t cs,
+                                                        double thr, int words, uint32_t* __restrict__ out_pos,
+                                                        uint32_t* __restrict__ out_nz, uint32_t* __restrict__ flags) {
+  typedef typename Elem<T>::cmp_t C;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int64_t unit_begin = row0 * words;
+  const int64_t unit_end = row_end * words;
+  const C cthr = static_cast<C>(thr);
+  const bool has_thr = thr != 0.0;
+  uint32_t fl = 0;
+  for (int64_t u0 = unit_begin + warp * 32; u0 < unit_end; u0 += nwarps * 32) {
+    uint32_t my_pos = 0, my_nz = 0;
+#pragma unroll 8
+    for (int u = 0; u < 32; ++u) {
+      const int64_t unit = u0 + u;
+      const int64_t r = unit / words;
+      const int w = static_cast<int>(unit - r * words);
+      const int col = w * 32 + lane;
+      bool pos = false, nzb = false;
+      if (unit < unit_end && r < n && col < ncols) {
+        C x = Elem<T>::load(src + (r - row0) * rs + static_cast<int64_t>(col) * cs);
+        if (x != x) fl |= 2u;
+        if (has_thr && (x < C(0) ? -x : x) < cthr) x = C(0);
+        pos = x > C(0);
+        nzb = x != C(0);
+        if (!nzb) fl |= 1u;
+      }
+      const uint32_t bp = __ballot_sync(0xffffffffu, pos);
+      const uint32_t bn = __ballot_sync(0xffffffffu, nzb);
+      if (lane == u) {
+        my_pos = bp;
+        my_nz = bn;
+      }
+    }
+    const int64_t mine = u0 + lane;
+    if (mine < unit_end) {
+      out_pos[mine] = my_pos;
+      if (out_nz != nullptr) out_nz[mine] = my_nz;
+    }
+  }
+  fl = __reduce_or_sync(0xffffffffu, fl);
+  if (lane == 0 && fl != 0 && flags != nullptr) atomicOr(flags, fl);
+}
+
+// per-row summary of a label bitmask: id of the first positive (or nolabel), statistics
+__global__ void label_rows_kernel(const uint32_t* __restrict__ masks, int64_t n, int64_t rows_pad, int words,
+                                  uint32_t nolabel, uint32_t* __restrict__ ids, uint32_t* __restrict__ info) {
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  uint32_t cnt = 0, first = nolabel;
+  if (r < n) {
+    for (int w = 0; w < words; ++w) {
+      const uint32_t m = masks[r * words + w];
+      if (m != 0 && cnt == 0) first = static_cast<uint32_t>(w * 32 + __ffs(m) - 1);
+      cnt += __popc(m);
+    }
+  }
+  if (r < rows_pad) ids[r] = first;
+  // warp-aggregate the statistics
+  uint32_t mx = __reduce_max_sync(0xffffffffu, cnt);
+  uint32_t mid = __reduce_max_sync(0xffffffffu, (r < n && cnt > 0) ? first + 1 : 0u);
+  uint32_t nz = __popc(__ballot_sync(0xffffffffu, r < n && cnt == 0));
+  if ((threadIdx.x & 31) == 0) {
+    if (mx) atomicMax(info + 0, mx);
+    if (mid) atomicMax(info + 1, mid);
+    if (nz) atomicAdd(info + 2, nz);
+  }
+}
+
+// 1-D integer class ids -> u32 ids (negative -> nolabel)
+template <typename T>
+__global__ void label_ids_kernel(const T* __restrict__ src, int64_t row0, int64_t row_end, int64_t n, int64_t rs,
+                                 uint32_t nolabel, uint32_t* __restrict__ ids, uint32_t* __restrict__ info) {
+  const int64_t r = row0 + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  uint32_t id = nolabel;
+  bool valid = false;
+  if (r < n) {
+    const double v = static_cast<double>(Elem<T>::load(src + (r - row0) * rs));
+    if (v >= 0.0 && v < 4294967000.0) {
+      id = static_cast<uint32_t>(v);
+      valid = true;
+    }
+  }
+  if (r < row_end) ids[r] = id;
+  uint32_t mid = __reduce_max_sync(0xffffffffu, valid ? id + 1 : 0u);
+  uint32_t nz = __popc(__ballot_sync(0xffffffffu, r < n && !valid));
+  uint32_t any = __ballot_sync(0xffffffffu, valid);
+  if ((threadIdx.x & 31) == 0) {
+    if (any) atomicMax(info + 0, 1u);
+    if (mid) atomicMax(info + 1, mid);
+    if (nz) atomicAdd(info + 2, nz);
+  }
+}
+
+size_t elem_size(int dtype) {
+  switch (dtype) {
+    case CH_F32: return 4;
+    case CH_F16: return 2;
+    case CH_BF16: return 2;
+    case CH_F64: return 8;
+    case CH_I64: return 8;
+    case CH_I32: return 4;
+    case CH_U8: return 1;
+    case CH_I16: return 2;
+    case CH_I8: return 1;
+    default: return 0;
+  }
+}
+
+int launch_pack(ch_ws* ws, const void* src, int dtype, int64_t row0, int64_t row_end, int64_t n, int ncols,
+                int64_t rs, int64_t cs, double thr, int words, uint32_t* out_pos, uint32_t* out_nz,
+                uint32_t* flags, cudaStream_t st) {
+  const int64_t units = (row_end - row0) * words;
+  if (units <= 0) return 0;
+  const int64_t warps = (units + 31) / 32;
+  int64_t blocks = (warps + 7) / 8;
+  const int64_t cap = static_cast<int64_t>(ws->sm_count) * 16;
+  if (blocks > cap) blocks = cap;
+  const dim3 grid(static_cast<unsigned>(blocks)), block(256);
+#define CH_PACK_CASE(ENUM, TYPE)                                                                            \
+  case ENUM:                                                                                                \
+    pack_bits_kernel<TYPE><<<grid, block, 0, st>>>(static_cast<const TYPE*>(src), row0, row_end, n, ncols,  \
+                                                   rs, cs, thr, words, out_pos, out_nz, flags);             \
+    break;
+  switch (dtype) {
+    CH_PACK_CASE(CH_F32, float)
+    CH_PACK_CASE(CH_F16, __half)
+    CH_PACK_CASE(CH_BF16, __nv_bfloat16)
+    CH_PACK_CASE(CH_F64, double)
+    CH_PACK_CASE(CH_I64, int64_t)
+    CH_PACK_CASE(CH_I32, int32_t)
+    CH_PACK_CASE(CH_U8, uint8_t)
+    CH_PACK_CASE(CH_I16, int16_t)
+    CH_PACK_CASE(CH_I8, int8_t)
+    default:
+      CH_FAIL("unsupported dtype %d", dtype);
+  }
+#undef CH_PACK_CASE
+  CH_LAUNCH_CHECK(ws);
+  return 0;
+}
+
+// Runs `launch_pack` over a host buffer in pipelined chunks: H2D of chunk c+1 (copy stream) overlaps
+// the pack kernel of chunk c (compute stream).  The host buffer must be row-contiguous (cs == 1).
+int pack_from_host(ch_ws* ws, const void* src, int dtype, int64_t n, int ncols, int64_t rs, int64_t cs,
+                   double thr, int words, int64_t rows_pad, uint32_t* out_pos, uint32_t* out_nz,
+                   uint32_t* flags, cudaStream_t st) {
+  const size_t es = elem_size(dtype);
+  if (cs != 1 && ncols > 1) CH_FAIL("host buffers must have unit column stride");
+  if (ch_ws_ensure_stage(ws)) return 1;
+  const size_t row_bytes = static_cast<size_t>(rs) * es;
+  if (row_bytes == 0) CH_FAIL("bad row stride");
+  int64_t chunk_rows = static_cast<int64_t>(ws->stage_bytes / row_bytes) / 64 * 64;
+  if (chunk_rows < 64) CH_FAIL("row of %zu bytes does not fit the staging buffer", row_bytes);
+  if (n == 0) return launch_pack(ws, nullptr, dtype, 0, rows_pad, 0, ncols, rs, cs, thr, words, out_pos, out_nz, flags, st);
+  int c = 0;
+  for (int64_t r0 = 0; r0 < n; r0 += chunk_rows, ++c) {
+    const int b = c & 1;
+    const int64_t r1 = (r0 + chunk_rows < n) ? r0 + chunk_rows : n;
+    const bool last = r1 == n;
+    // the staging buffer may still be read by the pack kernel of chunk c - 2 (or of an earlier call)
+    CH_CUDA(cudaStreamWaitEvent(ws->copy_stream, ws->ev_consumed[b], 0));
+    // last row of a strided buffer may be shorter than rs elements: copy only what exists
+    const size_t bytes = static_cast<size_t>(r1 - r0 - 1) * row_bytes + static_cast<size_t>(ncols) * es;
+    CH_CUDA(cudaMemcpyAsync(ws->stage[b], static_cast<const char*>(src) + static_cast<size_t>(r0) * row_bytes, bytes,
+                            cudaMemcpyHostToDevice, ws->copy_stream));
+    CH_CUDA(cudaEventRecord(ws->ev_copied[b], ws->copy_stream));
+    CH_CUDA(cudaStreamWaitEvent(st, ws->ev_copied[b], 0));
+    if (launch_pack(ws, ws->stage[b], dtype, r0, last ? rows_pad : r1, n, ncols, rs, cs, thr, words, out_pos, out_nz,
+                    flags, st))
+      return 1;
+    CH_CUDA(cudaEventRecord(ws->ev_consumed[b], st));
+  }
+  // the caller may free / reuse the host buffer after return
+  CH_CUDA(cudaStreamSynchronize(ws->copy_stream));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int64_t ch_padded_rows(int64_t n) { return ch_round_up(n < 0 ? 0 : n, 64) + 64; }
+
+extern "C" int ch_code_words(int nbit) {
+  if (nbit <= 0 || nbit > CH_MAX_NBIT) return 0;
+  if (nbit <= 32) return 1;
+  if (nbit <= 64) return 2;
+  if (nbit <= 128) return 4;
+  return 8;
+}
+
+extern "C" int ch_pack_sign(ch_ws* ws, const void* codes, int mem, int dtype, int64_t n, int nbit,
+                            int64_t row_stride, int64_t col_stride, double threshold, uint32_t* out_bits_dev,
+                            uint32_t* out_nz_dev, uint32_t* flags_dev, void* stream) {
+  if (ws == nullptr) CH_FAIL("null workspace");
+  const int words = ch_code_words(nbit);
+  if (words == 0) CH_FAIL("nbit=%d unsupported (1..%d)", nbit, CH_MAX_NBIT);
+  if (n < 0 || out_bits_dev == nullptr) CH_FAIL("bad arguments to ch_pack_sign");
+  if (!(dtype == CH_F32 || dtype == CH_F16 || dtype == CH_BF16 || dtype == CH_F64))
+    CH_FAIL("codes must be a floating dtype (got %d)", dtype);
+  ChDeviceGuard g(ws->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t rows_pad = ch_padded_rows(n);
+  if (mem == CH_MEM_HOST)
+    return pack_from_host(ws, codes, dtype, n, nbit, row_stride, col_stride, threshold, words, rows_pad,
+                          out_bits_dev, out_nz_dev, flags_dev, st);
+  return launch_pack(ws, codes, dtype, 0, rows_pad, n, nbit, row_stride, col_stride, threshold, words, out_bits_dev,
+                     out_nz_dev, flags_dev, st);
+}
+
+extern "C" int ch_pack_labels(ch_ws* ws, const void* labels, int mem, int dtype, int64_t n, int C,
+                              int64_t row_stride, int64_t col_stride, uint32_t nolabel, uint32_t* out_ids_dev,
+                              uint32_t* out_masks_dev, uint32_t* info_dev, void* stream) {
+  if (ws == nullptr) CH_FAIL("null workspace");
+  if (n < 0 || out_ids_dev == nullptr || info_dev == nullptr) CH_FAIL("bad arguments to ch_pack_labels");
+  if (elem_size(dtype) == 0) CH_FAIL("unsupported label dtype %d", dtype);
+  ChDeviceGuard g(ws->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t rows_pad = ch_padded_rows(n);
+  if (C > 0) {
+    if (out_masks_dev == nullptr) CH_FAIL("2-D labels need a mask buffer");
+    const int words = (C + 31) / 32;
+    int rc;
+    if (mem == CH_MEM_HOST)
+      rc = pack_from_host(ws, labels, dtype, n, C, row_stride, col_stride, 0.0, words, rows_pad, out_masks_dev,
+                          nullptr, nullptr, st);
+    else
+      rc = launch_pack(ws, labels, dtype, 0, rows_pad, n, C, row_stride, col_stride, 0.0, words, out_masks_dev,
+                       nullptr, nullptr, st);
+    if (rc) return rc;
+    const unsigned blocks = static_cast<unsigned>((rows_pad + 255) / 256);
+    label_rows_kernel<<<blocks, 256, 0, st>>>(out_masks_dev, n, rows_pad, words, nolabel, out_ids_dev, info_dev);
+    CH_LAUNCH_CHECK(ws);
+    return 0;
+  }
+  // 1-D ids (host arrays go through the staging buffer in stream-ordered chunks)
+  const size_t es = elem_size(dtype);
+  const int64_t chunk_rows = mem == CH_MEM_HOST
+                                 ? static_cast<int64_t>(ws->stage_bytes / (static_cast<size_t>(row_stride) * es)) / 64 * 64
+                                 : rows_pad;
+  if (mem == CH_MEM_HOST) {
+    if (chunk_rows < 64) CH_FAIL("label row stride too large for the staging buffer");
+    if (ch_ws_ensure_stage(ws)) return 1;
+  }
+  for (int64_t r0 = 0; r0 == 0 || r0 < n; r0 += chunk_rows) {
+    const int64_t r1 = (r0 + chunk_rows < n) ? r0 + chunk_rows : n;
+    const bool last = r1 >= n;
+    const void* src = labels;
+    if (mem == CH_MEM_HOST) {
+      const size_t bytes = r1 > r0 ? (static_cast<size_t>(r1 - r0 - 1) * row_stride + 1) * es : 0;
+      if (bytes)
+        CH_CUDA(cudaMemcpyAsync(ws->stage[0], static_cast<const char*>(labels) + static_cast<size_t>(r0) * row_stride * es,
+                                bytes, cudaMemcpyHostToDevice, st));
+      src = ws->stage[0];
+    } else {
+      src = static_cast<const char*>(labels);
+    }
+    const int64_t row_end = last ? rows_pad : r1;
+    const unsigned blocks = static_cast<unsigned>((row_end - r0 + 255) / 256);
+#define CH_ID_CASE(ENUM, TYPE)                                                                              \
+  case ENUM:                                                                                                \
+    label_ids_kernel<TYPE><<<blocks, 256, 0, st>>>(static_cast<const TYPE*>(src), r0, row_end, n, row_stride, \
+                                                   nolabel, out_ids_dev, info_dev);                         \
+    break;
+    switch (dtype) {
+      CH_ID_CASE(CH_I64, int64_t)
+      CH_ID_CASE(CH_I32, int32_t)
+      CH_ID_CASE(CH_I16, int16_t)
+      CH_ID_CASE(CH_I8, int8_t)
+      CH_ID_CASE(CH_U8, uint8_t)
+      CH_ID_CASE(CH_F32, float)
+      CH_ID_CASE(CH_F64, double)
+      default:
+        CH_FAIL("unsupported dtype %d for 1-D labels", dtype);
+    }
+    CH_LAUNCH_CHECK(ws);
+    if (last) break;
+  }
+#undef CH_ID_CASE
+  if (mem == CH_MEM_HOST) CH_CUDA(cudaStreamSynchronize(st));  // staging buffer reusable, host buffer released
+  return 0;
+}

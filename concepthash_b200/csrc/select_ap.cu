@@ -1,0 +1,562 @@
+// K3 (exact, sort-free top-R selection from the key histograms) and K4 (label match / precision@k /
+// AP reduction), plus the small helpers around them.  Everything here touches O(nq * nbins) or
+// O(#records) data -- tiny next to the nq * ndb pair loop of K2.
+#include "common.cuh"
+
+namespace {
+
+// ---- K3: bases + thresholds ---------------------------------------------------------------------
+// tot_all: (world, nbins, nq_pad) per-rank key totals.  One thread per query walks the keys.
+__global__ void scan_bases_kernel(const uint32_t* __restrict__ tot_all, int world, int rank, int nbins,
+                                  long long nq, long long nq_pad, long long rmax, uint32_t* __restrict__ base0,
+                                  uint32_t* __restrict__ thresh, uint32_t* __restrict__ total) {
+  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= nq_pad) return;
+  unsigned long long cum = 0;
+  uint32_t t = static_cast<uint32_t>(nbins - 1);
+  bool found = false;
+  for (int key = 0; key < nbins; ++key) {
+    unsigned long long lower = 0, tot = 0;
+    if (q < nq) {
+      for (int g = 0; g < world; ++g) {
+        const uint32_t v = tot_all[(static_cast<size_t>(g) * nbins + key) * nq_pad + q];
+        if (g < rank) lower += v;
+        tot += v;
+      }
+    }
+    base0[static_cast<size_t>(key) * nq_pad + q] = static_cast<uint32_t>(cum + lower);
+    cum += tot;
+    if (!found && rmax >= 0 && cum >= static_cast<unsigned long long>(rmax)) {
+      t = static_cast<uint32_t>(key);
+      found = true;
+    }
+  }
+  if (thresh != nullptr) thresh[q] = t;
+  if (total != nullptr) total[q] = static_cast<uint32_t>(cum);
+}
+
+// ---- record capacities / offsets ------------------------------------------------------------------
+__global__ void record_caps_kernel(int source, const uint32_t* __restrict__ a0, const uint32_t* __restrict__ a1,
+                                   int nstripes, int nb, long long nq, long long nq_pad, int min_with_prev,
+                                   uint32_t* __restrict__ cap) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(nstripes) * nq_pad) return;
+  const int s = static_cast<int>(i / nq_pad);
+  const long long q = i - static_cast<long long>(s) * nq_pad;
+  uint32_t c = 0;
+  if (q < nq) {
+    if (source == 0 || source == 1) {
+      const int last = source == 0 ? static_cast<int>(a1[q]) : nb - 1;
+      for (int key = 0; key <= last && key < nb; ++key) c += a0[(static_cast<size_t>(s) * nb + key) * nq_pad + q];
+    } else {
+      const uint32_t id = a1[q];
+      if (id < static_cast<uint32_t>(nb)) c = a0[static_cast<size_t>(s) * nb + id];
+    }
+  }
+  if (min_with_prev) {
+    const uint32_t p = cap[i];
+    c = p < c ? p : c;
+  }
+  cap[i] = c;
+}
+
+__global__ void row_totals_kernel(const uint32_t* __restrict__ cap, int nstripes, long long nq_pad,
+                                  unsigned long long* __restrict__ rowtot) {
+  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= nq_pad) return;
+  unsigned long long s = 0;
+  for (int k = 0; k < nstripes; ++k) s += cap[static_cast<size_t>(k) * nq_pad + q];
+  rowtot[q] = s;
+}
+
+// single-CTA exclusive scan (in place) of n u64 values; result[n] = total
+__global__ void __launch_bounds__(1024) exscan_u64_kernel(unsigned long long* __restrict__ v, long long n) {
+  __shared__ unsigned long long part[1024];
+  const int t = threadIdx.x;
+  const long long chunk = (n + 1023) / 1024;
+  const long long b = t * chunk;
+  long long e = b + chunk;
+  if (e > n) e = n;
+  unsigned long long s = 0;
+  for (long long i = b; i < e; ++i) s += v[i];
+  part[t] = s;
+  __syncthreads();
+  if (t == 0) {
+    unsigned long long run = 0;
+    for (int i = 0; i < 1024; ++i) {
+      const unsigned long long x = part[i];
+      part[i] = run;
+      run += x;
+    }
+    v[n] = run;
+  }
+  __syncthreads();
+  unsigned long long run = part[t];
+  for (long long i = b; i < e; ++i) {
+    const unsigned long long x = v[i];
+    v[i] = run;
+    run += x;
+  }
+}
+
+__global__ void record_offsets_kernel(const uint32_t* __restrict__ cap, const unsigned long long* __restrict__ start,
+                                      int nstripes, long long nq_pad, uint32_t* __restrict__ off) {
+  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= nq_pad) return;
+  unsigned long long run = start[q];
+  for (int k = 0; k < nstripes; ++k) {
+    const size_t o = static_cast<size_t>(k) * nq_pad + q;
+    off[o] = static_cast<uint32_t>(run);
+    run += cap[o];
+  }
+}
+
+// ---- K4: records -> AP sums / hit counts ------------------------------------------------------------
+struct FinalDev {
+  const uint4* recs; const uint32_t* rec_off; const uint32_t* rec_cnt;
+  const uint32_t* base0_all; const uint32_t* base0_rel;
+  const uint32_t* sbase_all; const uint32_t* sbase_rel;
+  const uint32_t* first_rel;
+  double* partial;
+  long long nq, nq_pad;
+  int nstripes, nbins, remove_first, nR, nPR;
+  long long r_eff[CH_MAX_R];
+  long long pr_k[CH_MAX_PR];
+};
+
+__device__ __forceinline__ bool record_rank(const FinalDev& a, const uint4 r, int s, long long q, bool need_rel,
+                                            long long* rank, long long* relrank) {
+  const uint32_t key = r.x & 0x7fffffffu;
+  const size_t o0 = static_cast<size_t>(key) * a.nq_pad + q;
+  const size_t os = (static_cast<size_t>(s) * a.nbins + key) * a.nq_pad + q;
+  *rank = static_cast<long long>(a.base0_all[o0]) + a.sbase_all[os] + r.y;
+  if (need_rel) *relrank = static_cast<long long>(a.base0_rel[o0]) + a.sbase_rel[os] + r.z;
+  return (r.x >> 31) != 0u;
+}
+
+__global__ void finalize_kernel(const FinalDev a) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(a.nstripes) * a.nq_pad) return;
+  const int s = static_cast<int>(i / a.nq_pad);
+  const long long q = i - static_cast<long long>(s) * a.nq_pad;
+  if (q >= a.nq) return;
+  const int ncols = 2 * a.nR + a.nPR;
+  double acc[2 * CH_MAX_R + CH_MAX_PR];
+  for (int c = 0; c < ncols; ++c) acc[c] = 0.0;
+  const uint32_t b = a.rec_off[i], n = a.rec_cnt[i];
+  const long long shift = a.remove_first ? 1 : 0;
+  const long long frel = (a.remove_first && a.first_rel != nullptr) ? a.first_rel[q] : 0;
+  for (uint32_t k = 0; k < n; ++k) {
+    const uint4 r = a.recs[b + k];
+    long long rank, relrank = 0;
+    if (!record_rank(a, r, s, q, true, &rank, &relrank)) continue;  // candidate records may be non-relevant
+    if (a.remove_first) {
+      if (rank == 0) continue;  // the dropped self-retrieval
+      rank -= shift;
+      relrank -= frel;
+    }
+    const double prec = static_cast<double>(relrank + 1) / static_cast<double>(rank + 1);
+    for (int j = 0; j < a.nR; ++j)
+      if (rank < a.r_eff[j]) {
+        acc[2 * j] += prec;
+        acc[2 * j + 1] += 1.0;
+      }
+    for (int j = 0; j < a.nPR; ++j)
+      if (rank < a.pr_k[j]) acc[2 * a.nR + j] += 1.0;
+  }
+  double* out = a.partial + static_cast<size_t>(i) * ncols;
+  for (int c = 0; c < ncols; ++c) out[c] = acc[c];
+}
+
+// cols[q][c] = sum over stripes (fixed order -> deterministic)
+__global__ void reduce_stripes_kernel(const double* __restrict__ partial, int nstripes, long long nq,
+                                      long long nq_pad, int ncols, double* __restrict__ cols) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= nq * ncols) return;
+  const long long q = i / ncols;
+  const int c = static_cast<int>(i - q * ncols);
+  double s = 0.0;
+  for (int k = 0; k < nstripes; ++k) s += partial[(static_cast<size_t>(k) * nq_pad + q) * ncols + c];
+  cols[i] = s;
+}
+
+__global__ void first_relevant_kernel(const FinalDev a, uint32_t* __restrict__ first_rel) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(a.nstripes) * a.nq_pad) return;
+  const int s = static_cast<int>(i / a.nq_pad);
+  const long long q = i - static_cast<long long>(s) * a.nq_pad;
+  if (q >= a.nq) return;
+  const uint32_t b = a.rec_off[i], n = a.rec_cnt[i];
+  for (uint32_t k = 0; k < n; ++k) {
+    long long rank, relrank;
+    if (record_rank(a, a.recs[b + k], s, q, false, &rank, &relrank) && rank == 0) first_rel[q] = 1u;
+  }
+}
+
+__global__ void scatter_ranked_kernel(const FinalDev a, long long R, long long row_offset, long long* __restrict__ ids,
+                                      int* __restrict__ keys) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(a.nstripes) * a.nq_pad) return;
+  const int s = static_cast<int>(i / a.nq_pad);
+  const long long q = i - static_cast<long long>(s) * a.nq_pad;
+  if (q >= a.nq) return;
+  const uint32_t b = a.rec_off[i], n = a.rec_cnt[i];
+  for (uint32_t k = 0; k < n; ++k) {
+    const uint4 r = a.recs[b + k];
+    long long rank, relrank;
+    record_rank(a, r, s, q, false, &rank, &relrank);
+    if (a.remove_first) {
+      if (rank == 0) continue;
+      rank -= 1;
+    }
+    if (rank < R) {
+      ids[q * R + rank] = row_offset + r.w;
+      if (keys != nullptr) keys[q * R + rank] = static_cast<int>(r.x & 0x7fffffffu);
+    }
+  }
+}
+
+// deterministic block sum of per-query values; one block per output scalar
+__device__ double block_sum_1024(double v, double* sh) {
+  const int t = threadIdx.x;
+  sh[t] = v;
+  __syncthreads();
+  for (int w = 512; w > 0; w >>= 1) {
+    if (t < w) sh[t] += sh[t + w];
+    __syncthreads();
+  }
+  const double r = sh[0];
+  __syncthreads();
+  return r;
+}
+
+// out[0..nR) = mAP_i, out[nR..nR+nPR) = recall@k, out[nR+nPR..nR+2nPR) = precision@k
+__global__ void __launch_bounds__(1024) reduce_means_kernel(const double* __restrict__ cols,
+                                                            const uint32_t* __restrict__ total_rel,
+                                                            const uint32_t* __restrict__ first_rel, long long nq,
+                                                            int nR, int nPR, const long long* __restrict__ pr_k,
+                                                            double* __restrict__ ap_out, double* __restrict__ out) {
+  __shared__ double sh[1024];
+  const int ncols = 2 * nR + nPR;
+  const int which = blockIdx.x;
+  double s = 0.0;
+  for (long long q = threadIdx.x; q < nq; q += 1024) {
+    const double* c = cols + q * ncols;
+    double v;
+    if (which < nR) {
+      v = c[2 * which + 1] > 0.0 ? c[2 * which] / c[2 * which + 1] : 0.0;
+      if (ap_out != nullptr) ap_out[static_cast<size_t>(which) * nq + q] = v;
+    } else if (which < nR + nPR) {
+      const int j = which - nR;
+      double tr = total_rel != nullptr ? static_cast<double>(total_rel[q]) : 0.0;
+      if (first_rel != nullptr) tr -= static_cast<double>(first_rel[q]);
+      v = c[2 * nR + j] / (tr > 1.0 ? tr : 1.0);
+    } else {
+      const int j = which - nR - nPR;
+      v = c[2 * nR + j] / static_cast<double>(pr_k[j]);
+    }
+    s += v;
+  }
+  const double tot = block_sum_1024(s, sh);
+  if (threadIdx.x == 0) out[which] = nq > 0 ? tot / static_cast<double>(nq) : 0.0;
+}
+
+// ---- K4 (list form): AP straight from a ranked id list, one warp per query -------------------------
+__global__ void ap_from_ranked_kernel(const long long* __restrict__ ids, long long nq, long long R,
+                                      const uint32_t* __restrict__ q_lab, const uint32_t* __restrict__ g_lab,
+                                      int label_mode, int lw, int nPR, const long long* __restrict__ pr_k,
+                                      double* __restrict__ cols) {
+  const int lane = threadIdx.x & 31;
+  const long long q = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (q >= nq) return;
+  const int ncols = 2 + nPR;
+  double sum = 0.0;
+  uint32_t run = 0;
+  uint32_t hits[CH_MAX_PR];
+  for (int j = 0; j < nPR; ++j) hits[j] = 0;
+  const uint32_t qid = label_mode == CH_LAB_ID ? q_lab[q] : 0u;
+  for (long long k0 = 0; k0 < R; k0 += 32) {
+    const long long k = k0 + lane;
+    bool rel = false;
+    if (k < R) {
+      const long long id = ids[q * R + k];
+      if (id >= 0) {
+        if (label_mode == CH_LAB_ID) {
+          rel = g_lab[id] == qid;
+        } else {
+          uint32_t any = 0;
+          for (int w = 0; w < lw; ++w) any |= q_lab[q * lw + w] & g_lab[id * lw + w];
+          rel = any != 0u;
+        }
+      }
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, rel);
+    if (rel) {
+      const uint32_t before = run + __popc(m & lanemask_lt());
+      sum += static_cast<double>(before + 1) / static_cast<double>(k + 1);
+      for (int j = 0; j < nPR; ++j)
+        if (k < pr_k[j]) hits[j] += 1;
+    }
+    run += __popc(m);
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  for (int j = 0; j < nPR; ++j) hits[j] = __reduce_add_sync(0xffffffffu, hits[j]);
+  if (lane == 0) {
+    double* c = cols + q * ncols;
+    c[0] = sum;
+    c[1] = static_cast<double>(run);
+    for (int j = 0; j < nPR; ++j) c[2 + j] = static_cast<double>(hits[j]);
+  }
+}
+
+// ---- dense key matrix (tests, get_hamm_dist) ---------------------------------------------------------
+__global__ void hamming_matrix_kernel(const uint32_t* __restrict__ qb, const uint32_t* __restrict__ qz,
+                                      const uint32_t* __restrict__ gb, const uint32_t* __restrict__ gz, long long nq,
+                                      long long ndb, int nbit, int nw, int tern, uint16_t* __restrict__ out) {
+  const long long total = nq * ndb;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long q = i / ndb, j = i - q * ndb;
+    uint32_t key;
+    if (!tern) {
+      key = 0;
+      for (int w = 0; w < nw; ++w) key += __popc(qb[q * nw + w] ^ gb[j * nw + w]);
+    } else {
+      uint32_t both = 0, dis = 0;
+      for (int w = 0; w < nw; ++w) {
+        const uint32_t m = qz[q * nw + w] & gz[j * nw + w];
+        both += __popc(m);
+        dis += __popc((qb[q * nw + w] ^ gb[j * nw + w]) & m);
+      }
+      key = static_cast<uint32_t>(nbit) - both + 2u * dis;
+    }
+    out[i] = static_cast<uint16_t>(key);
+  }
+}
+
+// ---- integer-pipe micro-benchmark ----------------------------------------------------------------------
+__global__ void __launch_bounds__(256) popc_peak_kernel(uint32_t* __restrict__ out, int iters, uint32_t seed) {
+  uint32_t a0 = seed + threadIdx.x, a1 = a0 * 3u, a2 = a0 * 5u, a3 = a0 * 7u;
+  uint32_t a4 = a0 * 11u, a5 = a0 * 13u, a6 = a0 * 17u, a7 = a0 * 19u;
+  const uint32_t c = seed * 0x9E3779B9u + blockIdx.x;
+  for (int i = 0; i < iters; ++i) {
+    // 8 independent chains; each step = 1 LOP3 (alu pipe) + 1 POPC
+    a0 = __popc(a0 ^ c) ^ a1; a1 = __popc(a1 ^ c) ^ a2; a2 = __popc(a2 ^ c) ^ a3; a3 = __popc(a3 ^ c) ^ a4;
+    a4 = __popc(a4 ^ c) ^ a5; a5 = __popc(a5 ^ c) ^ a6; a6 = __popc(a6 ^ c) ^ a7; a7 = __popc(a7 ^ c) ^ a0;
+  }
+  const uint32_t r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (r == 0xdeadbeefu) out[0] = r;  // never true in practice; keeps the loop alive
+}
+
+FinalDev to_dev(const ch_final_args* a) {
+  FinalDev d;
+  d.recs = static_cast<const uint4*>(a->recs); d.rec_off = a->rec_off; d.rec_cnt = a->rec_cnt;
+  d.base0_all = a->base0_all; d.base0_rel = a->base0_rel; d.sbase_all = a->sbase_all; d.sbase_rel = a->sbase_rel;
+  d.first_rel = a->first_rel; d.partial = a->partial; d.nq = a->nq; d.nq_pad = a->nq_pad;
+  d.nstripes = a->nstripes; d.nbins = a->nbins; d.remove_first = a->remove_first; d.nR = a->nR; d.nPR = a->nPR;
+  for (int i = 0; i < CH_MAX_R; ++i) d.r_eff[i] = i < a->nR ? a->r_eff[i] : 0;
+  for (int i = 0; i < CH_MAX_PR; ++i) d.pr_k[i] = i < a->nPR ? a->pr_k[i] : 0;
+  return d;
+}
+
+int check_final(const ch_final_args* a, bool need_rel) {
+  if (a == nullptr) CH_FAIL("null ch_final_args");
+  if (a->nR < 0 || a->nR > CH_MAX_R || a->nPR < 0 || a->nPR > CH_MAX_PR) CH_FAIL("too many R / PRs entries");
+  if (a->recs == nullptr || a->rec_off == nullptr || a->rec_cnt == nullptr || a->base0_all == nullptr ||
+      a->sbase_all == nullptr)
+    CH_FAIL("null record / base arrays");
+  if (need_rel && (a->base0_rel == nullptr || a->sbase_rel == nullptr)) CH_FAIL("null relevant base arrays");
+  return 0;
+}
+
+unsigned blocks_for(long long n, int t) { return static_cast<unsigned>((n + t - 1) / t); }
+
+}  // namespace
+
+extern "C" int ch_scan_bases(ch_ws* ws, const uint32_t* tot_all_dev, int world, int rank, int nbins, int64_t nq,
+                             int64_t nq_pad, int64_t rmax, uint32_t* base0_dev, uint32_t* thresh_out_dev,
+                             uint32_t* total_out_dev, void* stream) {
+  if (ws == nullptr || tot_all_dev == nullptr || base0_dev == nullptr) CH_FAIL("null argument to ch_scan_bases");
+  if (world < 1 || rank < 0 || rank >= world) CH_FAIL("bad world/rank %d/%d", world, rank);
+  ChDeviceGuard guard(ws->device);
+  scan_bases_kernel<<<blocks_for(nq_pad, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      tot_all_dev, world, rank, nbins, nq, nq_pad, rmax, base0_dev, thresh_out_dev, total_out_dev);
+  CH_LAUNCH_CHECK(ws);
+  return 0;
+}
+
+extern "C" int ch_record_caps(ch_ws* ws, int source, const uint32_t* slab_or_cls, const uint32_t* thresh_or_qids,
+                              int nstripes, int nbins_or_nclass, int64_t nq, int64_t nq_pad, int min_with_prev,
+                              uint32_t* cap_dev, void* stream) {
+  if (ws == nullptr || slab_or_cls == nullptr || cap_dev == nullptr) CH_FAIL("null argument to ch_record_caps");
+  if (source < 0 || source > 2) CH_FAIL("bad capacity source %d", source);
+  if (source != 1 && thresh_or_qids == nullptr) CH_FAIL("capacity source %d needs thresholds / query ids", source);
+  ChDeviceGuard guard(ws->device);
+  record_caps_kernel<<<blocks_for(static_cast<long long>(nstripes) * nq_pad, 256), 256, 0,
+                       static_cast<cudaStream_t>(stream)>>>(source, slab_or_cls, thresh_or_qids, nstripes,
+                                                            nbins_or_nclass, nq, nq_pad, min_with_prev, cap_dev);
+  CH_LAUNCH_CHECK(ws);
+  return 0;
+}
+
+int ch_ws_scratch(ch_ws* ws, size_t bytes, void** out);  // api.cu
+
+extern "C" int ch_record_offsets(ch_ws* ws, const uint32_t* cap_dev, int nstripes, int64_t nq, int64_t nq_pad,
+                                 uint32_t* off_dev, uint64_t* total_host, void* stream) {
+  if (ws == nullptr || cap_dev == nullptr || off_dev == nullptr || total_host == nullptr)
+    CH_FAIL("null argument to ch_record_offsets");
+  (void)nq;
+  ChDeviceGuard guard(ws->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  void* scratch = nullptr;
+  if (ch_ws_scratch(ws, static_cast<size_t>(nq_pad + 1) * 8, &scratch)) return 1;
+  unsigned long long* rowtot = static_cast<unsigned long long*>(scratch);
+  row_totals_kernel<<<blocks_for(nq_pad, 256), 256, 0, st>>>(cap_dev, nstripes, nq_pad, rowtot);
+  CH_LAUNCH_CHECK(ws);
+  exscan_u64_kernel<<<1, 1024, 0, st>>>(rowtot, nq_pad);
+  CH_LAUNCH_CHECK(ws);
+  record_offsets_kernel<<<blocks_for(nq_pad, 256), 256, 0, st>>>(cap_dev, rowtot, nstripes, nq_pad, off_dev);
+  CH_LAUNCH_CHECK(ws);
+  unsigned long long total = 0;
+  CH_CUDA(cudaMemcpyAsync(&total, rowtot + nq_pad, 8, cudaMemcpyDeviceToHost, st));
+  CH_CUDA(cudaStreamSynchronize(st));
+  *total_host = total;
+  if (total >= 0xffffffffull) CH_FAIL("%llu records exceed the 32-bit record index", total);
+  return 0;
+}
+
+extern "C" int ch_finalize_records(ch_ws* ws, const ch_final_args* a, void* stream) {
+  if (ws == nullptr) CH_FAIL("null workspace");
+  if (check_final(a, true)) return 1;
+  if (a->partial == nullptr || a->cols == nullptr) CH_FAIL("null partial / cols");
+  ChDeviceGuard guard(ws->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const FinalDev d = to_dev(a);
+  const int ncols = 2 * a->nR + a->nPR;
+  CH_CUDA(cudaMemsetAsync(a->partial, 0, static_cast<size_t>(a->nstripes) * a->nq_pad * ncols * sizeof(double), st));
+  finalize_kernel<<<blocks_for(static_cast<long long>(a->nstripes) * a->nq_pad, 128), 128, 0, st>>>(d);
+  CH_LAUNCH_CHECK(ws);
+  reduce_stripes_kernel<<<blocks_for(a->nq * ncols, 256), 256, 0, st>>>(a->partial, a->nstripes, a->nq, a->nq_pad,
+                                                                         ncols, a->cols);
+  CH_LAUNCH_CHECK(ws);
+  return 0;
+}
+
+extern "C" int ch_first_relevant(ch_ws* ws, const ch_final_args* a, uint32_t* first_rel_dev, void* stream) {
+  if (ws == nullptr || first_rel_dev == nullptr) CH_FAIL("null argument to ch_first_relevant");
+  if (check_final(a, false)) return 1;
+  ChDeviceGuard guard(ws->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const FinalDev d = to_dev(a);
+  first_relevant_kernel<<<blocks_for(static_cast<long long>(a->nstripes) * a->nq_pad, 128), 128, 0, st>>>(
+      d, first_rel_dev);
+  CH_LAUNCH_CHECK(ws);
+  return 0;
+}
+
+extern "C" int ch_reduce_means(ch_ws* ws, const double* cols_dev, const uint32_t* total_rel_dev,
+                               const uint32_t* first_rel_dev, int64_t nq, int nR, int nPR, const int64_t* pr_k,
+                               double* ap_out_dev, double* out_host, void* stream) {
+  if (ws == nullptr || cols_dev == nullptr || out_host == nullptr) CH_FAIL("null argument to ch_reduce_means");
+  if (nR < 0 || nR > CH_MAX_R || nPR < 0 || nPR > CH_MAX_PR) CH_FAIL("too many R / PRs entries");
+  const int nout = nR + 2 * nPR;
+  if (nout == 0) return 0;
+  ChDeviceGuard guard(ws->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  void* scratch = nullptr;
+  if (ch_ws_scratch(ws, (CH_MAX_PR + CH_MAX_R + 2 * CH_MAX_PR) * 8, &scratch)) return 1;
+  long long* prk_dev = static_cast<long long*>(scratch);
+  double* out_dev = reinterpret_cast<double*>(prk_dev + CH_MAX_PR);
+  long long prk_host[CH_MAX_PR];
+  for (int i = 0; i < CH_MAX_PR; ++i) prk_host[i] = i < nPR ? pr_k[i] : 1;
+  CH_CUDA(cudaMemcpyAsync(prk_dev, prk_host, sizeof(prk_host), cudaMemcpyHostToDevice, st));
+  reduce_means_kernel<<<nout, 1024, 0, st>>>(cols_dev, total_rel_dev, first_rel_dev, nq, nR, nPR, prk_dev, ap_out_dev,
+                                             out_dev);
+  CH_LAUNCH_CHECK(ws);
+  CH_CUDA(cudaMemcpyAsync(out_host, out_dev, static_cast<size_t>(nout) * 8, cudaMemcpyDeviceToHost, st));
+  CH_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int ch_scatter_ranked(ch_ws* ws, const ch_final_args* a, int64_t R, int64_t row_offset, int64_t* ids_dev,
+                                 int32_t* keys_dev, void* stream) {
+  if (ws == nullptr || ids_dev == nullptr) CH_FAIL("null argument to ch_scatter_ranked");
+  if (check_final(a, false)) return 1;
+  ChDeviceGuard guard(ws->device);
+  const FinalDev d = to_dev(a);
+  scatter_ranked_kernel<<<blocks_for(static_cast<long long>(a->nstripes) * a->nq_pad, 128), 128, 0,
+                          static_cast<cudaStream_t>(stream)>>>(d, R, row_offset,
+                                                               reinterpret_cast<long long*>(ids_dev), keys_dev);
+  CH_LAUNCH_CHECK(ws);
+  return 0;
+}
+
+extern "C" int ch_ap_from_ranked(ch_ws* ws, const int64_t* ids_dev, int64_t nq, int64_t R, const uint32_t* q_lab,
+                                 const uint32_t* g_lab, int label_mode, int mask_words, int nPR,
+                                 const int64_t* pr_k, double* cols_dev, void* stream) {
+  if (ws == nullptr || ids_dev == nullptr || q_lab == nullptr || g_lab == nullptr || cols_dev == nullptr)
+    CH_FAIL("null argument to ch_ap_from_ranked");
+  if (label_mode != CH_LAB_ID && label_mode != CH_LAB_MASK) CH_FAIL("bad label mode %d", label_mode);
+  if (nPR < 0 || nPR > CH_MAX_PR) CH_FAIL("too many PRs entries");
+  ChDeviceGuard guard(ws->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  void* scratch = nullptr;
+  if (ch_ws_scratch(ws, CH_MAX_PR * 8, &scratch)) return 1;
+  long long* prk_dev = static_cast<long long*>(scratch);
+  long long prk_host[CH_MAX_PR];
+  for (int i = 0; i < CH_MAX_PR; ++i) prk_host[i] = i < nPR ? pr_k[i] : 1;
+  CH_CUDA(cudaMemcpyAsync(prk_dev, prk_host, sizeof(prk_host), cudaMemcpyHostToDevice, st));
+  ap_from_ranked_kernel<<<blocks_for(nq * 32, 256), 256, 0, st>>>(reinterpret_cast<const long long*>(ids_dev), nq, R,
+                                                                  q_lab, g_lab, label_mode, mask_words, nPR, prk_dev,
+                                                                  cols_dev);
+  CH_LAUNCH_CHECK(ws);
+  // prk_host lives on this stack frame: make sure the copy has been consumed
+  CH_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int ch_hamming_matrix(ch_ws* ws, const uint32_t* q_bits, const uint32_t* q_nz, const uint32_t* g_bits,
+                                 const uint32_t* g_nz, int64_t nq, int64_t ndb, int nbit, int ternary,
+                                 uint16_t* out_dev, void* stream) {
+  if (ws == nullptr || q_bits == nullptr || g_bits == nullptr || out_dev == nullptr)
+    CH_FAIL("null argument to ch_hamming_matrix");
+  if (ternary && (q_nz == nullptr || g_nz == nullptr)) CH_FAIL("ternary codes need the non-zero planes");
+  const int nw = ch_code_words(nbit);
+  if (nw == 0) CH_FAIL("nbit=%d unsupported", nbit);
+  if (nq * ndb == 0) return 0;
+  ChDeviceGuard guard(ws->device);
+  long long blocks = (nq * ndb + 255) / 256;
+  if (blocks > ws->sm_count * 32ll) blocks = ws->sm_count * 32ll;
+  hamming_matrix_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      q_bits, q_nz, g_bits, g_nz, nq, ndb, nbit, nw, ternary, out_dev);
+  CH_LAUNCH_CHECK(ws);
+  return 0;
+}
+
+extern "C" int ch_popc_peak(ch_ws* ws, double* popc32_per_s, double* elapsed_ms) {
+  if (ws == nullptr || popc32_per_s == nullptr) CH_FAIL("null argument to ch_popc_peak");
+  ChDeviceGuard guard(ws->device);
+  void* scratch = nullptr;
+  if (ch_ws_scratch(ws, 64, &scratch)) return 1;
+  cudaEvent_t e0, e1;
+  CH_CUDA(cudaEventCreate(&e0));
+  CH_CUDA(cudaEventCreate(&e1));
+  const int iters = 4096, blocks = ws->sm_count * 8;
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    CH_CUDA(cudaEventRecord(e0, 0));
+    popc_peak_kernel<<<blocks, 256>>>(static_cast<uint32_t*>(scratch), iters, 12345u + rep);
+    CH_LAUNCH_CHECK(ws);
+    CH_CUDA(cudaEventRecord(e1, 0));
+    CH_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CH_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  const double ops = static_cast<double>(blocks) * 256.0 * iters * 8.0;
+  *popc32_per_s = ops / (best * 1e-3);
+  if (elapsed_ms) *elapsed_ms = best;
+  return 0;
+}

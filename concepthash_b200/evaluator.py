@@ -1,0 +1,358 @@
+"""Orchestration of one retrieval evaluation (codes -> ranked Hamming retrieval -> mAP@R / P@k / R@k).
+
+The same code runs on 1 GPU and on a gallery row-sharded over G GPUs (one process per GPU, contiguous
+row blocks in rank order, queries replicated).  The only data exchanged between ranks are
+
+  * one all-gather of the per-rank key histograms  (nbins x nq u32, x2 when labels are counted),
+  * (top-R mode) one all-gather of the relevant-candidate histograms,
+  * one all-reduce(sum) of the per-query partial AP sums / hit counts (fp64),
+  * a few scalars (flags, row counts) and, for ``remove_first_retrieved``, an nq-element max.
+
+Stable ties "ascending gallery row index" == (rank, stripe, in-stripe prefix), which is why the gather
+(not a plain sum) is needed: every rank takes the exclusive prefix over lower ranks.
+
+All arithmetic happens in the backend (CUDA kernels behind the C-ABI); this file only sequences the
+calls.  ``tests/`` substitute a numpy emulation of the backend to exercise this file on CPU with gloo.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+
+
+class LocalComm:
+    """world_size == 1: collectives are the identity."""
+    world, rank = 1, 0
+
+    def all_gather(self, t):
+        return t.unsqueeze(0)
+
+    def all_reduce_sum(self, t):
+        return t
+
+    def all_reduce_max(self, t):
+        return t
+
+
+class DistComm:
+    """torch.distributed (NCCL over NVLink on GPUs; gloo in the CPU tests)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+
+    def all_gather(self, t):
+        flat = t.contiguous().view(-1)
+        out = torch.empty((self.world * flat.numel(),), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, flat, group=self.group)
+        return out.view((self.world,) + tuple(t.shape))
+
+    def all_reduce_sum(self, t):
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def all_reduce_max(self, t):
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        return t
+
+
+def _as_int_list(t):
+    return [int(v) for v in t.cpu().tolist()]
+
+
+class Packed:
+    """Packed codes + labels of one side (query or gallery shard)."""
+    __slots__ = ("n", "nbit", "bits", "nz", "ids", "masks", "info", "ncls")
+
+
+class Evaluator:
+    def __init__(self, backend, comm=None):
+        self.b = backend
+        self.comm = comm if comm is not None else LocalComm()
+        self.stats = {}
+        self.stripe_rows_override = None   # tests: force the stripe length (multiple of 256 on CUDA)
+        self.profile = False               # bench: bracket the kernels with CUDA events on the launch stream
+        self.events = []                   # (kind, work units, start event, end event)
+
+    def _timed(self, kind, units, fn):
+        if not self.profile:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        self.events.append((kind, units, e0, e1))
+        return out
+
+    # ------------------------------------------------------------------ packing
+    def _pack_side(self, codes, labels, threshold, flags, nolabel):
+        p = Packed()
+        p.n, p.nbit = int(codes.shape[0]), int(codes.shape[1])
+        # algorithmic bytes of K1: the real-valued codes read once + the packed bits written once
+        pack_bytes = p.n * p.nbit * codes.element_size() + p.n * p.nbit // 8
+        kind = "pack_dev" if codes.is_cuda else "pack_host"
+        p.bits, p.nz = self._timed(kind, pack_bytes, lambda: self.b.pack_sign(codes, threshold, flags))
+        p.ids = p.masks = p.info = None
+        p.ncls = 0
+        if labels is not None:
+            if labels.shape[0] != p.n:
+                raise ValueError(f"{labels.shape[0]} label rows for {p.n} code rows")
+            p.ids, p.masks, p.info = self.b.pack_labels(labels, nolabel)
+            p.ncls = int(labels.shape[1]) if labels.dim() == 2 else 0
+        return p
+
+    def _prepare(self, db_codes, db_labels, q_codes, q_labels, threshold):
+        if q_codes.dim() != 2 or db_codes.dim() != 2:
+            raise ValueError("codes must be 2-D (N, nbit)")
+        if q_codes.shape[1] != db_codes.shape[1]:
+            raise ValueError(f"nbit mismatch: query {q_codes.shape[1]} vs gallery {db_codes.shape[1]}")
+        if q_codes.shape[0] == 0:
+            raise ValueError("no queries")
+        if (q_labels is None) != (db_labels is None):
+            raise ValueError("labels must be given for both sides or neither")
+        if q_labels is not None and q_labels.dim() == 2 and db_labels.dim() == 2 and \
+                q_labels.shape[1] != db_labels.shape[1]:
+            raise ValueError("query and gallery labels have different class counts")
+        flags = self.b.zeros((1,), torch.int32)
+        q = self._pack_side(q_codes, q_labels, threshold, flags, L.CH_QUERY_NOLABEL)
+        g = self._pack_side(db_codes, db_labels, threshold, flags, L.CH_GALLERY_NOLABEL)
+        # one small exchange: [flags, max positives per row (both sides), local gallery rows]
+        meta = self.b.zeros((4,), torch.int64)
+        meta[0] = flags[0] & 1           # some sign is 0 -> ternary keys
+        meta[3] = (flags[0] >> 1) & 1    # NaN seen
+        if q_labels is not None:
+            meta[1] = torch.maximum(q.info[0], g.info[0])
+            meta[2] = torch.maximum(q.info[1], g.info[1])
+        meta = self.comm.all_reduce_max(meta)
+        rows = self.b.zeros((self.comm.world,), torch.int64)
+        rows[self.comm.rank] = g.n
+        rows = _as_int_list(self.comm.all_reduce_sum(rows))
+        m = _as_int_list(meta)
+        if m[3]:
+            raise ValueError("codes contain NaN")
+        ternary = bool(m[0])
+        label_mode, lw, nclass = L.CH_LAB_NONE, 0, 0
+        if q_labels is not None:
+            if m[1] <= 1:
+                label_mode, nclass = L.CH_LAB_ID, m[2]
+            else:
+                if q.masks is None or g.masks is None:
+                    raise ValueError("multi-hot labels on one side need 2-D labels on the other side too")
+                label_mode, lw = L.CH_LAB_MASK, int(q.masks.shape[1])
+        return q, g, ternary, label_mode, lw, nclass, rows
+
+    # ------------------------------------------------------------------ one histogram pass
+    def _hist(self, q, g, geo, ternary, label_mode, lw, slab_all, slab_rel, thresh=None, emit=L.CH_EMIT_NONE,
+              rec=None):
+        threads, nq_pad, nstripes, rps = geo
+        lab = lambda p: None if label_mode == L.CH_LAB_NONE else (p.ids if label_mode == L.CH_LAB_ID else p.masks)
+        kind = "hist_select" if thresh is not None else ("hist_count_rec" if emit else "hist_count")
+        self._timed(kind, q.n * g.n, lambda: self.b.hamming_hist(
+            q_bits=q.bits, q_nz=q.nz, g_bits=g.bits, g_nz=g.nz, q_lab=lab(q), g_lab=lab(g),
+            slab_all=slab_all, slab_rel=slab_rel if label_mode != L.CH_LAB_NONE else None, thresh=thresh,
+            rec_off=rec["off"] if rec else None, rec_cap=rec["cap"] if rec else None,
+            rec_cnt=rec["cnt"] if rec else None, recs=rec["recs"] if rec else None,
+            err_flag=rec["err"] if rec else None, nq=q.n, nq_pad=nq_pad, ndb=g.n, nbit=q.nbit, ternary=ternary,
+            label_mode=label_mode, mask_words=lw, emit_mode=emit, nstripes=nstripes, threads=threads,
+            rows_per_stripe=rps))
+
+    def _gathered_totals(self, slab, nstripes, nbins, nq_pad):
+        tot = self.b.empty((nbins, nq_pad), torch.int32)
+        self.b.slab_totals(slab, nstripes, nbins, nq_pad, tot)
+        return self.comm.all_gather(tot)           # (world, nbins, nq_pad)
+
+    def _alloc_records(self, cap, geo, nq):
+        threads, nq_pad, nstripes, rps = geo
+        off = self.b.empty((nstripes, nq_pad), torch.int32)
+        total = self.b.record_offsets(cap, nstripes, nq, nq_pad, off)
+        self.stats["record_slots"] = total
+        return dict(off=off, cap=cap, cnt=self.b.zeros((nstripes, nq_pad), torch.int32),
+                    recs=self.b.empty((max(total, 1), 4), torch.int32), err=self.b.zeros((1,), torch.int32))
+
+    def _check_records(self, rec):
+        if int(rec["err"].cpu()[0]) != 0:
+            raise RuntimeError("internal error: record buffer overflow")
+
+    # ------------------------------------------------------------------ the evaluation
+    def evaluate(self, db_codes, db_labels, q_codes, q_labels, R, threshold=0.0, PRs=(),
+                 remove_first_retrieved=False, return_ap=False):
+        """Returns ``(mAPs list, recalls list, precisions list[, ap (nR, nq) tensor])``.
+
+        ``db_codes`` / ``db_labels`` are THIS rank's contiguous gallery row block; queries are replicated."""
+        b, comm = self.b, self.comm
+        r_list = [int(r) for r in R]
+        pr_k = [int(k) for k in PRs]
+        if len(r_list) == 0 and len(pr_k) == 0:
+            return [], [], []
+        if any(r == 0 or r < -1 for r in r_list) or any(k <= 0 for k in pr_k):
+            raise ValueError("R must be -1 or positive; PRs must be positive")
+        q, g, ternary, label_mode, lw, nclass, rows = self._prepare(db_codes, db_labels, q_codes, q_labels, threshold)
+        if label_mode == L.CH_LAB_NONE:
+            raise ValueError("labels are required")
+        nq, nbit = q.n, q.nbit
+        nbins = (2 * nbit if ternary else nbit) + 1
+        ndb_total = sum(rows)
+        rf = 1 if remove_first_retrieved else 0
+        list_len = max(ndb_total - rf, 0)
+        r_eff = [list_len if r == -1 else min(r, list_len) for r in r_list]
+        rmax = max(r_eff + [min(k, list_len) for k in pr_k] + [0])
+        geo = b.geometry(nq, g.n, nbit, ternary, label_mode, lw)
+        geo = self._agree_geometry(geo, g.n)
+        threads, nq_pad, nstripes, rps = geo
+        self.stats.update(dict(ternary=ternary, label_mode=label_mode, geometry=geo, nbins=nbins,
+                               ndb_total=ndb_total, world=comm.world))
+
+        slab_all = b.zeros((nstripes, nbins, nq_pad), torch.int32)
+        slab_rel = b.zeros((nstripes, nbins, nq_pad), torch.int32)
+        base0_all = b.empty((nbins, nq_pad), torch.int32)
+        base0_rel = b.empty((nbins, nq_pad), torch.int32)
+        total_rel = b.zeros((nq_pad,), torch.int32)
+
+        full_ranking = rmax * 4 >= list_len          # top-R close to "all": one pass is cheaper than two
+        self.stats["mode"] = "all" if full_ranking else "topR"
+        if full_ranking:
+            # ---- single pass: count every pair, record every relevant pair ----
+            cap = b.empty((nstripes, nq_pad), torch.int32)
+            if label_mode == L.CH_LAB_ID and 0 < nclass * nstripes <= (1 << 26):
+                cls = b.zeros((nstripes, nclass), torch.int32)
+                b.class_counts(g.ids, g.n, rps, nclass, cls)
+                b.record_caps(2, cls, q.ids, nstripes, nclass, nq, nq_pad, False, cap)
+            else:
+                # capacities from a counting pass (multi-hot labels, or too many classes for the table)
+                self._hist(q, g, geo, ternary, label_mode, lw, slab_all, slab_rel)
+                b.record_caps(1, slab_rel, None, nstripes, nbins, nq, nq_pad, False, cap)
+                slab_all.zero_()
+                slab_rel.zero_()
+            rec = self._alloc_records(cap, geo, nq)
+            self._hist(q, g, geo, ternary, label_mode, lw, slab_all, slab_rel, emit=L.CH_EMIT_RELEVANT, rec=rec)
+            tot = comm.all_gather(torch.stack([self._local_totals(slab_all, geo, nbins),
+                                               self._local_totals(slab_rel, geo, nbins)]))
+            b.scan_bases(tot[:, 0].contiguous(), comm.world, comm.rank, nbins, nq, nq_pad, -1, base0_all, None, None)
+            b.scan_bases(tot[:, 1].contiguous(), comm.world, comm.rank, nbins, nq, nq_pad, -1, base0_rel, None,
+                         total_rel)
+            b.slab_exscan(slab_all, nstripes, nbins, nq_pad)
+            b.slab_exscan(slab_rel, nstripes, nbins, nq_pad)
+            sbase_all, sbase_rel = slab_all, slab_rel
+        else:
+            # ---- pass 1: key histogram of every pair -> per-query threshold key ----
+            need_total_rel = len(pr_k) > 0
+            lm1 = label_mode if need_total_rel else L.CH_LAB_NONE
+            self._hist(q, g, geo, ternary, lm1, lw, slab_all, slab_rel)
+            thresh = b.empty((nq_pad,), torch.int32)
+            tot_a = comm.all_gather(self._local_totals(slab_all, geo, nbins))
+            b.scan_bases(tot_a, comm.world, comm.rank, nbins, nq, nq_pad, rmax + rf, base0_all, thresh, None)
+            if need_total_rel:
+                tot_r = comm.all_gather(self._local_totals(slab_rel, geo, nbins))
+                b.scan_bases(tot_r, comm.world, comm.rank, nbins, nq, nq_pad, -1, base0_rel, None, total_rel)
+            cap = b.empty((nstripes, nq_pad), torch.int32)
+            b.record_caps(0, slab_all, thresh, nstripes, nbins, nq, nq_pad, False, cap)
+            if label_mode == L.CH_LAB_ID and 0 < nclass * nstripes <= (1 << 26):
+                cls = b.zeros((nstripes, nclass), torch.int32)
+                b.class_counts(g.ids, g.n, rps, nclass, cls)
+                b.record_caps(2, cls, q.ids, nstripes, nclass, nq, nq_pad, True, cap)
+            b.slab_exscan(slab_all, nstripes, nbins, nq_pad)
+            sbase_all = slab_all
+            rec = self._alloc_records(cap, geo, nq)
+            # ---- pass 2: only pairs with key <= threshold are counted / matched / recorded ----
+            scratch_all = b.zeros((nstripes, nbins, nq_pad), torch.int32)
+            slab_rel.zero_()
+            self._hist(q, g, geo, ternary, label_mode, lw, scratch_all, slab_rel, thresh=thresh,
+                       emit=L.CH_EMIT_RELEVANT, rec=rec)
+            del scratch_all
+            tot_r2 = comm.all_gather(self._local_totals(slab_rel, geo, nbins))
+            b.scan_bases(tot_r2, comm.world, comm.rank, nbins, nq, nq_pad, -1, base0_rel, None, None)
+            b.slab_exscan(slab_rel, nstripes, nbins, nq_pad)
+            sbase_rel = slab_rel
+
+        ncols = 2 * len(r_eff) + len(pr_k)
+        cols = b.zeros((nq, max(ncols, 1)), torch.float64)
+        f = dict(recs=rec["recs"], rec_off=rec["off"], rec_cnt=rec["cnt"], base0_all=base0_all, base0_rel=base0_rel,
+                 sbase_all=sbase_all, sbase_rel=sbase_rel, first_rel=None,
+                 partial=b.empty((nstripes, nq_pad, max(ncols, 1)), torch.float64), cols=cols,
+                 nq=nq, nq_pad=nq_pad, nstripes=nstripes, nbins=nbins, remove_first=bool(rf), r_eff=r_eff, pr_k=pr_k)
+        first_rel = None
+        if rf:
+            first_rel = b.zeros((nq_pad,), torch.int32)
+            b.first_relevant(f, first_rel)
+            first_rel = comm.all_reduce_max(first_rel)
+            f["first_rel"] = first_rel
+        b.finalize_records(f)
+        self._check_records(rec)
+        self.stats["records"] = None
+        cols = comm.all_reduce_sum(cols)
+        ap = b.empty((len(r_eff), nq), torch.float64) if return_ap else None
+        maps, recalls, precisions = b.reduce_means(cols, total_rel if pr_k else None, first_rel, nq, len(r_eff), pr_k,
+                                                   ap)
+        if return_ap:
+            return maps, recalls, precisions, ap
+        return maps, recalls, precisions
+
+    def _local_totals(self, slab, geo, nbins):
+        threads, nq_pad, nstripes, rps = geo
+        tot = self.b.empty((nbins, nq_pad), torch.int32)
+        self.b.slab_totals(slab, nstripes, nbins, nq_pad, tot)
+        return tot
+
+    def _agree_geometry(self, geo, ndb=None):
+        """threads / nq_pad depend only on (nq, nbins) and are identical on all ranks; the stripe layout is
+        per rank (shards may differ in length), so nothing has to be exchanged."""
+        if self.stripe_rows_override and ndb is not None:
+            threads, nq_pad, _, _ = geo
+            rps = int(self.stripe_rows_override)
+            return threads, nq_pad, max(1, (ndb + rps - 1) // rps), rps
+        return geo
+
+    # ------------------------------------------------------------------ ranked retrieval
+    def retrieve(self, db_codes, q_codes, R, threshold=0.0, remove_first_retrieved=False):
+        """Exact ranked retrieval: ``(ids int64 (nq, L), keys int32 (nq, L), ternary)`` with
+        ``L = min(R, gallery size)``, canonical order (distance, then global gallery row).
+        keys = Hamming distance (binary codes) or 2 x distance (ternary)."""
+        b, comm = self.b, self.comm
+        q, g, ternary, _, _, _, rows = self._prepare(db_codes, None, q_codes, None, threshold)
+        nq, nbit = q.n, q.nbit
+        nbins = (2 * nbit if ternary else nbit) + 1
+        ndb_total = sum(rows)
+        rf = 1 if remove_first_retrieved else 0
+        list_len = max(ndb_total - rf, 0)
+        R = list_len if R == -1 else min(int(R), list_len)
+        row_offset = sum(rows[:comm.rank])
+        geo = self._agree_geometry(b.geometry(nq, g.n, nbit, ternary, L.CH_LAB_NONE, 0), g.n)
+        threads, nq_pad, nstripes, rps = geo
+        slab_all = b.zeros((nstripes, nbins, nq_pad), torch.int32)
+        self._hist(q, g, geo, ternary, L.CH_LAB_NONE, 0, slab_all, None)
+        base0_all = b.empty((nbins, nq_pad), torch.int32)
+        thresh = b.empty((nq_pad,), torch.int32)
+        tot_a = comm.all_gather(self._local_totals(slab_all, geo, nbins))
+        b.scan_bases(tot_a, comm.world, comm.rank, nbins, nq, nq_pad, R + rf, base0_all, thresh, None)
+        cap = b.empty((nstripes, nq_pad), torch.int32)
+        b.record_caps(0, slab_all, thresh, nstripes, nbins, nq, nq_pad, False, cap)
+        b.slab_exscan(slab_all, nstripes, nbins, nq_pad)
+        rec = self._alloc_records(cap, geo, nq)
+        scratch_all = b.zeros((nstripes, nbins, nq_pad), torch.int32)
+        self._hist(q, g, geo, ternary, L.CH_LAB_NONE, 0, scratch_all, None, thresh=thresh,
+                   emit=L.CH_EMIT_CANDIDATES, rec=rec)
+        ids = b.full((nq, max(R, 1)), -1, torch.int64)
+        keys = b.full((nq, max(R, 1)), -1, torch.int32)
+        f = dict(recs=rec["recs"], rec_off=rec["off"], rec_cnt=rec["cnt"], base0_all=base0_all, base0_rel=None,
+                 sbase_all=slab_all, sbase_rel=None, first_rel=None, partial=None, cols=None, nq=nq, nq_pad=nq_pad,
+                 nstripes=nstripes, nbins=nbins, remove_first=bool(rf), r_eff=[], pr_k=[])
+        b.scatter_ranked(f, R, row_offset, ids, keys)
+        self._check_records(rec)
+        if comm.world > 1:
+            ids = comm.all_reduce_max(ids)
+            keys = comm.all_reduce_max(keys)
+        return ids[:, :R], keys[:, :R], ternary
+
+    # ------------------------------------------------------------------ dense distances (small)
+    def hamming_matrix(self, a_codes, b_codes, threshold=0.0):
+        """Dense key matrix (na, nb) int16 and the ternary flag (local, no collectives)."""
+        flags = self.b.zeros((1,), torch.int32)
+        pa = self._pack_side(a_codes, None, threshold, flags, 0)
+        pb = self._pack_side(b_codes, None, 0.0, flags, 0)
+        fl = int(flags.cpu()[0])
+        if fl & 2:
+            raise ValueError("codes contain NaN")
+        ternary = bool(fl & 1)
+        return self.b.hamming_matrix(pa.bits, pa.nz, pb.bits, pb.nz, pa.n, pb.n, pa.nbit, ternary), ternary

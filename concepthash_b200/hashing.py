@@ -1,0 +1,130 @@
+"""Public Python surface of the B200-native retrieval evaluation -- the drop-in for the reference's
+missing ``utils.hashing`` module (imported at ``experiments/test_hashing.py:15`` and
+``experiments/train_helper.py:18``; called at ``test_hashing.py:106-119,153-162`` and
+``train_helper.py:228-234``).  Same names, argument meaning, return types and error behaviour.
+
+Positional order is the call sites': GALLERY first, QUERY second.
+"""
+from __future__ import annotations
+
+import torch
+
+from .evaluator import DistComm, Evaluator, LocalComm
+
+_EVALUATORS = {}
+
+
+def get_evaluator(device=None, group=None):
+    """Process-wide evaluator for ``device`` (one ``ch_ws`` workspace per GPU), optionally bound to a
+    ``torch.distributed`` process group for the row-sharded gallery mode."""
+    from .backend_cuda import CudaBackend   # raises loudly if CUDA or the native library is missing
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+    key = (str(device), id(group) if group is not None else None)
+    ev = _EVALUATORS.get(key)
+    if ev is None:
+        comm = DistComm(group) if group is not None else LocalComm()
+        ev = Evaluator(CudaBackend(device), comm)
+        _EVALUATORS[key] = ev
+    return ev
+
+
+def _device_of(*tensors):
+    for t in tensors:
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            return t.device
+    return None
+
+
+def _check_common(dist_metric, landmark_gt, db_id, test_id):
+    if dist_metric != "hamming":
+        # only "hamming" is ever configured (configs/train.yaml:21, configs/val.yaml:11)
+        raise NotImplementedError(f"dist_metric={dist_metric!r}: only 'hamming' is implemented")
+    if landmark_gt is not None:
+        raise NotImplementedError("GLDv2 landmark ground truth (landmark_gt/db_id/test_id) is not implemented")
+
+
+def _as_tensor(x):
+    return x.detach() if isinstance(x, torch.Tensor) else torch.as_tensor(x)
+
+
+def calculate_mAP(db_codes, db_labels, test_codes, test_labels, R, threshold=0., dist_metric="hamming",
+                  PRs=None, multiclass=False, landmark_gt=None, db_id=None, test_id=None,
+                  remove_first_retrieved=False, group=None, **_ignored):
+    """mAP@R (+ R@k, P@k for ``PRs``) of a Hamming ranking on sign-binarised codes.
+
+    ``R``: int, ``-1`` = whole gallery (configs/val.yaml:7), or a list (test_hashing.py:124-128).
+    Returns ``(mAP | [mAP, ...], recalls, precisions)`` as Python floats / lists of floats.
+    Ties are broken by ascending gallery row index.  Inputs are neither retained nor mutated.
+    With ``group`` (a torch.distributed process group) ``db_*`` is this rank's contiguous gallery block.
+    """
+    _check_common(dist_metric, landmark_gt, db_id, test_id)
+    db_codes, db_labels, test_codes, test_labels = map(_as_tensor, (db_codes, db_labels, test_codes, test_labels))
+    r_is_list = isinstance(R, (list, tuple)) or (hasattr(R, "__iter__") and not isinstance(R, (str, bytes)))
+    r_list = [int(r) for r in R] if r_is_list else [int(R)]
+    pr_list = [] if PRs is None else [int(k) for k in PRs]
+    ev = get_evaluator(_device_of(db_codes, test_codes, db_labels, test_labels), group)
+    maps, recalls, precisions = ev.evaluate(db_codes, db_labels, test_codes, test_labels, r_list, threshold,
+                                            pr_list, bool(remove_first_retrieved))
+    return (maps if r_is_list else maps[0]), recalls, precisions
+
+
+def map_at_r(*, query_codes, db_codes, query_labels, db_labels, R, **kw):
+    """Keyword-only convenience in BASELINE.json's wording (query first)."""
+    return calculate_mAP(db_codes, db_labels, query_codes, query_labels, R, **kw)[0]
+
+
+def default_pr_cutoffs(n):
+    out, k = [], 1
+    while k < n:
+        out.append(k)
+        k *= 2
+    if n > 0:
+        out.append(int(n))
+    return out
+
+
+def calculate_pr_curve(db_codes, db_labels, test_codes, test_labels, threshold=0., dist_metric="hamming",
+                       remove_first_retrieved=False, Rs=None, group=None, **_ignored):
+    """Precision / recall at a set of cut-offs (second symbol imported at test_hashing.py:15; used at
+    :152-168).  Returns ``(recalls, precisions, Rs)``; default ``Rs`` = powers of two up to the list
+    length, plus the length itself.  Hit counting as in ``calculate_mAP``."""
+    _check_common(dist_metric, None, None, None)
+    db_codes = _as_tensor(db_codes)
+    n = int(db_codes.shape[0])
+    if group is not None:
+        import torch.distributed as dist
+        t = torch.tensor([n], dtype=torch.int64, device=_device_of(db_codes) or "cuda")
+        dist.all_reduce(t, group=group)
+        n = int(t.item())
+    n -= 1 if remove_first_retrieved else 0
+    rs = default_pr_cutoffs(n) if Rs is None else [int(r) for r in Rs]
+    recalls, precisions = [], []
+    for i in range(0, len(rs), 32):      # CH_MAX_PR cut-offs per pass
+        _, r, p = calculate_mAP(db_codes, db_labels, test_codes, test_labels, [], threshold=threshold,
+                                PRs=rs[i:i + 32], remove_first_retrieved=remove_first_retrieved, group=group)
+        recalls += r
+        precisions += p
+    return recalls, precisions, rs
+
+
+def retrieve_topk(query_codes, db_codes, R, threshold=0., remove_first_retrieved=False, group=None):
+    """Exact ranked retrieval: ``(ids int64 (nq, L), dist float32 (nq, L))``, ascending (distance, gallery
+    row) -- bit-identical to a stable sort of the dense distance matrix."""
+    query_codes, db_codes = _as_tensor(query_codes), _as_tensor(db_codes)
+    ev = get_evaluator(_device_of(db_codes, query_codes), group)
+    ids, keys, ternary = ev.retrieve(db_codes, query_codes, int(R), threshold, bool(remove_first_retrieved))
+    dist = keys.to(torch.float32) * (0.5 if ternary else 1.0)
+    return ids, dist
+
+
+def get_hamm_dist(codes, centroids, margin=0., normalize=False):
+    """Code -> codebook Hamming distance matrix (callers: trainers/orthohash.py:362,397,430,465,
+    trainers/dpn.py:30,62; identity: trainers/orthohash.py:263-264).  float32, on the GPU."""
+    codes, centroids = _as_tensor(codes), _as_tensor(centroids)
+    if codes.shape[1] != centroids.shape[1]:
+        raise ValueError("nbit mismatch")
+    ev = get_evaluator(_device_of(codes, centroids))
+    keys, ternary = ev.hamming_matrix(codes, centroids, margin)
+    d = keys.to(torch.float32) * (0.5 if ternary else 1.0)
+    return d / codes.shape[1] if normalize else d

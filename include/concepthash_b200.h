@@ -1,0 +1,222 @@
+/*
+ * concepthash_b200 -- C-ABI of the B200-native retrieval-evaluation hot path
+ * (real-valued hash codes -> sign/bit-pack -> Hamming ranking -> exact top-R -> mAP@R / P@k / R@k).
+ *
+ * Drop-in boundary.  The reference (kamwoh/concepthash) is pure Python; the interface this
+ * library sits under is the import
+ *     from utils.hashing import calculate_mAP, calculate_pr_curve      experiments/test_hashing.py:15
+ *     from utils.hashing import calculate_mAP                          experiments/train_helper.py:18
+ * and the two call sites experiments/test_hashing.py:106-119 and experiments/train_helper.py:228-234.
+ * `utils/hashing.py` in this repository is the ctypes binding a maintainer drops into the reference's
+ * `utils/` directory.  Every entry point below is one step of that function;
+ * the reference-side statement of the step it replaces is cited next to it.
+ *
+ * Conventions
+ *   - plain C, `extern "C"`, no torch / C++ types in any signature;
+ *   - every function returns 0 on success, non-zero on failure; `ch_last_error()` gives the message
+ *     (thread-local); nothing aborts, nothing falls back to the CPU;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream);
+ *   - all `*_dev` pointers are device pointers owned by the caller (the Python side allocates them as
+ *     torch tensors: torch is plumbing for memory / streams / NCCL only);
+ *   - "rows_pad" = ch_padded_rows(n): packed arrays are allocated with that many rows, pad rows are
+ *     written as zero by the pack kernels (the streaming kernels bulk-copy whole 16-byte groups);
+ *   - sort key of a (query, gallery) pair: key = Hamming distance (binary codes) or
+ *     key = 2 * distance (ternary codes: sign(0) = 0 gives half-integer distances);
+ *     nbins = nbit + 1 (binary) or 2 * nbit + 1 (ternary);
+ *   - canonical ranking: ascending (key, global gallery row index)  (SURVEY.md F4).
+ */
+#ifndef CONCEPTHASH_B200_H
+#define CONCEPTHASH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CH_ABI_VERSION 1
+#define CH_MAX_NBIT 256          /* words per code: 1, 2, 4 or 8 x u32 */
+#define CH_MAX_R 8               /* length of an `R` list (test_hashing.py:124-128) */
+#define CH_MAX_PR 32             /* length of `PRs` */
+
+/* element types of caller tensors */
+enum { CH_F32 = 0, CH_F16 = 1, CH_BF16 = 2, CH_F64 = 3, CH_I64 = 4, CH_I32 = 5, CH_U8 = 6, CH_I16 = 7, CH_I8 = 8 };
+/* where a caller buffer lives */
+enum { CH_MEM_DEVICE = 0, CH_MEM_HOST = 1 };
+/* label representation after ch_pack_labels */
+enum { CH_LAB_NONE = 0, CH_LAB_ID = 1, CH_LAB_MASK = 2 };
+/* what the histogram pass records per (query, stripe) */
+enum { CH_EMIT_NONE = 0, CH_EMIT_RELEVANT = 1, CH_EMIT_CANDIDATES = 2 };
+
+#define CH_QUERY_NOLABEL   0xFFFFFFFFu   /* id of a query row without any positive class  */
+#define CH_GALLERY_NOLABEL 0xFFFFFFFEu   /* id of a gallery row without any positive class */
+
+typedef struct ch_ws ch_ws;     /* per-process / per-GPU workspace: device props, H2D staging, copy stream */
+
+int         ch_abi_version(void);
+const char* ch_last_error(void);
+int         ch_workspace_create(int device, ch_ws** out);
+int         ch_workspace_destroy(ch_ws* ws);
+int         ch_device_info(ch_ws* ws, int* sm_count, int* max_smem_optin, int* l2_bytes, int* clock_khz);
+
+/* rows a packed array must be allocated with */
+int64_t ch_padded_rows(int64_t n);
+/* u32 words per packed code row for `nbit` (1, 2, 4 or 8); 0 if unsupported */
+int     ch_code_words(int nbit);
+
+/* ---- K1: sign + bit-pack ---------------------------------------------------------------------
+ * Replaces `torch.sign(codes)` (+ `codes[|codes| < threshold] = 0` when threshold != 0) of the
+ * missing utils.hashing.calculate_mAP; in-tree statements: models/layers/signhash.py:11,
+ * trainers/orthohash.py:78; threshold: experiments/test_hashing.py:109, configs/val.yaml:12.
+ *   codes   : (n, nbit) real-valued, element (i, k) at codes[i * row_stride + k * col_stride]
+ *             (strides in elements; non-contiguous slices of test_hashing.py:91-98 are fine);
+ *             CH_MEM_HOST buffers are staged through the workspace in pipelined chunks.
+ *   threshold: already rounded to the dtype of `codes` by the caller (torch compares in that dtype)
+ *   out_bits: (rows_pad, words) u32, bit (k % 32) of word k / 32 = codes[i, k] > 0
+ *   out_nz  : same shape, bit = sign(codes[i, k]) != 0; may be NULL only if the caller knows there
+ *             are no zeros (it is still checked: flags bit 0)
+ *   flags   : device u32, OR-ed: bit 0 = some sign is 0 (ternary needed), bit 1 = NaN seen
+ */
+int ch_pack_sign(ch_ws* ws, const void* codes, int mem, int dtype, int64_t n, int nbit,
+                 int64_t row_stride, int64_t col_stride, double threshold,
+                 uint32_t* out_bits_dev, uint32_t* out_nz_dev, uint32_t* flags_dev, void* stream);
+
+/* ---- labels ----------------------------------------------------------------------------------
+ * Relevance in the reference = "share >= 1 positive class" on (N, C) one-/multi-hot labels
+ * (missing utils.hashing; same notion as models/loss/dpsh.py:58, trainers/adsh.py:144).
+ *   labels (n, C): positives are entries > 0.  C == 0 means 1-D integer class ids (n,).
+ *   out_ids  : (rows_pad) u32 = index of the first positive (or `nolabel`)
+ *   out_masks: (rows_pad, mask_words) u32 bitmask of positives, mask_words = ceil(C / 32); may be
+ *              NULL when C == 0
+ *   info     : device u32[4]: [0] max positives per row (atomicMax), [1] max id + 1,
+ *              [2] rows with no positive, [3] reserved
+ */
+int ch_pack_labels(ch_ws* ws, const void* labels, int mem, int dtype, int64_t n, int C,
+                   int64_t row_stride, int64_t col_stride, uint32_t nolabel,
+                   uint32_t* out_ids_dev, uint32_t* out_masks_dev, uint32_t* info_dev, void* stream);
+
+/* ---- K2: Hamming + per-query key histogram (+ stable in-bucket prefixes) ---------------------
+ * Replaces the 32-row chunked `0.5 * (nbit - q @ chunk.T)` GEMM loop + the dense (nq, ndb) matrix
+ * (identity: trainers/orthohash.py:263-264 `get_hd`, trainers/orthohash.py:49) and is the counting
+ * half of `torch.topk(dist, R, largest=False)` (sibling in tree: utils/metrics.py:20).
+ * One thread owns one query; a CTA owns `threads` queries x one gallery stripe (contiguous rows,
+ * streamed through shared memory by bulk async copies); the per-thread histogram lives in shared
+ * memory as {lo16 = all items, hi16 = relevant items} per key and is flushed to the stripe slabs.
+ */
+typedef struct ch_hist_args {
+  /* packed inputs */
+  const uint32_t* q_bits;  const uint32_t* q_nz;   /* (nq_pad', words); q_nz NULL unless ternary */
+  const uint32_t* g_bits;  const uint32_t* g_nz;   /* (rows_pad, words) local gallery shard       */
+  const uint32_t* q_lab;   const uint32_t* g_lab;  /* ids (n) or masks (n, mask_words); NULL if CH_LAB_NONE */
+  /* outputs: stripe slabs, zero-initialised by the caller */
+  uint32_t* slab_all;      /* (nstripes, nbins, nq_pad) */
+  uint32_t* slab_rel;      /* same; NULL if label_mode == CH_LAB_NONE */
+  /* thresholded ("select") mode: only pairs with key <= thresh[q] are counted / recorded */
+  const uint32_t* thresh;  /* (nq_pad) or NULL = count every pair */
+  /* records (16 B each: {key | rel << 31, in-stripe prefix all, in-stripe prefix relevant, local row}) */
+  const uint32_t* rec_off; /* (nstripes, nq_pad) first record slot of (stripe, query) */
+  const uint32_t* rec_cap; /* (nstripes, nq_pad) capacity of (stripe, query)          */
+  uint32_t* rec_cnt;       /* (nstripes, nq_pad) records written                      */
+  void*     recs;          /* uint4[]                                                 */
+  uint32_t* err_flag;      /* device u32, set non-zero on record overflow             */
+  int64_t nq, nq_pad, ndb;             /* ndb = rows of the local shard */
+  int32_t nbit, ternary, label_mode, mask_words, emit_mode;
+  int32_t nstripes, threads, rows_per_stripe;   /* geometry from ch_hist_geometry */
+} ch_hist_args;
+
+/* chooses threads per CTA (= queries per CTA), nq_pad, stripes and rows per stripe (a multiple of 256)
+ * for a problem on this device; call it once per evaluation with the richest label mode used. */
+int ch_hist_geometry(ch_ws* ws, int64_t nq, int64_t ndb, int nbit, int ternary, int label_mode,
+                     int mask_words, int32_t* threads, int64_t* nq_pad, int32_t* nstripes,
+                     int32_t* rows_per_stripe);
+int ch_hamming_hist(ch_ws* ws, const ch_hist_args* a, void* stream);
+
+/* slab reductions: totals over stripes -> tot (nbins, nq_pad); exclusive scan over stripes in place */
+int ch_slab_totals(ch_ws* ws, const uint32_t* slab, int nstripes, int nbins, int64_t nq_pad,
+                   uint32_t* tot_dev, void* stream);
+int ch_slab_exscan(ch_ws* ws, uint32_t* slab, int nstripes, int nbins, int64_t nq_pad, void* stream);
+
+/* ---- K3: exact top-R selection ----------------------------------------------------------------
+ * Counting half of `torch.topk` finished: from the per-rank totals (all-gathered over ranks, laid out
+ * (world, nbins, nq_pad)) derive per query
+ *   base0[key][q] = #items with smaller key on all ranks + #items with equal key on lower ranks,
+ *   thresh[q]     = smallest key t with #(key <= t) >= min(rmax, ndb_total)   (if thresh_out != NULL),
+ *   total[q]      = number of counted items over all ranks                     (if total_out != NULL).
+ * Gallery rows are partitioned contiguously in rank order, so (rank, stripe, in-stripe prefix) is the
+ * ascending-global-row-index tie order.
+ */
+int ch_scan_bases(ch_ws* ws, const uint32_t* tot_all_dev, int world, int rank, int nbins,
+                  int64_t nq, int64_t nq_pad, int64_t rmax, uint32_t* base0_dev,
+                  uint32_t* thresh_out_dev, uint32_t* total_out_dev, void* stream);
+
+/* record capacities per (stripe, query) and their offsets.
+ *   source 0: candidates  = sum_{key <= thresh[q]} slab_all[s][key][q]   (un-scanned slab)
+ *   source 1: relevant    = sum_key slab_rel[s][key][q]                  (un-scanned slab)
+ *   source 2: class count = cls_cnt[s][q_ids[q]]                          (single-label fast path)
+ *   min_with_prev != 0 keeps min(existing cap, new cap).
+ */
+int ch_record_caps(ch_ws* ws, int source, const uint32_t* slab_or_cls, const uint32_t* thresh_or_qids,
+                   int nstripes, int nbins_or_nclass, int64_t nq, int64_t nq_pad, int min_with_prev,
+                   uint32_t* cap_dev, void* stream);
+/* off[s][q] = start[q] + sum_{s' < s} cap[s'][q]; start = exclusive scan of per-query totals;
+ * total_host receives the total number of record slots (the call synchronises the stream). */
+int ch_record_offsets(ch_ws* ws, const uint32_t* cap_dev, int nstripes, int64_t nq, int64_t nq_pad,
+                      uint32_t* off_dev, uint64_t* total_host, void* stream);
+/* per-stripe class histogram of single-label gallery ids: cls (nstripes, nclass), zeroed by caller */
+int ch_class_counts(ch_ws* ws, const uint32_t* g_ids, int64_t ndb, int rows_per_stripe, int nclass,
+                    uint32_t* cls_dev, void* stream);
+
+/* ---- K4: label match, precision@k, AP ---------------------------------------------------------
+ * Replaces the per-query numpy loop of the missing calculate_mAP (97 % of its wall time):
+ * `imatch -> cumsum -> Px -> sum(Px * imatch) / sum(imatch)`.  Works on the records of the relevant
+ * retrieved items: rank = base0_all + stripe base + prefix, relrank likewise on the relevant counts.
+ * cols (nq, ncols) fp64 per rank, ncols = 2 * nR + nPR: [sum_i, cnt_i]*nR, hits_k*nPR -- these are
+ * SUMMED over ranks (NCCL all-reduce) before ch_reduce_means.
+ */
+typedef struct ch_final_args {
+  const void*     recs;  const uint32_t* rec_off;  const uint32_t* rec_cnt;
+  const uint32_t* base0_all;   const uint32_t* base0_rel;      /* (nbins, nq_pad) */
+  const uint32_t* sbase_all;   const uint32_t* sbase_rel;      /* scanned slabs (nstripes, nbins, nq_pad) */
+  const uint32_t* first_rel;   /* (nq_pad) 1 if the rank-0 item is relevant (remove_first only) */
+  double*   partial;           /* (nstripes, nq_pad, ncols) scratch */
+  double*   cols;              /* (nq, ncols) out */
+  int64_t nq, nq_pad;
+  int32_t nstripes, nbins, remove_first, nR, nPR;
+  int64_t r_eff[CH_MAX_R];     /* list lengths, already clamped to the (post-removal) gallery size */
+  int64_t pr_k[CH_MAX_PR];
+} ch_final_args;
+int ch_finalize_records(ch_ws* ws, const ch_final_args* a, void* stream);
+/* remove_first_retrieved (test_hashing.py:105-112): first_rel[q] = 1 iff a relevant record has rank 0 */
+int ch_first_relevant(ch_ws* ws, const ch_final_args* a, uint32_t* first_rel_dev, void* stream);
+/* cols (summed over ranks) -> out_host[nR + 2 * nPR] = mAP_i..., recall_k..., precision_k...
+ * total_rel (nq_pad) = relevant items in the whole gallery per query (u32, already global). */
+int ch_reduce_means(ch_ws* ws, const double* cols_dev, const uint32_t* total_rel_dev,
+                    const uint32_t* first_rel_dev, int64_t nq, int nR, int nPR, const int64_t* pr_k,
+                    double* ap_out_dev /* (nR, nq) or NULL */, double* out_host, void* stream);
+
+/* ranked id list from CH_EMIT_CANDIDATES records: ids (nq, R) int64 / keys (nq, R) int32, pre-filled
+ * by the caller (-1); every rank writes only its own rows' slots. */
+int ch_scatter_ranked(ch_ws* ws, const ch_final_args* a, int64_t R, int64_t row_offset,
+                      int64_t* ids_dev, int32_t* keys_dev, void* stream);
+/* AP / hits straight from a ranked id list (one warp per query): the literal
+ * `imatch / cumsum / Px` loop.  labels as ids or masks.  cols layout as above with nR = 1. */
+int ch_ap_from_ranked(ch_ws* ws, const int64_t* ids_dev, int64_t nq, int64_t R,
+                      const uint32_t* q_lab, const uint32_t* g_lab, int label_mode, int mask_words,
+                      int nPR, const int64_t* pr_k, double* cols_dev, void* stream);
+
+/* ---- small / debug ----------------------------------------------------------------------------
+ * dense key matrix (nq, ndb) u16 for parity tests and for get_hamm_dist (trainers/orthohash.py:362,
+ * trainers/dpn.py:30; identity trainers/orthohash.py:263-264). */
+int ch_hamming_matrix(ch_ws* ws, const uint32_t* q_bits, const uint32_t* q_nz, const uint32_t* g_bits,
+                      const uint32_t* g_nz, int64_t nq, int64_t ndb, int nbit, int ternary,
+                      uint16_t* out_dev, void* stream);
+/* integer-pipe micro-benchmark: measured POPC.32 throughput of this GPU (ops / s) */
+int ch_popc_peak(ch_ws* ws, double* popc32_per_s, double* elapsed_ms);
+/* number of kernels this library launched since the workspace was created */
+int64_t ch_launch_count(ch_ws* ws);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONCEPTHASH_B200_H */

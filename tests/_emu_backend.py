@@ -1,0 +1,349 @@
+"""numpy emulation of the CUDA backend's entry points -- TEST INFRASTRUCTURE ONLY.
+
+It mirrors the *semantics* of every C-ABI call (stripes, {all, relevant} slabs, in-stripe stable
+prefixes, 16-byte records, bases, thresholds, capacities, finalisation) on CPU tensors so that
+``concepthash_b200.evaluator`` -- the real orchestration code, including its torch.distributed
+exchanges -- can be exercised without a GPU (single process and gloo world_size 2).  The product never
+imports this module; ``concepthash_b200.hashing`` only ever builds a ``CudaBackend``.
+"""
+import numpy as np
+import torch
+
+CH_LAB_NONE, CH_LAB_ID, CH_LAB_MASK = 0, 1, 2
+CH_EMIT_NONE, CH_EMIT_RELEVANT, CH_EMIT_CANDIDATES = 0, 1, 2
+
+
+def _u32(t):
+    return t.numpy().view(np.uint32)
+
+
+def _unpack(bits_u32, nbit):
+    """(n, words) uint32 -> (n, nbit) {0,1}"""
+    b = np.ascontiguousarray(bits_u32).view(np.uint8)
+    return np.unpackbits(b, axis=1, bitorder="little")[:, :nbit].astype(np.int32)
+
+
+class EmuBackend:
+    name = "emu"
+
+    def __init__(self, rows_per_stripe=64, threads=32):
+        self.rps = rows_per_stripe
+        self.threads = threads
+        self.launches = 0
+
+    # plumbing
+    def zeros(self, shape, dtype):
+        return torch.zeros(shape, dtype=dtype)
+
+    def empty(self, shape, dtype):
+        return torch.zeros(shape, dtype=dtype)
+
+    def full(self, shape, value, dtype):
+        return torch.full(shape, value, dtype=dtype)
+
+    def padded_rows(self, n):
+        return (n + 63) // 64 * 64 + 64
+
+    def code_words(self, nbit):
+        if nbit <= 0 or nbit > 256:
+            return 0
+        return 1 if nbit <= 32 else 2 if nbit <= 64 else 4 if nbit <= 128 else 8
+
+    def launch_count(self):
+        return self.launches
+
+    # K1
+    def pack_sign(self, codes, threshold, flags):
+        n, nbit = codes.shape
+        words = self.code_words(nbit)
+        if words == 0:
+            raise ValueError(f"nbit={nbit} unsupported")
+        x = codes.detach().cpu().clone()
+        if not x.dtype.is_floating_point:
+            x = x.float()
+        if threshold != 0:
+            x[x.abs() < torch.tensor(threshold, dtype=x.dtype)] = 0
+        xn = x.double().numpy()
+        if np.isnan(xn).any():
+            flags[0] |= 2
+        if (xn == 0).any():
+            flags[0] |= 1
+        rows = self.padded_rows(n)
+
+        def pack(mask):
+            full = np.zeros((rows, words * 32), dtype=np.uint8)
+            full[:n, :nbit] = mask
+            return torch.from_numpy(np.packbits(full, axis=1, bitorder="little").view(np.uint32).view(np.int32).copy())
+
+        self.launches += 1
+        return pack(xn > 0), pack(xn != 0)
+
+    def pack_labels(self, labels, nolabel):
+        lab = labels.detach().cpu()
+        n = lab.shape[0]
+        rows = self.padded_rows(n)
+        ids = np.full((rows,), nolabel, dtype=np.uint32)
+        info = np.zeros(4, dtype=np.uint32)
+        self.launches += 1
+        if lab.dim() == 2:
+            ncls = lab.shape[1]
+            lw = max((ncls + 31) // 32, 1)
+            pos = (lab.double().numpy() > 0)
+            full = np.zeros((rows, lw * 32), dtype=np.uint8)
+            full[:n, :ncls] = pos
+            masks = np.packbits(full, axis=1, bitorder="little").view(np.uint32)
+            cnt = pos.sum(1)
+            has = cnt > 0
+            ids[:n][has] = pos[has].argmax(1)
+            info[0] = cnt.max() if n else 0
+            info[1] = (ids[:n][has].max() + 1) if has.any() else 0
+            info[2] = (~has).sum()
+            return (torch.from_numpy(ids.view(np.int32)), torch.from_numpy(masks.view(np.int32).copy()),
+                    torch.from_numpy(info.view(np.int32)))
+        v = lab.double().numpy()
+        ok = v >= 0
+        ids[:n][ok] = v[ok].astype(np.uint32)
+        info[0] = 1 if ok.any() else 0
+        info[1] = (ids[:n][ok].max() + 1) if ok.any() else 0
+        info[2] = (~ok).sum()
+        return torch.from_numpy(ids.view(np.int32)), None, torch.from_numpy(info.view(np.int32))
+
+    # K2
+    def geometry(self, nq, ndb, nbit, ternary, label_mode, lw):
+        nq_pad = (max(nq, 1) + self.threads - 1) // self.threads * self.threads
+        nstripes = max(1, (ndb + self.rps - 1) // self.rps)
+        return self.threads, nq_pad, nstripes, self.rps
+
+    def _keys(self, q_bits, q_nz, g_bits, g_nz, nq, ndb, nbit, ternary):
+        qs, gs = _unpack(_u32(q_bits)[:nq], nbit), _unpack(_u32(g_bits)[:ndb], nbit)
+        if not ternary:
+            return (qs[:, None, :] != gs[None, :, :]).sum(-1)
+        qz, gz = _unpack(_u32(q_nz)[:nq], nbit), _unpack(_u32(g_nz)[:ndb], nbit)
+        both = (qz[:, None, :] & gz[None, :, :])
+        dis = ((qs[:, None, :] != gs[None, :, :]) & (both == 1)).sum(-1)
+        return nbit - both.sum(-1) + 2 * dis
+
+    def _rel(self, q_lab, g_lab, nq, ndb, label_mode, lw):
+        if label_mode == CH_LAB_NONE:
+            return np.zeros((nq, ndb), dtype=bool)
+        if label_mode == CH_LAB_ID:
+            return _u32(q_lab)[:nq, None] == _u32(g_lab)[None, :ndb]
+        qm, gm = _u32(q_lab)[:nq, :lw], _u32(g_lab)[:ndb, :lw]
+        return ((qm[:, None, :] & gm[None, :, :]) != 0).any(-1)
+
+    def hamming_hist(self, *, q_bits, q_nz, g_bits, g_nz, q_lab, g_lab, slab_all, slab_rel, thresh, rec_off,
+                     rec_cap, rec_cnt, recs, err_flag, nq, nq_pad, ndb, nbit, ternary, label_mode, mask_words,
+                     emit_mode, nstripes, threads, rows_per_stripe):
+        self.launches += 1
+        keys = self._keys(q_bits, q_nz, g_bits, g_nz, nq, ndb, nbit, ternary)
+        rel = self._rel(q_lab, g_lab, nq, ndb, label_mode, mask_words)
+        sa = _u32(slab_all)
+        sr = _u32(slab_rel) if slab_rel is not None else None
+        th = _u32(thresh) if thresh is not None else None
+        if emit_mode != CH_EMIT_NONE:
+            off, cap, cnt, rc = _u32(rec_off), _u32(rec_cap), _u32(rec_cnt), _u32(recs)
+        for s in range(nstripes):
+            r0, r1 = s * rows_per_stripe, min(ndb, (s + 1) * rows_per_stripe)
+            for q in range(nq):
+                run_all, run_rel = {}, {}
+                n_rec = 0
+                for j in range(r0, r1):
+                    k = int(keys[q, j])
+                    if th is not None and k > th[q]:
+                        continue
+                    r = bool(rel[q, j])
+                    pa, pr = run_all.get(k, 0), run_rel.get(k, 0)
+                    run_all[k] = pa + 1
+                    if r:
+                        run_rel[k] = pr + 1
+                    if emit_mode == CH_EMIT_CANDIDATES or (emit_mode == CH_EMIT_RELEVANT and r):
+                        if n_rec < cap[s, q]:
+                            rc[off[s, q] + n_rec] = (k | (0x80000000 if r else 0), pa, pr, j)
+                        else:
+                            _u32(err_flag)[0] |= 1
+                        n_rec += 1
+                for k, v in run_all.items():
+                    sa[s, k, q] += v
+                if sr is not None:
+                    for k, v in run_rel.items():
+                        sr[s, k, q] += v
+                if emit_mode != CH_EMIT_NONE:
+                    cnt[s, q] = min(n_rec, cap[s, q])
+
+    def slab_totals(self, slab, nstripes, nbins, nq_pad, out):
+        self.launches += 1
+        _u32(out)[...] = _u32(slab).sum(0, dtype=np.uint32)
+
+    def slab_exscan(self, slab, nstripes, nbins, nq_pad):
+        self.launches += 1
+        s = _u32(slab)
+        c = np.cumsum(s, axis=0, dtype=np.uint32)
+        s[1:] = c[:-1]
+        s[0] = 0
+
+    def class_counts(self, g_ids, ndb, rows_per_stripe, nclass, cls):
+        self.launches += 1
+        ids, c = _u32(g_ids)[:ndb], _u32(cls)
+        for r in range(ndb):
+            if ids[r] < nclass:
+                c[r // rows_per_stripe, ids[r]] += 1
+
+    # K3
+    def scan_bases(self, tot_all, world, rank, nbins, nq, nq_pad, rmax, base0, thresh, total):
+        self.launches += 1
+        t = _u32(tot_all).astype(np.int64).copy()            # (world, nbins, nq_pad)
+        t[:, :, nq:] = 0
+        tot = t.sum(0)
+        lower = t[:rank].sum(0)
+        cum_incl = np.cumsum(tot, axis=0)
+        _u32(base0)[...] = (cum_incl - tot + lower).astype(np.uint32)
+        if thresh is not None:
+            th = np.full(nq_pad, nbins - 1, dtype=np.uint32)
+            if rmax >= 0:
+                for q in range(nq_pad):
+                    hit = np.nonzero(cum_incl[:, q] >= rmax)[0]
+                    if len(hit):
+                        th[q] = hit[0]
+            _u32(thresh)[...] = th
+        if total is not None:
+            _u32(total)[...] = cum_incl[-1].astype(np.uint32)
+
+    def record_caps(self, source, a0, a1, nstripes, nb, nq, nq_pad, min_with_prev, cap):
+        self.launches += 1
+        c = np.zeros((nstripes, nq_pad), dtype=np.uint32)
+        if source in (0, 1):
+            s = _u32(a0)
+            for q in range(nq):
+                last = int(_u32(a1)[q]) if source == 0 else nb - 1
+                c[:, q] = s[:, :min(last, nb - 1) + 1, q].sum(1)
+        else:
+            cls, ids = _u32(a0), _u32(a1)
+            for q in range(nq):
+                if ids[q] < nb:
+                    c[:, q] = cls[:, ids[q]]
+        if min_with_prev:
+            c = np.minimum(c, _u32(cap))
+        _u32(cap)[...] = c
+
+    def record_offsets(self, cap, nstripes, nq, nq_pad, off):
+        self.launches += 1
+        c = _u32(cap).astype(np.int64)
+        rowtot = c.sum(0)
+        start = np.cumsum(rowtot) - rowtot
+        o = start[None, :] + np.cumsum(c, axis=0) - c
+        _u32(off)[...] = o.astype(np.uint32)
+        return int(rowtot.sum())
+
+    # K4
+    def _ranks(self, f, rec, s, q, need_rel):
+        key = int(rec[0] & 0x7FFFFFFF)
+        rank = int(_u32(f["base0_all"])[key, q]) + int(_u32(f["sbase_all"])[s, key, q]) + int(rec[1])
+        relrank = 0
+        if need_rel:
+            relrank = int(_u32(f["base0_rel"])[key, q]) + int(_u32(f["sbase_rel"])[s, key, q]) + int(rec[2])
+        return bool(rec[0] >> 31), rank, relrank
+
+    def finalize_records(self, f):
+        self.launches += 1
+        nq, nstripes = f["nq"], f["nstripes"]
+        r_eff, pr_k = f["r_eff"], f["pr_k"]
+        ncols = 2 * len(r_eff) + len(pr_k)
+        cols = f["cols"].numpy()
+        cols[...] = 0
+        rc, off, cnt = _u32(f["recs"]), _u32(f["rec_off"]), _u32(f["rec_cnt"])
+        rf = f.get("remove_first", False)
+        first = _u32(f["first_rel"]) if (rf and f.get("first_rel") is not None) else None
+        for s in range(nstripes):
+            for q in range(nq):
+                for k in range(cnt[s, q]):
+                    is_rel, rank, relrank = self._ranks(f, rc[off[s, q] + k], s, q, True)
+                    if not is_rel:
+                        continue
+                    if rf:
+                        if rank == 0:
+                            continue
+                        rank -= 1
+                        relrank -= int(first[q]) if first is not None else 0
+                    prec = (relrank + 1) / (rank + 1)
+                    for j, r in enumerate(r_eff):
+                        if rank < r:
+                            cols[q, 2 * j] += prec
+                            cols[q, 2 * j + 1] += 1
+                    for j, kk in enumerate(pr_k):
+                        if rank < kk:
+                            cols[q, 2 * len(r_eff) + j] += 1
+        assert ncols <= cols.shape[1] or ncols == 0
+
+    def first_relevant(self, f, out):
+        self.launches += 1
+        rc, off, cnt = _u32(f["recs"]), _u32(f["rec_off"]), _u32(f["rec_cnt"])
+        o = _u32(out)
+        for s in range(f["nstripes"]):
+            for q in range(f["nq"]):
+                for k in range(cnt[s, q]):
+                    is_rel, rank, _ = self._ranks(f, rc[off[s, q] + k], s, q, False)
+                    if is_rel and rank == 0:
+                        o[q] = 1
+
+    def reduce_means(self, cols, total_rel, first_rel, nq, n_r, pr_k, ap_out=None):
+        self.launches += 1
+        c = cols.numpy()
+        maps, recalls, precisions = [], [], []
+        for j in range(n_r):
+            ap = np.where(c[:, 2 * j + 1] > 0, c[:, 2 * j] / np.maximum(c[:, 2 * j + 1], 1), 0.0)
+            if ap_out is not None:
+                ap_out.numpy()[j] = ap
+            maps.append(float(ap.mean()))
+        for j, k in enumerate(pr_k):
+            hits = c[:, 2 * n_r + j]
+            tr = _u32(total_rel)[:nq].astype(np.float64)
+            if first_rel is not None:
+                tr = tr - _u32(first_rel)[:nq]
+            recalls.append(float((hits / np.maximum(tr, 1.0)).mean()))
+            precisions.append(float((hits / k).mean()))
+        return maps, recalls, precisions
+
+    def scatter_ranked(self, f, R, row_offset, ids, keys):
+        self.launches += 1
+        rc, off, cnt = _u32(f["recs"]), _u32(f["rec_off"]), _u32(f["rec_cnt"])
+        rf = f.get("remove_first", False)
+        for s in range(f["nstripes"]):
+            for q in range(f["nq"]):
+                for k in range(cnt[s, q]):
+                    rec = rc[off[s, q] + k]
+                    _, rank, _ = self._ranks(f, rec, s, q, False)
+                    if rf:
+                        if rank == 0:
+                            continue
+                        rank -= 1
+                    if rank < R:
+                        ids[q, rank] = row_offset + int(rec[3])
+                        keys[q, rank] = int(rec[0] & 0x7FFFFFFF)
+
+    def ap_from_ranked(self, ids, nq, R, q_lab, g_lab, label_mode, mask_words, pr_k, cols):
+        self.launches += 1
+        c = cols.numpy()
+        for q in range(nq):
+            run, s = 0, 0.0
+            hits = [0] * len(pr_k)
+            for k in range(R):
+                j = int(ids[q, k])
+                if j < 0:
+                    continue
+                if label_mode == CH_LAB_ID:
+                    r = _u32(q_lab)[q] == _u32(g_lab)[j]
+                else:
+                    r = bool((_u32(q_lab)[q, :mask_words] & _u32(g_lab)[j, :mask_words]).any())
+                if r:
+                    s += (run + 1) / (k + 1)
+                    run += 1
+                    for i, kk in enumerate(pr_k):
+                        if k < kk:
+                            hits[i] += 1
+            c[q, 0], c[q, 1] = s, run
+            for i in range(len(pr_k)):
+                c[q, 2 + i] = hits[i]
+
+    def hamming_matrix(self, q_bits, q_nz, g_bits, g_nz, nq, ndb, nbit, ternary):
+        self.launches += 1
+        return torch.from_numpy(self._keys(q_bits, q_nz, g_bits, g_nz, nq, ndb, nbit, ternary).astype(np.int16))

@@ -1,0 +1,74 @@
+"""CPU checks of the C-ABI: the library builds for sm_100a, loads, and exports exactly the entry points
+include/concepthash_b200.h declares (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+from concepthash_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "concepthash_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return set(re.findall(r"\b(ch_[a-z0-9_]+)\s*\(", text))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return _lib.load()
+
+
+def test_header_and_binding_agree(lib):
+    declared = header_functions()
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_exported_symbols_match_header(lib):
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\b(ch_[a-z0-9_]+)$", out, flags=re.M))
+    exported = {s for s in exported if not s.startswith("ch_ws_") and s != "ch_set_error"}
+    assert header_functions() <= exported
+
+
+def test_pure_host_entry_points(lib):
+    assert lib.ch_abi_version() == 1
+    assert lib.ch_padded_rows(0) == 64 and lib.ch_padded_rows(1) == 128 and lib.ch_padded_rows(64) == 128
+    assert [lib.ch_code_words(n) for n in (1, 16, 32, 33, 64, 65, 128, 129, 256, 257, 0)] == \
+           [1, 1, 1, 2, 2, 4, 4, 8, 8, 0, 0]
+
+
+def test_struct_layout_matches_c(lib):
+    # sizes as the C compiler lays them out (pointers 8, int64 8, int32 4, natural alignment)
+    assert ctypes.sizeof(_lib.HistArgs) == 14 * 8 + 3 * 8 + 8 * 4
+    assert ctypes.sizeof(_lib.FinalArgs) == 10 * 8 + 2 * 8 + 5 * 4 + 4 + 8 * 8 + 32 * 8
+
+
+def test_sass_is_blackwell_native():
+    out = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert "UBLKCP" in out          # cp.async.bulk (TMA engine) streaming of the gallery tiles
+    assert "POPC" in out
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_fails_loudly_without_gpu():
+    from concepthash_b200 import hashing
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        hashing.calculate_mAP(torch.randn(4, 8), torch.eye(4), torch.randn(2, 8), torch.eye(4)[:2], -1)
+    ws = ctypes.c_void_p()
+    assert lib_call_fails(ws)
+
+
+def lib_call_fails(ws):
+    lib = _lib.load()
+    rc = lib.ch_workspace_create(0, ctypes.byref(ws))
+    return rc != 0 and len(lib.ch_last_error()) > 0

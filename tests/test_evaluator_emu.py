@@ -1,0 +1,125 @@
+"""The real orchestration (concepthash_b200.evaluator) over the numpy emulation of the backend must
+reproduce the oracle: validates the sort-free rank algebra (stripes, bases, thresholds, records,
+remove_first, R lists, P@k / R@k, multi-hot, ternary) on CPU."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from concepthash_b200 import synth
+from concepthash_b200.evaluator import Evaluator
+from oracle import map_oracle as mo
+from tests._emu_backend import EmuBackend
+
+
+def run_case(d, dl, q, ql, R, PRs=(), rf=False, thr=0.0, rps=64):
+    ev = Evaluator(EmuBackend(rows_per_stripe=rps))
+    r_list = R if isinstance(R, list) else [R]
+    maps, rec, prec, ap = ev.evaluate(d, dl, q, ql, r_list, thr, list(PRs), rf, return_ap=True)
+    om, orec, oprec, oaps = mo.calculate_mAP(d, dl, q, ql, R, threshold=thr, PRs=list(PRs),
+                                             remove_first_retrieved=rf, return_per_query=True)
+    om = om if isinstance(om, list) else [om]
+    assert np.allclose(ap.numpy(), oaps, atol=1e-12), ev.stats
+    assert np.allclose(maps, om, atol=1e-12)
+    assert np.allclose(rec, orec, atol=1e-12)
+    assert np.allclose(prec, oprec, atol=1e-12)
+    return ev
+
+
+def test_golden_cases(golden_dir):
+    z = np.load(os.path.join(golden_dir, "oracle_cases.npz"))
+    modes = set()
+    for name in z["names"]:
+        R = z[f"{name}_R"].tolist()
+        R = R if bool(z[f"{name}_R_is_list"]) else R[0]
+        ev = run_case(torch.from_numpy(z[f"{name}_db_codes"]), torch.from_numpy(z[f"{name}_db_labels"]),
+                      torch.from_numpy(z[f"{name}_q_codes"]), torch.from_numpy(z[f"{name}_q_labels"]),
+                      R, z[f"{name}_PRs"].tolist(), bool(z[f"{name}_rf"]), float(z[f"{name}_thr"]))
+        modes.add((ev.stats["mode"], ev.stats["ternary"]))
+    assert ("all", False) in modes and ("topR", False) in modes and ("topR", True) in modes
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_heavy_ties(seed):
+    g = torch.Generator().manual_seed(seed)
+    nbit = [8, 16, 33, 64][seed % 4]
+    nq, ndb, ncls = 17, 150 + 37 * seed, 4
+    d, dl, q, ql, _ = synth.make_random_case(nq, ndb, nbit, ncls, p=0.3, seed=seed)
+    onehot = seed % 2 == 0
+    if onehot:
+        dl, ql = synth.one_hot(dl, ncls), synth.one_hot(ql, ncls)
+    R = [-1, 5, 20, ndb + 10][seed % 4]
+    run_case(d, dl, q, ql, R, PRs=[1, 5, 10], rf=False, rps=32)
+    run_case(d, dl, q, ql, [3, 11, -1], PRs=[2], rf=False, rps=48)
+
+
+def test_remove_first_topr_and_all():
+    d, dl, _, _, _ = synth.make_random_case(5, 120, 16, 3, p=0.3, seed=11)
+    run_case(d, dl, d.clone(), dl.clone(), -1, PRs=[1, 5], rf=True, rps=32)
+    run_case(d, dl, d.clone(), dl.clone(), 7, PRs=[1, 5], rf=True, rps=32)
+    run_case(d, dl, d.clone(), dl.clone(), [2, 9], rf=True, rps=32)
+
+
+def test_multi_hot_labels():
+    g = torch.Generator().manual_seed(3)
+    d, _, q, _, _ = synth.make_random_case(13, 140, 32, 5, p=0.3, seed=5)
+    dl = (torch.rand(140, 40, generator=g) < 0.06).float()      # 40 classes -> 2 mask words
+    ql = (torch.rand(13, 40, generator=g) < 0.08).float()
+    ev = run_case(d, dl, q, ql, -1, PRs=[1, 10], rps=32)
+    assert ev.stats["label_mode"] == 2
+    run_case(d, dl, q, ql, 9, PRs=[1, 10], rps=32)
+
+
+def test_ternary_zero_codes_and_threshold():
+    g = torch.Generator().manual_seed(4)
+    d, dl, q, ql, _ = synth.make_random_case(11, 130, 24, 4, p=0.3, seed=6)
+    d[torch.rand(d.shape, generator=g) < 0.1] = 0
+    q[torch.rand(q.shape, generator=g) < 0.1] = 0
+    ev = run_case(d, dl, q, ql, -1, PRs=[3], rps=32)
+    assert ev.stats["ternary"]
+    run_case(d, dl, q, ql, 10, PRs=[3], thr=0.4, rps=32)
+
+
+def test_all_identical_codes_single_bucket():
+    d = torch.ones(90, 8)
+    q = torch.ones(6, 8)
+    dl = torch.arange(90) % 3
+    ql = torch.arange(6) % 3
+    run_case(d, dl, q, ql, -1, PRs=[1, 4], rps=32)
+    run_case(d, dl, q, ql, 10, PRs=[1, 4], rps=32)
+
+
+def test_queries_without_labels_and_unseen_classes():
+    d, dl, q, ql, _ = synth.make_random_case(9, 100, 16, 4, p=0.3, seed=8)
+    dl2, ql2 = synth.one_hot(dl, 6), synth.one_hot(ql, 6)
+    ql2[0] = 0            # no positive class at all
+    ql2[1] = 0
+    ql2[1, 5] = 1         # class never seen in the gallery
+    run_case(d, dl2, q, ql2, -1, PRs=[1, 5], rps=32)
+    run_case(d, dl2, q, ql2, 12, PRs=[1, 5], rps=32)
+
+
+def test_retrieve_matches_stable_sort():
+    d, _, q, _, _ = synth.make_random_case(14, 170, 16, 4, p=0.3, seed=9)
+    for R, rf in [(25, False), (-1, False), (400, False), (10, True)]:
+        ev = Evaluator(EmuBackend(rows_per_stripe=32))
+        ids, keys, tern = ev.retrieve(d, q, R, 0.0, rf)
+        oids, odist = mo.topk_ids(q, d, R, remove_first_retrieved=rf)
+        assert torch.equal(ids, oids)
+        assert torch.equal(keys.float(), odist)
+
+
+def test_errors():
+    ev = Evaluator(EmuBackend())
+    d, dl, q, ql, _ = synth.make_random_case(4, 40, 16, 3, seed=1)
+    with pytest.raises(ValueError):
+        ev.evaluate(d, dl, q[:, :8], ql, [-1])
+    with pytest.raises(ValueError):
+        ev.evaluate(d, dl[:10], q, ql, [-1])
+    qn = q.clone()
+    qn[0, 0] = float("nan")
+    with pytest.raises(ValueError):
+        ev.evaluate(d, dl, qn, ql, [-1])
+    with pytest.raises(ValueError):
+        ev.evaluate(d, dl, q, ql, [0])

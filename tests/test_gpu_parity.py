@@ -1,0 +1,310 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI, against the CPU oracle and the
+committed golden fixtures.  Bit-exact for packed bits, distances and ranked ids; |mAP delta| <= 1e-9
+here (the north star allows 1e-6)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from concepthash_b200 import synth
+from oracle import map_oracle as mo
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def H():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from concepthash_b200 import hashing
+    hashing.get_evaluator()          # raises if the native library is missing: no fallback
+    return hashing
+
+
+def _unpack(bits, nbit):
+    b = bits.cpu().numpy().view(np.uint32).view(np.uint8)
+    return np.unpackbits(b, axis=1, bitorder="little")[:, :nbit]
+
+
+# ------------------------------------------------------------------ K1: sign + bit-pack
+@pytest.mark.parametrize("nbit", [1, 16, 31, 32, 33, 48, 64, 100, 128, 200, 256])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16, torch.float64])
+def test_pack_sign_bits(H, nbit, dtype):
+    ev = H.get_evaluator()
+    g = torch.Generator().manual_seed(nbit)
+    x = torch.randn(257, nbit, generator=g).to(dtype)
+    x[3, 0] = 0
+    x[200, nbit - 1] = -0.0
+    for src in (x, x.cuda()):
+        flags = ev.b.zeros((1,), torch.int32)
+        bits, nz = ev.b.pack_sign(src, 0.0, flags)
+        s = torch.sign(x.float()).numpy()
+        assert np.array_equal(_unpack(bits, nbit)[:257], (s > 0).astype(np.uint8))
+        assert np.array_equal(_unpack(nz, nbit)[:257], (s != 0).astype(np.uint8))
+        assert int(flags.cpu()[0]) == 1
+        assert int(bits[257:].abs().sum()) == 0 and int(nz[257:].abs().sum()) == 0   # pad rows are zero
+        # padding bits inside the last word are zero too
+        words = bits.shape[1]
+        full = np.unpackbits(bits.cpu().numpy().view(np.uint32).view(np.uint8), axis=1, bitorder="little")
+        assert full[:, nbit:words * 32].sum() == 0
+
+
+def test_pack_sign_strided_threshold_nan(H):
+    ev = H.get_evaluator()
+    g = torch.Generator().manual_seed(0)
+    base = torch.randn(300, 96, generator=g)
+    for view in (base[:, 10:74], base[:, ::2], base[5:205, 3:40], base.t()[:96, :300]):
+        for src in (view, view.cuda()):
+            flags = ev.b.zeros((1,), torch.int32)
+            bits, nz = ev.b.pack_sign(src, 0.5, flags)
+            ref = mo.sign_codes(view, 0.5).numpy()
+            n, nbit = view.shape
+            assert np.array_equal(_unpack(bits, nbit)[:n], (ref > 0).astype(np.uint8))
+            assert np.array_equal(_unpack(nz, nbit)[:n], (ref != 0).astype(np.uint8))
+    bad = base.clone()
+    bad[7, 7] = float("nan")
+    with pytest.raises(ValueError, match="NaN"):
+        H.calculate_mAP(bad, torch.zeros(300, dtype=torch.long), base[:4], torch.zeros(4, dtype=torch.long), -1)
+
+
+def test_pack_sign_large_host_chunks(H):
+    # > one 64 MB staging chunk from host memory: pipelined H2D path
+    ev = H.get_evaluator()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(300_001, 64, generator=g)            # 76.8 MB fp32
+    flags = ev.b.zeros((1,), torch.int32)
+    bits, _ = ev.b.pack_sign(x.pin_memory(), 0.0, flags)
+    bits2, _ = ev.b.pack_sign(x.cuda(), 0.0, flags)
+    assert torch.equal(bits, bits2)
+    assert np.array_equal(_unpack(bits[:300_001], 64), (x.numpy() > 0).astype(np.uint8))
+
+
+@pytest.mark.parametrize("ncls", [1, 5, 32, 33, 200, 555])
+def test_pack_labels(H, ncls):
+    ev = H.get_evaluator()
+    g = torch.Generator().manual_seed(ncls)
+    ids = torch.randint(ncls, (1000,), generator=g)
+    for dtype in (torch.float32, torch.int64, torch.uint8, torch.bool):
+        oh = synth.one_hot(ids, ncls).to(dtype)
+        for src in (oh, oh.cuda()):
+            pid, masks, info = ev.b.pack_labels(src, 0xFFFFFFFF)
+            assert torch.equal(pid[:1000].cpu().long(), ids)
+            assert info.cpu().tolist()[:3] == [1, int(ids.max()) + 1, 0]
+    pid, masks, info = ev.b.pack_labels(ids.cuda(), 0xFFFFFFFE)
+    assert masks is None and torch.equal(pid[:1000].cpu().long(), ids)
+    multi = (torch.rand(1000, ncls, generator=g) < 0.3).float()
+    multi[0] = 0
+    pid, masks, info = ev.b.pack_labels(multi, 0xFFFFFFFF)
+    got = _unpack(masks, ncls)[:1000]
+    assert np.array_equal(got, multi.numpy().astype(np.uint8))
+    assert int(info.cpu()[0]) == int(multi.sum(1).max()) and int(info.cpu()[2]) == int((multi.sum(1) == 0).sum())
+    assert int(pid[0]) == -1
+
+
+# ------------------------------------------------------------------ K2: distances, bit-exact
+@pytest.mark.parametrize("nbit", [8, 16, 32, 40, 64, 96, 128, 160, 256])
+@pytest.mark.parametrize("zeros", [False, True])
+def test_hamming_matrix_bit_exact(H, nbit, zeros):
+    g = torch.Generator().manual_seed(nbit + zeros)
+    q = torch.randn(70, nbit, generator=g)
+    d = torch.randn(333, nbit, generator=g)
+    if zeros:
+        q[torch.rand(q.shape, generator=g) < 0.1] = 0
+        d[torch.rand(d.shape, generator=g) < 0.1] = 0
+    ref = mo.hamming_distance_matrix(mo.sign_codes(q), mo.sign_codes(d))
+    got = H.get_hamm_dist(q.cuda(), d.cuda())
+    assert torch.equal(got.cpu(), ref)
+    assert torch.equal(H.get_hamm_dist(q, d, normalize=True).cpu(), ref / nbit)
+
+
+# ------------------------------------------------------------------ the drop-in call vs golden fixtures
+def _golden(golden_dir):
+    z = np.load(os.path.join(golden_dir, "oracle_cases.npz"))
+    for name in z["names"]:
+        R = z[f"{name}_R"].tolist()
+        yield name, z, (R if bool(z[f"{name}_R_is_list"]) else R[0])
+
+
+@pytest.mark.parametrize("where", ["cpu", "cuda"])
+def test_calculate_map_golden(H, golden_dir, where):
+    for name, z, R in _golden(golden_dir):
+        args = [torch.from_numpy(z[f"{name}_{k}"]).to(where) for k in ("db_codes", "db_labels", "q_codes", "q_labels")]
+        snap = [a.clone() for a in args]
+        m, rec, prec = H.calculate_mAP(*args, R, threshold=float(z[f"{name}_thr"]), PRs=z[f"{name}_PRs"].tolist(),
+                                       remove_first_retrieved=bool(z[f"{name}_rf"]))
+        assert isinstance(m, list) == isinstance(R, list)
+        m = m if isinstance(m, list) else [m]
+        assert all(isinstance(v, float) for v in m + rec + prec)
+        assert np.allclose(m, z[f"{name}_mAP"], atol=TOL), name
+        assert np.allclose(rec, z[f"{name}_recalls"], atol=TOL), name
+        assert np.allclose(prec, z[f"{name}_precisions"], atol=TOL), name
+        for a, b in zip(args, snap):
+            assert torch.equal(a, b)             # inputs are never mutated
+
+
+def test_per_query_ap_golden(H, golden_dir):
+    ev = H.get_evaluator()
+    for name, z, R in _golden(golden_dir):
+        args = [torch.from_numpy(z[f"{name}_{k}"]) for k in ("db_codes", "db_labels", "q_codes", "q_labels")]
+        r_list = R if isinstance(R, list) else [R]
+        _, _, _, ap = ev.evaluate(*args, r_list, float(z[f"{name}_thr"]), z[f"{name}_PRs"].tolist(),
+                                  bool(z[f"{name}_rf"]), return_ap=True)
+        assert np.allclose(ap.cpu().numpy(), z[f"{name}_aps"], atol=TOL), name
+
+
+def test_ranked_ids_golden_bit_exact(H, golden_dir):
+    for name, z, R in _golden(golden_dir):
+        ndb = z[f"{name}_db_codes"].shape[0]
+        r = max(x if x > 0 else ndb for x in R) if isinstance(R, list) else R
+        ids, dist = H.retrieve_topk(torch.from_numpy(z[f"{name}_q_codes"]), torch.from_numpy(z[f"{name}_db_codes"]),
+                                    r, threshold=float(z[f"{name}_thr"]),
+                                    remove_first_retrieved=bool(z[f"{name}_rf"]))
+        assert np.array_equal(ids.cpu().numpy(), z[f"{name}_ids"].astype(np.int64)), name
+        assert np.array_equal((2 * dist).round().cpu().numpy().astype(np.int16), z[f"{name}_dist2"]), name
+
+
+def test_known_answer(H):
+    A, B = [1, 0], [0, 1]
+    q = torch.tensor([[1., 1., 1., 1.]])
+    d = torch.tensor([[1., 1., 1., 1.], [1., 1., 1., -1.], [1., 1., -1., 1.], [-1., -1., -1., -1.], [1., -1., 1., 1.]])
+    ql = torch.tensor([A], dtype=torch.float32)
+    dl = torch.tensor([A, B, A, A, B], dtype=torch.float32)
+    m, rec, prec = H.calculate_mAP(d, dl, q, ql, -1, PRs=[1, 2])
+    assert m == pytest.approx((1 + 2 / 3 + 3 / 5) / 3, abs=1e-15)
+    assert prec == pytest.approx([1.0, 0.5]) and rec == pytest.approx([1 / 3, 1 / 3])
+    m, _, _ = H.calculate_mAP(d, dl, q, ql, [2, 3, -1, 100])
+    assert m == pytest.approx([1.0, (1 + 2 / 3) / 2, (1 + 2 / 3 + 3 / 5) / 3, (1 + 2 / 3 + 3 / 5) / 3])
+    m, rec, prec = H.calculate_mAP(d, dl, q, ql, -1, PRs=[2], remove_first_retrieved=True)
+    assert m == pytest.approx(0.5) and prec == pytest.approx([0.5]) and rec == pytest.approx([0.5])
+    ids, dist = H.retrieve_topk(q, d, -1)
+    assert ids.tolist() == [[0, 1, 2, 4, 3]] and dist.tolist() == [[0., 1., 1., 1., 4.]]
+    assert H.map_at_r(query_codes=q, db_codes=d, query_labels=ql, db_labels=dl, R=-1) == pytest.approx(m * 0 + (1 + 2 / 3 + 3 / 5) / 3)
+    with pytest.raises(NotImplementedError):
+        H.calculate_mAP(d, dl, q, ql, -1, dist_metric="euclidean")
+    with pytest.raises(ValueError):
+        H.calculate_mAP(d, dl, q[:, :3], ql, -1)
+    with pytest.raises(ValueError):
+        H.calculate_mAP(torch.randn(5, 300), dl, torch.randn(1, 300), ql, -1)      # nbit > 256
+
+
+# ------------------------------------------------------------------ randomised parity
+@pytest.mark.parametrize("seed", range(12))
+def test_random_cases_vs_oracle(H, seed):
+    rng = np.random.RandomState(seed)
+    nbit = int(rng.choice([8, 16, 24, 32, 48, 64, 96, 128, 192, 256]))
+    nq, ndb = int(rng.randint(1, 400)), int(rng.randint(1, 3000))
+    ncls = int(rng.choice([2, 7, 40, 300]))
+    d, dl, q, ql, _ = synth.make_random_case(nq, ndb, nbit, ncls, p=float(rng.choice([0.1, 0.3, 0.5])), seed=seed)
+    form = seed % 3
+    if form == 0:
+        dl, ql = synth.one_hot(dl, ncls), synth.one_hot(ql, ncls)
+    elif form == 1:
+        g = torch.Generator().manual_seed(seed)
+        dl = (synth.one_hot(dl, ncls) + (torch.rand(ndb, ncls, generator=g) < 0.02)).clamp(max=1)
+        ql = (synth.one_hot(ql, ncls) + (torch.rand(nq, ncls, generator=g) < 0.02)).clamp(max=1)
+    if seed % 4 == 3:
+        d[:, ::5] = torch.where(torch.rand(d[:, ::5].shape) < 0.3, 0.0, 1.0) * d[:, ::5]
+    R = [-1, 10, 100, 1000, [1, 50, -1]][seed % 5]
+    PRs = [[1, 5, 10], [], [3]][seed % 3]
+    thr = [0.0, 0.0, 0.3][seed % 3]
+    where = "cuda" if seed % 2 else "cpu"
+    m, rec, prec = H.calculate_mAP(d.to(where), dl.to(where), q.to(where), ql.to(where), R, threshold=thr, PRs=PRs)
+    om, orec, oprec = mo.calculate_mAP(d, dl, q, ql, R, threshold=thr, PRs=PRs)
+    assert np.allclose(m, om, atol=TOL) and np.allclose(rec, orec, atol=TOL) and np.allclose(prec, oprec, atol=TOL)
+    r = 64 if not isinstance(R, list) and R > 0 else -1
+    ids, dist = H.retrieve_topk(q.to(where), d.to(where), r, threshold=thr)
+    oids, odist = mo.topk_ids(q, d, r, threshold=thr)
+    assert torch.equal(ids.cpu(), oids) and torch.equal(dist.cpu(), odist)
+
+
+def test_edge_shapes(H):
+    for nq, ndb, nbit in [(1, 1, 8), (1, 3, 64), (300, 2, 16), (2, 255, 32), (2, 256, 32), (2, 257, 32), (5, 1025, 128)]:
+        d, dl, q, ql, _ = synth.make_random_case(nq, ndb, nbit, 3, seed=nq + ndb)
+        for R in (-1, 1, ndb, ndb + 5):
+            m, rec, prec = H.calculate_mAP(d, dl, q, ql, R, PRs=[1, 2])
+            om, orec, oprec = mo.calculate_mAP(d, dl, q, ql, R, PRs=[1, 2])
+            assert np.allclose(m, om, atol=TOL) and np.allclose(rec, orec, atol=TOL) and np.allclose(prec, oprec, atol=TOL)
+    # self-retrieval with the query set as its own gallery (test_as_database, test_hashing.py:105-112)
+    d, dl, _, _, _ = synth.make_random_case(1, 500, 32, 5, seed=3)
+    for R in (-1, 20):
+        m, rec, prec = H.calculate_mAP(d, dl, d, dl, R, PRs=[1, 5], remove_first_retrieved=True)
+        om, orec, oprec = mo.calculate_mAP(d, dl, d, dl, R, PRs=[1, 5], remove_first_retrieved=True)
+        assert np.allclose(m, om, atol=TOL) and np.allclose(rec, orec, atol=TOL) and np.allclose(prec, oprec, atol=TOL)
+
+
+def test_huge_tie_bucket_and_counter_flush(H):
+    """All-identical codes: one bucket holds the whole gallery (> 65535 rows in one stripe), so the
+    16-bit shared-memory counters must be flushed mid-stripe and the prefixes must survive it."""
+    ev = H.get_evaluator()
+    ndb, nq = 150_000, 40
+    d = torch.ones(ndb, 32)
+    q = torch.ones(nq, 32)
+    q[1::2, 0] = -1                      # half the queries at distance 1 from everything
+    g = torch.Generator().manual_seed(0)
+    dl = torch.randint(50, (ndb,), generator=g)
+    ql = torch.randint(50, (nq,), generator=g)
+    ev.stripe_rows_override = 75_008     # 2 stripes of > 65535 rows (multiple of 256)
+    try:
+        for R in (-1, 1000):
+            m, rec, prec = H.calculate_mAP(d, dl, q, ql, R, PRs=[1, 10])
+            # canonical order = gallery order for every query -> closed form via the oracle on labels only
+            rel = (ql[:, None] == dl[None, :]).numpy()
+            L = ndb if R == -1 else R
+            aps = [mo._ap_from_rel(rel[i, :L]) for i in range(nq)]
+            assert abs(m - float(np.mean(aps))) < TOL
+            assert np.allclose(prec, [rel[:, :1].mean(), (rel[:, :10].sum(1) / 10).mean()], atol=TOL)
+        ids, dist = H.retrieve_topk(q, d, 70_000)
+        assert torch.equal(ids.cpu(), torch.arange(70_000).expand(nq, -1))
+        assert torch.equal(dist.cpu(), (torch.arange(nq) % 2).float()[:, None].expand(-1, 70_000))
+    finally:
+        ev.stripe_rows_override = None
+
+
+# ------------------------------------------------------------------ BASELINE configs at full size
+@pytest.mark.parametrize("name,nbit", [("cub200", 64), ("cars196", 16), ("cars196", 32), ("cars196", 64)])
+def test_full_size_configs_vs_oracle(H, name, nbit):
+    d, dl, q, ql, ncls = synth.make_dataset_case(name, nbit=nbit, p=0.15, seed=0)
+    m, rec, prec = H.calculate_mAP(d, synth.one_hot(dl, ncls), q, synth.one_hot(ql, ncls), -1, PRs=[1, 5, 10])
+    om, orec, oprec = mo.calculate_mAP(d, dl, q, ql, -1, PRs=[1, 5, 10])
+    assert abs(m - om) < TOL and np.allclose(rec, orec, atol=TOL) and np.allclose(prec, oprec, atol=TOL)
+    m2, _, _ = H.calculate_mAP(d.cuda(), dl.cuda(), q.cuda(), ql.cuda(), -1)      # 1-D ids, device tensors
+    assert m2 == m
+
+
+def test_nabirds_subset_and_list_path_cross_check(H):
+    """cfg3 (NABirds, 24,633 x 23,929, 555 classes): oracle on a 1,500-query subset; on the full query set the
+    record path must agree with the independent ranked-list path (ch_ap_from_ranked over retrieve_topk)."""
+    d, dl, q, ql, ncls = synth.make_dataset_case("nabirds", nbit=64, p=0.15, seed=0)
+    sub = slice(0, 24633, 17)
+    m, rec, prec = H.calculate_mAP(d, dl, q[sub], ql[sub], -1, PRs=[1, 5, 10])
+    om, orec, oprec = mo.calculate_mAP(d, dl, q[sub], ql[sub], -1, PRs=[1, 5, 10])
+    assert abs(m - om) < TOL and np.allclose(rec, orec, atol=TOL) and np.allclose(prec, oprec, atol=TOL)
+    ev = H.get_evaluator()
+    m_full, _, _, ap = ev.evaluate(d.cuda(), dl.cuda(), q.cuda(), ql.cuda(), [1000], return_ap=True)
+    ids, _ = H.retrieve_topk(q.cuda(), d.cuda(), 1000)
+    _, gi, _ = ev.b.pack_labels(dl.cuda(), 0xFFFFFFFE)[0], None, None
+    qi = ev.b.pack_labels(ql.cuda(), 0xFFFFFFFF)[0]
+    gi = ev.b.pack_labels(dl.cuda(), 0xFFFFFFFE)[0]
+    cols = ev.b.zeros((q.shape[0], 2), torch.float64)
+    ev.b.ap_from_ranked(ids.contiguous(), q.shape[0], 1000, qi, gi, 1, 0, [], cols)
+    ap_list = torch.where(cols[:, 1] > 0, cols[:, 0] / cols[:, 1].clamp(min=1), torch.zeros_like(cols[:, 0]))
+    assert torch.allclose(ap_list, ap[0], atol=1e-12)
+    assert abs(float(ap_list.mean()) - m_full[0]) < 1e-12
+
+
+def test_cfg4_shape_subset_and_idempotence(H):
+    """cfg4 shape (128-bit, 1M gallery, mAP@1000) on a 48-query subset against the oracle, plus
+    run-to-run bit reproducibility."""
+    d, dl, q, ql, ncls = synth.make_random_case(48, 1_000_000, 128, 101, p=0.30, seed=0, device="cuda")
+    m, _, _ = H.calculate_mAP(d, dl, q, ql, 1000)
+    m2, _, _ = H.calculate_mAP(d, dl, q, ql, 1000)
+    assert m == m2
+    ids, dist = H.retrieve_topk(q, d, 1000)
+    dc, qc = d.cpu(), q.cpu()
+    oids, odist = mo.topk_ids(qc, dc, 1000)
+    assert torch.equal(ids.cpu(), oids) and torch.equal(dist.cpu(), odist)
+    rel = (ql.cpu()[:, None] == dl.cpu()[oids]).numpy()
+    om = float(np.mean([mo._ap_from_rel(r) for r in rel]))
+    assert abs(m - om) < TOL

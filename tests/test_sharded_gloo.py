@@ -1,0 +1,77 @@
+"""world_size-2 (gloo, CPU) run of the REAL multi-rank orchestration (evaluator + DistComm) over the numpy
+backend emulation: a row-sharded gallery must give the 1-rank / oracle answers exactly."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from concepthash_b200 import synth
+from concepthash_b200.evaluator import DistComm, Evaluator
+from oracle import map_oracle as mo
+from tests._emu_backend import EmuBackend
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        results = {}
+        for case, (R, PRs, rf, thr, zero) in enumerate([(-1, [1, 5, 10], False, 0.0, False),
+                                                         (15, [1, 5], False, 0.0, False),
+                                                         ([4, 30, -1], [3], False, 0.0, True),
+                                                         (9, [2], True, 0.0, False),
+                                                         (-1, [2], True, 0.3, False)]):
+            d, dl, q, ql, _ = synth.make_random_case(12, 230, 16, 4, p=0.3, seed=20 + case)
+            if rf:
+                q, ql = d[:12].clone(), dl[:12].clone()
+            if zero:
+                d[::7, 3] = 0
+            # uneven contiguous split in rank order
+            cut = [0, 97, 230] if world == 2 else np.linspace(0, 230, world + 1).astype(int).tolist()
+            ds, dls = d[cut[rank]:cut[rank + 1]], dl[cut[rank]:cut[rank + 1]]
+            ev = Evaluator(EmuBackend(rows_per_stripe=32), DistComm())
+            r_list = R if isinstance(R, list) else [R]
+            maps, rec, prec = ev.evaluate(ds, dls, q, ql, r_list, thr, PRs, rf)
+            ids, keys, tern = ev.retrieve(ds, q, 20, thr, rf)
+            results[case] = (maps, rec, prec, ids.clone(), keys.clone(), tern)
+        if rank == 0:
+            torch.save(results, out)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_ranks_match_oracle(tmp_path):
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    results = torch.load(out)
+    for case, (R, PRs, rf, thr, zero) in enumerate([(-1, [1, 5, 10], False, 0.0, False),
+                                                     (15, [1, 5], False, 0.0, False),
+                                                     ([4, 30, -1], [3], False, 0.0, True),
+                                                     (9, [2], True, 0.0, False),
+                                                     (-1, [2], True, 0.3, False)]):
+        d, dl, q, ql, _ = synth.make_random_case(12, 230, 16, 4, p=0.3, seed=20 + case)
+        if rf:
+            q, ql = d[:12].clone(), dl[:12].clone()
+        if zero:
+            d[::7, 3] = 0
+        om, orec, oprec = mo.calculate_mAP(d, dl, q, ql, R, threshold=thr, PRs=PRs, remove_first_retrieved=rf)
+        om = om if isinstance(om, list) else [om]
+        maps, rec, prec, ids, keys, tern = results[case]
+        assert np.allclose(maps, om, atol=1e-12), case
+        assert np.allclose(rec, orec, atol=1e-12), case
+        assert np.allclose(prec, oprec, atol=1e-12), case
+        oids, odist = mo.topk_ids(q, d, 20, threshold=thr, remove_first_retrieved=rf)
+        assert torch.equal(ids, oids), case
+        assert torch.equal(keys.float() * (0.5 if tern else 1.0), odist), case
