@@ -33,6 +33,9 @@ WORKLOADS = {
     "cfg5": dict(nq=100_000, ndb=12_500_000, nbit=64, nclass=1000, R=1000, p=0.30, scaling="weak",
                  desc="BASELINE configs[4] per-GPU shard: 64-bit, 100,000 queries x 12.5M gallery rows per GPU "
                       "(8 GPUs = the 100M gallery), top-R=1000, 1000 classes"),
+    # development-size stand-in for cfg5 (same code path, 1/12.5 of the per-GPU shard)
+    "cfg5s": dict(nq=100_000, ndb=1_000_000, nbit=64, nclass=1000, R=1000, p=0.30, scaling="strong",
+                  desc="cfg5 stand-in: 64-bit, 100,000 queries x 1,000,000 gallery, top-R=1000, 1000 classes"),
     "cub200": dict(dataset="cub200", nbit=64, R=-1, p=0.15, scaling="strong",
                    desc="BASELINE configs[0]: CUB-200-2011 64-bit mAP@all, 5,794 x 5,994, 200 classes"),
     "cars196": dict(dataset="cars196", nbit=64, R=-1, p=0.15, scaling="strong",

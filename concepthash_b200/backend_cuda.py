@@ -26,6 +26,7 @@ class CudaBackend:
     """One instance per process / GPU (owns a ``ch_ws`` workspace)."""
 
     name = "cuda"
+    stripe_align = 256     # stripe boundaries must be multiples of 256 gallery rows
 
     def __init__(self, device=None):
         if not torch.cuda.is_available():

@@ -19,6 +19,8 @@
 // Per pair (64-bit codes): 2 LOP3 + 2 POPC + 1 IADD3 (distance), 1 ISETP + 1 SEL (relevance), 1 IMAD
 // (address), LDS + IADD + STS (histogram) and 1/4 LDS.128 x2 (gallery code + label broadcast).
 // The limiter is the POPC pipe (16 lanes / clk / SM): algorithmic popc32 ops per pair = words.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -38,6 +40,15 @@ struct HistDev {
 
 constexpr int kStages = 2;
 
+// compile-time tile geometry of the code / id stages (static shared memory: the compiler then KNOWS the
+// gallery tiles do not alias the histogram, so tile loads are hoisted above histogram stores)
+template <int NW, bool TERN>
+struct TileCfg {
+  static constexpr int kRows = (NW <= 2 ? 256 : (NW == 4 ? 128 : 64)) / (TERN ? 2 : 1);
+  static constexpr int kGroup = (NW * (TERN ? 2 : 1) >= 8) ? 2 : 4;   // rows per register group
+  static constexpr int kPad = 2 * kGroup;                             // rows the prefetch may over-read
+};
+
 __host__ __device__ inline int tile_rows_for(int nw, bool tern, int label_mode, int lw) {
   int t = nw <= 2 ? 256 : (nw == 4 ? 128 : 64);
   if (tern) t /= 2;
@@ -47,27 +58,28 @@ __host__ __device__ inline int tile_rows_for(int nw, bool tern, int label_mode, 
 }
 
 struct SmemPlan {
-  size_t hist, qmask, stage_bits, stage_nz, stage_lab, stage, bars, total;
+  size_t hist, qmask, stage_mask, total_dynamic, total_static, total;
 };
 
+// dynamic part: histogram, query masks, gallery mask stages (CH_LAB_MASK only);
+// static part: code / non-zero / id stages + barriers (see the kernel)
 inline SmemPlan smem_plan(int nbins, int threads, int nw, bool tern, int label_mode, int lw, int tile) {
   SmemPlan p;
-  p.hist = static_cast<size_t>(nbins) * threads * 4;
-  p.hist = (p.hist + 15) / 16 * 16;
-  p.qmask = label_mode == CH_LAB_MASK ? static_cast<size_t>(lw) * threads * 4 : 0;
-  p.qmask = (p.qmask + 15) / 16 * 16;
-  p.stage_bits = static_cast<size_t>(tile) * nw * 4;
-  p.stage_nz = tern ? p.stage_bits : 0;
-  p.stage_lab = label_mode == CH_LAB_NONE ? 0 : static_cast<size_t>(tile) * (label_mode == CH_LAB_ID ? 1 : lw) * 4;
-  p.stage = p.stage_bits + p.stage_nz + p.stage_lab;
-  p.bars = 16 * kStages;
-  p.total = p.hist + p.qmask + kStages * p.stage + p.bars;
+  p.hist = (static_cast<size_t>(nbins) * threads * 4 + 15) / 16 * 16;
+  p.qmask = label_mode == CH_LAB_MASK ? (static_cast<size_t>(lw) * threads * 4 + 15) / 16 * 16 : 0;
+  p.stage_mask = label_mode == CH_LAB_MASK ? static_cast<size_t>(tile) * lw * 4 : 0;
+  p.total_dynamic = p.hist + p.qmask + kStages * p.stage_mask;
+  const int rows = (nw <= 2 ? 256 : (nw == 4 ? 128 : 64)) / (tern ? 2 : 1);
+  const int pad = 2 * ((nw * (tern ? 2 : 1) >= 8) ? 2 : 4);
+  p.total_static = static_cast<size_t>(kStages) * (rows + pad) * nw * 4 * (tern ? 2 : 1) +
+                   (label_mode == CH_LAB_ID ? static_cast<size_t>(kStages) * (rows + pad) * 4 : 0) + 64;
+  p.total = p.total_dynamic + p.total_static;
   return p;
 }
 
 template <int NW, bool TERN>
 __device__ __forceinline__ uint32_t pair_key(const uint32_t (&qb)[NW], const uint32_t (&qz)[NW],
-                                             const uint32_t (&gb)[NW], const uint32_t (&gz)[NW], int nbit) {
+                                             const uint32_t* gb, const uint32_t* gz, int nbit) {
   if constexpr (!TERN) {
     uint32_t d = 0;
 #pragma unroll
@@ -87,25 +99,57 @@ __device__ __forceinline__ uint32_t pair_key(const uint32_t (&qb)[NW], const uin
   }
 }
 
+// G consecutive gallery rows held in registers
+template <int NW, bool TERN, int LAB, int G>
+struct RowGroup {
+  uint32_t g[G * NW];
+  uint32_t z[TERN ? G * NW : 1];
+  uint32_t lab[LAB == CH_LAB_ID ? G : 1];
+  // i is a multiple of G; G * NW is a multiple of 4 -> all loads are aligned 128-bit broadcasts
+  __device__ __forceinline__ void load(const uint32_t* gb, const uint32_t* gz, const uint32_t* gl, int i) {
+#pragma unroll
+    for (int v = 0; v < G * NW / 4; ++v) {
+      const uint4 x = *reinterpret_cast<const uint4*>(gb + i * NW + 4 * v);
+      g[4 * v] = x.x; g[4 * v + 1] = x.y; g[4 * v + 2] = x.z; g[4 * v + 3] = x.w;
+      if constexpr (TERN) {
+        const uint4 y = *reinterpret_cast<const uint4*>(gz + i * NW + 4 * v);
+        z[4 * v] = y.x; z[4 * v + 1] = y.y; z[4 * v + 2] = y.z; z[4 * v + 3] = y.w;
+      }
+    }
+    if constexpr (LAB == CH_LAB_ID) {
+      if constexpr (G == 4) {
+        const uint4 x = *reinterpret_cast<const uint4*>(gl + i);
+        lab[0] = x.x; lab[1] = x.y; lab[2] = x.z; lab[3] = x.w;
+      } else {
+        const uint2 x = *reinterpret_cast<const uint2*>(gl + i);
+        lab[0] = x.x; lab[1] = x.y;
+      }
+    }
+  }
+};
+
 template <int NW, bool TERN, int LAB, bool THRESH>
 __global__ void __launch_bounds__(256, (NW <= 2 && !TERN) ? 3 : 1) hamming_hist_kernel(const HistDev a) {
+  typedef TileCfg<NW, TERN> Cfg;
+  constexpr int G = Cfg::kGroup;
+  constexpr int kStageRows = Cfg::kRows + Cfg::kPad;
+  // static: gallery code / non-zero / id stages and their barriers
+  __shared__ __align__(16) uint32_t s_bits[kStages][kStageRows * NW];
+  __shared__ __align__(16) uint32_t s_nz[TERN ? kStages : 1][TERN ? kStageRows * NW : 4];
+  __shared__ __align__(16) uint32_t s_ids[LAB == CH_LAB_ID ? kStages : 1][LAB == CH_LAB_ID ? kStageRows : 4];
+  __shared__ __align__(8) uint64_t bars[kStages];
+  // dynamic: histogram [key][thread], query masks, gallery mask stages
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int T = blockDim.x;
   const int tid = threadIdx.x;
-  const int TILE = a.tile_rows;
-  const int lws = LAB == CH_LAB_ID ? 1 : (LAB == CH_LAB_MASK ? a.lw : 0);
-
-  // ---- shared memory carve-up (must match smem_plan) ----
-  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw);
+  const int TILE = a.tile_rows;                      // <= Cfg::kRows (smaller only for wide label masks)
+  unsigned char* hist_b = smem_raw + tid * 4;        // this thread's column, byte-addressed
+  const uint32_t T4 = static_cast<uint32_t>(T) * 4u;
   size_t off = (static_cast<size_t>(a.nbins) * T * 4 + 15) / 16 * 16;
   uint32_t* qmask = reinterpret_cast<uint32_t*>(smem_raw + off);
   if (LAB == CH_LAB_MASK) off += (static_cast<size_t>(a.lw) * T * 4 + 15) / 16 * 16;
-  const size_t stage_bits = static_cast<size_t>(TILE) * NW * 4;
-  const size_t stage_nz = TERN ? stage_bits : 0;
-  const size_t stage_lab = static_cast<size_t>(TILE) * lws * 4;
-  const size_t stage_bytes = stage_bits + stage_nz + stage_lab;
-  unsigned char* stage0 = smem_raw + off;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + kStages * stage_bytes);
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem_raw + off);   // [kStages][TILE * lw]
+  const int lw = LAB == CH_LAB_MASK ? a.lw : 0;
 
   const int qtile = blockIdx.x % a.nqtiles;
   const int stripe = blockIdx.x / a.nqtiles;
@@ -122,15 +166,16 @@ __global__ void __launch_bounds__(256, (NW <= 2 && !TERN) ? 3 : 1) hamming_hist_
   uint32_t qid = CH_QUERY_NOLABEL;
   if (LAB == CH_LAB_ID && active) qid = a.q_lab[q];
   if (LAB == CH_LAB_MASK)
-    for (int w = 0; w < a.lw; ++w) qmask[w * T + tid] = active ? a.q_lab[q * a.lw + w] : 0u;
+    for (int w = 0; w < lw; ++w) qmask[w * T + tid] = active ? a.q_lab[q * lw + w] : 0u;
   uint32_t thr = 0;
   if (THRESH && active) thr = a.thresh[q];
 
-  for (int b = 0; b < a.nbins; ++b) hist[b * T + tid] = 0u;
+  for (int b = 0; b < a.nbins; ++b) *reinterpret_cast<uint32_t*>(hist_b + b * T4) = 0u;
 
   const size_t sq = static_cast<size_t>(stripe) * a.nq_pad + q;  // (stripe, query) slot
   uint32_t rptr = 0, rstart = 0, rend = 0;
-  if (a.emit_mode != CH_EMIT_NONE && active) {
+  const int emit_mode = active ? a.emit_mode : CH_EMIT_NONE;
+  if (emit_mode != CH_EMIT_NONE) {
     rstart = a.rec_off[sq];
     rend = rstart + a.rec_cap[sq];
     rptr = rstart;
@@ -154,22 +199,26 @@ __global__ void __launch_bounds__(256, (NW <= 2 && !TERN) ? 3 : 1) hamming_hist_
     long long rows = row_end - r0;
     if (rows > TILE) rows = TILE;
     const uint32_t rows4 = static_cast<uint32_t>((rows + 3) & ~3ll);  // pad rows exist (ch_padded_rows)
-    unsigned char* dst = stage0 + static_cast<size_t>(k % kStages) * stage_bytes;
-    uint64_t* bar = &bars[k % kStages];
+    const int s = k % kStages;
+    uint64_t* bar = &bars[s];
     const uint32_t bytes_bits = rows4 * NW * 4u;
-    const uint32_t bytes_lab = rows4 * static_cast<uint32_t>(lws) * 4u;
-    mbar_arrive_expect_tx(bar, bytes_bits * (TERN ? 2u : 1u) + bytes_lab);
-    bulk_g2s(dst, a.g_bits + r0 * NW, bytes_bits, bar);
-    if (TERN) bulk_g2s(dst + stage_bits, a.g_nz + r0 * NW, bytes_bits, bar);
-    if (LAB != CH_LAB_NONE) bulk_g2s(dst + stage_bits + stage_nz, a.g_lab + r0 * lws, bytes_lab, bar);
+    const uint32_t bytes_ids = LAB == CH_LAB_ID ? rows4 * 4u : 0u;
+    const uint32_t bytes_mask = rows4 * static_cast<uint32_t>(lw) * 4u;
+    mbar_arrive_expect_tx(bar, bytes_bits * (TERN ? 2u : 1u) + bytes_ids + bytes_mask);
+    bulk_g2s(&s_bits[s][0], a.g_bits + r0 * NW, bytes_bits, bar);
+    if constexpr (TERN) bulk_g2s(&s_nz[s][0], a.g_nz + r0 * NW, bytes_bits, bar);
+    if constexpr (LAB == CH_LAB_ID) bulk_g2s(&s_ids[s][0], a.g_lab + r0, bytes_ids, bar);
+    if constexpr (LAB == CH_LAB_MASK)
+      bulk_g2s(s_mask + static_cast<size_t>(s) * TILE * lw, a.g_lab + r0 * lw, bytes_mask, bar);
   };
 
   uint32_t epoch = 0;  // number of flushes so far (uniform over the CTA)
   auto flush = [&]() {
     for (int b = 0; b < a.nbins; ++b) {
-      const uint32_t v = hist[b * T + tid];
+      uint32_t* h = reinterpret_cast<uint32_t*>(hist_b + b * T4);
+      const uint32_t v = *h;
       if (v != 0u) {
-        hist[b * T + tid] = 0u;
+        *h = 0u;
         if (active) {
           const size_t o = (static_cast<size_t>(stripe) * a.nbins + b) * a.nq_pad + q;
           a.slab_all[o] += v & 0xffffu;
@@ -180,33 +229,71 @@ __global__ void __launch_bounds__(256, (NW <= 2 && !TERN) ? 3 : 1) hamming_hist_
     ++epoch;
   };
 
-  // one (query, gallery row) pair; `glab` = gallery id (CH_LAB_ID), `gmask` = gallery mask row (CH_LAB_MASK)
-  auto visit = [&](uint32_t key, uint32_t glab, const uint32_t* __restrict__ gmask, uint32_t shard_row) {
-    if (THRESH && key > thr) return;
-    bool rel = false;
-    if constexpr (LAB == CH_LAB_ID) rel = glab == qid;
+  // rare path: append one record to this thread's own slice
+  auto emit = [&](uint32_t key, bool rel, uint32_t old, uint32_t shard_row) {
+    uint32_t base_all = 0, base_rel = 0;
+    if (epoch != 0u) {  // counts already flushed to the slab belong to the in-stripe prefix as well
+      const size_t o = (static_cast<size_t>(stripe) * a.nbins + key) * a.nq_pad + q;
+      base_all = a.slab_all[o];
+      if (LAB != CH_LAB_NONE) base_rel = a.slab_rel[o];
+    }
+    if (rptr < rend)
+      a.recs[rptr] = make_uint4(key | (rel ? 0x80000000u : 0u), base_all + (old & 0xffffu), base_rel + (old >> 16),
+                                shard_row);
+    else
+      overflow = true;
+    ++rptr;
+  };
+
+  auto relevant = [&](uint32_t glab, const uint32_t* gmask) -> bool {
+    if constexpr (LAB == CH_LAB_ID) return glab == qid;
     if constexpr (LAB == CH_LAB_MASK) {
       uint32_t any = 0;
-      for (int w = 0; w < a.lw; ++w) any |= qmask[w * T + tid] & gmask[w];
-      rel = any != 0u;
+      for (int w = 0; w < lw; ++w) any |= qmask[w * T + tid] & gmask[w];
+      return any != 0u;
     }
-    const uint32_t idx = key * T + tid;
-    const uint32_t old = hist[idx];
-    hist[idx] = old + (rel ? 0x10001u : 1u);
-    if (a.emit_mode == CH_EMIT_CANDIDATES || (a.emit_mode == CH_EMIT_RELEVANT && rel)) {
-      if (active) {
-        uint32_t base_all = 0, base_rel = 0;
-        if (epoch != 0u) {  // counts already flushed to the slab belong to the prefix as well
-          const size_t o = (static_cast<size_t>(stripe) * a.nbins + key) * a.nq_pad + q;
-          base_all = a.slab_all[o];
-          if (LAB != CH_LAB_NONE) base_rel = a.slab_rel[o];
-        }
-        if (rptr < rend)
-          a.recs[rptr] = make_uint4(key | (rel ? 0x80000000u : 0u), base_all + (old & 0xffffu),
-                                    base_rel + (old >> 16), shard_row);
-        else
-          overflow = true;
-        ++rptr;
+    return false;
+  };
+
+  // N consecutive rows starting at tile row i
+  auto process = [&](const uint32_t* g, const uint32_t* z, const uint32_t* lab, const uint32_t* gmask_tile, int i,
+                     uint32_t shard_row, auto n_tag) {
+    constexpr int N = decltype(n_tag)::value;
+    uint32_t key[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) key[j] = pair_key<NW, TERN>(qb, qz, g + j * NW, z + (TERN ? j * NW : 0), a.nbit);
+    if constexpr (!THRESH) {
+      uint32_t old[N];
+      bool rel[N];
+      bool any = emit_mode == CH_EMIT_CANDIDATES;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        rel[j] = relevant(LAB == CH_LAB_ID ? lab[j] : 0u, gmask_tile + static_cast<size_t>(i + j) * lw);
+        uint32_t* h = reinterpret_cast<uint32_t*>(hist_b + key[j] * T4);
+        old[j] = *h;
+        *h = old[j] + (rel[j] ? 0x10001u : 1u);
+        any |= rel[j];
+      }
+      if (emit_mode != CH_EMIT_NONE && any) {
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+          if (emit_mode == CH_EMIT_CANDIDATES || rel[j]) emit(key[j], rel[j], old[j], shard_row + j);
+      }
+    } else {
+      bool any = false;
+#pragma unroll
+      for (int j = 0; j < N; ++j) any |= key[j] <= thr;
+      if (any) {  // candidates are rare: everything below is off the hot path
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+          if (key[j] <= thr) {
+            const bool rel = relevant(LAB == CH_LAB_ID ? lab[j] : 0u, gmask_tile + static_cast<size_t>(i + j) * lw);
+            uint32_t* h = reinterpret_cast<uint32_t*>(hist_b + key[j] * T4);
+            const uint32_t old = *h;
+            *h = old + (rel ? 0x10001u : 1u);
+            if (emit_mode == CH_EMIT_CANDIDATES || (emit_mode == CH_EMIT_RELEVANT && rel))
+              emit(key[j], rel, old, shard_row + j);
+          }
       }
     }
   };
@@ -214,81 +301,38 @@ __global__ void __launch_bounds__(256, (NW <= 2 && !TERN) ? 3 : 1) hamming_hist_
   if (ntiles > 0 && tid == 0) issue(0);
   for (int k = 0; k < ntiles; ++k) {
     if (tid == 0 && k + 1 < ntiles) issue(k + 1);  // slot (k+1)%2 was released by the barrier ending tile k-1
-    mbar_wait(&bars[k % kStages], static_cast<uint32_t>((k / kStages) & 1));
+    const int s = k % kStages;
+    mbar_wait(&bars[s], static_cast<uint32_t>((k / kStages) & 1));
 
-    const unsigned char* st = stage0 + static_cast<size_t>(k % kStages) * stage_bytes;
-    const uint32_t* gb = reinterpret_cast<const uint32_t*>(st);
-    const uint32_t* gz = reinterpret_cast<const uint32_t*>(st + stage_bits);
-    const uint32_t* gl = reinterpret_cast<const uint32_t*>(st + stage_bits + stage_nz);
+    const uint32_t* gb = &s_bits[s][0];
+    const uint32_t* gz = TERN ? &s_nz[s][0] : &s_nz[0][0];
+    const uint32_t* gl = LAB == CH_LAB_ID ? &s_ids[s][0] : &s_ids[0][0];
+    const uint32_t* gm = s_mask + static_cast<size_t>(s) * TILE * lw;
     long long rows_ll = row_end - (row_begin + static_cast<long long>(k) * TILE);
     const int rows = rows_ll > TILE ? TILE : static_cast<int>(rows_ll);
-
     const uint32_t shard_row0 = static_cast<uint32_t>(row_begin) + static_cast<uint32_t>(k) * TILE;
+
+    // register double-buffered walk over groups of G rows (prefetch may over-read into the kPad rows)
+    const int nfull = rows - rows % G;
+    RowGroup<NW, TERN, LAB, G> A, B;
     int i = 0;
-    if constexpr (NW <= 2) {
-      // groups of 4 rows: 128-bit broadcast loads of codes (and ids)
-      for (; i + 4 <= rows; i += 4) {
-        uint32_t g[4][NW], z[4][NW];
-        if constexpr (NW == 1) {
-          const uint4 v = *reinterpret_cast<const uint4*>(gb + i);
-          g[0][0] = v.x; g[1][0] = v.y; g[2][0] = v.z; g[3][0] = v.w;
-          if constexpr (TERN) {
-            const uint4 u = *reinterpret_cast<const uint4*>(gz + i);
-            z[0][0] = u.x; z[1][0] = u.y; z[2][0] = u.z; z[3][0] = u.w;
-          }
-        } else {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const uint4 v = *reinterpret_cast<const uint4*>(gb + (i + 2 * h) * 2);
-            g[2 * h][0] = v.x; g[2 * h][1] = v.y; g[2 * h + 1][0] = v.z; g[2 * h + 1][1] = v.w;
-            if constexpr (TERN) {
-              const uint4 u = *reinterpret_cast<const uint4*>(gz + (i + 2 * h) * 2);
-              z[2 * h][0] = u.x; z[2 * h][1] = u.y; z[2 * h + 1][0] = u.z; z[2 * h + 1][1] = u.w;
-            }
-          }
-        }
-        uint32_t lab4[4] = {0u, 0u, 0u, 0u};
-        if constexpr (LAB == CH_LAB_ID) {
-          const uint4 v = *reinterpret_cast<const uint4*>(gl + i);
-          lab4[0] = v.x; lab4[1] = v.y; lab4[2] = v.z; lab4[3] = v.w;
-        }
-        uint32_t key[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if constexpr (TERN) key[j] = pair_key<NW, TERN>(qb, qz, g[j], z[j], a.nbit);
-          else key[j] = pair_key<NW, TERN>(qb, qz, g[j], g[j], a.nbit);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          visit(key[j], lab4[j], gl + static_cast<size_t>(i + j) * lws, shard_row0 + i + j);
-      }
+    if (nfull > 0) A.load(gb, gz, gl, 0);
+    for (; i < nfull; i += 2 * G) {
+      B.load(gb, gz, gl, i + G);
+      process(A.g, A.z, A.lab, gm, i, shard_row0 + i, std::integral_constant<int, G>());
+      A.load(gb, gz, gl, i + 2 * G);
+      if (i + G < nfull) process(B.g, B.z, B.lab, gm, i + G, shard_row0 + i + G, std::integral_constant<int, G>());
     }
-    // wide codes, and the tail rows of the last tile: one row at a time
-    for (; i < rows; ++i) {
-      uint32_t g1[NW], z1[NW];
-      if constexpr (NW >= 4) {
+    // tail rows of the stripe's last tile
+    for (i = nfull; i < rows; ++i) {
+      uint32_t g1[NW], z1[TERN ? NW : 1], lab1[1] = {0u};
 #pragma unroll
-        for (int w4 = 0; w4 < NW / 4; ++w4) {
-          const uint4 v = *reinterpret_cast<const uint4*>(gb + i * NW + w4 * 4);
-          g1[w4 * 4 + 0] = v.x; g1[w4 * 4 + 1] = v.y; g1[w4 * 4 + 2] = v.z; g1[w4 * 4 + 3] = v.w;
-          if constexpr (TERN) {
-            const uint4 u = *reinterpret_cast<const uint4*>(gz + i * NW + w4 * 4);
-            z1[w4 * 4 + 0] = u.x; z1[w4 * 4 + 1] = u.y; z1[w4 * 4 + 2] = u.z; z1[w4 * 4 + 3] = u.w;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int w = 0; w < NW; ++w) {
-          g1[w] = gb[i * NW + w];
-          if constexpr (TERN) z1[w] = gz[i * NW + w];
-        }
+      for (int w = 0; w < NW; ++w) {
+        g1[w] = gb[i * NW + w];
+        if constexpr (TERN) z1[w] = gz[i * NW + w];
       }
-      uint32_t key;
-      if constexpr (TERN) key = pair_key<NW, TERN>(qb, qz, g1, z1, a.nbit);
-      else key = pair_key<NW, TERN>(qb, qz, g1, g1, a.nbit);
-      uint32_t lab1 = 0u;
-      if constexpr (LAB == CH_LAB_ID) lab1 = gl[i];
-      visit(key, lab1, gl + static_cast<size_t>(i) * lws, shard_row0 + i);
+      if constexpr (LAB == CH_LAB_ID) lab1[0] = gl[i];
+      process(g1, z1, lab1, gm, i, shard_row0 + i, std::integral_constant<int, 1>());
     }
     __syncthreads();  // everyone is done with this stage before it is refilled
     if ((k + 1) % a.flush_tiles == 0 && k + 1 < ntiles) flush();
@@ -370,7 +414,7 @@ int pick_threads(int nbins, long long nq) {
 struct Geometry {
   int threads, nstripes, rows_per_stripe, tile, flush_tiles, nqtiles;
   long long nq_pad;
-  size_t smem;
+  size_t smem, smem_total;
 };
 
 int make_geometry(ch_ws* ws, long long nq, long long ndb, int nbit, bool tern, int lab, int lw, int forced_threads,
@@ -381,7 +425,8 @@ int make_geometry(ch_ws* ws, long long nq, long long ndb, int nbit, bool tern, i
   g->threads = forced_threads > 0 ? forced_threads : pick_threads(nbins, nq);
   g->tile = tile_rows_for(nw, tern, lab, lw);
   const SmemPlan p = smem_plan(nbins, g->threads, nw, tern, lab, lw, g->tile);
-  g->smem = p.total;
+  g->smem = p.total_dynamic;
+  g->smem_total = p.total;
   if (p.total > static_cast<size_t>(ws->max_smem_optin))
     CH_FAIL("histogram needs %zu bytes of shared memory per CTA (nbit=%d ternary=%d classes/32=%d), device has %d",
             p.total, nbit, tern ? 1 : 0, lw, ws->max_smem_optin);
@@ -398,7 +443,7 @@ int make_geometry(ch_ws* ws, long long nq, long long ndb, int nbit, bool tern, i
     return 0;
   } else {
     // resident CTAs per SM by shared memory (1 KB reserved per CTA) and threads
-    long long per_sm = (228ll * 1024) / static_cast<long long>(p.total + 1024);
+    long long per_sm = (228ll * 1024) / static_cast<long long>(p.total + 1024);  // static + dynamic
     if (per_sm > 2048 / g->threads) per_sm = 2048 / g->threads;
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 32) per_sm = 32;

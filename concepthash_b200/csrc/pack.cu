@@ -87,15 +87,16 @@ __global__ void __launch_bounds__(256) pack_bits_kernel(const T* __restrict__ sr
   uint32_t fl = 0;
   for (int64_t u0 = unit_begin + warp * 32; u0 < unit_end; u0 += nwarps * 32) {
     uint32_t my_pos = 0, my_nz = 0;
+    // (row, word) of the first unit: one division per 32 units, then incremental
+    int64_t r = u0 / words;
+    int w = static_cast<int>(u0 - r * words);
+    const T* rowp = src + (r - row0) * rs;
 #pragma unroll 8
     for (int u = 0; u < 32; ++u) {
-      const int64_t unit = u0 + u;
-      const int64_t r = unit / words;
-      const int w = static_cast<int>(unit - r * words);
       const int col = w * 32 + lane;
       bool pos = false, nzb = false;
-      if (unit < unit_end && r < n && col < ncols) {
-        C x = Elem<T>::load(src + (r - row0) * rs + static_cast<int64_t>(col) * cs);
+      if (r < n && col < ncols) {   // units past unit_end have r >= rows_pad > n
+        C x = Elem<T>::load(rowp + static_cast<int64_t>(col) * cs);
         if (x != x) fl |= 2u;
         if (has_thr && (x < C(0) ? -x : x) < cthr) x = C(0);
         pos = x > C(0);
@@ -107,6 +108,11 @@ __global__ void __launch_bounds__(256) pack_bits_kernel(const T* __restrict__ sr
       if (lane == u) {
         my_pos = bp;
         my_nz = bn;
+      }
+      if (++w == words) {
+        w = 0;
+        ++r;
+        rowp += rs;
       }
     }
     const int64_t mine = u0 + lane;

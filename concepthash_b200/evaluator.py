@@ -73,6 +73,9 @@ class Evaluator:
         self.comm = comm if comm is not None else LocalComm()
         self.stats = {}
         self.stripe_rows_override = None   # tests: force the stripe length (multiple of 256 on CUDA)
+        self.sample_stride = 16            # top-R: 1-in-16 row sample picks the threshold (0/1 = exact two-pass)
+        self.sample_min_rows = 200_000     # below this the two-pass path is cheap anyway
+        self.sample_min_ratio = 64         # ... and the sample must still hold ~R/stride*... rows: need ndb >= ratio * R
         self.profile = False               # bench: bracket the kernels with CUDA events on the launch stream
         self.events = []                   # (kind, work units, start event, end event)
 
@@ -198,78 +201,34 @@ class Evaluator:
         list_len = max(ndb_total - rf, 0)
         r_eff = [list_len if r == -1 else min(r, list_len) for r in r_list]
         rmax = max(r_eff + [min(k, list_len) for k in pr_k] + [0])
-        geo = b.geometry(nq, g.n, nbit, ternary, label_mode, lw)
-        geo = self._agree_geometry(geo, g.n)
+        full_ranking = rmax * 4 >= list_len          # top-R close to "all": one pass is cheaper than two
+        cls_ok = label_mode == L.CH_LAB_ID and 0 < nclass <= (1 << 20)
+        sampled = (not full_ranking and self.sample_stride > 1 and cls_ok and
+                   ndb_total >= self.sample_min_rows and rmax * self.sample_min_ratio <= ndb_total)
+        geo = self._agree_geometry(b.geometry(nq, g.n, nbit, ternary, label_mode, lw), g.n,
+                                   self.sample_stride if sampled else 1)
         threads, nq_pad, nstripes, rps = geo
         self.stats.update(dict(ternary=ternary, label_mode=label_mode, geometry=geo, nbins=nbins,
                                ndb_total=ndb_total, world=comm.world))
-
-        slab_all = b.zeros((nstripes, nbins, nq_pad), torch.int32)
-        slab_rel = b.zeros((nstripes, nbins, nq_pad), torch.int32)
-        base0_all = b.empty((nbins, nq_pad), torch.int32)
-        base0_rel = b.empty((nbins, nq_pad), torch.int32)
-        total_rel = b.zeros((nq_pad,), torch.int32)
-
-        full_ranking = rmax * 4 >= list_len          # top-R close to "all": one pass is cheaper than two
-        self.stats["mode"] = "all" if full_ranking else "topR"
+        ctx = dict(q=q, g=g, geo=geo, ternary=ternary, label_mode=label_mode, lw=lw, nclass=nclass, nq=nq,
+                   nbins=nbins, rmax=rmax, rf=rf, pr_k=pr_k, ndb_total=ndb_total)
+        st = None
         if full_ranking:
-            # ---- single pass: count every pair, record every relevant pair ----
-            cap = b.empty((nstripes, nq_pad), torch.int32)
-            if label_mode == L.CH_LAB_ID and 0 < nclass * nstripes <= (1 << 26):
-                cls = b.zeros((nstripes, nclass), torch.int32)
-                b.class_counts(g.ids, g.n, rps, nclass, cls)
-                b.record_caps(2, cls, q.ids, nstripes, nclass, nq, nq_pad, False, cap)
-            else:
-                # capacities from a counting pass (multi-hot labels, or too many classes for the table)
-                self._hist(q, g, geo, ternary, label_mode, lw, slab_all, slab_rel)
-                b.record_caps(1, slab_rel, None, nstripes, nbins, nq, nq_pad, False, cap)
-                slab_all.zero_()
-                slab_rel.zero_()
-            rec = self._alloc_records(cap, geo, nq)
-            self._hist(q, g, geo, ternary, label_mode, lw, slab_all, slab_rel, emit=L.CH_EMIT_RELEVANT, rec=rec)
-            tot = comm.all_gather(torch.stack([self._local_totals(slab_all, geo, nbins),
-                                               self._local_totals(slab_rel, geo, nbins)]))
-            b.scan_bases(tot[:, 0].contiguous(), comm.world, comm.rank, nbins, nq, nq_pad, -1, base0_all, None, None)
-            b.scan_bases(tot[:, 1].contiguous(), comm.world, comm.rank, nbins, nq, nq_pad, -1, base0_rel, None,
-                         total_rel)
-            b.slab_exscan(slab_all, nstripes, nbins, nq_pad)
-            b.slab_exscan(slab_rel, nstripes, nbins, nq_pad)
-            sbase_all, sbase_rel = slab_all, slab_rel
+            self.stats["mode"] = "all"
+            st = self._pass_all(ctx)
         else:
-            # ---- pass 1: key histogram of every pair -> per-query threshold key ----
-            need_total_rel = len(pr_k) > 0
-            lm1 = label_mode if need_total_rel else L.CH_LAB_NONE
-            self._hist(q, g, geo, ternary, lm1, lw, slab_all, slab_rel)
-            thresh = b.empty((nq_pad,), torch.int32)
-            tot_a = comm.all_gather(self._local_totals(slab_all, geo, nbins))
-            b.scan_bases(tot_a, comm.world, comm.rank, nbins, nq, nq_pad, rmax + rf, base0_all, thresh, None)
-            if need_total_rel:
-                tot_r = comm.all_gather(self._local_totals(slab_rel, geo, nbins))
-                b.scan_bases(tot_r, comm.world, comm.rank, nbins, nq, nq_pad, -1, base0_rel, None, total_rel)
-            cap = b.empty((nstripes, nq_pad), torch.int32)
-            b.record_caps(0, slab_all, thresh, nstripes, nbins, nq, nq_pad, False, cap)
-            if label_mode == L.CH_LAB_ID and 0 < nclass * nstripes <= (1 << 26):
-                cls = b.zeros((nstripes, nclass), torch.int32)
-                b.class_counts(g.ids, g.n, rps, nclass, cls)
-                b.record_caps(2, cls, q.ids, nstripes, nclass, nq, nq_pad, True, cap)
-            b.slab_exscan(slab_all, nstripes, nbins, nq_pad)
-            sbase_all = slab_all
-            rec = self._alloc_records(cap, geo, nq)
-            # ---- pass 2: only pairs with key <= threshold are counted / matched / recorded ----
-            scratch_all = b.zeros((nstripes, nbins, nq_pad), torch.int32)
-            slab_rel.zero_()
-            self._hist(q, g, geo, ternary, label_mode, lw, scratch_all, slab_rel, thresh=thresh,
-                       emit=L.CH_EMIT_RELEVANT, rec=rec)
-            del scratch_all
-            tot_r2 = comm.all_gather(self._local_totals(slab_rel, geo, nbins))
-            b.scan_bases(tot_r2, comm.world, comm.rank, nbins, nq, nq_pad, -1, base0_rel, None, None)
-            b.slab_exscan(slab_rel, nstripes, nbins, nq_pad)
-            sbase_rel = slab_rel
+            if sampled:
+                self.stats["mode"] = "topR-sampled"
+                st = self._pass_topr_sampled(ctx)
+            if st is None:
+                self.stats["mode"] = "topR"
+                st = self._pass_topr_exact(ctx)
+        rec = st["rec"]
 
         ncols = 2 * len(r_eff) + len(pr_k)
         cols = b.zeros((nq, max(ncols, 1)), torch.float64)
-        f = dict(recs=rec["recs"], rec_off=rec["off"], rec_cnt=rec["cnt"], base0_all=base0_all, base0_rel=base0_rel,
-                 sbase_all=sbase_all, sbase_rel=sbase_rel, first_rel=None,
+        f = dict(recs=rec["recs"], rec_off=rec["off"], rec_cnt=rec["cnt"], base0_all=st["base0_all"],
+                 base0_rel=st["base0_rel"], sbase_all=st["sbase_all"], sbase_rel=st["sbase_rel"], first_rel=None,
                  partial=b.empty((nstripes, nq_pad, max(ncols, 1)), torch.float64), cols=cols,
                  nq=nq, nq_pad=nq_pad, nstripes=nstripes, nbins=nbins, remove_first=bool(rf), r_eff=r_eff, pr_k=pr_k)
         first_rel = None
@@ -279,15 +238,164 @@ class Evaluator:
             first_rel = comm.all_reduce_max(first_rel)
             f["first_rel"] = first_rel
         b.finalize_records(f)
-        self._check_records(rec)
-        self.stats["records"] = None
+        if not st.get("rec_checked"):
+            self._check_records(rec)
         cols = comm.all_reduce_sum(cols)
         ap = b.empty((len(r_eff), nq), torch.float64) if return_ap else None
-        maps, recalls, precisions = b.reduce_means(cols, total_rel if pr_k else None, first_rel, nq, len(r_eff), pr_k,
-                                                   ap)
+        maps, recalls, precisions = b.reduce_means(cols, st["total_rel"] if pr_k else None, first_rel, nq, len(r_eff),
+                                                   pr_k, ap)
         if return_ap:
             return maps, recalls, precisions, ap
         return maps, recalls, precisions
+
+    def _class_counts(self, ctx):
+        """(nstripes, nclass) per-stripe class histogram of the single-label gallery shard."""
+        threads, nq_pad, nstripes, rps = ctx["geo"]
+        cls = self.b.zeros((nstripes, ctx["nclass"]), torch.int32)
+        self.b.class_counts(ctx["g"].ids, ctx["g"].n, rps, ctx["nclass"], cls)
+        return cls
+
+    def _pass_all(self, c):
+        """Full ranking: ONE pass counts every pair and records every relevant pair."""
+        b, comm, q, g, geo = self.b, self.comm, c["q"], c["g"], c["geo"]
+        threads, nq_pad, nstripes, rps = geo
+        nbins, nq, label_mode, lw, ternary = c["nbins"], c["nq"], c["label_mode"], c["lw"], c["ternary"]
+        slab_all = b.zeros((nstripes, nbins, nq_pad), torch.int32)
+        slab_rel = b.zeros((nstripes, nbins, nq_pad), torch.int32)
+        base0_all = b.empty((nbins, nq_pad), torch.int32)
+        base0_rel = b.empty((nbins, nq_pad), torch.int32)
+        total_rel = b.zeros((nq_pad,), torch.int32)
+        cap = b.empty((nstripes, nq_pad), torch.int32)
+        if label_mode == L.CH_LAB_ID and 0 < c["nclass"] * nstripes <= (1 << 26):
+            b.record_caps(2, self._class_counts(c), q.ids, nstripes, c["nclass"], nq, nq_pad, False, cap)
+        else:
+            # capacities from a counting pass (multi-hot labels, or too many classes for the table)
+            self._hist(q, g, geo, ternary, label_mode, lw, slab_all, slab_rel)
+            b.record_caps(1, slab_rel, None, nstripes, nbins, nq, nq_pad, False, cap)
+            slab_all.zero_()
+            slab_rel.zero_()
+        rec = self._alloc_records(cap, geo, nq)
+        self._hist(q, g, geo, ternary, label_mode, lw, slab_all, slab_rel, emit=L.CH_EMIT_RELEVANT, rec=rec)
+        tot = comm.all_gather(torch.stack([self._local_totals(slab_all, geo, nbins),
+                                           self._local_totals(slab_rel, geo, nbins)]))
+        b.scan_bases(tot[:, 0].contiguous(), comm.world, comm.rank, nbins, nq, nq_pad, -1, base0_all, None, None)
+        b.scan_bases(tot[:, 1].contiguous(), comm.world, comm.rank, nbins, nq, nq_pad, -1, base0_rel, None, total_rel)
+        b.slab_exscan(slab_all, nstripes, nbins, nq_pad)
+        b.slab_exscan(slab_rel, nstripes, nbins, nq_pad)
+        return dict(rec=rec, base0_all=base0_all, base0_rel=base0_rel, sbase_all=slab_all, sbase_rel=slab_rel,
+                    total_rel=total_rel)
+
+    def _pass_topr_exact(self, c):
+        """Exact two-pass top-R: pass 1 counts every pair (-> per-query threshold key), pass 2 re-streams
+        and only counts / matches / records the pairs with key <= threshold."""
+        b, comm, q, g, geo = self.b, self.comm, c["q"], c["g"], c["geo"]
+        threads, nq_pad, nstripes, rps = geo
+        nbins, nq, label_mode, lw, ternary = c["nbins"], c["nq"], c["label_mode"], c["lw"], c["ternary"]
+        slab_all = b.zeros((nstripes, nbins, nq_pad), torch.int32)
+        slab_rel = b.zeros((nstripes, nbins, nq_pad), torch.int32)
+        base0_all = b.empty((nbins, nq_pad), torch.int32)
+        base0_rel = b.empty((nbins, nq_pad), torch.int32)
+        total_rel = b.zeros((nq_pad,), torch.int32)
+        need_total_rel = len(c["pr_k"]) > 0
+        lm1 = label_mode if need_total_rel else L.CH_LAB_NONE
+        self._hist(q, g, geo, ternary, lm1, lw, slab_all, slab_rel)
+        thresh = b.empty((nq_pad,), torch.int32)
+        tot_a = comm.all_gather(self._local_totals(slab_all, geo, nbins))
+        b.scan_bases(tot_a, comm.world, comm.rank, nbins, nq, nq_pad, c["rmax"] + c["rf"], base0_all, thresh, None)
+        if need_total_rel:
+            tot_r = comm.all_gather(self._local_totals(slab_rel, geo, nbins))
+            b.scan_bases(tot_r, comm.world, comm.rank, nbins, nq, nq_pad, -1, base0_rel, None, total_rel)
+        cap = b.empty((nstripes, nq_pad), torch.int32)
+        b.record_caps(0, slab_all, thresh, nstripes, nbins, nq, nq_pad, False, cap)
+        if label_mode == L.CH_LAB_ID and 0 < c["nclass"] * nstripes <= (1 << 26):
+            b.record_caps(2, self._class_counts(c), q.ids, nstripes, c["nclass"], nq, nq_pad, True, cap)
+        b.slab_exscan(slab_all, nstripes, nbins, nq_pad)
+        rec = self._alloc_records(cap, geo, nq)
+        scratch_all = b.zeros((nstripes, nbins, nq_pad), torch.int32)
+        slab_rel.zero_()
+        self._hist(q, g, geo, ternary, label_mode, lw, scratch_all, slab_rel, thresh=thresh,
+                   emit=L.CH_EMIT_RELEVANT, rec=rec)
+        del scratch_all
+        tot_r2 = comm.all_gather(self._local_totals(slab_rel, geo, nbins))
+        b.scan_bases(tot_r2, comm.world, comm.rank, nbins, nq, nq_pad, -1, base0_rel, None, None)
+        b.slab_exscan(slab_rel, nstripes, nbins, nq_pad)
+        return dict(rec=rec, base0_all=base0_all, base0_rel=base0_rel, sbase_all=slab_all, sbase_rel=slab_rel,
+                    total_rel=total_rel)
+
+    def _pass_topr_sampled(self, c):
+        """Top-R in ONE full pass.  A 1-in-``sample_stride`` row sample of the gallery is histogrammed first; from
+        it a per-query threshold key t^ is chosen high enough that #(key <= t^) >= R with overwhelming
+        probability.  The full pass then counts / matches / records only the pairs with key <= t^.  The result
+        is EXACT whenever the full pass confirms #(key <= t^) >= R for every query and no record slice
+        overflowed -- which it checks; otherwise ``None`` is returned and the exact two-pass path runs."""
+        b, comm, q, g, geo = self.b, self.comm, c["q"], c["g"], c["geo"]
+        threads, nq_pad, nstripes, rps = geo
+        nbins, nq, label_mode, lw, ternary = c["nbins"], c["nq"], c["label_mode"], c["lw"], c["ternary"]
+        stride = self.sample_stride
+        need = min(c["rmax"] + c["rf"], c["ndb_total"])
+        # ---- the sample: every stride-th row of the local shard, same stripes (rps is a multiple of stride) ----
+        ns = (g.n + stride - 1) // stride
+        sp = Packed()
+        sp.n, sp.nbit = ns, g.nbit
+        sp.bits = b.zeros((b.padded_rows(ns), g.bits.shape[1]), torch.int32)
+        sp.bits[:ns] = g.bits[:g.n][::stride]
+        sp.nz = None
+        if ternary:
+            sp.nz = b.zeros((b.padded_rows(ns), g.bits.shape[1]), torch.int32)
+            sp.nz[:ns] = g.nz[:g.n][::stride]
+        sp.ids = sp.masks = sp.info = None
+        geo_s = (threads, nq_pad, nstripes, rps // stride)
+        slab_s = b.zeros((nstripes, nbins, nq_pad), torch.int32)
+        self._hist(q, sp, geo_s, ternary, L.CH_LAB_NONE, 0, slab_s, None)
+        ns_all = b.zeros((1,), torch.int64)
+        ns_all[0] = ns
+        ns_total = int(comm.all_reduce_sum(ns_all).cpu()[0]) if comm.world > 1 else ns
+        mu = need * ns_total / max(c["ndb_total"], 1)
+        m = int(mu + 5.0 * mu ** 0.5 + 4.0) + 1
+        thresh = b.empty((nq_pad,), torch.int32)
+        base_tmp = b.empty((nbins, nq_pad), torch.int32)
+        tot_s = comm.all_gather(self._local_totals(slab_s, geo_s, nbins))
+        b.scan_bases(tot_s, comm.world, comm.rank, nbins, nq, nq_pad, m, base_tmp, thresh, None)
+        # ---- record capacities: scaled sample candidate counts, never more than the class counts ----
+        cap = b.empty((nstripes, nq_pad), torch.int32)
+        b.record_caps(0, slab_s, thresh, nstripes, nbins, nq, nq_pad, False, cap)
+        cap.mul_(2 * stride).add_(64)
+        cls = self._class_counts(c)
+        b.record_caps(2, cls, q.ids, nstripes, c["nclass"], nq, nq_pad, True, cap)
+        rec = self._alloc_records(cap, geo, nq)
+        del slab_s, base_tmp
+        # ---- the one full pass ----
+        slab_all = b.zeros((nstripes, nbins, nq_pad), torch.int32)
+        slab_rel = b.zeros((nstripes, nbins, nq_pad), torch.int32)
+        self._hist(q, g, geo, ternary, label_mode, lw, slab_all, slab_rel, thresh=thresh,
+                   emit=L.CH_EMIT_RELEVANT, rec=rec)
+        base0_all = b.empty((nbins, nq_pad), torch.int32)
+        base0_rel = b.empty((nbins, nq_pad), torch.int32)
+        found = b.zeros((nq_pad,), torch.int32)
+        tot = comm.all_gather(torch.stack([self._local_totals(slab_all, geo, nbins),
+                                           self._local_totals(slab_rel, geo, nbins)]))
+        b.scan_bases(tot[:, 0].contiguous(), comm.world, comm.rank, nbins, nq, nq_pad, -1, base0_all, None, found)
+        b.scan_bases(tot[:, 1].contiguous(), comm.world, comm.rank, nbins, nq, nq_pad, -1, base0_rel, None, None)
+        # ---- verification (one flag, agreed over ranks) ----
+        bad = b.zeros((1,), torch.int32)
+        bad[0] = (found[:nq] < need).any().to(torch.int32) | (rec["err"][0] != 0).to(torch.int32)
+        bad = comm.all_reduce_max(bad) if comm.world > 1 else bad
+        self.stats["sample"] = dict(stride=stride, rows=ns_total, m=m)
+        if int(bad.cpu()[0]) != 0:
+            self.stats["sample"]["fallback"] = True
+            return None
+        b.slab_exscan(slab_all, nstripes, nbins, nq_pad)
+        b.slab_exscan(slab_rel, nstripes, nbins, nq_pad)
+        total_rel = b.zeros((nq_pad,), torch.int32)
+        if c["pr_k"]:
+            # relevant items in the whole gallery = class frequency of the query's class
+            cls_tot = cls.sum(0, dtype=torch.int32)
+            cls_tot = comm.all_reduce_sum(cls_tot) if comm.world > 1 else cls_tot
+            qid = q.ids[:nq].to(torch.int64)
+            ok = (qid >= 0) & (qid < c["nclass"])
+            total_rel[:nq] = torch.where(ok, cls_tot[qid.clamp(0, c["nclass"] - 1)], torch.zeros_like(cls_tot[:1]))
+        return dict(rec=rec, base0_all=base0_all, base0_rel=base0_rel, sbase_all=slab_all, sbase_rel=slab_rel,
+                    total_rel=total_rel, rec_checked=True)
 
     def _local_totals(self, slab, geo, nbins):
         threads, nq_pad, nstripes, rps = geo
@@ -295,14 +403,19 @@ class Evaluator:
         self.b.slab_totals(slab, nstripes, nbins, nq_pad, tot)
         return tot
 
-    def _agree_geometry(self, geo, ndb=None):
+    def _agree_geometry(self, geo, ndb=None, stride=1):
         """threads / nq_pad depend only on (nq, nbins) and are identical on all ranks; the stripe layout is
-        per rank (shards may differ in length), so nothing has to be exchanged."""
+        per rank (shards may differ in length), so nothing has to be exchanged.  With row sampling the stripe
+        length is rounded up so that the sample of a stripe is itself a legal stripe."""
+        threads, nq_pad, nstripes, rps = geo
         if self.stripe_rows_override and ndb is not None:
-            threads, nq_pad, _, _ = geo
             rps = int(self.stripe_rows_override)
-            return threads, nq_pad, max(1, (ndb + rps - 1) // rps), rps
-        return geo
+        if stride > 1:
+            unit = stride * getattr(self.b, "stripe_align", 256)
+            rps = (rps + unit - 1) // unit * unit
+        if ndb is not None:
+            nstripes = max(1, (ndb + rps - 1) // rps)
+        return threads, nq_pad, nstripes, rps
 
     # ------------------------------------------------------------------ ranked retrieval
     def retrieve(self, db_codes, q_codes, R, threshold=0.0, remove_first_retrieved=False):

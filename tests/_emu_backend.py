@@ -25,6 +25,7 @@ def _unpack(bits_u32, nbit):
 
 class EmuBackend:
     name = "emu"
+    stripe_align = 1
 
     def __init__(self, rows_per_stripe=64, threads=32):
         self.rps = rows_per_stripe

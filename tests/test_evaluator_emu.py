@@ -13,8 +13,12 @@ from oracle import map_oracle as mo
 from tests._emu_backend import EmuBackend
 
 
-def run_case(d, dl, q, ql, R, PRs=(), rf=False, thr=0.0, rps=64):
+def run_case(d, dl, q, ql, R, PRs=(), rf=False, thr=0.0, rps=64, sampled=False):
     ev = Evaluator(EmuBackend(rows_per_stripe=rps))
+    if sampled:
+        ev.sample_stride, ev.sample_min_rows, ev.sample_min_ratio = 4, 0, 4
+    else:
+        ev.sample_stride = 0
     r_list = R if isinstance(R, list) else [R]
     maps, rec, prec, ap = ev.evaluate(d, dl, q, ql, r_list, thr, list(PRs), rf, return_ap=True)
     om, orec, oprec, oaps = mo.calculate_mAP(d, dl, q, ql, R, threshold=thr, PRs=list(PRs),
@@ -123,3 +127,34 @@ def test_errors():
         ev.evaluate(d, dl, qn, ql, [-1])
     with pytest.raises(ValueError):
         ev.evaluate(d, dl, q, ql, [0])
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_sampled_single_pass_topr(seed):
+    """Threshold from a 1-in-4 row sample + one full pass: exact whenever it verifies, else falls back."""
+    nbit = [16, 32, 64, 24][seed]
+    d, dl, q, ql, _ = synth.make_random_case(9, 900 + 50 * seed, nbit, 5, p=0.3, seed=40 + seed)
+    if seed == 3:
+        d[::9, 1] = 0                                     # ternary keys
+    ev = run_case(d, dl, q, ql, 20, PRs=[1, 5, 10], rps=64, sampled=True)
+    assert ev.stats["mode"] == "topR-sampled", ev.stats
+    ev = run_case(d, dl, q, ql, [5, 40], PRs=[], rf=(seed == 1), rps=128, sampled=True)
+    assert ev.stats["mode"] in ("topR-sampled", "topR")
+
+
+def test_sampled_falls_back_on_adversarial_order():
+    """35 near rows sit exactly on the sampled positions (every 4th row), everything else is far: the sample
+    over-represents them 4x, the sample threshold is too low, and the verification must catch it and fall
+    back to the exact two-pass path."""
+    nbit = 16
+    q = torch.ones(3, nbit)
+    d = -torch.ones(800, nbit)                            # distance 16
+    d[0:140:4] = 1.0
+    d[0:140:4, 0] = -1.0                                  # 35 rows at distance 1, all on sampled positions
+    dl = torch.arange(800) % 2
+    ql = torch.tensor([0, 1, 0])
+    ev = run_case(d, dl, q, ql, 40, PRs=[1, 5], rps=64, sampled=True)
+    assert ev.stats["mode"] == "topR" and ev.stats["sample"]["fallback"]
+    # benign order: verifies and stays in the one-pass mode
+    ev = run_case(d, dl, q, ql, 30, PRs=[1, 5], rps=64, sampled=True)
+    assert ev.stats["mode"] == "topR-sampled"

@@ -309,3 +309,34 @@ def test_cfg4_shape_subset_and_idempotence(H):
     rel = (ql.cpu()[:, None] == dl.cpu()[oids]).numpy()
     om = float(np.mean([mo._ap_from_rel(r) for r in rel]))
     assert abs(m - om) < TOL
+
+
+def test_sampled_one_pass_equals_exact_two_pass(H):
+    """Top-R with the sample-derived threshold (one full pass) must be bit-identical to the exact two-pass
+    path, and must fall back when the gallery order defeats the sample."""
+    ev = H.get_evaluator()
+    d, dl, q, ql, ncls = synth.make_random_case(3000, 300_000, 64, 50, p=0.30, seed=5, device="cuda")
+    res = {}
+    for stride in (16, 0):
+        ev.sample_stride = stride
+        try:
+            res[stride] = ev.evaluate(d, dl, q, ql, [100, 1000], 0.0, [1, 5, 10], False, return_ap=True)
+            mode = ev.stats["mode"]
+        finally:
+            ev.sample_stride = 16
+        assert mode == ("topR-sampled" if stride else "topR")
+    assert res[16][0] == res[0][0] and res[16][1] == res[0][1] and res[16][2] == res[0][2]
+    assert torch.equal(res[16][3], res[0][3])
+    # adversarial: the 1-in-16 sample sees only near duplicates, the rest of the gallery is far away
+    n = 400_000
+    dd = -torch.ones(n, 32, device="cuda")
+    dd[0:16 * 900:16] = 1.0                     # 900 near rows, all on sampled positions
+    qq = torch.ones(64, 32, device="cuda")
+    ll = torch.arange(n, device="cuda") % 7
+    ql2 = torch.arange(64, device="cuda") % 7
+    m, rec, prec = H.calculate_mAP(dd, ll, qq, ql2, 1000, PRs=[1, 10])
+    assert ev.stats["mode"] == "topR" and ev.stats["sample"]["fallback"]
+    rel = (ql2[:, None] == ll[None, :]).cpu().numpy()
+    order = np.concatenate([np.arange(0, 16 * 900, 16), np.setdiff1d(np.arange(n), np.arange(0, 16 * 900, 16))])[:1000]
+    aps = [mo._ap_from_rel(rel[i, order]) for i in range(64)]
+    assert abs(m - float(np.mean(aps))) < TOL
