@@ -253,15 +253,20 @@ def main():
     words32 = max(1, (w["nbit"] + 31) // 32)
     popc_peak, _ = ev.b.popc_peak()
     peaks, peak_src = measured_peaks()
-    hist_kind = "hist_count" if "hist_count" in kinds else "hist_count_rec"
+    # the dominant kernel = the histogram pass with the largest share of the step
+    hist_kind = max((k for k in kinds if k.startswith("hist")), key=lambda k: kinds[k][0])
     hk = kinds[hist_kind]
     hist_ms = hk[0] / hk[2]
     hist_popc = (hk[1] / hk[2]) * words32 / (hist_ms * 1e-3)
     sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+    pass_name = {"hist_count": "count pass: every pair histogrammed",
+                 "hist_count_rec": "count pass + records of relevant pairs (full ranking)",
+                 "hist_select": "select pass: pairs with key <= threshold counted / matched / recorded"}[hist_kind]
     roofline = {
-        "kernel": "hamming_hist_kernel (count pass)", "bound": "int-pipe (POPC)",
+        "kernel": f"hamming_hist_kernel ({pass_name})", "bound": "int-pipe (POPC)",
         "achieved": hist_popc / 1e9, "peak": popc_peak / 1e9, "unit": "Gpopc32/s",
         "frac": hist_popc / popc_peak, "traffic": None,
+        "algorithmic_work": f"nq x ndb_local pairs x {words32} popc32 per pair per launch",
         "peak_source": "ch_popc_peak micro-benchmark run live on this GPU (MEASURED_PEAKS.json has no integer-pipe "
                        "figure); nominal 148 SM x 16 lanes x f",
         "nominal_peak_at_sampled_clock": 148 * 16 * sm_mhz * 1e6 / 1e9,

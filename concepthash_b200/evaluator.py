@@ -359,7 +359,10 @@ class Evaluator:
         # ---- record capacities: scaled sample candidate counts, never more than the class counts ----
         cap = b.empty((nstripes, nq_pad), torch.int32)
         b.record_caps(0, slab_s, thresh, nstripes, nbins, nq, nq_pad, False, cap)
-        cap.mul_(2 * stride).add_(64)
+        # k sampled candidates in a stripe -> at most ~stride * (k + 6 sqrt(k + 1) + 10) real ones (Poisson tail);
+        # an overflow is detected by the kernel and sends the evaluation to the exact path
+        kf = cap.to(torch.float32)
+        cap.copy_(((kf + 6.0 * torch.sqrt(kf + 1.0) + 10.0) * float(stride)).to(torch.int32))
         cls = self._class_counts(c)
         b.record_caps(2, cls, q.ids, nstripes, c["nclass"], nq, nq_pad, True, cap)
         rec = self._alloc_records(cap, geo, nq)
@@ -377,11 +380,13 @@ class Evaluator:
         b.scan_bases(tot[:, 0].contiguous(), comm.world, comm.rank, nbins, nq, nq_pad, -1, base0_all, None, found)
         b.scan_bases(tot[:, 1].contiguous(), comm.world, comm.rank, nbins, nq, nq_pad, -1, base0_rel, None, None)
         # ---- verification (one flag, agreed over ranks) ----
-        bad = b.zeros((1,), torch.int32)
-        bad[0] = (found[:nq] < need).any().to(torch.int32) | (rec["err"][0] != 0).to(torch.int32)
+        bad = b.zeros((2,), torch.int32)
+        bad[0] = (found[:nq] < need).any().to(torch.int32)      # the sample threshold was too low for a query
+        bad[1] = (rec["err"][0] != 0).to(torch.int32)           # a record slice overflowed
         bad = comm.all_reduce_max(bad) if comm.world > 1 else bad
-        self.stats["sample"] = dict(stride=stride, rows=ns_total, m=m)
-        if int(bad.cpu()[0]) != 0:
+        bad = _as_int_list(bad)
+        self.stats["sample"] = dict(stride=stride, rows=ns_total, m=m, short=bad[0], overflow=bad[1])
+        if bad[0] or bad[1]:
             self.stats["sample"]["fallback"] = True
             return None
         b.slab_exscan(slab_all, nstripes, nbins, nq_pad)
