@@ -90,8 +90,10 @@ class CudaBackend:
             t = t.contiguous()
         return t, L.CH_MEM_HOST
 
-    def pack_sign(self, codes, threshold, flags):
-        """codes (n, nbit) real -> (bits, nz) u32 (rows_pad, words); ``flags`` u32[1] is OR-ed."""
+    def pack_sign(self, codes, threshold, flags, want_nz=True):
+        """codes (n, nbit) real -> (bits, nz) u32 (rows_pad, words); ``flags`` u32[1] is OR-ed.
+        ``want_nz=False`` skips the non-zero plane (zeros are still detected in ``flags``) and lets
+        contiguous inputs take the flat fast path."""
         n, nbit = codes.shape
         words = self.code_words(nbit)
         if words == 0:
@@ -101,7 +103,7 @@ class CudaBackend:
         t, mem = self._src(codes)
         rows = self.padded_rows(n)
         bits = self.empty((rows, words), torch.int32)
-        nz = self.empty((rows, words), torch.int32)
+        nz = self.empty((rows, words), torch.int32) if want_nz else None
         thr = float(threshold)
         if thr != 0.0:   # torch compares `codes.abs() < threshold` in the dtype of codes
             thr = float(torch.tensor(thr, dtype=t.dtype))

@@ -125,6 +125,37 @@ __global__ void __launch_bounds__(256) pack_bits_kernel(const T* __restrict__ sr
   if (lane == 0 && fl != 0 && flags != nullptr) atomicOr(flags, fl);
 }
 
+// Fast path of K1: contiguous (n, nbit) codes with nbit in {32, 64, 128, 256}, no threshold, no non-zero plane.
+// The tensor is then a flat stream of 128-byte units (32 elements -> one output word); a warp turns 32
+// consecutive units into one coalesced 128-byte store with 32 fully unrolled, independent, coalesced loads in
+// flight per thread (4 KB per warp).  Zeros / NaNs are only DETECTED here (flags); if a zero shows up the
+// caller re-packs with the general kernel to obtain the non-zero plane.
+template <typename T>
+__global__ void __launch_bounds__(256) pack_sign_flat_kernel(const T* __restrict__ src, int64_t nblocks32,
+                                                             uint32_t* __restrict__ out_pos,
+                                                             uint32_t* __restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  uint32_t fl = 0;
+  for (int64_t blk = warp; blk < nblocks32; blk += nwarps) {
+    const T* p = src + blk * 1024 + lane;
+    float x[32];
+#pragma unroll
+    for (int u = 0; u < 32; ++u) x[u] = static_cast<float>(Elem<T>::load(p + u * 32));
+    uint32_t mine = 0;
+#pragma unroll
+    for (int u = 0; u < 32; ++u) {
+      const uint32_t b = __ballot_sync(0xffffffffu, x[u] > 0.0f);
+      if (!(fabsf(x[u]) > 0.0f)) fl |= (x[u] != x[u]) ? 2u : 1u;   // zero or NaN: rare
+      if (lane == u) mine = b;
+    }
+    out_pos[blk * 32 + lane] = mine;
+  }
+  fl = __reduce_or_sync(0xffffffffu, fl);
+  if (lane == 0 && fl != 0) atomicOr(flags, fl);
+}
+
 // per-row summary of a label bitmask: id of the first positive (or nolabel), statistics
 __global__ void label_rows_kernel(const uint32_t* __restrict__ masks, int64_t n, int64_t rows_pad, int words,
                                   uint32_t nolabel, uint32_t* __restrict__ ids, uint32_t* __restrict__ info) {
@@ -285,8 +316,31 @@ extern "C" int ch_pack_sign(ch_ws* ws, const void* codes, int mem, int dtype, in
   if (mem == CH_MEM_HOST)
     return pack_from_host(ws, codes, dtype, n, nbit, row_stride, col_stride, threshold, words, rows_pad,
                           out_bits_dev, out_nz_dev, flags_dev, st);
-  return launch_pack(ws, codes, dtype, 0, rows_pad, n, nbit, row_stride, col_stride, threshold, words, out_bits_dev,
-                     out_nz_dev, flags_dev, st);
+  // flat fast path (see pack_sign_flat_kernel); the rows it does not cover go through the general kernel
+  int64_t row0 = 0;
+  const bool flat = out_nz_dev == nullptr && threshold == 0.0 && (col_stride == 1 || nbit == 1) &&
+                    (row_stride == nbit || n <= 1) && nbit == words * 32 && flags_dev != nullptr &&
+                    (dtype == CH_F32 || dtype == CH_F16 || dtype == CH_BF16) &&
+                    (reinterpret_cast<uintptr_t>(codes) & 3) == 0;
+  if (flat && n >= 32) {
+    row0 = n / 32 * 32;                                   // row0 * words is a multiple of 32 units
+    const int64_t nblocks32 = row0 * words / 32;
+    int64_t blocks = (nblocks32 + 7) / 8;
+    const int64_t cap = static_cast<int64_t>(ws->sm_count) * 8;
+    if (blocks > cap) blocks = cap;
+    const dim3 grid(static_cast<unsigned>(blocks)), block(256);
+    if (dtype == CH_F32)
+      pack_sign_flat_kernel<float><<<grid, block, 0, st>>>(static_cast<const float*>(codes), nblocks32, out_bits_dev, flags_dev);
+    else if (dtype == CH_F16)
+      pack_sign_flat_kernel<__half><<<grid, block, 0, st>>>(static_cast<const __half*>(codes), nblocks32, out_bits_dev, flags_dev);
+    else
+      pack_sign_flat_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(static_cast<const __nv_bfloat16*>(codes), nblocks32, out_bits_dev, flags_dev);
+    CH_LAUNCH_CHECK(ws);
+  }
+  const size_t es = dtype == CH_F32 ? 4 : (dtype == CH_F64 ? 8 : 2);
+  return launch_pack(ws, static_cast<const char*>(codes) + static_cast<size_t>(row0) * row_stride * es, dtype, row0,
+                     rows_pad, n, nbit, row_stride, col_stride, threshold, words, out_bits_dev, out_nz_dev, flags_dev,
+                     st);
 }
 
 extern "C" int ch_pack_labels(ch_ws* ws, const void* labels, int mem, int dtype, int64_t n, int C,

@@ -90,13 +90,13 @@ class Evaluator:
         return out
 
     # ------------------------------------------------------------------ packing
-    def _pack_side(self, codes, labels, threshold, flags, nolabel):
+    def _pack_side(self, codes, labels, threshold, flags, nolabel, want_nz=False):
         p = Packed()
         p.n, p.nbit = int(codes.shape[0]), int(codes.shape[1])
         # algorithmic bytes of K1: the real-valued codes read once + the packed bits written once
         pack_bytes = p.n * p.nbit * codes.element_size() + p.n * p.nbit // 8
         kind = "pack_dev" if codes.is_cuda else "pack_host"
-        p.bits, p.nz = self._timed(kind, pack_bytes, lambda: self.b.pack_sign(codes, threshold, flags))
+        p.bits, p.nz = self._timed(kind, pack_bytes, lambda: self.b.pack_sign(codes, threshold, flags, want_nz))
         p.ids = p.masks = p.info = None
         p.ncls = 0
         if labels is not None:
@@ -136,6 +136,10 @@ class Evaluator:
         if m[3]:
             raise ValueError("codes contain NaN")
         ternary = bool(m[0])
+        if ternary:
+            # rare: some sign is exactly 0 -> pack again, this time with the non-zero bit-plane
+            _, q.nz = self.b.pack_sign(q_codes, threshold, flags, True)
+            _, g.nz = self.b.pack_sign(db_codes, threshold, flags, True)
         label_mode, lw, nclass = L.CH_LAB_NONE, 0, 0
         if q_labels is not None:
             if m[1] <= 1:
@@ -467,8 +471,8 @@ class Evaluator:
     def hamming_matrix(self, a_codes, b_codes, threshold=0.0):
         """Dense key matrix (na, nb) int16 and the ternary flag (local, no collectives)."""
         flags = self.b.zeros((1,), torch.int32)
-        pa = self._pack_side(a_codes, None, threshold, flags, 0)
-        pb = self._pack_side(b_codes, None, 0.0, flags, 0)
+        pa = self._pack_side(a_codes, None, threshold, flags, 0, want_nz=True)
+        pb = self._pack_side(b_codes, None, 0.0, flags, 0, want_nz=True)
         fl = int(flags.cpu()[0])
         if fl & 2:
             raise ValueError("codes contain NaN")

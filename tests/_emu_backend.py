@@ -54,7 +54,7 @@ class EmuBackend:
         return self.launches
 
     # K1
-    def pack_sign(self, codes, threshold, flags):
+    def pack_sign(self, codes, threshold, flags, want_nz=True):
         n, nbit = codes.shape
         words = self.code_words(nbit)
         if words == 0:
@@ -77,7 +77,7 @@ class EmuBackend:
             return torch.from_numpy(np.packbits(full, axis=1, bitorder="little").view(np.uint32).view(np.int32).copy())
 
         self.launches += 1
-        return pack(xn > 0), pack(xn != 0)
+        return pack(xn > 0), (pack(xn != 0) if want_nz else None)
 
     def pack_labels(self, labels, nolabel):
         lab = labels.detach().cpu()

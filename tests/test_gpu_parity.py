@@ -340,3 +340,21 @@ def test_sampled_one_pass_equals_exact_two_pass(H):
     order = np.concatenate([np.arange(0, 16 * 900, 16), np.setdiff1d(np.arange(n), np.arange(0, 16 * 900, 16))])[:1000]
     aps = [mo._ap_from_rel(rel[i, order]) for i in range(64)]
     assert abs(m - float(np.mean(aps))) < TOL
+
+
+@pytest.mark.parametrize("nbit", [32, 64, 128, 256])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_pack_sign_flat_fast_path(H, nbit, dtype):
+    """Contiguous device codes without a non-zero plane take pack_sign_flat_kernel: same bits as the general
+    kernel, zeros / NaNs still reported in the flags, pad rows zero."""
+    ev = H.get_evaluator()
+    g = torch.Generator().manual_seed(nbit)
+    for n in (31, 32, 1000, 4099):
+        x = torch.randn(n, nbit, generator=g).to(dtype).cuda()
+        f1, f2 = ev.b.zeros((1,), torch.int32), ev.b.zeros((1,), torch.int32)
+        fast, none = ev.b.pack_sign(x, 0.0, f1, want_nz=False)
+        slow, _ = ev.b.pack_sign(x, 0.0, f2, want_nz=True)
+        assert none is None and torch.equal(fast, slow) and int(f1.cpu()[0]) == 0
+        x[n // 2, 3] = 0
+        ev.b.pack_sign(x, 0.0, f1, want_nz=False)
+        assert int(f1.cpu()[0]) == 1
