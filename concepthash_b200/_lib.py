@@ -50,6 +50,9 @@ SIGNATURES = {
                                    C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int32),
                                    C.POINTER(C.c_int32)]),
     "ch_hamming_hist": (C.c_int, [P, C.POINTER(HistArgs), P]),
+    "ch_tc_code_bytes": (C.c_int, [C.c_int]),
+    "ch_expand_i8": (C.c_int, [P, P, C.c_int64, C.c_int, P, P]),
+    "ch_hamming_select_tc": (C.c_int, [P, C.POINTER(HistArgs), P, P, P]),
     "ch_slab_totals": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int64, P, P]),
     "ch_slab_exscan": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int64, P]),
     "ch_scan_bases": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, P, P, P, P]),

@@ -144,9 +144,32 @@ class CudaBackend:
                                           C.byref(nqp), C.byref(st), C.byref(rps)), "ch_hist_geometry")
         return th.value, nqp.value, st.value, rps.value
 
-    def hamming_hist(self, *, q_bits, q_nz, g_bits, g_nz, q_lab, g_lab, slab_all, slab_rel, thresh, rec_off,
-                     rec_cap, rec_cnt, recs, err_flag, nq, nq_pad, ndb, nbit, ternary, label_mode, mask_words,
-                     emit_mode, nstripes, threads, rows_per_stripe):
+    # ---- tensor-core select pass ----
+    def tc_code_bytes(self, nbit):
+        return int(self.lib.ch_tc_code_bytes(int(nbit)))
+
+    def expand_i8(self, bits, nbit, min_rows=0):
+        """packed sign bits (rows_pad, words) -> +-1 int8 plane in the tiled operand order (rows, kb) int8;
+        ``min_rows`` over-allocates (zero rows) so that whole 128-query tiles can be read."""
+        kb = self.tc_code_bytes(nbit)
+        rows_pad = int(bits.shape[0])
+        rows = max(rows_pad, (int(min_rows) + 7) // 8 * 8)
+        out = self.zeros((rows, kb), torch.int8) if rows > rows_pad else self.empty((rows, kb), torch.int8)
+        L.check(self.lib.ch_expand_i8(self.ws, _ptr(bits), rows_pad, nbit, _ptr(out), self._stream()), "ch_expand_i8")
+        return out
+
+    def hamming_select_tc(self, q_i8, g_i8, **kw):
+        a = self._hist_args(**kw)
+        L.check(self.lib.ch_hamming_select_tc(self.ws, C.byref(a), _ptr(q_i8), _ptr(g_i8), self._stream()),
+                "ch_hamming_select_tc")
+
+    def hamming_hist(self, **kw):
+        a = self._hist_args(**kw)
+        L.check(self.lib.ch_hamming_hist(self.ws, C.byref(a), self._stream()), "ch_hamming_hist")
+
+    def _hist_args(self, *, q_bits, q_nz, g_bits, g_nz, q_lab, g_lab, slab_all, slab_rel, thresh, rec_off,
+                   rec_cap, rec_cnt, recs, err_flag, nq, nq_pad, ndb, nbit, ternary, label_mode, mask_words,
+                   emit_mode, nstripes, threads, rows_per_stripe):
         a = L.HistArgs()
         for k, v in dict(q_bits=q_bits, q_nz=q_nz if ternary else None, g_bits=g_bits,
                          g_nz=g_nz if ternary else None, q_lab=q_lab, g_lab=g_lab, slab_all=slab_all,
@@ -156,7 +179,7 @@ class CudaBackend:
         a.nq, a.nq_pad, a.ndb = nq, nq_pad, ndb
         a.nbit, a.ternary, a.label_mode, a.mask_words, a.emit_mode = nbit, int(ternary), label_mode, mask_words, emit_mode
         a.nstripes, a.threads, a.rows_per_stripe = nstripes, threads, rows_per_stripe
-        L.check(self.lib.ch_hamming_hist(self.ws, C.byref(a), self._stream()), "ch_hamming_hist")
+        return a
 
     def slab_totals(self, slab, nstripes, nbins, nq_pad, out):
         L.check(self.lib.ch_slab_totals(self.ws, _ptr(slab), nstripes, nbins, nq_pad, _ptr(out), self._stream()),

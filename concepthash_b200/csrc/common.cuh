@@ -67,6 +67,22 @@ static inline int64_t ch_round_up(int64_t x, int64_t m) { return (x + m - 1) / m
 // ---- device helpers -------------------------------------------------------------------------------
 #ifdef __CUDACC__
 
+// device-side view of ch_hist_args (+ derived geometry), shared by the POPC and the tensor-core kernels
+struct HistDev {
+  const uint32_t* q_bits; const uint32_t* q_nz;
+  const uint32_t* g_bits; const uint32_t* g_nz;
+  const uint32_t* q_lab;  const uint32_t* g_lab;
+  uint32_t* slab_all; uint32_t* slab_rel;
+  const uint32_t* thresh;
+  const uint32_t* rec_off; const uint32_t* rec_cap; uint32_t* rec_cnt; uint4* recs;
+  uint32_t* err_flag;
+  long long nq, nq_pad, ndb;
+  int nbit, nbins, lw, emit_mode;
+  int nqtiles, rows_per_stripe, tile_rows, flush_tiles;
+};
+
+
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

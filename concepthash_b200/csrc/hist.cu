@@ -25,19 +25,6 @@
 
 namespace {
 
-struct HistDev {
-  const uint32_t* q_bits; const uint32_t* q_nz;
-  const uint32_t* g_bits; const uint32_t* g_nz;
-  const uint32_t* q_lab;  const uint32_t* g_lab;
-  uint32_t* slab_all; uint32_t* slab_rel;
-  const uint32_t* thresh;
-  const uint32_t* rec_off; const uint32_t* rec_cap; uint32_t* rec_cnt; uint4* recs;
-  uint32_t* err_flag;
-  long long nq, nq_pad, ndb;
-  int nbit, nbins, lw, emit_mode;
-  int nqtiles, rows_per_stripe, tile_rows, flush_tiles;
-};
-
 constexpr int kStages = 2;
 
 // compile-time tile geometry of the code / id stages (static shared memory: the compiler then KNOWS the

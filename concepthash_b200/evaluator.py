@@ -64,7 +64,7 @@ def _as_int_list(t):
 
 class Packed:
     """Packed codes + labels of one side (query or gallery shard)."""
-    __slots__ = ("n", "nbit", "bits", "nz", "ids", "masks", "info", "ncls")
+    __slots__ = ("n", "nbit", "bits", "nz", "ids", "masks", "info", "ncls", "i8")
 
 
 class Evaluator:
@@ -76,6 +76,7 @@ class Evaluator:
         self.sample_stride = 16            # top-R: 1-in-16 row sample picks the threshold (0/1 = exact two-pass)
         self.sample_min_rows = 200_000     # below this the two-pass path is cheap anyway
         self.sample_min_ratio = 64         # ... and the sample must still hold ~R/stride*... rows: need ndb >= ratio * R
+        self.use_tensor_cores = True       # select pass on tcgen05 (int8 +-1 codes) when the shape allows it
         self.profile = False               # bench: bracket the kernels with CUDA events on the launch stream
         self.events = []                   # (kind, work units, start event, end event)
 
@@ -92,6 +93,7 @@ class Evaluator:
     # ------------------------------------------------------------------ packing
     def _pack_side(self, codes, labels, threshold, flags, nolabel, want_nz=False):
         p = Packed()
+        p.i8 = None
         p.n, p.nbit = int(codes.shape[0]), int(codes.shape[1])
         # algorithmic bytes of K1: the real-valued codes read once + the packed bits written once
         pack_bytes = p.n * p.nbit * codes.element_size() + p.n * p.nbit // 8
@@ -155,15 +157,29 @@ class Evaluator:
               rec=None):
         threads, nq_pad, nstripes, rps = geo
         lab = lambda p: None if label_mode == L.CH_LAB_NONE else (p.ids if label_mode == L.CH_LAB_ID else p.masks)
-        kind = "hist_select" if thresh is not None else ("hist_count_rec" if emit else "hist_count")
-        self._timed(kind, q.n * g.n, lambda: self.b.hamming_hist(
+        args = dict(
             q_bits=q.bits, q_nz=q.nz, g_bits=g.bits, g_nz=g.nz, q_lab=lab(q), g_lab=lab(g),
             slab_all=slab_all, slab_rel=slab_rel if label_mode != L.CH_LAB_NONE else None, thresh=thresh,
             rec_off=rec["off"] if rec else None, rec_cap=rec["cap"] if rec else None,
             rec_cnt=rec["cnt"] if rec else None, recs=rec["recs"] if rec else None,
             err_flag=rec["err"] if rec else None, nq=q.n, nq_pad=nq_pad, ndb=g.n, nbit=q.nbit, ternary=ternary,
             label_mode=label_mode, mask_words=lw, emit_mode=emit, nstripes=nstripes, threads=threads,
-            rows_per_stripe=rps))
+            rows_per_stripe=rps)
+        tc = (thresh is not None and self.use_tensor_cores and not ternary and hasattr(self.b, "hamming_select_tc")
+              and label_mode in (L.CH_LAB_NONE, L.CH_LAB_ID) and nq_pad % 128 == 0 and self.b.tc_code_bytes(q.nbit) > 0)
+        if tc:
+            # +-1 int8 planes in the tensor-core operand order, made once per evaluation from the packed bits
+            if q.i8 is None:
+                q.i8 = self._timed("expand_i8", 0, lambda: self.b.expand_i8(q.bits, q.nbit, nq_pad))
+            if g.i8 is None:
+                g.i8 = self._timed("expand_i8", 0, lambda: self.b.expand_i8(g.bits, g.nbit))
+            self._timed("hist_select_tc", q.n * g.n, lambda: self.b.hamming_select_tc(q.i8, g.i8, **args))
+            self.stats["select_kernel"] = "tcgen05"
+            return
+        kind = "hist_select" if thresh is not None else ("hist_count_rec" if emit else "hist_count")
+        if thresh is not None:
+            self.stats["select_kernel"] = "popc"
+        self._timed(kind, q.n * g.n, lambda: self.b.hamming_hist(**args))
 
     def _gathered_totals(self, slab, nstripes, nbins, nq_pad):
         tot = self.b.empty((nbins, nq_pad), torch.int32)
@@ -340,6 +356,7 @@ class Evaluator:
         # ---- the sample: every stride-th row of the local shard, same stripes (rps is a multiple of stride) ----
         ns = (g.n + stride - 1) // stride
         sp = Packed()
+        sp.i8 = None
         sp.n, sp.nbit = ns, g.nbit
         sp.bits = b.zeros((b.padded_rows(ns), g.bits.shape[1]), torch.int32)
         sp.bits[:ns] = g.bits[:g.n][::stride]

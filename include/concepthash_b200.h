@@ -132,6 +132,17 @@ int ch_hist_geometry(ch_ws* ws, int64_t nq, int64_t ndb, int nbit, int ternary, 
                      int32_t* rows_per_stripe);
 int ch_hamming_hist(ch_ws* ws, const ch_hist_args* a, void* stream);
 
+/* ---- K2, tensor-core form of the select pass (same inputs / outputs as ch_hamming_hist with `thresh` set) ----
+ * +-1 codes as int8: <q, g> = nbit - 2 * hamming, computed by tcgen05.mma kind::i8 (UTCIMMA) with the
+ * accumulators in TMEM; binary codes only, nbit <= 128, label modes NONE / ID.  The int8 planes are made from
+ * the packed bits by ch_expand_i8 in the shared-memory operand order (8-row x 16-byte core matrices), so the
+ * kernel streams them with plain 1-D bulk copies.  ch_tc_code_bytes(nbit) = bytes per row (multiple of 32),
+ * 0 if the path does not support nbit.  out_dev of ch_expand_i8: rows_pad * ch_tc_code_bytes(nbit) bytes. */
+int ch_tc_code_bytes(int nbit);
+int ch_expand_i8(ch_ws* ws, const uint32_t* bits_dev, int64_t rows_pad, int nbit, int8_t* out_dev, void* stream);
+int ch_hamming_select_tc(ch_ws* ws, const ch_hist_args* a, const int8_t* q_i8_dev, const int8_t* g_i8_dev,
+                         void* stream);
+
 /* slab reductions: totals over stripes -> tot (nbins, nq_pad); exclusive scan over stripes in place */
 int ch_slab_totals(ch_ws* ws, const uint32_t* slab, int nstripes, int nbins, int64_t nq_pad,
                    uint32_t* tot_dev, void* stream);

@@ -358,3 +358,30 @@ def test_pack_sign_flat_fast_path(H, nbit, dtype):
         x[n // 2, 3] = 0
         ev.b.pack_sign(x, 0.0, f1, want_nz=False)
         assert int(f1.cpu()[0]) == 1
+
+
+@pytest.mark.parametrize("nbit", [32, 48, 64, 96, 128])
+def test_tensor_core_select_equals_popc_select(H, nbit):
+    """The tcgen05 (int8 +-1, UTCIMMA) select pass must give bit-identical results to the XOR+POPC select pass:
+    same AP per query, same ranked ids -- and both match the oracle on a query subset."""
+    ev = H.get_evaluator()
+    nq, ndb = 700, 260_000 + nbit          # tail tile, several stripes, inactive query lanes in the last tile
+    d, dl, q, ql, ncls = synth.make_random_case(nq, ndb, nbit, 30, p=0.30, seed=nbit, device="cuda")
+    out = {}
+    for tc in (True, False):
+        ev.use_tensor_cores = tc
+        try:
+            res = ev.evaluate(d, dl, q, ql, [50, 500], 0.0, [1, 5, 10], False, return_ap=True)
+            kern = ev.stats["select_kernel"]
+            ids, keys, _ = ev.retrieve(d, q, 300)
+            out[tc] = (res, ids, keys)
+        finally:
+            ev.use_tensor_cores = True
+        assert kern == ("tcgen05" if tc else "popc")
+    (ra, ia, ka), (rb, ib, kb) = out[True], out[False]
+    assert ra[0] == rb[0] and ra[1] == rb[1] and ra[2] == rb[2] and torch.equal(ra[3], rb[3])
+    assert torch.equal(ia, ib) and torch.equal(ka, kb)
+    sub = slice(0, 40)
+    om, orec, oprec = mo.calculate_mAP(d.cpu(), dl.cpu(), q[sub].cpu(), ql[sub].cpu(), [50, 500], PRs=[1, 5, 10])
+    m, rec, prec = H.calculate_mAP(d, dl, q[sub], ql[sub], [50, 500], PRs=[1, 5, 10])
+    assert np.allclose(m, om, atol=TOL) and np.allclose(rec, orec, atol=TOL) and np.allclose(prec, oprec, atol=TOL)
