@@ -253,26 +253,51 @@ def main():
     words32 = max(1, (w["nbit"] + 31) // 32)
     popc_peak, _ = ev.b.popc_peak()
     peaks, peak_src = measured_peaks()
-    # the dominant kernel = the histogram pass with the largest share of the step
-    hist_kind = max((k for k in kinds if k.startswith("hist")), key=lambda k: kinds[k][0])
-    hk = kinds[hist_kind]
-    hist_ms = hk[0] / hk[2]
-    hist_popc = (hk[1] / hk[2]) * words32 / (hist_ms * 1e-3)
+    # the dominant kernel = the Hamming pass with the largest share of the step
     sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
-    pass_name = {"hist_count": "count pass: every pair histogrammed",
-                 "hist_count_rec": "count pass + records of relevant pairs (full ranking)",
-                 "hist_select": "select pass: pairs with key <= threshold counted / matched / recorded"}[hist_kind]
-    roofline = {
-        "kernel": f"hamming_hist_kernel ({pass_name})", "bound": "int-pipe (POPC)",
-        "achieved": hist_popc / 1e9, "peak": popc_peak / 1e9, "unit": "Gpopc32/s",
-        "frac": hist_popc / popc_peak, "traffic": None,
-        "algorithmic_work": f"nq x ndb_local pairs x {words32} popc32 per pair per launch",
-        "peak_source": "ch_popc_peak micro-benchmark run live on this GPU (MEASURED_PEAKS.json has no integer-pipe "
-                       "figure); nominal 148 SM x 16 lanes x f",
-        "nominal_peak_at_sampled_clock": 148 * 16 * sm_mhz * 1e6 / 1e9,
-        "ms_per_launch": hist_ms, "pairs_per_s": (hk[1] / hk[2]) / (hist_ms * 1e-3),
-        "share_of_step": hk[0] / (ms * args.steps),
-    }
+
+    def popc_roofline(kind):
+        hk = kinds[kind]
+        t_ms = hk[0] / hk[2]
+        popc = (hk[1] / hk[2]) * words32 / (t_ms * 1e-3)
+        name = {"hist_count": "count pass: every pair histogrammed",
+                "hist_count_rec": "count pass + records of relevant pairs (full ranking)",
+                "hist_select": "select pass: pairs with key <= threshold counted / matched / recorded"}[kind]
+        return {
+            "kernel": f"hamming_hist_kernel ({name})", "bound": "int-pipe (POPC)",
+            "achieved": popc / 1e9, "peak": popc_peak / 1e9, "unit": "Gpopc32/s", "frac": popc / popc_peak,
+            "traffic": None, "algorithmic_work": f"pairs x {words32} popc32 per pair per launch",
+            "peak_source": "ch_popc_peak micro-benchmark run live on this GPU (MEASURED_PEAKS.json has no "
+                           "integer-pipe figure); nominal 148 SM x 16 lanes x f",
+            "nominal_peak_at_sampled_clock": 148 * 16 * sm_mhz * 1e6 / 1e9,
+            "ms_per_launch": t_ms, "pairs_per_launch": hk[1] / hk[2], "pairs_per_s": (hk[1] / hk[2]) / (t_ms * 1e-3),
+            "share_of_step": hk[0] / (ms * args.steps)}
+
+    def tensor_roofline(kind):
+        hk = kinds[kind]
+        t_ms = hk[0] / hk[2]
+        kb = (w["nbit"] + 31) // 32 * 32
+        tops = (hk[1] / hk[2]) * kb * 2 / (t_ms * 1e-3) / 1e12
+        peak = 2.0 * peaks.get("bf16_tflops", 1590.0)
+        pairs_s = (hk[1] / hk[2]) / (t_ms * 1e-3)
+        return {
+            "kernel": "hamming_select_tc_kernel (select pass on tcgen05.mma kind::i8, accumulators in TMEM)",
+            "bound": "tensor", "achieved": tops, "peak": peak, "unit": "TOP/s (int8)", "frac": tops / peak,
+            "traffic": None, "algorithmic_work": f"pairs x {kb} int8 MACs x 2 per launch",
+            "peak_source": f"2 x bf16_tflops of {peak_src} (int8 dense runs at twice the bf16 rate; no int8 figure is "
+                           "measured)",
+            "note": "the MMA itself is a few percent of the kernel: the pass is bound by its epilogue (one TMEM word "
+                    "read + one compare per pair on 4 warps), reported below in pairs per clock per SM",
+            "pairs_per_clk_per_sm": pairs_s / (148 * sm_mhz * 1e6),
+            "popc_kernel_ceiling_pairs_per_s": popc_peak / words32,
+            "ms_per_launch": t_ms, "pairs_per_launch": hk[1] / hk[2], "pairs_per_s": pairs_s,
+            "share_of_step": hk[0] / (ms * args.steps)}
+
+    ham_kinds = [k for k in kinds if k.startswith("hist")]
+    dom = max(ham_kinds, key=lambda k: kinds[k][0])
+    roofline = tensor_roofline(dom) if dom == "hist_select_tc" else popc_roofline(dom)
+    roofline_other = {k: (tensor_roofline(k) if k == "hist_select_tc" else popc_roofline(k))
+                      for k in ham_kinds if k != dom}
     pack = kinds.get("pack_dev")
     roofline_pack = None
     if pack:
@@ -317,7 +342,8 @@ def main():
                        "parallelism": f"gallery row-sharded x{world}" if world > 1 else "single GPU",
                        "mAP": out[0][0] if out else None},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "kernel_ms_per_step": kernel_ms,
-            "roofline": roofline, "roofline_pack": roofline_pack, "cpu_baseline": cpu,
+            "roofline": roofline, "roofline_other_passes": roofline_other, "roofline_pack": roofline_pack,
+            "cpu_baseline": cpu,
         }
         print(json.dumps(line))
     if world > 1:

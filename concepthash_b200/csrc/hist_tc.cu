@@ -50,6 +50,24 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// single-thread waiters (producer, MMA issuer) back off so that their spin does not steal issue slots from
+// the epilogue warp sharing the scheduler
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(128);
+  }
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -80,7 +98,8 @@ struct TcSmem {
   static constexpr int offA = 0;
   static constexpr int offB = offA + kA;
   static constexpr int offLab = offB + kTcStages * kB;
-  static constexpr int offHist = offLab + kTcStages * kLab;
+  static constexpr int offQueue = offLab + kTcStages * kLab;        // u16 [32][128] candidate queue
+  static constexpr int offHist = offQueue + 32 * kTileM * 2;
   static size_t total(int nbins) { return offHist + static_cast<size_t>(nbins) * kTileM * 4; }
 };
 
@@ -130,7 +149,7 @@ __global__ void __launch_bounds__(256, 1) hamming_select_tc_kernel(const TcDev t
       bulk_g2s(smem + S::offA, t.q_i8 + static_cast<size_t>(qtile) * kTileM * KB, S::kA, &bar_a);
       for (int k = 0; k < ntiles; ++k) {
         const int s = k % kTcStages;
-        mbar_wait(&bar_empty[s], static_cast<uint32_t>(((k / kTcStages) & 1) ^ 1));
+        mbar_wait_backoff(&bar_empty[s], static_cast<uint32_t>(((k / kTcStages) & 1) ^ 1));
         const long long r0 = row_begin + static_cast<long long>(k) * kTileN;
         long long rows = row_end - r0;
         if (rows > kTileN) rows = kTileN;
@@ -153,8 +172,8 @@ __global__ void __launch_bounds__(256, 1) hamming_select_tc_kernel(const TcDev t
       mbar_wait(&bar_a, 0);
       for (int k = 0; k < ntiles; ++k) {
         const int s = k % kTcStages, b = k & 1;
-        mbar_wait(&bar_tempty[b], static_cast<uint32_t>(((k >> 1) & 1) ^ 1));
-        mbar_wait(&bar_full[s], static_cast<uint32_t>((k / kTcStages) & 1));
+        mbar_wait_backoff(&bar_tempty[b], static_cast<uint32_t>(((k >> 1) & 1) ^ 1));
+        mbar_wait_backoff(&bar_full[s], static_cast<uint32_t>((k / kTcStages) & 1));
         tc_fence_after();
         const uint32_t b_addr = smem_u32(smem + S::offB + s * S::kB);
         const uint32_t d_addr = tmem_base + static_cast<uint32_t>(b) * kTileN;
@@ -171,6 +190,7 @@ __global__ void __launch_bounds__(256, 1) hamming_select_tc_kernel(const TcDev t
     const int e = tid - 128;                       // 0..127
     const int ewarp = warp - 4;                    // == warp % 4 -> TMEM lanes 32 * ewarp ..
     unsigned char* hist_b = smem + S::offHist + e * 4;
+    unsigned short* queue = reinterpret_cast<unsigned short*>(smem + S::offQueue) + e;
     constexpr uint32_t T4 = kTileM * 4u;
     const long long q = static_cast<long long>(qtile) * kTileM + e;
     const bool active = q < a.nq;
@@ -219,34 +239,58 @@ __global__ void __launch_bounds__(256, 1) hamming_select_tc_kernel(const TcDev t
       for (int c0 = 0; c0 < rows; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(taddr0 + c0, r);
-        int m = static_cast<int>(r[0]);
+        // hot path: is any of the 32 dots >= tau?  (4 sub-maxima of 8, 3-input max tree; garbage columns past
+        // `rows` in the stripe's last tile can only cause a spurious visit of the cold path)
+        int mg[4];
 #pragma unroll
-        for (int j = 1; j < 32; ++j) m = max(m, (c0 + j < rows) ? static_cast<int>(r[j]) : static_cast<int>(0x80000000));
-        if (m >= tau) {   // some gallery row of this 32-column chunk is a candidate for this query (rare)
+        for (int g4 = 0; g4 < 4; ++g4) {
+          const int o = g4 * 8;
+          int x = max(max(static_cast<int>(r[o]), static_cast<int>(r[o + 1])), static_cast<int>(r[o + 2]));
+          x = max(max(x, static_cast<int>(r[o + 3])), static_cast<int>(r[o + 4]));
+          x = max(max(x, static_cast<int>(r[o + 5])), static_cast<int>(r[o + 6]));
+          mg[g4] = max(x, static_cast<int>(r[o + 7]));
+        }
+        if (max(max(mg[0], mg[1]), max(mg[2], mg[3])) >= tau) {
+          // cold path (a few lanes): queue the candidates of this chunk in column order, then handle them in a
+          // ROLLED loop -- one copy of the candidate code keeps the kernel inside the instruction cache
+          uint32_t n = 0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int dot = static_cast<int>(r[j]);
-            if (dot >= tau && c0 + j < rows) {
-              const uint32_t key = static_cast<uint32_t>(a.nbit - dot) >> 1;
-              bool rel = false;
-              if (LAB == CH_LAB_ID) rel = labs[c0 + j] == qid;
-              uint32_t* h = reinterpret_cast<uint32_t*>(hist_b + key * T4);
-              const uint32_t old = *h;
-              *h = old + (rel ? 0x10001u : 1u);
-              if (emit_mode == CH_EMIT_CANDIDATES || (emit_mode == CH_EMIT_RELEVANT && rel)) {
-                uint32_t base_all = 0, base_rel = 0;
-                if (epoch != 0u) {
-                  const size_t o = (static_cast<size_t>(stripe) * a.nbins + key) * a.nq_pad + q;
-                  base_all = a.slab_all[o];
-                  if (LAB != CH_LAB_NONE) base_rel = a.slab_rel[o];
+          for (int g4 = 0; g4 < 4; ++g4) {
+            if (mg[g4] >= tau) {
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                const int j = g4 * 8 + jj;
+                const int dot = static_cast<int>(r[j]);
+                if (dot >= tau) {
+                  queue[n * kTileM] = static_cast<unsigned short>(((static_cast<uint32_t>(a.nbit - dot) >> 1) << 5) | j);
+                  ++n;
                 }
-                if (rptr < rend)
-                  a.recs[rptr] = make_uint4(key | (rel ? 0x80000000u : 0u), base_all + (old & 0xffffu),
-                                            base_rel + (old >> 16), shard_row0 + c0 + j);
-                else
-                  overflow = true;
-                ++rptr;
               }
+            }
+          }
+          for (uint32_t i = 0; i < n; ++i) {
+            const uint32_t ent = queue[i * kTileM];
+            const uint32_t key = ent >> 5;
+            const int col = c0 + static_cast<int>(ent & 31u);
+            if (col >= rows) continue;
+            bool rel = false;
+            if (LAB == CH_LAB_ID) rel = labs[col] == qid;
+            uint32_t* h = reinterpret_cast<uint32_t*>(hist_b + key * T4);
+            const uint32_t old = *h;
+            *h = old + (rel ? 0x10001u : 1u);
+            if (emit_mode == CH_EMIT_CANDIDATES || (emit_mode == CH_EMIT_RELEVANT && rel)) {
+              uint32_t base_all = 0, base_rel = 0;
+              if (epoch != 0u) {
+                const size_t o = (static_cast<size_t>(stripe) * a.nbins + key) * a.nq_pad + q;
+                base_all = a.slab_all[o];
+                if (LAB != CH_LAB_NONE) base_rel = a.slab_rel[o];
+              }
+              if (rptr < rend)
+                a.recs[rptr] = make_uint4(key | (rel ? 0x80000000u : 0u), base_all + (old & 0xffffu),
+                                          base_rel + (old >> 16), shard_row0 + col);
+              else
+                overflow = true;
+              ++rptr;
             }
           }
         }
