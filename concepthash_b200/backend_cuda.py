@@ -169,7 +169,7 @@ class CudaBackend:
 
     def _hist_args(self, *, q_bits, q_nz, g_bits, g_nz, q_lab, g_lab, slab_all, slab_rel, thresh, rec_off,
                    rec_cap, rec_cnt, recs, err_flag, nq, nq_pad, ndb, nbit, ternary, label_mode, mask_words,
-                   emit_mode, nstripes, threads, rows_per_stripe):
+                   emit_mode, nstripes, threads, rows_per_stripe, key_limit=0):
         a = L.HistArgs()
         for k, v in dict(q_bits=q_bits, q_nz=q_nz if ternary else None, g_bits=g_bits,
                          g_nz=g_nz if ternary else None, q_lab=q_lab, g_lab=g_lab, slab_all=slab_all,
@@ -178,7 +178,7 @@ class CudaBackend:
             setattr(a, k, v.data_ptr() if v is not None else None)
         a.nq, a.nq_pad, a.ndb = nq, nq_pad, ndb
         a.nbit, a.ternary, a.label_mode, a.mask_words, a.emit_mode = nbit, int(ternary), label_mode, mask_words, emit_mode
-        a.nstripes, a.threads, a.rows_per_stripe = nstripes, threads, rows_per_stripe
+        a.nstripes, a.threads, a.rows_per_stripe, a.key_limit = nstripes, threads, rows_per_stripe, int(key_limit)
         return a
 
     def slab_totals(self, slab, nstripes, nbins, nq_pad, out):

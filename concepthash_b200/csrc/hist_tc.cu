@@ -21,7 +21,7 @@
 namespace {
 
 constexpr int kTcStages = 4;
-constexpr int kTileN = 256;   // gallery rows per MMA tile
+constexpr int kTileN = 128;   // gallery rows per MMA tile (TMEM columns per accumulator)
 constexpr int kTileM = 128;   // queries per CTA
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -85,35 +85,46 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 
 struct TcDev {
   HistDev h;
-  const int8_t* q_i8;   // tiled (nq_pad rows, KB)
+  const int8_t* q_i8;   // tiled (>= nq_pad rows, KB)
   const int8_t* g_i8;   // tiled (rows_pad, KB)
+  int kbins;            // histogram keys actually reachable in this pass (max threshold + 1)
+  int nqtiles128;       // 128-query tiles in total
+  int nqgroups;         // CTAs along the query axis (each owns QT consecutive query tiles)
 };
 
 // shared-memory carve-up (bytes), all offsets multiples of 128
-template <int KB>
+template <int KB, int QT>
 struct TcSmem {
-  static constexpr int kA = kTileM * KB;
-  static constexpr int kB = kTileN * KB;
+  static constexpr int kA = kTileM * KB;             // one query tile
+  static constexpr int kB = kTileN * KB;             // one gallery tile
   static constexpr int kLab = kTileN * 4;
+  static constexpr int kQueue = 8 * kTileM * 2;      // u16 [8][128] candidate queue per query tile
   static constexpr int offA = 0;
-  static constexpr int offB = offA + kA;
+  static constexpr int offB = offA + QT * kA;
   static constexpr int offLab = offB + kTcStages * kB;
-  static constexpr int offQueue = offLab + kTcStages * kLab;        // u16 [32][128] candidate queue
-  static constexpr int offHist = offQueue + 32 * kTileM * 2;
-  static size_t total(int nbins) { return offHist + static_cast<size_t>(nbins) * kTileM * 4; }
+  static constexpr int offQueue = offLab + kTcStages * kLab;
+  static constexpr int offHist = offQueue + QT * kQueue;
+  static size_t total(int kbins) { return offHist + static_cast<size_t>(QT) * kbins * kTileM * 4; }
 };
 
-template <int KB, int LAB>
-__global__ void __launch_bounds__(256, 1) hamming_select_tc_kernel(const TcDev t) {
-  typedef TcSmem<KB> S;
+// One CTA = QT consecutive 128-query tiles x one gallery stripe.  Every gallery tile (128 rows) is multiplied
+// against all QT query tiles (QT accumulators of 128 TMEM columns each, 512 columns in total for QT = 4); each
+// query tile has its own epilogue warpgroup (4 warps), so 4 * QT warps hide each other's latencies while every
+// query still sees its gallery rows strictly in row order (which the stable prefixes need).
+template <int KB, int LAB, int QT>
+__global__ void __launch_bounds__(128 + 128 * QT, 1) hamming_select_tc_kernel(const TcDev t) {
+  typedef TcSmem<KB, QT> S;
   const HistDev& a = t.h;
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t bar_a, bar_full[kTcStages], bar_empty[kTcStages], bar_tfull[2], bar_tempty[2];
+  __shared__ __align__(8) uint64_t bar_a, bar_full[kTcStages], bar_empty[kTcStages], bar_tfull[QT], bar_tempty[QT];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  const int qtile = blockIdx.x % a.nqtiles;
-  const int stripe = blockIdx.x / a.nqtiles;
+  const int qgroup = blockIdx.x % t.nqgroups;
+  const int stripe = blockIdx.x / t.nqgroups;
+  const int qtile0 = qgroup * QT;
+  int nvalid = t.nqtiles128 - qtile0;
+  if (nvalid > QT) nvalid = QT;
   const long long row_begin = static_cast<long long>(stripe) * a.rows_per_stripe;
   long long row_end = row_begin + a.rows_per_stripe;
   if (row_end > a.ndb) row_end = a.ndb;
@@ -123,11 +134,11 @@ __global__ void __launch_bounds__(256, 1) hamming_select_tc_kernel(const TcDev t
     mbar_init(&bar_a, 1);
     for (int s = 0; s < kTcStages; ++s) {
       mbar_init(&bar_full[s], 1);
-      mbar_init(&bar_empty[s], 1 + 4);   // MMA commit + the four epilogue warps (class ids live in the stage)
+      mbar_init(&bar_empty[s], 1 + 4 * nvalid);   // MMA commit + every epilogue warp (class ids live in the stage)
     }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&bar_tfull[b], 1);
-      mbar_init(&bar_tempty[b], 4);
+    for (int i = 0; i < QT; ++i) {
+      mbar_init(&bar_tfull[i], 1);
+      mbar_init(&bar_tempty[i], 4);
     }
     fence_mbar_init();
   }
@@ -145,8 +156,8 @@ __global__ void __launch_bounds__(256, 1) hamming_select_tc_kernel(const TcDev t
   if (warp == 0) {
     // ===================== producer =====================
     if (lane == 0 && ntiles > 0) {
-      mbar_arrive_expect_tx(&bar_a, S::kA);
-      bulk_g2s(smem + S::offA, t.q_i8 + static_cast<size_t>(qtile) * kTileM * KB, S::kA, &bar_a);
+      mbar_arrive_expect_tx(&bar_a, nvalid * S::kA);
+      bulk_g2s(smem + S::offA, t.q_i8 + static_cast<size_t>(qtile0) * kTileM * KB, nvalid * S::kA, &bar_a);
       for (int k = 0; k < ntiles; ++k) {
         const int s = k % kTcStages;
         mbar_wait_backoff(&bar_empty[s], static_cast<uint32_t>(((k / kTcStages) & 1) ^ 1));
@@ -164,41 +175,44 @@ __global__ void __launch_bounds__(256, 1) hamming_select_tc_kernel(const TcDev t
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0 && ntiles > 0) {
-      // s32 accumulate, s8 x s8, both K-major, N = 256, M = 128
+      // s32 accumulate, s8 x s8, both K-major, N = kTileN, M = 128
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kTileN >> 3) << 17) |
                              (static_cast<uint32_t>(kTileM >> 4) << 24);
       const uint32_t sbo = 8 * KB, lbo = 128;
       const uint32_t a_addr = smem_u32(smem + S::offA);
-      mbar_wait(&bar_a, 0);
+      mbar_wait_backoff(&bar_a, 0);
       for (int k = 0; k < ntiles; ++k) {
-        const int s = k % kTcStages, b = k & 1;
-        mbar_wait_backoff(&bar_tempty[b], static_cast<uint32_t>(((k >> 1) & 1) ^ 1));
+        const int s = k % kTcStages;
         mbar_wait_backoff(&bar_full[s], static_cast<uint32_t>((k / kTcStages) & 1));
-        tc_fence_after();
         const uint32_t b_addr = smem_u32(smem + S::offB + s * S::kB);
-        const uint32_t d_addr = tmem_base + static_cast<uint32_t>(b) * kTileN;
+        for (int i = 0; i < nvalid; ++i) {
+          mbar_wait_backoff(&bar_tempty[i], static_cast<uint32_t>((k & 1) ^ 1));   // accumulator i drained
+          tc_fence_after();
+          const uint32_t d_addr = tmem_base + static_cast<uint32_t>(i) * kTileN;
 #pragma unroll
-        for (int kk = 0; kk < KB / 32; ++kk)
-          umma_i8(d_addr, umma_desc(a_addr + kk * 256, lbo, sbo), umma_desc(b_addr + kk * 256, lbo, sbo), idesc,
-                  kk > 0 ? 1u : 0u);
-        umma_commit(&bar_empty[s]);   // the stage's code bytes may be overwritten once these MMAs retire
-        umma_commit(&bar_tfull[b]);   // accumulator b is complete
+          for (int kk = 0; kk < KB / 32; ++kk)
+            umma_i8(d_addr, umma_desc(a_addr + i * S::kA + kk * 256, lbo, sbo), umma_desc(b_addr + kk * 256, lbo, sbo),
+                    idesc, kk > 0 ? 1u : 0u);
+          umma_commit(&bar_tfull[i]);   // accumulator i holds tile k
+        }
+        umma_commit(&bar_empty[s]);     // the stage's code bytes may be overwritten once these MMAs retire
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && ((warp - 4) >> 2) < nvalid) {
     // ===================== epilogue: thread = TMEM lane = query =====================
-    const int e = tid - 128;                       // 0..127
-    const int ewarp = warp - 4;                    // == warp % 4 -> TMEM lanes 32 * ewarp ..
-    unsigned char* hist_b = smem + S::offHist + e * 4;
-    unsigned short* queue = reinterpret_cast<unsigned short*>(smem + S::offQueue) + e;
+    const int qt = (warp - 4) >> 2;                // query tile of this warpgroup
+    const int e = (tid - 128) & 127;               // 0..127 within the query tile
+    const int ewarp = warp & 3;                    // TMEM lanes 32 * ewarp ..
+    unsigned char* hist_b = smem + S::offHist + static_cast<size_t>(qt) * t.kbins * kTileM * 4 + e * 4;
+    unsigned short* queue = reinterpret_cast<unsigned short*>(smem + S::offQueue + qt * S::kQueue) + e;
     constexpr uint32_t T4 = kTileM * 4u;
-    const long long q = static_cast<long long>(qtile) * kTileM + e;
+    const long long q = static_cast<long long>(qtile0 + qt) * kTileM + e;
     const bool active = q < a.nq;
     uint32_t qid = CH_QUERY_NOLABEL;
     if (LAB == CH_LAB_ID && active) qid = a.q_lab[q];
     // key <= thresh  <=>  dot >= nbit - 2 * thresh
     const int tau = active ? a.nbit - 2 * static_cast<int>(a.thresh[q]) : 0x7fffffff;
-    for (int b = 0; b < a.nbins; ++b) *reinterpret_cast<uint32_t*>(hist_b + b * T4) = 0u;
+    for (int b = 0; b < t.kbins; ++b) *reinterpret_cast<uint32_t*>(hist_b + b * T4) = 0u;
 
     const size_t sq = static_cast<size_t>(stripe) * a.nq_pad + q;
     uint32_t rptr = 0, rstart = 0, rend = 0;
@@ -211,7 +225,7 @@ __global__ void __launch_bounds__(256, 1) hamming_select_tc_kernel(const TcDev t
     bool overflow = false;
     uint32_t epoch = 0;
     auto flush = [&]() {
-      for (int b = 0; b < a.nbins; ++b) {
+      for (int b = 0; b < t.kbins; ++b) {
         uint32_t* h = reinterpret_cast<uint32_t*>(hist_b + b * T4);
         const uint32_t v = *h;
         if (v != 0u) {
@@ -225,17 +239,45 @@ __global__ void __launch_bounds__(256, 1) hamming_select_tc_kernel(const TcDev t
       }
       ++epoch;
     };
+    // cold path: the queued candidates of one 8-column group, in column order
+    auto drain = [&](uint32_t n, int c0, int rows, const uint32_t* labs, uint32_t shard_row0) {
+      for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t ent = queue[i * kTileM];
+        const uint32_t key = ent >> 5;
+        const int col = c0 + static_cast<int>(ent & 31u);
+        if (col >= rows) continue;
+        bool rel = false;
+        if (LAB == CH_LAB_ID) rel = labs[col] == qid;
+        uint32_t* h = reinterpret_cast<uint32_t*>(hist_b + key * T4);
+        const uint32_t old = *h;
+        *h = old + (rel ? 0x10001u : 1u);
+        if (emit_mode == CH_EMIT_CANDIDATES || (emit_mode == CH_EMIT_RELEVANT && rel)) {
+          uint32_t base_all = 0, base_rel = 0;
+          if (epoch != 0u) {
+            const size_t o = (static_cast<size_t>(stripe) * a.nbins + key) * a.nq_pad + q;
+            base_all = a.slab_all[o];
+            if (LAB != CH_LAB_NONE) base_rel = a.slab_rel[o];
+          }
+          if (rptr < rend)
+            a.recs[rptr] = make_uint4(key | (rel ? 0x80000000u : 0u), base_all + (old & 0xffffu),
+                                      base_rel + (old >> 16), shard_row0 + col);
+          else
+            overflow = true;
+          ++rptr;
+        }
+      }
+    };
 
     for (int k = 0; k < ntiles; ++k) {
-      const int s = k % kTcStages, b = k & 1;
+      const int s = k % kTcStages;
       long long rows_ll = row_end - (row_begin + static_cast<long long>(k) * kTileN);
       const int rows = rows_ll > kTileN ? kTileN : static_cast<int>(rows_ll);
       const uint32_t shard_row0 = static_cast<uint32_t>(row_begin) + static_cast<uint32_t>(k) * kTileN;
       const uint32_t* labs = reinterpret_cast<const uint32_t*>(smem + S::offLab + s * S::kLab);
       mbar_wait(&bar_full[s], static_cast<uint32_t>((k / kTcStages) & 1));   // class ids of the stage are visible
-      mbar_wait(&bar_tfull[b], static_cast<uint32_t>((k >> 1) & 1));
+      mbar_wait(&bar_tfull[qt], static_cast<uint32_t>(k & 1));
       tc_fence_after();
-      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ewarp * 32) << 16) + static_cast<uint32_t>(b) * kTileN;
+      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ewarp * 32) << 16) + static_cast<uint32_t>(qt) * kTileN;
       for (int c0 = 0; c0 < rows; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(taddr0 + c0, r);
@@ -251,12 +293,11 @@ __global__ void __launch_bounds__(256, 1) hamming_select_tc_kernel(const TcDev t
           mg[g4] = max(x, static_cast<int>(r[o + 7]));
         }
         if (max(max(mg[0], mg[1]), max(mg[2], mg[3])) >= tau) {
-          // cold path (a few lanes): queue the candidates of this chunk in column order, then handle them in a
-          // ROLLED loop -- one copy of the candidate code keeps the kernel inside the instruction cache
-          uint32_t n = 0;
+          // cold path (a few lanes): per 8-column group queue the candidates, then handle them in a rolled loop
 #pragma unroll
           for (int g4 = 0; g4 < 4; ++g4) {
             if (mg[g4] >= tau) {
+              uint32_t n = 0;
 #pragma unroll
               for (int jj = 0; jj < 8; ++jj) {
                 const int j = g4 * 8 + jj;
@@ -266,40 +307,16 @@ __global__ void __launch_bounds__(256, 1) hamming_select_tc_kernel(const TcDev t
                   ++n;
                 }
               }
-            }
-          }
-          for (uint32_t i = 0; i < n; ++i) {
-            const uint32_t ent = queue[i * kTileM];
-            const uint32_t key = ent >> 5;
-            const int col = c0 + static_cast<int>(ent & 31u);
-            if (col >= rows) continue;
-            bool rel = false;
-            if (LAB == CH_LAB_ID) rel = labs[col] == qid;
-            uint32_t* h = reinterpret_cast<uint32_t*>(hist_b + key * T4);
-            const uint32_t old = *h;
-            *h = old + (rel ? 0x10001u : 1u);
-            if (emit_mode == CH_EMIT_CANDIDATES || (emit_mode == CH_EMIT_RELEVANT && rel)) {
-              uint32_t base_all = 0, base_rel = 0;
-              if (epoch != 0u) {
-                const size_t o = (static_cast<size_t>(stripe) * a.nbins + key) * a.nq_pad + q;
-                base_all = a.slab_all[o];
-                if (LAB != CH_LAB_NONE) base_rel = a.slab_rel[o];
-              }
-              if (rptr < rend)
-                a.recs[rptr] = make_uint4(key | (rel ? 0x80000000u : 0u), base_all + (old & 0xffffu),
-                                          base_rel + (old >> 16), shard_row0 + col);
-              else
-                overflow = true;
-              ++rptr;
+              drain(n, c0, rows, labs, shard_row0);
             }
           }
         }
       }
-      // this warp is done with accumulator b and with the stage's class ids
+      // this warp is done with the accumulator and with the stage's class ids
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&bar_tempty[b]);
+        mbar_arrive(&bar_tempty[qt]);
         mbar_arrive(&bar_empty[s]);
       }
       if ((k + 1) % a.flush_tiles == 0 && k + 1 < ntiles) flush();
@@ -349,9 +366,25 @@ __global__ void expand_i8_tiled_kernel(const uint32_t* __restrict__ bits, long l
 }
 
 typedef void (*tc_fn_t)(const TcDev);
-template <int KB>
+template <int KB, int QT>
 tc_fn_t pick_lab_tc(int lab) {
-  return lab == CH_LAB_ID ? hamming_select_tc_kernel<KB, CH_LAB_ID> : hamming_select_tc_kernel<KB, CH_LAB_NONE>;
+  return lab == CH_LAB_ID ? hamming_select_tc_kernel<KB, CH_LAB_ID, QT> : hamming_select_tc_kernel<KB, CH_LAB_NONE, QT>;
+}
+template <int KB>
+tc_fn_t pick_qt_tc(int qt, int lab, int kbins, size_t* smem) {
+  switch (qt) {
+    case 4: *smem = TcSmem<KB, 4>::total(kbins); return pick_lab_tc<KB, 4>(lab);
+    case 2: *smem = TcSmem<KB, 2>::total(kbins); return pick_lab_tc<KB, 2>(lab);
+    default: *smem = TcSmem<KB, 1>::total(kbins); return pick_lab_tc<KB, 1>(lab);
+  }
+}
+tc_fn_t pick_tc(int kb, int qt, int lab, int kbins, size_t* smem) {
+  switch (kb) {
+    case 32: return pick_qt_tc<32>(qt, lab, kbins, smem);
+    case 64: return pick_qt_tc<64>(qt, lab, kbins, smem);
+    case 96: return pick_qt_tc<96>(qt, lab, kbins, smem);
+    default: return pick_qt_tc<128>(qt, lab, kbins, smem);
+  }
 }
 
 }  // namespace
@@ -408,20 +441,29 @@ extern "C" int ch_hamming_select_tc(ch_ws* ws, const ch_hist_args* a, const int8
   h.nqtiles = static_cast<int>(a->nq_pad / kTileM); h.rows_per_stripe = a->rows_per_stripe; h.tile_rows = kTileN;
   h.flush_tiles = 65535 / kTileN;
   d.q_i8 = q_i8; d.g_i8 = g_i8;
+  // only keys <= max threshold are reachable: the caller may pass that bound (key_limit = max thresh + 1)
+  d.kbins = (a->key_limit > 0 && a->key_limit < h.nbins) ? a->key_limit : h.nbins;
+  d.nqtiles128 = static_cast<int>(a->nq_pad / kTileM);
+  // as many query tiles per CTA as shared memory allows (more epilogue warps = better latency hiding)
   tc_fn_t fn = nullptr;
   size_t smem = 0;
-  switch (kb) {
-    case 32: fn = pick_lab_tc<32>(a->label_mode); smem = TcSmem<32>::total(h.nbins); break;
-    case 64: fn = pick_lab_tc<64>(a->label_mode); smem = TcSmem<64>::total(h.nbins); break;
-    case 96: fn = pick_lab_tc<96>(a->label_mode); smem = TcSmem<96>::total(h.nbins); break;
-    default: fn = pick_lab_tc<128>(a->label_mode); smem = TcSmem<128>::total(h.nbins); break;
+  int qt = 4;
+  for (;; qt >>= 1) {
+    fn = pick_tc(kb, qt, a->label_mode, d.kbins, &smem);
+    if (smem + 1024 <= static_cast<size_t>(ws->max_smem_optin) || qt == 1) break;
   }
+  if (smem + 1024 > static_cast<size_t>(ws->max_smem_optin))
+    CH_FAIL("tensor-core kernel needs %zu bytes of shared memory (key_limit=%d)", smem, d.kbins);
+  if (d.nqtiles128 < qt) {   // fewer query tiles than the CTA could take: do not waste accumulators
+    while (qt > 1 && d.nqtiles128 <= qt / 2) qt >>= 1;
+    fn = pick_tc(kb, qt, a->label_mode, d.kbins, &smem);
+  }
+  d.nqgroups = (d.nqtiles128 + qt - 1) / qt;
   if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: each CTA owns all 512 TMEM columns
-  if (smem > static_cast<size_t>(ws->max_smem_optin)) CH_FAIL("tensor-core kernel needs %zu bytes of shared memory", smem);
   CH_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  const long long ctas = static_cast<long long>(h.nqtiles) * a->nstripes;
+  const long long ctas = static_cast<long long>(d.nqgroups) * a->nstripes;
   if (ctas > 0x7fffffffll) CH_FAIL("grid too large");
-  fn<<<static_cast<unsigned>(ctas), 256, smem, static_cast<cudaStream_t>(stream)>>>(d);
+  fn<<<static_cast<unsigned>(ctas), 128 + 128 * qt, smem, static_cast<cudaStream_t>(stream)>>>(d);
   CH_LAUNCH_CHECK(ws);
   return 0;
 }
