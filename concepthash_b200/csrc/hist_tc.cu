@@ -20,7 +20,6 @@
 
 namespace {
 
-constexpr int kTcStages = 4;
 constexpr int kTileN = 128;   // gallery rows per MMA tile (TMEM columns per accumulator)
 constexpr int kTileM = 128;   // queries per CTA
 
@@ -93,7 +92,7 @@ struct TcDev {
 };
 
 // shared-memory carve-up (bytes), all offsets multiples of 128
-template <int KB, int QT>
+template <int KB, int QT, int kTcStages>
 struct TcSmem {
   static constexpr int kA = kTileM * KB;             // one query tile
   static constexpr int kB = kTileN * KB;             // one gallery tile
@@ -111,9 +110,9 @@ struct TcSmem {
 // against all QT query tiles (QT accumulators of 128 TMEM columns each, 512 columns in total for QT = 4); each
 // query tile has its own epilogue warpgroup (4 warps), so 4 * QT warps hide each other's latencies while every
 // query still sees its gallery rows strictly in row order (which the stable prefixes need).
-template <int KB, int LAB, int QT>
+template <int KB, int LAB, int QT, int kTcStages>
 __global__ void __launch_bounds__(128 + 128 * QT, 1) hamming_select_tc_kernel(const TcDev t) {
-  typedef TcSmem<KB, QT> S;
+  typedef TcSmem<KB, QT, kTcStages> S;
   const HistDev& a = t.h;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar_a, bar_full[kTcStages], bar_empty[kTcStages], bar_tfull[QT], bar_tempty[QT];
@@ -366,24 +365,35 @@ __global__ void expand_i8_tiled_kernel(const uint32_t* __restrict__ bits, long l
 }
 
 typedef void (*tc_fn_t)(const TcDev);
-template <int KB, int QT>
-tc_fn_t pick_lab_tc(int lab) {
-  return lab == CH_LAB_ID ? hamming_select_tc_kernel<KB, CH_LAB_ID, QT> : hamming_select_tc_kernel<KB, CH_LAB_NONE, QT>;
+template <int KB, int QT, int ST>
+tc_fn_t pick_lab_tc(int lab, int kbins, size_t* smem) {
+  *smem = TcSmem<KB, QT, ST>::total(kbins);
+  return lab == CH_LAB_ID ? hamming_select_tc_kernel<KB, CH_LAB_ID, QT, ST>
+                          : hamming_select_tc_kernel<KB, CH_LAB_NONE, QT, ST>;
 }
 template <int KB>
-tc_fn_t pick_qt_tc(int qt, int lab, int kbins, size_t* smem) {
+tc_fn_t pick_qt_tc(int qt, int st, int lab, int kbins, size_t* smem) {
+  if (st == 4) {
+    switch (qt) {
+      case 4: return pick_lab_tc<KB, 4, 4>(lab, kbins, smem);
+      case 3: return pick_lab_tc<KB, 3, 4>(lab, kbins, smem);
+      case 2: return pick_lab_tc<KB, 2, 4>(lab, kbins, smem);
+      default: return pick_lab_tc<KB, 1, 4>(lab, kbins, smem);
+    }
+  }
   switch (qt) {
-    case 4: *smem = TcSmem<KB, 4>::total(kbins); return pick_lab_tc<KB, 4>(lab);
-    case 2: *smem = TcSmem<KB, 2>::total(kbins); return pick_lab_tc<KB, 2>(lab);
-    default: *smem = TcSmem<KB, 1>::total(kbins); return pick_lab_tc<KB, 1>(lab);
+    case 4: return pick_lab_tc<KB, 4, 3>(lab, kbins, smem);
+    case 3: return pick_lab_tc<KB, 3, 3>(lab, kbins, smem);
+    case 2: return pick_lab_tc<KB, 2, 3>(lab, kbins, smem);
+    default: return pick_lab_tc<KB, 1, 3>(lab, kbins, smem);
   }
 }
-tc_fn_t pick_tc(int kb, int qt, int lab, int kbins, size_t* smem) {
+tc_fn_t pick_tc(int kb, int qt, int st, int lab, int kbins, size_t* smem) {
   switch (kb) {
-    case 32: return pick_qt_tc<32>(qt, lab, kbins, smem);
-    case 64: return pick_qt_tc<64>(qt, lab, kbins, smem);
-    case 96: return pick_qt_tc<96>(qt, lab, kbins, smem);
-    default: return pick_qt_tc<128>(qt, lab, kbins, smem);
+    case 32: return pick_qt_tc<32>(qt, st, lab, kbins, smem);
+    case 64: return pick_qt_tc<64>(qt, st, lab, kbins, smem);
+    case 96: return pick_qt_tc<96>(qt, st, lab, kbins, smem);
+    default: return pick_qt_tc<128>(qt, st, lab, kbins, smem);
   }
 }
 
@@ -444,20 +454,22 @@ extern "C" int ch_hamming_select_tc(ch_ws* ws, const ch_hist_args* a, const int8
   // only keys <= max threshold are reachable: the caller may pass that bound (key_limit = max thresh + 1)
   d.kbins = (a->key_limit > 0 && a->key_limit < h.nbins) ? a->key_limit : h.nbins;
   d.nqtiles128 = static_cast<int>(a->nq_pad / kTileM);
-  // as many query tiles per CTA as shared memory allows (more epilogue warps = better latency hiding)
+  // as many query tiles per CTA as shared memory allows (more epilogue warps = better latency hiding);
+  // never more than the problem has; 4 pipeline stages if they fit, else 3
+  const size_t smem_max = static_cast<size_t>(ws->max_smem_optin) - 1024;
   tc_fn_t fn = nullptr;
   size_t smem = 0;
-  int qt = 4;
-  for (;; qt >>= 1) {
-    fn = pick_tc(kb, qt, a->label_mode, d.kbins, &smem);
-    if (smem + 1024 <= static_cast<size_t>(ws->max_smem_optin) || qt == 1) break;
+  int qt = d.nqtiles128 < 4 ? d.nqtiles128 : 4;
+  int st = 4;
+  for (;; --qt) {
+    st = 4;
+    fn = pick_tc(kb, qt, st, a->label_mode, d.kbins, &smem);
+    if (smem <= smem_max) break;
+    st = 3;
+    fn = pick_tc(kb, qt, st, a->label_mode, d.kbins, &smem);
+    if (smem <= smem_max || qt == 1) break;
   }
-  if (smem + 1024 > static_cast<size_t>(ws->max_smem_optin))
-    CH_FAIL("tensor-core kernel needs %zu bytes of shared memory (key_limit=%d)", smem, d.kbins);
-  if (d.nqtiles128 < qt) {   // fewer query tiles than the CTA could take: do not waste accumulators
-    while (qt > 1 && d.nqtiles128 <= qt / 2) qt >>= 1;
-    fn = pick_tc(kb, qt, a->label_mode, d.kbins, &smem);
-  }
+  if (smem > smem_max) CH_FAIL("tensor-core kernel needs %zu bytes of shared memory (key_limit=%d)", smem, d.kbins);
   d.nqgroups = (d.nqtiles128 + qt - 1) / qt;
   if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: each CTA owns all 512 TMEM columns
   CH_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
