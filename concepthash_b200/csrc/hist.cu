@@ -517,6 +517,8 @@ extern "C" int ch_hamming_hist(ch_ws* ws, const ch_hist_args* a, void* stream) {
   d.recs = static_cast<uint4*>(a->recs); d.err_flag = a->err_flag;
   d.nq = a->nq; d.nq_pad = a->nq_pad; d.ndb = a->ndb;
   d.nbit = a->nbit; d.nbins = (a->ternary ? 2 * a->nbit : a->nbit) + 1; d.lw = a->mask_words;
+  // select pass: keys above max(thresh) never occur -> the caller may keep narrower slabs / histograms
+  if (a->thresh != nullptr && a->key_limit > 0 && a->key_limit < d.nbins) d.nbins = a->key_limit;
   d.emit_mode = a->emit_mode;
   d.nqtiles = g.nqtiles; d.rows_per_stripe = g.rows_per_stripe; d.tile_rows = g.tile; d.flush_tiles = g.flush_tiles;
   CH_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(g.smem)));

@@ -448,11 +448,13 @@ extern "C" int ch_hamming_select_tc(ch_ws* ws, const ch_hist_args* a, const int8
   h.recs = static_cast<uint4*>(a->recs); h.err_flag = a->err_flag;
   h.nq = a->nq; h.nq_pad = a->nq_pad; h.ndb = a->ndb;
   h.nbit = a->nbit; h.nbins = a->nbit + 1; h.lw = 0; h.emit_mode = a->emit_mode;
+  // keys above max(thresh) never occur: with key_limit the slabs have key_limit rows per stripe
+  if (a->key_limit > 0 && a->key_limit < h.nbins) h.nbins = a->key_limit;
   h.nqtiles = static_cast<int>(a->nq_pad / kTileM); h.rows_per_stripe = a->rows_per_stripe; h.tile_rows = kTileN;
   h.flush_tiles = 65535 / kTileN;
   d.q_i8 = q_i8; d.g_i8 = g_i8;
   // only keys <= max threshold are reachable: the caller may pass that bound (key_limit = max thresh + 1)
-  d.kbins = (a->key_limit > 0 && a->key_limit < h.nbins) ? a->key_limit : h.nbins;
+  d.kbins = h.nbins;
   d.nqtiles128 = static_cast<int>(a->nq_pad / kTileM);
   // as many query tiles per CTA as shared memory allows (more epilogue warps = better latency hiding);
   // never more than the problem has; 4 pipeline stages if they fit, else 3

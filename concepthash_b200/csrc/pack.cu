@@ -131,24 +131,43 @@ __global__ void __launch_bounds__(256) pack_bits_kernel(const T* __restrict__ sr
 // flight per thread (4 KB per warp).  Zeros / NaNs are only DETECTED here (flags); if a zero shows up the
 // caller re-packs with the general kernel to obtain the non-zero plane.
 template <typename T>
-__global__ void __launch_bounds__(256) pack_sign_flat_kernel(const T* __restrict__ src, int64_t nblocks32,
+__global__ void __launch_bounds__(256) pack_sign_flat_kernel(const T* __restrict__ src, int64_t n, int nbit, int words,
+                                                             int64_t nblocks_full, int64_t nblocks_all,
                                                              uint32_t* __restrict__ out_pos,
                                                              uint32_t* __restrict__ flags) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   uint32_t fl = 0;
-  for (int64_t blk = warp; blk < nblocks32; blk += nwarps) {
-    const T* p = src + blk * 1024 + lane;
-    float x[32];
-#pragma unroll
-    for (int u = 0; u < 32; ++u) x[u] = static_cast<float>(Elem<T>::load(p + u * 32));
+  for (int64_t blk = warp; blk < nblocks_all; blk += nwarps) {
     uint32_t mine = 0;
+    if (blk < nblocks_full) {
+      // 32 units entirely inside the tensor: no bounds checks, 32 independent coalesced loads in flight
+      const T* p = src + blk * 1024 + lane;
+      float x[32];
 #pragma unroll
-    for (int u = 0; u < 32; ++u) {
-      const uint32_t b = __ballot_sync(0xffffffffu, x[u] > 0.0f);
-      if (!(fabsf(x[u]) > 0.0f)) fl |= (x[u] != x[u]) ? 2u : 1u;   // zero or NaN: rare
-      if (lane == u) mine = b;
+      for (int u = 0; u < 32; ++u) x[u] = static_cast<float>(Elem<T>::load(p + u * 32));
+#pragma unroll
+      for (int u = 0; u < 32; ++u) {
+        const uint32_t b = __ballot_sync(0xffffffffu, x[u] > 0.0f);
+        if (!(fabsf(x[u]) > 0.0f)) fl |= (x[u] != x[u]) ? 2u : 1u;   // zero or NaN: rare
+        if (lane == u) mine = b;
+      }
+    } else {
+      // the last rows of the tensor and the zero pad rows
+      for (int u = 0; u < 32; ++u) {
+        const int64_t unit = blk * 32 + u;
+        const int64_t r = unit / words;
+        const int col = static_cast<int>(unit - r * words) * 32 + lane;
+        bool pos = false;
+        if (r < n && col < nbit) {
+          const float x = static_cast<float>(Elem<T>::load(src + r * nbit + col));
+          pos = x > 0.0f;
+          if (!(fabsf(x) > 0.0f)) fl |= (x != x) ? 2u : 1u;
+        }
+        const uint32_t b = __ballot_sync(0xffffffffu, pos);
+        if (lane == u) mine = b;
+      }
     }
     out_pos[blk * 32 + lane] = mine;
   }
@@ -316,31 +335,33 @@ extern "C" int ch_pack_sign(ch_ws* ws, const void* codes, int mem, int dtype, in
   if (mem == CH_MEM_HOST)
     return pack_from_host(ws, codes, dtype, n, nbit, row_stride, col_stride, threshold, words, rows_pad,
                           out_bits_dev, out_nz_dev, flags_dev, st);
-  // flat fast path (see pack_sign_flat_kernel); the rows it does not cover go through the general kernel
-  int64_t row0 = 0;
+  // flat fast path (see pack_sign_flat_kernel): one launch covers the tensor, its tail and the pad rows
   const bool flat = out_nz_dev == nullptr && threshold == 0.0 && (col_stride == 1 || nbit == 1) &&
                     (row_stride == nbit || n <= 1) && nbit == words * 32 && flags_dev != nullptr &&
                     (dtype == CH_F32 || dtype == CH_F16 || dtype == CH_BF16) &&
                     (reinterpret_cast<uintptr_t>(codes) & 3) == 0;
-  if (flat && n >= 32) {
-    row0 = n / 32 * 32;                                   // row0 * words is a multiple of 32 units
-    const int64_t nblocks32 = row0 * words / 32;
-    int64_t blocks = (nblocks32 + 7) / 8;
+  if (flat) {
+    const int64_t nblocks_full = n * words / 32;             // 32-unit blocks without any bounds check
+    const int64_t nblocks_all = rows_pad * words / 32;       // rows_pad is a multiple of 64
+    int64_t blocks = (nblocks_all + 7) / 8;
     const int64_t cap = static_cast<int64_t>(ws->sm_count) * 8;
     if (blocks > cap) blocks = cap;
     const dim3 grid(static_cast<unsigned>(blocks)), block(256);
     if (dtype == CH_F32)
-      pack_sign_flat_kernel<float><<<grid, block, 0, st>>>(static_cast<const float*>(codes), nblocks32, out_bits_dev, flags_dev);
+      pack_sign_flat_kernel<float><<<grid, block, 0, st>>>(static_cast<const float*>(codes), n, nbit, words,
+                                                           nblocks_full, nblocks_all, out_bits_dev, flags_dev);
     else if (dtype == CH_F16)
-      pack_sign_flat_kernel<__half><<<grid, block, 0, st>>>(static_cast<const __half*>(codes), nblocks32, out_bits_dev, flags_dev);
+      pack_sign_flat_kernel<__half><<<grid, block, 0, st>>>(static_cast<const __half*>(codes), n, nbit, words,
+                                                            nblocks_full, nblocks_all, out_bits_dev, flags_dev);
     else
-      pack_sign_flat_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(static_cast<const __nv_bfloat16*>(codes), nblocks32, out_bits_dev, flags_dev);
+      pack_sign_flat_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(static_cast<const __nv_bfloat16*>(codes), n, nbit,
+                                                                   words, nblocks_full, nblocks_all, out_bits_dev,
+                                                                   flags_dev);
     CH_LAUNCH_CHECK(ws);
+    return 0;
   }
-  const size_t es = dtype == CH_F32 ? 4 : (dtype == CH_F64 ? 8 : 2);
-  return launch_pack(ws, static_cast<const char*>(codes) + static_cast<size_t>(row0) * row_stride * es, dtype, row0,
-                     rows_pad, n, nbit, row_stride, col_stride, threshold, words, out_bits_dev, out_nz_dev, flags_dev,
-                     st);
+  return launch_pack(ws, codes, dtype, 0, rows_pad, n, nbit, row_stride, col_stride, threshold, words, out_bits_dev,
+                     out_nz_dev, flags_dev, st);
 }
 
 extern "C" int ch_pack_labels(ch_ws* ws, const void* labels, int mem, int dtype, int64_t n, int C,

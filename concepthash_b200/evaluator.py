@@ -154,7 +154,7 @@ class Evaluator:
 
     # ------------------------------------------------------------------ one histogram pass
     def _hist(self, q, g, geo, ternary, label_mode, lw, slab_all, slab_rel, thresh=None, emit=L.CH_EMIT_NONE,
-              rec=None):
+              rec=None, key_limit=0):
         threads, nq_pad, nstripes, rps = geo
         lab = lambda p: None if label_mode == L.CH_LAB_NONE else (p.ids if label_mode == L.CH_LAB_ID else p.masks)
         args = dict(
@@ -164,7 +164,7 @@ class Evaluator:
             rec_cnt=rec["cnt"] if rec else None, recs=rec["recs"] if rec else None,
             err_flag=rec["err"] if rec else None, nq=q.n, nq_pad=nq_pad, ndb=g.n, nbit=q.nbit, ternary=ternary,
             label_mode=label_mode, mask_words=lw, emit_mode=emit, nstripes=nstripes, threads=threads,
-            rows_per_stripe=rps)
+            rows_per_stripe=rps, key_limit=key_limit)
         tc = (thresh is not None and self.use_tensor_cores and not ternary and hasattr(self.b, "hamming_select_tc")
               and label_mode in (L.CH_LAB_NONE, L.CH_LAB_ID) and nq_pad % 128 == 0 and self.b.tc_code_bytes(q.nbit) > 0)
         if tc:
@@ -173,8 +173,9 @@ class Evaluator:
                 q.i8 = self._timed("expand_i8", 0, lambda: self.b.expand_i8(q.bits, q.nbit, nq_pad))
             if g.i8 is None:
                 g.i8 = self._timed("expand_i8", 0, lambda: self.b.expand_i8(g.bits, g.nbit))
-            # only keys <= max threshold are reachable: smaller private histograms -> more query tiles per CTA
-            args["key_limit"] = int(thresh[:q.n].max().item()) + 1
+            if not key_limit:
+                # only keys <= max threshold are reachable: smaller private histograms -> more query tiles per CTA
+                args["key_limit"] = int(thresh[:q.n].max().item()) + 1
             self._timed("hist_select_tc", q.n * g.n, lambda: self.b.hamming_select_tc(q.i8, g.i8, **args))
             self.stats["select_kernel"] = "tcgen05"
             return
@@ -252,7 +253,8 @@ class Evaluator:
         f = dict(recs=rec["recs"], rec_off=rec["off"], rec_cnt=rec["cnt"], base0_all=st["base0_all"],
                  base0_rel=st["base0_rel"], sbase_all=st["sbase_all"], sbase_rel=st["sbase_rel"], first_rel=None,
                  partial=b.empty((nstripes, nq_pad, max(ncols, 1)), torch.float64), cols=cols,
-                 nq=nq, nq_pad=nq_pad, nstripes=nstripes, nbins=nbins, remove_first=bool(rf), r_eff=r_eff, pr_k=pr_k)
+                 nq=nq, nq_pad=nq_pad, nstripes=nstripes, nbins=st.get("nbins", nbins), remove_first=bool(rf),
+                 r_eff=r_eff, pr_k=pr_k)
         first_rel = None
         if rf:
             first_rel = b.zeros((nq_pad,), torch.int32)
@@ -390,11 +392,12 @@ class Evaluator:
         b.record_caps(2, cls, q.ids, nstripes, c["nclass"], nq, nq_pad, True, cap)
         rec = self._alloc_records(cap, geo, nq)
         del slab_s, base_tmp
-        # ---- the one full pass ----
+        # ---- the one full pass; only keys <= max threshold can occur, all slabs / bases are that narrow ----
+        nbins = min(nbins, int(thresh[:nq].max().item()) + 1)
         slab_all = b.zeros((nstripes, nbins, nq_pad), torch.int32)
         slab_rel = b.zeros((nstripes, nbins, nq_pad), torch.int32)
         self._hist(q, g, geo, ternary, label_mode, lw, slab_all, slab_rel, thresh=thresh,
-                   emit=L.CH_EMIT_RELEVANT, rec=rec)
+                   emit=L.CH_EMIT_RELEVANT, rec=rec, key_limit=nbins)
         base0_all = b.empty((nbins, nq_pad), torch.int32)
         base0_rel = b.empty((nbins, nq_pad), torch.int32)
         found = b.zeros((nq_pad,), torch.int32)
@@ -423,7 +426,7 @@ class Evaluator:
             ok = (qid >= 0) & (qid < c["nclass"])
             total_rel[:nq] = torch.where(ok, cls_tot[qid.clamp(0, c["nclass"] - 1)], torch.zeros_like(cls_tot[:1]))
         return dict(rec=rec, base0_all=base0_all, base0_rel=base0_rel, sbase_all=slab_all, sbase_rel=slab_rel,
-                    total_rel=total_rel, rec_checked=True)
+                    total_rel=total_rel, rec_checked=True, nbins=nbins)
 
     def _local_totals(self, slab, geo, nbins):
         threads, nq_pad, nstripes, rps = geo

@@ -123,7 +123,8 @@ typedef struct ch_hist_args {
   int64_t nq, nq_pad, ndb;             /* ndb = rows of the local shard */
   int32_t nbit, ternary, label_mode, mask_words, emit_mode;
   int32_t nstripes, threads, rows_per_stripe;   /* geometry from ch_hist_geometry */
-  int32_t key_limit;       /* select pass: max(thresh) + 1 if the caller knows it (smaller histograms), else 0 */
+  int32_t key_limit;       /* select pass only: max(thresh) + 1 if the caller knows it, else 0.  When set, keys >= key_limit
+                              cannot occur and the slabs are (nstripes, key_limit, nq_pad) instead of (.., nbins, ..) */
 } ch_hist_args;
 
 /* chooses threads per CTA (= queries per CTA), nq_pad, stripes and rows per stripe (a multiple of 256)

@@ -134,7 +134,7 @@ class EmuBackend:
 
     def hamming_hist(self, *, q_bits, q_nz, g_bits, g_nz, q_lab, g_lab, slab_all, slab_rel, thresh, rec_off,
                      rec_cap, rec_cnt, recs, err_flag, nq, nq_pad, ndb, nbit, ternary, label_mode, mask_words,
-                     emit_mode, nstripes, threads, rows_per_stripe):
+                     emit_mode, nstripes, threads, rows_per_stripe, key_limit=0):
         self.launches += 1
         keys = self._keys(q_bits, q_nz, g_bits, g_nz, nq, ndb, nbit, ternary)
         rel = self._rel(q_lab, g_lab, nq, ndb, label_mode, mask_words)
