@@ -173,9 +173,6 @@ class Evaluator:
                 q.i8 = self._timed("expand_i8", 0, lambda: self.b.expand_i8(q.bits, q.nbit, nq_pad))
             if g.i8 is None:
                 g.i8 = self._timed("expand_i8", 0, lambda: self.b.expand_i8(g.bits, g.nbit))
-            if not key_limit:
-                # only keys <= max threshold are reachable: smaller private histograms -> more query tiles per CTA
-                args["key_limit"] = int(thresh[:q.n].max().item()) + 1
             self._timed("hist_select_tc", q.n * g.n, lambda: self.b.hamming_select_tc(q.i8, g.i8, **args))
             self.stats["select_kernel"] = "tcgen05"
             return
