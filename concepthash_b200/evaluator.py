@@ -225,13 +225,17 @@ class Evaluator:
         cls_ok = label_mode == L.CH_LAB_ID and 0 < nclass <= (1 << 20)
         sampled = (not full_ranking and self.sample_stride > 1 and cls_ok and
                    ndb_total >= self.sample_min_rows and rmax * self.sample_min_ratio <= ndb_total)
-        geo = self._agree_geometry(b.geometry(nq, g.n, nbit, ternary, label_mode, lw), g.n,
-                                   self.sample_stride if sampled else 1)
+        # sparser sample when the candidates are a tiny fraction of the gallery (their handling is then off the
+        # critical path of the select pass, so a looser threshold costs nothing and the sample pass shrinks)
+        stride = self.sample_stride
+        if sampled and stride > 1 and (rmax + rf) * 5000 <= ndb_total:
+            stride *= 4
+        geo = self._agree_geometry(b.geometry(nq, g.n, nbit, ternary, label_mode, lw), g.n, stride if sampled else 1)
         threads, nq_pad, nstripes, rps = geo
         self.stats.update(dict(ternary=ternary, label_mode=label_mode, geometry=geo, nbins=nbins,
                                ndb_total=ndb_total, world=comm.world))
         ctx = dict(q=q, g=g, geo=geo, ternary=ternary, label_mode=label_mode, lw=lw, nclass=nclass, nq=nq,
-                   nbins=nbins, rmax=rmax, rf=rf, pr_k=pr_k, ndb_total=ndb_total)
+                   nbins=nbins, rmax=rmax, rf=rf, pr_k=pr_k, ndb_total=ndb_total, stride=stride)
         st = None
         if full_ranking:
             self.stats["mode"] = "all"
@@ -352,8 +356,8 @@ class Evaluator:
         b, comm, q, g, geo = self.b, self.comm, c["q"], c["g"], c["geo"]
         threads, nq_pad, nstripes, rps = geo
         nbins, nq, label_mode, lw, ternary = c["nbins"], c["nq"], c["label_mode"], c["lw"], c["ternary"]
-        stride = self.sample_stride
         need = min(c["rmax"] + c["rf"], c["ndb_total"])
+        stride = c["stride"]
         # ---- the sample: every stride-th row of the local shard, same stripes (rps is a multiple of stride) ----
         ns = (g.n + stride - 1) // stride
         sp = Packed()
