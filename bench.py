@@ -45,7 +45,7 @@ WORKLOADS = {
 }
 
 
-def make_workload(name, device, nbit_override=None):
+def make_workload(name, device, nbit_override=None, shard=0):
     from concepthash_b200 import synth
     w = dict(WORKLOADS[name])
     if nbit_override:
@@ -55,7 +55,7 @@ def make_workload(name, device, nbit_override=None):
         w.update(nq=q.shape[0], ndb=d.shape[0], nclass=ncls)
     else:
         d, dl, q, ql, ncls = synth.make_random_case(w["nq"], w["ndb"], w["nbit"], w["nclass"], p=w["p"], seed=0,
-                                                    device=device)
+                                                    device=device, shard=shard)
     return w, d, dl, q, ql
 
 
@@ -200,7 +200,8 @@ def main():
         group = dist.group.WORLD
     from concepthash_b200 import hashing
 
-    w, d, dl, q, ql = make_workload(args.workload, device, args.nbit)
+    # weak scaling: every rank generates its own gallery block (same queries), no duplicates across ranks
+    w, d, dl, q, ql = make_workload(args.workload, device, args.nbit, shard=rank if wl["scaling"] == "weak" else 0)
     ndb_full = d.shape[0]
     if w["scaling"] == "strong" and world > 1:        # row-shard the named gallery over the ranks
         cut = [ndb_full * r // world for r in range(world + 1)]
@@ -327,6 +328,7 @@ def main():
                          f"oracle/map_oracle.calculate_mAP_upstream_style; linear in nq)"}
 
     if rank == 0:
+        print("evaluator stats:", ev.stats, file=sys.stderr)
         line = {
             "metric": "hamming_comparisons_per_sec_64bit", "value": value, "unit": "64-bit comparisons/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,

@@ -66,16 +66,20 @@ def make_dataset_case(name, nbit=64, p=0.15, seed=0, device="cpu"):
     return d, d_ids.to(device), q, q_ids.to(device), nclass
 
 
-def make_random_case(nq, ndb, nbit, nclass, p=0.30, seed=0, device="cpu", db_chunk=1 << 20):
-    """cfg4/5-style: labels ``randint(nclass)``; gallery generated in chunks on ``device``."""
+def make_random_case(nq, ndb, nbit, nclass, p=0.30, seed=0, device="cpu", db_chunk=1 << 20, shard=0):
+    """cfg4/5-style: labels ``randint(nclass)``; gallery generated in chunks on ``device``.
+    ``shard`` selects an independent gallery block (same codebook and queries): rank r of a weak-scaled run
+    generates shard r, so the concatenation over ranks is one large gallery without duplicates."""
     device = torch.device(device)
     g = torch.Generator(device=device).manual_seed(int(seed) + 7919)
     cb = codebook(nclass, nbit, seed)
     q_ids = torch.randint(nclass, (nq,), generator=g, device=device)
+    if shard:
+        g = torch.Generator(device=device).manual_seed(int(seed) + 7919 + 104729 * int(shard))
     d_ids = torch.randint(nclass, (ndb,), generator=g, device=device)
     q = codes_from_labels(q_ids, cb, p, seed * 2 + 1, device)
     d = torch.empty(ndb, nbit, dtype=torch.float32, device=device)
     for s in range(0, ndb, db_chunk):
         e = min(ndb, s + db_chunk)
-        d[s:e] = codes_from_labels(d_ids[s:e], cb, p, (seed * 2 + 2) * 1000003 + s, device)
+        d[s:e] = codes_from_labels(d_ids[s:e], cb, p, (seed * 2 + 2) * 1000003 + s + 15485863 * int(shard), device)
     return d, d_ids, q, q_ids, nclass
