@@ -113,13 +113,15 @@ class CudaBackend:
                                       self._stream()), "ch_pack_sign")
         return bits, nz
 
-    def pack_labels(self, labels, nolabel):
-        """labels (n, C) one-/multi-hot or (n,) ids -> (ids u32 (rows_pad), masks (rows_pad, lw) | None, info u32[4])."""
+    def pack_labels(self, labels, nolabel, info=None):
+        """labels (n, C) one-/multi-hot or (n,) ids -> (ids u32 (rows_pad), masks (rows_pad, lw) | None, info u32[4]).
+        ``info`` may be a zeroed u32[4] view supplied by the caller (statistics are accumulated into it)."""
         t, mem = self._src(labels)
         n = t.shape[0]
         rows = self.padded_rows(n)
         ids = self.empty((rows,), torch.int32)
-        info = self.zeros((4,), torch.int32)
+        if info is None:
+            info = self.zeros((4,), torch.int32)
         if t.dim() == 2:
             ncls = t.shape[1]
             lw = (ncls + 31) // 32
@@ -198,15 +200,21 @@ class CudaBackend:
         L.check(self.lib.ch_scan_bases(self.ws, _ptr(tot_all), world, rank, nbins, nq, nq_pad, rmax, _ptr(base0),
                                        _ptr(thresh), _ptr(total), self._stream()), "ch_scan_bases")
 
-    def record_caps(self, source, a0, a1, nstripes, nb, nq, nq_pad, min_with_prev, cap):
+    def record_caps(self, source, a0, a1, nstripes, nb, nq, nq_pad, min_with_prev, cap, sample_stride=0):
         L.check(self.lib.ch_record_caps(self.ws, source, _ptr(a0), _ptr(a1), nstripes, nb, nq, nq_pad,
-                                        int(min_with_prev), _ptr(cap), self._stream()), "ch_record_caps")
+                                        int(min_with_prev), int(sample_stride), _ptr(cap), self._stream()),
+                "ch_record_caps")
 
-    def record_offsets(self, cap, nstripes, nq, nq_pad, off):
-        total = C.c_uint64()
+    def record_offsets(self, cap, nstripes, nq, nq_pad, off, thresh=None):
+        """-> (total record slots, max(thresh[:nq]) or None); ONE host sync for both."""
+        total, tmax = C.c_uint64(), C.c_uint32()
         L.check(self.lib.ch_record_offsets(self.ws, _ptr(cap), nstripes, nq, nq_pad, _ptr(off), C.byref(total),
-                                           self._stream()), "ch_record_offsets")
-        return int(total.value)
+                                           _ptr(thresh), C.byref(tmax), self._stream()), "ch_record_offsets")
+        return int(total.value), (int(tmax.value) if thresh is not None else None)
+
+    def check_counts(self, total, nq, need, flags):
+        L.check(self.lib.ch_check_counts(self.ws, _ptr(total), nq, need, _ptr(flags), self._stream()),
+                "ch_check_counts")
 
     # ---- K4 ----
     def _final_args(self, f):
@@ -235,14 +243,16 @@ class CudaBackend:
         L.check(self.lib.ch_first_relevant(self.ws, C.byref(self._final_args(f)), _ptr(out), self._stream()),
                 "ch_first_relevant")
 
-    def reduce_means(self, cols, total_rel, first_rel, nq, n_r, pr_k, ap_out=None):
+    def reduce_means(self, cols, total_rel, first_rel, nq, n_r, pr_k, ap_out=None, flags=None):
+        """-> (mAPs, recalls, precisions, [flag0, flag1]); ``flags`` (u32[2] device) rides on the same host sync."""
         n_pr = len(pr_k)
         out = (C.c_double * max(1, n_r + 2 * n_pr))()
+        fl = (C.c_uint32 * 2)(0, 0)
         prk = (C.c_int64 * max(1, n_pr))(*[int(k) for k in pr_k])
         L.check(self.lib.ch_reduce_means(self.ws, _ptr(cols), _ptr(total_rel), _ptr(first_rel), nq, n_r, n_pr, prk,
-                                         _ptr(ap_out), out, self._stream()), "ch_reduce_means")
+                                         _ptr(ap_out), out, _ptr(flags), fl, self._stream()), "ch_reduce_means")
         vals = [float(out[i]) for i in range(n_r + 2 * n_pr)]
-        return vals[:n_r], vals[n_r:n_r + n_pr], vals[n_r + n_pr:]
+        return vals[:n_r], vals[n_r:n_r + n_pr], vals[n_r + n_pr:], [int(fl[0]), int(fl[1])]
 
     def scatter_ranked(self, f, R, row_offset, ids, keys):
         L.check(self.lib.ch_scatter_ranked(self.ws, C.byref(self._final_args(f)), R, row_offset, _ptr(ids),

@@ -38,7 +38,7 @@ __global__ void scan_bases_kernel(const uint32_t* __restrict__ tot_all, int worl
 // ---- record capacities / offsets ------------------------------------------------------------------
 __global__ void record_caps_kernel(int source, const uint32_t* __restrict__ a0, const uint32_t* __restrict__ a1,
                                    int nstripes, int nb, long long nq, long long nq_pad, int min_with_prev,
-                                   uint32_t* __restrict__ cap) {
+                                   int sample_stride, uint32_t* __restrict__ cap) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<long long>(nstripes) * nq_pad) return;
   const int s = static_cast<int>(i / nq_pad);
@@ -52,6 +52,12 @@ __global__ void record_caps_kernel(int source, const uint32_t* __restrict__ a0, 
       const uint32_t id = a1[q];
       if (id < static_cast<uint32_t>(nb)) c = a0[static_cast<size_t>(s) * nb + id];
     }
+  }
+  if (sample_stride > 1) {
+    // c candidates seen in a 1-in-stride row sample -> bound on the real count (Poisson tail, checked later:
+    // an overflowing slice raises the error flag and the caller redoes the evaluation exactly)
+    const float k = static_cast<float>(c);
+    c = static_cast<uint32_t>((k + 6.0f * sqrtf(k + 1.0f) + 10.0f) * static_cast<float>(sample_stride));
   }
   if (min_with_prev) {
     const uint32_t p = cap[i];
@@ -97,6 +103,21 @@ __global__ void __launch_bounds__(1024) exscan_u64_kernel(unsigned long long* __
     v[i] = run;
     run += x;
   }
+}
+
+// max over the first n entries (single CTA), written next to the scan total
+__global__ void __launch_bounds__(1024) max_u32_kernel(const uint32_t* __restrict__ v, long long n,
+                                                       unsigned long long* __restrict__ out) {
+  __shared__ uint32_t sh[1024];
+  uint32_t m = 0;
+  for (long long i = threadIdx.x; i < n; i += 1024) m = max(m, v[i]);
+  sh[threadIdx.x] = m;
+  __syncthreads();
+  for (int w = 512; w > 0; w >>= 1) {
+    if (threadIdx.x < w) sh[threadIdx.x] = max(sh[threadIdx.x], sh[threadIdx.x + w]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sh[0];
 }
 
 __global__ void record_offsets_kernel(const uint32_t* __restrict__ cap, const unsigned long long* __restrict__ start,
@@ -214,6 +235,14 @@ __global__ void scatter_ranked_kernel(const FinalDev a, long long R, long long r
       if (keys != nullptr) keys[q * R + rank] = static_cast<int>(r.x & 0x7fffffffu);
     }
   }
+}
+
+// verification of the sampled threshold: flag bit 0 if some query counted fewer than `need` candidates
+__global__ void check_counts_kernel(const uint32_t* __restrict__ total, long long nq, uint32_t need,
+                                    uint32_t* __restrict__ flags) {
+  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool bad = q < nq && total[q] < need;
+  if (__ballot_sync(0xffffffffu, bad) != 0u && (threadIdx.x & 31) == 0) atomicOr(flags, 1u);
 }
 
 // deterministic block sum of per-query values; one block per output scalar
@@ -387,14 +416,15 @@ extern "C" int ch_scan_bases(ch_ws* ws, const uint32_t* tot_all_dev, int world, 
 
 extern "C" int ch_record_caps(ch_ws* ws, int source, const uint32_t* slab_or_cls, const uint32_t* thresh_or_qids,
                               int nstripes, int nbins_or_nclass, int64_t nq, int64_t nq_pad, int min_with_prev,
-                              uint32_t* cap_dev, void* stream) {
+                              int sample_stride, uint32_t* cap_dev, void* stream) {
   if (ws == nullptr || slab_or_cls == nullptr || cap_dev == nullptr) CH_FAIL("null argument to ch_record_caps");
   if (source < 0 || source > 2) CH_FAIL("bad capacity source %d", source);
   if (source != 1 && thresh_or_qids == nullptr) CH_FAIL("capacity source %d needs thresholds / query ids", source);
   ChDeviceGuard guard(ws->device);
   record_caps_kernel<<<blocks_for(static_cast<long long>(nstripes) * nq_pad, 256), 256, 0,
                        static_cast<cudaStream_t>(stream)>>>(source, slab_or_cls, thresh_or_qids, nstripes,
-                                                            nbins_or_nclass, nq, nq_pad, min_with_prev, cap_dev);
+                                                            nbins_or_nclass, nq, nq_pad, min_with_prev, sample_stride,
+                                                            cap_dev);
   CH_LAUNCH_CHECK(ws);
   return 0;
 }
@@ -402,14 +432,15 @@ extern "C" int ch_record_caps(ch_ws* ws, int source, const uint32_t* slab_or_cls
 int ch_ws_scratch(ch_ws* ws, size_t bytes, void** out);  // api.cu
 
 extern "C" int ch_record_offsets(ch_ws* ws, const uint32_t* cap_dev, int nstripes, int64_t nq, int64_t nq_pad,
-                                 uint32_t* off_dev, uint64_t* total_host, void* stream) {
+                                 uint32_t* off_dev, uint64_t* total_host, const uint32_t* thresh_dev,
+                                 uint32_t* thresh_max_host, void* stream) {
   if (ws == nullptr || cap_dev == nullptr || off_dev == nullptr || total_host == nullptr)
     CH_FAIL("null argument to ch_record_offsets");
   (void)nq;
   ChDeviceGuard guard(ws->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   void* scratch = nullptr;
-  if (ch_ws_scratch(ws, static_cast<size_t>(nq_pad + 1) * 8, &scratch)) return 1;
+  if (ch_ws_scratch(ws, static_cast<size_t>(nq_pad + 2) * 8, &scratch)) return 1;
   unsigned long long* rowtot = static_cast<unsigned long long*>(scratch);
   row_totals_kernel<<<blocks_for(nq_pad, 256), 256, 0, st>>>(cap_dev, nstripes, nq_pad, rowtot);
   CH_LAUNCH_CHECK(ws);
@@ -417,10 +448,16 @@ extern "C" int ch_record_offsets(ch_ws* ws, const uint32_t* cap_dev, int nstripe
   CH_LAUNCH_CHECK(ws);
   record_offsets_kernel<<<blocks_for(nq_pad, 256), 256, 0, st>>>(cap_dev, rowtot, nstripes, nq_pad, off_dev);
   CH_LAUNCH_CHECK(ws);
-  unsigned long long total = 0;
-  CH_CUDA(cudaMemcpyAsync(&total, rowtot + nq_pad, 8, cudaMemcpyDeviceToHost, st));
+  if (thresh_dev != nullptr) {   // the same round trip also brings back max(thresh) (-> key_limit)
+    max_u32_kernel<<<1, 1024, 0, st>>>(thresh_dev, nq, rowtot + nq_pad + 1);
+    CH_LAUNCH_CHECK(ws);
+  }
+  unsigned long long both[2] = {0, 0};
+  CH_CUDA(cudaMemcpyAsync(both, rowtot + nq_pad, thresh_dev != nullptr ? 16 : 8, cudaMemcpyDeviceToHost, st));
   CH_CUDA(cudaStreamSynchronize(st));
+  const unsigned long long total = both[0];
   *total_host = total;
+  if (thresh_max_host != nullptr) *thresh_max_host = static_cast<uint32_t>(both[1]);
   if (total >= 0xffffffffull) CH_FAIL("%llu records exceed the 32-bit record index", total);
   return 0;
 }
@@ -454,15 +491,32 @@ extern "C" int ch_first_relevant(ch_ws* ws, const ch_final_args* a, uint32_t* fi
   return 0;
 }
 
+extern "C" int ch_check_counts(ch_ws* ws, const uint32_t* total_dev, int64_t nq, int64_t need, uint32_t* flags_dev,
+                               void* stream) {
+  if (ws == nullptr || total_dev == nullptr || flags_dev == nullptr) CH_FAIL("null argument to ch_check_counts");
+  ChDeviceGuard guard(ws->device);
+  check_counts_kernel<<<blocks_for(nq, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      total_dev, nq, static_cast<uint32_t>(need < 0 ? 0 : need), flags_dev);
+  CH_LAUNCH_CHECK(ws);
+  return 0;
+}
+
 extern "C" int ch_reduce_means(ch_ws* ws, const double* cols_dev, const uint32_t* total_rel_dev,
                                const uint32_t* first_rel_dev, int64_t nq, int nR, int nPR, const int64_t* pr_k,
-                               double* ap_out_dev, double* out_host, void* stream) {
+                               double* ap_out_dev, double* out_host, const uint32_t* flags_dev, uint32_t* flags_host,
+                               void* stream) {
   if (ws == nullptr || cols_dev == nullptr || out_host == nullptr) CH_FAIL("null argument to ch_reduce_means");
   if (nR < 0 || nR > CH_MAX_R || nPR < 0 || nPR > CH_MAX_PR) CH_FAIL("too many R / PRs entries");
   const int nout = nR + 2 * nPR;
-  if (nout == 0) return 0;
   ChDeviceGuard guard(ws->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // up to two status words of the caller (record overflow, verification) ride on the same host sync
+  if (flags_dev != nullptr && flags_host != nullptr)
+    CH_CUDA(cudaMemcpyAsync(flags_host, flags_dev, 8, cudaMemcpyDeviceToHost, st));
+  if (nout == 0) {
+    CH_CUDA(cudaStreamSynchronize(st));
+    return 0;
+  }
   void* scratch = nullptr;
   if (ch_ws_scratch(ws, (CH_MAX_PR + CH_MAX_R + 2 * CH_MAX_PR) * 8, &scratch)) return 1;
   long long* prk_dev = static_cast<long long*>(scratch);

@@ -91,7 +91,7 @@ class Evaluator:
         return out
 
     # ------------------------------------------------------------------ packing
-    def _pack_side(self, codes, labels, threshold, flags, nolabel, want_nz=False):
+    def _pack_side(self, codes, labels, threshold, flags, nolabel, want_nz=False, info=None):
         p = Packed()
         p.i8 = None
         p.n, p.nbit = int(codes.shape[0]), int(codes.shape[1])
@@ -104,7 +104,7 @@ class Evaluator:
         if labels is not None:
             if labels.shape[0] != p.n:
                 raise ValueError(f"{labels.shape[0]} label rows for {p.n} code rows")
-            p.ids, p.masks, p.info = self.b.pack_labels(labels, nolabel)
+            p.ids, p.masks, p.info = self.b.pack_labels(labels, nolabel, info)
             p.ncls = int(labels.shape[1]) if labels.dim() == 2 else 0
         return p
 
@@ -120,21 +120,27 @@ class Evaluator:
         if q_labels is not None and q_labels.dim() == 2 and db_labels.dim() == 2 and \
                 q_labels.shape[1] != db_labels.shape[1]:
             raise ValueError("query and gallery labels have different class counts")
-        flags = self.b.zeros((1,), torch.int32)
-        q = self._pack_side(q_codes, q_labels, threshold, flags, L.CH_QUERY_NOLABEL)
-        g = self._pack_side(db_codes, db_labels, threshold, flags, L.CH_GALLERY_NOLABEL)
-        # one small exchange: [flags, max positives per row (both sides), local gallery rows]
-        meta = self.b.zeros((4,), torch.int64)
-        meta[0] = flags[0] & 1           # some sign is 0 -> ternary keys
-        meta[3] = (flags[0] >> 1) & 1    # NaN seen
-        if q_labels is not None:
-            meta[1] = torch.maximum(q.info[0], g.info[0])
-            meta[2] = torch.maximum(q.info[1], g.info[1])
-        meta = self.comm.all_reduce_max(meta)
-        rows = self.b.zeros((self.comm.world,), torch.int64)
-        rows[self.comm.rank] = g.n
-        rows = _as_int_list(self.comm.all_reduce_sum(rows))
-        m = _as_int_list(meta)
+        # every small status word of the packing step lives in ONE tensor -> one device-to-host read:
+        # [0] flags (bit 0: some sign is 0, bit 1: NaN); [4:8] query label statistics; [8:12] gallery label statistics
+        meta = self.b.zeros((12,), torch.int32)
+        flags = meta[0:1]
+        q = self._pack_side(q_codes, q_labels, threshold, flags, L.CH_QUERY_NOLABEL, info=meta[4:8])
+        g = self._pack_side(db_codes, db_labels, threshold, flags, L.CH_GALLERY_NOLABEL, info=meta[8:12])
+        if self.comm.world == 1:
+            mm = _as_int_list(meta)
+            rows = [g.n]
+        else:
+            # ranks must agree: [zero flag, max positives per row, max class id + 1, NaN flag] by MAX, rows by SUM
+            red = self.b.zeros((4 + self.comm.world,), torch.int64)
+            red[0] = meta[0] & 1
+            red[1] = torch.maximum(meta[4], meta[8])
+            red[2] = torch.maximum(meta[5], meta[9])
+            red[3] = (meta[0] >> 1) & 1
+            red[4 + self.comm.rank] = g.n
+            red = _as_int_list(self.comm.all_reduce_max(red))
+            mm = [red[0] | (red[3] << 1), 0, 0, 0, red[1], red[2], 0, 0, 0, 0, 0, 0]
+            rows = red[4:]
+        m = [mm[0] & 1, max(mm[4], mm[8]), max(mm[5], mm[9]), (mm[0] >> 1) & 1]
         if m[3]:
             raise ValueError("codes contain NaN")
         ternary = bool(m[0])
@@ -186,13 +192,18 @@ class Evaluator:
         self.b.slab_totals(slab, nstripes, nbins, nq_pad, tot)
         return self.comm.all_gather(tot)           # (world, nbins, nq_pad)
 
-    def _alloc_records(self, cap, geo, nq):
+    def _alloc_records(self, cap, geo, nq, thresh=None, status=None):
+        """Offsets of the per-(stripe, query) record slices and the record buffer.  ``status`` u32[2]: [0] is raised
+        by the pass when a slice overflows.  With ``thresh`` the same host round trip also returns max(thresh)."""
         threads, nq_pad, nstripes, rps = geo
         off = self.b.empty((nstripes, nq_pad), torch.int32)
-        total = self.b.record_offsets(cap, nstripes, nq, nq_pad, off)
+        total, tmax = self.b.record_offsets(cap, nstripes, nq, nq_pad, off, thresh)
         self.stats["record_slots"] = total
-        return dict(off=off, cap=cap, cnt=self.b.zeros((nstripes, nq_pad), torch.int32),
-                    recs=self.b.empty((max(total, 1), 4), torch.int32), err=self.b.zeros((1,), torch.int32))
+        if status is None:
+            status = self.b.zeros((2,), torch.int32)
+        rec = dict(off=off, cap=cap, cnt=self.b.zeros((nstripes, nq_pad), torch.int32),
+                   recs=self.b.empty((max(total, 1), 4), torch.int32), err=status[0:1], status=status)
+        return (rec, tmax) if thresh is not None else rec
 
     def _check_records(self, rec):
         if int(rec["err"].cpu()[0]) != 0:
@@ -235,26 +246,44 @@ class Evaluator:
         self.stats.update(dict(ternary=ternary, label_mode=label_mode, geometry=geo, nbins=nbins,
                                ndb_total=ndb_total, world=comm.world))
         ctx = dict(q=q, g=g, geo=geo, ternary=ternary, label_mode=label_mode, lw=lw, nclass=nclass, nq=nq,
-                   nbins=nbins, rmax=rmax, rf=rf, pr_k=pr_k, ndb_total=ndb_total, stride=stride)
-        st = None
+                   nbins=nbins, rmax=rmax, rf=rf, pr_k=pr_k, ndb_total=ndb_total, stride=stride, rows=rows)
+        ctx.update(r_eff=r_eff, return_ap=return_ap)
         if full_ranking:
             self.stats["mode"] = "all"
-            st = self._pass_all(ctx)
+            res = self._finish(ctx, self._pass_all(ctx))
         else:
+            res = None
             if sampled:
                 self.stats["mode"] = "topR-sampled"
-                st = self._pass_topr_sampled(ctx)
-            if st is None:
+                res = self._finish(ctx, self._pass_topr_sampled(ctx))
+                if res[4][0] or res[4][1]:
+                    # a record slice overflowed or some query has fewer than R candidates under the sampled
+                    # threshold: redo the evaluation by the exact two-pass path
+                    self.stats["sample"].update(fallback=True, overflow=res[4][0], short=res[4][1])
+                    res = None
+            if res is None:
                 self.stats["mode"] = "topR"
-                st = self._pass_topr_exact(ctx)
-        rec = st["rec"]
+                res = self._finish(ctx, self._pass_topr_exact(ctx))
+        maps, recalls, precisions, ap, flags = res
+        if flags[0]:
+            raise RuntimeError("internal error: record buffer overflow")
+        if return_ap:
+            return maps, recalls, precisions, ap
+        return maps, recalls, precisions
 
+    def _finish(self, c, st):
+        """Records -> per-query sums (K4) -> all-reduce -> means.  The status words of the passes come back
+        with the results in the one final host sync."""
+        b, comm = self.b, self.comm
+        threads, nq_pad, nstripes, rps = c["geo"]
+        nq, rf, r_eff, pr_k = c["nq"], c["rf"], c["r_eff"], c["pr_k"]
+        rec = st["rec"]
         ncols = 2 * len(r_eff) + len(pr_k)
         cols = b.zeros((nq, max(ncols, 1)), torch.float64)
         f = dict(recs=rec["recs"], rec_off=rec["off"], rec_cnt=rec["cnt"], base0_all=st["base0_all"],
                  base0_rel=st["base0_rel"], sbase_all=st["sbase_all"], sbase_rel=st["sbase_rel"], first_rel=None,
                  partial=b.empty((nstripes, nq_pad, max(ncols, 1)), torch.float64), cols=cols,
-                 nq=nq, nq_pad=nq_pad, nstripes=nstripes, nbins=st.get("nbins", nbins), remove_first=bool(rf),
+                 nq=nq, nq_pad=nq_pad, nstripes=nstripes, nbins=st.get("nbins", c["nbins"]), remove_first=bool(rf),
                  r_eff=r_eff, pr_k=pr_k)
         first_rel = None
         if rf:
@@ -263,15 +292,14 @@ class Evaluator:
             first_rel = comm.all_reduce_max(first_rel)
             f["first_rel"] = first_rel
         b.finalize_records(f)
-        if not st.get("rec_checked"):
-            self._check_records(rec)
         cols = comm.all_reduce_sum(cols)
-        ap = b.empty((len(r_eff), nq), torch.float64) if return_ap else None
-        maps, recalls, precisions = b.reduce_means(cols, st["total_rel"] if pr_k else None, first_rel, nq, len(r_eff),
-                                                   pr_k, ap)
-        if return_ap:
-            return maps, recalls, precisions, ap
-        return maps, recalls, precisions
+        status = rec["status"]
+        if comm.world > 1:
+            status = comm.all_reduce_max(status)
+        ap = b.empty((len(r_eff), nq), torch.float64) if c["return_ap"] else None
+        maps, recalls, precisions, flags = b.reduce_means(cols, st["total_rel"] if pr_k else None, first_rel, nq,
+                                                          len(r_eff), pr_k, ap, status)
+        return maps, recalls, precisions, ap, flags
 
     def _class_counts(self, ctx):
         """(nstripes, nclass) per-stripe class histogram of the single-label gallery shard."""
@@ -373,9 +401,7 @@ class Evaluator:
         geo_s = (threads, nq_pad, nstripes, rps // stride)
         slab_s = b.zeros((nstripes, nbins, nq_pad), torch.int32)
         self._hist(q, sp, geo_s, ternary, L.CH_LAB_NONE, 0, slab_s, None)
-        ns_all = b.zeros((1,), torch.int64)
-        ns_all[0] = ns
-        ns_total = int(comm.all_reduce_sum(ns_all).cpu()[0]) if comm.world > 1 else ns
+        ns_total = sum((r + stride - 1) // stride for r in c["rows"])      # every rank samples the same way
         mu = need * ns_total / max(c["ndb_total"], 1)
         m = int(mu + 5.0 * mu ** 0.5 + 4.0) + 1
         thresh = b.empty((nq_pad,), torch.int32)
@@ -384,17 +410,13 @@ class Evaluator:
         b.scan_bases(tot_s, comm.world, comm.rank, nbins, nq, nq_pad, m, base_tmp, thresh, None)
         # ---- record capacities: scaled sample candidate counts, never more than the class counts ----
         cap = b.empty((nstripes, nq_pad), torch.int32)
-        b.record_caps(0, slab_s, thresh, nstripes, nbins, nq, nq_pad, False, cap)
-        # k sampled candidates in a stripe -> at most ~stride * (k + 6 sqrt(k + 1) + 10) real ones (Poisson tail);
-        # an overflow is detected by the kernel and sends the evaluation to the exact path
-        kf = cap.to(torch.float32)
-        cap.copy_(((kf + 6.0 * torch.sqrt(kf + 1.0) + 10.0) * float(stride)).to(torch.int32))
+        b.record_caps(0, slab_s, thresh, nstripes, nbins, nq, nq_pad, False, cap, sample_stride=stride)
         cls = self._class_counts(c)
         b.record_caps(2, cls, q.ids, nstripes, c["nclass"], nq, nq_pad, True, cap)
-        rec = self._alloc_records(cap, geo, nq)
+        rec, tmax = self._alloc_records(cap, geo, nq, thresh)      # one host sync: slots + max threshold
         del slab_s, base_tmp
         # ---- the one full pass; only keys <= max threshold can occur, all slabs / bases are that narrow ----
-        nbins = min(nbins, int(thresh[:nq].max().item()) + 1)
+        nbins = min(nbins, tmax + 1)
         slab_all = b.zeros((nstripes, nbins, nq_pad), torch.int32)
         slab_rel = b.zeros((nstripes, nbins, nq_pad), torch.int32)
         self._hist(q, g, geo, ternary, label_mode, lw, slab_all, slab_rel, thresh=thresh,
@@ -406,16 +428,10 @@ class Evaluator:
                                            self._local_totals(slab_rel, geo, nbins)]))
         b.scan_bases(tot[:, 0].contiguous(), comm.world, comm.rank, nbins, nq, nq_pad, -1, base0_all, None, found)
         b.scan_bases(tot[:, 1].contiguous(), comm.world, comm.rank, nbins, nq, nq_pad, -1, base0_rel, None, None)
-        # ---- verification (one flag, agreed over ranks) ----
-        bad = b.zeros((2,), torch.int32)
-        bad[0] = (found[:nq] < need).any().to(torch.int32)      # the sample threshold was too low for a query
-        bad[1] = (rec["err"][0] != 0).to(torch.int32)           # a record slice overflowed
-        bad = comm.all_reduce_max(bad) if comm.world > 1 else bad
-        bad = _as_int_list(bad)
-        self.stats["sample"] = dict(stride=stride, rows=ns_total, m=m, short=bad[0], overflow=bad[1])
-        if bad[0] or bad[1]:
-            self.stats["sample"]["fallback"] = True
-            return None
+        # ---- verification: status[1] is raised if some query has fewer than `need` candidates; it is read back
+        # together with the results (the finalisation below runs speculatively)
+        b.check_counts(found, nq, need, rec["status"][1:2])
+        self.stats["sample"] = dict(stride=stride, rows=ns_total, m=m, key_limit=nbins)
         b.slab_exscan(slab_all, nstripes, nbins, nq_pad)
         b.slab_exscan(slab_rel, nstripes, nbins, nq_pad)
         total_rel = b.zeros((nq_pad,), torch.int32)
@@ -427,7 +443,7 @@ class Evaluator:
             ok = (qid >= 0) & (qid < c["nclass"])
             total_rel[:nq] = torch.where(ok, cls_tot[qid.clamp(0, c["nclass"] - 1)], torch.zeros_like(cls_tot[:1]))
         return dict(rec=rec, base0_all=base0_all, base0_rel=base0_rel, sbase_all=slab_all, sbase_rel=slab_rel,
-                    total_rel=total_rel, rec_checked=True, nbins=nbins)
+                    total_rel=total_rel, nbins=nbins)
 
     def _local_totals(self, slab, geo, nbins):
         threads, nq_pad, nstripes, rps = geo

@@ -168,14 +168,17 @@ int ch_scan_bases(ch_ws* ws, const uint32_t* tot_all_dev, int world, int rank, i
  *   source 1: relevant    = sum_key slab_rel[s][key][q]                  (un-scanned slab)
  *   source 2: class count = cls_cnt[s][q_ids[q]]                          (single-label fast path)
  *   min_with_prev != 0 keeps min(existing cap, new cap).
+ *   sample_stride > 1: the counts come from a 1-in-stride row sample; they are scaled to a high-probability
+ *   bound stride * (k + 6 sqrt(k + 1) + 10) (an overflow is detected by the pass and reported in err_flag).
  */
 int ch_record_caps(ch_ws* ws, int source, const uint32_t* slab_or_cls, const uint32_t* thresh_or_qids,
                    int nstripes, int nbins_or_nclass, int64_t nq, int64_t nq_pad, int min_with_prev,
-                   uint32_t* cap_dev, void* stream);
+                   int sample_stride, uint32_t* cap_dev, void* stream);
 /* off[s][q] = start[q] + sum_{s' < s} cap[s'][q]; start = exclusive scan of per-query totals;
  * total_host receives the total number of record slots (the call synchronises the stream). */
 int ch_record_offsets(ch_ws* ws, const uint32_t* cap_dev, int nstripes, int64_t nq, int64_t nq_pad,
-                      uint32_t* off_dev, uint64_t* total_host, void* stream);
+                      uint32_t* off_dev, uint64_t* total_host, const uint32_t* thresh_dev /* or NULL */,
+                      uint32_t* thresh_max_host /* max(thresh[0..nq)) rides on the same sync */, void* stream);
 /* per-stripe class histogram of single-label gallery ids: cls (nstripes, nclass), zeroed by caller */
 int ch_class_counts(ch_ws* ws, const uint32_t* g_ids, int64_t ndb, int rows_per_stripe, int nclass,
                     uint32_t* cls_dev, void* stream);
@@ -206,7 +209,12 @@ int ch_first_relevant(ch_ws* ws, const ch_final_args* a, uint32_t* first_rel_dev
  * total_rel (nq_pad) = relevant items in the whole gallery per query (u32, already global). */
 int ch_reduce_means(ch_ws* ws, const double* cols_dev, const uint32_t* total_rel_dev,
                     const uint32_t* first_rel_dev, int64_t nq, int nR, int nPR, const int64_t* pr_k,
-                    double* ap_out_dev /* (nR, nq) or NULL */, double* out_host, void* stream);
+                    double* ap_out_dev /* (nR, nq) or NULL */, double* out_host,
+                    const uint32_t* flags_dev /* u32[2] or NULL */, uint32_t* flags_host /* same sync */,
+                    void* stream);
+/* flags_dev[0] |= 1 if some total_dev[q] < need  (verification of a sampled threshold) */
+int ch_check_counts(ch_ws* ws, const uint32_t* total_dev, int64_t nq, int64_t need, uint32_t* flags_dev,
+                    void* stream);
 
 /* ranked id list from CH_EMIT_CANDIDATES records: ids (nq, R) int64 / keys (nq, R) int32, pre-filled
  * by the caller (-1); every rank writes only its own rows' slots. */

@@ -79,7 +79,8 @@ class EmuBackend:
         self.launches += 1
         return pack(xn > 0), (pack(xn != 0) if want_nz else None)
 
-    def pack_labels(self, labels, nolabel):
+    def pack_labels(self, labels, nolabel, info=None):
+        info_out = info
         lab = labels.detach().cpu()
         n = lab.shape[0]
         rows = self.padded_rows(n)
@@ -100,14 +101,24 @@ class EmuBackend:
             info[1] = (ids[:n][has].max() + 1) if has.any() else 0
             info[2] = (~has).sum()
             return (torch.from_numpy(ids.view(np.int32)), torch.from_numpy(masks.view(np.int32).copy()),
-                    torch.from_numpy(info.view(np.int32)))
+                    self._info(info, info_out))
         v = lab.double().numpy()
         ok = v >= 0
         ids[:n][ok] = v[ok].astype(np.uint32)
         info[0] = 1 if ok.any() else 0
         info[1] = (ids[:n][ok].max() + 1) if ok.any() else 0
         info[2] = (~ok).sum()
-        return torch.from_numpy(ids.view(np.int32)), None, torch.from_numpy(info.view(np.int32))
+        return torch.from_numpy(ids.view(np.int32)), None, self._info(info, info_out)
+
+    @staticmethod
+    def _info(info, info_out):
+        t = torch.from_numpy(info.view(np.int32))
+        if info_out is None:
+            return t
+        info_out[0] = max(int(info_out[0]), int(t[0]))
+        info_out[1] = max(int(info_out[1]), int(t[1]))
+        info_out[2] = int(info_out[2]) + int(t[2])
+        return info_out
 
     # K2
     def geometry(self, nq, ndb, nbit, ternary, label_mode, lw):
@@ -209,7 +220,7 @@ class EmuBackend:
         if total is not None:
             _u32(total)[...] = cum_incl[-1].astype(np.uint32)
 
-    def record_caps(self, source, a0, a1, nstripes, nb, nq, nq_pad, min_with_prev, cap):
+    def record_caps(self, source, a0, a1, nstripes, nb, nq, nq_pad, min_with_prev, cap, sample_stride=0):
         self.launches += 1
         c = np.zeros((nstripes, nq_pad), dtype=np.uint32)
         if source in (0, 1):
@@ -222,18 +233,26 @@ class EmuBackend:
             for q in range(nq):
                 if ids[q] < nb:
                     c[:, q] = cls[:, ids[q]]
+        if sample_stride > 1:
+            k = c.astype(np.float32)
+            c = ((k + np.float32(6.0) * np.sqrt(k + np.float32(1.0)) + np.float32(10.0)) * np.float32(sample_stride)).astype(np.uint32)
         if min_with_prev:
             c = np.minimum(c, _u32(cap))
         _u32(cap)[...] = c
 
-    def record_offsets(self, cap, nstripes, nq, nq_pad, off):
+    def record_offsets(self, cap, nstripes, nq, nq_pad, off, thresh=None):
         self.launches += 1
         c = _u32(cap).astype(np.int64)
         rowtot = c.sum(0)
         start = np.cumsum(rowtot) - rowtot
         o = start[None, :] + np.cumsum(c, axis=0) - c
         _u32(off)[...] = o.astype(np.uint32)
-        return int(rowtot.sum())
+        return int(rowtot.sum()), (int(_u32(thresh)[:nq].max()) if thresh is not None else None)
+
+    def check_counts(self, total, nq, need, flags):
+        self.launches += 1
+        if (_u32(total)[:nq] < need).any():
+            _u32(flags)[0] |= 1
 
     # K4
     def _ranks(self, f, rec, s, q, need_rel):
@@ -286,7 +305,7 @@ class EmuBackend:
                     if is_rel and rank == 0:
                         o[q] = 1
 
-    def reduce_means(self, cols, total_rel, first_rel, nq, n_r, pr_k, ap_out=None):
+    def reduce_means(self, cols, total_rel, first_rel, nq, n_r, pr_k, ap_out=None, flags=None):
         self.launches += 1
         c = cols.numpy()
         maps, recalls, precisions = [], [], []
@@ -302,7 +321,8 @@ class EmuBackend:
                 tr = tr - _u32(first_rel)[:nq]
             recalls.append(float((hits / np.maximum(tr, 1.0)).mean()))
             precisions.append(float((hits / k).mean()))
-        return maps, recalls, precisions
+        fl = [int(_u32(flags)[0]), int(_u32(flags)[1])] if flags is not None else [0, 0]
+        return maps, recalls, precisions, fl
 
     def scatter_ranked(self, f, R, row_offset, ids, keys):
         self.launches += 1
