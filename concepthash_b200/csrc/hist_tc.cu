@@ -70,22 +70,16 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// 16 columns, no wait: lets the next chunk's TMEM read overlap the processing of the current one
-__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
-      "[%16];\n"
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-}
-// the registers are in/out operands of the wait so that no use of them can be scheduled above it
-__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-               :
-               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
 struct TcDev {
@@ -283,29 +277,29 @@ __global__ void __launch_bounds__(128 + 128 * QT, 1) hamming_select_tc_kernel(co
       mbar_wait(&bar_tfull[qt], static_cast<uint32_t>(k & 1));
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ewarp * 32) << 16) + static_cast<uint32_t>(qt) * kTileN;
-      // 16-column chunks, register double-buffered: the TMEM read of chunk c+1 is in flight while chunk c is
-      // examined.  (Columns past `rows` in the stripe's last tile hold stale data: they can only cause a
-      // spurious visit of the cold path, where the column bound is checked.)
-      auto examine = [&](const uint32_t (&r)[16], int c0) {
-        // hot path: is any of the 16 dots >= tau?  two sub-maxima of 8 (3-input max tree)
-        int mg[2];
+      for (int c0 = 0; c0 < rows; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr0 + c0, r);
+        // hot path: is any of the 32 dots >= tau?  (4 sub-maxima of 8, 3-input max tree; garbage columns past
+        // `rows` in the stripe's last tile can only cause a spurious visit of the cold path)
+        int mg[4];
 #pragma unroll
-        for (int g2 = 0; g2 < 2; ++g2) {
-          const int o = g2 * 8;
+        for (int g4 = 0; g4 < 4; ++g4) {
+          const int o = g4 * 8;
           int x = max(max(static_cast<int>(r[o]), static_cast<int>(r[o + 1])), static_cast<int>(r[o + 2]));
           x = max(max(x, static_cast<int>(r[o + 3])), static_cast<int>(r[o + 4]));
           x = max(max(x, static_cast<int>(r[o + 5])), static_cast<int>(r[o + 6]));
-          mg[g2] = max(x, static_cast<int>(r[o + 7]));
+          mg[g4] = max(x, static_cast<int>(r[o + 7]));
         }
-        if (max(mg[0], mg[1]) >= tau) {
+        if (max(max(mg[0], mg[1]), max(mg[2], mg[3])) >= tau) {
           // cold path (a few lanes): per 8-column group queue the candidates, then handle them in a rolled loop
 #pragma unroll
-          for (int g2 = 0; g2 < 2; ++g2) {
-            if (mg[g2] >= tau) {
+          for (int g4 = 0; g4 < 4; ++g4) {
+            if (mg[g4] >= tau) {
               uint32_t n = 0;
 #pragma unroll
               for (int jj = 0; jj < 8; ++jj) {
-                const int j = g2 * 8 + jj;
+                const int j = g4 * 8 + jj;
                 const int dot = static_cast<int>(r[j]);
                 if (dot >= tau) {
                   queue[n * kTileM] = static_cast<unsigned short>(((static_cast<uint32_t>(a.nbit - dot) >> 1) << 5) | j);
@@ -316,17 +310,6 @@ __global__ void __launch_bounds__(128 + 128 * QT, 1) hamming_select_tc_kernel(co
             }
           }
         }
-      };
-      uint32_t ra[16], rb[16];
-      tmem_ld16_issue(taddr0, ra);
-      tmem_ld_wait(ra);
-      for (int c0 = 0; c0 < rows; c0 += 32) {
-        tmem_ld16_issue(taddr0 + c0 + 16, rb);          // c0 + 16 < kTileN always
-        examine(ra, c0);
-        tmem_ld_wait(rb);
-        if (c0 + 32 < kTileN) tmem_ld16_issue(taddr0 + c0 + 32, ra);
-        if (c0 + 16 < rows) examine(rb, c0 + 16);
-        tmem_ld_wait(ra);
       }
       // this warp is done with the accumulator and with the stage's class ids
       tc_fence_before();
