@@ -444,12 +444,18 @@ int make_geometry(ch_ws* ws, long long nq, long long ndb, int nbit, bool tern, i
     if (hi > max_stripes) hi = max_stripes;
     if (hi > 4096) hi = 4096;
     if (lo > hi) lo = hi;
+    // every stripe costs a (nbins x nq_pad) slab plane that is zeroed, flushed, summed and scanned: take the
+    // SMALLEST stripe count whose last wave is >= 90 % full, else the best one in range
     long long best = lo;
     double best_eff = -1.0;
     for (long long s = lo; s <= hi; ++s) {
       const long long ctas = s * g->nqtiles;
       const long long waves = (ctas + slots - 1) / slots;
       const double eff = static_cast<double>(ctas) / static_cast<double>(waves * slots);
+      if (eff >= 0.90) {
+        best = s;
+        break;
+      }
       if (eff > best_eff + 1e-9) {
         best_eff = eff;
         best = s;
