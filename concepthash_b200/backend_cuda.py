@@ -50,8 +50,15 @@ class CudaBackend:
             pass
 
     # ---- plumbing ----
+    def begin(self):
+        """Called once per evaluation: caches the current torch stream handle (looked up ~20x per evaluation)."""
+        self._stream_cache = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        s = getattr(self, "_stream_cache", None)
+        if s is None:
+            return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return s
 
     def zeros(self, shape, dtype):
         return torch.zeros(shape, dtype=dtype, device=self.device)

@@ -216,6 +216,8 @@ class Evaluator:
 
         ``db_codes`` / ``db_labels`` are THIS rank's contiguous gallery row block; queries are replicated."""
         b, comm = self.b, self.comm
+        if hasattr(b, "begin"):
+            b.begin()
         r_list = [int(r) for r in R]
         pr_k = [int(k) for k in PRs]
         if len(r_list) == 0 and len(pr_k) == 0:
@@ -471,6 +473,8 @@ class Evaluator:
         ``L = min(R, gallery size)``, canonical order (distance, then global gallery row).
         keys = Hamming distance (binary codes) or 2 x distance (ternary)."""
         b, comm = self.b, self.comm
+        if hasattr(b, "begin"):
+            b.begin()
         q, g, ternary, _, _, _, rows = self._prepare(db_codes, None, q_codes, None, threshold)
         nq, nbit = q.n, q.nbit
         nbins = (2 * nbit if ternary else nbit) + 1
@@ -509,6 +513,8 @@ class Evaluator:
     # ------------------------------------------------------------------ dense distances (small)
     def hamming_matrix(self, a_codes, b_codes, threshold=0.0):
         """Dense key matrix (na, nb) int16 and the ternary flag (local, no collectives)."""
+        if hasattr(self.b, "begin"):
+            self.b.begin()
         flags = self.b.zeros((1,), torch.int32)
         pa = self._pack_side(a_codes, None, threshold, flags, 0, want_nz=True)
         pb = self._pack_side(b_codes, None, 0.0, flags, 0, want_nz=True)
