@@ -22,7 +22,8 @@ class HistArgs(C.Structure):
                                  "thresh", "rec_off", "rec_cap", "rec_cnt", "recs", "err_flag")] + \
                [(n, C.c_int64) for n in ("nq", "nq_pad", "ndb")] + \
                [(n, C.c_int32) for n in ("nbit", "ternary", "label_mode", "mask_words", "emit_mode",
-                                         "nstripes", "threads", "rows_per_stripe", "key_limit")]
+                                         "nstripes", "threads", "rows_per_stripe")] + \
+               [("row_base", C.c_int64), ("key_limit", C.c_int32)]
 
 
 class FinalArgs(C.Structure):

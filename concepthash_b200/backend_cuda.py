@@ -97,7 +97,7 @@ class CudaBackend:
             t = t.contiguous()
         return t, L.CH_MEM_HOST
 
-    def pack_sign(self, codes, threshold, flags, want_nz=True):
+    def pack_sign(self, codes, threshold, flags, want_nz=True, out=None):
         """codes (n, nbit) real -> (bits, nz) u32 (rows_pad, words); ``flags`` u32[1] is OR-ed.
         ``want_nz=False`` skips the non-zero plane (zeros are still detected in ``flags``) and lets
         contiguous inputs take the flat fast path."""
@@ -109,7 +109,11 @@ class CudaBackend:
             codes = codes.to(torch.float32)
         t, mem = self._src(codes)
         rows = self.padded_rows(n)
-        bits = self.empty((rows, words), torch.int32)
+        if out is not None:      # a row block of a larger packed array (streamed galleries); needs `rows` rows
+            assert not want_nz and out.shape[0] >= rows and out.shape[1] == words and out.is_contiguous()
+            bits = out
+        else:
+            bits = self.empty((rows, words), torch.int32)
         nz = self.empty((rows, words), torch.int32) if want_nz else None
         thr = float(threshold)
         if thr != 0.0:   # torch compares `codes.abs() < threshold` in the dtype of codes
@@ -157,6 +161,12 @@ class CudaBackend:
     def tc_code_bytes(self, nbit):
         return int(self.lib.ch_tc_code_bytes(int(nbit)))
 
+    def expand_i8_into(self, bits, nbit, out):
+        """the same, for a row block: ``bits`` (rows, words) -> ``out`` (rows, kb) views of larger arrays"""
+        assert bits.shape[0] % 8 == 0 and out.shape[0] >= bits.shape[0]
+        L.check(self.lib.ch_expand_i8(self.ws, _ptr(bits), int(bits.shape[0]), nbit, _ptr(out), self._stream()),
+                "ch_expand_i8")
+
     def expand_i8(self, bits, nbit, min_rows=0):
         """packed sign bits (rows_pad, words) -> +-1 int8 plane in the tiled operand order (rows, kb) int8;
         ``min_rows`` over-allocates (zero rows) so that whole 128-query tiles can be read."""
@@ -178,7 +188,7 @@ class CudaBackend:
 
     def _hist_args(self, *, q_bits, q_nz, g_bits, g_nz, q_lab, g_lab, slab_all, slab_rel, thresh, rec_off,
                    rec_cap, rec_cnt, recs, err_flag, nq, nq_pad, ndb, nbit, ternary, label_mode, mask_words,
-                   emit_mode, nstripes, threads, rows_per_stripe, key_limit=0):
+                   emit_mode, nstripes, threads, rows_per_stripe, key_limit=0, row_base=0):
         a = L.HistArgs()
         for k, v in dict(q_bits=q_bits, q_nz=q_nz if ternary else None, g_bits=g_bits,
                          g_nz=g_nz if ternary else None, q_lab=q_lab, g_lab=g_lab, slab_all=slab_all,
@@ -188,6 +198,7 @@ class CudaBackend:
         a.nq, a.nq_pad, a.ndb = nq, nq_pad, ndb
         a.nbit, a.ternary, a.label_mode, a.mask_words, a.emit_mode = nbit, int(ternary), label_mode, mask_words, emit_mode
         a.nstripes, a.threads, a.rows_per_stripe, a.key_limit = nstripes, threads, rows_per_stripe, int(key_limit)
+        a.row_base = int(row_base)
         return a
 
     def slab_totals(self, slab, nstripes, nbins, nq_pad, out):

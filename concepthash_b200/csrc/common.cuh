@@ -76,7 +76,7 @@ struct HistDev {
   const uint32_t* thresh;
   const uint32_t* rec_off; const uint32_t* rec_cap; uint32_t* rec_cnt; uint4* recs;
   uint32_t* err_flag;
-  long long nq, nq_pad, ndb;
+  long long nq, nq_pad, ndb, row_base;
   int nbit, nbins, lw, emit_mode;
   int nqtiles, rows_per_stripe, tile_rows, flush_tiles;
 };

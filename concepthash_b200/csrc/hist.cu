@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(256, (NW <= 2 && !TERN) ? 3 : 1) hamming_hist_
     const uint32_t* gm = s_mask + static_cast<size_t>(s) * TILE * lw;
     long long rows_ll = row_end - (row_begin + static_cast<long long>(k) * TILE);
     const int rows = rows_ll > TILE ? TILE : static_cast<int>(rows_ll);
-    const uint32_t shard_row0 = static_cast<uint32_t>(row_begin) + static_cast<uint32_t>(k) * TILE;
+    const uint32_t shard_row0 = static_cast<uint32_t>(a.row_base + row_begin) + static_cast<uint32_t>(k) * TILE;
 
     // register double-buffered walk over groups of G rows (prefetch may over-read into the kPad rows)
     const int nfull = rows - rows % G;
@@ -521,7 +521,7 @@ extern "C" int ch_hamming_hist(ch_ws* ws, const ch_hist_args* a, void* stream) {
   d.q_lab = a->q_lab; d.g_lab = a->g_lab; d.slab_all = a->slab_all; d.slab_rel = a->slab_rel;
   d.thresh = a->thresh; d.rec_off = a->rec_off; d.rec_cap = a->rec_cap; d.rec_cnt = a->rec_cnt;
   d.recs = static_cast<uint4*>(a->recs); d.err_flag = a->err_flag;
-  d.nq = a->nq; d.nq_pad = a->nq_pad; d.ndb = a->ndb;
+  d.nq = a->nq; d.nq_pad = a->nq_pad; d.ndb = a->ndb; d.row_base = a->row_base;
   d.nbit = a->nbit; d.nbins = (a->ternary ? 2 * a->nbit : a->nbit) + 1; d.lw = a->mask_words;
   // select pass: keys above max(thresh) never occur -> the caller may keep narrower slabs / histograms
   if (a->thresh != nullptr && a->key_limit > 0 && a->key_limit < d.nbins) d.nbins = a->key_limit;

@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(128 + 128 * QT, 1) hamming_select_tc_kernel(co
       const int s = k % kTcStages;
       long long rows_ll = row_end - (row_begin + static_cast<long long>(k) * kTileN);
       const int rows = rows_ll > kTileN ? kTileN : static_cast<int>(rows_ll);
-      const uint32_t shard_row0 = static_cast<uint32_t>(row_begin) + static_cast<uint32_t>(k) * kTileN;
+      const uint32_t shard_row0 = static_cast<uint32_t>(a.row_base + row_begin) + static_cast<uint32_t>(k) * kTileN;
       const uint32_t* labs = reinterpret_cast<const uint32_t*>(smem + S::offLab + s * S::kLab);
       mbar_wait(&bar_full[s], static_cast<uint32_t>((k / kTcStages) & 1));   // class ids of the stage are visible
       mbar_wait(&bar_tfull[qt], static_cast<uint32_t>(k & 1));
@@ -447,7 +447,7 @@ extern "C" int ch_hamming_select_tc(ch_ws* ws, const ch_hist_args* a, const int8
   h.q_lab = a->q_lab; h.g_lab = a->g_lab; h.slab_all = a->slab_all; h.slab_rel = a->slab_rel;
   h.thresh = a->thresh; h.rec_off = a->rec_off; h.rec_cap = a->rec_cap; h.rec_cnt = a->rec_cnt;
   h.recs = static_cast<uint4*>(a->recs); h.err_flag = a->err_flag;
-  h.nq = a->nq; h.nq_pad = a->nq_pad; h.ndb = a->ndb;
+  h.nq = a->nq; h.nq_pad = a->nq_pad; h.ndb = a->ndb; h.row_base = a->row_base;
   h.nbit = a->nbit; h.nbins = a->nbit + 1; h.lw = 0; h.emit_mode = a->emit_mode;
   // keys above max(thresh) never occur: with key_limit the slabs have key_limit rows per stripe
   if (a->key_limit > 0 && a->key_limit < h.nbins) h.nbins = a->key_limit;

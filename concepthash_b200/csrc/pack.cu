@@ -280,11 +280,13 @@ int pack_from_host(ch_ws* ws, const void* src, int dtype, int64_t n, int ncols, 
   const size_t es = elem_size(dtype);
   if (cs != 1 && ncols > 1) CH_FAIL("host buffers must have unit column stride");
   if (ch_ws_ensure_stage(ws)) return 1;
-  const size_t row_bytes = static_cast<size_t>(rs) * es;
-  if (row_bytes == 0) CH_FAIL("bad row stride");
-  int64_t chunk_rows = static_cast<int64_t>(ws->stage_bytes / row_bytes) / 64 * 64;
-  if (chunk_rows < 64) CH_FAIL("row of %zu bytes does not fit the staging buffer", row_bytes);
-  if (n == 0) return launch_pack(ws, nullptr, dtype, 0, rows_pad, 0, ncols, rs, cs, thr, words, out_pos, out_nz, flags, st);
+  const size_t row_bytes = static_cast<size_t>(rs) * es;          // host pitch
+  const size_t dense_bytes = static_cast<size_t>(ncols) * es;     // what a row really holds
+  if (row_bytes == 0 || rs < ncols) CH_FAIL("bad row stride");
+  // rows are staged DENSELY (a strided 2-D DMA drops the gaps of column slices / row-sampled views)
+  int64_t chunk_rows = static_cast<int64_t>(ws->stage_bytes / dense_bytes) / 64 * 64;
+  if (chunk_rows < 64) CH_FAIL("row of %zu bytes does not fit the staging buffer", dense_bytes);
+  if (n == 0) return launch_pack(ws, nullptr, dtype, 0, rows_pad, 0, ncols, ncols, 1, thr, words, out_pos, out_nz, flags, st);
   int c = 0;
   for (int64_t r0 = 0; r0 < n; r0 += chunk_rows, ++c) {
     const int b = c & 1;
@@ -292,13 +294,16 @@ int pack_from_host(ch_ws* ws, const void* src, int dtype, int64_t n, int ncols, 
     const bool last = r1 == n;
     // the staging buffer may still be read by the pack kernel of chunk c - 2 (or of an earlier call)
     CH_CUDA(cudaStreamWaitEvent(ws->copy_stream, ws->ev_consumed[b], 0));
-    // last row of a strided buffer may be shorter than rs elements: copy only what exists
-    const size_t bytes = static_cast<size_t>(r1 - r0 - 1) * row_bytes + static_cast<size_t>(ncols) * es;
-    CH_CUDA(cudaMemcpyAsync(ws->stage[b], static_cast<const char*>(src) + static_cast<size_t>(r0) * row_bytes, bytes,
-                            cudaMemcpyHostToDevice, ws->copy_stream));
+    const char* src_rows = static_cast<const char*>(src) + static_cast<size_t>(r0) * row_bytes;
+    if (rs == ncols)
+      CH_CUDA(cudaMemcpyAsync(ws->stage[b], src_rows, static_cast<size_t>(r1 - r0) * dense_bytes,
+                              cudaMemcpyHostToDevice, ws->copy_stream));
+    else
+      CH_CUDA(cudaMemcpy2DAsync(ws->stage[b], dense_bytes, src_rows, row_bytes, dense_bytes,
+                                static_cast<size_t>(r1 - r0), cudaMemcpyHostToDevice, ws->copy_stream));
     CH_CUDA(cudaEventRecord(ws->ev_copied[b], ws->copy_stream));
     CH_CUDA(cudaStreamWaitEvent(st, ws->ev_copied[b], 0));
-    if (launch_pack(ws, ws->stage[b], dtype, r0, last ? rows_pad : r1, n, ncols, rs, cs, thr, words, out_pos, out_nz,
+    if (launch_pack(ws, ws->stage[b], dtype, r0, last ? rows_pad : r1, n, ncols, ncols, 1, thr, words, out_pos, out_nz,
                     flags, st))
       return 1;
     CH_CUDA(cudaEventRecord(ws->ev_consumed[b], st));

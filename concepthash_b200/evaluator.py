@@ -76,6 +76,9 @@ class Evaluator:
         self.sample_stride = 16            # top-R: 1-in-16 row sample picks the threshold (0/1 = exact two-pass)
         self.sample_min_rows = 200_000     # below this the two-pass path is cheap anyway
         self.sample_min_ratio = 64         # ... and the sample must still hold ~R/stride*... rows: need ndb >= ratio * R
+        self.stream_host_gallery = True    # host-resident gallery: overlap its H2D copy with the select pass
+        self.stream_min_rows = 200_000
+        self.stream_chunks = 4
         self.use_tensor_cores = True       # select pass on tcgen05 (int8 +-1 codes) when the shape allows it
         self.profile = False               # bench: bracket the kernels with CUDA events on the launch stream
         self.events = []                   # (kind, work units, start event, end event)
@@ -91,14 +94,19 @@ class Evaluator:
         return out
 
     # ------------------------------------------------------------------ packing
-    def _pack_side(self, codes, labels, threshold, flags, nolabel, want_nz=False, info=None):
+    def _pack_codes(self, p, codes, threshold, flags, want_nz=False):
+        pack_bytes = p.n * p.nbit * codes.element_size() + p.n * p.nbit // 8
+        kind = "pack_dev" if codes.is_cuda else "pack_host"
+        p.bits, p.nz = self._timed(kind, pack_bytes, lambda: self.b.pack_sign(codes, threshold, flags, want_nz))
+
+    def _pack_side(self, codes, labels, threshold, flags, nolabel, want_nz=False, info=None, defer_codes=False):
         p = Packed()
         p.i8 = None
         p.n, p.nbit = int(codes.shape[0]), int(codes.shape[1])
         # algorithmic bytes of K1: the real-valued codes read once + the packed bits written once
-        pack_bytes = p.n * p.nbit * codes.element_size() + p.n * p.nbit // 8
-        kind = "pack_dev" if codes.is_cuda else "pack_host"
-        p.bits, p.nz = self._timed(kind, pack_bytes, lambda: self.b.pack_sign(codes, threshold, flags, want_nz))
+        p.bits = p.nz = None
+        if not defer_codes:
+            self._pack_codes(p, codes, threshold, flags, want_nz)
         p.ids = p.masks = p.info = None
         p.ncls = 0
         if labels is not None:
@@ -108,7 +116,7 @@ class Evaluator:
             p.ncls = int(labels.shape[1]) if labels.dim() == 2 else 0
         return p
 
-    def _prepare(self, db_codes, db_labels, q_codes, q_labels, threshold):
+    def _prepare(self, db_codes, db_labels, q_codes, q_labels, threshold, allow_defer=False):
         if q_codes.dim() != 2 or db_codes.dim() != 2:
             raise ValueError("codes must be 2-D (N, nbit)")
         if q_codes.shape[1] != db_codes.shape[1]:
@@ -125,7 +133,12 @@ class Evaluator:
         meta = self.b.zeros((12,), torch.int32)
         flags = meta[0:1]
         q = self._pack_side(q_codes, q_labels, threshold, flags, L.CH_QUERY_NOLABEL, info=meta[4:8])
-        g = self._pack_side(db_codes, db_labels, threshold, flags, L.CH_GALLERY_NOLABEL, info=meta[8:12])
+        # a large HOST gallery is not copied yet: the top-R path streams it in row blocks behind the select pass
+        defer = (allow_defer and self.stream_host_gallery and not db_codes.is_cuda and threshold == 0 and
+                 db_labels is not None and db_codes.shape[0] >= self.stream_min_rows and
+                 hasattr(self.b, "hamming_select_tc") and self.b.tc_code_bytes(int(db_codes.shape[1])) > 0)
+        g = self._pack_side(db_codes, db_labels, threshold, flags, L.CH_GALLERY_NOLABEL, info=meta[8:12],
+                            defer_codes=defer)
         if self.comm.world == 1:
             mm = _as_int_list(meta)
             rows = [g.n]
@@ -147,7 +160,7 @@ class Evaluator:
         if ternary:
             # rare: some sign is exactly 0 -> pack again, this time with the non-zero bit-plane
             _, q.nz = self.b.pack_sign(q_codes, threshold, flags, True)
-            _, g.nz = self.b.pack_sign(db_codes, threshold, flags, True)
+            g.bits, g.nz = self.b.pack_sign(db_codes, threshold, flags, True)
         label_mode, lw, nclass = L.CH_LAB_NONE, 0, 0
         if q_labels is not None:
             if m[1] <= 1:
@@ -224,7 +237,8 @@ class Evaluator:
             return [], [], []
         if any(r == 0 or r < -1 for r in r_list) or any(k <= 0 for k in pr_k):
             raise ValueError("R must be -1 or positive; PRs must be positive")
-        q, g, ternary, label_mode, lw, nclass, rows = self._prepare(db_codes, db_labels, q_codes, q_labels, threshold)
+        q, g, ternary, label_mode, lw, nclass, rows = self._prepare(db_codes, db_labels, q_codes, q_labels, threshold,
+                                                                    allow_defer=True)
         if label_mode == L.CH_LAB_NONE:
             raise ValueError("labels are required")
         nq, nbit = q.n, q.nbit
@@ -243,18 +257,50 @@ class Evaluator:
         stride = self.sample_stride
         if sampled and stride > 1 and (rmax + rf) * 5000 <= ndb_total:
             stride *= 4
-        geo = self._agree_geometry(b.geometry(nq, g.n, nbit, ternary, label_mode, lw), g.n, stride if sampled else 1)
+        geo = b.geometry(nq, g.n, nbit, ternary, label_mode, lw)
+        # host-resident gallery on the sampled top-R path: it is streamed in row blocks behind the select pass
+        streamed = (g.bits is None and sampled and not ternary and label_mode == L.CH_LAB_ID and geo[1] % 128 == 0
+                    and self.use_tensor_cores)
+        min_stripes = 0
+        if streamed:
+            per = max(1, -(-148 // max(1, -(-geo[1] // 512))))      # stripes per launch: >= one CTA per SM
+            min_stripes = per * 2 * self.stream_chunks
+        geo = self._agree_geometry(geo, g.n, stride if sampled else 1, min_stripes)
         threads, nq_pad, nstripes, rps = geo
         self.stats.update(dict(ternary=ternary, label_mode=label_mode, geometry=geo, nbins=nbins,
                                ndb_total=ndb_total, world=comm.world))
         ctx = dict(q=q, g=g, geo=geo, ternary=ternary, label_mode=label_mode, lw=lw, nclass=nclass, nq=nq,
                    nbins=nbins, rmax=rmax, rf=rf, pr_k=pr_k, ndb_total=ndb_total, stride=stride, rows=rows)
-        ctx.update(r_eff=r_eff, return_ap=return_ap)
-        if full_ranking:
+        ctx.update(r_eff=r_eff, return_ap=return_ap, db_codes=db_codes, threshold=threshold)
+        streamed = streamed and nstripes >= 2
+        res = None
+        if streamed:
+            self.stats["mode"] = "topR-sampled-streamed"
+            res = self._finish(ctx, self._pass_topr_sampled(ctx, streamed=True))
+            if res[4][0] or res[4][1]:
+                self.stats["sample"].update(fallback=True, overflow=res[4][0], short=res[4][1])
+                res, sampled = None, False          # the same sample would fail again: go exact
+        if g.bits is None or res is None and streamed:
+            # gallery codes were deferred but the streamed path is not applicable (or gave up): pack them now
+            fl = b.zeros((1,), torch.int32)
+            self._pack_codes(g, db_codes, threshold, fl)
+            fl = int(comm.all_reduce_max(fl).cpu()[0]) if comm.world > 1 else int(fl.cpu()[0])
+            if fl & 2:
+                raise ValueError("codes contain NaN")
+            if fl & 1:
+                # zeros in the gallery: ternary keys after all -> start over on the regular path
+                saved, self.stream_host_gallery = self.stream_host_gallery, False
+                try:
+                    return self.evaluate(db_codes, db_labels, q_codes, q_labels, R, threshold, PRs,
+                                         remove_first_retrieved, return_ap)
+                finally:
+                    self.stream_host_gallery = saved
+        if res is not None:
+            pass
+        elif full_ranking:
             self.stats["mode"] = "all"
             res = self._finish(ctx, self._pass_all(ctx))
         else:
-            res = None
             if sampled:
                 self.stats["mode"] = "topR-sampled"
                 res = self._finish(ctx, self._pass_topr_sampled(ctx))
@@ -377,7 +423,44 @@ class Evaluator:
         return dict(rec=rec, base0_all=base0_all, base0_rel=base0_rel, sbase_all=slab_all, sbase_rel=slab_rel,
                     total_rel=total_rel)
 
-    def _pass_topr_sampled(self, c):
+    def _select_streamed(self, c, rec, thresh, slab_all, slab_rel, nbins):
+        """Select pass over a HOST-resident gallery, one block of stripes at a time: the H2D copy + sign/bit-pack +
+        int8 expansion of block i+1 run (copy engine / tiny kernels) while the tensor-core select kernel works
+        on block i.  Outputs are exactly those of one whole-shard launch (slabs per stripe, records with shard
+        row ids)."""
+        b, q, g, geo = self.b, c["q"], c["g"], c["geo"]
+        threads, nq_pad, nstripes, rps = geo
+        db_codes, nq = c["db_codes"], c["nq"]
+        words, kb = q.bits.shape[1], b.tc_code_bytes(q.nbit)
+        rows_pad = b.padded_rows(g.n)
+        g.bits = b.empty((rows_pad, words), torch.int32)
+        g.i8 = b.empty((rows_pad, kb), torch.int8)
+        if q.i8 is None:
+            q.i8 = self._timed("expand_i8", 0, lambda: b.expand_i8(q.bits, q.nbit, nq_pad))
+        flags = rec["status"][1:2]          # a zero / NaN in the gallery invalidates this path -> fallback
+        per = max(1, -(-148 // max(1, -(-nq_pad // 512))))          # stripes per launch: >= one CTA per SM
+        per = max(per, -(-nstripes // max(1, self.stream_chunks * 4)))
+        for s0 in range(0, nstripes, per):
+            s1 = min(nstripes, s0 + per)
+            r0, r1 = s0 * rps, min(g.n, s1 * rps)
+            if r1 <= r0:
+                break
+            last = r1 == g.n
+            nrow8 = (rows_pad - r0) if last else (r1 - r0)
+            blk = db_codes[r0:r1]
+            nbytes = (r1 - r0) * q.nbit * db_codes.element_size()
+            self._timed("pack_host", nbytes, lambda: b.pack_sign(blk, 0.0, flags, False, out=g.bits[r0:]))
+            self._timed("expand_i8", 0, lambda: b.expand_i8_into(g.bits[r0:r0 + nrow8], q.nbit, g.i8[r0:]))
+            args = dict(q_bits=q.bits, q_nz=None, g_bits=g.bits[r0:], g_nz=None, q_lab=q.ids, g_lab=g.ids[r0:],
+                        slab_all=slab_all[s0:], slab_rel=slab_rel[s0:], thresh=thresh, rec_off=rec["off"][s0:],
+                        rec_cap=rec["cap"][s0:], rec_cnt=rec["cnt"][s0:], recs=rec["recs"], err_flag=rec["err"],
+                        nq=nq, nq_pad=nq_pad, ndb=r1 - r0, nbit=q.nbit, ternary=False, label_mode=L.CH_LAB_ID,
+                        mask_words=0, emit_mode=L.CH_EMIT_RELEVANT, nstripes=s1 - s0, threads=threads,
+                        rows_per_stripe=rps, key_limit=nbins, row_base=r0)
+            self._timed("hist_select_tc", nq * (r1 - r0), lambda: b.hamming_select_tc(q.i8, g.i8[r0:], **args))
+        self.stats["select_kernel"] = "tcgen05"
+
+    def _pass_topr_sampled(self, c, streamed=False):
         """Top-R in ONE full pass.  A 1-in-``sample_stride`` row sample of the gallery is histogrammed first; from
         it a per-query threshold key t^ is chosen high enough that #(key <= t^) >= R with overwhelming
         probability.  The full pass then counts / matches / records only the pairs with key <= t^.  The result
@@ -390,12 +473,19 @@ class Evaluator:
         stride = c["stride"]
         # ---- the sample: every stride-th row of the local shard, same stripes (rps is a multiple of stride) ----
         ns = (g.n + stride - 1) // stride
+        status = b.zeros((2,), torch.int32)
         sp = Packed()
         sp.i8 = None
         sp.n, sp.nbit = ns, g.nbit
-        sp.bits = b.zeros((b.padded_rows(ns), g.bits.shape[1]), torch.int32)
-        sp.bits[:ns] = g.bits[:g.n][::stride]
         sp.nz = None
+        if streamed:
+            # the gallery is still on the host: copy just the sampled rows (strided 2-D DMA) and pack them
+            view = c["db_codes"][::stride]
+            sp.bits, _ = self._timed("pack_host", ns * g.nbit * view.element_size(),
+                                     lambda: b.pack_sign(view, 0.0, status[1:2], False))
+        else:
+            sp.bits = b.zeros((b.padded_rows(ns), g.bits.shape[1]), torch.int32)
+            sp.bits[:ns] = g.bits[:g.n][::stride]
         if ternary:
             sp.nz = b.zeros((b.padded_rows(ns), g.bits.shape[1]), torch.int32)
             sp.nz[:ns] = g.nz[:g.n][::stride]
@@ -415,14 +505,17 @@ class Evaluator:
         b.record_caps(0, slab_s, thresh, nstripes, nbins, nq, nq_pad, False, cap, sample_stride=stride)
         cls = self._class_counts(c)
         b.record_caps(2, cls, q.ids, nstripes, c["nclass"], nq, nq_pad, True, cap)
-        rec, tmax = self._alloc_records(cap, geo, nq, thresh)      # one host sync: slots + max threshold
+        rec, tmax = self._alloc_records(cap, geo, nq, thresh, status)   # one host sync: slots + max threshold
         del slab_s, base_tmp
         # ---- the one full pass; only keys <= max threshold can occur, all slabs / bases are that narrow ----
         nbins = min(nbins, tmax + 1)
         slab_all = b.zeros((nstripes, nbins, nq_pad), torch.int32)
         slab_rel = b.zeros((nstripes, nbins, nq_pad), torch.int32)
-        self._hist(q, g, geo, ternary, label_mode, lw, slab_all, slab_rel, thresh=thresh,
-                   emit=L.CH_EMIT_RELEVANT, rec=rec, key_limit=nbins)
+        if streamed:
+            self._select_streamed(c, rec, thresh, slab_all, slab_rel, nbins)
+        else:
+            self._hist(q, g, geo, ternary, label_mode, lw, slab_all, slab_rel, thresh=thresh,
+                       emit=L.CH_EMIT_RELEVANT, rec=rec, key_limit=nbins)
         base0_all = b.empty((nbins, nq_pad), torch.int32)
         base0_rel = b.empty((nbins, nq_pad), torch.int32)
         found = b.zeros((nq_pad,), torch.int32)
@@ -453,15 +546,19 @@ class Evaluator:
         self.b.slab_totals(slab, nstripes, nbins, nq_pad, tot)
         return tot
 
-    def _agree_geometry(self, geo, ndb=None, stride=1):
+    def _agree_geometry(self, geo, ndb=None, stride=1, min_stripes=0):
         """threads / nq_pad depend only on (nq, nbins) and are identical on all ranks; the stripe layout is
         per rank (shards may differ in length), so nothing has to be exchanged.  With row sampling the stripe
         length is rounded up so that the sample of a stripe is itself a legal stripe."""
         threads, nq_pad, nstripes, rps = geo
         if self.stripe_rows_override and ndb is not None:
             rps = int(self.stripe_rows_override)
+        align = getattr(self.b, "stripe_align", 256)
+        if min_stripes > nstripes and ndb is not None:
+            rps = max(align, -(-ndb // min_stripes))
+            rps = (rps + align - 1) // align * align
         if stride > 1:
-            unit = stride * getattr(self.b, "stripe_align", 256)
+            unit = stride * align
             rps = (rps + unit - 1) // unit * unit
         if ndb is not None:
             nstripes = max(1, (ndb + rps - 1) // rps)

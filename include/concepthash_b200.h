@@ -123,6 +123,8 @@ typedef struct ch_hist_args {
   int64_t nq, nq_pad, ndb;             /* ndb = rows of the local shard */
   int32_t nbit, ternary, label_mode, mask_words, emit_mode;
   int32_t nstripes, threads, rows_per_stripe;   /* geometry from ch_hist_geometry */
+  int64_t row_base;        /* added to the local row index stored in records (streamed galleries: the shard is
+                              processed in row blocks, one call per block) */
   int32_t key_limit;       /* select pass only: max(thresh) + 1 if the caller knows it, else 0.  When set, keys >= key_limit
                               cannot occur and the slabs are (nstripes, key_limit, nq_pad) instead of (.., nbins, ..) */
 } ch_hist_args;

@@ -145,7 +145,7 @@ class EmuBackend:
 
     def hamming_hist(self, *, q_bits, q_nz, g_bits, g_nz, q_lab, g_lab, slab_all, slab_rel, thresh, rec_off,
                      rec_cap, rec_cnt, recs, err_flag, nq, nq_pad, ndb, nbit, ternary, label_mode, mask_words,
-                     emit_mode, nstripes, threads, rows_per_stripe, key_limit=0):
+                     emit_mode, nstripes, threads, rows_per_stripe, key_limit=0, row_base=0):
         self.launches += 1
         keys = self._keys(q_bits, q_nz, g_bits, g_nz, nq, ndb, nbit, ternary)
         rel = self._rel(q_lab, g_lab, nq, ndb, label_mode, mask_words)
@@ -170,7 +170,7 @@ class EmuBackend:
                         run_rel[k] = pr + 1
                     if emit_mode == CH_EMIT_CANDIDATES or (emit_mode == CH_EMIT_RELEVANT and r):
                         if n_rec < cap[s, q]:
-                            rc[off[s, q] + n_rec] = (k | (0x80000000 if r else 0), pa, pr, j)
+                            rc[off[s, q] + n_rec] = (k | (0x80000000 if r else 0), pa, pr, j + row_base)
                         else:
                             _u32(err_flag)[0] |= 1
                         n_rec += 1

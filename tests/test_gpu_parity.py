@@ -385,3 +385,26 @@ def test_tensor_core_select_equals_popc_select(H, nbit):
     om, orec, oprec = mo.calculate_mAP(d.cpu(), dl.cpu(), q[sub].cpu(), ql[sub].cpu(), [50, 500], PRs=[1, 5, 10])
     m, rec, prec = H.calculate_mAP(d, dl, q[sub], ql[sub], [50, 500], PRs=[1, 5, 10])
     assert np.allclose(m, om, atol=TOL) and np.allclose(rec, orec, atol=TOL) and np.allclose(prec, oprec, atol=TOL)
+
+
+def test_streamed_host_gallery_equals_resident(H):
+    """A large gallery passed as a HOST tensor is streamed in row blocks behind the select pass; the answer must
+    be bit-identical to the device-resident run, and a gallery with exact zeros must fall back cleanly."""
+    ev = H.get_evaluator()
+    for nbit, nq, ndb in [(64, 1500, 420_000), (128, 900, 300_123)]:
+        d, dl, q, ql, ncls = synth.make_random_case(nq, ndb, nbit, 40, p=0.30, seed=nbit + 1, device="cuda")
+        ref = ev.evaluate(d, dl, q, ql, [100, 1000], 0.0, [1, 5, 10], False, return_ap=True)
+        assert ev.stats["mode"] == "topR-sampled"
+        for host in (d.cpu(), d.cpu().pin_memory()):
+            out = ev.evaluate(host, dl.cpu(), q.cpu(), ql.cpu(), [100, 1000], 0.0, [1, 5, 10], False, return_ap=True)
+            assert ev.stats["mode"] == "topR-sampled-streamed", ev.stats
+            assert out[0] == ref[0] and out[1] == ref[1] and out[2] == ref[2] and torch.equal(out[3], ref[3])
+    # zeros in the gallery -> ternary keys: the streamed attempt must notice and restart on the regular path
+    dz = d.cpu().clone()
+    dz[::1000, 5] = 0.0
+    m, rec, prec = H.calculate_mAP(dz, dl.cpu(), q.cpu(), ql.cpu(), 200, PRs=[1, 10])
+    assert ev.stats["ternary"] and not ev.stats["mode"].endswith("streamed")
+    sub = slice(0, 30)
+    om, orec, oprec = mo.calculate_mAP(dz, dl.cpu(), q.cpu()[sub], ql.cpu()[sub], 200, PRs=[1, 10])
+    m2, rec2, prec2 = H.calculate_mAP(dz, dl.cpu(), q.cpu()[sub], ql.cpu()[sub], 200, PRs=[1, 10])
+    assert abs(m2 - om) < TOL and np.allclose(rec2, orec, atol=TOL) and np.allclose(prec2, oprec, atol=TOL)
