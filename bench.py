@@ -313,11 +313,14 @@ def main():
     if not args.no_e2e:
         hd, hdl, hq, hql = (t.cpu().pin_memory() for t in (d, dl, q, ql))
         step_host = lambda: hashing.calculate_mAP(hd, hdl, hq, hql, w["R"], group=group)
-        ms_e, out_e, _, _, _ = run(step_host, max(2, args.steps // 2), 1)
+        ms_e, out_e, _, _, ev_e = run(step_host, max(2, args.steps // 2), 1)
+        kinds_e = {}
+        for kind, units, a, b in ev_e:
+            kinds_e[kind] = kinds_e.get(kind, 0.0) + a.elapsed_time(b) / max(2, args.steps // 2)
         h2d = sum(t.numel() * t.element_size() for t in (hd, hdl, hq, hql))
         e2e = {"value": total_pairs * unit64 / (ms_e * 1e-3), "unit": "64-bit comparisons/s",
                "ms_per_step": ms_e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 * len(r_list) + 64,
-               "mAP": out_e[0]}
+               "mAP": out_e[0], "mode": ev.stats.get("mode"), "kernel_ms_per_step": kinds_e}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

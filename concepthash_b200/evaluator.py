@@ -263,8 +263,7 @@ class Evaluator:
                     and self.use_tensor_cores)
         min_stripes = 0
         if streamed:
-            per = max(1, -(-148 // max(1, -(-geo[1] // 512))))      # stripes per launch: >= one CTA per SM
-            min_stripes = per * 2 * self.stream_chunks
+            min_stripes = self._stream_per(geo[1]) * 2 * self.stream_chunks
         geo = self._agree_geometry(geo, g.n, stride if sampled else 1, min_stripes)
         threads, nq_pad, nstripes, rps = geo
         self.stats.update(dict(ternary=ternary, label_mode=label_mode, geometry=geo, nbins=nbins,
@@ -423,6 +422,19 @@ class Evaluator:
         return dict(rec=rec, base0_all=base0_all, base0_rel=base0_rel, sbase_all=slab_all, sbase_rel=slab_rel,
                     total_rel=total_rel)
 
+    def _stream_per(self, nq_pad):
+        """Stripes per streamed launch: the launch has per x ceil(nq_pad / 512) CTAs (4 query tiles each), one per
+        SM; pick the smallest per <= 8 that fills its last wave best."""
+        sms = getattr(self.b, "sm_count", 148)
+        groups = max(1, -(-nq_pad // 512))
+        best, best_eff = 1, -1.0
+        for per in range(1, 9):
+            ctas = per * groups
+            eff = ctas / (-(-ctas // sms) * sms)
+            if eff > best_eff + 0.02:
+                best, best_eff = per, eff
+        return best
+
     def _select_streamed(self, c, rec, thresh, slab_all, slab_rel, nbins):
         """Select pass over a HOST-resident gallery, one block of stripes at a time: the H2D copy + sign/bit-pack +
         int8 expansion of block i+1 run (copy engine / tiny kernels) while the tensor-core select kernel works
@@ -438,8 +450,7 @@ class Evaluator:
         if q.i8 is None:
             q.i8 = self._timed("expand_i8", 0, lambda: b.expand_i8(q.bits, q.nbit, nq_pad))
         flags = rec["status"][1:2]          # a zero / NaN in the gallery invalidates this path -> fallback
-        per = max(1, -(-148 // max(1, -(-nq_pad // 512))))          # stripes per launch: >= one CTA per SM
-        per = max(per, -(-nstripes // max(1, self.stream_chunks * 4)))
+        per = self._stream_per(nq_pad)
         for s0 in range(0, nstripes, per):
             s1 = min(nstripes, s0 + per)
             r0, r1 = s0 * rps, min(g.n, s1 * rps)
