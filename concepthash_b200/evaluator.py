@@ -144,15 +144,18 @@ class Evaluator:
             rows = [g.n]
         else:
             # ranks must agree: [zero flag, max positives per row, max class id + 1, NaN flag] by MAX, rows by SUM
-            red = self.b.zeros((4 + self.comm.world,), torch.int64)
+            red = self.b.zeros((5 + self.comm.world,), torch.int64)
             red[0] = meta[0] & 1
             red[1] = torch.maximum(meta[4], meta[8])
             red[2] = torch.maximum(meta[5], meta[9])
             red[3] = (meta[0] >> 1) & 1
-            red[4 + self.comm.rank] = g.n
+            red[4] = 0 if g.bits is None else 1          # some rank already packed its gallery: nobody streams
+            red[5 + self.comm.rank] = g.n
             red = _as_int_list(self.comm.all_reduce_max(red))
             mm = [red[0] | (red[3] << 1), 0, 0, 0, red[1], red[2], 0, 0, 0, 0, 0, 0]
-            rows = red[4:]
+            rows = red[5:]
+            if red[4] and g.bits is None:
+                self._pack_codes(g, db_codes, threshold, flags)      # (zeros / NaN are re-checked by the caller)
         m = [mm[0] & 1, max(mm[4], mm[8]), max(mm[5], mm[9]), (mm[0] >> 1) & 1]
         if m[3]:
             raise ValueError("codes contain NaN")
@@ -422,6 +425,20 @@ class Evaluator:
         return dict(rec=rec, base0_all=base0_all, base0_rel=base0_rel, sbase_all=slab_all, sbase_rel=slab_rel,
                     total_rel=total_rel)
 
+    @staticmethod
+    def _host_sample_rows(n, stride, run):
+        """rows in the host-side sample of an n-row shard (whole runs only)"""
+        return (n // (run * stride)) * run if n >= run * stride else 0
+
+    def _host_sample_view(self, codes, stride, run):
+        """(sample rows, 2-D strided view (super rows, run * nbit)) over the first rows of a contiguous host tensor"""
+        n, nbit = codes.shape
+        ns = self._host_sample_rows(n, stride, run)
+        nsup = ns // run
+        flat = codes.contiguous() if not codes.is_contiguous() else codes
+        view = flat[:nsup * run * stride].view(nsup, run * stride * nbit)[:, :run * nbit]
+        return ns, view
+
     def _stream_per(self, nq_pad):
         """Stripes per streamed launch: the launch has per x ceil(nq_pad / 512) CTAs (4 query tiles each), one per
         SM; pick the smallest per <= 8 that fills its last wave best."""
@@ -435,41 +452,52 @@ class Evaluator:
                 best, best_eff = per, eff
         return best
 
-    def _select_streamed(self, c, rec, thresh, slab_all, slab_rel, nbins):
-        """Select pass over a HOST-resident gallery, one block of stripes at a time: the H2D copy + sign/bit-pack +
-        int8 expansion of block i+1 run (copy engine / tiny kernels) while the tensor-core select kernel works
+    class _Streamer:
+        """Select pass over a HOST-resident gallery, one block of stripes at a time: the H2D copy + sign/bit-pack
+        + int8 expansion of block i+1 run (copy engine / tiny kernels) while the tensor-core select kernel works
         on block i.  Outputs are exactly those of one whole-shard launch (slabs per stripe, records with shard
         row ids)."""
-        b, q, g, geo = self.b, c["q"], c["g"], c["geo"]
-        threads, nq_pad, nstripes, rps = geo
-        db_codes, nq = c["db_codes"], c["nq"]
-        words, kb = q.bits.shape[1], b.tc_code_bytes(q.nbit)
-        rows_pad = b.padded_rows(g.n)
-        g.bits = b.empty((rows_pad, words), torch.int32)
-        g.i8 = b.empty((rows_pad, kb), torch.int8)
-        if q.i8 is None:
-            q.i8 = self._timed("expand_i8", 0, lambda: b.expand_i8(q.bits, q.nbit, nq_pad))
-        flags = rec["status"][1:2]          # a zero / NaN in the gallery invalidates this path -> fallback
-        per = self._stream_per(nq_pad)
-        for s0 in range(0, nstripes, per):
-            s1 = min(nstripes, s0 + per)
-            r0, r1 = s0 * rps, min(g.n, s1 * rps)
-            if r1 <= r0:
-                break
-            last = r1 == g.n
-            nrow8 = (rows_pad - r0) if last else (r1 - r0)
+
+        def __init__(self, ev, c, flags):
+            self.ev, self.c, self.flags = ev, c, flags
+            b, q, g = ev.b, c["q"], c["g"]
+            threads, nq_pad, nstripes, rps = c["geo"]
+            self.rows_pad = b.padded_rows(g.n)
+            g.bits = b.empty((self.rows_pad, q.bits.shape[1]), torch.int32)
+            g.i8 = b.empty((self.rows_pad, b.tc_code_bytes(q.nbit)), torch.int8)
+            if q.i8 is None:
+                q.i8 = ev._timed("expand_i8", 0, lambda: b.expand_i8(q.bits, q.nbit, nq_pad))
+            per = ev._stream_per(nq_pad)
+            self.blocks = []
+            for s0 in range(0, nstripes, per):
+                s1 = min(nstripes, s0 + per)
+                r0, r1 = s0 * rps, min(g.n, s1 * rps)
+                if r1 > r0:
+                    self.blocks.append((s0, s1, r0, r1))
+
+        def load(self, i):
+            """H2D + pack + expand of block i (the host returns when the copy is done; kernels are queued)"""
+            ev, b, q, g = self.ev, self.ev.b, self.c["q"], self.c["g"]
+            s0, s1, r0, r1 = self.blocks[i]
+            db_codes = self.c["db_codes"]
+            nrow8 = (self.rows_pad - r0) if r1 == g.n else (r1 - r0)
             blk = db_codes[r0:r1]
-            nbytes = (r1 - r0) * q.nbit * db_codes.element_size()
-            self._timed("pack_host", nbytes, lambda: b.pack_sign(blk, 0.0, flags, False, out=g.bits[r0:]))
-            self._timed("expand_i8", 0, lambda: b.expand_i8_into(g.bits[r0:r0 + nrow8], q.nbit, g.i8[r0:]))
+            ev._timed("pack_host", (r1 - r0) * q.nbit * db_codes.element_size(),
+                      lambda: b.pack_sign(blk, 0.0, self.flags, False, out=g.bits[r0:]))
+            ev._timed("expand_i8", 0, lambda: b.expand_i8_into(g.bits[r0:r0 + nrow8], q.nbit, g.i8[r0:]))
+
+        def select(self, i, rec, thresh, slab_all, slab_rel, nbins):
+            ev, b, q, g = self.ev, self.ev.b, self.c["q"], self.c["g"]
+            threads, nq_pad, nstripes, rps = self.c["geo"]
+            s0, s1, r0, r1 = self.blocks[i]
             args = dict(q_bits=q.bits, q_nz=None, g_bits=g.bits[r0:], g_nz=None, q_lab=q.ids, g_lab=g.ids[r0:],
                         slab_all=slab_all[s0:], slab_rel=slab_rel[s0:], thresh=thresh, rec_off=rec["off"][s0:],
                         rec_cap=rec["cap"][s0:], rec_cnt=rec["cnt"][s0:], recs=rec["recs"], err_flag=rec["err"],
-                        nq=nq, nq_pad=nq_pad, ndb=r1 - r0, nbit=q.nbit, ternary=False, label_mode=L.CH_LAB_ID,
-                        mask_words=0, emit_mode=L.CH_EMIT_RELEVANT, nstripes=s1 - s0, threads=threads,
-                        rows_per_stripe=rps, key_limit=nbins, row_base=r0)
-            self._timed("hist_select_tc", nq * (r1 - r0), lambda: b.hamming_select_tc(q.i8, g.i8[r0:], **args))
-        self.stats["select_kernel"] = "tcgen05"
+                        nq=self.c["nq"], nq_pad=nq_pad, ndb=r1 - r0, nbit=q.nbit, ternary=False,
+                        label_mode=L.CH_LAB_ID, mask_words=0, emit_mode=L.CH_EMIT_RELEVANT, nstripes=s1 - s0,
+                        threads=threads, rows_per_stripe=rps, key_limit=nbins, row_base=r0)
+            ev._timed("hist_select_tc", self.c["nq"] * (r1 - r0),
+                      lambda: b.hamming_select_tc(q.i8, g.i8[r0:], **args))
 
     def _pass_topr_sampled(self, c, streamed=False):
         """Top-R in ONE full pass.  A 1-in-``sample_stride`` row sample of the gallery is histogrammed first; from
@@ -483,20 +511,26 @@ class Evaluator:
         need = min(c["rmax"] + c["rf"], c["ndb_total"])
         stride = c["stride"]
         # ---- the sample: every stride-th row of the local shard, same stripes (rps is a multiple of stride) ----
-        ns = (g.n + stride - 1) // stride
         status = b.zeros((2,), torch.int32)
         sp = Packed()
         sp.i8 = None
-        sp.n, sp.nbit = ns, g.nbit
+        sp.nbit = g.nbit
         sp.nz = None
+        streamer = None
         if streamed:
-            # the gallery is still on the host: copy just the sampled rows (strided 2-D DMA) and pack them
-            view = c["db_codes"][::stride]
-            sp.bits, _ = self._timed("pack_host", ns * g.nbit * view.element_size(),
-                                     lambda: b.pack_sign(view, 0.0, status[1:2], False))
+            # the gallery is still on the host: copy just the sample with ONE strided 2-D DMA -- runs of `run`
+            # consecutive rows (1 KB segments) every run * stride rows -- and pack it
+            run = max(1, 256 // g.nbit) if g.nbit in (32, 64, 128, 256) else 1
+            ns, view = self._host_sample_view(c["db_codes"], stride, run)
+            packed, _ = self._timed("pack_host", ns * g.nbit * view.element_size(),
+                                    lambda: b.pack_sign(view, 0.0, status[1:2], False))
+            sp.bits = packed.view(-1, q.bits.shape[1])         # (super rows, run * words) -> (rows, words)
+            streamer = self._Streamer(self, c, status[1:2])
         else:
+            ns = (g.n + stride - 1) // stride
             sp.bits = b.zeros((b.padded_rows(ns), g.bits.shape[1]), torch.int32)
             sp.bits[:ns] = g.bits[:g.n][::stride]
+        sp.n = ns
         if ternary:
             sp.nz = b.zeros((b.padded_rows(ns), g.bits.shape[1]), torch.int32)
             sp.nz[:ns] = g.nz[:g.n][::stride]
@@ -504,7 +538,10 @@ class Evaluator:
         geo_s = (threads, nq_pad, nstripes, rps // stride)
         slab_s = b.zeros((nstripes, nbins, nq_pad), torch.int32)
         self._hist(q, sp, geo_s, ternary, L.CH_LAB_NONE, 0, slab_s, None)
-        ns_total = sum((r + stride - 1) // stride for r in c["rows"])      # every rank samples the same way
+        if streamed:        # every rank samples the same way (streaming is agreed on by all ranks)
+            ns_total = sum(self._host_sample_rows(r, stride, run) for r in c["rows"])
+        else:
+            ns_total = sum((r + stride - 1) // stride for r in c["rows"])
         mu = need * ns_total / max(c["ndb_total"], 1)
         m = int(mu + 5.0 * mu ** 0.5 + 4.0) + 1
         thresh = b.empty((nq_pad,), torch.int32)
@@ -516,6 +553,8 @@ class Evaluator:
         b.record_caps(0, slab_s, thresh, nstripes, nbins, nq, nq_pad, False, cap, sample_stride=stride)
         cls = self._class_counts(c)
         b.record_caps(2, cls, q.ids, nstripes, c["nclass"], nq, nq_pad, True, cap)
+        if streamer is not None:
+            streamer.load(0)        # block 0 travels while the GPU is still busy with the sample
         rec, tmax = self._alloc_records(cap, geo, nq, thresh, status)   # one host sync: slots + max threshold
         del slab_s, base_tmp
         # ---- the one full pass; only keys <= max threshold can occur, all slabs / bases are that narrow ----
@@ -523,7 +562,11 @@ class Evaluator:
         slab_all = b.zeros((nstripes, nbins, nq_pad), torch.int32)
         slab_rel = b.zeros((nstripes, nbins, nq_pad), torch.int32)
         if streamed:
-            self._select_streamed(c, rec, thresh, slab_all, slab_rel, nbins)
+            for i in range(len(streamer.blocks)):
+                streamer.select(i, rec, thresh, slab_all, slab_rel, nbins)
+                if i + 1 < len(streamer.blocks):
+                    streamer.load(i + 1)     # host waits for this copy while the GPU runs select(i)
+            self.stats["select_kernel"] = "tcgen05"
         else:
             self._hist(q, g, geo, ternary, label_mode, lw, slab_all, slab_rel, thresh=thresh,
                        emit=L.CH_EMIT_RELEVANT, rec=rec, key_limit=nbins)
