@@ -54,6 +54,22 @@ class CudaBackend:
         """Called once per evaluation: caches the current torch stream handle (looked up ~20x per evaluation)."""
         self._stream_cache = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def on_stream(self, torch_stream):
+        """Context manager: the entry points launch on ``torch_stream`` instead of the evaluation's stream."""
+        backend = self
+
+        class _Ctx:
+            def __enter__(self_inner):
+                self_inner.saved = getattr(backend, "_stream_cache", None)
+                backend._stream_cache = C.c_void_p(torch_stream.cuda_stream)
+                self_inner.guard = torch.cuda.stream(torch_stream)
+                self_inner.guard.__enter__()
+
+            def __exit__(self_inner, *exc):
+                self_inner.guard.__exit__(*exc)
+                backend._stream_cache = self_inner.saved
+        return _Ctx()
+
     def _stream(self):
         s = getattr(self, "_stream_cache", None)
         if s is None:

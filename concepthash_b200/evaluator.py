@@ -468,6 +468,9 @@ class Evaluator:
             if q.i8 is None:
                 q.i8 = ev._timed("expand_i8", 0, lambda: b.expand_i8(q.bits, q.nbit, nq_pad))
             per = ev._stream_per(nq_pad)
+            # loads run on a side stream so that they are not queued behind the (long) select kernels
+            self.side = torch.cuda.Stream(device=g.bits.device)
+            self.loaded = {}
             self.blocks = []
             for s0 in range(0, nstripes, per):
                 s1 = min(nstripes, s0 + per)
@@ -482,14 +485,19 @@ class Evaluator:
             db_codes = self.c["db_codes"]
             nrow8 = (self.rows_pad - r0) if r1 == g.n else (r1 - r0)
             blk = db_codes[r0:r1]
-            ev._timed("pack_host", (r1 - r0) * q.nbit * db_codes.element_size(),
-                      lambda: b.pack_sign(blk, 0.0, self.flags, False, out=g.bits[r0:]))
-            ev._timed("expand_i8", 0, lambda: b.expand_i8_into(g.bits[r0:r0 + nrow8], q.nbit, g.i8[r0:]))
+            with b.on_stream(self.side):
+                ev._timed("pack_host", (r1 - r0) * q.nbit * db_codes.element_size(),
+                          lambda: b.pack_sign(blk, 0.0, self.flags, False, out=g.bits[r0:]))
+                ev._timed("expand_i8", 0, lambda: b.expand_i8_into(g.bits[r0:r0 + nrow8], q.nbit, g.i8[r0:]))
+                done = torch.cuda.Event()
+                done.record(self.side)
+            self.loaded[i] = done
 
         def select(self, i, rec, thresh, slab_all, slab_rel, nbins):
             ev, b, q, g = self.ev, self.ev.b, self.c["q"], self.c["g"]
             threads, nq_pad, nstripes, rps = self.c["geo"]
             s0, s1, r0, r1 = self.blocks[i]
+            torch.cuda.current_stream().wait_event(self.loaded[i])
             args = dict(q_bits=q.bits, q_nz=None, g_bits=g.bits[r0:], g_nz=None, q_lab=q.ids, g_lab=g.ids[r0:],
                         slab_all=slab_all[s0:], slab_rel=slab_rel[s0:], thresh=thresh, rec_off=rec["off"][s0:],
                         rec_cap=rec["cap"][s0:], rec_cnt=rec["cnt"][s0:], recs=rec["recs"], err_flag=rec["err"],
@@ -526,6 +534,7 @@ class Evaluator:
                                     lambda: b.pack_sign(view, 0.0, status[1:2], False))
             sp.bits = packed.view(-1, q.bits.shape[1])         # (super rows, run * words) -> (rows, words)
             streamer = self._Streamer(self, c, status[1:2])
+            streamer.side.wait_stream(torch.cuda.current_stream())
         else:
             ns = (g.n + stride - 1) // stride
             sp.bits = b.zeros((b.padded_rows(ns), g.bits.shape[1]), torch.int32)
