@@ -34,6 +34,22 @@ class FinalArgs(C.Structure):
                [("r_eff", C.c_int64 * CH_MAX_R), ("pr_k", C.c_int64 * CH_MAX_PR)]
 
 
+class SelectArgs(C.Structure):
+    _fields_ = [(n, P) for n in ("q_i8", "g_i8", "cand_off", "cand_cap", "cand_cnt", "cand_rows", "err_flag")] + \
+               [(n, C.c_int64) for n in ("nq", "nq_pad", "ndb", "row_base")] + \
+               [(n, C.c_int32) for n in ("nbit", "nstripes", "rows_per_stripe", "dense")]
+
+
+class CandArgs(C.Structure):
+    _fields_ = [(n, P) for n in ("cand_off", "cand_cnt", "cand_rows", "cand_key", "q_bits", "g_bits", "q_lab", "g_lab",
+                                 "tot_all", "tot_rel", "base0_all", "base0_rel", "first_rel", "first_rel_out", "cols",
+                                 "ids", "keys", "err_flag")] + \
+               [(n, C.c_int64) for n in ("nq", "nq_pad", "R", "row_offset")] + \
+               [(n, C.c_int32) for n in ("nstripes", "nbins", "nbit", "label_mode", "mask_words", "remove_first",
+                                         "nR", "nPR", "mode")] + \
+               [("r_eff", C.c_int64 * CH_MAX_R), ("pr_k", C.c_int64 * CH_MAX_PR)]
+
+
 # name -> (restype, argtypes); the authoritative list of exported symbols (tests check it against the header)
 SIGNATURES = {
     "ch_abi_version": (C.c_int, []),
@@ -52,8 +68,10 @@ SIGNATURES = {
                                    C.POINTER(C.c_int32)]),
     "ch_hamming_hist": (C.c_int, [P, C.POINTER(HistArgs), P]),
     "ch_tc_code_bytes": (C.c_int, [C.c_int]),
-    "ch_expand_i8": (C.c_int, [P, P, C.c_int64, C.c_int, P, P]),
-    "ch_hamming_select_tc": (C.c_int, [P, C.POINTER(HistArgs), P, P, P]),
+    "ch_expand_i8": (C.c_int, [P, P, C.c_int64, C.c_int, P, C.c_int64, P, C.c_int64, P]),
+    "ch_hamming_select_tc": (C.c_int, [P, C.POINTER(SelectArgs), P]),
+    "ch_cand_hist": (C.c_int, [P, C.POINTER(CandArgs), P]),
+    "ch_cand_finalize": (C.c_int, [P, C.POINTER(CandArgs), P]),
     "ch_slab_totals": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int64, P, P]),
     "ch_slab_exscan": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int64, P]),
     "ch_scan_bases": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, P, P, P, P]),

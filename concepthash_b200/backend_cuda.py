@@ -178,25 +178,69 @@ class CudaBackend:
         return int(self.lib.ch_tc_code_bytes(int(nbit)))
 
     def expand_i8_into(self, bits, nbit, out):
-        """the same, for a row block: ``bits`` (rows, words) -> ``out`` (rows, kb) views of larger arrays"""
+        """gallery plane of a row block: ``bits`` (rows, words) -> ``out`` (rows, kb) views of larger arrays"""
         assert bits.shape[0] % 8 == 0 and out.shape[0] >= bits.shape[0]
-        L.check(self.lib.ch_expand_i8(self.ws, _ptr(bits), int(bits.shape[0]), nbit, _ptr(out), self._stream()),
-                "ch_expand_i8")
+        L.check(self.lib.ch_expand_i8(self.ws, _ptr(bits), int(bits.shape[0]), nbit, _ptr(out), int(bits.shape[0]),
+                                      None, 0, self._stream()), "ch_expand_i8")
 
-    def expand_i8(self, bits, nbit, min_rows=0):
-        """packed sign bits (rows_pad, words) -> +-1 int8 plane in the tiled operand order (rows, kb) int8;
-        ``min_rows`` over-allocates (zero rows) so that whole 128-query tiles can be read."""
+    def expand_i8(self, bits, nbit, min_rows=0, thresh=None, nq=0):
+        """packed sign bits (rows_pad, words) -> +-1 int8 plane in the tiled operand order (rows, kb) int8, with the
+        threshold slots: gallery plane when ``thresh`` is None, else the query plane of ``nq`` queries.
+        ``min_rows`` over-allocates so that whole 128-query tiles can be read."""
         kb = self.tc_code_bytes(nbit)
         rows_pad = int(bits.shape[0])
         rows = max(rows_pad, (int(min_rows) + 7) // 8 * 8)
-        out = self.zeros((rows, kb), torch.int8) if rows > rows_pad else self.empty((rows, kb), torch.int8)
-        L.check(self.lib.ch_expand_i8(self.ws, _ptr(bits), rows_pad, nbit, _ptr(out), self._stream()), "ch_expand_i8")
+        out = self.empty((rows, kb), torch.int8)
+        L.check(self.lib.ch_expand_i8(self.ws, _ptr(bits), rows_pad, nbit, _ptr(out), rows, _ptr(thresh), int(nq),
+                                      self._stream()), "ch_expand_i8")
         return out
 
-    def hamming_select_tc(self, q_i8, g_i8, **kw):
-        a = self._hist_args(**kw)
-        L.check(self.lib.ch_hamming_select_tc(self.ws, C.byref(a), _ptr(q_i8), _ptr(g_i8), self._stream()),
-                "ch_hamming_select_tc")
+    def hamming_select_tc(self, *, q_i8, g_i8, cand, nq, nq_pad, ndb, nbit, nstripes, rows_per_stripe, row_base=0,
+                          dense=False, stripe0=0):
+        """``cand``: dict(off, cap, cnt (nstripes_total, nq_pad) u32, rows u32[], err u32[1]); ``stripe0`` = first
+        stripe of this call's row block (streamed galleries)."""
+        a = L.SelectArgs()
+        a.q_i8, a.g_i8 = q_i8.data_ptr(), g_i8.data_ptr()
+        a.cand_off, a.cand_cap, a.cand_cnt = (cand[k][stripe0:].data_ptr() for k in ("off", "cap", "cnt"))
+        a.cand_rows, a.err_flag = cand["rows"].data_ptr(), cand["err"].data_ptr()
+        a.nq, a.nq_pad, a.ndb, a.row_base = nq, nq_pad, ndb, int(row_base)
+        a.nbit, a.nstripes, a.rows_per_stripe, a.dense = nbit, nstripes, rows_per_stripe, int(bool(dense))
+        L.check(self.lib.ch_hamming_select_tc(self.ws, C.byref(a), self._stream()), "ch_hamming_select_tc")
+
+    # ---- K3/K4 on candidate lists ----
+    def _cand_args(self, cand, nq, nq_pad, nstripes, nbins, **kw):
+        a = L.CandArgs()
+        a.cand_off, a.cand_cnt = cand["off"].data_ptr(), cand["cnt"].data_ptr()
+        a.cand_rows, a.cand_key, a.err_flag = cand["rows"].data_ptr(), cand["key"].data_ptr(), cand["err"].data_ptr()
+        a.nq, a.nq_pad, a.nstripes, a.nbins = nq, nq_pad, nstripes, nbins
+        for k, v in kw.items():
+            if isinstance(v, torch.Tensor):
+                setattr(a, k, v.data_ptr())
+            elif v is not None:
+                setattr(a, k, v)
+        return a
+
+    def cand_hist(self, cand, *, q_bits, g_bits, q_lab, g_lab, label_mode, mask_words, tot_all, tot_rel, nq, nq_pad,
+                  nstripes, nbins, nbit):
+        a = self._cand_args(cand, nq, nq_pad, nstripes, nbins, q_bits=q_bits, g_bits=g_bits, q_lab=q_lab, g_lab=g_lab,
+                            label_mode=label_mode, mask_words=mask_words, tot_all=tot_all, tot_rel=tot_rel, nbit=nbit)
+        L.check(self.lib.ch_cand_hist(self.ws, C.byref(a), self._stream()), "ch_cand_hist")
+
+    def cand_finalize(self, cand, *, mode, base0_all, base0_rel, nq, nq_pad, nstripes, nbins, remove_first=False,
+                      first_rel=None, first_rel_out=None, cols=None, r_eff=(), pr_k=(), ids=None, keys=None, R=0,
+                      row_offset=0):
+        r_eff, pr_k = list(r_eff), list(pr_k)
+        if len(r_eff) > L.CH_MAX_R or len(pr_k) > L.CH_MAX_PR:
+            raise ValueError(f"at most {L.CH_MAX_R} R values and {L.CH_MAX_PR} PRs cut-offs are supported")
+        a = self._cand_args(cand, nq, nq_pad, nstripes, nbins, mode=mode, base0_all=base0_all, base0_rel=base0_rel,
+                            remove_first=int(bool(remove_first)), first_rel=first_rel, first_rel_out=first_rel_out,
+                            cols=cols, ids=ids, keys=keys, R=int(R), row_offset=int(row_offset), nR=len(r_eff),
+                            nPR=len(pr_k))
+        for i, v in enumerate(r_eff):
+            a.r_eff[i] = int(v)
+        for i, v in enumerate(pr_k):
+            a.pr_k[i] = int(v)
+        L.check(self.lib.ch_cand_finalize(self.ws, C.byref(a), self._stream()), "ch_cand_finalize")
 
     def hamming_hist(self, **kw):
         a = self._hist_args(**kw)

@@ -1,0 +1,248 @@
+// K3/K4 on candidate lists (the output of the tensor-core select pass, select_tc.cu).
+//
+// A candidate list holds, per (stripe, query), the shard-local row indices of the pairs with key <= thresh[q], in
+// ascending row order; concatenated over the stripes it is the query's candidate set in global tie order.  Because
+// EVERY item with key <= thresh is in the list, the canonical rank of a candidate is a count over candidates only:
+//
+//     rank(j) = #{cand : key < key_j} (all ranks) + #{cand on lower ranks : key = key_j} + #{cand before j : key = key_j}
+//
+// ch_cand_hist      one warp per query: key (XOR + POPC on the packed codes) and label match of every candidate;
+//                   per-query key histograms {all, relevant} -> (nbins, nq_pad) totals (all-gathered by the caller,
+//                   turned into bases by ch_scan_bases); the key and the relevance bit are kept per candidate.
+// ch_cand_finalize  one warp per query walks the list in order, 32 candidates at a time: stable in-bucket prefixes
+//                   by __match_any_sync + running per-key counters in shared memory; then either the AP / P@k sums
+//                   (mode 0), the relevance of the rank-0 item (mode 1) or the ranked id list (mode 2).
+#include "common.cuh"
+
+namespace {
+
+struct CandDev {
+  const uint32_t* cand_off; const uint32_t* cand_cnt;
+  uint32_t* cand_rows; uint8_t* cand_key;
+  const uint32_t* q_bits; const uint32_t* g_bits;
+  const uint32_t* q_lab; const uint32_t* g_lab;
+  uint32_t* tot_all; uint32_t* tot_rel;
+  const uint32_t* base0_all; const uint32_t* base0_rel;
+  const uint32_t* first_rel; uint32_t* first_rel_out;
+  double* cols; long long* ids; int* keys;
+  uint32_t* err_flag;
+  long long nq, nq_pad, R, row_offset;
+  int nstripes, nbins, label_mode, lw, remove_first, nR, nPR, mode;
+  long long r_eff[CH_MAX_R];
+  long long pr_k[CH_MAX_PR];
+};
+
+constexpr int kCandWarps = 8;
+
+template <int W>
+__device__ __forceinline__ uint32_t key_of(const uint32_t (&qw)[W], const uint32_t* __restrict__ g_bits, uint32_t row) {
+  uint32_t gw[W];
+  if constexpr (W == 4) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(g_bits) + row);
+    gw[0] = v.x; gw[1] = v.y; gw[2] = v.z; gw[3] = v.w;
+  } else if constexpr (W == 2) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(g_bits) + row);
+    gw[0] = v.x; gw[1] = v.y;
+  } else {
+#pragma unroll
+    for (int w = 0; w < W; ++w) gw[w] = __ldg(g_bits + static_cast<size_t>(row) * W + w);
+  }
+  uint32_t key = 0;
+#pragma unroll
+  for (int w = 0; w < W; ++w) key += __popc(qw[w] ^ gw[w]);
+  return key;
+}
+
+template <int W>
+__global__ void __launch_bounds__(kCandWarps * 32) cand_hist_kernel(const CandDev a) {
+  extern __shared__ uint32_t sh[];
+  const int wip = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long q = static_cast<long long>(blockIdx.x) * kCandWarps + wip;
+  if (q >= a.nq) return;                       // whole warps leave; only __syncwarp below
+  uint32_t* h_all = sh + static_cast<size_t>(wip) * 2 * a.nbins;
+  uint32_t* h_rel = h_all + a.nbins;
+  for (int b = lane; b < 2 * a.nbins; b += 32) h_all[b] = 0u;
+  uint32_t qw[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) qw[w] = a.q_bits[q * W + w];
+  const uint32_t qid = a.label_mode == CH_LAB_ID ? a.q_lab[q] : 0u;
+  const uint32_t* qm = a.label_mode == CH_LAB_MASK ? a.q_lab + q * a.lw : nullptr;
+  bool bad = false;
+  __syncwarp();
+  for (int s = 0; s < a.nstripes; ++s) {
+    const size_t sq = static_cast<size_t>(s) * a.nq_pad + q;
+    const uint32_t off = a.cand_off[sq], n = a.cand_cnt[sq];
+    for (uint32_t i = lane; i < n; i += 32) {
+      const uint32_t row = a.cand_rows[off + i] & 0x7fffffffu;
+      const uint32_t key = key_of<W>(qw, a.g_bits, row);
+      bool rel = false;
+      if (a.label_mode == CH_LAB_ID) {
+        rel = __ldg(a.g_lab + row) == qid;
+      } else if (a.label_mode == CH_LAB_MASK) {
+        uint32_t any = 0;
+        for (int w = 0; w < a.lw; ++w) any |= qm[w] & __ldg(a.g_lab + static_cast<size_t>(row) * a.lw + w);
+        rel = any != 0u;
+      }
+      if (key < static_cast<uint32_t>(a.nbins)) {
+        atomicAdd(&h_all[key], 1u);
+        if (rel) atomicAdd(&h_rel[key], 1u);
+      } else {
+        bad = true;
+      }
+      a.cand_key[off + i] = static_cast<uint8_t>(key);
+      a.cand_rows[off + i] = row | (rel ? 0x80000000u : 0u);
+    }
+  }
+  __syncwarp();
+  for (int b = lane; b < a.nbins; b += 32) {
+    a.tot_all[static_cast<size_t>(b) * a.nq_pad + q] = h_all[b];
+    if (a.tot_rel != nullptr) a.tot_rel[static_cast<size_t>(b) * a.nq_pad + q] = h_rel[b];
+  }
+  if (bad) atomicOr(a.err_flag, 2u);
+}
+
+__global__ void __launch_bounds__(kCandWarps * 32) cand_final_kernel(const CandDev a) {
+  extern __shared__ uint32_t sh[];
+  const int wip = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long q = static_cast<long long>(blockIdx.x) * kCandWarps + wip;
+  if (q >= a.nq) return;
+  uint32_t* run_all = sh + static_cast<size_t>(wip) * 2 * a.nbins;
+  uint32_t* run_rel = run_all + a.nbins;
+  for (int b = lane; b < a.nbins; b += 32) {
+    run_all[b] = a.base0_all[static_cast<size_t>(b) * a.nq_pad + q];
+    run_rel[b] = a.base0_rel != nullptr ? a.base0_rel[static_cast<size_t>(b) * a.nq_pad + q] : 0u;
+  }
+  const int ncols = 2 * a.nR + a.nPR;
+  double acc[2 * CH_MAX_R + CH_MAX_PR];
+  if (a.mode == 0)
+    for (int c = 0; c < ncols; ++c) acc[c] = 0.0;
+  const long long shift = a.remove_first ? 1 : 0;
+  const long long frel = (a.remove_first && a.first_rel != nullptr) ? a.first_rel[q] : 0;
+  const uint32_t lt = lanemask_lt();
+  __syncwarp();
+  for (int s = 0; s < a.nstripes; ++s) {
+    const size_t sq = static_cast<size_t>(s) * a.nq_pad + q;
+    const uint32_t off = a.cand_off[sq], n = a.cand_cnt[sq];
+    for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+      const uint32_t i = i0 + lane;
+      uint32_t rowv = 0u, key = 0xffffffffu;
+      if (i < n) {
+        rowv = a.cand_rows[off + i];
+        key = a.cand_key[off + i];
+        if (key >= static_cast<uint32_t>(a.nbins)) key = 0xffffffffu;     // flagged by ch_cand_hist
+      }
+      const bool valid = key != 0xffffffffu;
+      const bool rel = valid && (rowv >> 31) != 0u;
+      const uint32_t peers = __match_any_sync(0xffffffffu, key);
+      const uint32_t relm = __ballot_sync(0xffffffffu, rel);
+      long long rank = 0, relrank = 0;
+      if (valid) {
+        rank = static_cast<long long>(run_all[key]) + __popc(peers & lt);
+        relrank = static_cast<long long>(run_rel[key]) + __popc(peers & relm & lt);
+      }
+      __syncwarp();
+      if (valid && (peers >> lane) == 1u) {       // highest lane of the group publishes the new running counts
+        run_all[key] += __popc(peers);
+        run_rel[key] += __popc(peers & relm);
+      }
+      __syncwarp();
+      if (!valid) continue;
+      if (a.mode == 1) {
+        if (rank == 0 && rel) a.first_rel_out[q] = 1u;
+        continue;
+      }
+      if (a.remove_first) {
+        if (rank == 0) continue;                  // the dropped self-retrieval
+        rank -= shift;
+        relrank -= frel;
+      }
+      if (a.mode == 2) {
+        if (rank < a.R) {
+          a.ids[q * a.R + rank] = a.row_offset + static_cast<long long>(rowv & 0x7fffffffu);
+          if (a.keys != nullptr) a.keys[q * a.R + rank] = static_cast<int>(key);
+        }
+        continue;
+      }
+      if (!rel) continue;
+      const double prec = static_cast<double>(relrank + 1) / static_cast<double>(rank + 1);
+      for (int j = 0; j < a.nR; ++j)
+        if (rank < a.r_eff[j]) {
+          acc[2 * j] += prec;
+          acc[2 * j + 1] += 1.0;
+        }
+      for (int j = 0; j < a.nPR; ++j)
+        if (rank < a.pr_k[j]) acc[2 * a.nR + j] += 1.0;
+    }
+  }
+  if (a.mode == 0) {
+    for (int c = 0; c < ncols; ++c) {
+      double v = acc[c];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);   // fixed tree: deterministic
+      if (lane == 0) a.cols[q * ncols + c] = v;
+    }
+  }
+}
+
+int to_dev(const ch_cand_args* a, CandDev* d) {
+  if (a == nullptr) CH_FAIL("null ch_cand_args");
+  if (a->cand_off == nullptr || a->cand_cnt == nullptr || a->cand_rows == nullptr || a->cand_key == nullptr)
+    CH_FAIL("null candidate arrays");
+  if (a->nR < 0 || a->nR > CH_MAX_R || a->nPR < 0 || a->nPR > CH_MAX_PR) CH_FAIL("too many R / PRs entries");
+  if (a->nbins <= 0 || a->nbins > 257) CH_FAIL("bad nbins %d", a->nbins);
+  if (a->nq <= 0 || a->nq_pad < a->nq || a->nstripes <= 0) CH_FAIL("bad candidate geometry");
+  d->cand_off = a->cand_off; d->cand_cnt = a->cand_cnt; d->cand_rows = a->cand_rows; d->cand_key = a->cand_key;
+  d->q_bits = a->q_bits; d->g_bits = a->g_bits; d->q_lab = a->q_lab; d->g_lab = a->g_lab;
+  d->tot_all = a->tot_all; d->tot_rel = a->tot_rel; d->base0_all = a->base0_all; d->base0_rel = a->base0_rel;
+  d->first_rel = a->first_rel; d->first_rel_out = a->first_rel_out; d->cols = a->cols;
+  d->ids = reinterpret_cast<long long*>(a->ids); d->keys = a->keys; d->err_flag = a->err_flag;
+  d->nq = a->nq; d->nq_pad = a->nq_pad; d->R = a->R; d->row_offset = a->row_offset;
+  d->nstripes = a->nstripes; d->nbins = a->nbins; d->label_mode = a->label_mode; d->lw = a->mask_words;
+  d->remove_first = a->remove_first; d->nR = a->nR; d->nPR = a->nPR; d->mode = a->mode;
+  for (int i = 0; i < CH_MAX_R; ++i) d->r_eff[i] = i < a->nR ? a->r_eff[i] : 0;
+  for (int i = 0; i < CH_MAX_PR; ++i) d->pr_k[i] = i < a->nPR ? a->pr_k[i] : 0;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int ch_cand_hist(ch_ws* ws, const ch_cand_args* a, void* stream) {
+  if (ws == nullptr) CH_FAIL("null workspace");
+  CandDev d;
+  if (to_dev(a, &d)) return 1;
+  if (a->q_bits == nullptr || a->g_bits == nullptr || a->tot_all == nullptr || a->err_flag == nullptr)
+    CH_FAIL("null argument to ch_cand_hist");
+  if (a->label_mode != CH_LAB_NONE && (a->q_lab == nullptr || a->g_lab == nullptr || a->tot_rel == nullptr))
+    CH_FAIL("labels / relevant totals missing");
+  if (a->label_mode == CH_LAB_NONE) d.tot_rel = nullptr;
+  const int words = ch_code_words(a->nbit);
+  if (words == 0) CH_FAIL("nbit=%d unsupported", a->nbit);
+  ChDeviceGuard guard(ws->device);
+  const unsigned blocks = static_cast<unsigned>((a->nq + kCandWarps - 1) / kCandWarps);
+  const size_t smem = static_cast<size_t>(kCandWarps) * 2 * a->nbins * sizeof(uint32_t);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (words) {
+    case 1: cand_hist_kernel<1><<<blocks, kCandWarps * 32, smem, st>>>(d); break;
+    case 2: cand_hist_kernel<2><<<blocks, kCandWarps * 32, smem, st>>>(d); break;
+    case 4: cand_hist_kernel<4><<<blocks, kCandWarps * 32, smem, st>>>(d); break;
+    default: cand_hist_kernel<8><<<blocks, kCandWarps * 32, smem, st>>>(d); break;
+  }
+  CH_LAUNCH_CHECK(ws);
+  return 0;
+}
+
+extern "C" int ch_cand_finalize(ch_ws* ws, const ch_cand_args* a, void* stream) {
+  if (ws == nullptr) CH_FAIL("null workspace");
+  CandDev d;
+  if (to_dev(a, &d)) return 1;
+  if (a->base0_all == nullptr) CH_FAIL("null bases");
+  if (a->mode == 0 && (a->cols == nullptr || a->base0_rel == nullptr)) CH_FAIL("mode 0 needs cols and base0_rel");
+  if (a->mode == 1 && a->first_rel_out == nullptr) CH_FAIL("mode 1 needs first_rel_out");
+  if (a->mode == 2 && (a->ids == nullptr || a->R <= 0)) CH_FAIL("mode 2 needs ids and R > 0");
+  if (a->mode < 0 || a->mode > 2) CH_FAIL("bad mode %d", a->mode);
+  ChDeviceGuard guard(ws->device);
+  const unsigned blocks = static_cast<unsigned>((a->nq + kCandWarps - 1) / kCandWarps);
+  const size_t smem = static_cast<size_t>(kCandWarps) * 2 * a->nbins * sizeof(uint32_t);
+  cand_final_kernel<<<blocks, kCandWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(d);
+  CH_LAUNCH_CHECK(ws);
+  return 0;
+}

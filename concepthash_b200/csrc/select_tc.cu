@@ -1,0 +1,430 @@
+// K2, tensor-core form of the SELECT pass: which (query, gallery row) pairs have key <= the query's threshold?
+//
+// For +-1 codes held as int8, <q, g> = nbit - 2 * hamming(q, g) exactly, so tcgen05.mma kind::i8 (UTCIMMA, int32
+// accumulators in TMEM) produces the distances of a 128-query x 128-gallery-row tile at a cost of KB/32
+// instructions.  The per-query threshold rides in the contraction as well: two extra K slots hold
+// (a, b), a + b = -(nbit - 2 * thresh[q]), on the query side and (1, 1) on the gallery side, so the accumulator is
+//
+//     D[q][j] = <q, g_j> - (nbit - 2 * thresh[q])        and        key(q, j) <= thresh[q]  <=>  D[q][j] >= 0.
+//
+// What is left per pair is the SIGN BIT of one TMEM word.  The epilogue funnels the 32 sign bits of a 32-column
+// chunk into one mask (SHF, alu pipe) -- in the "sparse" variant only after a 3-input max tree said that the chunk
+// holds a candidate at all -- and appends the shard-local row index of every candidate to the (stripe, query)
+// slice of the candidate list, in ascending row order (thread = TMEM lane = query; tiles, chunks and bits are
+// visited in row order).  Nothing else happens here: keys, label matches, stable ranks and AP are the business of
+// cand.cu, which only ever sees the candidates (~0.01-0.3 % of the pairs).
+//
+// Warp roles (640 threads, one CTA per SM, persistent over the tiles of one (4 query tiles, stripe)):
+//   warp 0      producer: 1-D bulk async copies (UBLKCP) of gallery tiles into a 4-stage ring
+//   warp 1      MMA issuer: one elected thread issues KB/32 UTCIMMA per (tile, query tile) into that query tile's
+//               TMEM accumulator (4 accumulators x 128 columns = all 512 columns)
+//   warp 2      TMEM allocator
+//   warps 4-19  epilogue: one warpgroup per query tile; tcgen05.ld 32 columns at a time, double-buffered in
+//               registers so that the load of chunk c+1 is in flight while chunk c is examined
+// Operands live in shared memory in the canonical NO-SWIZZLE K-major core-matrix layout (8 rows x 16 bytes =
+// 128 contiguous bytes; next 16-byte K chunk at +128 B (LBO); next 8-row group at +8*KB (SBO)).  The int8 planes
+// are stored in HBM already in that order (expand_i8_tiled_kernel), so a tile is one contiguous bulk copy.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kTileN = 128;   // gallery rows per MMA tile (TMEM columns per accumulator)
+constexpr int kTileM = 128;   // queries per query tile
+constexpr int kQT = 4;        // query tiles per CTA (4 accumulators x 128 columns = 512 TMEM columns)
+constexpr int kStages = 4;    // gallery-tile ring
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3fffu);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fffu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fffu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;  // descriptor version 1 (Blackwell); SWIZZLE_NONE, base offset 0
+  return d;
+}
+
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// single-thread waiters (producer, MMA issuer) back off so that their spin does not steal issue slots from
+// the epilogue warps sharing the scheduler
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(64);
+  }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+#define CH_R32(r)                                                                                                  \
+  r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8], r[9], r[10], r[11], r[12], r[13], r[14], r[15], r[16],     \
+      r[17], r[18], r[19], r[20], r[21], r[22], r[23], r[24], r[25], r[26], r[27], r[28], r[29], r[30], r[31]
+#define CH_OUT32(r)                                                                                                \
+  "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),      \
+      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),       \
+      "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),      \
+      "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+#define CH_INOUT32(r)                                                                                              \
+  "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),      \
+      "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),       \
+      "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),      \
+      "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+
+// issue only: the registers are NOT valid until tmem_wait(r) has been executed
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : CH_OUT32(r)
+      : "r"(taddr)
+      : "memory");
+}
+// the wait names the registers as in/out operands: no use of r[] can be scheduled above it
+__device__ __forceinline__ void tmem_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" : CH_INOUT32(r)::"memory");
+}
+
+struct SelDev {
+  const int8_t* q_i8;          // tiled (>= nq_pad rows, KB); threshold slots filled by expand_i8_tiled_kernel
+  const int8_t* g_i8;          // tiled (rows_pad, KB)
+  const uint32_t* cand_off;    // (nstripes, nq_pad)
+  const uint32_t* cand_cap;    // (nstripes, nq_pad)
+  uint32_t* cand_cnt;          // (nstripes, nq_pad)
+  uint32_t* cand_rows;         // shard-local row index of every candidate
+  uint32_t* err_flag;
+  long long nq, nq_pad, ndb, row_base;
+  int rows_per_stripe;
+  int nqtiles128;              // 128-query tiles in total
+  int nqgroups;                // CTAs along the query axis (each owns kQT consecutive query tiles)
+};
+
+template <int KB>
+struct SelSmem {
+  static constexpr int kA = kTileM * KB;   // one query tile
+  static constexpr int kB = kTileN * KB;   // one gallery tile
+  static constexpr int offA = 0;
+  static constexpr int offB = offA + kQT * kA;
+  static constexpr int total = offB + kStages * kB;
+};
+
+// sign bits of the 32 accumulators of a chunk: bit j = (r[j] < 0); four independent funnel-shift chains
+__device__ __forceinline__ uint32_t sign_mask32(const uint32_t (&r)[32]) {
+  uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+#pragma unroll
+  for (int j = 7; j >= 0; --j) {
+    m0 = __funnelshift_l(r[j], m0, 1);
+    m1 = __funnelshift_l(r[8 + j], m1, 1);
+    m2 = __funnelshift_l(r[16 + j], m2, 1);
+    m3 = __funnelshift_l(r[24 + j], m3, 1);
+  }
+  return __byte_perm(__byte_perm(m0, m1, 0x0040), __byte_perm(m2, m3, 0x0040), 0x5410);
+}
+
+__device__ __forceinline__ int max32(const uint32_t (&r)[32]) {
+  int x[11];
+#pragma unroll
+  for (int i = 0; i < 10; ++i)
+    x[i] = max(max(static_cast<int>(r[3 * i]), static_cast<int>(r[3 * i + 1])), static_cast<int>(r[3 * i + 2]));
+  x[10] = max(static_cast<int>(r[30]), static_cast<int>(r[31]));
+  const int y0 = max(max(x[0], x[1]), x[2]), y1 = max(max(x[3], x[4]), x[5]);
+  const int y2 = max(max(x[6], x[7]), x[8]), y3 = max(x[9], x[10]);
+  return max(max(max(y0, y1), y2), y3);
+}
+
+// One CTA = kQT consecutive 128-query tiles x one gallery stripe.
+template <int KB, bool DENSE>
+__global__ void __launch_bounds__(128 + 128 * kQT, 1) hamming_select_tc_kernel(const SelDev a) {
+  typedef SelSmem<KB> S;
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar_a, bar_full[kStages], bar_empty[kStages], bar_tfull[kQT], bar_tempty[kQT];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  const int qgroup = blockIdx.x % a.nqgroups;
+  const int stripe = blockIdx.x / a.nqgroups;
+  const int qtile0 = qgroup * kQT;
+  int nvalid = a.nqtiles128 - qtile0;
+  if (nvalid > kQT) nvalid = kQT;
+  const long long row_begin = static_cast<long long>(stripe) * a.rows_per_stripe;
+  long long row_end = row_begin + a.rows_per_stripe;
+  if (row_end > a.ndb) row_end = a.ndb;
+  const int ntiles = row_end > row_begin ? static_cast<int>((row_end - row_begin + kTileN - 1) / kTileN) : 0;
+
+  if (tid == 0) {
+    mbar_init(&bar_a, 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&bar_full[s], 1);
+      mbar_init(&bar_empty[s], 1);     // the MMA commit of the tile that used the stage
+    }
+    for (int i = 0; i < kQT; ++i) {
+      mbar_init(&bar_tfull[i], 1);
+      mbar_init(&bar_tempty[i], 4);    // the four epilogue warps of the query tile
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ===================== producer =====================
+    if (lane == 0 && ntiles > 0) {
+      mbar_arrive_expect_tx(&bar_a, nvalid * S::kA);
+      bulk_g2s(smem + S::offA, a.q_i8 + static_cast<size_t>(qtile0) * kTileM * KB, nvalid * S::kA, &bar_a);
+      for (int k = 0; k < ntiles; ++k) {
+        const int s = k % kStages;
+        mbar_wait_backoff(&bar_empty[s], static_cast<uint32_t>(((k / kStages) & 1) ^ 1));
+        const long long r0 = row_begin + static_cast<long long>(k) * kTileN;
+        long long rows = row_end - r0;
+        if (rows > kTileN) rows = kTileN;
+        const uint32_t rows8 = static_cast<uint32_t>((rows + 7) & ~7ll);   // pad rows exist (ch_padded_rows)
+        const uint32_t bytes_b = rows8 * KB;
+        mbar_arrive_expect_tx(&bar_full[s], bytes_b);
+        bulk_g2s(smem + S::offB + s * S::kB, a.g_i8 + static_cast<size_t>(r0) * KB, bytes_b, &bar_full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0 && ntiles > 0) {
+      // s32 accumulate, s8 x s8, both K-major, N = kTileN, M = 128
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kTileN >> 3) << 17) |
+                             (static_cast<uint32_t>(kTileM >> 4) << 24);
+      const uint32_t sbo = 8 * KB, lbo = 128;
+      const uint32_t a_addr = smem_u32(smem + S::offA);
+      mbar_wait_backoff(&bar_a, 0);
+      for (int k = 0; k < ntiles; ++k) {
+        const int s = k % kStages;
+        mbar_wait_backoff(&bar_full[s], static_cast<uint32_t>((k / kStages) & 1));
+        const uint32_t b_addr = smem_u32(smem + S::offB + s * S::kB);
+        for (int i = 0; i < nvalid; ++i) {
+          mbar_wait_backoff(&bar_tempty[i], static_cast<uint32_t>((k & 1) ^ 1));   // accumulator i drained
+          tc_fence_after();
+          const uint32_t d_addr = tmem_base + static_cast<uint32_t>(i) * kTileN;
+#pragma unroll
+          for (int kk = 0; kk < KB / 32; ++kk)
+            umma_i8(d_addr, umma_desc(a_addr + i * S::kA + kk * 256, lbo, sbo), umma_desc(b_addr + kk * 256, lbo, sbo),
+                    idesc, kk > 0 ? 1u : 0u);
+          umma_commit(&bar_tfull[i]);   // accumulator i holds tile k
+        }
+        umma_commit(&bar_empty[s]);     // the stage may be overwritten once these MMAs retire
+      }
+    }
+  } else if (warp >= 4 && ((warp - 4) >> 2) < nvalid) {
+    // ===================== epilogue: thread = TMEM lane = query =====================
+    const int qt = (warp - 4) >> 2;                // query tile of this warpgroup
+    const int e = (tid - 128) & 127;               // 0..127 within the query tile
+    const int ewarp = warp & 3;                    // TMEM lanes 32 * ewarp ..
+    const long long q = static_cast<long long>(qtile0 + qt) * kTileM + e;
+    const bool active = q < a.nq;
+    const size_t sq = static_cast<size_t>(stripe) * a.nq_pad + q;
+    uint32_t n = 0, cap = 0;
+    uint32_t* out = a.cand_rows;
+    if (active) {
+      out += a.cand_off[sq];
+      cap = a.cand_cap[sq];
+    }
+    // rows >= row_lim (pad rows of the shard's last tile, stale columns of a short tile) are never candidates;
+    // an inactive lane (query padding) accepts nothing
+    const uint32_t row_lim = active ? static_cast<uint32_t>(a.row_base + row_end) : 0u;
+    const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ewarp * 32) << 16) + static_cast<uint32_t>(qt) * kTileN;
+
+    auto examine = [&](const uint32_t (&r)[32], uint32_t row0) {
+      if (!DENSE) {
+        if (max32(r) < 0) return;                  // no candidate among the 32 rows (the usual case)
+      }
+      uint32_t cand = ~sign_mask32(r);
+      while (cand != 0u) {
+        const uint32_t row = row0 + static_cast<uint32_t>(__ffs(static_cast<int>(cand)) - 1);
+        cand &= cand - 1u;
+        if (row < row_lim) {
+          if (n < cap) out[n] = row;
+          ++n;
+        }
+      }
+    };
+
+    uint32_t ra[32], rb[32];
+    for (int k = 0; k < ntiles; ++k) {
+      const uint32_t row0 = static_cast<uint32_t>(a.row_base + row_begin) + static_cast<uint32_t>(k) * kTileN;
+      mbar_wait(&bar_tfull[qt], static_cast<uint32_t>(k & 1));
+      tc_fence_after();
+      tmem_ld32_issue(taddr0, ra);
+      tmem_wait(ra);
+      tmem_ld32_issue(taddr0 + 32, rb);            // in flight while chunk 0 is examined
+      examine(ra, row0);
+      tmem_wait(rb);
+      tmem_ld32_issue(taddr0 + 64, ra);
+      examine(rb, row0 + 32);
+      tmem_wait(ra);
+      tmem_ld32_issue(taddr0 + 96, rb);
+      examine(ra, row0 + 64);
+      tmem_wait(rb);
+      // every column of the accumulator is in registers: hand it back to the MMA before the last examination
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tempty[qt]);
+      examine(rb, row0 + 96);
+    }
+    if (active) {
+      a.cand_cnt[sq] = n < cap ? n : cap;
+      if (n > cap) atomicOr(a.err_flag, 1u);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// packed sign bits -> +-1 int8 in the tiled core-matrix order; one thread per (row, 16-byte K chunk).
+// Bytes nbit and nbit + 1 of a row are the threshold slots: (1, 1) on the gallery side; on the query side
+// (thresh != NULL) a + b = -(nbit - 2 * thresh[row]) for row < nq and (-128, -128) for the padding queries.
+__global__ void expand_i8_tiled_kernel(const uint32_t* __restrict__ bits, long long rows_bits, long long rows_out,
+                                       int words, int nbit, int kb, const uint32_t* __restrict__ thresh, long long nq,
+                                       int8_t* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int chunks = kb / 16;
+  if (i >= rows_out * chunks) return;
+  // consecutive threads -> consecutive 16-byte slots of the OUTPUT (coalesced 128-bit stores)
+  const long long group = i / (8ll * chunks);
+  const int within = static_cast<int>(i - group * 8ll * chunks);
+  const int chunk = within / 8, r8 = within % 8;
+  const long long row = group * 8 + r8;
+  const int k0 = chunk * 16;
+  uint32_t w = 0;
+  const bool has_bits = row < rows_bits;
+  if (has_bits && k0 < words * 32) w = bits[row * words + (k0 >> 5)] >> (k0 & 31);
+  int s0 = 1, s1 = 1;
+  if (thresh != nullptr) {
+    s0 = s1 = -128;
+    if (row < nq) {
+      const int neg_tau = 2 * static_cast<int>(thresh[row]) - nbit;     // in [-nbit, nbit]
+      s0 = neg_tau < -128 ? -128 : (neg_tau > 127 ? 127 : neg_tau);
+      s1 = neg_tau - s0;
+    }
+  }
+  uint32_t o[4];
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    uint32_t x = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + v * 4 + j;
+      uint32_t byte = 0u;
+      if (k < nbit) byte = has_bits ? ((((w >> (v * 4 + j)) & 1u) != 0u) ? 0x01u : 0xffu) : 0u;
+      else if (k == nbit) byte = static_cast<uint32_t>(s0) & 0xffu;
+      else if (k == nbit + 1) byte = static_cast<uint32_t>(s1) & 0xffu;
+      x |= byte << (8 * j);
+    }
+    o[v] = x;
+  }
+  reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+typedef void (*sel_fn_t)(const SelDev);
+template <int KB>
+sel_fn_t pick_dense(int dense, size_t* smem) {
+  *smem = SelSmem<KB>::total;
+  return dense ? hamming_select_tc_kernel<KB, true> : hamming_select_tc_kernel<KB, false>;
+}
+sel_fn_t pick_sel(int kb, int dense, size_t* smem) {
+  switch (kb) {
+    case 32: return pick_dense<32>(dense, smem);
+    case 64: return pick_dense<64>(dense, smem);
+    case 96: return pick_dense<96>(dense, smem);
+    case 128: return pick_dense<128>(dense, smem);
+    default: return pick_dense<160>(dense, smem);
+  }
+}
+
+}  // namespace
+
+extern "C" int ch_tc_code_bytes(int nbit) {
+  if (nbit <= 0 || nbit > 128) return 0;
+  return (nbit + 2 + 31) / 32 * 32;   // the codes + the two threshold slots, in whole 32-byte K blocks
+}
+
+extern "C" int ch_expand_i8(ch_ws* ws, const uint32_t* bits_dev, int64_t rows_bits, int nbit, int8_t* out_dev,
+                            int64_t rows_out, const uint32_t* thresh_dev, int64_t nq, void* stream) {
+  if (ws == nullptr || bits_dev == nullptr || out_dev == nullptr) CH_FAIL("null argument to ch_expand_i8");
+  const int kb = ch_tc_code_bytes(nbit);
+  if (kb == 0) CH_FAIL("nbit=%d unsupported by the tensor-core path (1..128)", nbit);
+  if (rows_out % 8 || rows_bits < 0 || rows_out < rows_bits) CH_FAIL("rows_out must be a multiple of 8 and >= rows_bits");
+  if (rows_out == 0) return 0;
+  ChDeviceGuard guard(ws->device);
+  const long long n = rows_out * (kb / 16);
+  expand_i8_tiled_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      bits_dev, rows_bits, rows_out, ch_code_words(nbit), nbit, kb, thresh_dev, nq, out_dev);
+  CH_LAUNCH_CHECK(ws);
+  return 0;
+}
+
+extern "C" int ch_hamming_select_tc(ch_ws* ws, const ch_select_args* a, void* stream) {
+  if (ws == nullptr || a == nullptr) CH_FAIL("null argument to ch_hamming_select_tc");
+  if (a->q_i8 == nullptr || a->g_i8 == nullptr || a->cand_off == nullptr || a->cand_cap == nullptr ||
+      a->cand_cnt == nullptr || a->cand_rows == nullptr || a->err_flag == nullptr)
+    CH_FAIL("null array in ch_select_args");
+  const int kb = ch_tc_code_bytes(a->nbit);
+  if (kb == 0) CH_FAIL("nbit=%d unsupported by the tensor-core path (1..128)", a->nbit);
+  if (a->nq <= 0 || a->ndb < 0) CH_FAIL("bad arguments");
+  if (a->nq_pad % kTileM || a->nq_pad < a->nq) CH_FAIL("nq_pad must be a multiple of %d and >= nq", kTileM);
+  if (a->nstripes <= 0 || a->rows_per_stripe <= 0 || a->rows_per_stripe % kTileN ||
+      static_cast<long long>(a->nstripes) * a->rows_per_stripe < a->ndb)
+    CH_FAIL("bad stripe geometry");
+  if (a->row_base < 0 || a->row_base + a->ndb > 0x7fffffffll) CH_FAIL("shard-local row indices must fit 31 bits");
+  if ((reinterpret_cast<uintptr_t>(a->q_i8) | reinterpret_cast<uintptr_t>(a->g_i8)) & 15)
+    CH_FAIL("operands must be 16-byte aligned");
+  ChDeviceGuard guard(ws->device);
+  SelDev d;
+  d.q_i8 = a->q_i8; d.g_i8 = a->g_i8;
+  d.cand_off = a->cand_off; d.cand_cap = a->cand_cap; d.cand_cnt = a->cand_cnt; d.cand_rows = a->cand_rows;
+  d.err_flag = a->err_flag;
+  d.nq = a->nq; d.nq_pad = a->nq_pad; d.ndb = a->ndb; d.row_base = a->row_base;
+  d.rows_per_stripe = a->rows_per_stripe;
+  d.nqtiles128 = static_cast<int>(a->nq_pad / kTileM);
+  d.nqgroups = (d.nqtiles128 + kQT - 1) / kQT;
+  size_t smem = 0;
+  sel_fn_t fn = pick_sel(kb, a->dense != 0, &smem);
+  if (smem > static_cast<size_t>(ws->max_smem_optin)) CH_FAIL("tensor-core kernel needs %zu bytes of shared memory", smem);
+  if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: each CTA owns all 512 TMEM columns
+  CH_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const long long ctas = static_cast<long long>(d.nqgroups) * a->nstripes;
+  if (ctas > 0x7fffffffll) CH_FAIL("grid too large");
+  fn<<<static_cast<unsigned>(ctas), 128 + 128 * kQT, smem, static_cast<cudaStream_t>(stream)>>>(d);
+  CH_LAUNCH_CHECK(ws);
+  return 0;
+}

@@ -80,6 +80,7 @@ class Evaluator:
         self.stream_min_rows = 200_000
         self.stream_chunks = 4
         self.use_tensor_cores = True       # select pass on tcgen05 (int8 +-1 codes) when the shape allows it
+        self.select_dense_override = None  # tests: force the dense / sparse epilogue of the tensor-core kernel
         self.profile = False               # bench: bracket the kernels with CUDA events on the launch stream
         self.events = []                   # (kind, work units, start event, end event)
 
@@ -187,17 +188,6 @@ class Evaluator:
             err_flag=rec["err"] if rec else None, nq=q.n, nq_pad=nq_pad, ndb=g.n, nbit=q.nbit, ternary=ternary,
             label_mode=label_mode, mask_words=lw, emit_mode=emit, nstripes=nstripes, threads=threads,
             rows_per_stripe=rps, key_limit=key_limit)
-        tc = (thresh is not None and self.use_tensor_cores and not ternary and hasattr(self.b, "hamming_select_tc")
-              and label_mode in (L.CH_LAB_NONE, L.CH_LAB_ID) and nq_pad % 128 == 0 and self.b.tc_code_bytes(q.nbit) > 0)
-        if tc:
-            # +-1 int8 planes in the tensor-core operand order, made once per evaluation from the packed bits
-            if q.i8 is None:
-                q.i8 = self._timed("expand_i8", 0, lambda: self.b.expand_i8(q.bits, q.nbit, nq_pad))
-            if g.i8 is None:
-                g.i8 = self._timed("expand_i8", 0, lambda: self.b.expand_i8(g.bits, g.nbit))
-            self._timed("hist_select_tc", q.n * g.n, lambda: self.b.hamming_select_tc(q.i8, g.i8, **args))
-            self.stats["select_kernel"] = "tcgen05"
-            return
         kind = "hist_select" if thresh is not None else ("hist_count_rec" if emit else "hist_count")
         if thresh is not None:
             self.stats["select_kernel"] = "popc"
@@ -224,6 +214,69 @@ class Evaluator:
     def _check_records(self, rec):
         if int(rec["err"].cpu()[0]) != 0:
             raise RuntimeError("internal error: record buffer overflow")
+
+    # ------------------------------------------------------------------ tensor-core select pass -> candidate lists
+    def _tc_ok(self, q, ternary, nq_pad):
+        """the select pass can run on tcgen05: binary codes of <= 128 bits, whole 128-query tiles"""
+        return (self.use_tensor_cores and not ternary and hasattr(self.b, "hamming_select_tc") and
+                nq_pad % 128 == 0 and self.b.tc_code_bytes(q.nbit) > 0)
+
+    def _alloc_cands(self, cap, geo, nq, thresh=None, status=None):
+        """Candidate-list slices per (stripe, query): offsets from the capacities, row / key arrays.  ``status``
+        u32[2]: bit 0 of [0] is raised by the select pass when a slice overflows."""
+        threads, nq_pad, nstripes, rps = geo
+        off = self.b.empty((nstripes, nq_pad), torch.int32)
+        total, tmax = self.b.record_offsets(cap, nstripes, nq, nq_pad, off, thresh)
+        self.stats["record_slots"] = total
+        if status is None:
+            status = self.b.zeros((2,), torch.int32)
+        cand = dict(off=off, cap=cap, cnt=self.b.zeros((nstripes, nq_pad), torch.int32),
+                    rows=self.b.empty((max(total, 1),), torch.int32), key=self.b.empty((max(total, 1),), torch.uint8),
+                    err=status[0:1], status=status)
+        return (cand, tmax) if thresh is not None else cand
+
+    def _dense(self, expected_per_query, ndb_total):
+        """most 32-row x 32-query chunks hold a candidate: the select kernel skips its max-tree pre-filter"""
+        if self.select_dense_override is not None:
+            return bool(self.select_dense_override)
+        return expected_per_query * 1024.0 > 0.78 * max(ndb_total, 1)
+
+    def _query_plane(self, q, nq_pad, thresh):
+        """int8 query plane with the thresholds in its threshold slots (made per select pass)"""
+        return self._timed("expand_i8", 0, lambda: self.b.expand_i8(q.bits, q.nbit, nq_pad, thresh=thresh, nq=q.n))
+
+    def _select_tc(self, q, g, geo, thresh, cand, dense):
+        threads, nq_pad, nstripes, rps = geo
+        q_i8 = self._query_plane(q, nq_pad, thresh)
+        if g.i8 is None:
+            g.i8 = self._timed("expand_i8", 0, lambda: self.b.expand_i8(g.bits, g.nbit))
+        self._timed("hist_select_tc", q.n * g.n, lambda: self.b.hamming_select_tc(
+            q_i8=q_i8, g_i8=g.i8, cand=cand, nq=q.n, nq_pad=nq_pad, ndb=g.n, nbit=q.nbit, nstripes=nstripes,
+            rows_per_stripe=rps, dense=dense))
+        self.stats["select_kernel"] = "tcgen05"
+        self.stats["select_dense"] = bool(dense)
+
+    def _cand_bases(self, c, cand, nbins, need=None):
+        """keys + label matches of the candidates -> per-rank key totals -> all-gather -> bases (+ verification
+        that every query has >= ``need`` candidates: status[1])"""
+        b, comm, q, g = self.b, self.comm, c["q"], c["g"]
+        threads, nq_pad, nstripes, rps = c["geo"]
+        nq, label_mode, lw = c["nq"], c["label_mode"], c["lw"]
+        lab = lambda p: None if label_mode == L.CH_LAB_NONE else (p.ids if label_mode == L.CH_LAB_ID else p.masks)
+        tot = b.zeros((2, nbins, nq_pad), torch.int32)
+        self._timed("cand_hist", 0, lambda: b.cand_hist(
+            cand, q_bits=q.bits, g_bits=g.bits, q_lab=lab(q), g_lab=lab(g), label_mode=label_mode, mask_words=lw,
+            tot_all=tot[0], tot_rel=tot[1] if label_mode != L.CH_LAB_NONE else None, nq=nq, nq_pad=nq_pad,
+            nstripes=nstripes, nbins=nbins, nbit=q.nbit))
+        tot = comm.all_gather(tot)                                   # (world, 2, nbins, nq_pad)
+        base0_all = b.empty((nbins, nq_pad), torch.int32)
+        base0_rel = b.empty((nbins, nq_pad), torch.int32)
+        found = b.zeros((nq_pad,), torch.int32)
+        b.scan_bases(tot[:, 0].contiguous(), comm.world, comm.rank, nbins, nq, nq_pad, -1, base0_all, None, found)
+        b.scan_bases(tot[:, 1].contiguous(), comm.world, comm.rank, nbins, nq, nq_pad, -1, base0_rel, None, None)
+        if need is not None:
+            b.check_counts(found, nq, need, cand["status"][1:2])
+        return base0_all, base0_rel
 
     # ------------------------------------------------------------------ the evaluation
     def evaluate(self, db_codes, db_labels, q_codes, q_labels, R, threshold=0.0, PRs=(),
@@ -327,9 +380,29 @@ class Evaluator:
         b, comm = self.b, self.comm
         threads, nq_pad, nstripes, rps = c["geo"]
         nq, rf, r_eff, pr_k = c["nq"], c["rf"], c["r_eff"], c["pr_k"]
-        rec = st["rec"]
         ncols = 2 * len(r_eff) + len(pr_k)
         cols = b.zeros((nq, max(ncols, 1)), torch.float64)
+        if "cand" in st:
+            # candidate lists (tensor-core select pass): ranks straight from the lists
+            cand, nbins = st["cand"], st["nbins"]
+            kw = dict(base0_all=st["base0_all"], base0_rel=st["base0_rel"], nq=nq, nq_pad=nq_pad, nstripes=nstripes,
+                      nbins=nbins, remove_first=bool(rf))
+            first_rel = None
+            if rf:
+                first_rel = b.zeros((nq_pad,), torch.int32)
+                b.cand_finalize(cand, mode=1, first_rel_out=first_rel, **kw)
+                first_rel = comm.all_reduce_max(first_rel)
+            self._timed("cand_finalize", 0, lambda: b.cand_finalize(cand, mode=0, first_rel=first_rel, cols=cols,
+                                                                    r_eff=r_eff, pr_k=pr_k, **kw))
+            cols = comm.all_reduce_sum(cols)
+            status = cand["status"]
+            if comm.world > 1:
+                status = comm.all_reduce_max(status)
+            ap = b.empty((len(r_eff), nq), torch.float64) if c["return_ap"] else None
+            maps, recalls, precisions, flags = b.reduce_means(cols, st["total_rel"] if pr_k else None, first_rel, nq,
+                                                              len(r_eff), pr_k, ap, status)
+            return maps, recalls, precisions, ap, flags
+        rec = st["rec"]
         f = dict(recs=rec["recs"], rec_off=rec["off"], rec_cnt=rec["cnt"], base0_all=st["base0_all"],
                  base0_rel=st["base0_rel"], sbase_all=st["sbase_all"], sbase_rel=st["sbase_rel"], first_rel=None,
                  partial=b.empty((nstripes, nq_pad, max(ncols, 1)), torch.float64), cols=cols,
@@ -410,6 +483,13 @@ class Evaluator:
             b.scan_bases(tot_r, comm.world, comm.rank, nbins, nq, nq_pad, -1, base0_rel, None, total_rel)
         cap = b.empty((nstripes, nq_pad), torch.int32)
         b.record_caps(0, slab_all, thresh, nstripes, nbins, nq, nq_pad, False, cap)
+        if self._tc_ok(q, ternary, nq_pad):
+            # pass 2 on the tensor cores: candidate lists (exact capacities), ranks from the lists
+            del slab_rel
+            cand = self._alloc_cands(cap, geo, nq)
+            self._select_tc(q, g, geo, thresh, cand, self._dense(1.3 * (c["rmax"] + c["rf"]), c["ndb_total"]))
+            base0_all, base0_rel = self._cand_bases(c, cand, nbins)
+            return dict(cand=cand, base0_all=base0_all, base0_rel=base0_rel, total_rel=total_rel, nbins=nbins)
         if label_mode == L.CH_LAB_ID and 0 < c["nclass"] * nstripes <= (1 << 26):
             b.record_caps(2, self._class_counts(c), q.ids, nstripes, c["nclass"], nq, nq_pad, True, cap)
         b.slab_exscan(slab_all, nstripes, nbins, nq_pad)
@@ -465,8 +545,6 @@ class Evaluator:
             self.rows_pad = b.padded_rows(g.n)
             g.bits = b.empty((self.rows_pad, q.bits.shape[1]), torch.int32)
             g.i8 = b.empty((self.rows_pad, b.tc_code_bytes(q.nbit)), torch.int8)
-            if q.i8 is None:
-                q.i8 = ev._timed("expand_i8", 0, lambda: b.expand_i8(q.bits, q.nbit, nq_pad))
             per = ev._stream_per(nq_pad)
             # loads run on a side stream so that they are not queued behind the (long) select kernels
             self.side = torch.cuda.Stream(device=g.bits.device)
@@ -493,19 +571,14 @@ class Evaluator:
                 done.record(self.side)
             self.loaded[i] = done
 
-        def select(self, i, rec, thresh, slab_all, slab_rel, nbins):
+        def select(self, i, cand, q_i8, dense):
             ev, b, q, g = self.ev, self.ev.b, self.c["q"], self.c["g"]
             threads, nq_pad, nstripes, rps = self.c["geo"]
             s0, s1, r0, r1 = self.blocks[i]
             torch.cuda.current_stream().wait_event(self.loaded[i])
-            args = dict(q_bits=q.bits, q_nz=None, g_bits=g.bits[r0:], g_nz=None, q_lab=q.ids, g_lab=g.ids[r0:],
-                        slab_all=slab_all[s0:], slab_rel=slab_rel[s0:], thresh=thresh, rec_off=rec["off"][s0:],
-                        rec_cap=rec["cap"][s0:], rec_cnt=rec["cnt"][s0:], recs=rec["recs"], err_flag=rec["err"],
-                        nq=self.c["nq"], nq_pad=nq_pad, ndb=r1 - r0, nbit=q.nbit, ternary=False,
-                        label_mode=L.CH_LAB_ID, mask_words=0, emit_mode=L.CH_EMIT_RELEVANT, nstripes=s1 - s0,
-                        threads=threads, rows_per_stripe=rps, key_limit=nbins, row_base=r0)
-            ev._timed("hist_select_tc", self.c["nq"] * (r1 - r0),
-                      lambda: b.hamming_select_tc(q.i8, g.i8[r0:], **args))
+            ev._timed("hist_select_tc", self.c["nq"] * (r1 - r0), lambda: b.hamming_select_tc(
+                q_i8=q_i8, g_i8=g.i8[r0:], cand=cand, nq=self.c["nq"], nq_pad=nq_pad, ndb=r1 - r0, nbit=q.nbit,
+                nstripes=s1 - s0, rows_per_stripe=rps, row_base=r0, dense=dense, stripe0=s0))
 
     def _pass_topr_sampled(self, c, streamed=False):
         """Top-R in ONE full pass.  A 1-in-``sample_stride`` row sample of the gallery is histogrammed first; from
@@ -557,28 +630,42 @@ class Evaluator:
         base_tmp = b.empty((nbins, nq_pad), torch.int32)
         tot_s = comm.all_gather(self._local_totals(slab_s, geo_s, nbins))
         b.scan_bases(tot_s, comm.world, comm.rank, nbins, nq, nq_pad, m, base_tmp, thresh, None)
-        # ---- record capacities: scaled sample candidate counts, never more than the class counts ----
+        # ---- capacities: scaled sample candidate counts (record path: never more than the class counts) ----
         cap = b.empty((nstripes, nq_pad), torch.int32)
         b.record_caps(0, slab_s, thresh, nstripes, nbins, nq, nq_pad, False, cap, sample_stride=stride)
         cls = self._class_counts(c)
-        b.record_caps(2, cls, q.ids, nstripes, c["nclass"], nq, nq_pad, True, cap)
         if streamer is not None:
             streamer.load(0)        # block 0 travels while the GPU is still busy with the sample
+        self.stats["sample"] = dict(stride=stride, rows=ns_total, m=m)
+        if streamed or self._tc_ok(q, ternary, nq_pad):
+            # ---- the one full pass on the tensor cores: candidate lists, then ranks from the lists ----
+            cand, tmax = self._alloc_cands(cap, geo, nq, thresh, status)    # one host sync: slots + max threshold
+            del slab_s, base_tmp
+            nbins = min(nbins, tmax + 1)
+            self.stats["sample"]["key_limit"] = nbins
+            dense = self._dense(1.25 * stride * m, c["ndb_total"])
+            if streamed:
+                q_i8 = self._query_plane(q, nq_pad, thresh)
+                for i in range(len(streamer.blocks)):
+                    streamer.select(i, cand, q_i8, dense)
+                    if i + 1 < len(streamer.blocks):
+                        streamer.load(i + 1)     # host waits for this copy while the GPU runs select(i)
+                self.stats["select_kernel"] = "tcgen05"
+                self.stats["select_dense"] = bool(dense)
+            else:
+                self._select_tc(q, g, geo, thresh, cand, dense)
+            base0_all, base0_rel = self._cand_bases(c, cand, nbins, need)
+            return dict(cand=cand, base0_all=base0_all, base0_rel=base0_rel, nbins=nbins,
+                        total_rel=self._total_rel_from_classes(c, cls))
+        b.record_caps(2, cls, q.ids, nstripes, c["nclass"], nq, nq_pad, True, cap)
         rec, tmax = self._alloc_records(cap, geo, nq, thresh, status)   # one host sync: slots + max threshold
         del slab_s, base_tmp
         # ---- the one full pass; only keys <= max threshold can occur, all slabs / bases are that narrow ----
         nbins = min(nbins, tmax + 1)
         slab_all = b.zeros((nstripes, nbins, nq_pad), torch.int32)
         slab_rel = b.zeros((nstripes, nbins, nq_pad), torch.int32)
-        if streamed:
-            for i in range(len(streamer.blocks)):
-                streamer.select(i, rec, thresh, slab_all, slab_rel, nbins)
-                if i + 1 < len(streamer.blocks):
-                    streamer.load(i + 1)     # host waits for this copy while the GPU runs select(i)
-            self.stats["select_kernel"] = "tcgen05"
-        else:
-            self._hist(q, g, geo, ternary, label_mode, lw, slab_all, slab_rel, thresh=thresh,
-                       emit=L.CH_EMIT_RELEVANT, rec=rec, key_limit=nbins)
+        self._hist(q, g, geo, ternary, label_mode, lw, slab_all, slab_rel, thresh=thresh,
+                   emit=L.CH_EMIT_RELEVANT, rec=rec, key_limit=nbins)
         base0_all = b.empty((nbins, nq_pad), torch.int32)
         base0_rel = b.empty((nbins, nq_pad), torch.int32)
         found = b.zeros((nq_pad,), torch.int32)
@@ -589,19 +676,23 @@ class Evaluator:
         # ---- verification: status[1] is raised if some query has fewer than `need` candidates; it is read back
         # together with the results (the finalisation below runs speculatively)
         b.check_counts(found, nq, need, rec["status"][1:2])
-        self.stats["sample"] = dict(stride=stride, rows=ns_total, m=m, key_limit=nbins)
+        self.stats["sample"]["key_limit"] = nbins
         b.slab_exscan(slab_all, nstripes, nbins, nq_pad)
         b.slab_exscan(slab_rel, nstripes, nbins, nq_pad)
-        total_rel = b.zeros((nq_pad,), torch.int32)
+        return dict(rec=rec, base0_all=base0_all, base0_rel=base0_rel, sbase_all=slab_all, sbase_rel=slab_rel,
+                    total_rel=self._total_rel_from_classes(c, cls), nbins=nbins)
+
+    def _total_rel_from_classes(self, c, cls):
+        """relevant items in the whole gallery per query = class frequency of the query's class (single-label)"""
+        b, comm, q, nq = self.b, self.comm, c["q"], c["nq"]
+        total_rel = b.zeros((c["geo"][1],), torch.int32)
         if c["pr_k"]:
-            # relevant items in the whole gallery = class frequency of the query's class
             cls_tot = cls.sum(0, dtype=torch.int32)
             cls_tot = comm.all_reduce_sum(cls_tot) if comm.world > 1 else cls_tot
             qid = q.ids[:nq].to(torch.int64)
             ok = (qid >= 0) & (qid < c["nclass"])
             total_rel[:nq] = torch.where(ok, cls_tot[qid.clamp(0, c["nclass"] - 1)], torch.zeros_like(cls_tot[:1]))
-        return dict(rec=rec, base0_all=base0_all, base0_rel=base0_rel, sbase_all=slab_all, sbase_rel=slab_rel,
-                    total_rel=total_rel, nbins=nbins)
+        return total_rel
 
     def _local_totals(self, slab, geo, nbins):
         threads, nq_pad, nstripes, rps = geo
@@ -653,13 +744,26 @@ class Evaluator:
         b.scan_bases(tot_a, comm.world, comm.rank, nbins, nq, nq_pad, R + rf, base0_all, thresh, None)
         cap = b.empty((nstripes, nq_pad), torch.int32)
         b.record_caps(0, slab_all, thresh, nstripes, nbins, nq, nq_pad, False, cap)
+        ids = b.full((nq, max(R, 1)), -1, torch.int64)
+        keys = b.full((nq, max(R, 1)), -1, torch.int32)
+        if self._tc_ok(q, ternary, nq_pad) and R > 0:
+            cand = self._alloc_cands(cap, geo, nq)
+            self._select_tc(q, g, geo, thresh, cand, self._dense(1.3 * (R + rf), ndb_total))
+            c = dict(q=q, g=g, geo=geo, nq=nq, label_mode=L.CH_LAB_NONE, lw=0)
+            base0_c, _ = self._cand_bases(c, cand, nbins)
+            b.cand_finalize(cand, mode=2, base0_all=base0_c, base0_rel=None, nq=nq, nq_pad=nq_pad, nstripes=nstripes,
+                            nbins=nbins, remove_first=bool(rf), ids=ids, keys=keys, R=R, row_offset=row_offset)
+            if int(cand["err"].cpu()[0]) != 0:
+                raise RuntimeError("internal error: candidate list overflow")
+            if comm.world > 1:
+                ids = comm.all_reduce_max(ids)
+                keys = comm.all_reduce_max(keys)
+            return ids[:, :R], keys[:, :R], ternary
         b.slab_exscan(slab_all, nstripes, nbins, nq_pad)
         rec = self._alloc_records(cap, geo, nq)
         scratch_all = b.zeros((nstripes, nbins, nq_pad), torch.int32)
         self._hist(q, g, geo, ternary, L.CH_LAB_NONE, 0, scratch_all, None, thresh=thresh,
                    emit=L.CH_EMIT_CANDIDATES, rec=rec)
-        ids = b.full((nq, max(R, 1)), -1, torch.int64)
-        keys = b.full((nq, max(R, 1)), -1, torch.int32)
         f = dict(recs=rec["recs"], rec_off=rec["off"], rec_cnt=rec["cnt"], base0_all=base0_all, base0_rel=None,
                  sbase_all=slab_all, sbase_rel=None, first_rel=None, partial=None, cols=None, nq=nq, nq_pad=nq_pad,
                  nstripes=nstripes, nbins=nbins, remove_first=bool(rf), r_eff=[], pr_k=[])

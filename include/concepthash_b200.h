@@ -136,16 +136,71 @@ int ch_hist_geometry(ch_ws* ws, int64_t nq, int64_t ndb, int nbit, int ternary, 
                      int32_t* rows_per_stripe);
 int ch_hamming_hist(ch_ws* ws, const ch_hist_args* a, void* stream);
 
-/* ---- K2, tensor-core form of the select pass (same inputs / outputs as ch_hamming_hist with `thresh` set) ----
- * +-1 codes as int8: <q, g> = nbit - 2 * hamming, computed by tcgen05.mma kind::i8 (UTCIMMA) with the
- * accumulators in TMEM; binary codes only, nbit <= 128, label modes NONE / ID.  The int8 planes are made from
- * the packed bits by ch_expand_i8 in the shared-memory operand order (8-row x 16-byte core matrices), so the
- * kernel streams them with plain 1-D bulk copies.  ch_tc_code_bytes(nbit) = bytes per row (multiple of 32),
- * 0 if the path does not support nbit.  out_dev of ch_expand_i8: rows_pad * ch_tc_code_bytes(nbit) bytes. */
+/* ---- K2, tensor-core form of the select pass -------------------------------------------------------
+ * Same question as ch_hamming_hist with `thresh` set -- which pairs have key <= thresh[q]? -- answered by
+ * tcgen05.mma kind::i8 (UTCIMMA) with the accumulators in TMEM: for +-1 codes held as int8,
+ * <q, g> = nbit - 2 * hamming.  Binary codes only, nbit <= 128.  The int8 planes are made from the packed bits
+ * by ch_expand_i8 in the shared-memory operand order (8-row x 16-byte core matrices), so the kernel streams
+ * them with plain 1-D bulk copies.  ch_tc_code_bytes(nbit) = bytes per plane row: the codes plus two
+ * "threshold slots" (bytes nbit, nbit + 1), rounded up to whole 32-byte K blocks; 0 if nbit is unsupported.
+ * The slots hold (1, 1) on the gallery side and (a, b), a + b = -(nbit - 2 * thresh[q]), on the query side, so
+ * that the accumulator is  <q, g> - (nbit - 2 * thresh[q])  and  key <= thresh  <=>  accumulator >= 0: the
+ * epilogue only looks at sign bits.
+ *   ch_expand_i8: bits (rows_bits, words) -> out (rows_out, kb) int8, rows_out >= rows_bits, rows_out % 8 == 0
+ *                 (rows past rows_bits get zero codes); thresh_dev == NULL: gallery plane; else query plane
+ *                 (thresh (>= nq) u32; rows >= nq are padding queries that accept nothing).
+ * Output = candidate lists: for every (stripe, query) the shard-local row indices (row_base + row) of the
+ * pairs with key <= thresh[q], ascending, in the slice [cand_off, cand_off + cand_cap) of cand_rows;
+ * cand_cnt = number written; err_flag |= 1 if a slice overflowed (capacities: ch_record_caps source 0,
+ * offsets: ch_record_offsets).  Keys, label matches, ranks and AP follow in ch_cand_hist / ch_cand_finalize. */
+typedef struct ch_select_args {
+  const int8_t* q_i8;         /* query plane  (>= nq_pad rows) */
+  const int8_t* g_i8;         /* gallery plane (rows_pad rows)  */
+  const uint32_t* cand_off;   /* (nstripes, nq_pad) */
+  const uint32_t* cand_cap;   /* (nstripes, nq_pad) */
+  uint32_t* cand_cnt;         /* (nstripes, nq_pad) */
+  uint32_t* cand_rows;        /* u32[] */
+  uint32_t* err_flag;
+  int64_t nq, nq_pad, ndb, row_base;   /* nq_pad % 128 == 0; ndb = rows of this call's row block */
+  int32_t nbit, nstripes, rows_per_stripe;   /* rows_per_stripe % 128 == 0 */
+  int32_t dense;              /* != 0: most 32-row chunks of a warp hold a candidate -> skip the max-tree filter */
+} ch_select_args;
 int ch_tc_code_bytes(int nbit);
-int ch_expand_i8(ch_ws* ws, const uint32_t* bits_dev, int64_t rows_pad, int nbit, int8_t* out_dev, void* stream);
-int ch_hamming_select_tc(ch_ws* ws, const ch_hist_args* a, const int8_t* q_i8_dev, const int8_t* g_i8_dev,
-                         void* stream);
+int ch_expand_i8(ch_ws* ws, const uint32_t* bits_dev, int64_t rows_bits, int nbit, int8_t* out_dev,
+                 int64_t rows_out, const uint32_t* thresh_dev /* or NULL */, int64_t nq, void* stream);
+int ch_hamming_select_tc(ch_ws* ws, const ch_select_args* a, void* stream);
+
+/* ---- K3/K4 on candidate lists ---------------------------------------------------------------------
+ * The rest of `torch.topk` + the per-query numpy AP loop of the missing calculate_mAP, on the candidates only.
+ * Every item with key <= thresh[q] is a candidate, so canonical ranks are counts over candidates:
+ *   ch_cand_hist     per candidate: key = popcount(q ^ g) on the packed codes, relevance by the labels (ids or
+ *                    masks); writes cand_key, ORs bit 31 of cand_rows for relevant candidates, and the per-query
+ *                    key totals tot_all / tot_rel (nbins, nq_pad) of this rank (rows q >= nq untouched).
+ *                    err_flag |= 2 if a candidate has key >= nbins.
+ *   (caller: all-gather the totals over ranks, ch_scan_bases -> base0_all / base0_rel)
+ *   ch_cand_finalize walks each query's list in order (stripe-major = ascending row): rank = base0_all[key] +
+ *                    #earlier candidates of the same key; relrank likewise on relevant ones.
+ *                    mode 0: cols (nq, 2 nR + nPR) AP sums / counts / hits as in ch_finalize_records;
+ *                    mode 1: first_rel_out[q] = 1 iff the rank-0 item is relevant (remove_first_retrieved);
+ *                    mode 2: ids (nq, R) int64 = row_offset + row at its rank, keys (nq, R) int32 (pre-filled -1). */
+typedef struct ch_cand_args {
+  const uint32_t* cand_off;  const uint32_t* cand_cnt;    /* (nstripes, nq_pad) */
+  uint32_t* cand_rows;       uint8_t* cand_key;           /* per candidate slot */
+  const uint32_t* q_bits;    const uint32_t* g_bits;      /* packed codes (hist only) */
+  const uint32_t* q_lab;     const uint32_t* g_lab;       /* ids or masks; NULL if CH_LAB_NONE (hist only) */
+  uint32_t* tot_all;         uint32_t* tot_rel;           /* (nbins, nq_pad) out of ch_cand_hist */
+  const uint32_t* base0_all; const uint32_t* base0_rel;   /* (nbins, nq_pad) in of ch_cand_finalize */
+  const uint32_t* first_rel; uint32_t* first_rel_out;     /* (nq_pad) */
+  double*  cols;             /* (nq, ncols) */
+  int64_t* ids;  int32_t* keys;   /* (nq, R) */
+  uint32_t* err_flag;
+  int64_t nq, nq_pad, R, row_offset;
+  int32_t nstripes, nbins, nbit, label_mode, mask_words, remove_first, nR, nPR, mode;
+  int64_t r_eff[CH_MAX_R];
+  int64_t pr_k[CH_MAX_PR];
+} ch_cand_args;
+int ch_cand_hist(ch_ws* ws, const ch_cand_args* a, void* stream);
+int ch_cand_finalize(ch_ws* ws, const ch_cand_args* a, void* stream);
 
 /* slab reductions: totals over stripes -> tot (nbins, nq_pad); exclusive scan over stripes in place */
 int ch_slab_totals(ch_ws* ws, const uint32_t* slab, int nstripes, int nbins, int64_t nq_pad,

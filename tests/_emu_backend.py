@@ -1,7 +1,7 @@
 """numpy emulation of the CUDA backend's entry points -- TEST INFRASTRUCTURE ONLY.
 
 It mirrors the *semantics* of every C-ABI call (stripes, {all, relevant} slabs, in-stripe stable
-prefixes, 16-byte records, bases, thresholds, capacities, finalisation) on CPU tensors so that
+prefixes, 16-byte records, candidate lists, bases, thresholds, capacities, finalisation) on CPU tensors so that
 ``concepthash_b200.evaluator`` -- the real orchestration code, including its torch.distributed
 exchanges -- can be exercised without a GPU (single process and gloo world_size 2).  The product never
 imports this module; ``concepthash_b200.hashing`` only ever builds a ``CudaBackend``.
@@ -27,10 +27,11 @@ class EmuBackend:
     name = "emu"
     stripe_align = 1
 
-    def __init__(self, rows_per_stripe=64, threads=32):
+    def __init__(self, rows_per_stripe=64, threads=32, tensor_cores=False):
         self.rps = rows_per_stripe
         self.threads = threads
         self.launches = 0
+        self.tensor_cores = tensor_cores     # emulate the candidate-list path (needs threads % 128 == 0)
 
     # plumbing
     def zeros(self, shape, dtype):
@@ -181,6 +182,117 @@ class EmuBackend:
                         sr[s, k, q] += v
                 if emit_mode != CH_EMIT_NONE:
                     cnt[s, q] = min(n_rec, cap[s, q])
+
+    # K2, tensor-core form (candidate lists).  The emulation keeps the packed bits + thresholds instead of int8 planes.
+    def tc_code_bytes(self, nbit):
+        if not self.tensor_cores or nbit <= 0 or nbit > 128:
+            return 0
+        return (nbit + 2 + 31) // 32 * 32
+
+    def expand_i8(self, bits, nbit, min_rows=0, thresh=None, nq=0):
+        self.launches += 1
+        return dict(bits=bits, nbit=nbit, nq=nq, thresh=None if thresh is None else thresh.clone())
+
+    def hamming_select_tc(self, *, q_i8, g_i8, cand, nq, nq_pad, ndb, nbit, nstripes, rows_per_stripe, row_base=0,
+                          dense=False, stripe0=0):
+        self.launches += 1
+        keys = self._keys(q_i8["bits"], None, g_i8["bits"], None, nq, ndb, nbit, False)
+        th = _u32(q_i8["thresh"])
+        off, cap, cnt, rows = _u32(cand["off"]), _u32(cand["cap"]), _u32(cand["cnt"]), _u32(cand["rows"])
+        for s in range(nstripes):
+            r0, r1 = s * rows_per_stripe, min(ndb, (s + 1) * rows_per_stripe)
+            for q in range(nq):
+                js = [j + row_base for j in range(r0, r1) if keys[q, j] <= th[q]]
+                w = min(len(js), int(cap[s + stripe0, q]))
+                o = int(off[s + stripe0, q])
+                rows[o:o + w] = js[:w]
+                cnt[s + stripe0, q] = w
+                if len(js) > w:
+                    _u32(cand["err"])[0] |= 1
+
+    # K3/K4 on candidate lists
+    def cand_hist(self, cand, *, q_bits, g_bits, q_lab, g_lab, label_mode, mask_words, tot_all, tot_rel, nq, nq_pad,
+                  nstripes, nbins, nbit):
+        self.launches += 1
+        off, cnt, rows, key = _u32(cand["off"]), _u32(cand["cnt"]), _u32(cand["rows"]), cand["key"].numpy()
+        qs, gs = _unpack(_u32(q_bits)[:nq], nbit), _unpack(_u32(g_bits), nbit)
+        ta = _u32(tot_all)
+        tr = _u32(tot_rel) if tot_rel is not None else None
+        for q in range(nq):
+            ta[:, q] = 0
+            if tr is not None:
+                tr[:, q] = 0
+            for s in range(nstripes):
+                o = int(off[s, q])
+                for i in range(int(cnt[s, q])):
+                    row = int(rows[o + i] & 0x7FFFFFFF)
+                    k = int((qs[q] != gs[row]).sum())
+                    if label_mode == CH_LAB_ID:
+                        r = _u32(q_lab)[q] == _u32(g_lab)[row]
+                    elif label_mode == CH_LAB_MASK:
+                        r = bool((_u32(q_lab)[q, :mask_words] & _u32(g_lab)[row, :mask_words]).any())
+                    else:
+                        r = False
+                    if k < nbins:
+                        ta[k, q] += 1
+                        if r and tr is not None:
+                            tr[k, q] += 1
+                    else:
+                        _u32(cand["err"])[0] |= 2
+                    key[o + i] = k
+                    rows[o + i] = row | (0x80000000 if r else 0)
+
+    def cand_finalize(self, cand, *, mode, base0_all, base0_rel, nq, nq_pad, nstripes, nbins, remove_first=False,
+                      first_rel=None, first_rel_out=None, cols=None, r_eff=(), pr_k=(), ids=None, keys=None, R=0,
+                      row_offset=0):
+        self.launches += 1
+        off, cnt, rows, key = _u32(cand["off"]), _u32(cand["cnt"]), _u32(cand["rows"]), cand["key"].numpy()
+        ba = _u32(base0_all)
+        br = _u32(base0_rel) if base0_rel is not None else None
+        r_eff, pr_k = list(r_eff), list(pr_k)
+        if mode == 0:
+            cols.numpy()[...] = 0
+        for q in range(nq):
+            run_all = {k: int(ba[k, q]) for k in range(nbins)}
+            run_rel = {k: (int(br[k, q]) if br is not None else 0) for k in range(nbins)}
+            for s in range(nstripes):
+                o = int(off[s, q])
+                for i in range(int(cnt[s, q])):
+                    k = int(key[o + i])
+                    if k >= nbins:
+                        continue
+                    rel = bool(rows[o + i] >> 31)
+                    row = int(rows[o + i] & 0x7FFFFFFF)
+                    rank, relrank = run_all[k], run_rel[k]
+                    run_all[k] += 1
+                    if rel:
+                        run_rel[k] += 1
+                    if mode == 1:
+                        if rank == 0 and rel:
+                            _u32(first_rel_out)[q] = 1
+                        continue
+                    if remove_first:
+                        if rank == 0:
+                            continue
+                        rank -= 1
+                        relrank -= int(_u32(first_rel)[q]) if first_rel is not None else 0
+                    if mode == 2:
+                        if rank < R:
+                            ids[q, rank] = row_offset + row
+                            if keys is not None:
+                                keys[q, rank] = k
+                        continue
+                    if not rel:
+                        continue
+                    prec = (relrank + 1) / (rank + 1)
+                    c = cols.numpy()
+                    for j, r in enumerate(r_eff):
+                        if rank < r:
+                            c[q, 2 * j] += prec
+                            c[q, 2 * j + 1] += 1
+                    for j, kk in enumerate(pr_k):
+                        if rank < kk:
+                            c[q, 2 * len(r_eff) + j] += 1
 
     def slab_totals(self, slab, nstripes, nbins, nq_pad, out):
         self.launches += 1

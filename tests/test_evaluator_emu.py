@@ -13,8 +13,10 @@ from oracle import map_oracle as mo
 from tests._emu_backend import EmuBackend
 
 
-def run_case(d, dl, q, ql, R, PRs=(), rf=False, thr=0.0, rps=64, sampled=False):
-    ev = Evaluator(EmuBackend(rows_per_stripe=rps))
+def run_case(d, dl, q, ql, R, PRs=(), rf=False, thr=0.0, rps=64, sampled=False, tc=False):
+    # tc: the candidate-list path of the tensor-core select pass (whole 128-query tiles)
+    ev = Evaluator(EmuBackend(rows_per_stripe=rps, threads=128, tensor_cores=True) if tc
+                   else EmuBackend(rows_per_stripe=rps))
     if sampled:
         ev.sample_stride, ev.sample_min_rows, ev.sample_min_ratio = 4, 0, 4
     else:
@@ -158,3 +160,57 @@ def test_sampled_falls_back_on_adversarial_order():
     # benign order: verifies and stays in the one-pass mode
     ev = run_case(d, dl, q, ql, 30, PRs=[1, 5], rps=64, sampled=True)
     assert ev.stats["mode"] == "topR-sampled"
+
+
+# ---------------------------------------------------------------- candidate-list path (tensor-core select pass)
+@pytest.mark.parametrize("seed", range(4))
+def test_candidate_path_exact_two_pass(seed):
+    nbit = [16, 32, 64, 128][seed]
+    d, dl, q, ql, _ = synth.make_random_case(11, 300 + 31 * seed, nbit, 4, p=0.3, seed=60 + seed)
+    ev = run_case(d, dl, q, ql, 20, PRs=[1, 5, 10], rps=64, tc=True)
+    assert ev.stats["mode"] == "topR" and ev.stats["select_kernel"] == "tcgen05"
+    run_case(d, dl, q, ql, [3, 11, 40], PRs=[2], rps=48, tc=True)
+    ev = run_case(d, dl, d[:9].clone(), dl[:9].clone(), 7, PRs=[1, 5], rf=True, rps=32, tc=True)
+    assert ev.stats["select_kernel"] == "tcgen05"
+
+
+def test_candidate_path_multi_hot():
+    g = torch.Generator().manual_seed(3)
+    d, _, q, _, _ = synth.make_random_case(13, 240, 32, 5, p=0.3, seed=5)
+    dl = (torch.rand(240, 40, generator=g) < 0.06).float()
+    ql = (torch.rand(13, 40, generator=g) < 0.08).float()
+    ev = run_case(d, dl, q, ql, 9, PRs=[1, 10], rps=32, tc=True)
+    assert ev.stats["label_mode"] == 2 and ev.stats["select_kernel"] == "tcgen05"
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_candidate_path_sampled(seed):
+    nbit = [16, 64, 128][seed]
+    d, dl, q, ql, _ = synth.make_random_case(9, 900 + 50 * seed, nbit, 5, p=0.3, seed=40 + seed)
+    ev = run_case(d, dl, q, ql, 20, PRs=[1, 5, 10], rps=64, sampled=True, tc=True)
+    assert ev.stats["mode"] == "topR-sampled" and ev.stats["select_kernel"] == "tcgen05", ev.stats
+    ev = run_case(d, dl, q, ql, [5, 40], PRs=[], rf=(seed == 1), rps=128, sampled=True, tc=True)
+    assert ev.stats["mode"] in ("topR-sampled", "topR")
+
+
+def test_candidate_path_sampled_falls_back():
+    nbit = 16
+    q = torch.ones(3, nbit)
+    d = -torch.ones(800, nbit)
+    d[0:140:4] = 1.0
+    d[0:140:4, 0] = -1.0
+    dl = torch.arange(800) % 2
+    ql = torch.tensor([0, 1, 0])
+    ev = run_case(d, dl, q, ql, 40, PRs=[1, 5], rps=64, sampled=True, tc=True)
+    assert ev.stats["mode"] == "topR" and ev.stats["sample"]["fallback"]
+
+
+def test_candidate_path_retrieve():
+    d, _, q, _, _ = synth.make_random_case(14, 170, 16, 4, p=0.3, seed=9)
+    for R, rf in [(25, False), (-1, False), (400, False), (10, True)]:
+        ev = Evaluator(EmuBackend(rows_per_stripe=32, threads=128, tensor_cores=True))
+        ids, keys, tern = ev.retrieve(d, q, R, 0.0, rf)
+        assert ev.stats["select_kernel"] == "tcgen05"
+        oids, odist = mo.topk_ids(q, d, R, remove_first_retrieved=rf)
+        assert torch.equal(ids, oids)
+        assert torch.equal(keys.float(), odist)

@@ -12,6 +12,14 @@ from oracle import map_oracle as mo
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-9
+# two exact paths of this library against each other: same ranks, fp64 sums taken in a different order
+EPS = 1e-12
+
+
+def _same(a, b):
+    """(maps, recalls, precisions, ap tensor) of two runs agree to EPS"""
+    return (np.allclose(a[0], b[0], rtol=0, atol=EPS) and np.allclose(a[1], b[1], rtol=0, atol=EPS) and
+            np.allclose(a[2], b[2], rtol=0, atol=EPS) and torch.allclose(a[3], b[3], rtol=0, atol=EPS))
 
 
 @pytest.fixture(scope="module")
@@ -325,8 +333,7 @@ def test_sampled_one_pass_equals_exact_two_pass(H):
         finally:
             ev.sample_stride = 16
         assert mode == ("topR-sampled" if stride else "topR")
-    assert res[16][0] == res[0][0] and res[16][1] == res[0][1] and res[16][2] == res[0][2]
-    assert torch.equal(res[16][3], res[0][3])
+    assert _same(res[16], res[0])
     # adversarial: the 1-in-16 sample sees only near duplicates, the rest of the gallery is far away
     n = 400_000
     dd = -torch.ones(n, 32, device="cuda")
@@ -362,25 +369,28 @@ def test_pack_sign_flat_fast_path(H, nbit, dtype):
 
 @pytest.mark.parametrize("nbit", [32, 48, 64, 96, 128])
 def test_tensor_core_select_equals_popc_select(H, nbit):
-    """The tcgen05 (int8 +-1, UTCIMMA) select pass must give bit-identical results to the XOR+POPC select pass:
-    same AP per query, same ranked ids -- and both match the oracle on a query subset."""
+    """The tcgen05 (int8 +-1, UTCIMMA) select pass + candidate-list ranking must give the results of the XOR+POPC
+    select pass + record ranking: same AP per query (to fp64 summation order), bit-identical ranked ids -- and
+    both match the oracle on a query subset."""
     ev = H.get_evaluator()
     nq, ndb = 700, 260_000 + nbit          # tail tile, several stripes, inactive query lanes in the last tile
     d, dl, q, ql, ncls = synth.make_random_case(nq, ndb, nbit, 30, p=0.30, seed=nbit, device="cuda")
     out = {}
-    for tc in (True, False):
-        ev.use_tensor_cores = tc
+    for tc, dense in ((True, False), (True, True), (False, None)):
+        ev.use_tensor_cores, ev.select_dense_override = tc, dense
         try:
             res = ev.evaluate(d, dl, q, ql, [50, 500], 0.0, [1, 5, 10], False, return_ap=True)
             kern = ev.stats["select_kernel"]
             ids, keys, _ = ev.retrieve(d, q, 300)
-            out[tc] = (res, ids, keys)
+            out[(tc, dense)] = (res, ids, keys)
         finally:
-            ev.use_tensor_cores = True
+            ev.use_tensor_cores, ev.select_dense_override = True, None
         assert kern == ("tcgen05" if tc else "popc")
-    (ra, ia, ka), (rb, ib, kb) = out[True], out[False]
-    assert ra[0] == rb[0] and ra[1] == rb[1] and ra[2] == rb[2] and torch.equal(ra[3], rb[3])
-    assert torch.equal(ia, ib) and torch.equal(ka, kb)
+    rb, ib, kb = out[(False, None)]
+    for dense in (False, True):                 # both epilogue variants of the tensor-core kernel
+        ra, ia, ka = out[(True, dense)]
+        assert _same(ra, rb)
+        assert torch.equal(ia, ib) and torch.equal(ka, kb)
     sub = slice(0, 40)
     om, orec, oprec = mo.calculate_mAP(d.cpu(), dl.cpu(), q[sub].cpu(), ql[sub].cpu(), [50, 500], PRs=[1, 5, 10])
     m, rec, prec = H.calculate_mAP(d, dl, q[sub], ql[sub], [50, 500], PRs=[1, 5, 10])
@@ -398,7 +408,7 @@ def test_streamed_host_gallery_equals_resident(H):
         for host in (d.cpu(), d.cpu().pin_memory()):
             out = ev.evaluate(host, dl.cpu(), q.cpu(), ql.cpu(), [100, 1000], 0.0, [1, 5, 10], False, return_ap=True)
             assert ev.stats["mode"] == "topR-sampled-streamed", ev.stats
-            assert out[0] == ref[0] and out[1] == ref[1] and out[2] == ref[2] and torch.equal(out[3], ref[3])
+            assert _same(out, ref)
     # zeros in the gallery -> ternary keys: the streamed attempt must notice and restart on the regular path
     dz = d.cpu().clone()
     dz[::1000, 5] = 0.0

@@ -40,7 +40,10 @@ def _worker(rank, world, port, out):
             # uneven contiguous split in rank order
             cut = [0, 97, 230] if world == 2 else np.linspace(0, 230, world + 1).astype(int).tolist()
             ds, dls = d[cut[rank]:cut[rank + 1]], dl[cut[rank]:cut[rank + 1]]
-            ev = Evaluator(EmuBackend(rows_per_stripe=32), DistComm())
+            # odd cases run the candidate-list path (tensor-core select pass) where it applies
+            be = EmuBackend(rows_per_stripe=32, threads=128, tensor_cores=True) if case % 2 else \
+                EmuBackend(rows_per_stripe=32)
+            ev = Evaluator(be, DistComm())
             r_list = R if isinstance(R, list) else [R]
             maps, rec, prec = ev.evaluate(ds, dls, q, ql, r_list, thr, PRs, rf)
             ids, keys, tern = ev.retrieve(ds, q, 20, thr, rf)
