@@ -179,7 +179,7 @@ class CudaBackend:
 
     def expand_i8_into(self, bits, nbit, out):
         """gallery plane of a row block: ``bits`` (rows, words) -> ``out`` (rows, kb) views of larger arrays"""
-        assert bits.shape[0] % 8 == 0 and out.shape[0] >= bits.shape[0]
+        assert bits.shape[0] % 32 == 0 and out.shape[0] >= bits.shape[0]
         L.check(self.lib.ch_expand_i8(self.ws, _ptr(bits), int(bits.shape[0]), nbit, _ptr(out), int(bits.shape[0]),
                                       None, 0, self._stream()), "ch_expand_i8")
 
@@ -189,7 +189,7 @@ class CudaBackend:
         ``min_rows`` over-allocates so that whole 128-query tiles can be read."""
         kb = self.tc_code_bytes(nbit)
         rows_pad = int(bits.shape[0])
-        rows = max(rows_pad, (int(min_rows) + 7) // 8 * 8)
+        rows = max(rows_pad, (int(min_rows) + 31) // 32 * 32)
         out = self.empty((rows, kb), torch.int8)
         L.check(self.lib.ch_expand_i8(self.ws, _ptr(bits), rows_pad, nbit, _ptr(out), rows, _ptr(thresh), int(nq),
                                       self._stream()), "ch_expand_i8")

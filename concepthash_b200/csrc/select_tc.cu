@@ -7,20 +7,24 @@
 //
 //     D[q][j] = <q, g_j> - (nbit - 2 * thresh[q])        and        key(q, j) <= thresh[q]  <=>  D[q][j] >= 0.
 //
-// What is left per pair is the SIGN BIT of one TMEM word.  The epilogue funnels the 32 sign bits of a 32-column
-// chunk into one mask (SHF, alu pipe) -- in the "sparse" variant only after a 3-input max tree said that the chunk
-// holds a candidate at all -- and appends the shard-local row index of every candidate to the (stripe, query)
-// slice of the candidate list, in ascending row order (thread = TMEM lane = query; tiles, chunks and bits are
-// visited in row order).  Nothing else happens here: keys, label matches, stable ranks and AP are the business of
-// cand.cu, which only ever sees the candidates (~0.01-0.3 % of the pairs).
+// What is left per pair is the SIGN BIT of one TMEM word.  The epilogue reads the accumulator with
+// tcgen05.ld ... .pack::16b (LDTM.PACK16BIT: the low 16 bits of two adjacent columns per register; |D| < 2^15), so a
+// whole 128-column accumulator fits in 64 registers and is handed back to the tensor core immediately.  Per 32
+// columns, 8 PRMT in sign-replicate mode turn the 32 sign bits into 32 sign BYTES and 8 LOP3 fold them into one
+// 32-bit mask -- in the "sparse" variant only after an 8-instruction AND tree said that the chunk holds a
+// candidate at all.  The gallery plane stores every 32-row block in the row order that makes bit t of that mask
+// the sign of row t (kRowOfColumn).  The shard-local row index of every candidate is appended to the
+// (stripe, query) slice of the candidate list, in ascending row order (thread = TMEM lane = query; tiles, chunks
+// and bits are visited in row order).  Nothing else happens here: keys, label matches, stable ranks and AP are
+// the business of cand.cu, which only ever sees the candidates (~0.01-0.3 % of the pairs).
 //
 // Warp roles (640 threads, one CTA per SM, persistent over the tiles of one (4 query tiles, stripe)):
 //   warp 0      producer: 1-D bulk async copies (UBLKCP) of gallery tiles into a 4-stage ring
-//   warp 1      MMA issuer: one elected thread issues KB/32 UTCIMMA per (tile, query tile) into that query tile's
-//               TMEM accumulator (4 accumulators x 128 columns = all 512 columns)
-//   warp 2      TMEM allocator
-//   warps 4-19  epilogue: one warpgroup per query tile; tcgen05.ld 32 columns at a time, double-buffered in
-//               registers so that the load of chunk c+1 is in flight while chunk c is examined
+//   warps 1-3   MMA issuers (one thread each; accumulators 0 / 1 / 2+3): KB/32 UTCIMMA (M = N = 128) per
+//               (tile, query tile) into that query tile's TMEM accumulator (4 x 128 columns = all 512 columns)
+//   warp 2      also the TMEM allocator
+//   warps 4-19  epilogue: one warpgroup per query tile; the accumulator is read with two packed tcgen05.ld.x32 and
+//               released to the MMA issuer BEFORE its sign bits are examined, so the refill overlaps the examination
 // Operands live in shared memory in the canonical NO-SWIZZLE K-major core-matrix layout (8 rows x 16 bytes =
 // 128 contiguous bytes; next 16-byte K chunk at +128 B (LBO); next 8-row group at +8*KB (SBO)).  The int8 planes
 // are stored in HBM already in that order (expand_i8_tiled_kernel), so a tile is one contiguous bulk copy.
@@ -28,9 +32,9 @@
 
 namespace {
 
-constexpr int kTileN = 128;   // gallery rows per MMA tile (TMEM columns per accumulator)
+constexpr int kTileN = 128;   // gallery rows per MMA tile (TMEM columns per accumulator, rows per shared-memory stage)
 constexpr int kTileM = 128;   // queries per query tile
-constexpr int kQT = 4;        // query tiles per CTA (4 accumulators x 128 columns = 512 TMEM columns)
+constexpr int kQT = 4;        // query tiles per CTA (4 accumulators x 128 columns = all 512 TMEM columns)
 constexpr int kStages = 4;    // gallery-tile ring
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -42,16 +46,6 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
-      : "memory");
-}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -94,11 +88,12 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
       "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),      \
       "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
 
+// 64 columns -> 32 registers: r[j] = lo16(column 2j) | lo16(column 2j + 1) << 16.
 // issue only: the registers are NOT valid until tmem_wait(r) has been executed
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld64p_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+      "%14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
       : CH_OUT32(r)
       : "r"(taddr)
       : "memory");
@@ -131,28 +126,56 @@ struct SelSmem {
   static constexpr int total = offB + kStages * kB;
 };
 
-// sign bits of the 32 accumulators of a chunk: bit j = (r[j] < 0); four independent funnel-shift chains
-__device__ __forceinline__ uint32_t sign_mask32(const uint32_t (&r)[32]) {
-  uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+// Column c of a 32-column block holds gallery row kRowOfColumn(c) of the 32-row block: with the PRMT / LOP3
+// folding below, bit 31 - t of the mask then is the sign of row t (leading-zero count = first candidate row).
+__host__ __device__ constexpr int kRowOfColumn(int c) { return 31 - (8 * (c & 3) + (c >> 2)); }
+
+// 16 packed registers = 32 columns -> mask, bit 31 - t = 1 iff the accumulator of row t is negative (no candidate).
+// PRMT selector nibbles 9, b, d, f: bytes 1, 3 (sign bytes of the halves of x) and 5, 7 (of y), sign-replicated.
+__device__ __forceinline__ uint32_t sign_mask32p(const uint32_t* r) {
+  uint32_t m = 0;
 #pragma unroll
-  for (int j = 7; j >= 0; --j) {
-    m0 = __funnelshift_l(r[j], m0, 1);
-    m1 = __funnelshift_l(r[8 + j], m1, 1);
-    m2 = __funnelshift_l(r[16 + j], m2, 1);
-    m3 = __funnelshift_l(r[24 + j], m3, 1);
+  for (int k = 0; k < 8; ++k) {
+    uint32_t p;
+    asm("prmt.b32 %0, %1, %2, 0xfdb9;" : "=r"(p) : "r"(r[2 * k]), "r"(r[2 * k + 1]));
+    m |= p & (0x01010101u << k);
   }
-  return __byte_perm(__byte_perm(m0, m1, 0x0040), __byte_perm(m2, m3, 0x0040), 0x5410);
+  return m;
+}
+// true iff some accumulator of the 32 columns is >= 0: 3-input AND tree over the packed registers
+__device__ __forceinline__ bool any_candidate32p(const uint32_t* r) {
+  const uint32_t a0 = r[0] & r[1] & r[2], a1 = r[3] & r[4] & r[5], a2 = r[6] & r[7] & r[8];
+  const uint32_t a3 = r[9] & r[10] & r[11], a4 = r[12] & r[13] & r[14];
+  const uint32_t x = (a0 & a1 & a2) & (a3 & a4 & r[15]);
+  return (x & 0x80008000u) != 0x80008000u;
 }
 
-__device__ __forceinline__ int max32(const uint32_t (&r)[32]) {
-  int x[11];
-#pragma unroll
-  for (int i = 0; i < 10; ++i)
-    x[i] = max(max(static_cast<int>(r[3 * i]), static_cast<int>(r[3 * i + 1])), static_cast<int>(r[3 * i + 2]));
-  x[10] = max(static_cast<int>(r[30]), static_cast<int>(r[31]));
-  const int y0 = max(max(x[0], x[1]), x[2]), y1 = max(max(x[3], x[4]), x[5]);
-  const int y2 = max(max(x[6], x[7]), x[8]), y3 = max(x[9], x[10]);
-  return max(max(max(y0, y1), y2), y3);
+// the MMA with a compile-time accumulate flag (no predicate set-up on the single issuing thread)
+template <bool ACC>
+__device__ __forceinline__ void umma_i8_imm(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc) {
+  if (ACC)
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.eq.u32 p, 1, 1;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc)
+        : "memory");
+  else
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.eq.u32 p, 1, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc)
+        : "memory");
+}
+// tight poll for the one thread whose latency is on the critical path of every tile (the MMA issuer)
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
 }
 
 // One CTA = kQT consecutive 128-query tiles x one gallery stripe.
@@ -178,7 +201,7 @@ __global__ void __launch_bounds__(128 + 128 * kQT, 1) hamming_select_tc_kernel(c
     mbar_init(&bar_a, 1);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&bar_full[s], 1);
-      mbar_init(&bar_empty[s], 1);     // the MMA commit of the tile that used the stage
+      mbar_init(&bar_empty[s], nvalid < 3 ? nvalid : 3);   // one commit per issuing thread that used the stage
     }
     for (int i = 0; i < kQT; ++i) {
       mbar_init(&bar_tfull[i], 1);
@@ -208,36 +231,51 @@ __global__ void __launch_bounds__(128 + 128 * kQT, 1) hamming_select_tc_kernel(c
         const long long r0 = row_begin + static_cast<long long>(k) * kTileN;
         long long rows = row_end - r0;
         if (rows > kTileN) rows = kTileN;
-        const uint32_t rows8 = static_cast<uint32_t>((rows + 7) & ~7ll);   // pad rows exist (ch_padded_rows)
-        const uint32_t bytes_b = rows8 * KB;
+        const uint32_t rows32 = static_cast<uint32_t>((rows + 31) & ~31ll);   // whole (permuted) 32-row blocks; pad
+        const uint32_t bytes_b = rows32 * KB;                                  // rows exist (ch_padded_rows)
         mbar_arrive_expect_tx(&bar_full[s], bytes_b);
         bulk_g2s(smem + S::offB + s * S::kB, a.g_i8 + static_cast<size_t>(r0) * KB, bytes_b, &bar_full[s]);
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0 && ntiles > 0) {
+  } else if (warp <= 3) {
+    // ===================== MMA issuers: warp 1 -> accumulator 0, warp 2 -> 1, warp 3 -> 2 and 3 =====================
+    // A tcgen05.mma is not queued deeply: the issuing thread stalls while its previous MMA executes, and every
+    // commit / barrier poll of that thread leaves the tensor core idle (measured: ~240 clk per accumulator and
+    // tile).  With three issuing threads those gaps are filled by the MMAs of the other threads.
+    const int acc_lo = warp == 3 ? 2 : warp - 1;
+    const int acc_hi = warp == 3 ? 4 : warp;                  // accumulators [acc_lo, acc_hi) of this thread
+    if (lane == 0 && ntiles > 0 && acc_lo < nvalid) {
       // s32 accumulate, s8 x s8, both K-major, N = kTileN, M = 128
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kTileN >> 3) << 17) |
                              (static_cast<uint32_t>(kTileM >> 4) << 24);
-      const uint32_t sbo = 8 * KB, lbo = 128;
-      const uint32_t a_addr = smem_u32(smem + S::offA);
-      mbar_wait_backoff(&bar_a, 0);
+      // descriptors differ only in their 14-bit start-address field (units of 16 B): build one per operand once,
+      // then add constants
+      const uint64_t da0 = umma_desc(smem_u32(smem + S::offA), 128, 8 * KB);
+      const uint64_t db0 = umma_desc(smem_u32(smem + S::offB), 128, 8 * KB);
+      mbar_wait_spin(&bar_a, 0);
+      int s = 0;
+      uint32_t ph_full = 0;
       for (int k = 0; k < ntiles; ++k) {
-        const int s = k % kStages;
-        mbar_wait_backoff(&bar_full[s], static_cast<uint32_t>((k / kStages) & 1));
-        const uint32_t b_addr = smem_u32(smem + S::offB + s * S::kB);
-        for (int i = 0; i < nvalid; ++i) {
-          mbar_wait_backoff(&bar_tempty[i], static_cast<uint32_t>((k & 1) ^ 1));   // accumulator i drained
+        mbar_wait_spin(&bar_full[s], ph_full);
+        const uint64_t db = db0 + static_cast<uint64_t>((s * S::kB) >> 4);
+        const uint32_t ph_empty = static_cast<uint32_t>((k & 1) ^ 1);
+        for (int i = acc_lo; i < acc_hi && i < nvalid; ++i) {
+          mbar_wait_spin(&bar_tempty[i], ph_empty);   // accumulator i read out by its four epilogue warps
           tc_fence_after();
-          const uint32_t d_addr = tmem_base + static_cast<uint32_t>(i) * kTileN;
+          const uint32_t d_addr = tmem_base + static_cast<uint32_t>(i * kTileN);
+          const uint64_t da = da0 + static_cast<uint64_t>((i * S::kA) >> 4);
+          umma_i8_imm<false>(d_addr, da, db, idesc);
 #pragma unroll
-          for (int kk = 0; kk < KB / 32; ++kk)
-            umma_i8(d_addr, umma_desc(a_addr + i * S::kA + kk * 256, lbo, sbo), umma_desc(b_addr + kk * 256, lbo, sbo),
-                    idesc, kk > 0 ? 1u : 0u);
-          umma_commit(&bar_tfull[i]);   // accumulator i holds tile k
+          for (int kk = 1; kk < KB / 32; ++kk)
+            umma_i8_imm<true>(d_addr, da + static_cast<uint64_t>((kk * 256) >> 4),
+                              db + static_cast<uint64_t>((kk * 256) >> 4), idesc);
+          umma_commit(&bar_tfull[i]);           // accumulator i holds tile k
         }
-        umma_commit(&bar_empty[s]);     // the stage may be overwritten once these MMAs retire
+        umma_commit(&bar_empty[s]);             // this thread's MMAs on the stage have retired (one of n_issuers)
+        if (++s == kStages) {
+          s = 0;
+          ph_full ^= 1u;
+        }
       }
     }
   } else if (warp >= 4 && ((warp - 4) >> 2) < nvalid) {
@@ -259,14 +297,12 @@ __global__ void __launch_bounds__(128 + 128 * kQT, 1) hamming_select_tc_kernel(c
     const uint32_t row_lim = active ? static_cast<uint32_t>(a.row_base + row_end) : 0u;
     const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ewarp * 32) << 16) + static_cast<uint32_t>(qt) * kTileN;
 
-    auto examine = [&](const uint32_t (&r)[32], uint32_t row0) {
-      if (!DENSE) {
-        if (max32(r) < 0) return;                  // no candidate among the 32 rows (the usual case)
-      }
-      uint32_t cand = ~sign_mask32(r);
+    // candidates of one 32-row block (bit 31 - t = row row0 + t), appended in ascending row order
+    auto emit = [&](uint32_t cand, uint32_t row0) {
       while (cand != 0u) {
-        const uint32_t row = row0 + static_cast<uint32_t>(__ffs(static_cast<int>(cand)) - 1);
-        cand &= cand - 1u;
+        const uint32_t z = static_cast<uint32_t>(__clz(static_cast<int>(cand)));
+        cand &= ~(0x80000000u >> z);
+        const uint32_t row = row0 + z;
         if (row < row_lim) {
           if (n < cap) out[n] = row;
           ++n;
@@ -279,22 +315,33 @@ __global__ void __launch_bounds__(128 + 128 * kQT, 1) hamming_select_tc_kernel(c
       const uint32_t row0 = static_cast<uint32_t>(a.row_base + row_begin) + static_cast<uint32_t>(k) * kTileN;
       mbar_wait(&bar_tfull[qt], static_cast<uint32_t>(k & 1));
       tc_fence_after();
-      tmem_ld32_issue(taddr0, ra);
+      tmem_ld64p_issue(taddr0, ra);
+      tmem_ld64p_issue(taddr0 + 64, rb);
       tmem_wait(ra);
-      tmem_ld32_issue(taddr0 + 32, rb);            // in flight while chunk 0 is examined
-      examine(ra, row0);
       tmem_wait(rb);
-      tmem_ld32_issue(taddr0 + 64, ra);
-      examine(rb, row0 + 32);
-      tmem_wait(ra);
-      tmem_ld32_issue(taddr0 + 96, rb);
-      examine(ra, row0 + 64);
-      tmem_wait(rb);
-      // every column of the accumulator is in registers: hand it back to the MMA before the last examination
+      // the whole accumulator is in registers: the MMA refills it while its sign bits are examined
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_tempty[qt]);
-      examine(rb, row0 + 96);
+      // all four masks first (independent instruction chains), then the (rare, divergent) candidate loops
+      uint32_t m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
+      if (DENSE) {
+        m0 = ~sign_mask32p(ra);
+        m1 = ~sign_mask32p(ra + 16);
+        m2 = ~sign_mask32p(rb);
+        m3 = ~sign_mask32p(rb + 16);
+      } else {
+        const bool h0 = any_candidate32p(ra), h1 = any_candidate32p(ra + 16);
+        const bool h2 = any_candidate32p(rb), h3 = any_candidate32p(rb + 16);
+        if (h0) m0 = ~sign_mask32p(ra);            // no candidate among the 32 rows is the usual case
+        if (h1) m1 = ~sign_mask32p(ra + 16);
+        if (h2) m2 = ~sign_mask32p(rb);
+        if (h3) m3 = ~sign_mask32p(rb + 16);
+      }
+      emit(m0, row0);
+      emit(m1, row0 + 32);
+      emit(m2, row0 + 64);
+      emit(m3, row0 + 96);
     }
     if (active) {
       a.cand_cnt[sq] = n < cap ? n : cap;
@@ -323,11 +370,13 @@ __global__ void expand_i8_tiled_kernel(const uint32_t* __restrict__ bits, long l
   const long long group = i / (8ll * chunks);
   const int within = static_cast<int>(i - group * 8ll * chunks);
   const int chunk = within / 8, r8 = within % 8;
-  const long long row = group * 8 + r8;
+  const long long row = group * 8 + r8;        // row of the PLANE = TMEM lane (queries) / TMEM column (gallery)
+  // gallery planes: column c of a 32-row block holds row kRowOfColumn(c) of that block (see sign_mask32p)
+  const long long src = thresh != nullptr ? row : (row & ~31ll) + kRowOfColumn(static_cast<int>(row & 31));
   const int k0 = chunk * 16;
   uint32_t w = 0;
-  const bool has_bits = row < rows_bits;
-  if (has_bits && k0 < words * 32) w = bits[row * words + (k0 >> 5)] >> (k0 & 31);
+  const bool has_bits = src < rows_bits;
+  if (has_bits && k0 < words * 32) w = bits[src * words + (k0 >> 5)] >> (k0 & 31);
   int s0 = 1, s1 = 1;
   if (thresh != nullptr) {
     s0 = s1 = -128;
@@ -383,7 +432,8 @@ extern "C" int ch_expand_i8(ch_ws* ws, const uint32_t* bits_dev, int64_t rows_bi
   if (ws == nullptr || bits_dev == nullptr || out_dev == nullptr) CH_FAIL("null argument to ch_expand_i8");
   const int kb = ch_tc_code_bytes(nbit);
   if (kb == 0) CH_FAIL("nbit=%d unsupported by the tensor-core path (1..128)", nbit);
-  if (rows_out % 8 || rows_bits < 0 || rows_out < rows_bits) CH_FAIL("rows_out must be a multiple of 8 and >= rows_bits");
+  if (rows_out % 32 || rows_bits < 0 || rows_out < rows_bits)
+    CH_FAIL("rows_out must be a multiple of 32 (whole permuted row blocks) and >= rows_bits");
   if (rows_out == 0) return 0;
   ChDeviceGuard guard(ws->device);
   const long long n = rows_out * (kb / 16);

@@ -146,9 +146,11 @@ int ch_hamming_hist(ch_ws* ws, const ch_hist_args* a, void* stream);
  * The slots hold (1, 1) on the gallery side and (a, b), a + b = -(nbit - 2 * thresh[q]), on the query side, so
  * that the accumulator is  <q, g> - (nbit - 2 * thresh[q])  and  key <= thresh  <=>  accumulator >= 0: the
  * epilogue only looks at sign bits.
- *   ch_expand_i8: bits (rows_bits, words) -> out (rows_out, kb) int8, rows_out >= rows_bits, rows_out % 8 == 0
- *                 (rows past rows_bits get zero codes); thresh_dev == NULL: gallery plane; else query plane
- *                 (thresh (>= nq) u32; rows >= nq are padding queries that accept nothing).
+ *   ch_expand_i8: bits (rows_bits, words) -> out (rows_out, kb) int8, rows_out >= rows_bits, rows_out % 32 == 0
+ *                 (rows past rows_bits get zero codes); thresh_dev == NULL: gallery plane, every 32-row block
+ *                 stored in the row order the kernel's sign-bit folding wants (plane row c of a block = block
+ *                 row 8 (c & 3) + (c >> 2)); else query plane (thresh (>= nq) u32; rows >= nq are padding
+ *                 queries that accept nothing).
  * Output = candidate lists: for every (stripe, query) the shard-local row indices (row_base + row) of the
  * pairs with key <= thresh[q], ascending, in the slice [cand_off, cand_off + cand_cap) of cand_rows;
  * cand_cnt = number written; err_flag |= 1 if a slice overflowed (capacities: ch_record_caps source 0,
