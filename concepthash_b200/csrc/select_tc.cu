@@ -19,9 +19,9 @@
 // the business of cand.cu, which only ever sees the candidates (~0.01-0.3 % of the pairs).
 //
 // Warp roles (640 threads, one CTA per SM, persistent over the tiles of one (4 query tiles, stripe)):
-//   warp 0      producer: 1-D bulk async copies (UBLKCP) of gallery tiles into a 4-stage ring
-//   warps 1-3   MMA issuers (one thread each; accumulators 0 / 1 / 2+3): KB/32 UTCIMMA (M = N = 128) per
-//               (tile, query tile) into that query tile's TMEM accumulator (4 x 128 columns = all 512 columns)
+//   warps 0-3   MMA issuers, one thread per query tile: KB/32 UTCIMMA (M = N = 128) per gallery tile into that
+//               query tile's TMEM accumulator (4 x 128 columns = all 512 columns)
+//   warp 0      its thread is also the producer: 1-D bulk async copies (UBLKCP) of gallery tiles into a 4-stage ring
 //   warp 2      also the TMEM allocator
 //   warps 4-19  epilogue: one warpgroup per query tile; the accumulator is read with two packed tcgen05.ld.x32 and
 //               released to the MMA issuer BEFORE its sign bits are examined, so the refill overlaps the examination
@@ -52,24 +52,6 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// single-thread waiters (producer, MMA issuer) back off so that their spin does not steal issue slots from
-// the epilogue warps sharing the scheduler
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
-  uint32_t done = 0;
-  while (true) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (done) break;
-    __nanosleep(64);
-  }
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -164,7 +146,19 @@ __device__ __forceinline__ void umma_i8_imm(uint32_t tmem_d, uint64_t da, uint64
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc)
         : "memory");
 }
-// tight poll for the one thread whose latency is on the critical path of every tile (the MMA issuer)
+// one non-blocking probe
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0u;
+}
+// tight poll for the threads whose latency is on the critical path of every tile (the MMA issuers)
 __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
   uint32_t done = 0;
   do {
@@ -201,7 +195,7 @@ __global__ void __launch_bounds__(128 + 128 * kQT, 1) hamming_select_tc_kernel(c
     mbar_init(&bar_a, 1);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&bar_full[s], 1);
-      mbar_init(&bar_empty[s], nvalid < 3 ? nvalid : 3);   // one commit per issuing thread that used the stage
+      mbar_init(&bar_empty[s], 4 * nvalid);   // every epilogue warp, once it has seen its accumulator complete
     }
     for (int i = 0; i < kQT; ++i) {
       mbar_init(&bar_tfull[i], 1);
@@ -220,58 +214,66 @@ __global__ void __launch_bounds__(128 + 128 * kQT, 1) hamming_select_tc_kernel(c
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp == 0) {
-    // ===================== producer =====================
-    if (lane == 0 && ntiles > 0) {
-      mbar_arrive_expect_tx(&bar_a, nvalid * S::kA);
-      bulk_g2s(smem + S::offA, a.q_i8 + static_cast<size_t>(qtile0) * kTileM * KB, nvalid * S::kA, &bar_a);
-      for (int k = 0; k < ntiles; ++k) {
-        const int s = k % kStages;
-        mbar_wait_backoff(&bar_empty[s], static_cast<uint32_t>(((k / kStages) & 1) ^ 1));
-        const long long r0 = row_begin + static_cast<long long>(k) * kTileN;
-        long long rows = row_end - r0;
-        if (rows > kTileN) rows = kTileN;
-        const uint32_t rows32 = static_cast<uint32_t>((rows + 31) & ~31ll);   // whole (permuted) 32-row blocks; pad
-        const uint32_t bytes_b = rows32 * KB;                                  // rows exist (ch_padded_rows)
-        mbar_arrive_expect_tx(&bar_full[s], bytes_b);
-        bulk_g2s(smem + S::offB + s * S::kB, a.g_i8 + static_cast<size_t>(r0) * KB, bytes_b, &bar_full[s]);
-      }
-    }
-  } else if (warp <= 3) {
-    // ===================== MMA issuers: warp 1 -> accumulator 0, warp 2 -> 1, warp 3 -> 2 and 3 =====================
-    // A tcgen05.mma is not queued deeply: the issuing thread stalls while its previous MMA executes, and every
-    // commit / barrier poll of that thread leaves the tensor core idle (measured: ~240 clk per accumulator and
-    // tile).  With three issuing threads those gaps are filled by the MMAs of the other threads.
-    const int acc_lo = warp == 3 ? 2 : warp - 1;
-    const int acc_hi = warp == 3 ? 4 : warp;                  // accumulators [acc_lo, acc_hi) of this thread
-    if (lane == 0 && ntiles > 0 && acc_lo < nvalid) {
+  if (warp <= 3) {
+    // ===================== MMA issuers (one thread per accumulator) + producer (the thread of warp 0) ==========
+    // A tcgen05.mma is not queued deeply: the issuing thread stalls ~85 clk per instruction, and every commit /
+    // barrier poll of that thread would leave the tensor core idle (measured with one issuer: ~240 clk per
+    // accumulator and tile).  With one issuing thread per accumulator those gaps are filled by the others' MMAs.
+    // The thread of warp 0 also feeds the gallery-tile ring; it never blocks on a stage unless the very next
+    // tile is missing.
+    const int i = warp;                                       // accumulator / query tile of this thread
+    if (lane == 0 && ntiles > 0 && (i < nvalid || warp == 0)) {
+      const bool issues = i < nvalid;
       // s32 accumulate, s8 x s8, both K-major, N = kTileN, M = 128
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kTileN >> 3) << 17) |
                              (static_cast<uint32_t>(kTileM >> 4) << 24);
       // descriptors differ only in their 14-bit start-address field (units of 16 B): build one per operand once,
       // then add constants
-      const uint64_t da0 = umma_desc(smem_u32(smem + S::offA), 128, 8 * KB);
+      const uint64_t da = umma_desc(smem_u32(smem + S::offA + i * S::kA), 128, 8 * KB);
       const uint64_t db0 = umma_desc(smem_u32(smem + S::offB), 128, 8 * KB);
-      mbar_wait_spin(&bar_a, 0);
+      const uint32_t d_addr = tmem_base + static_cast<uint32_t>(i * kTileN);
+      int next_load = 0;                                      // producer state (warp 0 only)
+      auto load_tile = [&](int t) {
+        const int st = t % kStages;
+        const long long r0 = row_begin + static_cast<long long>(t) * kTileN;
+        long long rows = row_end - r0;
+        if (rows > kTileN) rows = kTileN;
+        const uint32_t rows32 = static_cast<uint32_t>((rows + 31) & ~31ll);   // whole (permuted) 32-row blocks; pad
+        const uint32_t bytes_b = rows32 * KB;                                  // rows exist (ch_padded_rows)
+        mbar_arrive_expect_tx(&bar_full[st], bytes_b);
+        bulk_g2s(smem + S::offB + st * S::kB, a.g_i8 + static_cast<size_t>(r0) * KB, bytes_b, &bar_full[st]);
+      };
+      if (warp == 0) {
+        mbar_arrive_expect_tx(&bar_a, nvalid * S::kA);
+        bulk_g2s(smem + S::offA, a.q_i8 + static_cast<size_t>(qtile0) * kTileM * KB, nvalid * S::kA, &bar_a);
+        for (; next_load < kStages && next_load < ntiles; ++next_load) load_tile(next_load);
+      }
+      if (issues) mbar_wait_spin(&bar_a, 0);
       int s = 0;
       uint32_t ph_full = 0;
       for (int k = 0; k < ntiles; ++k) {
-        mbar_wait_spin(&bar_full[s], ph_full);
-        const uint64_t db = db0 + static_cast<uint64_t>((s * S::kB) >> 4);
-        const uint32_t ph_empty = static_cast<uint32_t>((k & 1) ^ 1);
-        for (int i = acc_lo; i < acc_hi && i < nvalid; ++i) {
-          mbar_wait_spin(&bar_tempty[i], ph_empty);   // accumulator i read out by its four epilogue warps
+        if (issues) {
+          mbar_wait_spin(&bar_full[s], ph_full);
+          mbar_wait_spin(&bar_tempty[i], static_cast<uint32_t>((k & 1) ^ 1));   // read out by its epilogue warps
           tc_fence_after();
-          const uint32_t d_addr = tmem_base + static_cast<uint32_t>(i * kTileN);
-          const uint64_t da = da0 + static_cast<uint64_t>((i * S::kA) >> 4);
+          const uint64_t db = db0 + static_cast<uint64_t>((s * S::kB) >> 4);
           umma_i8_imm<false>(d_addr, da, db, idesc);
 #pragma unroll
           for (int kk = 1; kk < KB / 32; ++kk)
             umma_i8_imm<true>(d_addr, da + static_cast<uint64_t>((kk * 256) >> 4),
                               db + static_cast<uint64_t>((kk * 256) >> 4), idesc);
-          umma_commit(&bar_tfull[i]);           // accumulator i holds tile k
+          umma_commit(&bar_tfull[i]);             // accumulator i holds tile k (and is done reading stage s)
         }
-        umma_commit(&bar_empty[s]);             // this thread's MMAs on the stage have retired (one of n_issuers)
+        if (warp == 0) {
+          // refill every stage whose tile all epilogue warps have seen complete; block only for tile k + 1
+          while (next_load < ntiles && next_load <= k + kStages) {
+            uint64_t* eb = &bar_empty[next_load % kStages];
+            const uint32_t par = static_cast<uint32_t>(((next_load / kStages) & 1) ^ 1);
+            if (next_load == k + 1) mbar_wait_spin(eb, par);
+            else if (!mbar_test(eb, par)) break;
+            load_tile(next_load++);
+          }
+        }
         if (++s == kStages) {
           s = 0;
           ph_full ^= 1u;
@@ -315,6 +317,7 @@ __global__ void __launch_bounds__(128 + 128 * kQT, 1) hamming_select_tc_kernel(c
       const uint32_t row0 = static_cast<uint32_t>(a.row_base + row_begin) + static_cast<uint32_t>(k) * kTileN;
       mbar_wait(&bar_tfull[qt], static_cast<uint32_t>(k & 1));
       tc_fence_after();
+      if (lane == 0) mbar_arrive(&bar_empty[k % kStages]);   // this query tile's MMAs are done with the stage
       tmem_ld64p_issue(taddr0, ra);
       tmem_ld64p_issue(taddr0 + 64, rb);
       tmem_wait(ra);
