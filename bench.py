@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--nbit", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sample-stride", type=int, default=0, help="override the evaluator's row-sample stride")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3 if args.impl == "ours" else args.warmup
@@ -208,6 +209,8 @@ def main():
         d, dl = d[cut[rank]:cut[rank + 1]].contiguous(), dl[cut[rank]:cut[rank + 1]].contiguous()
     total_pairs = float(w["nq"]) * (ndb_full if w["scaling"] == "strong" else ndb_full * world)
     ev = hashing.get_evaluator(device, group)
+    if args.sample_stride:
+        ev.sample_stride = args.sample_stride
     r_list = [w["R"]]
 
     def barrier():

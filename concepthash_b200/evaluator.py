@@ -73,7 +73,7 @@ class Evaluator:
         self.comm = comm if comm is not None else LocalComm()
         self.stats = {}
         self.stripe_rows_override = None   # tests: force the stripe length (multiple of 256 on CUDA)
-        self.sample_stride = 16            # top-R: 1-in-16 row sample picks the threshold (0/1 = exact two-pass)
+        self.sample_stride = 32            # top-R: 1-in-32 row sample picks the threshold (0/1 = exact two-pass)
         self.sample_min_rows = 200_000     # below this the two-pass path is cheap anyway
         self.sample_min_ratio = 64         # ... and the sample must still hold ~R/stride*... rows: need ndb >= ratio * R
         self.stream_host_gallery = True    # host-resident gallery: overlap its H2D copy with the select pass
@@ -308,11 +308,11 @@ class Evaluator:
         cls_ok = label_mode == L.CH_LAB_ID and 0 < nclass <= (1 << 20)
         sampled = (not full_ranking and self.sample_stride > 1 and cls_ok and
                    ndb_total >= self.sample_min_rows and rmax * self.sample_min_ratio <= ndb_total)
-        # sparser sample when the candidates are a tiny fraction of the gallery (their handling is then off the
-        # critical path of the select pass, so a looser threshold costs nothing and the sample pass shrinks)
+        # sparser sample when the candidates are a tiny fraction of the gallery (a looser threshold then costs
+        # little in the select pass and the sample pass shrinks)
         stride = self.sample_stride
         if sampled and stride > 1 and (rmax + rf) * 5000 <= ndb_total:
-            stride *= 4
+            stride *= 2
         geo = b.geometry(nq, g.n, nbit, ternary, label_mode, lw)
         # host-resident gallery on the sampled top-R path: it is streamed in row blocks behind the select pass
         streamed = (g.bits is None and sampled and not ternary and label_mode == L.CH_LAB_ID and geo[1] % 128 == 0
@@ -321,6 +321,10 @@ class Evaluator:
         if streamed:
             min_stripes = self._stream_per(geo[1]) * 2 * self.stream_chunks
         geo = self._agree_geometry(geo, g.n, stride if sampled else 1, min_stripes)
+        if (not streamed and not full_ranking and not self.stripe_rows_override and hasattr(b, "sm_count")
+                and self._tc_ok(q, ternary, geo[1])):
+            # the select pass will run on the tensor cores: stripes that fill its waves (one CTA per SM)
+            geo = self._tc_geometry(geo, g.n, stride if sampled else 1, 0.75 if sampled else 0.1)
         threads, nq_pad, nstripes, rps = geo
         self.stats.update(dict(ternary=ternary, label_mode=label_mode, geometry=geo, nbins=nbins,
                                ndb_total=ndb_total, world=comm.world))
@@ -699,6 +703,33 @@ class Evaluator:
         tot = self.b.empty((nbins, nq_pad), torch.int32)
         self.b.slab_totals(slab, nstripes, nbins, nq_pad, tot)
         return tot
+
+    def _tc_geometry(self, geo, ndb, stride, w_tc):
+        """Stripe count for an evaluation whose select pass runs on the tensor cores.  That kernel has one CTA per
+        SM and ceil(nq_pad / 512) CTAs per stripe; the XOR+POPC kernel (sample / count pass, same stripes) has
+        nq_pad / threads CTAs per stripe and ~3 per SM.  Score = modelled efficiency of both (longest stripe x
+        waves), weighted by the share of the step each pass has (``w_tc``), with a slight preference for few
+        stripes (fewer, tighter candidate slices)."""
+        threads, nq_pad, nstripes, rps = geo
+        sms = self.b.sm_count
+        align = getattr(self.b, "stripe_align", 256) * max(stride, 1)
+        groups, qtiles = -(-nq_pad // 512), -(-nq_pad // threads)
+        best, best_score = None, -1.0
+        for n in range(1, 97):
+            r = -(-ndb // n)
+            r = (r + align - 1) // align * align
+            if -(-ndb // r) != n or (n > 1 and r < 4096):
+                continue
+
+            def eff(ctas_per_stripe, slots):
+                waves = -(-(ctas_per_stripe * n) // slots)
+                return ndb * ctas_per_stripe / float(waves * slots * r)
+            score = w_tc * eff(groups, sms) + (1.0 - w_tc) * eff(qtiles, 3 * sms) - 0.001 * n
+            if score > best_score:
+                best, best_score = (n, r), score
+        if best is None:
+            return geo
+        return threads, nq_pad, best[0], best[1]
 
     def _agree_geometry(self, geo, ndb=None, stride=1, min_stripes=0):
         """threads / nq_pad depend only on (nq, nbins) and are identical on all ranks; the stripe layout is

@@ -325,26 +325,28 @@ def test_sampled_one_pass_equals_exact_two_pass(H):
     ev = H.get_evaluator()
     d, dl, q, ql, ncls = synth.make_random_case(3000, 300_000, 64, 50, p=0.30, seed=5, device="cuda")
     res = {}
-    for stride in (16, 0):
+    default_stride = ev.sample_stride
+    for stride in (default_stride, 16, 0):
         ev.sample_stride = stride
         try:
             res[stride] = ev.evaluate(d, dl, q, ql, [100, 1000], 0.0, [1, 5, 10], False, return_ap=True)
             mode = ev.stats["mode"]
         finally:
-            ev.sample_stride = 16
+            ev.sample_stride = default_stride
         assert mode == ("topR-sampled" if stride else "topR")
-    assert _same(res[16], res[0])
-    # adversarial: the 1-in-16 sample sees only near duplicates, the rest of the gallery is far away
+    assert _same(res[16], res[0]) and _same(res[default_stride], res[0])
+    # adversarial: the row sample sees only near duplicates, the rest of the gallery is far away
     n = 400_000
+    st = default_stride
     dd = -torch.ones(n, 32, device="cuda")
-    dd[0:16 * 900:16] = 1.0                     # 900 near rows, all on sampled positions
+    dd[0:st * 900:st] = 1.0                     # 900 near rows, all on sampled positions
     qq = torch.ones(64, 32, device="cuda")
     ll = torch.arange(n, device="cuda") % 7
     ql2 = torch.arange(64, device="cuda") % 7
     m, rec, prec = H.calculate_mAP(dd, ll, qq, ql2, 1000, PRs=[1, 10])
     assert ev.stats["mode"] == "topR" and ev.stats["sample"]["fallback"]
     rel = (ql2[:, None] == ll[None, :]).cpu().numpy()
-    order = np.concatenate([np.arange(0, 16 * 900, 16), np.setdiff1d(np.arange(n), np.arange(0, 16 * 900, 16))])[:1000]
+    order = np.concatenate([np.arange(0, st * 900, st), np.setdiff1d(np.arange(n), np.arange(0, st * 900, st))])[:1000]
     aps = [mo._ap_from_rel(rel[i, order]) for i in range(64)]
     assert abs(m - float(np.mean(aps))) < TOL
 
