@@ -62,7 +62,7 @@ def make_workload(name, device, nbit_override=None, shard=0):
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.1):
+    def __init__(self, index, period=0.002):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -270,32 +270,47 @@ def main():
         return {
             "kernel": f"hamming_hist_kernel ({name})", "bound": "int-pipe (POPC)",
             "achieved": popc / 1e9, "peak": popc_peak / 1e9, "unit": "Gpopc32/s", "frac": popc / popc_peak,
-            "traffic": None, "algorithmic_work": f"pairs x {words32} popc32 per pair per launch",
+            "traffic": ncu_traffic("hamming_hist_kernel"),
+            "algorithmic_work": f"pairs x {words32} popc32 per pair per launch",
             "peak_source": "ch_popc_peak micro-benchmark run live on this GPU (MEASURED_PEAKS.json has no "
                            "integer-pipe figure); nominal 148 SM x 16 lanes x f",
             "nominal_peak_at_sampled_clock": 148 * 16 * sm_mhz * 1e6 / 1e9,
             "ms_per_launch": t_ms, "pairs_per_launch": hk[1] / hk[2], "pairs_per_s": (hk[1] / hk[2]) / (t_ms * 1e-3),
             "share_of_step": hk[0] / (ms * args.steps)}
 
+    def ncu_traffic(kernel):
+        """DRAM bytes per launch of `kernel` from the committed ncu --set full capture of this workload, or None"""
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                t = json.load(f)
+            return t.get(args.workload, {}).get(kernel)
+        except Exception:
+            return None
+
     def tensor_roofline(kind):
         hk = kinds[kind]
         t_ms = hk[0] / hk[2]
-        kb = (w["nbit"] + 31) // 32 * 32
-        tops = (hk[1] / hk[2]) * kb * 2 / (t_ms * 1e-3) / 1e12
+        pairs = hk[1] / hk[2]
+        kb = ev.b.tc_code_bytes(w["nbit"])                    # K bytes the MMA really contracts (codes + threshold block)
+        tops = pairs * w["nbit"] * 2 / (t_ms * 1e-3) / 1e12   # ALGORITHMIC: nbit int8 MACs per pair
         peak = 2.0 * peaks.get("bf16_tflops", 1590.0)
-        pairs_s = (hk[1] / hk[2]) / (t_ms * 1e-3)
+        pairs_s = pairs / (t_ms * 1e-3)
         return {
-            "kernel": "hamming_select_tc_kernel (select pass on tcgen05.mma kind::i8, accumulators in TMEM)",
+            "kernel": "hamming_select_tc_kernel (select pass: tcgen05.mma kind::i8 -> TMEM, sign-bit epilogue, "
+                      "candidate lists)",
             "bound": "tensor", "achieved": tops, "peak": peak, "unit": "TOP/s (int8)", "frac": tops / peak,
-            "traffic": None, "algorithmic_work": f"pairs x {kb} int8 MACs x 2 per launch",
-            "peak_source": f"2 x bf16_tflops of {peak_src} (int8 dense runs at twice the bf16 rate; no int8 figure is "
-                           "measured)",
-            "note": "the MMA itself is a few percent of the kernel: the pass is bound by its epilogue (one TMEM word "
-                    "read + one compare per pair on 4 warps), reported below in pairs per clock per SM",
+            "traffic": ncu_traffic("hamming_select_tc_kernel"),
+            "algorithmic_work": f"pairs x {w['nbit']} int8 MACs x 2 per launch (the kernel contracts K = {kb} bytes: "
+                                "the codes plus the 32-byte block that carries the per-query threshold)",
+            "peak_source": f"2 x bf16_tflops of {peak_src}: int8 dense runs at twice the bf16 rate and no int8 figure "
+                           "is measured; nominal dense int8 is 4500 TOP/s",
+            "executed_tops_incl_threshold_block": tops * kb / w["nbit"],
+            "frac_of_nominal_int8_4500": tops / 4500.0,
             "pairs_per_clk_per_sm": pairs_s / (148 * sm_mhz * 1e6),
+            "mma_floor_pairs_per_clk_per_sm": 128.0 * 128.0 / (64.0 * (kb // 32)),
             "popc_kernel_ceiling_pairs_per_s": popc_peak / words32,
-            "ms_per_launch": t_ms, "pairs_per_launch": hk[1] / hk[2], "pairs_per_s": pairs_s,
-            "share_of_step": hk[0] / (ms * args.steps)}
+            "ms_per_launch": t_ms, "launches_per_step": hk[2] / args.steps, "pairs_per_launch": pairs,
+            "pairs_per_s": pairs_s, "share_of_step": hk[0] / (ms * args.steps)}
 
     ham_kinds = [k for k in kinds if k.startswith("hist")]
     dom = max(ham_kinds, key=lambda k: kinds[k][0])
@@ -338,7 +353,9 @@ def main():
         line = {
             "metric": "hamming_comparisons_per_sec_64bit", "value": value, "unit": "64-bit comparisons/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None, "dtype": "u32 (xor+popc)",
+            "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
+            "dtype": "s8 x s8 -> s32 (tcgen05 kind::i8 select pass) + u32 xor/popc (sample, count and key passes)"
+            if "hist_select_tc" in kinds else "u32 xor/popc",
             "data": "synthetic",
             "config": {"workload": w["desc"], "nq": w["nq"], "ndb_per_gpu": int(d.shape[0]),
                        "ndb_total": int(ndb_full if w["scaling"] == "strong" else ndb_full * world),

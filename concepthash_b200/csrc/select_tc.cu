@@ -146,6 +146,12 @@ __device__ __forceinline__ void umma_i8_imm(uint32_t tmem_d, uint64_t da, uint64
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc)
         : "memory");
 }
+// one lane of a converged warp (the warp stays converged: values computed around it can live in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0u;
+}
 // one non-blocking probe
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   uint32_t done;
@@ -221,8 +227,10 @@ __global__ void __launch_bounds__(128 + 128 * kQT, 1) hamming_select_tc_kernel(c
     // accumulator and tile).  With one issuing thread per accumulator those gaps are filled by the others' MMAs.
     // The thread of warp 0 also feeds the gallery-tile ring; it never blocks on a stage unless the very next
     // tile is missing.
-    const int i = warp;                                       // accumulator / query tile of this thread
-    if (lane == 0 && ntiles > 0 && (i < nvalid || warp == 0)) {
+    const int i = warp;                                       // accumulator / query tile of this warp
+    // The whole warp runs the loop (converged, warp-uniform values -> descriptors stay in uniform registers);
+    // only the tcgen05 / bulk-copy instructions themselves are issued by one elected lane.
+    if (ntiles > 0 && (i < nvalid || warp == 0)) {
       const bool issues = i < nvalid;
       // s32 accumulate, s8 x s8, both K-major, N = kTileN, M = 128
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kTileN >> 3) << 17) |
@@ -240,12 +248,16 @@ __global__ void __launch_bounds__(128 + 128 * kQT, 1) hamming_select_tc_kernel(c
         if (rows > kTileN) rows = kTileN;
         const uint32_t rows32 = static_cast<uint32_t>((rows + 31) & ~31ll);   // whole (permuted) 32-row blocks; pad
         const uint32_t bytes_b = rows32 * KB;                                  // rows exist (ch_padded_rows)
-        mbar_arrive_expect_tx(&bar_full[st], bytes_b);
-        bulk_g2s(smem + S::offB + st * S::kB, a.g_i8 + static_cast<size_t>(r0) * KB, bytes_b, &bar_full[st]);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&bar_full[st], bytes_b);
+          bulk_g2s(smem + S::offB + st * S::kB, a.g_i8 + static_cast<size_t>(r0) * KB, bytes_b, &bar_full[st]);
+        }
       };
       if (warp == 0) {
-        mbar_arrive_expect_tx(&bar_a, nvalid * S::kA);
-        bulk_g2s(smem + S::offA, a.q_i8 + static_cast<size_t>(qtile0) * kTileM * KB, nvalid * S::kA, &bar_a);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&bar_a, nvalid * S::kA);
+          bulk_g2s(smem + S::offA, a.q_i8 + static_cast<size_t>(qtile0) * kTileM * KB, nvalid * S::kA, &bar_a);
+        }
         for (; next_load < kStages && next_load < ntiles; ++next_load) load_tile(next_load);
       }
       if (issues) mbar_wait_spin(&bar_a, 0);
@@ -257,12 +269,15 @@ __global__ void __launch_bounds__(128 + 128 * kQT, 1) hamming_select_tc_kernel(c
           mbar_wait_spin(&bar_tempty[i], static_cast<uint32_t>((k & 1) ^ 1));   // read out by its epilogue warps
           tc_fence_after();
           const uint64_t db = db0 + static_cast<uint64_t>((s * S::kB) >> 4);
-          umma_i8_imm<false>(d_addr, da, db, idesc);
+          if (elect_one()) {
+            umma_i8_imm<false>(d_addr, da, db, idesc);
 #pragma unroll
-          for (int kk = 1; kk < KB / 32; ++kk)
-            umma_i8_imm<true>(d_addr, da + static_cast<uint64_t>((kk * 256) >> 4),
-                              db + static_cast<uint64_t>((kk * 256) >> 4), idesc);
-          umma_commit(&bar_tfull[i]);             // accumulator i holds tile k (and is done reading stage s)
+            for (int kk = 1; kk < KB / 32; ++kk)
+              umma_i8_imm<true>(d_addr, da + static_cast<uint64_t>((kk * 256) >> 4),
+                                db + static_cast<uint64_t>((kk * 256) >> 4), idesc);
+            umma_commit(&bar_tfull[i]);           // accumulator i holds tile k (and is done reading stage s)
+          }
+          __syncwarp();
         }
         if (warp == 0) {
           // refill every stage whose tile all epilogue warps have seen complete; block only for tile k + 1
