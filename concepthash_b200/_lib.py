@@ -68,6 +68,7 @@ SIGNATURES = {
                                    C.POINTER(C.c_int32)]),
     "ch_hamming_hist": (C.c_int, [P, C.POINTER(HistArgs), P]),
     "ch_tc_code_bytes": (C.c_int, [C.c_int]),
+    "ch_tc_queries_per_cta": (C.c_int, []),
     "ch_expand_i8": (C.c_int, [P, P, C.c_int64, C.c_int, P, C.c_int64, P, C.c_int64, P]),
     "ch_hamming_select_tc": (C.c_int, [P, C.POINTER(SelectArgs), P]),
     "ch_cand_hist": (C.c_int, [P, C.POINTER(CandArgs), P]),

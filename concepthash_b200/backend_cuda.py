@@ -40,6 +40,7 @@ class CudaBackend:
         sm, smem, l2, khz = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         L.check(self.lib.ch_device_info(self.ws, C.byref(sm), C.byref(smem), C.byref(l2), C.byref(khz)))
         self.sm_count, self.max_smem, self.l2_bytes, self.clock_khz = sm.value, smem.value, l2.value, khz.value
+        self.tc_queries_per_cta = int(self.lib.ch_tc_queries_per_cta())
 
     def __del__(self):
         try:

@@ -451,6 +451,8 @@ sel_fn_t pick_sel(int kb, int dense, size_t* smem) {
 
 }  // namespace
 
+extern "C" int ch_tc_queries_per_cta(void) { return kQT * kTileM; }
+
 extern "C" int ch_tc_code_bytes(int nbit) {
   if (nbit <= 0 || nbit > 128) return 0;
   return (nbit + 2 + 31) / 32 * 32;   // the codes + the two threshold slots, in whole 32-byte K blocks

@@ -524,10 +524,10 @@ class Evaluator:
         return ns, view
 
     def _stream_per(self, nq_pad):
-        """Stripes per streamed launch: the launch has per x ceil(nq_pad / 512) CTAs (4 query tiles each), one per
-        SM; pick the smallest per <= 8 that fills its last wave best."""
+        """Stripes per streamed launch: the launch has per x ceil(nq_pad / queries per CTA) CTAs, one per SM; pick
+        the smallest per <= 8 that fills its last wave best."""
         sms = getattr(self.b, "sm_count", 148)
-        groups = max(1, -(-nq_pad // 512))
+        groups = max(1, -(-nq_pad // getattr(self.b, "tc_queries_per_cta", 512)))
         best, best_eff = 1, -1.0
         for per in range(1, 9):
             ctas = per * groups
@@ -706,14 +706,14 @@ class Evaluator:
 
     def _tc_geometry(self, geo, ndb, stride, w_tc):
         """Stripe count for an evaluation whose select pass runs on the tensor cores.  That kernel has one CTA per
-        SM and ceil(nq_pad / 512) CTAs per stripe; the XOR+POPC kernel (sample / count pass, same stripes) has
+        SM and ceil(nq_pad / queries per CTA) CTAs per stripe; the XOR+POPC kernel (sample / count pass, same stripes) has
         nq_pad / threads CTAs per stripe and ~3 per SM.  Score = modelled efficiency of both (longest stripe x
         waves), weighted by the share of the step each pass has (``w_tc``), with a slight preference for few
         stripes (fewer, tighter candidate slices)."""
         threads, nq_pad, nstripes, rps = geo
         sms = self.b.sm_count
         align = getattr(self.b, "stripe_align", 256) * max(stride, 1)
-        groups, qtiles = -(-nq_pad // 512), -(-nq_pad // threads)
+        groups, qtiles = -(-nq_pad // getattr(self.b, "tc_queries_per_cta", 512)), -(-nq_pad // threads)
         best, best_score = None, -1.0
         for n in range(1, 97):
             r = -(-ndb // n)

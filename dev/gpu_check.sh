@@ -1,9 +1,9 @@
 #!/bin/bash
 # usage (under gpurun): bash dev/gpu_check.sh [pytest -k expr] -- runs the GPU parity tests and short benches
 K="${1:-}"
-if [ -n "$K" ]; then python -m pytest tests -m gpu -x -q -k "$K" 2>&1 | tail -8; else python -m pytest tests -m gpu -x -q 2>&1 | tail -8; fi
+if [ -n "$K" ]; then timeout 300 python -m pytest tests -m gpu -x -q -k "$K" 2>&1 | tail -8; else timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -8; fi
 for w in ${WORKLOADS:-cfg4 cfg5}; do
-  python bench.py --workload $w --steps 3 --warmup 3 --no-cpu-baseline ${BENCH_ARGS:-} > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err; echo rc=$?
+  timeout 300 python bench.py --workload $w --steps 3 --warmup 3 --no-cpu-baseline ${BENCH_ARGS:-} > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err; echo rc=$?
   tail -c 700 gpurun_out/bench_$w.err
   python - <<PY
 import json

@@ -168,6 +168,8 @@ typedef struct ch_select_args {
   int32_t dense;              /* != 0: most 32-row chunks of a warp hold a candidate -> skip the max-tree filter */
 } ch_select_args;
 int ch_tc_code_bytes(int nbit);
+/* queries one CTA of the select kernel owns (its grid is ceil(nq_pad / this) x nstripes, one CTA per SM) */
+int ch_tc_queries_per_cta(void);
 int ch_expand_i8(ch_ws* ws, const uint32_t* bits_dev, int64_t rows_bits, int nbit, int8_t* out_dev,
                  int64_t rows_out, const uint32_t* thresh_dev /* or NULL */, int64_t nq, void* stream);
 int ch_hamming_select_tc(ch_ws* ws, const ch_select_args* a, void* stream);
