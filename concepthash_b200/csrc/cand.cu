@@ -69,28 +69,46 @@ __global__ void __launch_bounds__(kCandWarps * 32) cand_hist_kernel(const CandDe
   const uint32_t* qm = a.label_mode == CH_LAB_MASK ? a.q_lab + q * a.lw : nullptr;
   bool bad = false;
   __syncwarp();
+  constexpr int U = 4;                         // candidates per lane in flight (independent gathers)
   for (int s = 0; s < a.nstripes; ++s) {
     const size_t sq = static_cast<size_t>(s) * a.nq_pad + q;
     const uint32_t off = a.cand_off[sq], n = a.cand_cnt[sq];
-    for (uint32_t i = lane; i < n; i += 32) {
-      const uint32_t row = a.cand_rows[off + i] & 0x7fffffffu;
-      const uint32_t key = key_of<W>(qw, a.g_bits, row);
-      bool rel = false;
-      if (a.label_mode == CH_LAB_ID) {
-        rel = __ldg(a.g_lab + row) == qid;
-      } else if (a.label_mode == CH_LAB_MASK) {
-        uint32_t any = 0;
-        for (int w = 0; w < a.lw; ++w) any |= qm[w] & __ldg(a.g_lab + static_cast<size_t>(row) * a.lw + w);
-        rel = any != 0u;
+    for (uint32_t i0 = 0; i0 < n; i0 += 32 * U) {
+      uint32_t row[U], key[U];
+      bool ok[U], rel[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t i = i0 + u * 32 + lane;
+        ok[u] = i < n;
+        row[u] = ok[u] ? (a.cand_rows[off + i] & 0x7fffffffu) : 0u;
       }
-      if (key < static_cast<uint32_t>(a.nbins)) {
-        atomicAdd(&h_all[key], 1u);
-        if (rel) atomicAdd(&h_rel[key], 1u);
-      } else {
-        bad = true;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        key[u] = ok[u] ? key_of<W>(qw, a.g_bits, row[u]) : 0u;
+        rel[u] = false;
+        if (ok[u]) {
+          if (a.label_mode == CH_LAB_ID) {
+            rel[u] = __ldg(a.g_lab + row[u]) == qid;
+          } else if (a.label_mode == CH_LAB_MASK) {
+            uint32_t any = 0;
+            for (int w = 0; w < a.lw; ++w) any |= qm[w] & __ldg(a.g_lab + static_cast<size_t>(row[u]) * a.lw + w);
+            rel[u] = any != 0u;
+          }
+        }
       }
-      a.cand_key[off + i] = static_cast<uint8_t>(key);
-      a.cand_rows[off + i] = row | (rel ? 0x80000000u : 0u);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!ok[u]) continue;
+        const uint32_t i = i0 + u * 32 + lane;
+        if (key[u] < static_cast<uint32_t>(a.nbins)) {
+          atomicAdd(&h_all[key[u]], 1u);
+          if (rel[u]) atomicAdd(&h_rel[key[u]], 1u);
+        } else {
+          bad = true;
+        }
+        a.cand_key[off + i] = static_cast<uint8_t>(key[u]);
+        if (rel[u]) a.cand_rows[off + i] = row[u] | 0x80000000u;
+      }
     }
   }
   __syncwarp();
@@ -99,6 +117,16 @@ __global__ void __launch_bounds__(kCandWarps * 32) cand_hist_kernel(const CandDe
     if (a.tot_rel != nullptr) a.tot_rel[static_cast<size_t>(b) * a.nq_pad + q] = h_rel[b];
   }
   if (bad) atomicOr(a.err_flag, 2u);
+}
+
+// 1 / x for x = 1 .. 2^32: MUFU.RCP64H seed + two Newton steps (relative error < 2^-52; the AP sums only need
+// ~1e-12, a correctly rounded division costs ~40 instructions per relevant candidate)
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
 }
 
 __global__ void __launch_bounds__(kCandWarps * 32) cand_final_kernel(const CandDev a) {
@@ -164,7 +192,7 @@ __global__ void __launch_bounds__(kCandWarps * 32) cand_final_kernel(const CandD
         continue;
       }
       if (!rel) continue;
-      const double prec = static_cast<double>(relrank + 1) / static_cast<double>(rank + 1);
+      const double prec = static_cast<double>(relrank + 1) * fast_rcp(static_cast<double>(rank + 1));
       for (int j = 0; j < a.nR; ++j)
         if (rank < a.r_eff[j]) {
           acc[2 * j] += prec;
