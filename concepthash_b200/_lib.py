@@ -60,7 +60,8 @@ SIGNATURES = {
     "ch_padded_rows": (C.c_int64, [C.c_int64]),
     "ch_code_words": (C.c_int, [C.c_int]),
     "ch_pack_sign": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_double,
-                               P, P, P, P]),
+                               P, P, P, P, P]),
+    "ch_column_sums": (C.c_int, [P, P, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int64, P, P]),
     "ch_pack_labels": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_uint32,
                                  P, P, P, P]),
     "ch_hist_geometry": (C.c_int, [P, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -120,7 +121,7 @@ def load():
             raise NativeLibraryError(f"{LIB_PATH} does not export {name}") from e
         fn.restype = res
         fn.argtypes = args
-    if lib.ch_abi_version() != 1:
+    if lib.ch_abi_version() != 2:
         raise NativeLibraryError("ABI version mismatch: rebuild the library")
     _lib = lib
     return lib

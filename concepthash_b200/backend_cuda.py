@@ -114,7 +114,19 @@ class CudaBackend:
             t = t.contiguous()
         return t, L.CH_MEM_HOST
 
-    def pack_sign(self, codes, threshold, flags, want_nz=True, out=None):
+    def column_sums(self, codes):
+        """fp64 column sums of DEVICE codes (n, nbit) -> f64[nbit] (deterministic)"""
+        if not codes.dtype.is_floating_point:
+            codes = codes.to(torch.float32)
+        t, mem = self._src(codes)
+        assert mem == L.CH_MEM_DEVICE
+        n, nbit = t.shape
+        out = self.empty((nbit,), torch.float64)
+        L.check(self.lib.ch_column_sums(self.ws, _ptr(t), _DTYPES[t.dtype], n, nbit, t.stride(0) if n > 1 else nbit,
+                                        t.stride(1) if nbit > 1 else 1, _ptr(out), self._stream()), "ch_column_sums")
+        return out
+
+    def pack_sign(self, codes, threshold, flags, want_nz=True, out=None, col_sub=None):
         """codes (n, nbit) real -> (bits, nz) u32 (rows_pad, words); ``flags`` u32[1] is OR-ed.
         ``want_nz=False`` skips the non-zero plane (zeros are still detected in ``flags``) and lets
         contiguous inputs take the flat fast path."""
@@ -137,8 +149,8 @@ class CudaBackend:
             thr = float(torch.tensor(thr, dtype=t.dtype))
         rs = t.stride(0) if n > 1 else nbit
         L.check(self.lib.ch_pack_sign(self.ws, _ptr(t), mem, _DTYPES[t.dtype], n, nbit, rs,
-                                      t.stride(1) if nbit > 1 else 1, thr, _ptr(bits), _ptr(nz), _ptr(flags),
-                                      self._stream()), "ch_pack_sign")
+                                      t.stride(1) if nbit > 1 else 1, thr, _ptr(col_sub), _ptr(bits), _ptr(nz),
+                                      _ptr(flags), self._stream()), "ch_pack_sign")
         return bits, nz
 
     def pack_labels(self, labels, nolabel, info=None):

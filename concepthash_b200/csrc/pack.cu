@@ -21,11 +21,13 @@ template <>
 struct Elem<float> {
   typedef float cmp_t;
   static __device__ __forceinline__ float load(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ float round16(float x) { return x; }
 };
 template <>
 struct Elem<double> {
   typedef double cmp_t;
   static __device__ __forceinline__ double load(const double* p) { return __ldg(p); }
+  static __device__ __forceinline__ float round16(float x) { return x; }
 };
 template <>
 struct Elem<__half> {
@@ -33,6 +35,7 @@ struct Elem<__half> {
   static __device__ __forceinline__ float load(const __half* p) {
     return __half2float(__ushort_as_half(__ldg(reinterpret_cast<const unsigned short*>(p))));
   }
+  static __device__ __forceinline__ float round16(float x) { return __half2float(__float2half_rn(x)); }
 };
 template <>
 struct Elem<__nv_bfloat16> {
@@ -40,21 +43,25 @@ struct Elem<__nv_bfloat16> {
   static __device__ __forceinline__ float load(const __nv_bfloat16* p) {
     return __uint_as_float(static_cast<uint32_t>(__ldg(reinterpret_cast<const unsigned short*>(p))) << 16);
   }
+  static __device__ __forceinline__ float round16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 };
 template <>
 struct Elem<int64_t> {
   typedef double cmp_t;
   static __device__ __forceinline__ double load(const int64_t* p) { return static_cast<double>(__ldg(p)); }
+  static __device__ __forceinline__ float round16(float x) { return x; }
 };
 template <>
 struct Elem<int32_t> {
   typedef double cmp_t;
   static __device__ __forceinline__ double load(const int32_t* p) { return static_cast<double>(__ldg(p)); }
+  static __device__ __forceinline__ float round16(float x) { return x; }
 };
 template <>
 struct Elem<int16_t> {
   typedef float cmp_t;
   static __device__ __forceinline__ float load(const int16_t* p) { return static_cast<float>(__ldg(p)); }
+  static __device__ __forceinline__ float round16(float x) { return x; }
 };
 template <>
 struct Elem<int8_t> {
@@ -62,11 +69,13 @@ struct Elem<int8_t> {
   static __device__ __forceinline__ float load(const int8_t* p) {
     return static_cast<float>(static_cast<int8_t>(__ldg(reinterpret_cast<const signed char*>(p))));
   }
+  static __device__ __forceinline__ float round16(float x) { return x; }
 };
 template <>
 struct Elem<uint8_t> {
   typedef float cmp_t;
   static __device__ __forceinline__ float load(const uint8_t* p) { return static_cast<float>(__ldg(p)); }
+  static __device__ __forceinline__ float round16(float x) { return x; }
 };
 
 // rows [row0, row_end) of the output are produced; rows >= n are zero pad rows.
@@ -74,7 +83,8 @@ struct Elem<uint8_t> {
 template <typename T>
 __global__ void __launch_bounds__(256) pack_bits_kernel(const T* __restrict__ src, int64_t row0, int64_t row_end,
                                                         int64_t n, int ncols, int64_t rs, int64_t cs,
-                                                        double thr, int words, uint32_t* __restrict__ out_pos,
+                                                        double thr, const double* __restrict__ sub, int words,
+                                                        uint32_t* __restrict__ out_pos,
                                                         uint32_t* __restrict__ out_nz, uint32_t* __restrict__ flags) {
   typedef typename Elem<T>::cmp_t C;
   const int lane = threadIdx.x & 31;
@@ -97,6 +107,10 @@ __global__ void __launch_bounds__(256) pack_bits_kernel(const T* __restrict__ sr
       bool pos = false, nzb = false;
       if (r < n && col < ncols) {   // units past unit_end have r >= rows_pad > n
         C x = Elem<T>::load(rowp + static_cast<int64_t>(col) * cs);
+        if (sub != nullptr) {   // zero_mean_eval: `codes - mean` as torch computes it, i.e. rounded to the codes' dtype
+          x -= static_cast<C>(__ldg(sub + col));
+          if (sizeof(T) == 2) x = static_cast<C>(Elem<T>::round16(static_cast<float>(x)));
+        }
         if (x != x) fl |= 2u;
         if (has_thr && (x < C(0) ? -x : x) < cthr) x = C(0);
         pos = x > C(0);
@@ -224,6 +238,33 @@ __global__ void label_ids_kernel(const T* __restrict__ src, int64_t row0, int64_
   }
 }
 
+// zero_mean_eval (experiments/train_helper.py:223-226): column sums of the gallery codes, deterministic --
+// every warp sums the rows r = warp, warp + nwarps, ... of 32 columns at a time into its own partial row,
+// a second kernel adds the partials in warp order.
+template <typename T>
+__global__ void __launch_bounds__(256) column_partials_kernel(const T* __restrict__ src, int64_t n, int ncols,
+                                                              int64_t rs, int64_t cs, double* __restrict__ part) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int c0 = 0; c0 < ncols; c0 += 32) {
+    const int col = c0 + lane;
+    double acc = 0.0;
+    if (col < ncols)
+      for (int64_t r = warp; r < n; r += nwarps)
+        acc += static_cast<double>(Elem<T>::load(src + r * rs + static_cast<int64_t>(col) * cs));
+    if (col < ncols) part[warp * ncols + col] = acc;
+  }
+}
+__global__ void column_reduce_kernel(const double* __restrict__ part, int64_t nwarps, int ncols,
+                                     double* __restrict__ sums) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncols) return;
+  double acc = 0.0;
+  for (int64_t w = 0; w < nwarps; ++w) acc += part[w * ncols + col];
+  sums[col] = acc;
+}
+
 size_t elem_size(int dtype) {
   switch (dtype) {
     case CH_F32: return 4;
@@ -241,7 +282,7 @@ size_t elem_size(int dtype) {
 
 int launch_pack(ch_ws* ws, const void* src, int dtype, int64_t row0, int64_t row_end, int64_t n, int ncols,
                 int64_t rs, int64_t cs, double thr, int words, uint32_t* out_pos, uint32_t* out_nz,
-                uint32_t* flags, cudaStream_t st) {
+                uint32_t* flags, cudaStream_t st, const double* sub = nullptr) {
   const int64_t units = (row_end - row0) * words;
   if (units <= 0) return 0;
   const int64_t warps = (units + 31) / 32;
@@ -252,7 +293,7 @@ int launch_pack(ch_ws* ws, const void* src, int dtype, int64_t row0, int64_t row
 #define CH_PACK_CASE(ENUM, TYPE)                                                                            \
   case ENUM:                                                                                                \
     pack_bits_kernel<TYPE><<<grid, block, 0, st>>>(static_cast<const TYPE*>(src), row0, row_end, n, ncols,  \
-                                                   rs, cs, thr, words, out_pos, out_nz, flags);             \
+                                                   rs, cs, thr, sub, words, out_pos, out_nz, flags);        \
     break;
   switch (dtype) {
     CH_PACK_CASE(CH_F32, float)
@@ -276,7 +317,7 @@ int launch_pack(ch_ws* ws, const void* src, int dtype, int64_t row0, int64_t row
 // the pack kernel of chunk c (compute stream).  The host buffer must be row-contiguous (cs == 1).
 int pack_from_host(ch_ws* ws, const void* src, int dtype, int64_t n, int ncols, int64_t rs, int64_t cs,
                    double thr, int words, int64_t rows_pad, uint32_t* out_pos, uint32_t* out_nz,
-                   uint32_t* flags, cudaStream_t st) {
+                   uint32_t* flags, cudaStream_t st, const double* sub = nullptr) {
   const size_t es = elem_size(dtype);
   if (cs != 1 && ncols > 1) CH_FAIL("host buffers must have unit column stride");
   if (ch_ws_ensure_stage(ws)) return 1;
@@ -286,7 +327,8 @@ int pack_from_host(ch_ws* ws, const void* src, int dtype, int64_t n, int ncols, 
   // rows are staged DENSELY (a strided 2-D DMA drops the gaps of column slices / row-sampled views)
   int64_t chunk_rows = static_cast<int64_t>(ws->stage_bytes / dense_bytes) / 64 * 64;
   if (chunk_rows < 64) CH_FAIL("row of %zu bytes does not fit the staging buffer", dense_bytes);
-  if (n == 0) return launch_pack(ws, nullptr, dtype, 0, rows_pad, 0, ncols, ncols, 1, thr, words, out_pos, out_nz, flags, st);
+  if (n == 0)
+    return launch_pack(ws, nullptr, dtype, 0, rows_pad, 0, ncols, ncols, 1, thr, words, out_pos, out_nz, flags, st, sub);
   int c = 0;
   for (int64_t r0 = 0; r0 < n; r0 += chunk_rows, ++c) {
     const int b = c & 1;
@@ -304,7 +346,7 @@ int pack_from_host(ch_ws* ws, const void* src, int dtype, int64_t n, int ncols, 
     CH_CUDA(cudaEventRecord(ws->ev_copied[b], ws->copy_stream));
     CH_CUDA(cudaStreamWaitEvent(st, ws->ev_copied[b], 0));
     if (launch_pack(ws, ws->stage[b], dtype, r0, last ? rows_pad : r1, n, ncols, ncols, 1, thr, words, out_pos, out_nz,
-                    flags, st))
+                    flags, st, sub))
       return 1;
     CH_CUDA(cudaEventRecord(ws->ev_consumed[b], st));
   }
@@ -325,9 +367,52 @@ extern "C" int ch_code_words(int nbit) {
   return 8;
 }
 
+int ch_ws_scratch(ch_ws* ws, size_t bytes, void** out);  // api.cu
+
+extern "C" int ch_column_sums(ch_ws* ws, const void* codes_dev, int dtype, int64_t n, int ncols, int64_t row_stride,
+                              int64_t col_stride, double* sums_dev, void* stream) {
+  if (ws == nullptr || sums_dev == nullptr || (codes_dev == nullptr && n > 0)) CH_FAIL("null argument to ch_column_sums");
+  if (ncols <= 0 || n < 0) CH_FAIL("bad shape (%lld, %d)", (long long)n, ncols);
+  if (!(dtype == CH_F32 || dtype == CH_F16 || dtype == CH_BF16 || dtype == CH_F64))
+    CH_FAIL("codes must be a floating dtype (got %d)", dtype);
+  ChDeviceGuard g(ws->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int64_t blocks = (n + 7) / 8;
+  const int64_t cap = static_cast<int64_t>(ws->sm_count) * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  const int64_t nwarps = blocks * 8;
+  void* scratch = nullptr;
+  if (ch_ws_scratch(ws, static_cast<size_t>(nwarps) * ncols * sizeof(double), &scratch)) return 1;
+  double* part = static_cast<double*>(scratch);
+  const dim3 grid(static_cast<unsigned>(blocks)), block(256);
+  switch (dtype) {
+    case CH_F32:
+      column_partials_kernel<float><<<grid, block, 0, st>>>(static_cast<const float*>(codes_dev), n, ncols,
+                                                            row_stride, col_stride, part);
+      break;
+    case CH_F16:
+      column_partials_kernel<__half><<<grid, block, 0, st>>>(static_cast<const __half*>(codes_dev), n, ncols,
+                                                             row_stride, col_stride, part);
+      break;
+    case CH_BF16:
+      column_partials_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(static_cast<const __nv_bfloat16*>(codes_dev), n,
+                                                                    ncols, row_stride, col_stride, part);
+      break;
+    default:
+      column_partials_kernel<double><<<grid, block, 0, st>>>(static_cast<const double*>(codes_dev), n, ncols,
+                                                             row_stride, col_stride, part);
+      break;
+  }
+  CH_LAUNCH_CHECK(ws);
+  column_reduce_kernel<<<(ncols + 127) / 128, 128, 0, st>>>(part, nwarps, ncols, sums_dev);
+  CH_LAUNCH_CHECK(ws);
+  return 0;
+}
+
 extern "C" int ch_pack_sign(ch_ws* ws, const void* codes, int mem, int dtype, int64_t n, int nbit,
-                            int64_t row_stride, int64_t col_stride, double threshold, uint32_t* out_bits_dev,
-                            uint32_t* out_nz_dev, uint32_t* flags_dev, void* stream) {
+                            int64_t row_stride, int64_t col_stride, double threshold, const double* col_sub_dev,
+                            uint32_t* out_bits_dev, uint32_t* out_nz_dev, uint32_t* flags_dev, void* stream) {
   if (ws == nullptr) CH_FAIL("null workspace");
   const int words = ch_code_words(nbit);
   if (words == 0) CH_FAIL("nbit=%d unsupported (1..%d)", nbit, CH_MAX_NBIT);
@@ -339,9 +424,10 @@ extern "C" int ch_pack_sign(ch_ws* ws, const void* codes, int mem, int dtype, in
   const int64_t rows_pad = ch_padded_rows(n);
   if (mem == CH_MEM_HOST)
     return pack_from_host(ws, codes, dtype, n, nbit, row_stride, col_stride, threshold, words, rows_pad,
-                          out_bits_dev, out_nz_dev, flags_dev, st);
+                          out_bits_dev, out_nz_dev, flags_dev, st, col_sub_dev);
   // flat fast path (see pack_sign_flat_kernel): one launch covers the tensor, its tail and the pad rows
-  const bool flat = out_nz_dev == nullptr && threshold == 0.0 && (col_stride == 1 || nbit == 1) &&
+  const bool flat = out_nz_dev == nullptr && threshold == 0.0 && col_sub_dev == nullptr &&
+                    (col_stride == 1 || nbit == 1) &&
                     (row_stride == nbit || n <= 1) && nbit == words * 32 && flags_dev != nullptr &&
                     (dtype == CH_F32 || dtype == CH_F16 || dtype == CH_BF16) &&
                     (reinterpret_cast<uintptr_t>(codes) & 3) == 0;
@@ -366,7 +452,7 @@ extern "C" int ch_pack_sign(ch_ws* ws, const void* codes, int mem, int dtype, in
     return 0;
   }
   return launch_pack(ws, codes, dtype, 0, rows_pad, n, nbit, row_stride, col_stride, threshold, words, out_bits_dev,
-                     out_nz_dev, flags_dev, st);
+                     out_nz_dev, flags_dev, st, col_sub_dev);
 }
 
 extern "C" int ch_pack_labels(ch_ws* ws, const void* labels, int mem, int dtype, int64_t n, int C,

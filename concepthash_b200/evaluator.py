@@ -81,6 +81,7 @@ class Evaluator:
         self.stream_chunks = 4
         self.use_tensor_cores = True       # select pass on tcgen05 (int8 +-1 codes) when the shape allows it
         self.select_dense_override = None  # tests: force the dense / sparse epilogue of the tensor-core kernel
+        self.col_sub = None                # zero_mean_eval: f64[nbit] column offset of the current evaluation
         self.profile = False               # bench: bracket the kernels with CUDA events on the launch stream
         self.events = []                   # (kind, work units, start event, end event)
 
@@ -98,7 +99,8 @@ class Evaluator:
     def _pack_codes(self, p, codes, threshold, flags, want_nz=False):
         pack_bytes = p.n * p.nbit * codes.element_size() + p.n * p.nbit // 8
         kind = "pack_dev" if codes.is_cuda else "pack_host"
-        p.bits, p.nz = self._timed(kind, pack_bytes, lambda: self.b.pack_sign(codes, threshold, flags, want_nz))
+        kw = {} if self.col_sub is None else dict(col_sub=self.col_sub)
+        p.bits, p.nz = self._timed(kind, pack_bytes, lambda: self.b.pack_sign(codes, threshold, flags, want_nz, **kw))
 
     def _pack_side(self, codes, labels, threshold, flags, nolabel, want_nz=False, info=None, defer_codes=False):
         p = Packed()
@@ -117,13 +119,37 @@ class Evaluator:
             p.ncls = int(labels.shape[1]) if labels.dim() == 2 else 0
         return p
 
-    def _prepare(self, db_codes, db_labels, q_codes, q_labels, threshold, allow_defer=False):
+    def _column_mean(self, db_codes):
+        """``db_codes.mean(dim=0)`` of the WHOLE gallery (all ranks), fp64 sums / row count, rounded to the dtype of
+        the codes (what ``codes - mean`` sees in torch); experiments/train_helper.py:223-226."""
+        b, comm = self.b, self.comm
+        nbit = int(db_codes.shape[1])
+        acc = b.zeros((nbit + 1,), torch.float64)
+        if db_codes.shape[0] > 0:
+            acc[:nbit] = b.column_sums(db_codes)
+        acc[nbit] = float(db_codes.shape[0])
+        if comm.world > 1:
+            acc = comm.all_reduce_sum(acc)
+        mean = acc[:nbit] / torch.clamp(acc[nbit], min=1.0)
+        dt = db_codes.dtype if db_codes.dtype.is_floating_point else torch.float32
+        return mean.to(dt).to(torch.float64).contiguous()
+
+    def _prepare(self, db_codes, db_labels, q_codes, q_labels, threshold, allow_defer=False, zero_mean=False):
         if q_codes.dim() != 2 or db_codes.dim() != 2:
             raise ValueError("codes must be 2-D (N, nbit)")
         if q_codes.shape[1] != db_codes.shape[1]:
             raise ValueError(f"nbit mismatch: query {q_codes.shape[1]} vs gallery {db_codes.shape[1]}")
         if q_codes.shape[0] == 0:
             raise ValueError("no queries")
+        self.col_sub = None
+        if zero_mean:
+            # zero_mean_eval fused into the pack kernel: the gallery's column mean is subtracted from both sets
+            # on the fly.  The mean needs the whole gallery first, so a host gallery is copied once, not streamed.
+            if hasattr(self.b, "device") and not db_codes.is_cuda:
+                db_codes = db_codes.to(self.b.device, non_blocking=True)
+            self.col_sub = self._column_mean(db_codes)
+            allow_defer = False
+        self._db_codes_eff = db_codes
         if (q_labels is None) != (db_labels is None):
             raise ValueError("labels must be given for both sides or neither")
         if q_labels is not None and q_labels.dim() == 2 and db_labels.dim() == 2 and \
@@ -163,8 +189,9 @@ class Evaluator:
         ternary = bool(m[0])
         if ternary:
             # rare: some sign is exactly 0 -> pack again, this time with the non-zero bit-plane
-            _, q.nz = self.b.pack_sign(q_codes, threshold, flags, True)
-            g.bits, g.nz = self.b.pack_sign(db_codes, threshold, flags, True)
+            kw = {} if self.col_sub is None else dict(col_sub=self.col_sub)
+            _, q.nz = self.b.pack_sign(q_codes, threshold, flags, True, **kw)
+            g.bits, g.nz = self.b.pack_sign(db_codes, threshold, flags, True, **kw)
         label_mode, lw, nclass = L.CH_LAB_NONE, 0, 0
         if q_labels is not None:
             if m[1] <= 1:
@@ -280,7 +307,7 @@ class Evaluator:
 
     # ------------------------------------------------------------------ the evaluation
     def evaluate(self, db_codes, db_labels, q_codes, q_labels, R, threshold=0.0, PRs=(),
-                 remove_first_retrieved=False, return_ap=False):
+                 remove_first_retrieved=False, return_ap=False, zero_mean=False):
         """Returns ``(mAPs list, recalls list, precisions list[, ap (nR, nq) tensor])``.
 
         ``db_codes`` / ``db_labels`` are THIS rank's contiguous gallery row block; queries are replicated."""
@@ -294,7 +321,8 @@ class Evaluator:
         if any(r == 0 or r < -1 for r in r_list) or any(k <= 0 for k in pr_k):
             raise ValueError("R must be -1 or positive; PRs must be positive")
         q, g, ternary, label_mode, lw, nclass, rows = self._prepare(db_codes, db_labels, q_codes, q_labels, threshold,
-                                                                    allow_defer=True)
+                                                                    allow_defer=True, zero_mean=zero_mean)
+        db_codes = self._db_codes_eff           # (the device copy when zero_mean moved a host gallery)
         if label_mode == L.CH_LAB_NONE:
             raise ValueError("labels are required")
         nq, nbit = q.n, q.nbit
@@ -351,7 +379,7 @@ class Evaluator:
                 saved, self.stream_host_gallery = self.stream_host_gallery, False
                 try:
                     return self.evaluate(db_codes, db_labels, q_codes, q_labels, R, threshold, PRs,
-                                         remove_first_retrieved, return_ap)
+                                         remove_first_retrieved, return_ap, zero_mean)
                 finally:
                     self.stream_host_gallery = saved
         if res is not None:
@@ -750,14 +778,14 @@ class Evaluator:
         return threads, nq_pad, nstripes, rps
 
     # ------------------------------------------------------------------ ranked retrieval
-    def retrieve(self, db_codes, q_codes, R, threshold=0.0, remove_first_retrieved=False):
+    def retrieve(self, db_codes, q_codes, R, threshold=0.0, remove_first_retrieved=False, zero_mean=False):
         """Exact ranked retrieval: ``(ids int64 (nq, L), keys int32 (nq, L), ternary)`` with
         ``L = min(R, gallery size)``, canonical order (distance, then global gallery row).
         keys = Hamming distance (binary codes) or 2 x distance (ternary)."""
         b, comm = self.b, self.comm
         if hasattr(b, "begin"):
             b.begin()
-        q, g, ternary, _, _, _, rows = self._prepare(db_codes, None, q_codes, None, threshold)
+        q, g, ternary, _, _, _, rows = self._prepare(db_codes, None, q_codes, None, threshold, zero_mean=zero_mean)
         nq, nbit = q.n, q.nbit
         nbins = (2 * nbit if ternary else nbit) + 1
         ndb_total = sum(rows)
@@ -810,6 +838,7 @@ class Evaluator:
         """Dense key matrix (na, nb) int16 and the ternary flag (local, no collectives)."""
         if hasattr(self.b, "begin"):
             self.b.begin()
+        self.col_sub = None
         flags = self.b.zeros((1,), torch.int32)
         pa = self._pack_side(a_codes, None, threshold, flags, 0, want_nz=True)
         pb = self._pack_side(b_codes, None, 0.0, flags, 0, want_nz=True)

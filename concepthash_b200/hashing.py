@@ -50,8 +50,13 @@ def _as_tensor(x):
 
 def calculate_mAP(db_codes, db_labels, test_codes, test_labels, R, threshold=0., dist_metric="hamming",
                   PRs=None, multiclass=False, landmark_gt=None, db_id=None, test_id=None,
-                  remove_first_retrieved=False, group=None, **_ignored):
+                  remove_first_retrieved=False, group=None, zero_mean_eval=False, **_ignored):
     """mAP@R (+ R@k, P@k for ``PRs``) of a Hamming ranking on sign-binarised codes.
+
+    ``zero_mean_eval=True`` (not in the reference signature) fuses the callers' preprocessing
+    ``db_mean = db.mean(0); db -= db_mean; test -= db_mean`` (experiments/train_helper.py:223-226,
+    test_hashing.py:100-103) into the sign/bit-pack kernel: no (N, nbit) temporaries, no extra passes.  Bit slices
+    (``sub_code_eval``, test_hashing.py:87-98) need nothing: strided column views are packed in place.
 
     ``R``: int, ``-1`` = whole gallery (configs/val.yaml:7), or a list (test_hashing.py:124-128).
     Returns ``(mAP | [mAP, ...], recalls, precisions)`` as Python floats / lists of floats.
@@ -65,7 +70,7 @@ def calculate_mAP(db_codes, db_labels, test_codes, test_labels, R, threshold=0.,
     pr_list = [] if PRs is None else [int(k) for k in PRs]
     ev = get_evaluator(_device_of(db_codes, test_codes, db_labels, test_labels), group)
     maps, recalls, precisions = ev.evaluate(db_codes, db_labels, test_codes, test_labels, r_list, threshold,
-                                            pr_list, bool(remove_first_retrieved))
+                                            pr_list, bool(remove_first_retrieved), zero_mean=bool(zero_mean_eval))
     return (maps if r_is_list else maps[0]), recalls, precisions
 
 
@@ -85,7 +90,7 @@ def default_pr_cutoffs(n):
 
 
 def calculate_pr_curve(db_codes, db_labels, test_codes, test_labels, threshold=0., dist_metric="hamming",
-                       remove_first_retrieved=False, Rs=None, group=None, **_ignored):
+                       remove_first_retrieved=False, Rs=None, group=None, zero_mean_eval=False, **_ignored):
     """Precision / recall at a set of cut-offs (second symbol imported at test_hashing.py:15; used at
     :152-168).  Returns ``(recalls, precisions, Rs)``; default ``Rs`` = powers of two up to the list
     length, plus the length itself.  Hit counting as in ``calculate_mAP``."""
@@ -102,18 +107,21 @@ def calculate_pr_curve(db_codes, db_labels, test_codes, test_labels, threshold=0
     recalls, precisions = [], []
     for i in range(0, len(rs), 32):      # CH_MAX_PR cut-offs per pass
         _, r, p = calculate_mAP(db_codes, db_labels, test_codes, test_labels, [], threshold=threshold,
-                                PRs=rs[i:i + 32], remove_first_retrieved=remove_first_retrieved, group=group)
+                                PRs=rs[i:i + 32], remove_first_retrieved=remove_first_retrieved, group=group,
+                                zero_mean_eval=zero_mean_eval)
         recalls += r
         precisions += p
     return recalls, precisions, rs
 
 
-def retrieve_topk(query_codes, db_codes, R, threshold=0., remove_first_retrieved=False, group=None):
+def retrieve_topk(query_codes, db_codes, R, threshold=0., remove_first_retrieved=False, group=None,
+                  zero_mean_eval=False):
     """Exact ranked retrieval: ``(ids int64 (nq, L), dist float32 (nq, L))``, ascending (distance, gallery
     row) -- bit-identical to a stable sort of the dense distance matrix."""
     query_codes, db_codes = _as_tensor(query_codes), _as_tensor(db_codes)
     ev = get_evaluator(_device_of(db_codes, query_codes), group)
-    ids, keys, ternary = ev.retrieve(db_codes, query_codes, int(R), threshold, bool(remove_first_retrieved))
+    ids, keys, ternary = ev.retrieve(db_codes, query_codes, int(R), threshold, bool(remove_first_retrieved),
+                                     zero_mean=bool(zero_mean_eval))
     dist = keys.to(torch.float32) * (0.5 if ternary else 1.0)
     return ids, dist
 

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CH_ABI_VERSION 1
+#define CH_ABI_VERSION 2
 #define CH_MAX_NBIT 256          /* words per code: 1, 2, 4 or 8 x u32 */
 #define CH_MAX_R 8               /* length of an `R` list (test_hashing.py:124-128) */
 #define CH_MAX_PR 32             /* length of `PRs` */
@@ -73,14 +73,22 @@ int     ch_code_words(int nbit);
  *             (strides in elements; non-contiguous slices of test_hashing.py:91-98 are fine);
  *             CH_MEM_HOST buffers are staged through the workspace in pipelined chunks.
  *   threshold: already rounded to the dtype of `codes` by the caller (torch compares in that dtype)
+ *   col_sub : NULL, or device f64[nbit] subtracted from every row before the sign (`zero_mean_eval`,
+ *             experiments/train_helper.py:223-226, test_hashing.py:100-103: both sets minus the gallery's column
+ *             mean); the difference is taken in fp32 (fp64 for fp64 codes), like `codes - mean` in torch, so the
+ *             sign is that of the exact difference.  Values already rounded to the dtype of `codes`.
  *   out_bits: (rows_pad, words) u32, bit (k % 32) of word k / 32 = codes[i, k] > 0
  *   out_nz  : same shape, bit = sign(codes[i, k]) != 0; may be NULL only if the caller knows there
  *             are no zeros (it is still checked: flags bit 0)
  *   flags   : device u32, OR-ed: bit 0 = some sign is 0 (ternary needed), bit 1 = NaN seen
  */
 int ch_pack_sign(ch_ws* ws, const void* codes, int mem, int dtype, int64_t n, int nbit,
-                 int64_t row_stride, int64_t col_stride, double threshold,
+                 int64_t row_stride, int64_t col_stride, double threshold, const double* col_sub_dev,
                  uint32_t* out_bits_dev, uint32_t* out_nz_dev, uint32_t* flags_dev, void* stream);
+/* column sums (fp64, deterministic) of DEVICE codes (n, ncols): the numerator of `db_codes.mean(dim=0)`
+ * (zero_mean_eval); with a row-sharded gallery the caller all-reduces the sums over ranks. */
+int ch_column_sums(ch_ws* ws, const void* codes_dev, int dtype, int64_t n, int ncols, int64_t row_stride,
+                   int64_t col_stride, double* sums_dev, void* stream);
 
 /* ---- labels ----------------------------------------------------------------------------------
  * Relevance in the reference = "share >= 1 positive class" on (N, C) one-/multi-hot labels

@@ -70,10 +70,12 @@ def sign_codes(codes, threshold=0.0):
     ``x[|x| < threshold] = 0`` iff ``threshold != 0`` (``test_hashing.py:109``,
     ``configs/val.yaml:12``); sign as in ``models/layers/signhash.py:11`` /
     ``trainers/orthohash.py:78``.  ``sign(0) == 0`` is kept (half-integer distances)."""
-    x = torch.as_tensor(codes).detach().to("cpu").to(torch.float32).clone()
+    x = torch.as_tensor(codes).detach().to("cpu").clone()
+    if not x.dtype.is_floating_point:
+        x = x.to(torch.float32)
     if threshold != 0:
-        x[x.abs() < threshold] = 0
-    return torch.sign(x)
+        x[x.abs() < threshold] = 0          # in the dtype of the codes, as the reference's in-place statement does
+    return torch.sign(x.to(torch.float32))
 
 
 def hamming_distance_matrix(q_sign, d_sign):
@@ -275,3 +277,14 @@ def get_hamm_dist(codes, centroids, margin=0.0, normalize=False):
     nbit = torch.as_tensor(centroids).shape[1]
     d = hamming_distance_matrix(sign_codes(codes, margin), sign_codes(centroids, 0.0))
     return d / nbit if normalize else d
+
+
+def zero_mean(db_codes, test_codes):
+    """The callers' ``zero_mean_eval`` preprocessing (experiments/train_helper.py:223-226,
+    experiments/test_hashing.py:100-103): both sets minus the gallery's column mean.  The mean is accumulated in
+    fp64 and rounded to the dtype of the codes (the reference lets torch accumulate in the dtype of the codes; the
+    two means agree to ~1e-7 relative, so only an element within that distance of the mean can binarise
+    differently)."""
+    db_codes, test_codes = torch.as_tensor(db_codes), torch.as_tensor(test_codes)
+    mean = db_codes.double().mean(dim=0, keepdim=True).to(db_codes.dtype)
+    return db_codes - mean, test_codes - mean.to(test_codes.dtype)

@@ -55,7 +55,11 @@ class EmuBackend:
         return self.launches
 
     # K1
-    def pack_sign(self, codes, threshold, flags, want_nz=True):
+    def column_sums(self, codes):
+        self.launches += 1
+        return codes.detach().cpu().double().sum(0)
+
+    def pack_sign(self, codes, threshold, flags, want_nz=True, col_sub=None):
         n, nbit = codes.shape
         words = self.code_words(nbit)
         if words == 0:
@@ -63,6 +67,8 @@ class EmuBackend:
         x = codes.detach().cpu().clone()
         if not x.dtype.is_floating_point:
             x = x.float()
+        if col_sub is not None:
+            x = x - col_sub.to(x.dtype)[None, :]
         if threshold != 0:
             x[x.abs() < torch.tensor(threshold, dtype=x.dtype)] = 0
         xn = x.double().numpy()

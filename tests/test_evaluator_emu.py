@@ -214,3 +214,25 @@ def test_candidate_path_retrieve():
         oids, odist = mo.topk_ids(q, d, R, remove_first_retrieved=rf)
         assert torch.equal(ids, oids)
         assert torch.equal(keys.float(), odist)
+
+
+# ---------------------------------------------------------------- zero_mean_eval fused into the pack step
+@pytest.mark.parametrize("tc", [False, True])
+def test_zero_mean_eval_matches_caller_side_subtraction(tc):
+    d, dl, q, ql, _ = synth.make_random_case(11, 400, 32, 4, p=0.3, seed=71)
+    d, q = d + 0.35, q + 0.35                                   # a real offset: the mean matters
+    be = EmuBackend(rows_per_stripe=64, threads=128, tensor_cores=True) if tc else EmuBackend(rows_per_stripe=64)
+    ev = Evaluator(be)
+    ev.sample_stride = 0
+    dz, qz = mo.zero_mean(d, q)
+    for R, thr in [(-1, 0.0), (25, 0.0), (25, 0.2)]:
+        maps, rec, prec = ev.evaluate(d, dl, q, ql, [R], thr, [1, 5], False, zero_mean=True)
+        om, orec, oprec = mo.calculate_mAP(dz, dl, qz, ql, R, threshold=thr, PRs=[1, 5])
+        assert np.allclose(maps, [om], atol=1e-12) and np.allclose(rec, orec, atol=1e-12)
+        assert np.allclose(prec, oprec, atol=1e-12)
+        # and it is not a no-op on this data
+        m0, _, _ = ev.evaluate(d, dl, q, ql, [R], thr, [], False)
+        assert abs(m0[0] - maps[0]) > 1e-6
+    ids, keys, _ = ev.retrieve(d, q, 30, 0.0, False, zero_mean=True)
+    oids, odist = mo.topk_ids(qz, dz, 30)
+    assert torch.equal(ids, oids) and torch.equal(keys.float(), odist)

@@ -420,3 +420,32 @@ def test_streamed_host_gallery_equals_resident(H):
     om, orec, oprec = mo.calculate_mAP(dz, dl.cpu(), q.cpu()[sub], ql.cpu()[sub], 200, PRs=[1, 10])
     m2, rec2, prec2 = H.calculate_mAP(dz, dl.cpu(), q.cpu()[sub], ql.cpu()[sub], 200, PRs=[1, 10])
     assert abs(m2 - om) < TOL and np.allclose(rec2, orec, atol=TOL) and np.allclose(prec2, oprec, atol=TOL)
+
+
+# ------------------------------------------------------------------ zero_mean_eval fused into K1
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64, torch.float16])
+def test_zero_mean_eval_fused(H, dtype):
+    """`calculate_mAP(..., zero_mean_eval=True)` == the callers' `db -= db.mean(0); test -= db_mean` followed by the
+    plain call (train_helper.py:223-226), for device and host inputs, mAP@all and top-R; the column sums are
+    deterministic."""
+    ev = H.get_evaluator()
+    d, dl, q, ql, ncls = synth.make_random_case(300, 6000, 64, 20, p=0.3, seed=3)
+    d, q = (d + 0.4).to(dtype), (q + 0.4).to(dtype)
+    dz, qz = mo.zero_mean(d, q)
+    s1, s2 = ev.b.column_sums(d.cuda()), ev.b.column_sums(d.cuda())
+    assert torch.equal(s1, s2)
+    assert torch.allclose(s1.cpu(), d.double().sum(0), rtol=1e-12, atol=1e-9)
+    for R in (-1, 100):
+        om, orec, oprec = mo.calculate_mAP(dz, dl, qz, ql, R, PRs=[1, 5, 10])
+        for dev in ("cuda", "cpu"):
+            m, rec, prec = H.calculate_mAP(d.to(dev), dl.to(dev), q.to(dev), ql.to(dev), R, PRs=[1, 5, 10],
+                                           zero_mean_eval=True)
+            assert abs(m - om) < TOL and np.allclose(rec, orec, atol=TOL) and np.allclose(prec, oprec, atol=TOL)
+        m0, _, _ = H.calculate_mAP(d.cuda(), dl.cuda(), q.cuda(), ql.cuda(), R)
+        assert abs(m0 - m) > 1e-6                     # the offset matters on this data
+    # strided bit slice (sub_code_eval, test_hashing.py:87-92) + zero mean + ternary threshold
+    ds, qs = d[:, 8:40], q[:, 8:40]
+    dzs, qzs = mo.zero_mean(ds, qs)
+    om, _, _ = mo.calculate_mAP(dzs, dl, qzs, ql, 50, threshold=0.1)
+    m, _, _ = H.calculate_mAP(ds.cuda(), dl.cuda(), qs.cuda(), ql.cuda(), 50, threshold=0.1, zero_mean_eval=True)
+    assert abs(m - om) < TOL

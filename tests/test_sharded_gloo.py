@@ -48,6 +48,9 @@ def _worker(rank, world, port, out):
             maps, rec, prec = ev.evaluate(ds, dls, q, ql, r_list, thr, PRs, rf)
             ids, keys, tern = ev.retrieve(ds, q, 20, thr, rf)
             results[case] = (maps, rec, prec, ids.clone(), keys.clone(), tern)
+            if case == 1:
+                # zero_mean_eval: the column mean is that of the WHOLE gallery (sums all-reduced over the ranks)
+                results["zm"] = ev.evaluate(ds + 0.3, dls, q + 0.3, ql, [15], 0.0, [1, 5], False, zero_mean=True)
         if rank == 0:
             torch.save(results, out)
     finally:
@@ -78,3 +81,9 @@ def test_two_ranks_match_oracle(tmp_path):
         oids, odist = mo.topk_ids(q, d, 20, threshold=thr, remove_first_retrieved=rf)
         assert torch.equal(ids, oids), case
         assert torch.equal(keys.float() * (0.5 if tern else 1.0), odist), case
+        if case == 1:
+            dz, qz = mo.zero_mean(d + 0.3, q + 0.3)
+            om, orec, oprec = mo.calculate_mAP(dz, dl, qz, ql, 15, PRs=[1, 5])
+            zm = results["zm"]
+            assert np.allclose(zm[0], [om], atol=1e-12) and np.allclose(zm[1], orec, atol=1e-12)
+            assert np.allclose(zm[2], oprec, atol=1e-12)
