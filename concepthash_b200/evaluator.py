@@ -19,6 +19,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib as L
+from .codes_io import PackedCodes
 
 
 class LocalComm:
@@ -97,6 +98,14 @@ class Evaluator:
 
     # ------------------------------------------------------------------ packing
     def _pack_codes(self, p, codes, threshold, flags, want_nz=False):
+        if isinstance(codes, PackedCodes):
+            # already sign bits (codes_io): K1 is skipped; only the zero pad rows are added
+            if threshold != 0 or self.col_sub is not None:
+                raise ValueError("packed codes carry no magnitudes: threshold / zero_mean_eval need real-valued codes")
+            bits = self.b.zeros((self.b.padded_rows(p.n), codes.bits.shape[1]), torch.int32)
+            bits[:p.n] = codes.bits.to(bits.device)
+            p.bits, p.nz = bits, None
+            return
         pack_bytes = p.n * p.nbit * codes.element_size() + p.n * p.nbit // 8
         kind = "pack_dev" if codes.is_cuda else "pack_host"
         kw = {} if self.col_sub is None else dict(col_sub=self.col_sub)
@@ -161,7 +170,8 @@ class Evaluator:
         flags = meta[0:1]
         q = self._pack_side(q_codes, q_labels, threshold, flags, L.CH_QUERY_NOLABEL, info=meta[4:8])
         # a large HOST gallery is not copied yet: the top-R path streams it in row blocks behind the select pass
-        defer = (allow_defer and self.stream_host_gallery and not db_codes.is_cuda and threshold == 0 and
+        defer = (allow_defer and self.stream_host_gallery and not isinstance(db_codes, PackedCodes) and
+                 not db_codes.is_cuda and threshold == 0 and
                  db_labels is not None and db_codes.shape[0] >= self.stream_min_rows and
                  hasattr(self.b, "hamming_select_tc") and self.b.tc_code_bytes(int(db_codes.shape[1])) > 0)
         g = self._pack_side(db_codes, db_labels, threshold, flags, L.CH_GALLERY_NOLABEL, info=meta[8:12],

@@ -31,7 +31,7 @@ def get_evaluator(device=None, group=None):
 
 def _device_of(*tensors):
     for t in tensors:
-        if isinstance(t, torch.Tensor) and t.is_cuda:
+        if getattr(t, "is_cuda", False):
             return t.device
     return None
 
@@ -45,6 +45,9 @@ def _check_common(dist_metric, landmark_gt, db_id, test_id):
 
 
 def _as_tensor(x):
+    from .codes_io import PackedCodes
+    if isinstance(x, PackedCodes):
+        return x
     return x.detach() if isinstance(x, torch.Tensor) else torch.as_tensor(x)
 
 

@@ -7,6 +7,7 @@ reference's ``utils/`` directory: it forwards to the B200-native implementation.
 ``utils/`` directory, so ``utils.metrics`` of the reference keeps resolving when both trees are on
 ``sys.path``.
 """
+from concepthash_b200.codes_io import PackedCodes, evaluate_dumps, load_packed, save_packed  # noqa: F401
 from concepthash_b200.hashing import (  # noqa: F401
     calculate_mAP,
     calculate_pr_curve,
@@ -15,4 +16,5 @@ from concepthash_b200.hashing import (  # noqa: F401
     retrieve_topk,
 )
 
-__all__ = ["calculate_mAP", "calculate_pr_curve", "get_hamm_dist", "map_at_r", "retrieve_topk"]
+__all__ = ["calculate_mAP", "calculate_pr_curve", "get_hamm_dist", "map_at_r", "retrieve_topk",
+           "PackedCodes", "evaluate_dumps", "load_packed", "save_packed"]
