@@ -27,6 +27,7 @@ class CudaBackend:
 
     name = "cuda"
     stripe_align = 256     # stripe boundaries must be multiples of 256 gallery rows
+    tc_tile_rows = 128     # rows per tile of the tensor-core select kernel (its stripes are whole tiles)
 
     def __init__(self, device=None):
         if not torch.cuda.is_available():
@@ -254,6 +255,11 @@ class CudaBackend:
         for i, v in enumerate(pr_k):
             a.pr_k[i] = int(v)
         L.check(self.lib.ch_cand_finalize(self.ws, C.byref(a), self._stream()), "ch_cand_finalize")
+
+    def cand_caps(self, cand, thresh, nstripes, nq, nq_pad, sample_stride, cap):
+        L.check(self.lib.ch_cand_caps(self.ws, _ptr(cand["off"]), _ptr(cand["cnt"]), _ptr(cand["key"]), _ptr(thresh),
+                                      nstripes, nq, nq_pad, int(sample_stride), _ptr(cap), self._stream()),
+                "ch_cand_caps")
 
     def hamming_hist(self, **kw):
         a = self._hist_args(**kw)

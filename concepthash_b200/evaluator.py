@@ -75,6 +75,9 @@ class Evaluator:
         self.stats = {}
         self.stripe_rows_override = None   # tests: force the stripe length (multiple of 256 on CUDA)
         self.sample_stride = 32            # top-R: 1-in-32 row sample picks the threshold (0/1 = exact two-pass)
+        self.sample_two_level = True       # thresholds from the sample by a tensor-core select pass (see below)
+        self.sample2_sub = 16              # ... whose own thresholds come from every 16th sample row
+        self.sample2_min_rows = 16_384     # ... when the sample has at least this many rows
         self.sample_min_rows = 200_000     # below this the two-pass path is cheap anyway
         self.sample_min_ratio = 64         # ... and the sample must still hold ~R/stride*... rows: need ndb >= ratio * R
         self.stream_host_gallery = True    # host-resident gallery: overlap its H2D copy with the select pass
@@ -364,6 +367,7 @@ class Evaluator:
             # the select pass will run on the tensor cores: stripes that fill its waves (one CTA per SM)
             geo = self._tc_geometry(geo, g.n, stride if sampled else 1, 0.75 if sampled else 0.1)
         threads, nq_pad, nstripes, rps = geo
+        self.stats.pop("sample2", None)
         self.stats.update(dict(ternary=ternary, label_mode=label_mode, geometry=geo, nbins=nbins,
                                ndb_total=ndb_total, world=comm.world))
         ctx = dict(q=q, g=g, geo=geo, ternary=ternary, label_mode=label_mode, lw=lw, nclass=nclass, nq=nq,
@@ -660,26 +664,33 @@ class Evaluator:
             sp.nz[:ns] = g.nz[:g.n][::stride]
         sp.ids = sp.masks = sp.info = None
         geo_s = (threads, nq_pad, nstripes, rps // stride)
-        slab_s = b.zeros((nstripes, nbins, nq_pad), torch.int32)
-        self._hist(q, sp, geo_s, ternary, L.CH_LAB_NONE, 0, slab_s, None)
         if streamed:        # every rank samples the same way (streaming is agreed on by all ranks)
-            ns_total = sum(self._host_sample_rows(r, stride, run) for r in c["rows"])
+            ns_ranks = [self._host_sample_rows(r, stride, run) for r in c["rows"]]
         else:
-            ns_total = sum((r + stride - 1) // stride for r in c["rows"])
+            ns_ranks = [(r + stride - 1) // stride for r in c["rows"]]
+        ns_total = sum(ns_ranks)
         mu = need * ns_total / max(c["ndb_total"], 1)
         m = int(mu + 5.0 * mu ** 0.5 + 4.0) + 1
-        thresh = b.empty((nq_pad,), torch.int32)
-        base_tmp = b.empty((nbins, nq_pad), torch.int32)
-        tot_s = comm.all_gather(self._local_totals(slab_s, geo_s, nbins))
-        b.scan_bases(tot_s, comm.world, comm.rank, nbins, nq, nq_pad, m, base_tmp, thresh, None)
-        # ---- capacities: scaled sample candidate counts (record path: never more than the class counts) ----
-        cap = b.empty((nstripes, nq_pad), torch.int32)
-        b.record_caps(0, slab_s, thresh, nstripes, nbins, nq, nq_pad, False, cap, sample_stride=stride)
-        cls = self._class_counts(c)
+        tc_pass = streamed or self._tc_ok(q, ternary, nq_pad)
+        slab_s = base_tmp = None
         if streamer is not None:
-            streamer.load(0)        # block 0 travels while the GPU is still busy with the sample
+            streamer.load(0)        # block 0 travels (copy engine, side stream) while the sample is worked on
+        if (tc_pass and self.sample_two_level and not ternary and min(ns_ranks) >= self.sample2_min_rows
+                and (rps // stride) % getattr(b, "tc_tile_rows", 1) == 0):
+            thresh, cap = self._sample_thresholds_tc(c, sp, ns_ranks, m, status)
+        else:
+            slab_s = b.zeros((nstripes, nbins, nq_pad), torch.int32)
+            self._hist(q, sp, geo_s, ternary, L.CH_LAB_NONE, 0, slab_s, None)
+            thresh = b.empty((nq_pad,), torch.int32)
+            base_tmp = b.empty((nbins, nq_pad), torch.int32)
+            tot_s = comm.all_gather(self._local_totals(slab_s, geo_s, nbins))
+            b.scan_bases(tot_s, comm.world, comm.rank, nbins, nq, nq_pad, m, base_tmp, thresh, None)
+            # ---- capacities: scaled sample candidate counts (record path: never more than the class counts) ----
+            cap = b.empty((nstripes, nq_pad), torch.int32)
+            b.record_caps(0, slab_s, thresh, nstripes, nbins, nq, nq_pad, False, cap, sample_stride=stride)
+        cls = self._class_counts(c)
         self.stats["sample"] = dict(stride=stride, rows=ns_total, m=m)
-        if streamed or self._tc_ok(q, ternary, nq_pad):
+        if tc_pass:
             # ---- the one full pass on the tensor cores: candidate lists, then ranks from the lists ----
             cand, tmax = self._alloc_cands(cap, geo, nq, thresh, status)    # one host sync: slots + max threshold
             del slab_s, base_tmp
@@ -723,6 +734,68 @@ class Evaluator:
         b.slab_exscan(slab_rel, nstripes, nbins, nq_pad)
         return dict(rec=rec, base0_all=base0_all, base0_rel=base0_rel, sbase_all=slab_all, sbase_rel=slab_rel,
                     total_rel=self._total_rel_from_classes(c, cls), nbins=nbins)
+
+    def _sample_thresholds_tc(self, c, sp, ns_ranks, m, status):
+        """Per-query thresholds t^ (and the capacities of the full pass) from the row sample WITHOUT histogramming
+        every (query, sample row) pair on the integer pipe:
+
+          level 0  every ``sample2_sub``-th sample row is histogrammed (POPC kernel) -> a loose threshold t0 per
+                   query, where that mini-sample holds >= mu0 + 5 sqrt(mu0) + 5 items;
+          level 1  the tensor-core select kernel runs over the SAMPLE with t0; its candidate list (a few hundred
+                   rows per query) is histogrammed by ``ch_cand_hist`` -> t^ = the smallest key at which the sample
+                   holds >= m items -- exactly the threshold the full sample histogram would give -- or t0 if the
+                   list holds fewer (then #(key <= t0) in the whole gallery is >= R with overwhelming probability:
+                   the mini-sample saw >= m0 of them).
+        Capacities come from the per-stripe sample candidates with key <= t^ (``ch_cand_caps``).  Nothing here
+        affects exactness: the full pass verifies its counts, an overflow anywhere raises ``status``."""
+        b, comm, q = self.b, self.comm, c["q"]
+        threads, nq_pad, nstripes, rps = c["geo"]
+        nbins, nq, stride = c["nbins"], c["nq"], c["stride"]
+        need = min(c["rmax"] + c["rf"], c["ndb_total"])
+        ns, sub = sp.n, self.sample2_sub
+        # ---- level 0 ----
+        ns0 = (ns + sub - 1) // sub
+        sp0 = Packed()
+        sp0.i8 = sp0.nz = sp0.ids = sp0.masks = sp0.info = None
+        sp0.n, sp0.nbit = ns0, sp.nbit
+        sp0.bits = b.zeros((b.padded_rows(ns0), sp.bits.shape[1]), torch.int32)
+        sp0.bits[:ns0] = sp.bits[:ns][::sub]
+        align = getattr(b, "stripe_align", 256)
+        geo0 = (threads, nq_pad, 1, max(align, (ns0 + align - 1) // align * align))
+        slab0 = b.zeros((1, nbins, nq_pad), torch.int32)
+        self._hist(q, sp0, geo0, False, L.CH_LAB_NONE, 0, slab0, None)
+        ns0_total = sum((r + sub - 1) // sub for r in ns_ranks)
+        mu0 = need * ns0_total / max(c["ndb_total"], 1)
+        m0 = int(mu0 + 5.0 * mu0 ** 0.5 + 4.0) + 1
+        thresh0 = b.empty((nq_pad,), torch.int32)
+        base_tmp = b.empty((nbins, nq_pad), torch.int32)
+        b.scan_bases(comm.all_gather(slab0[0]), comm.world, comm.rank, nbins, nq, nq_pad, m0, base_tmp, thresh0, None)
+        # list capacities of the sample select: the local mini-sample count <= t0, scaled -- for EVERY stripe (the
+        # row order may put all neighbours of a query into one stripe)
+        cap0 = b.empty((1, nq_pad), torch.int32)
+        b.record_caps(0, slab0, thresh0, 1, nbins, nq, nq_pad, False, cap0, sample_stride=sub)
+        geo_s = (threads, nq_pad, nstripes, rps // stride)
+        cand1, tmax0 = self._alloc_cands(cap0.expand(nstripes, nq_pad).contiguous(), geo_s, nq, thresh0, status)
+        nb0 = min(nbins, tmax0 + 1)
+        # ---- level 1 ----
+        q_i8 = self._query_plane(q, nq_pad, thresh0)
+        s_i8 = self._timed("expand_i8", 0, lambda: b.expand_i8(sp.bits, q.nbit))
+        dense = self._dense(1.25 * sub * m0, sum(ns_ranks))
+        self._timed("sample_select_tc", q.n * ns, lambda: b.hamming_select_tc(
+            q_i8=q_i8, g_i8=s_i8, cand=cand1, nq=nq, nq_pad=nq_pad, ndb=ns, nbit=q.nbit, nstripes=nstripes,
+            rows_per_stripe=rps // stride, dense=dense))
+        tot1 = b.zeros((nb0, nq_pad), torch.int32)
+        self._timed("cand_hist", 0, lambda: b.cand_hist(
+            cand1, q_bits=q.bits, g_bits=sp.bits, q_lab=None, g_lab=None, label_mode=L.CH_LAB_NONE, mask_words=0,
+            tot_all=tot1, tot_rel=None, nq=nq, nq_pad=nq_pad, nstripes=nstripes, nbins=nb0, nbit=q.nbit))
+        thresh1 = b.empty((nq_pad,), torch.int32)
+        base1 = b.empty((nb0, nq_pad), torch.int32)
+        b.scan_bases(comm.all_gather(tot1), comm.world, comm.rank, nb0, nq, nq_pad, m, base1, thresh1, None)
+        thresh = torch.minimum(thresh1, thresh0)
+        cap = b.empty((nstripes, nq_pad), torch.int32)
+        b.cand_caps(cand1, thresh, nstripes, nq, nq_pad, stride, cap)
+        self.stats["sample2"] = dict(sub=sub, m0=m0, key_limit0=nb0, slots=self.stats.get("record_slots"))
+        return thresh, cap
 
     def _total_rel_from_classes(self, c, cls):
         """relevant items in the whole gallery per query = class frequency of the query's class (single-label)"""

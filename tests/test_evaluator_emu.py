@@ -13,10 +13,13 @@ from oracle import map_oracle as mo
 from tests._emu_backend import EmuBackend
 
 
-def run_case(d, dl, q, ql, R, PRs=(), rf=False, thr=0.0, rps=64, sampled=False, tc=False):
+def run_case(d, dl, q, ql, R, PRs=(), rf=False, thr=0.0, rps=64, sampled=False, tc=False, two_level=False):
     # tc: the candidate-list path of the tensor-core select pass (whole 128-query tiles)
     ev = Evaluator(EmuBackend(rows_per_stripe=rps, threads=128, tensor_cores=True) if tc
                    else EmuBackend(rows_per_stripe=rps))
+    ev.sample_two_level = two_level
+    if two_level:
+        ev.sample2_min_rows, ev.sample2_sub = 0, 4
     if sampled:
         ev.sample_stride, ev.sample_min_rows, ev.sample_min_ratio = 4, 0, 4
     else:
@@ -236,3 +239,22 @@ def test_zero_mean_eval_matches_caller_side_subtraction(tc):
     ids, keys, _ = ev.retrieve(d, q, 30, 0.0, False, zero_mean=True)
     oids, odist = mo.topk_ids(qz, dz, 30)
     assert torch.equal(ids, oids) and torch.equal(keys.float(), odist)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_candidate_path_two_level_sample(seed):
+    """thresholds from the sample by a select pass over the sample itself (level 0: every 4th sample row)"""
+    nbit = [16, 64, 128][seed]
+    d, dl, q, ql, _ = synth.make_random_case(9, 1800 + 50 * seed, nbit, 5, p=0.3, seed=80 + seed)
+    ev = run_case(d, dl, q, ql, 20, PRs=[1, 5, 10], rps=64, sampled=True, tc=True, two_level=True)
+    assert ev.stats["mode"] == "topR-sampled" and "sample2" in ev.stats, ev.stats
+    ev = run_case(d, dl, q, ql, [5, 40], PRs=[], rf=(seed == 1), rps=128, sampled=True, tc=True, two_level=True)
+    assert ev.stats["mode"] in ("topR-sampled", "topR")
+    # adversarial order: falls back to the exact path, still the oracle's answer
+    qq = torch.ones(3, 16)
+    dd = -torch.ones(1600, 16)
+    dd[0:280:4] = 1.0
+    dd[0:280:4, 0] = -1.0
+    ev = run_case(dd, torch.arange(1600) % 2, qq, torch.tensor([0, 1, 0]), 80, PRs=[1, 5], rps=64, sampled=True,
+                  tc=True, two_level=True)
+    assert ev.stats["mode"] == "topR" and ev.stats["sample"]["fallback"]

@@ -49,6 +49,12 @@ def _worker(rank, world, port, out):
             ids, keys, tern = ev.retrieve(ds, q, 20, thr, rf)
             results[case] = (maps, rec, prec, ids.clone(), keys.clone(), tern)
             if case == 1:
+                # sampled top-R with two-level thresholds across ranks
+                ev2 = Evaluator(EmuBackend(rows_per_stripe=32, threads=128, tensor_cores=True), DistComm())
+                ev2.sample_stride, ev2.sample_min_rows, ev2.sample_min_ratio = 2, 0, 4
+                ev2.sample2_min_rows, ev2.sample2_sub = 0, 2
+                results["s2"] = ev2.evaluate(ds, dls, q, ql, [15], thr, PRs, rf) + (ev2.stats["mode"],
+                                                                                     "sample2" in ev2.stats)
                 # zero_mean_eval: the column mean is that of the WHOLE gallery (sums all-reduced over the ranks)
                 results["zm"] = ev.evaluate(ds + 0.3, dls, q + 0.3, ql, [15], 0.0, [1, 5], False, zero_mean=True)
         if rank == 0:
@@ -82,6 +88,9 @@ def test_two_ranks_match_oracle(tmp_path):
         assert torch.equal(ids, oids), case
         assert torch.equal(keys.float() * (0.5 if tern else 1.0), odist), case
         if case == 1:
+            s2 = results["s2"]
+            assert s2[4] and s2[3] in ("topR-sampled", "topR"), s2
+            assert np.allclose(s2[0], om, atol=1e-12) and np.allclose(s2[1], orec, atol=1e-12)
             dz, qz = mo.zero_mean(d + 0.3, q + 0.3)
             om, orec, oprec = mo.calculate_mAP(dz, dl, qz, ql, 15, PRs=[1, 5])
             zm = results["zm"]
