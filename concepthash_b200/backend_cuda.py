@@ -222,9 +222,9 @@ class CudaBackend:
         L.check(self.lib.ch_hamming_select_tc(self.ws, C.byref(a), self._stream()), "ch_hamming_select_tc")
 
     # ---- K3/K4 on candidate lists ----
-    def _cand_args(self, cand, nq, nq_pad, nstripes, nbins, **kw):
+    def _cand_args(self, cand, nq, nq_pad, nstripes, nbins, stripe0=0, **kw):
         a = L.CandArgs()
-        a.cand_off, a.cand_cnt = cand["off"].data_ptr(), cand["cnt"].data_ptr()
+        a.cand_off, a.cand_cnt = cand["off"][stripe0:].data_ptr(), cand["cnt"][stripe0:].data_ptr()
         a.cand_rows, a.cand_key, a.err_flag = cand["rows"].data_ptr(), cand["key"].data_ptr(), cand["err"].data_ptr()
         a.nq, a.nq_pad, a.nstripes, a.nbins = nq, nq_pad, nstripes, nbins
         for k, v in kw.items():
@@ -235,8 +235,9 @@ class CudaBackend:
         return a
 
     def cand_hist(self, cand, *, q_bits, g_bits, q_lab, g_lab, label_mode, mask_words, tot_all, tot_rel, nq, nq_pad,
-                  nstripes, nbins, nbit):
-        a = self._cand_args(cand, nq, nq_pad, nstripes, nbins, q_bits=q_bits, g_bits=g_bits, q_lab=q_lab, g_lab=g_lab,
+                  nstripes, nbins, nbit, stripe0=0):
+        """totals are accumulated; ``stripe0`` / ``nstripes`` select a block of stripes of the list"""
+        a = self._cand_args(cand, nq, nq_pad, nstripes, nbins, stripe0, q_bits=q_bits, g_bits=g_bits, q_lab=q_lab, g_lab=g_lab,
                             label_mode=label_mode, mask_words=mask_words, tot_all=tot_all, tot_rel=tot_rel, nbit=nbit)
         L.check(self.lib.ch_cand_hist(self.ws, C.byref(a), self._stream()), "ch_cand_hist")
 

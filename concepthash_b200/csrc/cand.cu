@@ -112,9 +112,11 @@ __global__ void __launch_bounds__(kCandWarps * 32) cand_hist_kernel(const CandDe
     }
   }
   __syncwarp();
+  // accumulated: the caller zero-initialises the totals and may histogram a list in several calls (row blocks of
+  // a streamed gallery); one warp owns a query, calls are stream-ordered -> no atomics
   for (int b = lane; b < a.nbins; b += 32) {
-    a.tot_all[static_cast<size_t>(b) * a.nq_pad + q] = h_all[b];
-    if (a.tot_rel != nullptr) a.tot_rel[static_cast<size_t>(b) * a.nq_pad + q] = h_rel[b];
+    if (h_all[b] != 0u) a.tot_all[static_cast<size_t>(b) * a.nq_pad + q] += h_all[b];
+    if (a.tot_rel != nullptr && h_rel[b] != 0u) a.tot_rel[static_cast<size_t>(b) * a.nq_pad + q] += h_rel[b];
   }
   if (bad) atomicOr(a.err_flag, 2u);
 }

@@ -296,18 +296,26 @@ class Evaluator:
         self.stats["select_kernel"] = "tcgen05"
         self.stats["select_dense"] = bool(dense)
 
-    def _cand_bases(self, c, cand, nbins, need=None):
-        """keys + label matches of the candidates -> per-rank key totals -> all-gather -> bases (+ verification
-        that every query has >= ``need`` candidates: status[1])"""
-        b, comm, q, g = self.b, self.comm, c["q"], c["g"]
-        threads, nq_pad, nstripes, rps = c["geo"]
-        nq, label_mode, lw = c["nq"], c["label_mode"], c["lw"]
+    def _cand_hist(self, c, cand, nbins, tot, stripe0=0, nstripes=None):
+        """keys + label matches of the candidates of a block of stripes, accumulated into ``tot`` (2, nbins, nq_pad)"""
+        b, q, g = self.b, c["q"], c["g"]
+        threads, nq_pad, nstripes_all, rps = c["geo"]
+        label_mode, lw = c["label_mode"], c["lw"]
         lab = lambda p: None if label_mode == L.CH_LAB_NONE else (p.ids if label_mode == L.CH_LAB_ID else p.masks)
-        tot = b.zeros((2, nbins, nq_pad), torch.int32)
         self._timed("cand_hist", 0, lambda: b.cand_hist(
             cand, q_bits=q.bits, g_bits=g.bits, q_lab=lab(q), g_lab=lab(g), label_mode=label_mode, mask_words=lw,
-            tot_all=tot[0], tot_rel=tot[1] if label_mode != L.CH_LAB_NONE else None, nq=nq, nq_pad=nq_pad,
-            nstripes=nstripes, nbins=nbins, nbit=q.nbit))
+            tot_all=tot[0], tot_rel=tot[1] if label_mode != L.CH_LAB_NONE else None, nq=c["nq"], nq_pad=nq_pad,
+            nstripes=nstripes_all if nstripes is None else nstripes, nbins=nbins, nbit=q.nbit, stripe0=stripe0))
+
+    def _cand_bases(self, c, cand, nbins, need=None, tot=None):
+        """keys + label matches of the candidates -> per-rank key totals -> all-gather -> bases (+ verification
+        that every query has >= ``need`` candidates: status[1]).  ``tot``: totals already accumulated per block."""
+        b, comm = self.b, self.comm
+        threads, nq_pad, nstripes, rps = c["geo"]
+        nq = c["nq"]
+        if tot is None:
+            tot = b.zeros((2, nbins, nq_pad), torch.int32)
+            self._cand_hist(c, cand, nbins, tot)
         tot = comm.all_gather(tot)                                   # (world, 2, nbins, nq_pad)
         base0_all = b.empty((nbins, nq_pad), torch.int32)
         base0_rel = b.empty((nbins, nq_pad), torch.int32)
@@ -594,6 +602,7 @@ class Evaluator:
             per = ev._stream_per(nq_pad)
             # loads run on a side stream so that they are not queued behind the (long) select kernels
             self.side = torch.cuda.Stream(device=g.bits.device)
+            self.pinned = bool(c["db_codes"].is_contiguous() and c["db_codes"].is_pinned())
             self.loaded = {}
             self.blocks = []
             for s0 in range(0, nstripes, per):
@@ -603,19 +612,33 @@ class Evaluator:
                     self.blocks.append((s0, s1, r0, r1))
 
         def load(self, i):
-            """H2D + pack + expand of block i (the host returns when the copy is done; kernels are queued)"""
+            """H2D + pack + expand of block i on the side stream.  Pageable host memory: staged copies, the host
+            returns when the copy is done (kernels are queued).  Pinned host memory: one asynchronous DMA into a
+            device block that the caching allocator recycles in stream order -- nothing blocks, so all blocks
+            can be queued up front and the copy engine never idles."""
             ev, b, q, g = self.ev, self.ev.b, self.c["q"], self.c["g"]
             s0, s1, r0, r1 = self.blocks[i]
             db_codes = self.c["db_codes"]
             nrow8 = (self.rows_pad - r0) if r1 == g.n else (r1 - r0)
             blk = db_codes[r0:r1]
             with b.on_stream(self.side):
-                ev._timed("pack_host", (r1 - r0) * q.nbit * db_codes.element_size(),
-                          lambda: b.pack_sign(blk, 0.0, self.flags, False, out=g.bits[r0:]))
+                if self.pinned:
+                    def copy_and_pack():
+                        dev = blk.to(g.bits.device, non_blocking=True)
+                        b.pack_sign(dev, 0.0, self.flags, False, out=g.bits[r0:])
+                    ev._timed("pack_host", (r1 - r0) * q.nbit * db_codes.element_size(), copy_and_pack)
+                else:
+                    ev._timed("pack_host", (r1 - r0) * q.nbit * db_codes.element_size(),
+                              lambda: b.pack_sign(blk, 0.0, self.flags, False, out=g.bits[r0:]))
                 ev._timed("expand_i8", 0, lambda: b.expand_i8_into(g.bits[r0:r0 + nrow8], q.nbit, g.i8[r0:]))
                 done = torch.cuda.Event()
                 done.record(self.side)
             self.loaded[i] = done
+
+        def load_first(self):
+            """block 0 -- or, from pinned memory, every block -- is queued while the GPU works on the sample"""
+            for i in range(len(self.blocks) if self.pinned else 1):
+                self.load(i)
 
         def select(self, i, cand, q_i8, dense):
             ev, b, q, g = self.ev, self.ev.b, self.c["q"], self.c["g"]
@@ -673,11 +696,12 @@ class Evaluator:
         m = int(mu + 5.0 * mu ** 0.5 + 4.0) + 1
         tc_pass = streamed or self._tc_ok(q, ternary, nq_pad)
         slab_s = base_tmp = None
-        if streamer is not None:
-            streamer.load(0)        # block 0 travels (copy engine, side stream) while the sample is worked on
+        # block 0 of a streamed gallery travels while the GPU works on the sample: its (host-blocking) copy is
+        # issued right after the first sample kernels have been queued
+        first_load = streamer.load_first if streamer is not None else (lambda: None)
         if (tc_pass and self.sample_two_level and not ternary and min(ns_ranks) >= self.sample2_min_rows
                 and (rps // stride) % getattr(b, "tc_tile_rows", 1) == 0):
-            thresh, cap = self._sample_thresholds_tc(c, sp, ns_ranks, m, status)
+            thresh, cap = self._sample_thresholds_tc(c, sp, ns_ranks, m, status, first_load)
         else:
             slab_s = b.zeros((nstripes, nbins, nq_pad), torch.int32)
             self._hist(q, sp, geo_s, ternary, L.CH_LAB_NONE, 0, slab_s, None)
@@ -688,6 +712,7 @@ class Evaluator:
             # ---- capacities: scaled sample candidate counts (record path: never more than the class counts) ----
             cap = b.empty((nstripes, nq_pad), torch.int32)
             b.record_caps(0, slab_s, thresh, nstripes, nbins, nq, nq_pad, False, cap, sample_stride=stride)
+            first_load()
         cls = self._class_counts(c)
         self.stats["sample"] = dict(stride=stride, rows=ns_total, m=m)
         if tc_pass:
@@ -697,17 +722,22 @@ class Evaluator:
             nbins = min(nbins, tmax + 1)
             self.stats["sample"]["key_limit"] = nbins
             dense = self._dense(1.25 * stride * m, c["ndb_total"])
+            tot = None
             if streamed:
                 q_i8 = self._query_plane(q, nq_pad, thresh)
+                tot = b.zeros((2, nbins, nq_pad), torch.int32)
                 for i in range(len(streamer.blocks)):
                     streamer.select(i, cand, q_i8, dense)
-                    if i + 1 < len(streamer.blocks):
+                    if i + 1 < len(streamer.blocks) and (i + 1) not in streamer.loaded:
                         streamer.load(i + 1)     # host waits for this copy while the GPU runs select(i)
+                    # keys / label matches of this block's candidates while the next block is still travelling
+                    s0, s1 = streamer.blocks[i][0], streamer.blocks[i][1]
+                    self._cand_hist(c, cand, nbins, tot, s0, s1 - s0)
                 self.stats["select_kernel"] = "tcgen05"
                 self.stats["select_dense"] = bool(dense)
             else:
                 self._select_tc(q, g, geo, thresh, cand, dense)
-            base0_all, base0_rel = self._cand_bases(c, cand, nbins, need)
+            base0_all, base0_rel = self._cand_bases(c, cand, nbins, need, tot)
             return dict(cand=cand, base0_all=base0_all, base0_rel=base0_rel, nbins=nbins,
                         total_rel=self._total_rel_from_classes(c, cls))
         b.record_caps(2, cls, q.ids, nstripes, c["nclass"], nq, nq_pad, True, cap)
@@ -735,7 +765,7 @@ class Evaluator:
         return dict(rec=rec, base0_all=base0_all, base0_rel=base0_rel, sbase_all=slab_all, sbase_rel=slab_rel,
                     total_rel=self._total_rel_from_classes(c, cls), nbins=nbins)
 
-    def _sample_thresholds_tc(self, c, sp, ns_ranks, m, status):
+    def _sample_thresholds_tc(self, c, sp, ns_ranks, m, status, after_level0=lambda: None):
         """Per-query thresholds t^ (and the capacities of the full pass) from the row sample WITHOUT histogramming
         every (query, sample row) pair on the integer pipe:
 
@@ -775,11 +805,12 @@ class Evaluator:
         cap0 = b.empty((1, nq_pad), torch.int32)
         b.record_caps(0, slab0, thresh0, 1, nbins, nq, nq_pad, False, cap0, sample_stride=sub)
         geo_s = (threads, nq_pad, nstripes, rps // stride)
+        s_i8 = self._timed("expand_i8", 0, lambda: b.expand_i8(sp.bits, q.nbit))
+        after_level0()              # (host-blocking work of the caller, while the GPU runs level 0)
         cand1, tmax0 = self._alloc_cands(cap0.expand(nstripes, nq_pad).contiguous(), geo_s, nq, thresh0, status)
         nb0 = min(nbins, tmax0 + 1)
         # ---- level 1 ----
         q_i8 = self._query_plane(q, nq_pad, thresh0)
-        s_i8 = self._timed("expand_i8", 0, lambda: b.expand_i8(sp.bits, q.nbit))
         dense = self._dense(1.25 * sub * m0, sum(ns_ranks))
         self._timed("sample_select_tc", q.n * ns, lambda: b.hamming_select_tc(
             q_i8=q_i8, g_i8=s_i8, cand=cand1, nq=nq, nq_pad=nq_pad, ndb=ns, nbit=q.nbit, nstripes=nstripes,

@@ -187,7 +187,8 @@ int ch_hamming_select_tc(ch_ws* ws, const ch_select_args* a, void* stream);
  * Every item with key <= thresh[q] is a candidate, so canonical ranks are counts over candidates:
  *   ch_cand_hist     per candidate: key = popcount(q ^ g) on the packed codes, relevance by the labels (ids or
  *                    masks); writes cand_key, ORs bit 31 of cand_rows for relevant candidates, and the per-query
- *                    key totals tot_all / tot_rel (nbins, nq_pad) of this rank (rows q >= nq untouched).
+ *                    key totals tot_all / tot_rel (nbins, nq_pad) of this rank are ACCUMULATED into the
+ *                    caller-zeroed arrays (a list may be histogrammed in several calls, one per row block).
  *                    err_flag |= 2 if a candidate has key >= nbins.
  *   (caller: all-gather the totals over ranks, ch_scan_bases -> base0_all / base0_rel)
  *   ch_cand_finalize walks each query's list in order (stripe-major = ascending row): rank = base0_all[key] +

@@ -218,17 +218,14 @@ class EmuBackend:
 
     # K3/K4 on candidate lists
     def cand_hist(self, cand, *, q_bits, g_bits, q_lab, g_lab, label_mode, mask_words, tot_all, tot_rel, nq, nq_pad,
-                  nstripes, nbins, nbit):
+                  nstripes, nbins, nbit, stripe0=0):
         self.launches += 1
         off, cnt, rows, key = _u32(cand["off"]), _u32(cand["cnt"]), _u32(cand["rows"]), cand["key"].numpy()
         qs, gs = _unpack(_u32(q_bits)[:nq], nbit), _unpack(_u32(g_bits), nbit)
         ta = _u32(tot_all)
         tr = _u32(tot_rel) if tot_rel is not None else None
         for q in range(nq):
-            ta[:, q] = 0
-            if tr is not None:
-                tr[:, q] = 0
-            for s in range(nstripes):
+            for s in range(stripe0, stripe0 + nstripes):       # totals are accumulated (caller zero-initialises)
                 o = int(off[s, q])
                 for i in range(int(cnt[s, q])):
                     row = int(rows[o + i] & 0x7FFFFFFF)
