@@ -331,7 +331,7 @@ def main():
     if not args.no_e2e:
         hd, hdl, hq, hql = (t.cpu().pin_memory() for t in (d, dl, q, ql))
         step_host = lambda: hashing.calculate_mAP(hd, hdl, hq, hql, w["R"], group=group)
-        ms_e, out_e, _, _, ev_e = run(step_host, max(2, args.steps // 2), 1)
+        ms_e, out_e, _, _, ev_e = run(step_host, max(2, args.steps // 2), 2)
         kinds_e = {}
         for kind, units, a, b in ev_e:
             kinds_e[kind] = kinds_e.get(kind, 0.0) + a.elapsed_time(b) / max(2, args.steps // 2)

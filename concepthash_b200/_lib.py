@@ -74,7 +74,7 @@ SIGNATURES = {
     "ch_hamming_select_tc": (C.c_int, [P, C.POINTER(SelectArgs), P]),
     "ch_cand_hist": (C.c_int, [P, C.POINTER(CandArgs), P]),
     "ch_cand_finalize": (C.c_int, [P, C.POINTER(CandArgs), P]),
-    "ch_cand_caps": (C.c_int, [P, P, P, P, P, C.c_int, C.c_int64, C.c_int64, C.c_int, P, P]),
+    "ch_cand_caps": (C.c_int, [P, P, P, P, P, P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, P, P]),
     "ch_slab_totals": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int64, P, P]),
     "ch_slab_exscan": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int64, P]),
     "ch_scan_bases": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, P, P, P, P]),

@@ -257,9 +257,10 @@ class CudaBackend:
             a.pr_k[i] = int(v)
         L.check(self.lib.ch_cand_finalize(self.ws, C.byref(a), self._stream()), "ch_cand_finalize")
 
-    def cand_caps(self, cand, thresh, nstripes, nq, nq_pad, sample_stride, cap):
-        L.check(self.lib.ch_cand_caps(self.ws, _ptr(cand["off"]), _ptr(cand["cnt"]), _ptr(cand["key"]), _ptr(thresh),
-                                      nstripes, nq, nq_pad, int(sample_stride), _ptr(cap), self._stream()),
+    def cand_caps(self, cand, thresh, list_stripes, rows_per_stripe, nstripes, nq, nq_pad, sample_stride, cap):
+        L.check(self.lib.ch_cand_caps(self.ws, _ptr(cand["off"]), _ptr(cand["cnt"]), _ptr(cand["rows"]),
+                                      _ptr(cand["key"]), _ptr(thresh), int(list_stripes), int(rows_per_stripe),
+                                      int(nstripes), nq, nq_pad, int(sample_stride), _ptr(cap), self._stream()),
                 "ch_cand_caps")
 
     def hamming_hist(self, **kw):

@@ -213,23 +213,35 @@ __global__ void __launch_bounds__(kCandWarps * 32) cand_final_kernel(const CandD
   }
 }
 
-// capacities of the full pass from a candidate list of the ROW SAMPLE: cap[s][q] = stride * (k + 6 sqrt(k + 1) + 10),
-// k = #candidates of (stripe s, query q) with key <= thresh[q]  (the bound of record_caps_kernel)
+// capacities of the full pass from a candidate list of the ROW SAMPLE (rows = sample row indices):
+// cap[s][q] = stride * (k + 6 sqrt(k + 1) + 10), k = #sample candidates of query q with key <= thresh[q] whose row
+// lies in stripe s of the full pass (sample rows [s * rows_per_stripe, (s + 1) * rows_per_stripe)) -- the bound of
+// record_caps_kernel.  One thread per query; `cap` is used as the counter array first.
 __global__ void cand_caps_kernel(const uint32_t* __restrict__ off, const uint32_t* __restrict__ cnt,
-                                 const uint8_t* __restrict__ key, const uint32_t* __restrict__ thresh, int nstripes,
-                                 long long nq, long long nq_pad, int stride, uint32_t* __restrict__ cap) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= static_cast<long long>(nstripes) * nq_pad) return;
-  const long long q = i % nq_pad;
-  uint32_t c = 0;
-  if (q < nq) {
-    const uint32_t o = off[i], n = cnt[i], t = thresh[q];
-    uint32_t k = 0;
-    for (uint32_t j = 0; j < n; ++j) k += key[o + j] <= t ? 1u : 0u;
-    const float kf = static_cast<float>(k);
-    c = static_cast<uint32_t>((kf + 6.0f * sqrtf(kf + 1.0f) + 10.0f) * static_cast<float>(stride));
+                                 const uint32_t* __restrict__ rows, const uint8_t* __restrict__ key,
+                                 const uint32_t* __restrict__ thresh, int list_stripes, int rows_per_stripe,
+                                 int nstripes, long long nq, long long nq_pad, int stride,
+                                 uint32_t* __restrict__ cap) {
+  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= nq_pad) return;
+  for (int s = 0; s < nstripes; ++s) cap[static_cast<size_t>(s) * nq_pad + q] = 0u;
+  if (q >= nq) return;
+  const uint32_t t = thresh[q];
+  for (int ls = 0; ls < list_stripes; ++ls) {
+    const size_t i = static_cast<size_t>(ls) * nq_pad + q;
+    const uint32_t o = off[i], n = cnt[i];
+    for (uint32_t j = 0; j < n; ++j) {
+      if (key[o + j] > t) continue;
+      int s = static_cast<int>((rows[o + j] & 0x7fffffffu) / static_cast<uint32_t>(rows_per_stripe));
+      if (s >= nstripes) s = nstripes - 1;
+      cap[static_cast<size_t>(s) * nq_pad + q] += 1u;
+    }
   }
-  cap[i] = c;
+  for (int s = 0; s < nstripes; ++s) {
+    const float kf = static_cast<float>(cap[static_cast<size_t>(s) * nq_pad + q]);
+    cap[static_cast<size_t>(s) * nq_pad + q] =
+        static_cast<uint32_t>((kf + 6.0f * sqrtf(kf + 1.0f) + 10.0f) * static_cast<float>(stride));
+  }
 }
 
 int to_dev(const ch_cand_args* a, CandDev* d) {
@@ -279,17 +291,19 @@ extern "C" int ch_cand_hist(ch_ws* ws, const ch_cand_args* a, void* stream) {
   return 0;
 }
 
-extern "C" int ch_cand_caps(ch_ws* ws, const uint32_t* cand_off, const uint32_t* cand_cnt, const uint8_t* cand_key,
-                            const uint32_t* thresh, int nstripes, int64_t nq, int64_t nq_pad, int sample_stride,
-                            uint32_t* cap_dev, void* stream) {
-  if (ws == nullptr || cand_off == nullptr || cand_cnt == nullptr || cand_key == nullptr || thresh == nullptr ||
-      cap_dev == nullptr)
+extern "C" int ch_cand_caps(ch_ws* ws, const uint32_t* cand_off, const uint32_t* cand_cnt, const uint32_t* cand_rows,
+                            const uint8_t* cand_key, const uint32_t* thresh, int list_stripes, int rows_per_stripe,
+                            int nstripes, int64_t nq, int64_t nq_pad, int sample_stride, uint32_t* cap_dev,
+                            void* stream) {
+  if (ws == nullptr || cand_off == nullptr || cand_cnt == nullptr || cand_rows == nullptr || cand_key == nullptr ||
+      thresh == nullptr || cap_dev == nullptr)
     CH_FAIL("null argument to ch_cand_caps");
-  if (nstripes <= 0 || nq <= 0 || nq_pad < nq || sample_stride < 1) CH_FAIL("bad arguments to ch_cand_caps");
+  if (list_stripes <= 0 || nstripes <= 0 || rows_per_stripe <= 0 || nq <= 0 || nq_pad < nq || sample_stride < 1)
+    CH_FAIL("bad arguments to ch_cand_caps");
   ChDeviceGuard guard(ws->device);
-  const long long n = static_cast<long long>(nstripes) * nq_pad;
-  cand_caps_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      cand_off, cand_cnt, cand_key, thresh, nstripes, nq, nq_pad, sample_stride, cap_dev);
+  cand_caps_kernel<<<static_cast<unsigned>((nq_pad + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      cand_off, cand_cnt, cand_rows, cand_key, thresh, list_stripes, rows_per_stripe, nstripes, nq, nq_pad,
+      sample_stride, cap_dev);
   CH_LAUNCH_CHECK(ws);
   return 0;
 }

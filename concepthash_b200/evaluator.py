@@ -601,7 +601,11 @@ class Evaluator:
             g.i8 = b.empty((self.rows_pad, b.tc_code_bytes(q.nbit)), torch.int8)
             per = ev._stream_per(nq_pad)
             # loads run on a side stream so that they are not queued behind the (long) select kernels
-            self.side = torch.cuda.Stream(device=g.bits.device)
+            # one side stream per evaluator, reused by every evaluation: the caching allocator pools blocks per
+            # stream, a fresh stream per call would cudaMalloc its copy blocks anew every time
+            if getattr(ev, "_side_stream", None) is None:
+                ev._side_stream = torch.cuda.Stream(device=g.bits.device)
+            self.side = ev._side_stream
             self.pinned = bool(c["db_codes"].is_contiguous() and c["db_codes"].is_pinned())
             self.loaded = {}
             self.blocks = []
@@ -699,8 +703,7 @@ class Evaluator:
         # block 0 of a streamed gallery travels while the GPU works on the sample: its (host-blocking) copy is
         # issued right after the first sample kernels have been queued
         first_load = streamer.load_first if streamer is not None else (lambda: None)
-        if (tc_pass and self.sample_two_level and not ternary and min(ns_ranks) >= self.sample2_min_rows
-                and (rps // stride) % getattr(b, "tc_tile_rows", 1) == 0):
+        if tc_pass and self.sample_two_level and not ternary and min(ns_ranks) >= self.sample2_min_rows:
             thresh, cap = self._sample_thresholds_tc(c, sp, ns_ranks, m, status, first_load)
         else:
             slab_s = b.zeros((nstripes, nbins, nq_pad), torch.int32)
@@ -804,27 +807,34 @@ class Evaluator:
         # row order may put all neighbours of a query into one stripe)
         cap0 = b.empty((1, nq_pad), torch.int32)
         b.record_caps(0, slab0, thresh0, 1, nbins, nq, nq_pad, False, cap0, sample_stride=sub)
-        geo_s = (threads, nq_pad, nstripes, rps // stride)
+        # the sample select has its own stripes: just enough CTAs to fill the GPU (capacity = the whole-sample bound
+        # per slice, because the row order may put all neighbours of a query into one stripe)
+        tile = getattr(b, "tc_tile_rows", 1)
+        groups = -(-nq_pad // getattr(b, "tc_queries_per_cta", 512))
+        n1 = max(1, min(-(-getattr(b, "sm_count", 148) // groups), max(1, ns // 4096)))
+        rps1 = (-(-ns // n1) + tile - 1) // tile * tile
+        n1 = max(1, -(-ns // rps1))
+        geo1 = (threads, nq_pad, n1, rps1)
         s_i8 = self._timed("expand_i8", 0, lambda: b.expand_i8(sp.bits, q.nbit))
         after_level0()              # (host-blocking work of the caller, while the GPU runs level 0)
-        cand1, tmax0 = self._alloc_cands(cap0.expand(nstripes, nq_pad).contiguous(), geo_s, nq, thresh0, status)
+        cand1, tmax0 = self._alloc_cands(cap0.expand(n1, nq_pad).contiguous(), geo1, nq, thresh0, status)
         nb0 = min(nbins, tmax0 + 1)
         # ---- level 1 ----
         q_i8 = self._query_plane(q, nq_pad, thresh0)
         dense = self._dense(1.25 * sub * m0, sum(ns_ranks))
         self._timed("sample_select_tc", q.n * ns, lambda: b.hamming_select_tc(
-            q_i8=q_i8, g_i8=s_i8, cand=cand1, nq=nq, nq_pad=nq_pad, ndb=ns, nbit=q.nbit, nstripes=nstripes,
-            rows_per_stripe=rps // stride, dense=dense))
+            q_i8=q_i8, g_i8=s_i8, cand=cand1, nq=nq, nq_pad=nq_pad, ndb=ns, nbit=q.nbit, nstripes=n1,
+            rows_per_stripe=rps1, dense=dense))
         tot1 = b.zeros((nb0, nq_pad), torch.int32)
         self._timed("cand_hist", 0, lambda: b.cand_hist(
             cand1, q_bits=q.bits, g_bits=sp.bits, q_lab=None, g_lab=None, label_mode=L.CH_LAB_NONE, mask_words=0,
-            tot_all=tot1, tot_rel=None, nq=nq, nq_pad=nq_pad, nstripes=nstripes, nbins=nb0, nbit=q.nbit))
+            tot_all=tot1, tot_rel=None, nq=nq, nq_pad=nq_pad, nstripes=n1, nbins=nb0, nbit=q.nbit))
         thresh1 = b.empty((nq_pad,), torch.int32)
         base1 = b.empty((nb0, nq_pad), torch.int32)
         b.scan_bases(comm.all_gather(tot1), comm.world, comm.rank, nb0, nq, nq_pad, m, base1, thresh1, None)
         thresh = torch.minimum(thresh1, thresh0)
         cap = b.empty((nstripes, nq_pad), torch.int32)
-        b.cand_caps(cand1, thresh, nstripes, nq, nq_pad, stride, cap)
+        b.cand_caps(cand1, thresh, n1, rps // stride, nstripes, nq, nq_pad, stride, cap)
         self.stats["sample2"] = dict(sub=sub, m0=m0, key_limit0=nb0, slots=self.stats.get("record_slots"))
         return thresh, cap
 

@@ -214,13 +214,14 @@ typedef struct ch_cand_args {
 } ch_cand_args;
 int ch_cand_hist(ch_ws* ws, const ch_cand_args* a, void* stream);
 int ch_cand_finalize(ch_ws* ws, const ch_cand_args* a, void* stream);
-/* Two-level threshold sampling: the candidate list came from a select pass over a 1-in-`sample_stride` ROW SAMPLE
- * (keys already written by ch_cand_hist).  cap[s][q] = sample_stride * (k + 6 sqrt(k + 1) + 10) with
- * k = #sample candidates of (stripe s, query q) whose key <= thresh[q]: the capacity of the full pass's slice
- * (same bound as ch_record_caps with sample_stride). */
-int ch_cand_caps(ch_ws* ws, const uint32_t* cand_off, const uint32_t* cand_cnt, const uint8_t* cand_key,
-                 const uint32_t* thresh, int nstripes, int64_t nq, int64_t nq_pad, int sample_stride,
-                 uint32_t* cap_dev, void* stream);
+/* Two-level threshold sampling: the candidate list (list_stripes slices per query, rows = SAMPLE row indices, keys
+ * already written by ch_cand_hist) came from a select pass over a 1-in-`sample_stride` row sample.
+ * cap[s][q] = sample_stride * (k + 6 sqrt(k + 1) + 10), k = #sample candidates of query q with key <= thresh[q]
+ * whose sample row lies in [s * rows_per_stripe, (s + 1) * rows_per_stripe): the capacity of slice (s, q) of the
+ * full pass (same bound as ch_record_caps with sample_stride).  cap_dev: (nstripes, nq_pad). */
+int ch_cand_caps(ch_ws* ws, const uint32_t* cand_off, const uint32_t* cand_cnt, const uint32_t* cand_rows,
+                 const uint8_t* cand_key, const uint32_t* thresh, int list_stripes, int rows_per_stripe,
+                 int nstripes, int64_t nq, int64_t nq_pad, int sample_stride, uint32_t* cap_dev, void* stream);
 
 /* slab reductions: totals over stripes -> tot (nbins, nq_pad); exclusive scan over stripes in place */
 int ch_slab_totals(ch_ws* ws, const uint32_t* slab, int nstripes, int nbins, int64_t nq_pad,

@@ -245,17 +245,20 @@ class EmuBackend:
                     key[o + i] = k
                     rows[o + i] = row | (0x80000000 if r else 0)
 
-    def cand_caps(self, cand, thresh, nstripes, nq, nq_pad, sample_stride, cap):
+    def cand_caps(self, cand, thresh, list_stripes, rows_per_stripe, nstripes, nq, nq_pad, sample_stride, cap):
         self.launches += 1
-        off, cnt, key = _u32(cand["off"]), _u32(cand["cnt"]), cand["key"].numpy()
+        off, cnt, rows, key = _u32(cand["off"]), _u32(cand["cnt"]), _u32(cand["rows"]), cand["key"].numpy()
         th, c = _u32(thresh), _u32(cap)
         c[...] = 0
-        for s in range(nstripes):
+        raw = np.zeros((nstripes, nq_pad), dtype=np.float32)
+        for ls in range(list_stripes):
             for q in range(nq):
-                o = int(off[s, q])
-                k = np.float32((key[o:o + int(cnt[s, q])] <= th[q]).sum())
-                c[s, q] = np.uint32((k + np.float32(6.0) * np.sqrt(k + np.float32(1.0)) + np.float32(10.0)) *
-                                    np.float32(sample_stride))
+                o = int(off[ls, q])
+                for j in range(int(cnt[ls, q])):
+                    if key[o + j] <= th[q]:
+                        raw[min(int(rows[o + j] & 0x7FFFFFFF) // rows_per_stripe, nstripes - 1), q] += 1
+        bound = (raw + np.float32(6.0) * np.sqrt(raw + np.float32(1.0)) + np.float32(10.0)) * np.float32(sample_stride)
+        c[:, :nq] = bound[:, :nq].astype(np.uint32)
 
     def cand_finalize(self, cand, *, mode, base0_all, base0_rel, nq, nq_pad, nstripes, nbins, remove_first=False,
                       first_rel=None, first_rel_out=None, cols=None, r_eff=(), pr_k=(), ids=None, keys=None, R=0,
