@@ -710,8 +710,8 @@ class Evaluator:
             self._hist(q, sp, geo_s, ternary, L.CH_LAB_NONE, 0, slab_s, None)
             thresh = b.empty((nq_pad,), torch.int32)
             base_tmp = b.empty((nbins, nq_pad), torch.int32)
-            tot_s = comm.all_gather(self._local_totals(slab_s, geo_s, nbins))
-            b.scan_bases(tot_s, comm.world, comm.rank, nbins, nq, nq_pad, m, base_tmp, thresh, None)
+            tot_s = self._summed_totals(self._local_totals(slab_s, geo_s, nbins))
+            b.scan_bases(tot_s, 1, 0, nbins, nq, nq_pad, m, base_tmp, thresh, None)
             # ---- capacities: scaled sample candidate counts (record path: never more than the class counts) ----
             cap = b.empty((nstripes, nq_pad), torch.int32)
             b.record_caps(0, slab_s, thresh, nstripes, nbins, nq, nq_pad, False, cap, sample_stride=stride)
@@ -802,7 +802,7 @@ class Evaluator:
         m0 = int(mu0 + 5.0 * mu0 ** 0.5 + 4.0) + 1
         thresh0 = b.empty((nq_pad,), torch.int32)
         base_tmp = b.empty((nbins, nq_pad), torch.int32)
-        b.scan_bases(comm.all_gather(slab0[0]), comm.world, comm.rank, nbins, nq, nq_pad, m0, base_tmp, thresh0, None)
+        b.scan_bases(self._summed_totals(slab0[0].clone()), 1, 0, nbins, nq, nq_pad, m0, base_tmp, thresh0, None)
         # list capacities of the sample select: the local mini-sample count <= t0, scaled -- for EVERY stripe (the
         # row order may put all neighbours of a query into one stripe)
         cap0 = b.empty((1, nq_pad), torch.int32)
@@ -831,7 +831,7 @@ class Evaluator:
             tot_all=tot1, tot_rel=None, nq=nq, nq_pad=nq_pad, nstripes=n1, nbins=nb0, nbit=q.nbit))
         thresh1 = b.empty((nq_pad,), torch.int32)
         base1 = b.empty((nb0, nq_pad), torch.int32)
-        b.scan_bases(comm.all_gather(tot1), comm.world, comm.rank, nb0, nq, nq_pad, m, base1, thresh1, None)
+        b.scan_bases(self._summed_totals(tot1), 1, 0, nb0, nq, nq_pad, m, base1, thresh1, None)
         thresh = torch.minimum(thresh1, thresh0)
         cap = b.empty((nstripes, nq_pad), torch.int32)
         b.cand_caps(cand1, thresh, n1, rps // stride, nstripes, nq, nq_pad, stride, cap)
@@ -849,6 +849,13 @@ class Evaluator:
             ok = (qid >= 0) & (qid < c["nclass"])
             total_rel[:nq] = torch.where(ok, cls_tot[qid.clamp(0, c["nclass"] - 1)], torch.zeros_like(cls_tot[:1]))
         return total_rel
+
+    def _summed_totals(self, tot):
+        """(nbins, nq_pad) key totals summed over the ranks, shaped (1, nbins, nq_pad) for ``scan_bases`` with
+        world = 1: thresholds only need the SUM (an all-reduce moves 1/world of what the all-gather would)."""
+        if self.comm.world > 1:
+            tot = self.comm.all_reduce_sum(tot.contiguous())
+        return tot.unsqueeze(0)
 
     def _local_totals(self, slab, geo, nbins):
         threads, nq_pad, nstripes, rps = geo
