@@ -41,7 +41,8 @@ class SelectArgs(C.Structure):
 
 
 class CandArgs(C.Structure):
-    _fields_ = [(n, P) for n in ("cand_off", "cand_cnt", "cand_rows", "cand_key", "q_bits", "g_bits", "q_lab", "g_lab",
+    _fields_ = [(n, P) for n in ("cand_off", "cand_cnt", "cand_rows", "cand_key", "q_bits", "g_bits", "g_plane", "q_lab",
+                                 "g_lab",
                                  "tot_all", "tot_rel", "base0_all", "base0_rel", "first_rel", "first_rel_out", "cols",
                                  "ids", "keys", "err_flag")] + \
                [(n, C.c_int64) for n in ("nq", "nq_pad", "R", "row_offset")] + \
@@ -73,6 +74,8 @@ SIGNATURES = {
     "ch_expand_i8": (C.c_int, [P, P, C.c_int64, C.c_int, P, C.c_int64, P, C.c_int64, P]),
     "ch_hamming_select_tc": (C.c_int, [P, C.POINTER(SelectArgs), P]),
     "ch_cand_hist": (C.c_int, [P, C.POINTER(CandArgs), P]),
+    "ch_gather_plane_words": (C.c_int, [C.c_int]),
+    "ch_gather_plane": (C.c_int, [P, P, P, C.c_int64, C.c_int, P, P]),
     "ch_cand_finalize": (C.c_int, [P, C.POINTER(CandArgs), P]),
     "ch_cand_caps": (C.c_int, [P, P, P, P, P, P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, P, P]),
     "ch_slab_totals": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int64, P, P]),

@@ -234,10 +234,23 @@ class CudaBackend:
                 setattr(a, k, v)
         return a
 
+    def gather_plane_words(self, nbit):
+        return int(self.lib.ch_gather_plane_words(int(nbit)))
+
+    def gather_plane(self, bits, ids, nbit, out=None):
+        """[code words | class id | pad] per gallery row (single-label shards): one sector per candidate lookup"""
+        rows = int(bits.shape[0])
+        if out is None:
+            out = self.empty((rows, self.gather_plane_words(nbit)), torch.int32)
+        assert out.is_contiguous() and out.shape[0] >= rows and ids.shape[0] >= rows
+        L.check(self.lib.ch_gather_plane(self.ws, _ptr(bits), _ptr(ids), rows, nbit, _ptr(out), self._stream()),
+                "ch_gather_plane")
+        return out
+
     def cand_hist(self, cand, *, q_bits, g_bits, q_lab, g_lab, label_mode, mask_words, tot_all, tot_rel, nq, nq_pad,
-                  nstripes, nbins, nbit, stripe0=0):
+                  nstripes, nbins, nbit, stripe0=0, g_plane=None):
         """totals are accumulated; ``stripe0`` / ``nstripes`` select a block of stripes of the list"""
-        a = self._cand_args(cand, nq, nq_pad, nstripes, nbins, stripe0, q_bits=q_bits, g_bits=g_bits, q_lab=q_lab, g_lab=g_lab,
+        a = self._cand_args(cand, nq, nq_pad, nstripes, nbins, stripe0, g_plane=g_plane, q_bits=q_bits, g_bits=g_bits, q_lab=q_lab, g_lab=g_lab,
                             label_mode=label_mode, mask_words=mask_words, tot_all=tot_all, tot_rel=tot_rel, nbit=nbit)
         L.check(self.lib.ch_cand_hist(self.ws, C.byref(a), self._stream()), "ch_cand_hist")
 

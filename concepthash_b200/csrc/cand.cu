@@ -20,6 +20,7 @@ struct CandDev {
   const uint32_t* cand_off; const uint32_t* cand_cnt;
   uint32_t* cand_rows; uint8_t* cand_key;
   const uint32_t* q_bits; const uint32_t* g_bits;
+  const uint32_t* g_plane;   // (rows, PW) [code words | class id | pad]: one sector per candidate; or NULL
   const uint32_t* q_lab; const uint32_t* g_lab;
   uint32_t* tot_all; uint32_t* tot_rel;
   const uint32_t* base0_all; const uint32_t* base0_rel;
@@ -53,6 +54,41 @@ __device__ __forceinline__ uint32_t key_of(const uint32_t (&qw)[W], const uint32
   return key;
 }
 
+// words per row of the gather plane: the code words + the class id, rounded up to a power of two (8 .. 64 bytes)
+__host__ __device__ constexpr int plane_words(int W) { return W == 1 ? 2 : W == 2 ? 4 : W == 4 ? 8 : 16; }
+
+// key and class id of one candidate from the gather plane: ONE 32-byte sector for codes of <= 128 bits
+template <int W>
+__device__ __forceinline__ uint32_t key_id_of(const uint32_t (&qw)[W], const uint32_t* __restrict__ plane, uint32_t row,
+                                              uint32_t* id) {
+  constexpr int PW = plane_words(W);
+  uint32_t g[PW];
+  if constexpr (PW == 2) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(plane) + row);
+    g[0] = v.x; g[1] = v.y;
+  } else {
+#pragma unroll
+    for (int v4 = 0; v4 < PW / 4; ++v4) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(plane) + static_cast<size_t>(row) * (PW / 4) + v4);
+      g[4 * v4] = v.x; g[4 * v4 + 1] = v.y; g[4 * v4 + 2] = v.z; g[4 * v4 + 3] = v.w;
+    }
+  }
+  uint32_t key = 0;
+#pragma unroll
+  for (int w = 0; w < W; ++w) key += __popc(qw[w] ^ g[w]);
+  *id = g[W];
+  return key;
+}
+
+__global__ void gather_plane_kernel(const uint32_t* __restrict__ bits, const uint32_t* __restrict__ ids, long long rows,
+                                    int W, int PW, uint32_t* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * PW) return;
+  const long long r = i / PW;
+  const int w = static_cast<int>(i - r * PW);
+  out[i] = w < W ? bits[r * W + w] : (w == W ? ids[r] : 0u);
+}
+
 template <int W>
 __global__ void __launch_bounds__(kCandWarps * 32) cand_hist_kernel(const CandDev a) {
   extern __shared__ uint32_t sh[];
@@ -84,8 +120,14 @@ __global__ void __launch_bounds__(kCandWarps * 32) cand_hist_kernel(const CandDe
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        key[u] = ok[u] ? key_of<W>(qw, a.g_bits, row[u]) : 0u;
         rel[u] = false;
+        if (a.g_plane != nullptr) {            // single-label: code and class id come in one sector
+          uint32_t id = 0u;
+          key[u] = ok[u] ? key_id_of<W>(qw, a.g_plane, row[u], &id) : 0u;
+          rel[u] = ok[u] && id == qid;
+          continue;
+        }
+        key[u] = ok[u] ? key_of<W>(qw, a.g_bits, row[u]) : 0u;
         if (ok[u]) {
           if (a.label_mode == CH_LAB_ID) {
             rel[u] = __ldg(a.g_lab + row[u]) == qid;
@@ -253,6 +295,7 @@ int to_dev(const ch_cand_args* a, CandDev* d) {
   if (a->nq <= 0 || a->nq_pad < a->nq || a->nstripes <= 0) CH_FAIL("bad candidate geometry");
   d->cand_off = a->cand_off; d->cand_cnt = a->cand_cnt; d->cand_rows = a->cand_rows; d->cand_key = a->cand_key;
   d->q_bits = a->q_bits; d->g_bits = a->g_bits; d->q_lab = a->q_lab; d->g_lab = a->g_lab;
+  d->g_plane = a->label_mode == CH_LAB_ID ? a->g_plane : nullptr;
   d->tot_all = a->tot_all; d->tot_rel = a->tot_rel; d->base0_all = a->base0_all; d->base0_rel = a->base0_rel;
   d->first_rel = a->first_rel; d->first_rel_out = a->first_rel_out; d->cols = a->cols;
   d->ids = reinterpret_cast<long long*>(a->ids); d->keys = a->keys; d->err_flag = a->err_flag;
@@ -265,6 +308,27 @@ int to_dev(const ch_cand_args* a, CandDev* d) {
 }
 
 }  // namespace
+
+extern "C" int ch_gather_plane_words(int nbit) {
+  const int w = ch_code_words(nbit);
+  return w == 0 ? 0 : plane_words(w);
+}
+
+extern "C" int ch_gather_plane(ch_ws* ws, const uint32_t* bits_dev, const uint32_t* ids_dev, int64_t rows, int nbit,
+                               uint32_t* out_dev, void* stream) {
+  if (ws == nullptr || bits_dev == nullptr || ids_dev == nullptr || out_dev == nullptr)
+    CH_FAIL("null argument to ch_gather_plane");
+  const int W = ch_code_words(nbit);
+  if (W == 0 || rows < 0) CH_FAIL("bad arguments to ch_gather_plane");
+  if (rows == 0) return 0;
+  ChDeviceGuard guard(ws->device);
+  const int PW = plane_words(W);
+  const long long n = rows * PW;
+  gather_plane_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      bits_dev, ids_dev, rows, W, PW, out_dev);
+  CH_LAUNCH_CHECK(ws);
+  return 0;
+}
 
 extern "C" int ch_cand_hist(ch_ws* ws, const ch_cand_args* a, void* stream) {
   if (ws == nullptr) CH_FAIL("null workspace");

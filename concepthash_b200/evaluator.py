@@ -65,7 +65,10 @@ def _as_int_list(t):
 
 class Packed:
     """Packed codes + labels of one side (query or gallery shard)."""
-    __slots__ = ("n", "nbit", "bits", "nz", "ids", "masks", "info", "ncls", "i8")
+    __slots__ = ("n", "nbit", "bits", "nz", "ids", "masks", "info", "ncls", "i8", "plane")
+
+    def __init__(self):
+        self.plane = None
 
 
 class Evaluator:
@@ -302,10 +305,23 @@ class Evaluator:
         threads, nq_pad, nstripes_all, rps = c["geo"]
         label_mode, lw = c["label_mode"], c["lw"]
         lab = lambda p: None if label_mode == L.CH_LAB_NONE else (p.ids if label_mode == L.CH_LAB_ID else p.masks)
+        kw = {}
+        if label_mode == L.CH_LAB_ID and hasattr(b, "gather_plane"):
+            # single-label gallery: [code | class id] rows, one memory sector per candidate instead of two gathers
+            if nstripes is None:
+                if g.plane is None:
+                    g.plane = b.gather_plane(g.bits, g.ids, g.nbit)
+            else:                                            # a row block of a streamed gallery
+                if g.plane is None:
+                    g.plane = b.empty((g.bits.shape[0], b.gather_plane_words(g.nbit)), torch.int32)
+                r0 = stripe0 * rps
+                r1 = min(g.bits.shape[0], (stripe0 + nstripes) * rps)
+                b.gather_plane(g.bits[r0:r1], g.ids[r0:r1], g.nbit, out=g.plane[r0:r1])
+            kw = dict(g_plane=g.plane)
         self._timed("cand_hist", 0, lambda: b.cand_hist(
             cand, q_bits=q.bits, g_bits=g.bits, q_lab=lab(q), g_lab=lab(g), label_mode=label_mode, mask_words=lw,
             tot_all=tot[0], tot_rel=tot[1] if label_mode != L.CH_LAB_NONE else None, nq=c["nq"], nq_pad=nq_pad,
-            nstripes=nstripes_all if nstripes is None else nstripes, nbins=nbins, nbit=q.nbit, stripe0=stripe0))
+            nstripes=nstripes_all if nstripes is None else nstripes, nbins=nbins, nbit=q.nbit, stripe0=stripe0, **kw))
 
     def _cand_bases(self, c, cand, nbins, need=None, tot=None):
         """keys + label matches of the candidates -> per-rank key totals -> all-gather -> bases (+ verification
@@ -716,7 +732,8 @@ class Evaluator:
             cap = b.empty((nstripes, nq_pad), torch.int32)
             b.record_caps(0, slab_s, thresh, nstripes, nbins, nq, nq_pad, False, cap, sample_stride=stride)
             first_load()
-        cls = self._class_counts(c)
+        # per-stripe class counts: record capacities of the POPC path; whole-gallery relevant counts for R@k
+        cls = self._class_counts(c) if (not tc_pass or c["pr_k"]) else None
         self.stats["sample"] = dict(stride=stride, rows=ns_total, m=m)
         if tc_pass:
             # ---- the one full pass on the tensor cores: candidate lists, then ranks from the lists ----

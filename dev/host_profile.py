@@ -10,7 +10,9 @@ import torch
 sys.path.insert(0, ".")
 from concepthash_b200 import hashing, synth  # noqa: E402
 
-d, dl, q, ql, ncls = synth.make_random_case(25000, 125000, 128, 101, p=0.30, seed=0, device="cuda")
+import os
+NDB = int(os.environ.get("NDB", "125000"))
+d, dl, q, ql, ncls = synth.make_random_case(25000, NDB, 128, 101, p=0.30, seed=0, device="cuda")
 ev = hashing.get_evaluator()
 f = lambda: ev.evaluate(d, dl, q, ql, [1000], 0.0, [], False)
 for _ in range(3):
@@ -27,4 +29,4 @@ for _ in range(10):
     f()
 torch.cuda.synchronize()
 pr.disable()
-pstats.Stats(pr).sort_stats("tottime").print_stats(28)
+pstats.Stats(pr).sort_stats("tottime").print_stats(22)

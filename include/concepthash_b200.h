@@ -200,6 +200,7 @@ typedef struct ch_cand_args {
   const uint32_t* cand_off;  const uint32_t* cand_cnt;    /* (nstripes, nq_pad) */
   uint32_t* cand_rows;       uint8_t* cand_key;           /* per candidate slot */
   const uint32_t* q_bits;    const uint32_t* g_bits;      /* packed codes (hist only) */
+  const uint32_t* g_plane;   /* optional (CH_LAB_ID): ch_gather_plane output -- code + class id in ONE sector */
   const uint32_t* q_lab;     const uint32_t* g_lab;       /* ids or masks; NULL if CH_LAB_NONE (hist only) */
   uint32_t* tot_all;         uint32_t* tot_rel;           /* (nbins, nq_pad) out of ch_cand_hist */
   const uint32_t* base0_all; const uint32_t* base0_rel;   /* (nbins, nq_pad) in of ch_cand_finalize */
@@ -213,6 +214,12 @@ typedef struct ch_cand_args {
   int64_t pr_k[CH_MAX_PR];
 } ch_cand_args;
 int ch_cand_hist(ch_ws* ws, const ch_cand_args* a, void* stream);
+/* gather plane of a single-label gallery shard: out (rows, ch_gather_plane_words(nbit)) u32 = [code words | class
+ * id | zero pad], 8 .. 64 bytes per row, so that the key + label match of a candidate costs one memory sector
+ * instead of two random gathers (ch_cand_hist is bound by L2 sectors) */
+int ch_gather_plane_words(int nbit);
+int ch_gather_plane(ch_ws* ws, const uint32_t* bits_dev, const uint32_t* ids_dev, int64_t rows, int nbit,
+                    uint32_t* out_dev, void* stream);
 int ch_cand_finalize(ch_ws* ws, const ch_cand_args* a, void* stream);
 /* Two-level threshold sampling: the candidate list (list_stripes slices per query, rows = SAMPLE row indices, keys
  * already written by ch_cand_hist) came from a select pass over a 1-in-`sample_stride` row sample.

@@ -218,7 +218,7 @@ class EmuBackend:
 
     # K3/K4 on candidate lists
     def cand_hist(self, cand, *, q_bits, g_bits, q_lab, g_lab, label_mode, mask_words, tot_all, tot_rel, nq, nq_pad,
-                  nstripes, nbins, nbit, stripe0=0):
+                  nstripes, nbins, nbit, stripe0=0, g_plane=None):
         self.launches += 1
         off, cnt, rows, key = _u32(cand["off"]), _u32(cand["cnt"]), _u32(cand["rows"]), cand["key"].numpy()
         qs, gs = _unpack(_u32(q_bits)[:nq], nbit), _unpack(_u32(g_bits), nbit)
