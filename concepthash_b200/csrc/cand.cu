@@ -258,31 +258,39 @@ __global__ void __launch_bounds__(kCandWarps * 32) cand_final_kernel(const CandD
 // capacities of the full pass from a candidate list of the ROW SAMPLE (rows = sample row indices):
 // cap[s][q] = stride * (k + 6 sqrt(k + 1) + 10), k = #sample candidates of query q with key <= thresh[q] whose row
 // lies in stripe s of the full pass (sample rows [s * rows_per_stripe, (s + 1) * rows_per_stripe)) -- the bound of
-// record_caps_kernel.  One thread per query; `cap` is used as the counter array first.
-__global__ void cand_caps_kernel(const uint32_t* __restrict__ off, const uint32_t* __restrict__ cnt,
-                                 const uint32_t* __restrict__ rows, const uint8_t* __restrict__ key,
-                                 const uint32_t* __restrict__ thresh, int list_stripes, int rows_per_stripe,
-                                 int nstripes, long long nq, long long nq_pad, int stride,
-                                 uint32_t* __restrict__ cap) {
-  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (q >= nq_pad) return;
-  for (int s = 0; s < nstripes; ++s) cap[static_cast<size_t>(s) * nq_pad + q] = 0u;
-  if (q >= nq) return;
-  const uint32_t t = thresh[q];
-  for (int ls = 0; ls < list_stripes; ++ls) {
-    const size_t i = static_cast<size_t>(ls) * nq_pad + q;
-    const uint32_t o = off[i], n = cnt[i];
-    for (uint32_t j = 0; j < n; ++j) {
-      if (key[o + j] > t) continue;
-      int s = static_cast<int>((rows[o + j] & 0x7fffffffu) / static_cast<uint32_t>(rows_per_stripe));
-      if (s >= nstripes) s = nstripes - 1;
-      cap[static_cast<size_t>(s) * nq_pad + q] += 1u;
+// record_caps_kernel.  One warp per query, per-stripe counters in shared memory.
+__global__ void __launch_bounds__(kCandWarps * 32) cand_caps_kernel(
+    const uint32_t* __restrict__ off, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ rows,
+    const uint8_t* __restrict__ key, const uint32_t* __restrict__ thresh, int list_stripes, int rows_per_stripe,
+    int nstripes, long long nq, long long nq_pad, int stride, uint32_t* __restrict__ cap) {
+  extern __shared__ uint32_t sh[];                       // per warp: nstripes counters
+  const int wip = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long q = static_cast<long long>(blockIdx.x) * kCandWarps + wip;
+  if (q >= nq_pad) return;                               // whole warps leave; only __syncwarp below
+  uint32_t* c = sh + static_cast<size_t>(wip) * nstripes;
+  for (int s = lane; s < nstripes; s += 32) c[s] = 0u;
+  __syncwarp();
+  if (q < nq) {
+    const uint32_t t = thresh[q];
+    for (int ls = 0; ls < list_stripes; ++ls) {
+      const size_t i = static_cast<size_t>(ls) * nq_pad + q;
+      const uint32_t o = off[i], n = cnt[i];
+      for (uint32_t j = lane; j < n; j += 32) {
+        if (key[o + j] > t) continue;
+        int s = static_cast<int>((rows[o + j] & 0x7fffffffu) / static_cast<uint32_t>(rows_per_stripe));
+        if (s >= nstripes) s = nstripes - 1;
+        atomicAdd(&c[s], 1u);
+      }
     }
   }
-  for (int s = 0; s < nstripes; ++s) {
-    const float kf = static_cast<float>(cap[static_cast<size_t>(s) * nq_pad + q]);
-    cap[static_cast<size_t>(s) * nq_pad + q] =
-        static_cast<uint32_t>((kf + 6.0f * sqrtf(kf + 1.0f) + 10.0f) * static_cast<float>(stride));
+  __syncwarp();
+  for (int s = lane; s < nstripes; s += 32) {
+    uint32_t v = 0u;
+    if (q < nq) {
+      const float kf = static_cast<float>(c[s]);
+      v = static_cast<uint32_t>((kf + 6.0f * sqrtf(kf + 1.0f) + 10.0f) * static_cast<float>(stride));
+    }
+    cap[static_cast<size_t>(s) * nq_pad + q] = v;
   }
 }
 
@@ -365,7 +373,8 @@ extern "C" int ch_cand_caps(ch_ws* ws, const uint32_t* cand_off, const uint32_t*
   if (list_stripes <= 0 || nstripes <= 0 || rows_per_stripe <= 0 || nq <= 0 || nq_pad < nq || sample_stride < 1)
     CH_FAIL("bad arguments to ch_cand_caps");
   ChDeviceGuard guard(ws->device);
-  cand_caps_kernel<<<static_cast<unsigned>((nq_pad + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  cand_caps_kernel<<<static_cast<unsigned>((nq_pad + kCandWarps - 1) / kCandWarps), kCandWarps * 32,
+                     static_cast<size_t>(kCandWarps) * nstripes * sizeof(uint32_t), static_cast<cudaStream_t>(stream)>>>(
       cand_off, cand_cnt, cand_rows, cand_key, thresh, list_stripes, rows_per_stripe, nstripes, nq, nq_pad,
       sample_stride, cap_dev);
   CH_LAUNCH_CHECK(ws);
