@@ -381,7 +381,7 @@ def test_pack_sign_flat_fast_path(H, nbit, dtype):
         assert int(f1.cpu()[0]) == 1
 
 
-@pytest.mark.parametrize("nbit", [32, 48, 64, 96, 128])
+@pytest.mark.parametrize("nbit", [16, 31, 32, 48, 64, 96, 100, 127, 128])
 def test_tensor_core_select_equals_popc_select(H, nbit):
     """The tcgen05 (int8 +-1, UTCIMMA) select pass + candidate-list ranking must give the results of the XOR+POPC
     select pass + record ranking: same AP per query (to fp64 summation order), bit-identical ranked ids -- and
@@ -461,3 +461,16 @@ def test_zero_mean_eval_fused(H, dtype):
     om, _, _ = mo.calculate_mAP(dzs, dl, qzs, ql, 50, threshold=0.1)
     m, _, _ = H.calculate_mAP(ds.cuda(), dl.cuda(), qs.cuda(), ql.cuda(), 50, threshold=0.1, zero_mean_eval=True)
     assert abs(m - om) < TOL
+
+
+def test_tensor_core_path_tiny_shapes(H):
+    """one query, a handful of rows, R larger than the gallery: the tensor-core select pass with mostly padding"""
+    ev = H.get_evaluator()
+    for nq, ndb, nbit, R in [(1, 300, 64, 10), (3, 129, 128, 5), (130, 1000, 32, 50), (5, 257, 16, 400)]:
+        d, dl, q, ql, ncls = synth.make_random_case(nq, ndb, nbit, 4, p=0.3, seed=nq + ndb)
+        m, rec, prec = H.calculate_mAP(d.cuda(), dl.cuda(), q.cuda(), ql.cuda(), R, PRs=[1, 5])
+        om, orec, oprec = mo.calculate_mAP(d, dl, q, ql, R, PRs=[1, 5])
+        assert abs(m - om) < TOL and np.allclose(rec, orec, atol=TOL) and np.allclose(prec, oprec, atol=TOL), (nq, ndb)
+        ids, dist = H.retrieve_topk(q.cuda(), d.cuda(), min(R, 40))
+        oids, odist = mo.topk_ids(q, d, min(R, 40))
+        assert torch.equal(ids.cpu(), oids) and torch.equal(dist.cpu(), odist)
