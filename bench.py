@@ -130,7 +130,7 @@ def cpu_reference_sample(w, d, dl, q, ql):
     elif w["R"] == -1:
         sq = min(nq, max(64, int(3.0e7 / ndb)))       # the numpy AP loop dominates: ~2e6 pairs/s
     else:
-        sq = min(nq, max(16, int(2.0e9 / ndb)))       # the chunked GEMM dominates: ~1.3e8 pairs/s on 16 cores
+        sq = min(nq, max(16, int(4.0e9 / ndb)))       # the chunked GEMM dominates: ~2.5e8 pairs/s on 16 cores
     dc, dlc = d.cpu(), dl.cpu()
     qc, qlc = q[:sq].cpu(), ql[:sq].cpu()
     t0 = time.perf_counter()
@@ -142,7 +142,7 @@ def cpu_reference_sample(w, d, dl, q, ql):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
