@@ -80,7 +80,9 @@ class Evaluator:
         self.sample_stride = 32            # top-R: 1-in-32 row sample picks the threshold (0/1 = exact two-pass)
         self.sample_two_level = True       # thresholds from the sample by a tensor-core select pass (see below)
         self.sample2_sub = 16              # ... whose own thresholds come from every 16th sample row
-        self.sample2_min_rows = 16_384     # ... when the sample has at least this many rows
+        self.sample2_min_rows = 2_048      # ... when every rank's sample has at least this many rows
+        self.sample2_min_work = 1.0e9      # ... and histogramming it would cost >= ~0.2 ms (nq x rows x words); the
+        #                                      two-level route adds a host sync and a collective
         self.sample_min_rows = 200_000     # below this the two-pass path is cheap anyway
         self.sample_min_ratio = 64         # ... and the sample must still hold ~R/stride*... rows: need ndb >= ratio * R
         self.stream_host_gallery = True    # host-resident gallery: overlap its H2D copy with the select pass
@@ -719,7 +721,8 @@ class Evaluator:
         # block 0 of a streamed gallery travels while the GPU works on the sample: its (host-blocking) copy is
         # issued right after the first sample kernels have been queued
         first_load = streamer.load_first if streamer is not None else (lambda: None)
-        if tc_pass and self.sample_two_level and not ternary and min(ns_ranks) >= self.sample2_min_rows:
+        if (tc_pass and self.sample_two_level and not ternary and min(ns_ranks) >= self.sample2_min_rows and
+                float(nq) * min(ns_ranks) * int(q.bits.shape[1]) >= self.sample2_min_work):
             thresh, cap = self._sample_thresholds_tc(c, sp, ns_ranks, m, status, first_load)
         else:
             slab_s = b.zeros((nstripes, nbins, nq_pad), torch.int32)

@@ -19,7 +19,7 @@ def run_case(d, dl, q, ql, R, PRs=(), rf=False, thr=0.0, rps=64, sampled=False, 
                    else EmuBackend(rows_per_stripe=rps))
     ev.sample_two_level = two_level
     if two_level:
-        ev.sample2_min_rows, ev.sample2_sub = 0, 4
+        ev.sample2_min_rows, ev.sample2_min_work, ev.sample2_sub = 0, 0, 4
     if sampled:
         ev.sample_stride, ev.sample_min_rows, ev.sample_min_ratio = 4, 0, 4
     else:

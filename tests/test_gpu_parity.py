@@ -336,16 +336,16 @@ def test_sampled_one_pass_equals_exact_two_pass(H):
         assert mode == ("topR-sampled" if stride else "topR")
     assert _same(res[16], res[0]) and _same(res[default_stride], res[0])
     # thresholds through the two-level sample (select pass over the sample itself), forced at this size, and off
-    saved = (ev.sample2_min_rows, ev.sample_two_level)
+    saved = (ev.sample2_min_rows, ev.sample2_min_work, ev.sample_two_level)
     try:
-        ev.sample2_min_rows = 0
+        ev.sample2_min_rows = ev.sample2_min_work = 0
         r2 = ev.evaluate(d, dl, q, ql, [100, 1000], 0.0, [1, 5, 10], False, return_ap=True)
         assert ev.stats["mode"] == "topR-sampled" and "sample2" in ev.stats, ev.stats
         ev.sample_two_level = False
         r1 = ev.evaluate(d, dl, q, ql, [100, 1000], 0.0, [1, 5, 10], False, return_ap=True)
         assert ev.stats["mode"] == "topR-sampled" and "sample2" not in ev.stats, ev.stats
     finally:
-        ev.sample2_min_rows, ev.sample_two_level = saved
+        ev.sample2_min_rows, ev.sample2_min_work, ev.sample_two_level = saved
     assert _same(r2, res[0]) and _same(r1, res[0])
     # adversarial: the row sample sees only near duplicates, the rest of the gallery is far away
     n = 400_000

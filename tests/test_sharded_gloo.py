@@ -52,7 +52,7 @@ def _worker(rank, world, port, out):
                 # sampled top-R with two-level thresholds across ranks
                 ev2 = Evaluator(EmuBackend(rows_per_stripe=32, threads=128, tensor_cores=True), DistComm())
                 ev2.sample_stride, ev2.sample_min_rows, ev2.sample_min_ratio = 2, 0, 4
-                ev2.sample2_min_rows, ev2.sample2_sub = 0, 2
+                ev2.sample2_min_rows, ev2.sample2_min_work, ev2.sample2_sub = 0, 0, 2
                 results["s2"] = ev2.evaluate(ds, dls, q, ql, [15], thr, PRs, rf) + (ev2.stats["mode"],
                                                                                      "sample2" in ev2.stats)
                 # zero_mean_eval: the column mean is that of the WHOLE gallery (sums all-reduced over the ranks)
