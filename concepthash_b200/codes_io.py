@@ -62,7 +62,8 @@ class PackedCodes:
 
     @staticmethod
     def from_codes(codes):
-        """CPU reference packing of real-valued codes (bit = code > 0); raises if a sign is 0."""
+        """Host-side writer of the bit layout (bit = code > 0) for tools and tests that have no GPU at hand; raises
+        if a sign is 0.  The evaluation path never calls it: ``hashing.pack_codes`` packs with the CUDA kernel."""
         x = torch.as_tensor(codes).detach().cpu()
         if (x == 0).any():
             raise ValueError("codes with exact zeros cannot be stored as packed bits")

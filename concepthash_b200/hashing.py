@@ -129,6 +129,24 @@ def retrieve_topk(query_codes, db_codes, R, threshold=0., remove_first_retrieved
     return ids, dist
 
 
+def pack_codes(codes):
+    """Real-valued codes -> ``PackedCodes`` through the sign/bit-pack KERNEL (K1): what ``codes_io.save_packed``
+    writes and what every entry point accepts in place of real-valued codes.  Raises if some sign is 0."""
+    from .codes_io import PackedCodes
+    codes = _as_tensor(codes)
+    ev = get_evaluator(_device_of(codes))
+    if hasattr(ev.b, "begin"):
+        ev.b.begin()
+    flags = ev.b.zeros((1,), torch.int32)
+    bits, _ = ev.b.pack_sign(codes, 0.0, flags, False)
+    fl = int(flags.cpu()[0])
+    if fl & 2:
+        raise ValueError("codes contain NaN")
+    if fl & 1:
+        raise ValueError("codes with exact zeros cannot be stored as packed bits")
+    return PackedCodes(bits[:codes.shape[0]].contiguous(), int(codes.shape[1]))
+
+
 def get_hamm_dist(codes, centroids, margin=0., normalize=False):
     """Code -> codebook Hamming distance matrix (callers: trainers/orthohash.py:362,397,430,465,
     trainers/dpn.py:30,62; identity: trainers/orthohash.py:263-264).  float32, on the GPU."""

@@ -79,6 +79,8 @@ def test_evaluate_dumps_on_gpu(tmp_path):
     pk, lab, _ = codes_io.load_packed(str(tmp_path / "db.chpk"))
     m, _, _ = hashing.calculate_mAP(pk, lab, codes_io.PackedCodes.from_codes(q), ql, 100)
     assert abs(m - om) < 1e-9
+    pg = hashing.pack_codes(d.cuda())                                # the kernel writes the same bits
+    assert torch.equal(pg.bits.cpu(), pk.bits) and pg.nbit == pk.nbit
     ids, dist = hashing.retrieve_topk(codes_io.PackedCodes.from_codes(q), pk.to("cuda"), 50)
     oids, odist = mo.topk_ids(q, d, 50)
     assert torch.equal(ids.cpu(), oids) and torch.equal(dist.cpu(), odist)

@@ -13,8 +13,9 @@ from concepthash_b200.hashing import (  # noqa: F401
     calculate_pr_curve,
     get_hamm_dist,
     map_at_r,
+    pack_codes,
     retrieve_topk,
 )
 
 __all__ = ["calculate_mAP", "calculate_pr_curve", "get_hamm_dist", "map_at_r", "retrieve_topk",
-           "PackedCodes", "evaluate_dumps", "load_packed", "save_packed"]
+           "PackedCodes", "evaluate_dumps", "load_packed", "save_packed", "pack_codes"]
