@@ -43,7 +43,7 @@ class SelectArgs(C.Structure):
 class CandArgs(C.Structure):
     _fields_ = [(n, P) for n in ("cand_off", "cand_cnt", "cand_rows", "cand_key", "q_bits", "g_bits", "g_plane", "q_lab",
                                  "g_lab",
-                                 "tot_all", "tot_rel", "base0_all", "base0_rel", "first_rel", "first_rel_out", "cols",
+                                 "tot_all", "tot_rel", "base0_all", "base0_rel", "first_rel", "first_rel_out", "key_max", "cols",
                                  "ids", "keys", "err_flag")] + \
                [(n, C.c_int64) for n in ("nq", "nq_pad", "R", "row_offset")] + \
                [(n, C.c_int32) for n in ("nstripes", "nbins", "nbit", "label_mode", "mask_words", "remove_first",

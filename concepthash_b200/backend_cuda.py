@@ -256,13 +256,14 @@ class CudaBackend:
 
     def cand_finalize(self, cand, *, mode, base0_all, base0_rel, nq, nq_pad, nstripes, nbins, remove_first=False,
                       first_rel=None, first_rel_out=None, cols=None, r_eff=(), pr_k=(), ids=None, keys=None, R=0,
-                      row_offset=0):
+                      row_offset=0, key_max=None):
         r_eff, pr_k = list(r_eff), list(pr_k)
         if len(r_eff) > L.CH_MAX_R or len(pr_k) > L.CH_MAX_PR:
             raise ValueError(f"at most {L.CH_MAX_R} R values and {L.CH_MAX_PR} PRs cut-offs are supported")
         a = self._cand_args(cand, nq, nq_pad, nstripes, nbins, mode=mode, base0_all=base0_all, base0_rel=base0_rel,
                             remove_first=int(bool(remove_first)), first_rel=first_rel, first_rel_out=first_rel_out,
-                            cols=cols, ids=ids, keys=keys, R=int(R), row_offset=int(row_offset), nR=len(r_eff),
+                            cols=cols, ids=ids, keys=keys, R=int(R), row_offset=int(row_offset), key_max=key_max,
+                            nR=len(r_eff),
                             nPR=len(pr_k))
         for i, v in enumerate(r_eff):
             a.r_eff[i] = int(v)

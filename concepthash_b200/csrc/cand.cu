@@ -25,6 +25,7 @@ struct CandDev {
   uint32_t* tot_all; uint32_t* tot_rel;
   const uint32_t* base0_all; const uint32_t* base0_rel;
   const uint32_t* first_rel; uint32_t* first_rel_out;
+  const uint32_t* key_max;   // (nq_pad) or NULL: candidates with a larger key cannot rank below rmax
   double* cols; long long* ids; int* keys;
   uint32_t* err_flag;
   long long nq, nq_pad, R, row_offset;
@@ -191,6 +192,57 @@ __global__ void __launch_bounds__(kCandWarps * 32) cand_final_kernel(const CandD
   const long long shift = a.remove_first ? 1 : 0;
   const long long frel = (a.remove_first && a.first_rel != nullptr) ? a.first_rel[q] : 0;
   const uint32_t lt = lanemask_lt();
+  // Only candidates with key <= kmax[q] (the smallest key at which the list holds rmax items) can rank below rmax:
+  // the others are dropped while the list is read, the survivors are compacted (in order) through a small
+  // shared-memory queue and ranked 32 at a time.
+  const uint32_t kmax = a.key_max != nullptr ? a.key_max[q] : 0xfffffffeu;
+  uint32_t* qrow = sh + static_cast<size_t>(kCandWarps) * 2 * a.nbins + static_cast<size_t>(wip) * 128;
+  uint32_t* qkey = qrow + 64;
+  uint32_t queued = 0;                                            // warp-uniform
+  // ranks the candidates held by the lanes (key == 0xffffffff: none) -- one step of the in-order walk
+  auto step = [&](uint32_t rowv, uint32_t key) {
+    const bool valid = key != 0xffffffffu;
+    const bool rel = valid && (rowv >> 31) != 0u;
+    const uint32_t peers = __match_any_sync(0xffffffffu, key);
+    const uint32_t relm = __ballot_sync(0xffffffffu, rel);
+    long long rank = 0, relrank = 0;
+    if (valid) {
+      rank = static_cast<long long>(run_all[key]) + __popc(peers & lt);
+      relrank = static_cast<long long>(run_rel[key]) + __popc(peers & relm & lt);
+    }
+    __syncwarp();
+    if (valid && (peers >> lane) == 1u) {         // highest lane of the group publishes the new running counts
+      run_all[key] += __popc(peers);
+      run_rel[key] += __popc(peers & relm);
+    }
+    __syncwarp();
+    if (!valid) return;
+    if (a.mode == 1) {
+      if (rank == 0 && rel) a.first_rel_out[q] = 1u;
+      return;
+    }
+    if (a.remove_first) {
+      if (rank == 0) return;                      // the dropped self-retrieval
+      rank -= shift;
+      relrank -= frel;
+    }
+    if (a.mode == 2) {
+      if (rank < a.R) {
+        a.ids[q * a.R + rank] = a.row_offset + static_cast<long long>(rowv & 0x7fffffffu);
+        if (a.keys != nullptr) a.keys[q * a.R + rank] = static_cast<int>(key);
+      }
+      return;
+    }
+    if (!rel) return;
+    const double prec = static_cast<double>(relrank + 1) * fast_rcp(static_cast<double>(rank + 1));
+    for (int j = 0; j < a.nR; ++j)
+      if (rank < a.r_eff[j]) {
+        acc[2 * j] += prec;
+        acc[2 * j + 1] += 1.0;
+      }
+    for (int j = 0; j < a.nPR; ++j)
+      if (rank < a.pr_k[j]) acc[2 * a.nR + j] += 1.0;
+  };
   __syncwarp();
   for (int s = 0; s < a.nstripes; ++s) {
     const size_t sq = static_cast<size_t>(s) * a.nq_pad + q;
@@ -201,51 +253,37 @@ __global__ void __launch_bounds__(kCandWarps * 32) cand_final_kernel(const CandD
       if (i < n) {
         rowv = a.cand_rows[off + i];
         key = a.cand_key[off + i];
-        if (key >= static_cast<uint32_t>(a.nbins)) key = 0xffffffffu;     // flagged by ch_cand_hist
       }
-      const bool valid = key != 0xffffffffu;
-      const bool rel = valid && (rowv >> 31) != 0u;
-      const uint32_t peers = __match_any_sync(0xffffffffu, key);
-      const uint32_t relm = __ballot_sync(0xffffffffu, rel);
-      long long rank = 0, relrank = 0;
-      if (valid) {
-        rank = static_cast<long long>(run_all[key]) + __popc(peers & lt);
-        relrank = static_cast<long long>(run_rel[key]) + __popc(peers & relm & lt);
+      // keys >= nbins were flagged by ch_cand_hist; keys > kmax cannot rank below rmax
+      const bool keep = i < n && key < static_cast<uint32_t>(a.nbins) && key <= kmax;
+      const uint32_t km = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const uint32_t pos = queued + __popc(km & lt);
+        qrow[pos] = rowv;
+        qkey[pos] = key;
       }
+      queued += __popc(km);
       __syncwarp();
-      if (valid && (peers >> lane) == 1u) {       // highest lane of the group publishes the new running counts
-        run_all[key] += __popc(peers);
-        run_rel[key] += __popc(peers & relm);
-      }
-      __syncwarp();
-      if (!valid) continue;
-      if (a.mode == 1) {
-        if (rank == 0 && rel) a.first_rel_out[q] = 1u;
-        continue;
-      }
-      if (a.remove_first) {
-        if (rank == 0) continue;                  // the dropped self-retrieval
-        rank -= shift;
-        relrank -= frel;
-      }
-      if (a.mode == 2) {
-        if (rank < a.R) {
-          a.ids[q * a.R + rank] = a.row_offset + static_cast<long long>(rowv & 0x7fffffffu);
-          if (a.keys != nullptr) a.keys[q * a.R + rank] = static_cast<int>(key);
+      if (queued >= 32u) {
+        const uint32_t r0 = qrow[lane], k0 = qkey[lane];
+        const uint32_t rest = queued - 32u;
+        uint32_t r1 = 0u, k1 = 0u;
+        if (lane < rest) {
+          r1 = qrow[32 + lane];
+          k1 = qkey[32 + lane];
         }
-        continue;
-      }
-      if (!rel) continue;
-      const double prec = static_cast<double>(relrank + 1) * fast_rcp(static_cast<double>(rank + 1));
-      for (int j = 0; j < a.nR; ++j)
-        if (rank < a.r_eff[j]) {
-          acc[2 * j] += prec;
-          acc[2 * j + 1] += 1.0;
+        __syncwarp();
+        if (lane < rest) {
+          qrow[lane] = r1;
+          qkey[lane] = k1;
         }
-      for (int j = 0; j < a.nPR; ++j)
-        if (rank < a.pr_k[j]) acc[2 * a.nR + j] += 1.0;
+        queued = rest;
+        __syncwarp();
+        step(r0, k0);
+      }
     }
   }
+  if (queued > 0u) step(lane < queued ? qrow[lane] : 0u, lane < queued ? qkey[lane] : 0xffffffffu);
   if (a.mode == 0) {
     for (int c = 0; c < ncols; ++c) {
       double v = acc[c];
@@ -306,6 +344,7 @@ int to_dev(const ch_cand_args* a, CandDev* d) {
   d->g_plane = a->label_mode == CH_LAB_ID ? a->g_plane : nullptr;
   d->tot_all = a->tot_all; d->tot_rel = a->tot_rel; d->base0_all = a->base0_all; d->base0_rel = a->base0_rel;
   d->first_rel = a->first_rel; d->first_rel_out = a->first_rel_out; d->cols = a->cols;
+  d->key_max = a->key_max;
   d->ids = reinterpret_cast<long long*>(a->ids); d->keys = a->keys; d->err_flag = a->err_flag;
   d->nq = a->nq; d->nq_pad = a->nq_pad; d->R = a->R; d->row_offset = a->row_offset;
   d->nstripes = a->nstripes; d->nbins = a->nbins; d->label_mode = a->label_mode; d->lw = a->mask_words;
@@ -392,7 +431,7 @@ extern "C" int ch_cand_finalize(ch_ws* ws, const ch_cand_args* a, void* stream) 
   if (a->mode < 0 || a->mode > 2) CH_FAIL("bad mode %d", a->mode);
   ChDeviceGuard guard(ws->device);
   const unsigned blocks = static_cast<unsigned>((a->nq + kCandWarps - 1) / kCandWarps);
-  const size_t smem = static_cast<size_t>(kCandWarps) * 2 * a->nbins * sizeof(uint32_t);
+  const size_t smem = static_cast<size_t>(kCandWarps) * (2 * a->nbins + 128) * sizeof(uint32_t);   // counters + queue
   cand_final_kernel<<<blocks, kCandWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(d);
   CH_LAUNCH_CHECK(ws);
   return 0;

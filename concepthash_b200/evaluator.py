@@ -325,7 +325,7 @@ class Evaluator:
             tot_all=tot[0], tot_rel=tot[1] if label_mode != L.CH_LAB_NONE else None, nq=c["nq"], nq_pad=nq_pad,
             nstripes=nstripes_all if nstripes is None else nstripes, nbins=nbins, nbit=q.nbit, stripe0=stripe0, **kw))
 
-    def _cand_bases(self, c, cand, nbins, need=None, tot=None):
+    def _cand_bases(self, c, cand, nbins, need=None, tot=None, rmax=None):
         """keys + label matches of the candidates -> per-rank key totals -> all-gather -> bases (+ verification
         that every query has >= ``need`` candidates: status[1]).  ``tot``: totals already accumulated per block."""
         b, comm = self.b, self.comm
@@ -338,11 +338,14 @@ class Evaluator:
         base0_all = b.empty((nbins, nq_pad), torch.int32)
         base0_rel = b.empty((nbins, nq_pad), torch.int32)
         found = b.zeros((nq_pad,), torch.int32)
-        b.scan_bases(tot[:, 0].contiguous(), comm.world, comm.rank, nbins, nq, nq_pad, -1, base0_all, None, found)
+        # key_max[q] = smallest key at which the (global) list holds rmax items: larger keys cannot rank below rmax
+        key_max = b.empty((nq_pad,), torch.int32) if rmax is not None else None
+        b.scan_bases(tot[:, 0].contiguous(), comm.world, comm.rank, nbins, nq, nq_pad, -1 if rmax is None else rmax,
+                     base0_all, key_max, found)
         b.scan_bases(tot[:, 1].contiguous(), comm.world, comm.rank, nbins, nq, nq_pad, -1, base0_rel, None, None)
         if need is not None:
             b.check_counts(found, nq, need, cand["status"][1:2])
-        return base0_all, base0_rel
+        return base0_all, base0_rel, key_max
 
     # ------------------------------------------------------------------ the evaluation
     def evaluate(self, db_codes, db_labels, q_codes, q_labels, R, threshold=0.0, PRs=(),
@@ -458,7 +461,7 @@ class Evaluator:
             # candidate lists (tensor-core select pass): ranks straight from the lists
             cand, nbins = st["cand"], st["nbins"]
             kw = dict(base0_all=st["base0_all"], base0_rel=st["base0_rel"], nq=nq, nq_pad=nq_pad, nstripes=nstripes,
-                      nbins=nbins, remove_first=bool(rf))
+                      nbins=nbins, remove_first=bool(rf), key_max=st.get("key_max"))
             first_rel = None
             if rf:
                 first_rel = b.zeros((nq_pad,), torch.int32)
@@ -560,8 +563,9 @@ class Evaluator:
             del slab_rel
             cand = self._alloc_cands(cap, geo, nq)
             self._select_tc(q, g, geo, thresh, cand, self._dense(1.3 * (c["rmax"] + c["rf"]), c["ndb_total"]))
-            base0_all, base0_rel = self._cand_bases(c, cand, nbins)
-            return dict(cand=cand, base0_all=base0_all, base0_rel=base0_rel, total_rel=total_rel, nbins=nbins)
+            base0_all, base0_rel, key_max = self._cand_bases(c, cand, nbins, rmax=c["rmax"] + c["rf"])
+            return dict(cand=cand, base0_all=base0_all, base0_rel=base0_rel, total_rel=total_rel, nbins=nbins,
+                        key_max=key_max)
         if label_mode == L.CH_LAB_ID and 0 < c["nclass"] * nstripes <= (1 << 26):
             b.record_caps(2, self._class_counts(c), q.ids, nstripes, c["nclass"], nq, nq_pad, True, cap)
         b.slab_exscan(slab_all, nstripes, nbins, nq_pad)
@@ -760,8 +764,8 @@ class Evaluator:
                 self.stats["select_dense"] = bool(dense)
             else:
                 self._select_tc(q, g, geo, thresh, cand, dense)
-            base0_all, base0_rel = self._cand_bases(c, cand, nbins, need, tot)
-            return dict(cand=cand, base0_all=base0_all, base0_rel=base0_rel, nbins=nbins,
+            base0_all, base0_rel, key_max = self._cand_bases(c, cand, nbins, need, tot, rmax=c["rmax"] + c["rf"])
+            return dict(cand=cand, base0_all=base0_all, base0_rel=base0_rel, nbins=nbins, key_max=key_max,
                         total_rel=self._total_rel_from_classes(c, cls))
         b.record_caps(2, cls, q.ids, nstripes, c["nclass"], nq, nq_pad, True, cap)
         rec, tmax = self._alloc_records(cap, geo, nq, thresh, status)   # one host sync: slots + max threshold
@@ -960,9 +964,10 @@ class Evaluator:
             cand = self._alloc_cands(cap, geo, nq)
             self._select_tc(q, g, geo, thresh, cand, self._dense(1.3 * (R + rf), ndb_total))
             c = dict(q=q, g=g, geo=geo, nq=nq, label_mode=L.CH_LAB_NONE, lw=0)
-            base0_c, _ = self._cand_bases(c, cand, nbins)
+            base0_c, _, key_max = self._cand_bases(c, cand, nbins, rmax=R + rf)
             b.cand_finalize(cand, mode=2, base0_all=base0_c, base0_rel=None, nq=nq, nq_pad=nq_pad, nstripes=nstripes,
-                            nbins=nbins, remove_first=bool(rf), ids=ids, keys=keys, R=R, row_offset=row_offset)
+                            nbins=nbins, remove_first=bool(rf), ids=ids, keys=keys, R=R, row_offset=row_offset,
+                            key_max=key_max)
             if int(cand["err"].cpu()[0]) != 0:
                 raise RuntimeError("internal error: candidate list overflow")
             if comm.world > 1:

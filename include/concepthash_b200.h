@@ -205,6 +205,8 @@ typedef struct ch_cand_args {
   uint32_t* tot_all;         uint32_t* tot_rel;           /* (nbins, nq_pad) out of ch_cand_hist */
   const uint32_t* base0_all; const uint32_t* base0_rel;   /* (nbins, nq_pad) in of ch_cand_finalize */
   const uint32_t* first_rel; uint32_t* first_rel_out;     /* (nq_pad) */
+  const uint32_t* key_max;   /* (nq_pad) or NULL (ch_cand_finalize): thresh output of ch_scan_bases for rmax = the
+                                longest list asked for -- candidates with a larger key are skipped */
   double*  cols;             /* (nq, ncols) */
   int64_t* ids;  int32_t* keys;   /* (nq, R) */
   uint32_t* err_flag;

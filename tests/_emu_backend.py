@@ -262,7 +262,7 @@ class EmuBackend:
 
     def cand_finalize(self, cand, *, mode, base0_all, base0_rel, nq, nq_pad, nstripes, nbins, remove_first=False,
                       first_rel=None, first_rel_out=None, cols=None, r_eff=(), pr_k=(), ids=None, keys=None, R=0,
-                      row_offset=0):
+                      row_offset=0, key_max=None):
         self.launches += 1
         off, cnt, rows, key = _u32(cand["off"]), _u32(cand["cnt"]), _u32(cand["rows"]), cand["key"].numpy()
         ba = _u32(base0_all)
@@ -277,8 +277,8 @@ class EmuBackend:
                 o = int(off[s, q])
                 for i in range(int(cnt[s, q])):
                     k = int(key[o + i])
-                    if k >= nbins:
-                        continue
+                    if k >= nbins or (key_max is not None and k > int(_u32(key_max)[q])):
+                        continue                      # flagged / cannot rank below rmax
                     rel = bool(rows[o + i] >> 31)
                     row = int(rows[o + i] & 0x7FFFFFFF)
                     rank, relrank = run_all[k], run_rel[k]
