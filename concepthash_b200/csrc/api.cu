@@ -1,5 +1,8 @@
 // Workspace, error reporting and device queries of the C-ABI (include/concepthash_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
+
+#include <thread>
 
 #include "common.cuh"
 
@@ -59,8 +62,17 @@ extern "C" int ch_workspace_create(int device, ch_ws** out) {
   cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
   ws->clock_khz = khz;
   ws->stage_bytes = static_cast<size_t>(64) << 20;
+  {
+    unsigned hc = std::thread::hardware_concurrency();
+    ws->host_threads = hc >= 16 ? 8 : (hc >= 4 ? static_cast<int>(hc / 2) : 1);
+    if (const char* e = getenv("CH_HOST_THREADS")) {          // tuning knob for the pageable-source copies
+      const int v = atoi(e);
+      if (v >= 1 && v <= 64) ws->host_threads = v;
+    }
+  }
   for (int i = 0; i < 2; ++i) {
     ws->stage[i] = nullptr;
+    ws->bounce[i] = nullptr;
     CH_CUDA(cudaEventCreateWithFlags(&ws->ev_copied[i], cudaEventDisableTiming));
     CH_CUDA(cudaEventCreateWithFlags(&ws->ev_consumed[i], cudaEventDisableTiming));
   }
@@ -76,6 +88,12 @@ int ch_ws_ensure_stage(ch_ws* ws) {
   return 0;
 }
 
+int ch_ws_ensure_bounce(ch_ws* ws) {
+  for (int i = 0; i < 2; ++i)
+    if (ws->bounce[i] == nullptr) CH_CUDA(cudaHostAlloc(&ws->bounce[i], ws->stage_bytes, cudaHostAllocDefault));
+  return 0;
+}
+
 extern "C" int ch_workspace_destroy(ch_ws* ws) {
   if (ws == nullptr) return 0;
   ch_ws_priv* p = reinterpret_cast<ch_ws_priv*>(ws);
@@ -83,6 +101,7 @@ extern "C" int ch_workspace_destroy(ch_ws* ws) {
   cudaDeviceSynchronize();
   for (int i = 0; i < 2; ++i) {
     if (ws->stage[i]) cudaFree(ws->stage[i]);
+    if (ws->bounce[i]) cudaFreeHost(ws->bounce[i]);
     cudaEventDestroy(ws->ev_copied[i]);
     cudaEventDestroy(ws->ev_consumed[i]);
   }

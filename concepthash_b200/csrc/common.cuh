@@ -19,6 +19,10 @@ struct ch_ws {
   cudaStream_t copy_stream;
   cudaEvent_t ev_copied[2];
   cudaEvent_t ev_consumed[2];
+  // pageable host sources: pinned bounce buffers filled by a few host threads (the driver's own pageable path
+  // copies single-threaded, ~9 GB/s)
+  void* bounce[2];
+  int host_threads;
   int64_t launches;
 };
 

@@ -9,9 +9,13 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <thread>
+#include <vector>
+
 #include "common.cuh"
 
-int ch_ws_ensure_stage(ch_ws* ws);  // api.cu
+int ch_ws_ensure_stage(ch_ws* ws);   // api.cu
+int ch_ws_ensure_bounce(ch_ws* ws);  // api.cu
 
 namespace {
 
@@ -329,6 +333,18 @@ int pack_from_host(ch_ws* ws, const void* src, int dtype, int64_t n, int ncols, 
   if (chunk_rows < 64) CH_FAIL("row of %zu bytes does not fit the staging buffer", dense_bytes);
   if (n == 0)
     return launch_pack(ws, nullptr, dtype, 0, rows_pad, 0, ncols, ncols, 1, thr, words, out_pos, out_nz, flags, st, sub);
+  // pageable source?  (cudaMemcpyAsync from pageable memory is staged by the driver on one thread, ~9 GB/s: copy
+  // into pinned bounce buffers with a few host threads instead and DMA from there -- the memcpy of chunk c + 1
+  // overlaps the DMA of chunk c)
+  bool pageable = true;
+  {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, src) == cudaSuccess)
+      pageable = attr.type == cudaMemoryTypeUnregistered;
+    else
+      cudaGetLastError();   // older drivers report unregistered host pointers as an error
+  }
+  if (pageable && ch_ws_ensure_bounce(ws)) return 1;
   int c = 0;
   for (int64_t r0 = 0; r0 < n; r0 += chunk_rows, ++c) {
     const int b = c & 1;
@@ -337,12 +353,37 @@ int pack_from_host(ch_ws* ws, const void* src, int dtype, int64_t n, int ncols, 
     // the staging buffer may still be read by the pack kernel of chunk c - 2 (or of an earlier call)
     CH_CUDA(cudaStreamWaitEvent(ws->copy_stream, ws->ev_consumed[b], 0));
     const char* src_rows = static_cast<const char*>(src) + static_cast<size_t>(r0) * row_bytes;
-    if (rs == ncols)
-      CH_CUDA(cudaMemcpyAsync(ws->stage[b], src_rows, static_cast<size_t>(r1 - r0) * dense_bytes,
-                              cudaMemcpyHostToDevice, ws->copy_stream));
-    else
-      CH_CUDA(cudaMemcpy2DAsync(ws->stage[b], dense_bytes, src_rows, row_bytes, dense_bytes,
-                                static_cast<size_t>(r1 - r0), cudaMemcpyHostToDevice, ws->copy_stream));
+    const size_t rows_c = static_cast<size_t>(r1 - r0);
+    if (pageable) {
+      // the bounce buffer is free once the DMA of chunk c - 2 has been issued AND completed
+      CH_CUDA(cudaEventSynchronize(ws->ev_copied[b]));
+      char* dst = static_cast<char*>(ws->bounce[b]);
+      int nt = ws->host_threads;
+      if (rows_c * dense_bytes < (static_cast<size_t>(4) << 20)) nt = 1;
+      auto work = [=](int t) {
+        const size_t ra = rows_c * t / nt, rb = rows_c * (t + 1) / nt;
+        if (rs == ncols) {
+          memcpy(dst + ra * dense_bytes, src_rows + ra * dense_bytes, (rb - ra) * dense_bytes);
+        } else {
+          for (size_t r = ra; r < rb; ++r) memcpy(dst + r * dense_bytes, src_rows + r * row_bytes, dense_bytes);
+        }
+      };
+      if (nt == 1) {
+        work(0);
+      } else {
+        std::vector<std::thread> pool;
+        pool.reserve(nt - 1);
+        for (int t = 1; t < nt; ++t) pool.emplace_back(work, t);
+        work(0);
+        for (auto& th : pool) th.join();
+      }
+      CH_CUDA(cudaMemcpyAsync(ws->stage[b], dst, rows_c * dense_bytes, cudaMemcpyHostToDevice, ws->copy_stream));
+    } else if (rs == ncols) {
+      CH_CUDA(cudaMemcpyAsync(ws->stage[b], src_rows, rows_c * dense_bytes, cudaMemcpyHostToDevice, ws->copy_stream));
+    } else {
+      CH_CUDA(cudaMemcpy2DAsync(ws->stage[b], dense_bytes, src_rows, row_bytes, dense_bytes, rows_c,
+                                cudaMemcpyHostToDevice, ws->copy_stream));
+    }
     CH_CUDA(cudaEventRecord(ws->ev_copied[b], ws->copy_stream));
     CH_CUDA(cudaStreamWaitEvent(st, ws->ev_copied[b], 0));
     if (launch_pack(ws, ws->stage[b], dtype, r0, last ? rows_pad : r1, n, ncols, ncols, 1, thr, words, out_pos, out_nz,
@@ -350,8 +391,9 @@ int pack_from_host(ch_ws* ws, const void* src, int dtype, int64_t n, int ncols, 
       return 1;
     CH_CUDA(cudaEventRecord(ws->ev_consumed[b], st));
   }
-  // the caller may free / reuse the host buffer after return
-  CH_CUDA(cudaStreamSynchronize(ws->copy_stream));
+  // the caller may free / reuse the host buffer after return: a pageable source has been copied out by the host
+  // threads already (its last DMA may still be in flight -- the next call's host copy overlaps it)
+  if (!pageable) CH_CUDA(cudaStreamSynchronize(ws->copy_stream));
   return 0;
 }
 

@@ -11,7 +11,9 @@ from concepthash_b200 import hashing  # noqa: E402
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg5s"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 w, d, dl, q, ql = bench.make_workload(name, "cuda")
-hd, hdl, hq, hql = (t.cpu().pin_memory() for t in (d, dl, q, ql))
+import os
+PIN = os.environ.get("PIN", "1") == "1"
+hd, hdl, hq, hql = ((t.cpu().pin_memory() if PIN else t.cpu()) for t in (d, dl, q, ql))
 del d, dl, q, ql
 ev = hashing.get_evaluator()
 for i in range(steps):
