@@ -339,7 +339,13 @@ def main():
         for kind, units, a, b in ev_e:
             kinds_e[kind] = kinds_e.get(kind, 0.0) + a.elapsed_time(b) / max(2, args.steps // 2)
         h2d = sum(t.numel() * t.element_size() for t in (hd, hdl, hq, hql))
+        # the same call with ordinary (pageable) CPU tensors -- what the reference's trainers hand over
+        pd, pdl, pq, pql = (t.cpu() for t in (d, dl, q, ql))
+        step_page = lambda: hashing.calculate_mAP(pd, pdl, pq, pql, w["R"], group=group)
+        ms_p, _, _, _, _ = run(step_page, 2, 1)
+        del pd, pdl, pq, pql
         e2e = {"value": total_pairs * unit64 / (ms_e * 1e-3), "unit": "64-bit comparisons/s",
+               "ms_per_step_pageable_host_tensors": ms_p,
                "ms_per_step": ms_e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 * len(r_list) + 64,
                "mAP": out_e[0], "mode": ev.stats.get("mode"), "kernel_ms_per_step": kinds_e}
 
