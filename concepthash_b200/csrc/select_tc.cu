@@ -12,8 +12,8 @@
 // whole 128-column accumulator fits in 64 registers and is handed back to the tensor core immediately.  Per 32
 // columns, 8 PRMT in sign-replicate mode turn the 32 sign bits into 32 sign BYTES and 8 LOP3 fold them into one
 // 32-bit mask -- in the "sparse" variant only after an 8-instruction AND tree said that the chunk holds a
-// candidate at all.  The gallery plane stores every 32-row block in the row order that makes bit t of that mask
-// the sign of row t (kRowOfColumn).  The shard-local row index of every candidate is appended to the
+// candidate at all.  The gallery plane stores every 32-row block in the row order that makes bit 31 - t of that
+// mask the sign of row t (kRowOfColumn), so a leading-zero count walks the candidates in row order.  The shard-local row index of every candidate is appended to the
 // (stripe, query) slice of the candidate list, in ascending row order (thread = TMEM lane = query; tiles, chunks
 // and bits are visited in row order).  Nothing else happens here: keys, label matches, stable ranks and AP are
 // the business of cand.cu, which only ever sees the candidates (~0.01-0.3 % of the pairs).
