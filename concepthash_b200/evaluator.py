@@ -726,7 +726,8 @@ class Evaluator:
         # issued right after the first sample kernels have been queued
         first_load = streamer.load_first if streamer is not None else (lambda: None)
         if (tc_pass and self.sample_two_level and not ternary and min(ns_ranks) >= self.sample2_min_rows and
-                float(nq) * min(ns_ranks) * int(q.bits.shape[1]) >= self.sample2_min_work):
+                float(nq) * min(ns_ranks) * int(q.bits.shape[1]) >=
+                self.sample2_min_work * (1.0 if comm.world > 1 else 0.2)):   # one GPU: no extra collective to pay
             thresh, cap = self._sample_thresholds_tc(c, sp, ns_ranks, m, status, first_load)
         else:
             slab_s = b.zeros((nstripes, nbins, nq_pad), torch.int32)
