@@ -15,20 +15,33 @@ __global__ void scan_bases_kernel(const uint32_t* __restrict__ tot_all, int worl
   unsigned long long cum = 0;
   uint32_t t = static_cast<uint32_t>(nbins - 1);
   bool found = false;
-  for (int key = 0; key < nbins; ++key) {
-    unsigned long long lower = 0, tot = 0;
-    if (q < nq) {
-      for (int g = 0; g < world; ++g) {
-        const uint32_t v = tot_all[(static_cast<size_t>(g) * nbins + key) * nq_pad + q];
-        if (g < rank) lower += v;
-        tot += v;
+  // keys in batches of 8: the loads of a batch are independent (the walk itself is a dependent chain, and one
+  // global-memory latency per key made this kernel latency-bound)
+  constexpr int B = 8;
+  for (int key0 = 0; key0 < nbins; key0 += B) {
+    unsigned long long lower[B], tot[B];
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+      lower[j] = tot[j] = 0;
+      const int key = key0 + j;
+      if (q < nq && key < nbins) {
+        for (int g = 0; g < world; ++g) {
+          const uint32_t v = __ldg(tot_all + (static_cast<size_t>(g) * nbins + key) * nq_pad + q);
+          if (g < rank) lower[j] += v;
+          tot[j] += v;
+        }
       }
     }
-    base0[static_cast<size_t>(key) * nq_pad + q] = static_cast<uint32_t>(cum + lower);
-    cum += tot;
-    if (!found && rmax >= 0 && cum >= static_cast<unsigned long long>(rmax)) {
-      t = static_cast<uint32_t>(key);
-      found = true;
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+      const int key = key0 + j;
+      if (key >= nbins) break;
+      base0[static_cast<size_t>(key) * nq_pad + q] = static_cast<uint32_t>(cum + lower[j]);
+      cum += tot[j];
+      if (!found && rmax >= 0 && cum >= static_cast<unsigned long long>(rmax)) {
+        t = static_cast<uint32_t>(key);
+        found = true;
+      }
     }
   }
   if (thresh != nullptr) thresh[q] = t;
