@@ -474,3 +474,22 @@ def test_tensor_core_path_tiny_shapes(H):
         ids, dist = H.retrieve_topk(q.cuda(), d.cuda(), min(R, 40))
         oids, odist = mo.topk_ids(q, d, min(R, 40))
         assert torch.equal(ids.cpu(), oids) and torch.equal(dist.cpu(), odist)
+
+
+# ------------------------------------------------------------------ calculate_pr_curve
+def test_pr_curve_matches_oracle(H):
+    """second symbol imported at experiments/test_hashing.py:15 (used at :152-168): recall / precision at the
+    default power-of-two cut-offs (more than CH_MAX_PR of them: several passes) and at explicit ones, with and
+    without remove_first_retrieved, device and host inputs."""
+    d, dl, q, ql, ncls = synth.make_random_case(150, 9000, 48, 12, p=0.3, seed=21)
+    for rf in (False, True):
+        qq, qql = (d[:150].clone(), dl[:150].clone()) if rf else (q, ql)
+        orec, oprec, ors = mo.calculate_pr_curve(d, dl, qq, qql, remove_first_retrieved=rf)
+        for dev in ("cuda", "cpu"):
+            rec, prec, rs = H.calculate_pr_curve(d.to(dev), dl.to(dev), qq.to(dev), qql.to(dev),
+                                                 remove_first_retrieved=rf)
+            assert rs == ors and np.allclose(rec, orec, atol=TOL) and np.allclose(prec, oprec, atol=TOL)
+    cuts = list(range(1, 80, 2))                                  # 40 cut-offs -> two passes of <= 32
+    orec, oprec, _ = mo.calculate_pr_curve(d, dl, q, ql, Rs=cuts)
+    rec, prec, rs = H.calculate_pr_curve(d.cuda(), dl.cuda(), q.cuda(), ql.cuda(), Rs=cuts)
+    assert rs == cuts and np.allclose(rec, orec, atol=TOL) and np.allclose(prec, oprec, atol=TOL)
