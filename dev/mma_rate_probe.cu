@@ -1,0 +1,142 @@
+// Development probe: back-to-back tcgen05.mma kind::i8 throughput (clocks per instruction) for M=128 and
+// N=128 / N=256 with operands resident in shared memory (no-swizzle K-major core-matrix layout, K = 160 bytes),
+// one CTA per SM on every SM.  Answers: is the M=N=128 instruction limited by its operand fetch?
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -o mma_rate_probe mma_rate_probe.cu && ./mma_rate_probe
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d: %s\n", #x, __LINE__, cudaGetErrorString(e)); exit(1);} } while (0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t c) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(c) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile("{\n.reg .pred p;\nWAIT_LOOP:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra.uni WAIT_DONE;\nbra.uni WAIT_LOOP;\nWAIT_DONE:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ inline uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+constexpr int KB = 160;
+
+// N = MMA width; NACC accumulators used round-robin; KBLK k-blocks (32 bytes) per batch.
+template <int N, int NACC, int KBLK, int LDW>
+__global__ void __launch_bounds__(128 + 32 * LDW + 32) probe(int iters, long long* out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ volatile int stop_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (128 + 256) * KB / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x01ff01ffu;
+  if (tid == 0) {
+    stop_s = 0;
+    mbar_init(&bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+  if (tid == 0) {
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
+    const uint32_t sbo = 8 * KB, lbo = 128;
+    const uint32_t sA = smem_u32(smem), sB = smem_u32(smem + 128 * KB);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t acc_col = (uint32_t)(it % NACC) * N;
+#pragma unroll
+      for (int k = 0; k < KBLK; ++k) {
+        const uint64_t da = make_desc(sA + k * 256, lbo, sbo);
+        const uint64_t db = make_desc(sB + k * 256, lbo, sbo);
+        const uint32_t acc = k > 0 ? 1u : 0u;
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n}\n" ::"r"(tmem_base + acc_col),
+            "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+            : "memory");
+      }
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_mma)) : "memory");
+    mbar_wait(&bar_mma, 0);
+    const long long t1 = clock64();
+    out[blockIdx.x] = t1 - t0;
+    stop_s = 1;
+  } else if (warp >= 4 && warp < 4 + LDW) {
+    // LDW warps keep reading (packed, 64 columns per instruction) the LAST 128 columns of TMEM, which the MMAs
+    // of the NACC < 512 / N configurations never touch: does the read-out slow the MMA down?
+    uint32_t sink = 0;
+    long long n = 0;
+    while (stop_s == 0) {
+      uint32_t r[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 384 + (n & 1) * 64;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+            "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+            "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sink ^= r[j];
+      ++n;
+    }
+    if (sink == 0x12345u) out[0] = n;
+    if ((tid & 31) == 0 && warp == 4) out[148 + blockIdx.x] = n;
+  }
+  __syncthreads();
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+template <int N, int NACC, int KBLK, int LDW = 0>
+void run(const char* name) {
+  long long* d;
+  const int ctas = 148, iters = 2000;
+  CK(cudaMalloc(&d, 2 * ctas * 8));
+  CK(cudaMemset(d, 0, 2 * ctas * 8));
+  const int smem = 384 * KB;
+  CK(cudaFuncSetAttribute(probe<N, NACC, KBLK, LDW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  for (int rep = 0; rep < 2; ++rep) {
+    probe<N, NACC, KBLK, LDW><<<ctas, 128 + 32 * LDW + 32, smem>>>(iters, d);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+  }
+  std::vector<long long> h(2 * ctas);
+  CK(cudaMemcpy(h.data(), d, 2 * ctas * 8, cudaMemcpyDeviceToHost));
+  long long mx = 0, mn = 1LL << 60;
+  for (int i = 0; i < ctas; ++i) {
+    const long long v = h[i]; mx = v > mx ? v : mx; mn = v < mn ? v : mn; }
+  const double mmas = (double)iters * KBLK;
+  printf("%-34s clk/MMA min %.1f max %.1f   MAC/clk/SM %.0f (of 8192)\n", name, mn / mmas, mx / mmas,
+         128.0 * N * 32 * mmas / mx);
+  if (LDW > 0) printf("    with %d warps reading TMEM: %.1f clk per packed x32 load and warp\n", LDW, (double)mx / h[ctas]);
+  cudaFree(d);
+}
+
+int main() {
+  run<128, 4, 5>("N=128, 4 accumulators, 5 k-blocks");
+  run<128, 1, 5>("N=128, 1 accumulator, 5 k-blocks");
+  run<128, 4, 1>("N=128, 4 accumulators, 1 k-block");
+  run<256, 2, 5>("N=256, 2 accumulators, 5 k-blocks");
+  run<256, 1, 5>("N=256, 1 accumulator, 5 k-blocks");
+  run<64, 8, 5>("N=64, 8 accumulators, 5 k-blocks");
+  run<128, 3, 5, 4>("N=128, 3 acc + 4 warps LDTM");
+  run<128, 3, 5, 8>("N=128, 3 acc + 8 warps LDTM");
+  run<128, 3, 5, 16>("N=128, 3 acc + 16 warps LDTM");
+  return 0;
+}
