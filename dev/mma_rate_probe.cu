@@ -27,17 +27,21 @@ __device__ inline uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_
 constexpr int KB = 160;
 
 // N = MMA width; NACC accumulators used round-robin; KBLK k-blocks (32 bytes) per batch.
-template <int N, int NACC, int KBLK, int LDW>
-__global__ void __launch_bounds__(128 + 32 * LDW + 32) probe(int iters, long long* out) {
+template <int N, int NACC, int KBLK, int LDW, int TMA, int SPIN>
+__global__ void __launch_bounds__(128 + 32 * LDW + 32 + 32 * (1 + SPIN)) probe(int iters, long long* out, const unsigned char* gsrc) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar_mma;
   __shared__ uint32_t tmem_base_s;
   __shared__ volatile int stop_s;
+  __shared__ __align__(8) uint64_t bar_cp;
+  __shared__ unsigned int spin_word;
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < (128 + 256) * KB / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x01ff01ffu;
   if (tid == 0) {
     stop_s = 0;
+    spin_word = 1u;
     mbar_init(&bar_mma, 1);
+    mbar_init(&bar_cp, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -73,6 +77,32 @@ __global__ void __launch_bounds__(128 + 32 * LDW + 32) probe(int iters, long lon
     const long long t1 = clock64();
     out[blockIdx.x] = t1 - t0;
     stop_s = 1;
+  } else if (TMA && warp == 4 + LDW) {
+    // one thread streams 20 KB tiles from global (L2-resident) memory into a spare shared-memory region, back to
+    // back, like the gallery ring of the select kernel
+    if ((tid & 31) == 0) {
+      unsigned char* dst = smem + (128 + 256) * KB;
+      uint32_t ph = 0;
+      long long n = 0;
+      while (stop_s == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar_cp)), "r"(20480u) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(gsrc + (size_t)blockIdx.x * 20480 + (n & 7) * 20480 * 148), "r"(20480u), "r"(smem_u32(&bar_cp)) : "memory");
+        mbar_wait(&bar_cp, ph);
+        ph ^= 1u;
+        ++n;
+      }
+      out[296 + blockIdx.x] = n;
+    }
+  } else if (SPIN > 0 && warp > 4 + LDW && warp <= 4 + LDW + SPIN) {
+    // spinning threads: compare-and-swap on a shared word that never becomes free (the MMA lock / barrier polls)
+    if ((tid & 31) == 0) {
+      long long n = 0;
+      while (stop_s == 0) {
+        if (atomicCAS(&spin_word, 0u, 1u) == 0u) break;
+        ++n;
+      }
+      if (warp == 5 + LDW) out[444 + blockIdx.x] = n;
+    }
   } else if (warp >= 4 && warp < 4 + LDW) {
     // LDW warps keep reading (packed, 64 columns per instruction) the LAST 128 columns of TMEM, which the MMAs
     // of the NACC < 512 / N configurations never touch: does the read-out slow the MMA down?
@@ -103,21 +133,24 @@ __global__ void __launch_bounds__(128 + 32 * LDW + 32) probe(int iters, long lon
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
-template <int N, int NACC, int KBLK, int LDW = 0>
+template <int N, int NACC, int KBLK, int LDW = 0, int TMA = 0, int SPIN = 0>
 void run(const char* name) {
   long long* d;
   const int ctas = 148, iters = 2000;
-  CK(cudaMalloc(&d, 2 * ctas * 8));
-  CK(cudaMemset(d, 0, 2 * ctas * 8));
-  const int smem = 384 * KB;
-  CK(cudaFuncSetAttribute(probe<N, NACC, KBLK, LDW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaMalloc(&d, 4 * ctas * 8));
+  CK(cudaMemset(d, 0, 4 * ctas * 8));
+  unsigned char* gsrc;
+  CK(cudaMalloc(&gsrc, (size_t)20480 * 148 * 8));
+  CK(cudaMemset(gsrc, 1, (size_t)20480 * 148 * 8));
+  const int smem = 384 * KB + 20480;
+  CK(cudaFuncSetAttribute(probe<N, NACC, KBLK, LDW, TMA, SPIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   for (int rep = 0; rep < 2; ++rep) {
-    probe<N, NACC, KBLK, LDW><<<ctas, 128 + 32 * LDW + 32, smem>>>(iters, d);
+    probe<N, NACC, KBLK, LDW, TMA, SPIN><<<ctas, 128 + 32 * LDW + 32 + 32 * (1 + SPIN), smem>>>(iters, d, gsrc);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
   }
-  std::vector<long long> h(2 * ctas);
-  CK(cudaMemcpy(h.data(), d, 2 * ctas * 8, cudaMemcpyDeviceToHost));
+  std::vector<long long> h(4 * ctas);
+  CK(cudaMemcpy(h.data(), d, 4 * ctas * 8, cudaMemcpyDeviceToHost));
   long long mx = 0, mn = 1LL << 60;
   for (int i = 0; i < ctas; ++i) {
     const long long v = h[i]; mx = v > mx ? v : mx; mn = v < mn ? v : mn; }
@@ -125,7 +158,10 @@ void run(const char* name) {
   printf("%-34s clk/MMA min %.1f max %.1f   MAC/clk/SM %.0f (of 8192)\n", name, mn / mmas, mx / mmas,
          128.0 * N * 32 * mmas / mx);
   if (LDW > 0) printf("    with %d warps reading TMEM: %.1f clk per packed x32 load and warp\n", LDW, (double)mx / h[ctas]);
+  if (TMA) printf("    with a bulk-copy stream: %.0f clk per 20 KB tile (%.1f B/clk/SM)\n", (double)mx / h[2 * ctas], 20480.0 * h[2 * ctas] / mx);
+  if (SPIN) printf("    with %d spinning threads: %.0f clk per CAS\n", SPIN, (double)mx / h[3 * ctas]);
   cudaFree(d);
+  cudaFree(gsrc);
 }
 
 int main() {
@@ -138,5 +174,12 @@ int main() {
   run<128, 3, 5, 4>("N=128, 3 acc + 4 warps LDTM");
   run<128, 3, 5, 8>("N=128, 3 acc + 8 warps LDTM");
   run<128, 3, 5, 16>("N=128, 3 acc + 16 warps LDTM");
+  run<128, 4, 5, 0, 1, 0>("N=128 + bulk-copy stream");
+  run<256, 2, 5, 0, 1, 0>("N=256 + bulk-copy stream");
+  run<128, 4, 5, 0, 0, 3>("N=128 + 3 CAS spinners");
+  run<256, 2, 5, 0, 0, 3>("N=256 + 3 CAS spinners");
+  run<128, 4, 5, 0, 1, 3>("N=128 + bulk copies + spinners");
+  run<256, 2, 5, 0, 1, 3>("N=256 + bulk copies + spinners");
+  run<128, 3, 5, 16, 1, 3>("N=128 + LDTM x16 + copies + spin");
   return 0;
 }
