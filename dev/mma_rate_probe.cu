@@ -58,8 +58,12 @@ __global__ void __launch_bounds__(128 + 32 * LDW + 32 + 32 * (1 + SPIN)) probe(i
     const uint32_t sbo = 8 * KB, lbo = 128;
     const uint32_t sA = smem_u32(smem), sB = smem_u32(smem + 128 * KB);
     const long long t0 = clock64();
-    for (int it = 0; it < iters; ++it) {
-      const uint32_t acc_col = (uint32_t)(it % NACC) * N;
+    if (NACC == 0) {                       // idle baseline: no MMA at all, just let the other threads run
+      while (clock64() - t0 < 1000000) {
+      }
+    }
+    for (int it = 0; it < (NACC == 0 ? 0 : iters); ++it) {
+      const uint32_t acc_col = (uint32_t)(it % (NACC == 0 ? 1 : NACC)) * N;
 #pragma unroll
       for (int k = 0; k < KBLK; ++k) {
         const uint64_t da = make_desc(sA + k * 256, lbo, sbo);
@@ -181,5 +185,11 @@ int main() {
   run<128, 4, 5, 0, 1, 3>("N=128 + bulk copies + spinners");
   run<256, 2, 5, 0, 1, 3>("N=256 + bulk copies + spinners");
   run<128, 3, 5, 16, 1, 3>("N=128 + LDTM x16 + copies + spin");
+  run<128, 0, 5, 0, 1, 1>("IDLE tensor pipe: copies + 1 spinner");
+  run<128, 0, 5, 0, 1, 3>("IDLE tensor pipe: copies + 3 spinners");
+  run<128, 0, 5, 16, 0, 0>("IDLE tensor pipe: LDTM x16");
+  run<128, 4, 5, 0, 1, 1>("N=128 + copies + 1 spinner");
+  run<256, 2, 5, 0, 1, 1>("N=256 + copies + 1 spinner");
+  run<128, 3, 5, 16, 1, 1>("N=128 + LDTM x16 + copies + 1 spinner");
   return 0;
 }
