@@ -28,9 +28,10 @@ constexpr int KB = 160;
 
 // N = MMA width; NACC accumulators used round-robin; KBLK k-blocks (32 bytes) per batch.
 template <int N, int NACC, int KBLK, int LDW, int TMA, int SPIN>
-__global__ void __launch_bounds__(128 + 32 * LDW + 32 + 32 * (1 + SPIN)) probe(int iters, long long* out, const unsigned char* gsrc) {
+__global__ void __launch_bounds__(128 + 32 * LDW + 32 + 32 * (1 + SPIN)) probe(int iters, long long* out, const unsigned char* gsrc, int commit_every) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar_mma;
+  __shared__ __align__(8) uint64_t bar_batch[4];
   __shared__ uint32_t tmem_base_s;
   __shared__ volatile int stop_s;
   __shared__ __align__(8) uint64_t bar_cp;
@@ -42,6 +43,7 @@ __global__ void __launch_bounds__(128 + 32 * LDW + 32 + 32 * (1 + SPIN)) probe(i
     spin_word = 1u;
     mbar_init(&bar_mma, 1);
     mbar_init(&bar_cp, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_batch[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -75,6 +77,8 @@ __global__ void __launch_bounds__(128 + 32 * LDW + 32 + 32 * (1 + SPIN)) probe(i
             "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
             : "memory");
       }
+      // a commit after every batch (nobody waits on these barriers): does the commit itself cost tensor time?
+      if (commit_every) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_batch[it & 3])) : "memory");
     }
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar_mma)) : "memory");
     mbar_wait(&bar_mma, 0);
@@ -138,7 +142,7 @@ __global__ void __launch_bounds__(128 + 32 * LDW + 32 + 32 * (1 + SPIN)) probe(i
 }
 
 template <int N, int NACC, int KBLK, int LDW = 0, int TMA = 0, int SPIN = 0>
-void run(const char* name) {
+void run(const char* name, int commit_every = 0) {
   long long* d;
   const int ctas = 148, iters = 2000;
   CK(cudaMalloc(&d, 4 * ctas * 8));
@@ -149,7 +153,7 @@ void run(const char* name) {
   const int smem = 384 * KB + 20480;
   CK(cudaFuncSetAttribute(probe<N, NACC, KBLK, LDW, TMA, SPIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   for (int rep = 0; rep < 2; ++rep) {
-    probe<N, NACC, KBLK, LDW, TMA, SPIN><<<ctas, 128 + 32 * LDW + 32 + 32 * (1 + SPIN), smem>>>(iters, d, gsrc);
+    probe<N, NACC, KBLK, LDW, TMA, SPIN><<<ctas, 128 + 32 * LDW + 32 + 32 * (1 + SPIN), smem>>>(iters, d, gsrc, commit_every);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
   }
@@ -169,27 +173,11 @@ void run(const char* name) {
 }
 
 int main() {
-  run<128, 4, 5>("N=128, 4 accumulators, 5 k-blocks");
-  run<128, 1, 5>("N=128, 1 accumulator, 5 k-blocks");
-  run<128, 4, 1>("N=128, 4 accumulators, 1 k-block");
-  run<256, 2, 5>("N=256, 2 accumulators, 5 k-blocks");
-  run<256, 1, 5>("N=256, 1 accumulator, 5 k-blocks");
-  run<64, 8, 5>("N=64, 8 accumulators, 5 k-blocks");
-  run<128, 3, 5, 4>("N=128, 3 acc + 4 warps LDTM");
-  run<128, 3, 5, 8>("N=128, 3 acc + 8 warps LDTM");
-  run<128, 3, 5, 16>("N=128, 3 acc + 16 warps LDTM");
-  run<128, 4, 5, 0, 1, 0>("N=128 + bulk-copy stream");
-  run<256, 2, 5, 0, 1, 0>("N=256 + bulk-copy stream");
-  run<128, 4, 5, 0, 0, 3>("N=128 + 3 CAS spinners");
-  run<256, 2, 5, 0, 0, 3>("N=256 + 3 CAS spinners");
-  run<128, 4, 5, 0, 1, 3>("N=128 + bulk copies + spinners");
-  run<256, 2, 5, 0, 1, 3>("N=256 + bulk copies + spinners");
-  run<128, 3, 5, 16, 1, 3>("N=128 + LDTM x16 + copies + spin");
-  run<128, 0, 5, 0, 1, 1>("IDLE tensor pipe: copies + 1 spinner");
-  run<128, 0, 5, 0, 1, 3>("IDLE tensor pipe: copies + 3 spinners");
-  run<128, 0, 5, 16, 0, 0>("IDLE tensor pipe: LDTM x16");
-  run<128, 4, 5, 0, 1, 1>("N=128 + copies + 1 spinner");
-  run<256, 2, 5, 0, 1, 1>("N=256 + copies + 1 spinner");
-  run<128, 3, 5, 16, 1, 1>("N=128 + LDTM x16 + copies + 1 spinner");
+  run<128, 4, 5>("N=128, 4 acc, 5 k-blocks");
+  run<128, 4, 5>("N=128, 4 acc, 5 k-blocks, commit per batch", 1);
+  run<128, 4, 3>("N=128, 4 acc, 3 k-blocks, commit per batch", 1);
+  run<128, 4, 1>("N=128, 4 acc, 1 k-block, commit per batch", 1);
+  run<256, 2, 5>("N=256, 2 acc, 5 k-blocks, commit per batch", 1);
+  run<128, 3, 5, 16, 1, 1>("N=128 + LDTM x16 + copies + 1 spinner, commit per batch", 1);
   return 0;
 }
