@@ -175,9 +175,18 @@ void run(const char* name, int commit_every = 0) {
 int main() {
   run<128, 4, 5>("N=128, 4 acc, 5 k-blocks");
   run<128, 4, 5>("N=128, 4 acc, 5 k-blocks, commit per batch", 1);
-  run<128, 4, 3>("N=128, 4 acc, 3 k-blocks, commit per batch", 1);
   run<128, 4, 1>("N=128, 4 acc, 1 k-block, commit per batch", 1);
   run<256, 2, 5>("N=256, 2 acc, 5 k-blocks, commit per batch", 1);
-  run<128, 3, 5, 16, 1, 1>("N=128 + LDTM x16 + copies + 1 spinner, commit per batch", 1);
+  run<64, 8, 5>("N=64, 8 acc, 5 k-blocks");
+  run<128, 3, 5, 16, 0, 0>("N=128 + LDTM x16");
+  run<128, 3, 5, 16, 0, 0>("N=128 + LDTM x16, commit per batch", 1);
+  run<128, 3, 3, 16, 0, 0>("N=128, 3 k-blocks + LDTM x16, commit per batch", 1);
+  run<128, 3, 5, 4, 0, 0>("N=128 + LDTM x4, commit per batch", 1);
+  run<128, 4, 5, 0, 1, 0>("N=128 + bulk copies, commit per batch", 1);
+  run<128, 4, 5, 0, 0, 1>("N=128 + 1 CAS spinner, commit per batch", 1);
+  run<128, 3, 5, 16, 1, 1>("N=128 + LDTM x16 + copies + spinner");
+  run<128, 3, 5, 16, 1, 1>("N=128 + LDTM x16 + copies + spinner, commit per batch", 1);
+  run<128, 0, 5, 0, 1, 1>("IDLE tensor pipe: copies + 1 spinner");
+  run<128, 0, 5, 16, 0, 0>("IDLE tensor pipe: LDTM x16");
   return 0;
 }
