@@ -7,7 +7,15 @@ mAP@R eval wall-time at 1/2/4/8 B200).
 
 One "step" = one complete calculate_mAP evaluation (sign/bit-pack of queries + gallery, Hamming passes,
 exact top-R selection, label match + AP, means) over one batch of synthetic codes.  The last stdout line
-is ONE JSON object (see DESIGN.md "Measurement").
+is ONE JSON object (see DESIGN.md "Measurement").  Besides the headline workload the line carries
+
+  * ``parity_check``     -- outside the timed region, at every N: per-query AP of the timed configuration and the
+                            ranked ids of 32 queries against the CPU oracle (oracle/packed_oracle.py, checker only)
+                            over the CONCATENATED gallery of all ranks; a mismatch aborts with a non-zero exit code;
+  * ``other_workloads``  -- the other BASELINE configs on the same box: configs[4]'s per-GPU shard (weak-scaled) at
+                            every N, and at N = 1 CUB-200 / Cars196-16/32/64 / NABirds, each with its own
+                            parity_check;
+  * ``phase_ms``         -- kernels / collectives / host share of a step.
 """
 from __future__ import annotations
 
@@ -39,10 +47,13 @@ WORKLOADS = {
     "cub200": dict(dataset="cub200", nbit=64, R=-1, p=0.15, scaling="strong",
                    desc="BASELINE configs[0]: CUB-200-2011 64-bit mAP@all, 5,794 x 5,994, 200 classes"),
     "cars196": dict(dataset="cars196", nbit=64, R=-1, p=0.15, scaling="strong",
-                    desc="BASELINE configs[1]: Cars196 64-bit mAP@all, 8,041 x 8,144, 196 classes"),
+                    desc="BASELINE configs[1]: Cars196 mAP@all, 8,041 x 8,144, 196 classes"),
     "nabirds": dict(dataset="nabirds", nbit=64, R=-1, p=0.15, scaling="strong",
                     desc="BASELINE configs[2]: NABirds 64-bit mAP@all, 24,633 x 23,929, 555 classes"),
 }
+# measured by dev/mma_rate_probe.cu on this pool's B200 (profiles/r1i_mma_rate_probe.txt): one UTCIMMA
+# M = N = 128, K = 32 per 64.0 clk and SM = 8192 int8 MAC / clk / SM
+MMA_ISSUE_MAC_PER_CLK_SM = 8192.0
 
 
 def make_workload(name, device, nbit_override=None, shard=0):
@@ -139,6 +150,324 @@ def cpu_reference_sample(w, d, dl, q, ql, scale=1.0):
     return dict(seconds=dt, pairs=float(sq) * ndb, queries=sq, cores=cores, threads=torch.get_num_threads(), mAP=m)
 
 
+# ---------------------------------------------------------------------------------------------------- parity check
+def _torch_sign_bytes(codes, chunk=1 << 20):
+    """(n, nbit) real codes -> (n, 8 * ceil(nbit / 64)) uint8, little-endian sign bits, by PLAIN torch ops (the
+    checker must not depend on the pack kernel it checks).  Also returns whether an exact zero / NaN was seen."""
+    n, nbit = codes.shape
+    nb = (nbit + 63) // 64 * 8
+    out = torch.empty((n, nb), dtype=torch.uint8, device=codes.device)
+    w = (2 ** torch.arange(8, device=codes.device)).to(torch.int32)
+    bad = False
+    for s in range(0, n, chunk):
+        x = codes[s:s + chunk]
+        bad = bad or bool(((x == 0) | (x != x)).any())
+        pos = torch.zeros((x.shape[0], nb * 8), dtype=torch.int32, device=codes.device)
+        pos[:, :nbit] = x > 0
+        out[s:s + chunk] = (pos.view(-1, nb, 8) * w).sum(-1).to(torch.uint8)
+    return out, bad
+
+
+def parity_check(ev, w, d, dl, q, ql, rank, world, device, nsub=32):
+    """The timed configuration against the CPU oracle, outside the timed region.  Every rank runs the collective
+    GPU calls; rank 0 runs the oracle over the concatenated gallery."""
+    from oracle import packed_oracle as po                # checker only
+    R, nbit, nq = w["R"], int(q.shape[1]), int(q.shape[0])
+    ndb_total = int(d.shape[0]) * (world if w["scaling"] == "weak" else 1)
+    if ndb_total > 20_000_000:
+        nsub = min(nsub, 16)                               # the oracle costs ~1 s per query per 100 M rows
+    sub = torch.unique(torch.linspace(0, nq - 1, nsub).round().long()).to(device)
+    _, _, _, ap = ev.evaluate(d, dl, q, ql, [R], 0.0, [], False, return_ap=True)
+    mode = ev.stats.get("mode")
+    ids, keys, _ = ev.retrieve(d, q[sub].contiguous(), R)
+    bits, bad = _torch_sign_bytes(d)
+    lab = dl.to(torch.int32).contiguous()
+    if world > 1:
+        import torch.distributed as dist
+        n_loc = torch.tensor([d.shape[0]], dtype=torch.int64, device=device)
+        n_all = [torch.zeros_like(n_loc) for _ in range(world)]
+        dist.all_gather(n_all, n_loc)
+        n_all = [int(t.item()) for t in n_all]
+        nmax = max(n_all)
+        pb = torch.zeros((nmax, bits.shape[1]), dtype=torch.uint8, device=device)
+        pb[:bits.shape[0]] = bits
+        pl = torch.zeros((nmax,), dtype=torch.int32, device=device)
+        pl[:lab.shape[0]] = lab
+        gb = torch.empty((world * nmax, bits.shape[1]), dtype=torch.uint8, device=device)
+        gl = torch.empty((world * nmax,), dtype=torch.int32, device=device)
+        dist.all_gather_into_tensor(gb, pb)
+        dist.all_gather_into_tensor(gl, pl)
+        del pb, pl
+        if rank == 0:
+            bits = torch.cat([gb[r * nmax:r * nmax + n_all[r]] for r in range(world)])
+            lab = torch.cat([gl[r * nmax:r * nmax + n_all[r]] for r in range(world)])
+        del gb, gl
+    res = None
+    if rank == 0:
+        t0 = time.perf_counter()
+        g64 = bits.cpu().numpy().view(np.uint64)
+        qbits, qbad = _torch_sign_bytes(q[sub])
+        q64 = qbits.cpu().numpy().view(np.uint64)
+        oids, odist = po.topk_packed(q64, g64, R, nbit)
+        oap = po.ap_of_ranked(oids, ql[sub].cpu().numpy(), lab.cpu().numpy())
+        got_ap = ap[0][sub].cpu().numpy()
+        ids_equal = bool(np.array_equal(ids.cpu().numpy(), oids))
+        dist_equal = bool(np.array_equal(keys.cpu().numpy().astype(np.int32), odist))
+        delta = float(np.abs(got_ap - oap).max())
+        res = {"queries": int(sub.numel()), "gallery_rows": int(g64.shape[0]), "R": R,
+               "max_abs_ap_delta": delta, "ids_equal": ids_equal, "dist_equal": dist_equal,
+               "ok": bool(ids_equal and dist_equal and delta <= 1e-9 and not bad and not qbad),
+               "mode": mode, "oracle": "oracle/packed_oracle.py (popcount + stable (distance, row) order)",
+               "oracle_seconds": round(time.perf_counter() - t0, 2)}
+    del bits, lab
+    ok = torch.tensor([1 if (res is None or res["ok"]) else 0], dtype=torch.int32, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
+    return res, bool(ok.item())
+
+
+def tie_order_delta(w, d, dl, q, ql, nsub=512):
+    """mAP(upstream's torch.topk tie order) - mAP(canonical stable order) on a query subset, CPU oracle: what a
+    maintainer would see move against numbers produced by the old utils.hashing."""
+    from oracle import map_oracle as mo
+    sub = torch.unique(torch.linspace(0, q.shape[0] - 1, nsub).round().long())
+    dc, dlc, qc, qlc = d.cpu(), dl.cpu(), q.cpu()[sub], ql.cpu()[sub]
+    a, _, _ = mo.calculate_mAP(dc, dlc, qc, qlc, w["R"], tie="torch_topk")
+    b, _, _ = mo.calculate_mAP(dc, dlc, qc, qlc, w["R"], tie="stable")
+    return {"queries": int(sub.numel()), "mAP_torch_topk_order": a, "mAP_canonical": b, "delta": a - b}
+
+
+# ---------------------------------------------------------------------------------------------------- one workload
+def measure(ctx, name, nbit, steps, warmup, *, main, e2e=True, cpu=True):
+    """Times one workload on this rank set; returns the fields of its JSON object (rank 0) and the parity verdict."""
+    from concepthash_b200 import hashing
+    rank, world, device, group, ev, peaks, peak_src = (ctx[k] for k in
+                                                       ("rank", "world", "device", "group", "ev", "peaks", "peak_src"))
+    wl = WORKLOADS[name]
+    # weak scaling: every rank generates its own gallery block (same queries), no duplicates across ranks
+    w, d, dl, q, ql = make_workload(name, device, nbit, shard=rank if wl["scaling"] == "weak" else 0)
+    unit64 = w["nbit"] / 64.0
+    ndb_full = d.shape[0]
+    if w["scaling"] == "strong" and world > 1:        # row-shard the named gallery over the ranks
+        cut = [ndb_full * r // world for r in range(world + 1)]
+        d, dl = d[cut[rank]:cut[rank + 1]].contiguous(), dl[cut[rank]:cut[rank + 1]].contiguous()
+    total_pairs = float(w["nq"]) * (ndb_full if w["scaling"] == "strong" else ndb_full * world)
+    r_list = [w["R"]]
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def run(fn, steps, warmup, sample_clocks=False):
+        out = None
+        for _ in range(warmup):
+            out = fn()
+        sampler = ClockSampler(device.index) if sample_clocks else None
+        barrier()
+        if sampler:
+            sampler.start()
+        ev.events = []
+        ev.profile = True
+        l0 = ev.b.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        ev.profile = False
+        clocks = sampler.stop() if sampler else None
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=device)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return float(ms.item()), out, ev.b.launch_count() - l0, clocks, list(ev.events)
+
+    # value: inputs resident in HBM (fp32 codes + int64 ids as torch CUDA tensors)
+    step_dev = lambda: ev.evaluate(d, dl, q, ql, r_list, 0.0, [], False)
+    ms, out, launches, clocks, events = run(step_dev, steps, warmup, sample_clocks=True)
+    value = total_pairs * unit64 / (ms * 1e-3)
+    stats = dict(ev.stats)
+
+    # per-kernel times from the CUDA events recorded on the launch stream inside the timed region
+    kinds, biggest = {}, {}
+    for kind, units, a, b in events:
+        t = a.elapsed_time(b)
+        k = kinds.setdefault(kind, [0.0, 0.0, 0])
+        k[0] += t
+        k[1] += units
+        k[2] += 1
+        if kind not in biggest or units > biggest[kind][1]:
+            biggest[kind] = [0.0, units, 0]
+        if units == biggest[kind][1]:
+            biggest[kind][0] += t
+            biggest[kind][2] += 1
+    words32 = max(1, (w["nbit"] + 31) // 32)
+    popc_peak = ctx["popc_peak"]
+    sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+    sm_count = ev.b.sm_count
+
+    def ncu_traffic(kernel):
+        """DRAM bytes per launch of `kernel` from the committed ncu --set full capture of this workload, or None"""
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                t = json.load(f)
+            return t.get(name, {}).get(kernel)
+        except Exception:
+            return None
+
+    def popc_roofline(kind):
+        hk = kinds[kind]
+        t_ms = hk[0] / hk[2]
+        popc = (hk[1] / hk[2]) * words32 / (t_ms * 1e-3)
+        what = {"hist_count": "count pass: every pair histogrammed",
+                "hist_count_rec": "count pass + records of relevant pairs (full ranking)",
+                "hist_select": "select pass: pairs with key <= threshold counted / matched / recorded"}[kind]
+        return {
+            "kernel": f"hamming_hist_kernel ({what})", "bound": "int-pipe (POPC)",
+            "achieved": popc / 1e9, "peak": popc_peak / 1e9, "unit": "Gpopc32/s", "frac": popc / popc_peak,
+            "traffic": ncu_traffic("hamming_hist_kernel"),
+            "traffic_source": "profiles/ncu_traffic.json (committed ncu --set full capture, not measured in this run)",
+            "algorithmic_work": f"pairs x {words32} popc32 per pair per launch",
+            "peak_source": "ch_popc_peak micro-benchmark run live on this GPU (MEASURED_PEAKS.json has no "
+                           "integer-pipe figure); nominal 148 SM x 16 lanes x f",
+            "nominal_peak_at_sampled_clock": sm_count * 16 * sm_mhz * 1e6 / 1e9,
+            "ms_per_launch": t_ms, "pairs_per_launch": hk[1] / hk[2], "pairs_per_s": (hk[1] / hk[2]) / (t_ms * 1e-3),
+            "share_of_step": hk[0] / (ms * steps)}
+
+    def tensor_roofline(kind):
+        hk = kinds[kind]
+        t_ms = hk[0] / hk[2]
+        pairs = hk[1] / hk[2]
+        kb = ev.b.tc_code_bytes(w["nbit"])                    # K bytes the MMA really contracts (codes + threshold block)
+        tops = pairs * w["nbit"] * 2 / (t_ms * 1e-3) / 1e12   # ALGORITHMIC: nbit int8 MACs per pair
+        peak = 2.0 * peaks.get("bf16_tflops", 1590.0)
+        issue_peak = sm_count * MMA_ISSUE_MAC_PER_CLK_SM * 2 * sm_mhz * 1e6 / 1e12
+        pairs_s = pairs / (t_ms * 1e-3)
+        return {
+            "kernel": "hamming_select_tc_kernel (select pass: tcgen05.mma kind::i8 -> TMEM, sign-bit epilogue, "
+                      "candidate lists)",
+            "bound": "tensor", "achieved": tops, "peak": peak, "unit": "TOP/s (int8)", "frac": tops / peak,
+            "traffic": ncu_traffic("hamming_select_tc_kernel"),
+            "traffic_source": "profiles/ncu_traffic.json (committed ncu --set full capture, not measured in this run)",
+            "algorithmic_work": f"pairs x {w['nbit']} int8 MACs x 2 per launch (the kernel contracts K = {kb} bytes: "
+                                "the codes plus the block that carries the per-query threshold)",
+            "peak_source": f"2 x bf16_tflops of {peak_src}: int8 dense runs at twice the bf16 rate and no int8 figure "
+                           "is measured; nominal dense int8 is 4500 TOP/s",
+            "measured_mma_issue_peak_tops": issue_peak,
+            "frac_of_measured_mma_issue_peak": tops / issue_peak,
+            "frac_of_measured_mma_issue_peak_executed": tops * kb / w["nbit"] / issue_peak,
+            "mma_issue_peak_source": "dev/mma_rate_probe.cu (profiles/r1i_mma_rate_probe.txt): 64.0 clk per UTCIMMA "
+                                     "M=N=128 K=32 = 8192 MAC/clk/SM, x SMs x sampled SM clock",
+            "executed_tops_incl_threshold_block": tops * kb / w["nbit"],
+            "frac_of_nominal_int8_4500": tops / 4500.0,
+            "pairs_per_clk_per_sm": pairs_s / (sm_count * sm_mhz * 1e6),
+            "mma_floor_pairs_per_clk_per_sm": 128.0 * 128.0 / (64.0 * (kb // 32)),
+            "popc_kernel_ceiling_pairs_per_s": popc_peak / words32,
+            "ms_per_launch": t_ms, "launches_per_step": hk[2] / steps, "pairs_per_launch": pairs,
+            "pairs_per_s": pairs_s, "share_of_step": hk[0] / (ms * steps)}
+
+    ham_kinds = [k for k in kinds if k.startswith("hist")]
+    roofline, roofline_other = None, {}
+    if ham_kinds:
+        dom = max(ham_kinds, key=lambda k: kinds[k][0])
+        roofline = tensor_roofline(dom) if dom == "hist_select_tc" else popc_roofline(dom)
+        roofline_other = {k: (tensor_roofline(k) if k == "hist_select_tc" else popc_roofline(k))
+                          for k in ham_kinds if k != dom}
+    roofline_pack = None
+    pack = biggest.get("pack_dev")
+    if pack and pack[0] > 0:
+        # the LARGEST pack launch (the gallery) by itself: one launch per event bracket
+        gbs = pack[1] * pack[2] / (pack[0] * 1e-3) / 1e9
+        roofline_pack = {"kernel": "pack_sign_flat_kernel / pack_bits_kernel (sign + bit-pack of the gallery codes)",
+                         "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": gbs / peaks["hbm_gbs"], "traffic": ncu_traffic("pack_sign_flat_kernel"),
+                         "peak_source": peak_src, "ms_per_launch": pack[0] / pack[2], "bytes_per_launch": pack[1]}
+    kernel_ms = {k: v[0] / steps for k, v in kinds.items()}
+    coll_ms = sum(v for k, v in kernel_ms.items() if k.startswith("comm_"))
+    kern_ms = sum(v for k, v in kernel_ms.items() if not k.startswith("comm_"))
+    phase_ms = {"kernels": kern_ms, "collectives": coll_ms, "host_and_launch_gaps": max(0.0, ms - kern_ms - coll_ms),
+                "host_syncs_per_step": stats.get("host_syncs")}
+
+    # e2e: the public call with HOST tensors; H2D of codes + labels and D2H of the result inside.  Led by what the
+    # reference's trainers really hand over -- PAGEABLE tensors (trainers/base.py:291-304) -- with pinned beside it.
+    e2e_obj = None
+    if e2e:
+        es, ew = max(2, steps // 2), 2
+        pd, pdl, pq, pql = (t.cpu() for t in (d, dl, q, ql))
+        step_page = lambda: hashing.calculate_mAP(pd, pdl, pq, pql, w["R"], group=group)
+        ms_p, out_p, _, _, ev_p = run(step_page, es, ew)
+        kinds_p = {}
+        for kind, units, a, b in ev_p:
+            kinds_p[kind] = kinds_p.get(kind, 0.0) + a.elapsed_time(b) / es
+        mode_p = ev.stats.get("mode")
+        hd, hdl, hq, hql = (t.pin_memory() for t in (pd, pdl, pq, pql))
+        del pd, pdl, pq, pql
+        step_host = lambda: hashing.calculate_mAP(hd, hdl, hq, hql, w["R"], group=group)
+        ms_e, out_e, _, _, _ = run(step_host, es, ew)
+        h2d = sum(t.numel() * t.element_size() for t in (hd, hdl, hq, hql))
+        del hd, hdl, hq, hql
+        e2e_obj = {"value": total_pairs * unit64 / (ms_p * 1e-3), "unit": "64-bit comparisons/s",
+                   "ms_per_step": ms_p, "host_memory": "pageable (what trainers/base.py:291-304 hands over)",
+                   "ms_per_step_pinned_host_tensors": ms_e,
+                   "value_pinned_host_tensors": total_pairs * unit64 / (ms_e * 1e-3),
+                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 * len(r_list) + 64,
+                   "mAP": out_p[0], "mAP_pinned": out_e[0], "mode": mode_p, "kernel_ms_per_step": kinds_p}
+
+    pc, ok = parity_check(ev, w, d, dl, q, ql, rank, world, device)
+
+    cpu_obj = None
+    if cpu and rank == 0 and world == 1:
+        r = cpu_reference_sample(w, d, dl, q, ql)
+        cpu_obj = {"value": r["pairs"] * unit64 / r["seconds"], "unit": "64-bit comparisons/s", "cores": r["cores"],
+                   "kind": "port", "threads": r["threads"], "seconds": r["seconds"],
+                   "sample": f"{r['queries']} of {w['nq']} queries x {w['ndb']} gallery rows (upstream-style "
+                             f"oracle/map_oracle.calculate_mAP_upstream_style; linear in nq)"}
+    tie = None
+    if rank == 0 and world == 1 and "dataset" in wl:
+        tie = tie_order_delta(w, d, dl, q, ql)
+
+    config = {"workload": w["desc"], "nq": w["nq"], "ndb_per_gpu": int(d.shape[0]),
+              "ndb_total": int(ndb_full if w["scaling"] == "strong" else ndb_full * world),
+              "nbit": w["nbit"], "R": w["R"], "nclass": w["nclass"],
+              "pairs_per_s": total_pairs / (ms * 1e-3),
+              "mode": stats.get("mode"), "geometry(threads,nq_pad,stripes,rows/stripe)": stats.get("geometry"),
+              "l2_policy": "inputs larger than L2 (fp32 gallery codes >= 512 MB vs 126 MB L2)"
+              if w["ndb"] * w["nbit"] * 4 > 2.0e8 else "small workload: inputs fit L2 (latency-bound case)",
+              "parallelism": f"gallery row-sharded x{world}" if world > 1 else "single GPU",
+              "mAP": out[0][0] if out else None}
+    dtype = ("s8 x s8 -> s32 (tcgen05 kind::i8 select pass) + u32 xor/popc (sample, count and key passes)"
+             if "hist_select_tc" in kinds else "u32 xor/popc")
+    if rank == 0:
+        print(f"[{name}/{w['nbit']}] evaluator stats:", stats, file=sys.stderr)
+    del d, dl, q, ql
+    torch.cuda.empty_cache()
+    if main:
+        return {
+            "metric": "hamming_comparisons_per_sec_64bit", "value": value, "unit": "64-bit comparisons/s",
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None, "dtype": dtype,
+            "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e_obj, "gpu_launches": launches,
+            "kernel_ms_per_step": kernel_ms, "phase_ms": phase_ms, "parity_check": pc,
+            "roofline": roofline, "roofline_other_passes": roofline_other, "roofline_pack": roofline_pack,
+            "cpu_baseline": cpu_obj, "tie_order_delta": tie,
+        }, ok
+    slim = None
+    if roofline is not None:
+        slim = {k: roofline[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "ms_per_launch",
+                                         "share_of_step") if k in roofline}
+        if "frac_of_measured_mma_issue_peak" in roofline:
+            slim["frac_of_measured_mma_issue_peak"] = roofline["frac_of_measured_mma_issue_peak"]
+    return {
+        "workload": w["desc"], "nbit": w["nbit"], "R": w["R"], "scaling": w["scaling"], "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms, "value": value, "unit": "64-bit comparisons/s",
+        "mAP": config["mAP"], "mode": stats.get("mode"), "ndb_per_gpu": config["ndb_per_gpu"],
+        "ndb_total": config["ndb_total"], "gpu_launches": launches, "kernel_ms_per_step": kernel_ms,
+        "phase_ms": phase_ms, "clocks": clocks, "roofline": slim, "parity_check": pc, "tie_order_delta": tie,
+        "e2e": e2e_obj,
+    }, ok
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -149,6 +478,7 @@ def main():
     ap.add_argument("--nbit", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the other_workloads block")
     ap.add_argument("--sample-stride", type=int, default=0, help="override the evaluator's row-sample stride")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -204,184 +534,38 @@ def main():
         group = dist.group.WORLD
     from concepthash_b200 import hashing
 
-    # weak scaling: every rank generates its own gallery block (same queries), no duplicates across ranks
-    w, d, dl, q, ql = make_workload(args.workload, device, args.nbit, shard=rank if wl["scaling"] == "weak" else 0)
-    ndb_full = d.shape[0]
-    if w["scaling"] == "strong" and world > 1:        # row-shard the named gallery over the ranks
-        cut = [ndb_full * r // world for r in range(world + 1)]
-        d, dl = d[cut[rank]:cut[rank + 1]].contiguous(), dl[cut[rank]:cut[rank + 1]].contiguous()
-    total_pairs = float(w["nq"]) * (ndb_full if w["scaling"] == "strong" else ndb_full * world)
     ev = hashing.get_evaluator(device, group)
     if args.sample_stride:
         ev.sample_stride = args.sample_stride
-    r_list = [w["R"]]
-
-    def barrier():
-        if world > 1:
-            torch.distributed.barrier()
-        torch.cuda.synchronize()
-
-    def run(fn, steps, warmup, sample_clocks=False):
-        out = None
-        for _ in range(warmup):
-            out = fn()
-        sampler = ClockSampler(local_rank) if sample_clocks else None
-        barrier()
-        if sampler:
-            sampler.start()
-        ev.events = []
-        ev.profile = True
-        l0 = ev.b.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            out = fn()
-        e1.record()
-        barrier()
-        ev.profile = False
-        clocks = sampler.stop() if sampler else None
-        ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=device)
-        if world > 1:
-            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
-        return float(ms.item()), out, ev.b.launch_count() - l0, clocks, list(ev.events)
-
-    # value: inputs resident in HBM (fp32 codes + int64 ids as torch CUDA tensors)
-    step_dev = lambda: ev.evaluate(d, dl, q, ql, r_list, 0.0, [], False)
-    ms, out, launches, clocks, events = run(step_dev, args.steps, args.warmup, sample_clocks=True)
-    value = total_pairs * unit64 / (ms * 1e-3)
-
-    # per-kernel times from the CUDA events recorded on the launch stream inside the timed region
-    kinds = {}
-    for kind, units, a, b in events:
-        k = kinds.setdefault(kind, [0.0, 0.0, 0])
-        k[0] += a.elapsed_time(b)
-        k[1] += units
-        k[2] += 1
-    words32 = max(1, (w["nbit"] + 31) // 32)
-    popc_peak, _ = ev.b.popc_peak()
     peaks, peak_src = measured_peaks()
-    # the dominant kernel = the Hamming pass with the largest share of the step
-    sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+    popc_peak, _ = ev.b.popc_peak()
+    ctx = dict(rank=rank, world=world, device=device, group=group, ev=ev, peaks=peaks, peak_src=peak_src,
+               popc_peak=popc_peak)
 
-    def popc_roofline(kind):
-        hk = kinds[kind]
-        t_ms = hk[0] / hk[2]
-        popc = (hk[1] / hk[2]) * words32 / (t_ms * 1e-3)
-        name = {"hist_count": "count pass: every pair histogrammed",
-                "hist_count_rec": "count pass + records of relevant pairs (full ranking)",
-                "hist_select": "select pass: pairs with key <= threshold counted / matched / recorded"}[kind]
-        return {
-            "kernel": f"hamming_hist_kernel ({name})", "bound": "int-pipe (POPC)",
-            "achieved": popc / 1e9, "peak": popc_peak / 1e9, "unit": "Gpopc32/s", "frac": popc / popc_peak,
-            "traffic": ncu_traffic("hamming_hist_kernel"),
-            "algorithmic_work": f"pairs x {words32} popc32 per pair per launch",
-            "peak_source": "ch_popc_peak micro-benchmark run live on this GPU (MEASURED_PEAKS.json has no "
-                           "integer-pipe figure); nominal 148 SM x 16 lanes x f",
-            "nominal_peak_at_sampled_clock": 148 * 16 * sm_mhz * 1e6 / 1e9,
-            "ms_per_launch": t_ms, "pairs_per_launch": hk[1] / hk[2], "pairs_per_s": (hk[1] / hk[2]) / (t_ms * 1e-3),
-            "share_of_step": hk[0] / (ms * args.steps)}
-
-    def ncu_traffic(kernel):
-        """DRAM bytes per launch of `kernel` from the committed ncu --set full capture of this workload, or None"""
-        try:
-            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-                t = json.load(f)
-            return t.get(args.workload, {}).get(kernel)
-        except Exception:
-            return None
-
-    def tensor_roofline(kind):
-        hk = kinds[kind]
-        t_ms = hk[0] / hk[2]
-        pairs = hk[1] / hk[2]
-        kb = ev.b.tc_code_bytes(w["nbit"])                    # K bytes the MMA really contracts (codes + threshold block)
-        tops = pairs * w["nbit"] * 2 / (t_ms * 1e-3) / 1e12   # ALGORITHMIC: nbit int8 MACs per pair
-        peak = 2.0 * peaks.get("bf16_tflops", 1590.0)
-        pairs_s = pairs / (t_ms * 1e-3)
-        return {
-            "kernel": "hamming_select_tc_kernel (select pass: tcgen05.mma kind::i8 -> TMEM, sign-bit epilogue, "
-                      "candidate lists)",
-            "bound": "tensor", "achieved": tops, "peak": peak, "unit": "TOP/s (int8)", "frac": tops / peak,
-            "traffic": ncu_traffic("hamming_select_tc_kernel"),
-            "algorithmic_work": f"pairs x {w['nbit']} int8 MACs x 2 per launch (the kernel contracts K = {kb} bytes: "
-                                "the codes plus the 32-byte block that carries the per-query threshold)",
-            "peak_source": f"2 x bf16_tflops of {peak_src}: int8 dense runs at twice the bf16 rate and no int8 figure "
-                           "is measured; nominal dense int8 is 4500 TOP/s",
-            "executed_tops_incl_threshold_block": tops * kb / w["nbit"],
-            "frac_of_nominal_int8_4500": tops / 4500.0,
-            "pairs_per_clk_per_sm": pairs_s / (148 * sm_mhz * 1e6),
-            "mma_floor_pairs_per_clk_per_sm": 128.0 * 128.0 / (64.0 * (kb // 32)),
-            "popc_kernel_ceiling_pairs_per_s": popc_peak / words32,
-            "ms_per_launch": t_ms, "launches_per_step": hk[2] / args.steps, "pairs_per_launch": pairs,
-            "pairs_per_s": pairs_s, "share_of_step": hk[0] / (ms * args.steps)}
-
-    ham_kinds = [k for k in kinds if k.startswith("hist")]
-    dom = max(ham_kinds, key=lambda k: kinds[k][0])
-    roofline = tensor_roofline(dom) if dom == "hist_select_tc" else popc_roofline(dom)
-    roofline_other = {k: (tensor_roofline(k) if k == "hist_select_tc" else popc_roofline(k))
-                      for k in ham_kinds if k != dom}
-    pack = kinds.get("pack_dev")
-    roofline_pack = None
-    if pack:
-        gbs = pack[1] / (pack[0] * 1e-3) / 1e9
-        roofline_pack = {"kernel": "pack_bits_kernel (sign + bit-pack)", "bound": "hbm", "achieved": gbs,
-                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None,
-                         "peak_source": peak_src, "ms_per_step": pack[0] / args.steps}
-    kernel_ms = {k: v[0] / args.steps for k, v in kinds.items()}
-
-    # e2e: the public call with HOST (pinned) tensors; H2D of codes + labels and D2H of the result inside
-    e2e = None
-    if not args.no_e2e:
-        hd, hdl, hq, hql = (t.cpu().pin_memory() for t in (d, dl, q, ql))
-        step_host = lambda: hashing.calculate_mAP(hd, hdl, hq, hql, w["R"], group=group)
-        ms_e, out_e, _, _, ev_e = run(step_host, max(2, args.steps // 2), 2)
-        kinds_e = {}
-        for kind, units, a, b in ev_e:
-            kinds_e[kind] = kinds_e.get(kind, 0.0) + a.elapsed_time(b) / max(2, args.steps // 2)
-        h2d = sum(t.numel() * t.element_size() for t in (hd, hdl, hq, hql))
-        # the same call with ordinary (pageable) CPU tensors -- what the reference's trainers hand over
-        pd, pdl, pq, pql = (t.cpu() for t in (d, dl, q, ql))
-        step_page = lambda: hashing.calculate_mAP(pd, pdl, pq, pql, w["R"], group=group)
-        ms_p, _, _, _, _ = run(step_page, 2, 1)
-        del pd, pdl, pq, pql
-        e2e = {"value": total_pairs * unit64 / (ms_e * 1e-3), "unit": "64-bit comparisons/s",
-               "ms_per_step_pageable_host_tensors": ms_p,
-               "ms_per_step": ms_e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 * len(r_list) + 64,
-               "mAP": out_e[0], "mode": ev.stats.get("mode"), "kernel_ms_per_step": kinds_e}
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_sample(w, d, dl, q, ql)
-        cpu = {"value": r["pairs"] * unit64 / r["seconds"], "unit": "64-bit comparisons/s", "cores": r["cores"],
-               "kind": "port", "threads": r["threads"], "seconds": r["seconds"],
-               "sample": f"{r['queries']} of {w['nq']} queries x {w['ndb']} gallery rows (upstream-style "
-                         f"oracle/map_oracle.calculate_mAP_upstream_style; linear in nq)"}
-
+    line, ok_all = measure(ctx, args.workload, args.nbit, args.steps, args.warmup, main=True,
+                           e2e=not args.no_e2e, cpu=not args.no_cpu_baseline)
+    others = []
+    if not args.no_others:
+        plan = []
+        if args.workload != "cfg5":
+            plan.append(("cfg5", 0, 5, 3))              # configs[4]: weak-scaled shard, at every N
+        if world == 1:
+            plan += [(n, b, 10, 3) for n, b in (("cub200", 64), ("cars196", 16), ("cars196", 32), ("cars196", 64),
+                                                ("nabirds", 64)) if not (n == args.workload and b == wl["nbit"])]
+        for name, nbit, steps, warm in plan:
+            obj, ok = measure(ctx, name, nbit, steps, warm, main=False, e2e=False, cpu=False)
+            others.append(obj)
+            ok_all = ok_all and ok
     if rank == 0:
-        print("evaluator stats:", ev.stats, file=sys.stderr)
-        line = {
-            "metric": "hamming_comparisons_per_sec_64bit", "value": value, "unit": "64-bit comparisons/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
-            "dtype": "s8 x s8 -> s32 (tcgen05 kind::i8 select pass) + u32 xor/popc (sample, count and key passes)"
-            if "hist_select_tc" in kinds else "u32 xor/popc",
-            "data": "synthetic",
-            "config": {"workload": w["desc"], "nq": w["nq"], "ndb_per_gpu": int(d.shape[0]),
-                       "ndb_total": int(ndb_full if w["scaling"] == "strong" else ndb_full * world),
-                       "nbit": w["nbit"], "R": w["R"], "nclass": w["nclass"],
-                       "pairs_per_s": total_pairs / (ms * 1e-3),
-                       "mode": ev.stats.get("mode"), "geometry(threads,nq_pad,stripes,rows/stripe)": ev.stats.get("geometry"),
-                       "l2_policy": "inputs larger than L2 (fp32 gallery codes >= 512 MB vs 126 MB L2)"
-                       if w["ndb"] * w["nbit"] * 4 > 2.0e8 else "small workload: inputs fit L2 (latency-bound case)",
-                       "parallelism": f"gallery row-sharded x{world}" if world > 1 else "single GPU",
-                       "mAP": out[0][0] if out else None},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "kernel_ms_per_step": kernel_ms,
-            "roofline": roofline, "roofline_other_passes": roofline_other, "roofline_pack": roofline_pack,
-            "cpu_baseline": cpu,
-        }
+        line["other_workloads"] = others
+        line["parity_ok"] = ok_all
         print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
+    if not ok_all:
+        if rank == 0:
+            print("PARITY CHECK FAILED (see parity_check in the JSON line)", file=sys.stderr)
+        return 3
     return 0
 
 

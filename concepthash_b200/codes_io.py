@@ -108,10 +108,20 @@ def load_packed(path):
     return PackedCodes(torch.from_numpy(bits.astype(np.uint32).view(np.int32).copy()), nbit), labels, nclass
 
 
-def load_code_dump(path, part=None):
+def load_code_dump(path, part=None, trusted=False):
     """A reference code dump -> ``{'codes...': tensor, 'labels': tensor, ...}``.  ``outputs.pth`` files hold both
-    sides; pick one with ``part`` = ``'db'`` / ``'test'``."""
-    obj = torch.load(path, map_location="cpu", weights_only=False)
+    sides; pick one with ``part`` = ``'db'`` / ``'test'``.
+
+    Dumps are plain dicts of tensors (trainers/base.py:184-188), so they load with ``weights_only=True`` -- a
+    crafted file cannot execute code.  ``trusted=True`` opts into full unpickling for a legacy dump that holds
+    other objects (numpy arrays pickled by ``np.concatenate`` outputs, base.py:303); only for files you wrote."""
+    try:
+        obj = torch.load(path, map_location="cpu", weights_only=True)
+    except Exception as e:
+        if not trusted:
+            raise ValueError(f"{path}: not loadable as tensors only ({type(e).__name__}: {e}); pass trusted=True "
+                             "(--trusted) if this dump is your own and holds non-tensor objects") from e
+        obj = torch.load(path, map_location="cpu", weights_only=False)
     if isinstance(obj, dict) and "db" in obj and "test" in obj and "labels" not in obj:
         if part is None:
             raise ValueError(f"{path} holds both sides: pass part='db' or part='test'")
@@ -122,12 +132,12 @@ def load_code_dump(path, part=None):
 
 
 def evaluate_dumps(db, test, R, PRs=(1, 5, 10), threshold=0.0, zero_mean_eval=False, remove_first_retrieved=False,
-                   group=None):
+                   group=None, trusted=False):
     """``db`` / ``test``: paths of code dumps (or already loaded dicts).  Returns ``{'mAP': ..., 'recalls': ...,
     'precisions': ..., 'mAP_<name>': ...}`` exactly as ``RetrievalExperiment.evaluation`` names them."""
     from .hashing import calculate_mAP
-    db_out = load_code_dump(db, "db") if isinstance(db, str) else db
-    test_out = load_code_dump(test, "test") if isinstance(test, str) else test
+    db_out = load_code_dump(db, "db", trusted) if isinstance(db, str) else db
+    test_out = load_code_dump(test, "test", trusted) if isinstance(test, str) else test
     names = [k for k in db_out if "codes" in k]                      # train_helper.py:207-214
     res = {}
     for name in names:
@@ -151,5 +161,6 @@ if __name__ == "__main__":
     ap.add_argument("--PRs", type=int, nargs="*", default=[1, 5, 10])
     ap.add_argument("--threshold", type=float, default=0.0)
     ap.add_argument("--zero-mean-eval", action="store_true")
+    ap.add_argument("--trusted", action="store_true", help="allow full unpickling of the dumps (your own files only)")
     a = ap.parse_args()
-    print(json.dumps(evaluate_dumps(a.db, a.test, a.R, a.PRs, a.threshold, a.zero_mean_eval)))
+    print(json.dumps(evaluate_dumps(a.db, a.test, a.R, a.PRs, a.threshold, a.zero_mean_eval, trusted=a.trusted)))

@@ -43,19 +43,26 @@ class DistComm:
         import torch.distributed as dist
         self.dist, self.group = dist, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.timer = None      # the evaluator's event bracket (bench: time spent in collectives)
+
+    def _t(self, kind, nbytes, fn):
+        return fn() if self.timer is None else self.timer(kind, nbytes, fn)
 
     def all_gather(self, t):
         flat = t.contiguous().view(-1)
         out = torch.empty((self.world * flat.numel(),), dtype=t.dtype, device=t.device)
-        self.dist.all_gather_into_tensor(out, flat, group=self.group)
+        self._t("comm_all_gather", out.numel() * out.element_size(),
+                lambda: self.dist.all_gather_into_tensor(out, flat, group=self.group))
         return out.view((self.world,) + tuple(t.shape))
 
     def all_reduce_sum(self, t):
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        self._t("comm_all_reduce", t.numel() * t.element_size(),
+                lambda: self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group))
         return t
 
     def all_reduce_max(self, t):
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        self._t("comm_all_reduce", t.numel() * t.element_size(),
+                lambda: self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group))
         return t
 
 
@@ -75,7 +82,10 @@ class Evaluator:
     def __init__(self, backend, comm=None):
         self.b = backend
         self.comm = comm if comm is not None else LocalComm()
+        if hasattr(self.comm, "timer"):
+            self.comm.timer = self._timed
         self.stats = {}
+        self.host_syncs = 0                # device -> host round trips of the current evaluation
         self.stripe_rows_override = None   # tests: force the stripe length (multiple of 256 on CUDA)
         self.sample_stride = 32            # top-R: 1-in-32 row sample picks the threshold (0/1 = exact two-pass)
         self.sample_two_level = True       # thresholds from the sample by a tensor-core select pass (see below)
@@ -93,6 +103,11 @@ class Evaluator:
         self.col_sub = None                # zero_mean_eval: f64[nbit] column offset of the current evaluation
         self.profile = False               # bench: bracket the kernels with CUDA events on the launch stream
         self.events = []                   # (kind, work units, start event, end event)
+
+    def _host_ints(self, t):
+        """device -> host read of a small integer tensor (ONE round trip; counted)"""
+        self.host_syncs += 1
+        return _as_int_list(t)
 
     def _timed(self, kind, units, fn):
         if not self.profile:
@@ -158,6 +173,8 @@ class Evaluator:
             raise ValueError(f"nbit mismatch: query {q_codes.shape[1]} vs gallery {db_codes.shape[1]}")
         if q_codes.shape[0] == 0:
             raise ValueError("no queries")
+        if (zero_mean or threshold != 0) and (isinstance(db_codes, PackedCodes) or isinstance(q_codes, PackedCodes)):
+            raise ValueError("packed codes carry no magnitudes: threshold / zero_mean_eval need real-valued codes")
         self.col_sub = None
         if zero_mean:
             # zero_mean_eval fused into the pack kernel: the gallery's column mean is subtracted from both sets
@@ -185,7 +202,7 @@ class Evaluator:
         g = self._pack_side(db_codes, db_labels, threshold, flags, L.CH_GALLERY_NOLABEL, info=meta[8:12],
                             defer_codes=defer)
         if self.comm.world == 1:
-            mm = _as_int_list(meta)
+            mm = self._host_ints(meta)
             rows = [g.n]
         else:
             # ranks must agree: [zero flag, max positives per row, max class id + 1, NaN flag] by MAX, rows by SUM
@@ -196,7 +213,7 @@ class Evaluator:
             red[3] = (meta[0] >> 1) & 1
             red[4] = 0 if g.bits is None else 1          # some rank already packed its gallery: nobody streams
             red[5 + self.comm.rank] = g.n
-            red = _as_int_list(self.comm.all_reduce_max(red))
+            red = self._host_ints(self.comm.all_reduce_max(red))
             mm = [red[0] | (red[3] << 1), 0, 0, 0, red[1], red[2], 0, 0, 0, 0, 0, 0]
             rows = red[5:]
             if red[4] and g.bits is None:
@@ -207,6 +224,9 @@ class Evaluator:
         ternary = bool(m[0])
         if ternary:
             # rare: some sign is exactly 0 -> pack again, this time with the non-zero bit-plane
+            if isinstance(db_codes, PackedCodes) or isinstance(q_codes, PackedCodes):
+                raise ValueError("the real-valued side holds exact zeros (ternary keys): it cannot be ranked against "
+                                 "packed sign bits -- pass both sides real-valued")
             kw = {} if self.col_sub is None else dict(col_sub=self.col_sub)
             _, q.nz = self.b.pack_sign(q_codes, threshold, flags, True, **kw)
             g.bits, g.nz = self.b.pack_sign(db_codes, threshold, flags, True, **kw)
@@ -249,6 +269,7 @@ class Evaluator:
         threads, nq_pad, nstripes, rps = geo
         off = self.b.empty((nstripes, nq_pad), torch.int32)
         total, tmax = self.b.record_offsets(cap, nstripes, nq, nq_pad, off, thresh)
+        self.host_syncs += 1
         self.stats["record_slots"] = total
         if status is None:
             status = self.b.zeros((2,), torch.int32)
@@ -257,7 +278,7 @@ class Evaluator:
         return (rec, tmax) if thresh is not None else rec
 
     def _check_records(self, rec):
-        if int(rec["err"].cpu()[0]) != 0:
+        if self._host_ints(rec["err"])[0] != 0:
             raise RuntimeError("internal error: record buffer overflow")
 
     # ------------------------------------------------------------------ tensor-core select pass -> candidate lists
@@ -272,6 +293,7 @@ class Evaluator:
         threads, nq_pad, nstripes, rps = geo
         off = self.b.empty((nstripes, nq_pad), torch.int32)
         total, tmax = self.b.record_offsets(cap, nstripes, nq, nq_pad, off, thresh)
+        self.host_syncs += 1
         self.stats["record_slots"] = total
         if status is None:
             status = self.b.zeros((2,), torch.int32)
@@ -356,6 +378,7 @@ class Evaluator:
         b, comm = self.b, self.comm
         if hasattr(b, "begin"):
             b.begin()
+        self.host_syncs = 0
         r_list = [int(r) for r in R]
         pr_k = [int(k) for k in PRs]
         if len(r_list) == 0 and len(pr_k) == 0:
@@ -414,7 +437,7 @@ class Evaluator:
             # gallery codes were deferred but the streamed path is not applicable (or gave up): pack them now
             fl = b.zeros((1,), torch.int32)
             self._pack_codes(g, db_codes, threshold, fl)
-            fl = int(comm.all_reduce_max(fl).cpu()[0]) if comm.world > 1 else int(fl.cpu()[0])
+            fl = self._host_ints(comm.all_reduce_max(fl) if comm.world > 1 else fl)[0]
             if fl & 2:
                 raise ValueError("codes contain NaN")
             if fl & 1:
@@ -443,6 +466,7 @@ class Evaluator:
                 self.stats["mode"] = "topR"
                 res = self._finish(ctx, self._pass_topr_exact(ctx))
         maps, recalls, precisions, ap, flags = res
+        self.stats["host_syncs"] = self.host_syncs
         if flags[0]:
             raise RuntimeError("internal error: record buffer overflow")
         if return_ap:
@@ -474,7 +498,9 @@ class Evaluator:
             if comm.world > 1:
                 status = comm.all_reduce_max(status)
             ap = b.empty((len(r_eff), nq), torch.float64) if c["return_ap"] else None
-            maps, recalls, precisions, flags = b.reduce_means(cols, st["total_rel"] if pr_k else None, first_rel, nq,
+            self.host_syncs += 1
+            self.host_syncs += 1
+        maps, recalls, precisions, flags = b.reduce_means(cols, st["total_rel"] if pr_k else None, first_rel, nq,
                                                               len(r_eff), pr_k, ap, status)
             return maps, recalls, precisions, ap, flags
         rec = st["rec"]
@@ -495,6 +521,7 @@ class Evaluator:
         if comm.world > 1:
             status = comm.all_reduce_max(status)
         ap = b.empty((len(r_eff), nq), torch.float64) if c["return_ap"] else None
+        self.host_syncs += 1
         maps, recalls, precisions, flags = b.reduce_means(cols, st["total_rel"] if pr_k else None, first_rel, nq,
                                                           len(r_eff), pr_k, ap, status)
         return maps, recalls, precisions, ap, flags
@@ -969,7 +996,7 @@ class Evaluator:
             b.cand_finalize(cand, mode=2, base0_all=base0_c, base0_rel=None, nq=nq, nq_pad=nq_pad, nstripes=nstripes,
                             nbins=nbins, remove_first=bool(rf), ids=ids, keys=keys, R=R, row_offset=row_offset,
                             key_max=key_max)
-            if int(cand["err"].cpu()[0]) != 0:
+            if self._host_ints(cand["err"])[0] != 0:
                 raise RuntimeError("internal error: candidate list overflow")
             if comm.world > 1:
                 ids = comm.all_reduce_max(ids)
@@ -999,7 +1026,7 @@ class Evaluator:
         flags = self.b.zeros((1,), torch.int32)
         pa = self._pack_side(a_codes, None, threshold, flags, 0, want_nz=True)
         pb = self._pack_side(b_codes, None, 0.0, flags, 0, want_nz=True)
-        fl = int(flags.cpu()[0])
+        fl = self._host_ints(flags)[0]
         if fl & 2:
             raise ValueError("codes contain NaN")
         ternary = bool(fl & 1)

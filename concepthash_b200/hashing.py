@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import torch
 
+from . import _lib
 from .evaluator import DistComm, Evaluator, LocalComm
 
 _EVALUATORS = {}
@@ -72,8 +73,19 @@ def calculate_mAP(db_codes, db_labels, test_codes, test_labels, R, threshold=0.,
     r_list = [int(r) for r in R] if r_is_list else [int(R)]
     pr_list = [] if PRs is None else [int(k) for k in PRs]
     ev = get_evaluator(_device_of(db_codes, test_codes, db_labels, test_labels), group)
-    maps, recalls, precisions = ev.evaluate(db_codes, db_labels, test_codes, test_labels, r_list, threshold,
-                                            pr_list, bool(remove_first_retrieved), zero_mean=bool(zero_mean_eval))
+    maps, recalls, precisions = [], [], []
+    # one pass serves up to CH_MAX_R values of R and CH_MAX_PR cut-offs; longer lists take several passes
+    nr, npr = max(1, -(-len(r_list) // _lib.CH_MAX_R)), max(1, -(-len(pr_list) // _lib.CH_MAX_PR))
+    for i in range(max(nr, npr)):
+        rs = r_list[i * _lib.CH_MAX_R:(i + 1) * _lib.CH_MAX_R]
+        ks = pr_list[i * _lib.CH_MAX_PR:(i + 1) * _lib.CH_MAX_PR]
+        if not rs and not ks:
+            continue
+        m, r, p = ev.evaluate(db_codes, db_labels, test_codes, test_labels, rs, threshold, ks,
+                              bool(remove_first_retrieved), zero_mean=bool(zero_mean_eval))
+        maps += m
+        recalls += r
+        precisions += p
     return (maps if r_is_list else maps[0]), recalls, precisions
 
 
@@ -107,13 +119,9 @@ def calculate_pr_curve(db_codes, db_labels, test_codes, test_labels, threshold=0
         n = int(t.item())
     n -= 1 if remove_first_retrieved else 0
     rs = default_pr_cutoffs(n) if Rs is None else [int(r) for r in Rs]
-    recalls, precisions = [], []
-    for i in range(0, len(rs), 32):      # CH_MAX_PR cut-offs per pass
-        _, r, p = calculate_mAP(db_codes, db_labels, test_codes, test_labels, [], threshold=threshold,
-                                PRs=rs[i:i + 32], remove_first_retrieved=remove_first_retrieved, group=group,
-                                zero_mean_eval=zero_mean_eval)
-        recalls += r
-        precisions += p
+    _, recalls, precisions = calculate_mAP(db_codes, db_labels, test_codes, test_labels, [], threshold=threshold,
+                                           PRs=rs, remove_first_retrieved=remove_first_retrieved, group=group,
+                                           zero_mean_eval=zero_mean_eval)       # (chunks of CH_MAX_PR cut-offs)
     return recalls, precisions, rs
 
 
@@ -149,11 +157,18 @@ def pack_codes(codes):
 
 def get_hamm_dist(codes, centroids, margin=0., normalize=False):
     """Code -> codebook Hamming distance matrix (callers: trainers/orthohash.py:362,397,430,465,
-    trainers/dpn.py:30,62; identity: trainers/orthohash.py:263-264).  float32, on the GPU."""
+    trainers/dpn.py:30,62; identity: trainers/orthohash.py:263-264).  float32, returned on the device of ``codes``
+    (the trainers hand the matrix straight to ``calculate_accuracy_hamm_dist(hamm_dist, labels)``,
+    utils/metrics.py:18-29, with labels on that device); the arithmetic runs on the GPU either way.
+
+    ``margin`` zeroes ``|codes| < margin`` before the sign (ternary keys, half-integer distances) and ONE matrix is
+    returned; no in-tree caller passes it (every call is ``get_hamm_dist(codes, codebook, normalize=True)``), and
+    the upstream helper's behaviour for ``margin != 0`` is unpinned -- see INTEGRATION.md."""
     codes, centroids = _as_tensor(codes), _as_tensor(centroids)
-    if codes.shape[1] != centroids.shape[1]:
+    if codes.dim() != 2 or centroids.dim() != 2 or codes.shape[1] != centroids.shape[1]:
         raise ValueError("nbit mismatch")
     ev = get_evaluator(_device_of(codes, centroids))
     keys, ternary = ev.hamming_matrix(codes, centroids, margin)
     d = keys.to(torch.float32) * (0.5 if ternary else 1.0)
-    return d / codes.shape[1] if normalize else d
+    d = d / codes.shape[1] if normalize else d
+    return d.to(codes.device) if isinstance(codes, torch.Tensor) and d.device != codes.device else d

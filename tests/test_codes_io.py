@@ -41,6 +41,16 @@ def test_code_dump_layouts(tmp_path):
     torch.save({"x": 1}, tmp_path / "bad.pth")
     with pytest.raises(ValueError):
         codes_io.load_code_dump(str(tmp_path / "bad.pth"))
+    # a dump holding arbitrary pickled objects is refused unless the caller vouches for it (no code execution
+    # from a crafted file); with trusted=True the legacy path loads it
+    import pickle
+    import types
+    legacy = dict(db_out, labels=dl, extra=types.SimpleNamespace(v=3))
+    with open(tmp_path / "legacy.pth", "wb") as f:
+        torch.save(legacy, f, pickle_module=pickle)
+    with pytest.raises(ValueError, match="trusted"):
+        codes_io.load_code_dump(str(tmp_path / "legacy.pth"))
+    assert torch.equal(codes_io.load_code_dump(str(tmp_path / "legacy.pth"), trusted=True)["codes"], d)
 
 
 @pytest.mark.parametrize("tc", [False, True])

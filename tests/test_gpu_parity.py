@@ -319,6 +319,51 @@ def test_cfg4_shape_subset_and_idempotence(H):
     assert abs(m - om) < TOL
 
 
+def _check_subset_against_packed_oracle(H, d, dl, q, ql, R, ap_full, nsub=32):
+    """AP rows of a full-size run and the ranked ids of the same queries against the packed-bit CPU oracle
+    (oracle/packed_oracle.py: popcount + stable (distance, row) order over the WHOLE gallery)."""
+    from oracle import packed_oracle as po
+    nq, nbit = q.shape
+    sub = torch.unique(torch.linspace(0, nq - 1, nsub).round().long())
+    gb = po.pack_sign_bits(d.cpu().numpy())
+    qb = po.pack_sign_bits(q[sub.to(q.device)].cpu().numpy())
+    oids, odist = po.topk_packed(qb, gb, R, nbit)
+    oap = po.ap_of_ranked(oids, ql.cpu().numpy()[sub.numpy()], dl.cpu().numpy())
+    got = ap_full[0].cpu().numpy()[sub.numpy()]
+    assert np.abs(got - oap).max() < TOL, np.abs(got - oap).max()
+    ids, dist = H.retrieve_topk(q[sub.to(q.device)], d, R)
+    assert np.array_equal(ids.cpu().numpy(), oids)
+    assert np.array_equal(dist.cpu().numpy().astype(np.int32), odist)
+    return float(oap.mean())
+
+
+def test_cfg4_full_query_set_vs_oracle(H):
+    """BASELINE configs[3] exactly as bench.py times it (128-bit, 25,000 queries x 1,000,000 rows, mAP@1000: 49 query
+    groups x several stripes, dense epilogue, two-level sample): per-query AP of the FULL run, on 32 queries spread
+    over all query groups, against the CPU oracle; ranked ids of those queries bit-exact."""
+    ev = H.get_evaluator()
+    d, dl, q, ql, ncls = synth.make_random_case(25_000, 1_000_000, 128, 101, p=0.30, seed=0, device="cuda")
+    maps, _, _, ap = ev.evaluate(d, dl, q, ql, [1000], 0.0, [], False, return_ap=True)
+    assert ev.stats["mode"] == "topR-sampled" and ev.stats["select_kernel"] == "tcgen05", ev.stats
+    assert abs(float(ap[0].mean()) - maps[0]) < 1e-12
+    _check_subset_against_packed_oracle(H, d, dl, q, ql, 1000, ap)
+
+
+def test_cfg5_shard_geometry_vs_oracle(H):
+    """BASELINE configs[4] geometry (64-bit, 1000 classes, top-R = 1000; configs/dataset/inat_birds.yaml:4) at a
+    size the oracle can check: 20,500 queries (41 query groups, a partial last tile) x 2,000,077 rows (KB = 96
+    kernel variant, sparse epilogue, stride-64 sample)."""
+    ev = H.get_evaluator()
+    d, dl, q, ql, ncls = synth.make_random_case(20_500, 2_000_077, 64, 1000, p=0.30, seed=0, device="cuda")
+    maps, rec, prec, ap = ev.evaluate(d, dl, q, ql, [1000], 0.0, [1, 10], False, return_ap=True)
+    assert ev.stats["mode"] == "topR-sampled" and ev.stats["select_kernel"] == "tcgen05", ev.stats
+    assert not ev.stats.get("select_dense"), ev.stats
+    _check_subset_against_packed_oracle(H, d, dl, q, ql, 1000, ap)
+    # the same call through the drop-in surface returns the same numbers
+    m, rec2, prec2 = H.calculate_mAP(d, dl, q, ql, 1000, PRs=[1, 10])
+    assert m == maps[0] and rec2 == rec and prec2 == prec
+
+
 def test_sampled_one_pass_equals_exact_two_pass(H):
     """Top-R with the sample-derived threshold (one full pass) must be bit-identical to the exact two-pass
     path, and must fall back when the gallery order defeats the sample."""
