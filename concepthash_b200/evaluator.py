@@ -499,8 +499,7 @@ class Evaluator:
                 status = comm.all_reduce_max(status)
             ap = b.empty((len(r_eff), nq), torch.float64) if c["return_ap"] else None
             self.host_syncs += 1
-            self.host_syncs += 1
-        maps, recalls, precisions, flags = b.reduce_means(cols, st["total_rel"] if pr_k else None, first_rel, nq,
+            maps, recalls, precisions, flags = b.reduce_means(cols, st["total_rel"] if pr_k else None, first_rel, nq,
                                                               len(r_eff), pr_k, ap, status)
             return maps, recalls, precisions, ap, flags
         rec = st["rec"]
