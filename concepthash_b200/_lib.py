@@ -81,7 +81,12 @@ SIGNATURES = {
     "ch_slab_totals": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int64, P, P]),
     "ch_slab_exscan": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int64, P]),
     "ch_scan_bases": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, P, P, P, P]),
-    "ch_record_caps": (C.c_int, [P, C.c_int, P, P, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, P, P]),
+    "ch_record_caps": (C.c_int, [P, C.c_int, P, P, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                 P, P]),
+    "ch_record_offsets_async": (C.c_int, [P, P, C.c_int, C.c_int64, C.c_int64, P, P, C.c_uint64, C.c_uint32, P, P, P]),
+    "ch_scan_bases_pair": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                     P, P, P, P, P, P]),
+    "ch_gather_rows": (C.c_int, [P, P, C.c_int64, C.c_int, C.c_int64, P, C.c_int64, P]),
     "ch_record_offsets": (C.c_int, [P, P, C.c_int, C.c_int64, C.c_int64, P, C.POINTER(C.c_uint64), P,
                                     C.POINTER(C.c_uint32), P]),
     "ch_check_counts": (C.c_int, [P, P, C.c_int64, C.c_int64, P, P]),
@@ -89,7 +94,7 @@ SIGNATURES = {
     "ch_finalize_records": (C.c_int, [P, C.POINTER(FinalArgs), P]),
     "ch_first_relevant": (C.c_int, [P, C.POINTER(FinalArgs), P, P]),
     "ch_reduce_means": (C.c_int, [P, P, P, P, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), P,
-                                  C.POINTER(C.c_double), P, C.POINTER(C.c_uint32), P]),
+                                  C.POINTER(C.c_double), P, C.POINTER(C.c_uint32), C.c_int, P]),
     "ch_scatter_ranked": (C.c_int, [P, C.POINTER(FinalArgs), C.c_int64, C.c_int64, P, P, P]),
     "ch_ap_from_ranked": (C.c_int, [P, P, C.c_int64, C.c_int64, P, P, C.c_int, C.c_int, C.c_int,
                                     C.POINTER(C.c_int64), P, P]),
@@ -125,7 +130,7 @@ def load():
             raise NativeLibraryError(f"{LIB_PATH} does not export {name}") from e
         fn.restype = res
         fn.argtypes = args
-    if lib.ch_abi_version() != 2:
+    if lib.ch_abi_version() != 3:
         raise NativeLibraryError("ABI version mismatch: rebuild the library")
     _lib = lib
     return lib

@@ -313,10 +313,33 @@ class CudaBackend:
         L.check(self.lib.ch_scan_bases(self.ws, _ptr(tot_all), world, rank, nbins, nq, nq_pad, rmax, _ptr(base0),
                                        _ptr(thresh), _ptr(total), self._stream()), "ch_scan_bases")
 
-    def record_caps(self, source, a0, a1, nstripes, nb, nq, nq_pad, min_with_prev, cap, sample_stride=0):
+    def record_caps(self, source, a0, a1, nstripes, nb, nq, nq_pad, min_with_prev, cap, sample_stride=0,
+                    replicate=False):
+        """``replicate``: ``a0`` holds ONE stripe whose capacities are written to all ``nstripes`` rows of ``cap``"""
         L.check(self.lib.ch_record_caps(self.ws, source, _ptr(a0), _ptr(a1), nstripes, nb, nq, nq_pad,
-                                        int(min_with_prev), int(sample_stride), _ptr(cap), self._stream()),
-                "ch_record_caps")
+                                        int(min_with_prev), int(sample_stride), 1 if replicate else nstripes,
+                                        _ptr(cap), self._stream()), "ch_record_caps")
+
+    def record_offsets_async(self, cap, nstripes, nq, nq_pad, off, thresh, limit_slots, key_limit, info, status):
+        """offsets without a host round trip; ``info`` u32[2] <- (total slots, max thresh), ``status`` |= 4 / 8"""
+        L.check(self.lib.ch_record_offsets_async(self.ws, _ptr(cap), nstripes, nq, nq_pad, _ptr(off), _ptr(thresh),
+                                                 int(limit_slots), int(key_limit), _ptr(info), _ptr(status),
+                                                 self._stream()), "ch_record_offsets_async")
+
+    def scan_bases_pair(self, tot, world, rank, nbins, nq, nq_pad, rmax, need, base0_all, base0_rel, key_max,
+                        total_rel, status):
+        """``tot`` (world, 2, nbins, nq_pad) contiguous"""
+        L.check(self.lib.ch_scan_bases_pair(self.ws, _ptr(tot), world, rank, nbins, nq, nq_pad, int(rmax), int(need),
+                                            _ptr(base0_all), _ptr(base0_rel), _ptr(key_max), _ptr(total_rel),
+                                            _ptr(status), self._stream()), "ch_scan_bases_pair")
+
+    def gather_rows(self, bits, n_src, nbit, stride):
+        """every ``stride``-th of the first ``n_src`` rows of a packed plane -> (rows, packed plane with zero pad rows)"""
+        n_out = (int(n_src) + stride - 1) // stride
+        out = self.empty((self.padded_rows(n_out), bits.shape[1]), torch.int32)
+        L.check(self.lib.ch_gather_rows(self.ws, _ptr(bits), int(n_src), int(nbit), int(stride), _ptr(out),
+                                        int(out.shape[0]), self._stream()), "ch_gather_rows")
+        return n_out, out
 
     def record_offsets(self, cap, nstripes, nq, nq_pad, off, thresh=None):
         """-> (total record slots, max(thresh[:nq]) or None); ONE host sync for both."""
@@ -357,15 +380,17 @@ class CudaBackend:
                 "ch_first_relevant")
 
     def reduce_means(self, cols, total_rel, first_rel, nq, n_r, pr_k, ap_out=None, flags=None):
-        """-> (mAPs, recalls, precisions, [flag0, flag1]); ``flags`` (u32[2] device) rides on the same host sync."""
+        """-> (mAPs, recalls, precisions, status words); ``flags`` (the u32 status block on the device) rides on
+        the same host sync."""
         n_pr = len(pr_k)
         out = (C.c_double * max(1, n_r + 2 * n_pr))()
-        fl = (C.c_uint32 * 2)(0, 0)
+        nfl = int(flags.numel()) if flags is not None else 0
+        fl = (C.c_uint32 * max(2, nfl))()
         prk = (C.c_int64 * max(1, n_pr))(*[int(k) for k in pr_k])
         L.check(self.lib.ch_reduce_means(self.ws, _ptr(cols), _ptr(total_rel), _ptr(first_rel), nq, n_r, n_pr, prk,
-                                         _ptr(ap_out), out, _ptr(flags), fl, self._stream()), "ch_reduce_means")
+                                         _ptr(ap_out), out, _ptr(flags), fl, nfl, self._stream()), "ch_reduce_means")
         vals = [float(out[i]) for i in range(n_r + 2 * n_pr)]
-        return vals[:n_r], vals[n_r:n_r + n_pr], vals[n_r + n_pr:], [int(fl[0]), int(fl[1])]
+        return vals[:n_r], vals[n_r:n_r + n_pr], vals[n_r + n_pr:], [int(fl[i]) for i in range(max(2, nfl))]
 
     def scatter_ranked(self, f, R, row_offset, ids, keys):
         L.check(self.lib.ch_scatter_ranked(self.ws, C.byref(self._final_args(f)), R, row_offset, _ptr(ids),

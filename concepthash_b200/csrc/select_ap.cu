@@ -51,11 +51,12 @@ __global__ void scan_bases_kernel(const uint32_t* __restrict__ tot_all, int worl
 // ---- record capacities / offsets ------------------------------------------------------------------
 __global__ void record_caps_kernel(int source, const uint32_t* __restrict__ a0, const uint32_t* __restrict__ a1,
                                    int nstripes, int nb, long long nq, long long nq_pad, int min_with_prev,
-                                   int sample_stride, uint32_t* __restrict__ cap) {
+                                   int sample_stride, int src_stripes, uint32_t* __restrict__ cap) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<long long>(nstripes) * nq_pad) return;
-  const int s = static_cast<int>(i / nq_pad);
-  const long long q = i - static_cast<long long>(s) * nq_pad;
+  // src_stripes == 1 < nstripes: the one source stripe is replicated into every output stripe
+  const int s = src_stripes == 1 ? 0 : static_cast<int>(i / nq_pad);
+  const long long q = i % nq_pad;
   uint32_t c = 0;
   if (q < nq) {
     if (source == 0 || source == 1) {
@@ -142,6 +143,148 @@ __global__ void record_offsets_kernel(const uint32_t* __restrict__ cap, const un
     const size_t o = static_cast<size_t>(k) * nq_pad + q;
     off[o] = static_cast<uint32_t>(run);
     run += cap[o];
+  }
+}
+
+// {all, relevant} totals of the candidate lists in ONE walk: tot (world, 2, nbins, nq_pad).  Besides the two base
+// arrays: key_max[q] = smallest key at which the global list holds rmax items (0xfffffffe-like "no limit" = nbins-1
+// when it never does), optional total_rel[q], and the verification of a sampled threshold -- status |= 1 when some
+// query counted fewer than `need` candidates (replaces a separate ch_check_counts launch).
+__global__ void scan_bases_pair_kernel(const uint32_t* __restrict__ tot, int world, int rank, int nbins, long long nq,
+                                       long long nq_pad, long long rmax, long long need,
+                                       uint32_t* __restrict__ base0_all, uint32_t* __restrict__ base0_rel,
+                                       uint32_t* __restrict__ key_max, uint32_t* __restrict__ total_rel,
+                                       uint32_t* __restrict__ status) {
+  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  bool short_list = false;
+  if (q < nq_pad) {
+    unsigned long long cum_a = 0, cum_r = 0;
+    uint32_t t = static_cast<uint32_t>(nbins - 1);
+    bool found = false;
+    constexpr int B = 4;
+    for (int key0 = 0; key0 < nbins; key0 += B) {
+      unsigned long long la[B], ta[B], lr[B], tr[B];
+#pragma unroll
+      for (int j = 0; j < B; ++j) {
+        la[j] = ta[j] = lr[j] = tr[j] = 0;
+        const int key = key0 + j;
+        if (q < nq && key < nbins) {
+          for (int g = 0; g < world; ++g) {
+            const size_t o = ((static_cast<size_t>(g) * 2) * nbins + key) * nq_pad + q;
+            const uint32_t va = __ldg(tot + o);
+            const uint32_t vr = base0_rel != nullptr ? __ldg(tot + o + static_cast<size_t>(nbins) * nq_pad) : 0u;
+            if (g < rank) {
+              la[j] += va;
+              lr[j] += vr;
+            }
+            ta[j] += va;
+            tr[j] += vr;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < B; ++j) {
+        const int key = key0 + j;
+        if (key >= nbins) break;
+        const size_t o = static_cast<size_t>(key) * nq_pad + q;
+        base0_all[o] = static_cast<uint32_t>(cum_a + la[j]);
+        if (base0_rel != nullptr) base0_rel[o] = static_cast<uint32_t>(cum_r + lr[j]);
+        cum_a += ta[j];
+        cum_r += tr[j];
+        if (!found && rmax >= 0 && cum_a >= static_cast<unsigned long long>(rmax)) {
+          t = static_cast<uint32_t>(key);
+          found = true;
+        }
+      }
+    }
+    if (key_max != nullptr) key_max[q] = t;
+    if (total_rel != nullptr) total_rel[q] = static_cast<uint32_t>(cum_r);
+    short_list = need > 0 && q < nq && cum_a < static_cast<unsigned long long>(need);
+  }
+  if (status != nullptr && __ballot_sync(0xffffffffu, short_list) != 0u && (threadIdx.x & 31) == 0)
+    atomicOr(status, 1u);
+}
+
+// every stride-th row of a packed bit plane (rows, words) -> (rows_out_pad, words), pad rows zero
+__global__ void gather_rows_kernel(const uint32_t* __restrict__ src, long long n_out, long long rows_out_pad,
+                                   long long stride, int words, uint32_t* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows_out_pad * words) return;
+  const long long r = i / words;
+  const int w = static_cast<int>(i - r * words);
+  out[i] = r < n_out ? __ldg(src + (r * stride) * words + w) : 0u;
+}
+
+// single-CTA exclusive scan like exscan_u64_kernel, plus what the host used to do after its round trip:
+// info[0] = total slots (saturated), info[1] = max(thresh[0..nq)); status |= 4 when the total exceeds `limit`
+// (the arena the caller allocated from a hint), |= 8 when a threshold reaches `key_limit` (the narrowed key range).
+__global__ void __launch_bounds__(1024) exscan_check_kernel(unsigned long long* __restrict__ v, long long n,
+                                                            const uint32_t* __restrict__ thresh, long long nq,
+                                                            unsigned long long limit, uint32_t key_limit,
+                                                            uint32_t* __restrict__ info, uint32_t* __restrict__ status) {
+  __shared__ unsigned long long part[1024];
+  __shared__ uint32_t mx[1024];
+  const int t = threadIdx.x;
+  const long long chunk = (n + 1023) / 1024;
+  const long long b = t * chunk;
+  long long e = b + chunk;
+  if (e > n) e = n;
+  unsigned long long s = 0;
+  for (long long i = b; i < e; ++i) s += v[i];
+  part[t] = s;
+  uint32_t m = 0;
+  if (thresh != nullptr)
+    for (long long i = t; i < nq; i += 1024) m = max(m, thresh[i]);
+  mx[t] = m;
+  __syncthreads();
+  for (int w = 512; w > 0; w >>= 1) {
+    if (t < w) mx[t] = max(mx[t], mx[t + w]);
+    __syncthreads();
+  }
+  if (t == 0) {
+    unsigned long long run = 0;
+    for (int i = 0; i < 1024; ++i) {
+      const unsigned long long x = part[i];
+      part[i] = run;
+      run += x;
+    }
+    v[n] = run;
+    if (info != nullptr) {
+      info[0] = run > 0xffffffffull ? 0xffffffffu : static_cast<uint32_t>(run);
+      info[1] = mx[0];
+    }
+    uint32_t fl = 0;
+    if (run > limit) fl |= 4u;
+    if (thresh != nullptr && key_limit != 0u && mx[0] >= key_limit) fl |= 8u;
+    if (fl != 0u && status != nullptr) atomicOr(status, fl);
+  }
+  __syncthreads();
+  unsigned long long run = part[t];
+  for (long long i = b; i < e; ++i) {
+    const unsigned long long x = v[i];
+    v[i] = run;
+    run += x;
+  }
+}
+
+// offsets as record_offsets_kernel; slices that would leave the arena get capacity 0 (the overflow is already
+// flagged: nothing may be written there)
+__global__ void record_offsets_clamp_kernel(uint32_t* __restrict__ cap, const unsigned long long* __restrict__ start,
+                                            int nstripes, long long nq_pad, unsigned long long limit,
+                                            uint32_t* __restrict__ off) {
+  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= nq_pad) return;
+  unsigned long long run = start[q];
+  for (int k = 0; k < nstripes; ++k) {
+    const size_t o = static_cast<size_t>(k) * nq_pad + q;
+    const uint32_t c = cap[o];
+    if (run + c > limit) {
+      cap[o] = 0u;
+      off[o] = 0u;
+    } else {
+      off[o] = static_cast<uint32_t>(run);
+      run += c;
+    }
   }
 }
 
@@ -429,15 +572,16 @@ extern "C" int ch_scan_bases(ch_ws* ws, const uint32_t* tot_all_dev, int world, 
 
 extern "C" int ch_record_caps(ch_ws* ws, int source, const uint32_t* slab_or_cls, const uint32_t* thresh_or_qids,
                               int nstripes, int nbins_or_nclass, int64_t nq, int64_t nq_pad, int min_with_prev,
-                              int sample_stride, uint32_t* cap_dev, void* stream) {
+                              int sample_stride, int src_stripes, uint32_t* cap_dev, void* stream) {
   if (ws == nullptr || slab_or_cls == nullptr || cap_dev == nullptr) CH_FAIL("null argument to ch_record_caps");
   if (source < 0 || source > 2) CH_FAIL("bad capacity source %d", source);
   if (source != 1 && thresh_or_qids == nullptr) CH_FAIL("capacity source %d needs thresholds / query ids", source);
+  if (src_stripes != nstripes && src_stripes != 1) CH_FAIL("src_stripes must be nstripes or 1 (replicate)");
   ChDeviceGuard guard(ws->device);
   record_caps_kernel<<<blocks_for(static_cast<long long>(nstripes) * nq_pad, 256), 256, 0,
                        static_cast<cudaStream_t>(stream)>>>(source, slab_or_cls, thresh_or_qids, nstripes,
                                                             nbins_or_nclass, nq, nq_pad, min_with_prev, sample_stride,
-                                                            cap_dev);
+                                                            src_stripes, cap_dev);
   CH_LAUNCH_CHECK(ws);
   return 0;
 }
@@ -471,7 +615,59 @@ extern "C" int ch_record_offsets(ch_ws* ws, const uint32_t* cap_dev, int nstripe
   const unsigned long long total = both[0];
   *total_host = total;
   if (thresh_max_host != nullptr) *thresh_max_host = static_cast<uint32_t>(both[1]);
-  if (total >= 0xffffffffull) CH_FAIL("%llu records exceed the 32-bit record index", total);
+  // (a total beyond the 32-bit slot index is the CALLER's to handle -- it evaluates the query set in chunks; the
+  // offsets written above are meaningless then and must not be used)
+  return 0;
+}
+
+extern "C" int ch_record_offsets_async(ch_ws* ws, uint32_t* cap_dev, int nstripes, int64_t nq, int64_t nq_pad,
+                                       uint32_t* off_dev, const uint32_t* thresh_dev, uint64_t limit_slots,
+                                       uint32_t key_limit, uint32_t* info_dev, uint32_t* status_dev, void* stream) {
+  if (ws == nullptr || cap_dev == nullptr || off_dev == nullptr || status_dev == nullptr)
+    CH_FAIL("null argument to ch_record_offsets_async");
+  if (limit_slots == 0 || limit_slots >= 0xffffffffull) CH_FAIL("limit_slots must be in 1 .. 2^32 - 2");
+  ChDeviceGuard guard(ws->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  void* scratch = nullptr;
+  if (ch_ws_scratch(ws, static_cast<size_t>(nq_pad + 2) * 8, &scratch)) return 1;
+  unsigned long long* rowtot = static_cast<unsigned long long*>(scratch);
+  row_totals_kernel<<<blocks_for(nq_pad, 256), 256, 0, st>>>(cap_dev, nstripes, nq_pad, rowtot);
+  CH_LAUNCH_CHECK(ws);
+  exscan_check_kernel<<<1, 1024, 0, st>>>(rowtot, nq_pad, thresh_dev, nq, limit_slots, key_limit, info_dev, status_dev);
+  CH_LAUNCH_CHECK(ws);
+  record_offsets_clamp_kernel<<<blocks_for(nq_pad, 256), 256, 0, st>>>(cap_dev, rowtot, nstripes, nq_pad, limit_slots,
+                                                                       off_dev);
+  CH_LAUNCH_CHECK(ws);
+  return 0;
+}
+
+extern "C" int ch_scan_bases_pair(ch_ws* ws, const uint32_t* tot_dev, int world, int rank, int nbins, int64_t nq,
+                                  int64_t nq_pad, int64_t rmax, int64_t need, uint32_t* base0_all_dev,
+                                  uint32_t* base0_rel_dev, uint32_t* key_max_dev, uint32_t* total_rel_dev,
+                                  uint32_t* status_dev, void* stream) {
+  if (ws == nullptr || tot_dev == nullptr || base0_all_dev == nullptr) CH_FAIL("null argument to ch_scan_bases_pair");
+  if (world < 1 || rank < 0 || rank >= world) CH_FAIL("bad world/rank %d/%d", world, rank);
+  if (need > 0 && status_dev == nullptr) CH_FAIL("verification needs a status word");
+  ChDeviceGuard guard(ws->device);
+  scan_bases_pair_kernel<<<blocks_for(nq_pad, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      tot_dev, world, rank, nbins, nq, nq_pad, rmax, need, base0_all_dev, base0_rel_dev, key_max_dev, total_rel_dev,
+      status_dev);
+  CH_LAUNCH_CHECK(ws);
+  return 0;
+}
+
+extern "C" int ch_gather_rows(ch_ws* ws, const uint32_t* bits_dev, int64_t n_src, int nbit, int64_t stride,
+                              uint32_t* out_dev, int64_t rows_out_pad, void* stream) {
+  if (ws == nullptr || bits_dev == nullptr || out_dev == nullptr) CH_FAIL("null argument to ch_gather_rows");
+  const int words = ch_code_words(nbit);
+  if (words == 0 || stride < 1 || n_src < 0) CH_FAIL("bad arguments to ch_gather_rows");
+  const int64_t n_out = (n_src + stride - 1) / stride;
+  if (rows_out_pad < n_out) CH_FAIL("output holds %lld rows, the sample has %lld", (long long)rows_out_pad, (long long)n_out);
+  if (rows_out_pad == 0) return 0;
+  ChDeviceGuard guard(ws->device);
+  gather_rows_kernel<<<blocks_for(rows_out_pad * words, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      bits_dev, n_out, rows_out_pad, stride, words, out_dev);
+  CH_LAUNCH_CHECK(ws);
   return 0;
 }
 
@@ -517,15 +713,16 @@ extern "C" int ch_check_counts(ch_ws* ws, const uint32_t* total_dev, int64_t nq,
 extern "C" int ch_reduce_means(ch_ws* ws, const double* cols_dev, const uint32_t* total_rel_dev,
                                const uint32_t* first_rel_dev, int64_t nq, int nR, int nPR, const int64_t* pr_k,
                                double* ap_out_dev, double* out_host, const uint32_t* flags_dev, uint32_t* flags_host,
-                               void* stream) {
+                               int nflags, void* stream) {
   if (ws == nullptr || cols_dev == nullptr || out_host == nullptr) CH_FAIL("null argument to ch_reduce_means");
   if (nR < 0 || nR > CH_MAX_R || nPR < 0 || nPR > CH_MAX_PR) CH_FAIL("too many R / PRs entries");
   const int nout = nR + 2 * nPR;
   ChDeviceGuard guard(ws->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // up to two status words of the caller (record overflow, verification) ride on the same host sync
-  if (flags_dev != nullptr && flags_host != nullptr)
-    CH_CUDA(cudaMemcpyAsync(flags_host, flags_dev, 8, cudaMemcpyDeviceToHost, st));
+  // the caller's status block (overflow / verification flags, packing statistics, slot totals) rides on the same
+  // host sync
+  if (flags_dev != nullptr && flags_host != nullptr && nflags > 0)
+    CH_CUDA(cudaMemcpyAsync(flags_host, flags_dev, static_cast<size_t>(nflags) * 4, cudaMemcpyDeviceToHost, st));
   if (nout == 0) {
     CH_CUDA(cudaStreamSynchronize(st));
     return 0;

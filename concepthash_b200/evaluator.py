@@ -70,6 +70,25 @@ def _as_int_list(t):
     return [int(v) for v in t.cpu().tolist()]
 
 
+# Layout of the per-evaluation status block (u32 words on the device; read back ONCE, with the results):
+ST_PASS = 0     # bit 0 slice overflow (select / record pass), bit 1 key outside the narrowed key range,
+#                 bit 2 slot arena smaller than the capacities need, bit 3 a threshold beyond the narrowed key range
+#                 (bits 2, 3: a stale hint of a speculative run -- the evaluation is repeated with host round trips)
+ST_SHORT = 1    # bit 0: some query holds fewer than R candidates under its sampled threshold (-> exact path)
+ST_CODES = 2    # ch_pack_sign flags: bit 0 some sign is exactly 0 (ternary keys), bit 1 NaN
+ST_PACKED = 3   # group mode: 1 if this rank packed its gallery up front (then nobody streams)
+# (total slots, max threshold) of the list / record allocations (ch_record_offsets_async): the sample-level list, and
+# the one full-size allocation an evaluation makes (sampled pass, exact pass or full ranking)
+ST_SITE = {"s1": 4, "full": 6, "exact": 6, "all": 6}
+ST_QINFO, ST_GINFO = 8, 12       # ch_pack_labels statistics [max positives per row, max id + 1, rows w/o label, -]
+ST_ROWS = 16    # gallery rows of every rank (group mode)
+_RETRY = object()
+
+
+class _TooManySlots(Exception):
+    """the slices of one evaluation would need >= 2^32 slots: the query set is evaluated in chunks instead"""
+
+
 class Packed:
     """Packed codes + labels of one side (query or gallery shard)."""
     __slots__ = ("n", "nbit", "bits", "nz", "ids", "masks", "info", "ncls", "i8", "plane")
@@ -78,14 +97,48 @@ class Packed:
         self.plane = None
 
 
+class _TimedBackend:
+    """Pass-through to the backend; while the evaluator profiles (bench), every entry point that is not already
+    inside an explicit bracket gets its own CUDA-event bracket (kind = "k_<entry point>")."""
+    _PLAIN = frozenset(("empty", "padded_rows", "code_words", "geometry", "tc_code_bytes", "launch_count", "begin",
+                        "on_stream", "to_host", "gather_plane_words", "popc_peak"))
+
+    def __init__(self, ev, backend):
+        object.__setattr__(self, "_ev", ev)
+        object.__setattr__(self, "_b", backend)
+
+    def __getattr__(self, name):
+        attr = getattr(self._b, name)
+        ev = self._ev
+        if not ev.profile or ev._bracket_open or name in self._PLAIN or not callable(attr):
+            return attr
+        return lambda *a, **k: ev._timed("k_" + name, 0, lambda: attr(*a, **k))
+
+    def __setattr__(self, name, value):
+        setattr(self._b, name, value)
+
+
 class Evaluator:
     def __init__(self, backend, comm=None):
-        self.b = backend
+        self.profile = False               # bench: bracket the kernels with CUDA events on the launch stream
+        self._bracket_open = False
+        self.b = _TimedBackend(self, backend)
         self.comm = comm if comm is not None else LocalComm()
         if hasattr(self.comm, "timer"):
             self.comm.timer = self._timed
         self.stats = {}
         self.host_syncs = 0                # device -> host round trips of the current evaluation
+        # Repeated evaluations of one shape (every eval_interval epochs, train_helper.py:273; the bench's steps) run
+        # SPECULATIVELY: what the first evaluation had to ask the device for in mid-flight -- label form, list
+        # sizes, the largest threshold -- is assumed to hold again, buffers are sized from it, the kernels verify
+        # it on the device and the verdict comes back with the results in the ONE final round trip.  A failed
+        # assumption repeats the evaluation the slow way; results never depend on the hint.
+        self.speculate = True
+        self.max_slots = 0xFFFFFFF0        # slices of one evaluation are addressed with 32-bit offsets
+        self._hints = {}                   # shape key -> what the last evaluation of that shape found
+        self._hint = None                  # the hint the running evaluation relies on (None: ask the device)
+        self._new_hint = None
+        self._status = None
         self.stripe_rows_override = None   # tests: force the stripe length (multiple of 256 on CUDA)
         self.sample_stride = 32            # top-R: 1-in-32 row sample picks the threshold (0/1 = exact two-pass)
         self.sample_two_level = True       # thresholds from the sample by a tensor-core select pass (see below)
@@ -101,7 +154,6 @@ class Evaluator:
         self.use_tensor_cores = True       # select pass on tcgen05 (int8 +-1 codes) when the shape allows it
         self.select_dense_override = None  # tests: force the dense / sparse epilogue of the tensor-core kernel
         self.col_sub = None                # zero_mean_eval: f64[nbit] column offset of the current evaluation
-        self.profile = False               # bench: bracket the kernels with CUDA events on the launch stream
         self.events = []                   # (kind, work units, start event, end event)
 
     def _host_ints(self, t):
@@ -110,11 +162,15 @@ class Evaluator:
         return _as_int_list(t)
 
     def _timed(self, kind, units, fn):
-        if not self.profile:
+        if not self.profile or self._bracket_open:
             return fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        out = fn()
+        self._bracket_open = True
+        try:
+            out = fn()
+        finally:
+            self._bracket_open = False
         e1.record()
         self.events.append((kind, units, e0, e1))
         return out
@@ -189,35 +245,37 @@ class Evaluator:
         if q_labels is not None and q_labels.dim() == 2 and db_labels.dim() == 2 and \
                 q_labels.shape[1] != db_labels.shape[1]:
             raise ValueError("query and gallery labels have different class counts")
-        # every small status word of the packing step lives in ONE tensor -> one device-to-host read:
-        # [0] flags (bit 0: some sign is 0, bit 1: NaN); [4:8] query label statistics; [8:12] gallery label statistics
-        meta = self.b.zeros((12,), torch.int32)
-        flags = meta[0:1]
-        q = self._pack_side(q_codes, q_labels, threshold, flags, L.CH_QUERY_NOLABEL, info=meta[4:8])
+        # every small status word of the evaluation lives in ONE tensor (layout: ST_* above) -> one device-to-host
+        # read.  A speculative run (self._hint) does not read it here at all: the label form, the ternary flag and
+        # the rows of the other ranks are taken from the hint and verified against the block after the final sync.
+        st = self._status = self.b.zeros((ST_ROWS + self.comm.world,), torch.int32)
+        flags = st[ST_CODES:ST_CODES + 1]
+        q = self._pack_side(q_codes, q_labels, threshold, flags, L.CH_QUERY_NOLABEL, info=st[ST_QINFO:ST_QINFO + 4])
         # a large HOST gallery is not copied yet: the top-R path streams it in row blocks behind the select pass
         defer = (allow_defer and self.stream_host_gallery and not isinstance(db_codes, PackedCodes) and
                  not db_codes.is_cuda and threshold == 0 and
                  db_labels is not None and db_codes.shape[0] >= self.stream_min_rows and
                  hasattr(self.b, "hamming_select_tc") and self.b.tc_code_bytes(int(db_codes.shape[1])) > 0)
-        g = self._pack_side(db_codes, db_labels, threshold, flags, L.CH_GALLERY_NOLABEL, info=meta[8:12],
-                            defer_codes=defer)
-        if self.comm.world == 1:
-            mm = self._host_ints(meta)
-            rows = [g.n]
+        g = self._pack_side(db_codes, db_labels, threshold, flags, L.CH_GALLERY_NOLABEL,
+                            info=st[ST_GINFO:ST_GINFO + 4], defer_codes=defer)
+        if self.comm.world > 1:
+            # ranks must agree: everything by MAX (each rank fills only its own slot of the row counts)
+            st[ST_ROWS + self.comm.rank] = g.n
+            if g.bits is not None:
+                st[ST_PACKED] = 1
+        if self._hint is not None:
+            mm, rows, any_packed = self._hint["mm"], self._hint["rows"], self._hint["any_packed"]
         else:
-            # ranks must agree: [zero flag, max positives per row, max class id + 1, NaN flag] by MAX, rows by SUM
-            red = self.b.zeros((5 + self.comm.world,), torch.int64)
-            red[0] = meta[0] & 1
-            red[1] = torch.maximum(meta[4], meta[8])
-            red[2] = torch.maximum(meta[5], meta[9])
-            red[3] = (meta[0] >> 1) & 1
-            red[4] = 0 if g.bits is None else 1          # some rank already packed its gallery: nobody streams
-            red[5 + self.comm.rank] = g.n
-            red = self._host_ints(self.comm.all_reduce_max(red))
-            mm = [red[0] | (red[3] << 1), 0, 0, 0, red[1], red[2], 0, 0, 0, 0, 0, 0]
-            rows = red[5:]
-            if red[4] and g.bits is None:
-                self._pack_codes(g, db_codes, threshold, flags)      # (zeros / NaN are re-checked by the caller)
+            if self.comm.world > 1:
+                self.comm.all_reduce_max(st)
+            mm = self._host_ints(st)
+            rows = mm[ST_ROWS:] if self.comm.world > 1 else [g.n]
+            any_packed = bool(mm[ST_PACKED])
+            mm = mm[:ST_ROWS]
+        self._new_hint.update(mm=list(mm), rows=list(rows), any_packed=any_packed)
+        if self.comm.world > 1 and any_packed and g.bits is None:
+            self._pack_codes(g, db_codes, threshold, flags)      # (zeros / NaN are re-checked by the caller)
+        mm = [mm[ST_CODES], 0, 0, 0] + list(mm[ST_QINFO:ST_QINFO + 4]) + list(mm[ST_GINFO:ST_GINFO + 4])
         m = [mm[0] & 1, max(mm[4], mm[8]), max(mm[5], mm[9]), (mm[0] >> 1) & 1]
         if m[3]:
             raise ValueError("codes contain NaN")
@@ -263,18 +321,48 @@ class Evaluator:
         self.b.slab_totals(slab, nstripes, nbins, nq_pad, tot)
         return self.comm.all_gather(tot)           # (world, nbins, nq_pad)
 
-    def _alloc_records(self, cap, geo, nq, thresh=None, status=None):
-        """Offsets of the per-(stripe, query) record slices and the record buffer.  ``status`` u32[2]: [0] is raised
-        by the pass when a slice overflows.  With ``thresh`` the same host round trip also returns max(thresh)."""
+    def _offsets(self, cap, geo, nq, thresh, site, nbins_full):
+        """Offsets of the per-(stripe, query) slices -> (off, slots to allocate, max threshold | None).
+
+        Without a hint for ``site`` this is a host round trip (exact total, exact max threshold).  With one, the
+        arena is sized from the previous evaluation's total (+ 12.5 % + 64 Ki slots), the key range from its largest
+        threshold (+ 2), and ``ch_record_offsets_async`` verifies both on the device (ST_PASS bits 2 / 3)."""
         threads, nq_pad, nstripes, rps = geo
         off = self.b.empty((nstripes, nq_pad), torch.int32)
-        total, tmax = self.b.record_offsets(cap, nstripes, nq, nq_pad, off, thresh)
-        self.host_syncs += 1
-        self.stats["record_slots"] = total
-        if status is None:
-            status = self.b.zeros((2,), torch.int32)
+        hint = self._hint["sites"].get(site) if (self._hint is not None and site is not None) else None
+        if hint is None or not hasattr(self.b, "record_offsets_async"):
+            total, tmax = self.b.record_offsets(cap, nstripes, nq, nq_pad, off, thresh)
+            self.host_syncs += 1
+            worst = total
+            if self.comm.world > 1:
+                # every rank must chunk the query set (or not) together: agree on the largest local total
+                worst = self._host_ints(self.comm.all_reduce_max(self.b.full((1,), total, torch.int64)))[0]
+            if worst >= self.max_slots:
+                raise _TooManySlots(worst)
+            if site is not None:
+                self._new_hint["sites"][site] = (total, tmax)
+            self.stats["record_slots"] = total
+            return off, max(total, 1), tmax
+        ptotal, ptmax = hint
+        alloc = min(int(ptotal * 1.125) + 65536, self.max_slots - 1)
+        key_limit = 0
+        if thresh is not None:
+            key_limit = min(int(nbins_full), int(ptmax) + 3)
+        w = ST_SITE[site]
+        self.b.record_offsets_async(cap, nstripes, nq, nq_pad, off, thresh, alloc, key_limit,
+                                    self._status[w:w + 2], self._status[ST_PASS:ST_PASS + 1])
+        self._new_hint["sites"][site] = None          # filled in from the status block after the final read
+        self.stats["record_slots"] = alloc
+        return off, alloc, (key_limit - 1 if thresh is not None else None)
+
+    def _alloc_records(self, cap, geo, nq, thresh=None, site=None, nbins_full=0):
+        """Offsets of the per-(stripe, query) record slices and the record buffer.  ST_PASS bit 0 of the status
+        block is raised by the pass when a slice overflows.  With ``thresh`` max(thresh) is returned too."""
+        threads, nq_pad, nstripes, rps = geo
+        off, total, tmax = self._offsets(cap, geo, nq, thresh, site, nbins_full)
+        status = self._status
         rec = dict(off=off, cap=cap, cnt=self.b.zeros((nstripes, nq_pad), torch.int32),
-                   recs=self.b.empty((max(total, 1), 4), torch.int32), err=status[0:1], status=status)
+                   recs=self.b.empty((total, 4), torch.int32), err=status[ST_PASS:ST_PASS + 1], status=status)
         return (rec, tmax) if thresh is not None else rec
 
     def _check_records(self, rec):
@@ -287,19 +375,16 @@ class Evaluator:
         return (self.use_tensor_cores and not ternary and hasattr(self.b, "hamming_select_tc") and
                 nq_pad % 128 == 0 and self.b.tc_code_bytes(q.nbit) > 0)
 
-    def _alloc_cands(self, cap, geo, nq, thresh=None, status=None):
-        """Candidate-list slices per (stripe, query): offsets from the capacities, row / key arrays.  ``status``
-        u32[2]: bit 0 of [0] is raised by the select pass when a slice overflows."""
+    def _alloc_cands(self, cap, geo, nq, thresh=None, site=None, nbins_full=0):
+        """Candidate-list slices per (stripe, query): offsets from the capacities, row / key arrays.  ST_PASS bit 0
+        of the status block is raised by the select pass when a slice overflows.  (``cnt`` needs no zeroing: the
+        select kernel writes the count of every (stripe, query < nq) slice, empty stripes included.)"""
         threads, nq_pad, nstripes, rps = geo
-        off = self.b.empty((nstripes, nq_pad), torch.int32)
-        total, tmax = self.b.record_offsets(cap, nstripes, nq, nq_pad, off, thresh)
-        self.host_syncs += 1
-        self.stats["record_slots"] = total
-        if status is None:
-            status = self.b.zeros((2,), torch.int32)
-        cand = dict(off=off, cap=cap, cnt=self.b.zeros((nstripes, nq_pad), torch.int32),
-                    rows=self.b.empty((max(total, 1),), torch.int32), key=self.b.empty((max(total, 1),), torch.uint8),
-                    err=status[0:1], status=status)
+        off, total, tmax = self._offsets(cap, geo, nq, thresh, site, nbins_full)
+        status = self._status
+        cand = dict(off=off, cap=cap, cnt=self.b.empty((nstripes, nq_pad), torch.int32),
+                    rows=self.b.empty((total,), torch.int32), key=self.b.empty((total,), torch.uint8),
+                    err=status[ST_PASS:ST_PASS + 1], status=status)
         return (cand, tmax) if thresh is not None else cand
 
     def _dense(self, expected_per_query, ndb_total):
@@ -349,24 +434,22 @@ class Evaluator:
 
     def _cand_bases(self, c, cand, nbins, need=None, tot=None, rmax=None):
         """keys + label matches of the candidates -> per-rank key totals -> all-gather -> bases (+ verification
-        that every query has >= ``need`` candidates: status[1]).  ``tot``: totals already accumulated per block."""
+        that every query has >= ``need`` candidates: ST_SHORT).  ``tot``: totals already accumulated per block."""
         b, comm = self.b, self.comm
         threads, nq_pad, nstripes, rps = c["geo"]
         nq = c["nq"]
+        labelled = c["label_mode"] != L.CH_LAB_NONE
         if tot is None:
             tot = b.zeros((2, nbins, nq_pad), torch.int32)
             self._cand_hist(c, cand, nbins, tot)
         tot = comm.all_gather(tot)                                   # (world, 2, nbins, nq_pad)
         base0_all = b.empty((nbins, nq_pad), torch.int32)
-        base0_rel = b.empty((nbins, nq_pad), torch.int32)
-        found = b.zeros((nq_pad,), torch.int32)
+        base0_rel = b.empty((nbins, nq_pad), torch.int32) if labelled else None
         # key_max[q] = smallest key at which the (global) list holds rmax items: larger keys cannot rank below rmax
         key_max = b.empty((nq_pad,), torch.int32) if rmax is not None else None
-        b.scan_bases(tot[:, 0].contiguous(), comm.world, comm.rank, nbins, nq, nq_pad, -1 if rmax is None else rmax,
-                     base0_all, key_max, found)
-        b.scan_bases(tot[:, 1].contiguous(), comm.world, comm.rank, nbins, nq, nq_pad, -1, base0_rel, None, None)
-        if need is not None:
-            b.check_counts(found, nq, need, cand["status"][1:2])
+        b.scan_bases_pair(tot, comm.world, comm.rank, nbins, nq, nq_pad, -1 if rmax is None else rmax,
+                          0 if need is None else need, base0_all, base0_rel, key_max, None,
+                          self._status[ST_SHORT:ST_SHORT + 1])
         return base0_all, base0_rel, key_max
 
     # ------------------------------------------------------------------ the evaluation
@@ -374,7 +457,11 @@ class Evaluator:
                  remove_first_retrieved=False, return_ap=False, zero_mean=False):
         """Returns ``(mAPs list, recalls list, precisions list[, ap (nR, nq) tensor])``.
 
-        ``db_codes`` / ``db_labels`` are THIS rank's contiguous gallery row block; queries are replicated."""
+        ``db_codes`` / ``db_labels`` are THIS rank's contiguous gallery row block; queries are replicated.
+
+        A repeated evaluation of a known shape runs speculatively (see ``__init__``); a query set whose candidate /
+        record slices would need >= 2^32 slots is evaluated in query chunks (AP, hit counts are per-query
+        quantities: the chunk means combine by a weighted mean)."""
         b, comm = self.b, self.comm
         if hasattr(b, "begin"):
             b.begin()
@@ -385,6 +472,82 @@ class Evaluator:
             return [], [], []
         if any(r == 0 or r < -1 for r in r_list) or any(k <= 0 for k in pr_k):
             raise ValueError("R must be -1 or positive; PRs must be positive")
+        args = (db_codes, db_labels, q_codes, q_labels, r_list, threshold, pr_k, remove_first_retrieved, return_ap,
+                zero_mean)
+        key = self._hint_key(*args)
+        hint = self._hints.get(key) if self.speculate else None
+        if comm.world > 1 and self.speculate:
+            # every rank must take the same road (the collectives differ): speculate only if ALL ranks hold a hint.
+            # (The stream is idle here -- the previous evaluation ended with a sync -- so this round trip is cheap.)
+            have = b.full((1,), 0 if hint is None else 1, torch.int32)
+            if self._host_ints(comm.all_reduce_max(-have))[0] != -1:
+                hint = None
+        try:
+            out = self._evaluate(*args, hint=hint)
+            if out is _RETRY:
+                # a stale hint (the data changed under the same shape): once more, asking the device
+                self._hints.pop(key, None)
+                out = self._evaluate(*args, hint=None)
+                self.stats["speculation"] = "retried"
+            else:
+                self.stats["speculation"] = "hit" if hint is not None else "none"
+        except _TooManySlots as e:
+            self._hints.pop(key, None)
+            return self._evaluate_chunked(args, int(e.args[0]))
+        if self.speculate and self._new_hint is not None and self._new_hint.get("complete"):
+            self._hints[key] = self._new_hint
+        self.stats["host_syncs"] = self.host_syncs
+        return out
+
+    def _hint_key(self, db_codes, db_labels, q_codes, q_labels, r_list, threshold, pr_k, rf, return_ap, zero_mean):
+        def sig(t):
+            if t is None:
+                return None
+            dev = getattr(t, "device", None)
+            return (type(t).__name__, tuple(t.shape), str(getattr(t, "dtype", "")), getattr(dev, "type", None),
+                    bool(getattr(t, "is_pinned", lambda: False)()) if getattr(dev, "type", None) == "cpu" else False)
+        knobs = (self.sample_stride, self.sample_two_level, self.sample2_sub, self.sample2_min_rows,
+                 self.sample2_min_work, self.sample_min_rows, self.sample_min_ratio, self.stream_host_gallery,
+                 self.stream_min_rows, self.stream_chunks, self.use_tensor_cores, self.select_dense_override,
+                 self.stripe_rows_override)
+        return (sig(db_codes), sig(db_labels), sig(q_codes), sig(q_labels), tuple(r_list), float(threshold),
+                tuple(pr_k), bool(rf), bool(zero_mean), self.comm.world, knobs)
+
+    def _evaluate_chunked(self, args, total_slots):
+        """The query set in chunks (each small enough for 32-bit slot offsets), combined exactly: every output is a
+        mean over queries of a per-query quantity."""
+        db_codes, db_labels, q_codes, q_labels, r_list, threshold, pr_k, rf, return_ap, zero_mean = args
+        nq = int(q_codes.shape[0])
+        nchunks = min(nq, max(2, int(total_slots // max(1, (self.max_slots * 3) // 8)) + 1))
+        if nq < 2:
+            raise RuntimeError(f"{total_slots} candidate slots for a single query exceed the 32-bit slot index")
+        bounds = [nq * i // nchunks for i in range(nchunks + 1)]
+        maps, recalls, precisions = [0.0] * len(r_list), [0.0] * len(pr_k), [0.0] * len(pr_k)
+        aps, syncs = [], 0
+        for i in range(nchunks):
+            lo, hi = bounds[i], bounds[i + 1]
+            if hi == lo:
+                continue
+            out = self.evaluate(db_codes, db_labels, q_codes[lo:hi], q_labels[lo:hi], r_list, threshold, pr_k, rf,
+                                return_ap, zero_mean)
+            syncs += self.stats.get("host_syncs", 0)
+            wgt = (hi - lo) / nq
+            maps = [a + wgt * v for a, v in zip(maps, out[0])]
+            recalls = [a + wgt * v for a, v in zip(recalls, out[1])]
+            precisions = [a + wgt * v for a, v in zip(precisions, out[2])]
+            if return_ap:
+                aps.append(out[3])
+        self.stats.update(query_chunks=nchunks, host_syncs=syncs)
+        if return_ap:
+            return maps, recalls, precisions, torch.cat(aps, dim=1)
+        return maps, recalls, precisions
+
+    def _evaluate(self, db_codes, db_labels, q_codes, q_labels, r_list, threshold, pr_k, remove_first_retrieved,
+                  return_ap, zero_mean, hint=None):
+        b, comm = self.b, self.comm
+        self._hint = hint
+        self._new_hint = dict(sites={}, complete=False)
+        self.stats.pop("query_chunks", None)
         q, g, ternary, label_mode, lw, nclass, rows = self._prepare(db_codes, db_labels, q_codes, q_labels, threshold,
                                                                     allow_defer=True, zero_mean=zero_mean)
         db_codes = self._db_codes_eff           # (the device copy when zero_mean moved a host gallery)
@@ -430,9 +593,12 @@ class Evaluator:
         if streamed:
             self.stats["mode"] = "topR-sampled-streamed"
             res = self._finish(ctx, self._pass_topr_sampled(ctx, streamed=True))
-            if res[4][0] or res[4][1]:
-                self.stats["sample"].update(fallback=True, overflow=res[4][0], short=res[4][1])
+            if hint is not None and self._stale(res[4]):
+                return _RETRY
+            if res[4][ST_PASS] or res[4][ST_SHORT]:
+                self.stats["sample"].update(fallback=True, overflow=res[4][ST_PASS], short=res[4][ST_SHORT])
                 res, sampled = None, False          # the same sample would fail again: go exact
+                self._status[:ST_CODES].zero_()
         if g.bits is None or res is None and streamed:
             # gallery codes were deferred but the streamed path is not applicable (or gave up): pack them now
             fl = b.zeros((1,), torch.int32)
@@ -444,7 +610,7 @@ class Evaluator:
                 # zeros in the gallery: ternary keys after all -> start over on the regular path
                 saved, self.stream_host_gallery = self.stream_host_gallery, False
                 try:
-                    return self.evaluate(db_codes, db_labels, q_codes, q_labels, R, threshold, PRs,
+                    return self.evaluate(db_codes, db_labels, q_codes, q_labels, r_list, threshold, pr_k,
                                          remove_first_retrieved, return_ap, zero_mean)
                 finally:
                     self.stream_host_gallery = saved
@@ -457,21 +623,53 @@ class Evaluator:
             if sampled:
                 self.stats["mode"] = "topR-sampled"
                 res = self._finish(ctx, self._pass_topr_sampled(ctx))
-                if res[4][0] or res[4][1]:
+                if hint is not None and self._stale(res[4]):
+                    return _RETRY
+                if res[4][ST_PASS] or res[4][ST_SHORT]:
                     # a record slice overflowed or some query has fewer than R candidates under the sampled
                     # threshold: redo the evaluation by the exact two-pass path
-                    self.stats["sample"].update(fallback=True, overflow=res[4][0], short=res[4][1])
+                    self.stats["sample"].update(fallback=True, overflow=res[4][ST_PASS], short=res[4][ST_SHORT])
                     res = None
+                    self._status[:ST_CODES].zero_()
             if res is None:
                 self.stats["mode"] = "topR"
                 res = self._finish(ctx, self._pass_topr_exact(ctx))
         maps, recalls, precisions, ap, flags = res
-        self.stats["host_syncs"] = self.host_syncs
-        if flags[0]:
+        if hint is not None and self._stale(flags):
+            return _RETRY
+        if flags[ST_PASS]:
             raise RuntimeError("internal error: record buffer overflow")
+        self._close_hint(flags)
         if return_ap:
             return maps, recalls, precisions, ap
         return maps, recalls, precisions
+
+    def _stale(self, flags):
+        """did the status block of a speculative run contradict its hint?  (flags = the block, MAX over ranks)"""
+        h = self._hint
+        if flags[ST_PASS] & 12:
+            return True                                  # arena too small / threshold beyond the key range
+        if flags[ST_CODES] & 2:
+            raise ValueError("codes contain NaN")
+        hm = h["mm"]
+        if (flags[ST_CODES] & 1) and not (hm[ST_CODES] & 1):
+            return True                                  # zeros showed up: ternary keys
+        for a, bq in ((ST_QINFO, ST_GINFO),):
+            if max(flags[a], flags[bq]) != max(hm[a], hm[bq]) or max(flags[a + 1], flags[bq + 1]) != max(hm[a + 1], hm[bq + 1]):
+                return True                              # label form / class count changed
+        if self.comm.world > 1 and (list(flags[ST_ROWS:]) != list(h["rows"]) or
+                                     bool(flags[ST_PACKED]) != bool(h["any_packed"])):
+            return True
+        return False
+
+    def _close_hint(self, flags):
+        """the totals the device reported for the speculative allocations become the next hint"""
+        nh = self._new_hint
+        for site, v in list(nh["sites"].items()):
+            if v is None:
+                w = ST_SITE[site]
+                nh["sites"][site] = (int(flags[w]), int(flags[w + 1]))
+        nh["complete"] = True
 
     def _finish(self, c, st):
         """Records -> per-query sums (K4) -> all-reduce -> means.  The status words of the passes come back
@@ -480,7 +678,7 @@ class Evaluator:
         threads, nq_pad, nstripes, rps = c["geo"]
         nq, rf, r_eff, pr_k = c["nq"], c["rf"], c["r_eff"], c["pr_k"]
         ncols = 2 * len(r_eff) + len(pr_k)
-        cols = b.zeros((nq, max(ncols, 1)), torch.float64)
+        cols = b.empty((nq, max(ncols, 1)), torch.float64)       # (every entry is written by the K4 kernels)
         if "cand" in st:
             # candidate lists (tensor-core select pass): ranks straight from the lists
             cand, nbins = st["cand"], st["nbins"]
@@ -551,7 +749,7 @@ class Evaluator:
             b.record_caps(1, slab_rel, None, nstripes, nbins, nq, nq_pad, False, cap)
             slab_all.zero_()
             slab_rel.zero_()
-        rec = self._alloc_records(cap, geo, nq)
+        rec = self._alloc_records(cap, geo, nq, site="all")
         self._hist(q, g, geo, ternary, label_mode, lw, slab_all, slab_rel, emit=L.CH_EMIT_RELEVANT, rec=rec)
         tot = comm.all_gather(torch.stack([self._local_totals(slab_all, geo, nbins),
                                            self._local_totals(slab_rel, geo, nbins)]))
@@ -587,7 +785,7 @@ class Evaluator:
         if self._tc_ok(q, ternary, nq_pad):
             # pass 2 on the tensor cores: candidate lists (exact capacities), ranks from the lists
             del slab_rel
-            cand = self._alloc_cands(cap, geo, nq)
+            cand = self._alloc_cands(cap, geo, nq, site="exact")
             self._select_tc(q, g, geo, thresh, cand, self._dense(1.3 * (c["rmax"] + c["rf"]), c["ndb_total"]))
             base0_all, base0_rel, key_max = self._cand_bases(c, cand, nbins, rmax=c["rmax"] + c["rf"])
             return dict(cand=cand, base0_all=base0_all, base0_rel=base0_rel, total_rel=total_rel, nbins=nbins,
@@ -595,7 +793,7 @@ class Evaluator:
         if label_mode == L.CH_LAB_ID and 0 < c["nclass"] * nstripes <= (1 << 26):
             b.record_caps(2, self._class_counts(c), q.ids, nstripes, c["nclass"], nq, nq_pad, True, cap)
         b.slab_exscan(slab_all, nstripes, nbins, nq_pad)
-        rec = self._alloc_records(cap, geo, nq)
+        rec = self._alloc_records(cap, geo, nq, site="exact")
         scratch_all = b.zeros((nstripes, nbins, nq_pad), torch.int32)
         slab_rel.zero_()
         self._hist(q, g, geo, ternary, label_mode, lw, scratch_all, slab_rel, thresh=thresh,
@@ -713,7 +911,7 @@ class Evaluator:
         need = min(c["rmax"] + c["rf"], c["ndb_total"])
         stride = c["stride"]
         # ---- the sample: every stride-th row of the local shard, same stripes (rps is a multiple of stride) ----
-        status = b.zeros((2,), torch.int32)
+        status = self._status            # [ST_PASS] overflow bits, [ST_SHORT] verification / zeros in a streamed sample
         sp = Packed()
         sp.i8 = None
         sp.nbit = g.nbit
@@ -724,19 +922,17 @@ class Evaluator:
             # consecutive rows (1 KB segments) every run * stride rows -- and pack it
             run = max(1, 256 // g.nbit) if g.nbit in (32, 64, 128, 256) else 1
             ns, view = self._host_sample_view(c["db_codes"], stride, run)
+            zflag = status[ST_SHORT:ST_SHORT + 1]     # a zero / NaN in the streamed codes sends the run to the exact path
             packed, _ = self._timed("pack_host", ns * g.nbit * view.element_size(),
-                                    lambda: b.pack_sign(view, 0.0, status[1:2], False))
+                                    lambda: b.pack_sign(view, 0.0, zflag, False))
             sp.bits = packed.view(-1, q.bits.shape[1])         # (super rows, run * words) -> (rows, words)
-            streamer = self._Streamer(self, c, status[1:2])
+            streamer = self._Streamer(self, c, zflag)
             streamer.side.wait_stream(torch.cuda.current_stream())
         else:
-            ns = (g.n + stride - 1) // stride
-            sp.bits = b.zeros((b.padded_rows(ns), g.bits.shape[1]), torch.int32)
-            sp.bits[:ns] = g.bits[:g.n][::stride]
+            ns, sp.bits = b.gather_rows(g.bits, g.n, g.nbit, stride)
         sp.n = ns
         if ternary:
-            sp.nz = b.zeros((b.padded_rows(ns), g.bits.shape[1]), torch.int32)
-            sp.nz[:ns] = g.nz[:g.n][::stride]
+            _, sp.nz = b.gather_rows(g.nz, g.n, g.nbit, stride)
         sp.ids = sp.masks = sp.info = None
         geo_s = (threads, nq_pad, nstripes, rps // stride)
         if streamed:        # every rank samples the same way (streaming is agreed on by all ranks)
@@ -771,7 +967,7 @@ class Evaluator:
         self.stats["sample"] = dict(stride=stride, rows=ns_total, m=m)
         if tc_pass:
             # ---- the one full pass on the tensor cores: candidate lists, then ranks from the lists ----
-            cand, tmax = self._alloc_cands(cap, geo, nq, thresh, status)    # one host sync: slots + max threshold
+            cand, tmax = self._alloc_cands(cap, geo, nq, thresh, "full", nbins)   # (a host sync unless hinted)
             del slab_s, base_tmp
             nbins = min(nbins, tmax + 1)
             self.stats["sample"]["key_limit"] = nbins
@@ -795,7 +991,7 @@ class Evaluator:
             return dict(cand=cand, base0_all=base0_all, base0_rel=base0_rel, nbins=nbins, key_max=key_max,
                         total_rel=self._total_rel_from_classes(c, cls))
         b.record_caps(2, cls, q.ids, nstripes, c["nclass"], nq, nq_pad, True, cap)
-        rec, tmax = self._alloc_records(cap, geo, nq, thresh, status)   # one host sync: slots + max threshold
+        rec, tmax = self._alloc_records(cap, geo, nq, thresh, "full", nbins)   # (a host sync unless hinted)
         del slab_s, base_tmp
         # ---- the one full pass; only keys <= max threshold can occur, all slabs / bases are that narrow ----
         nbins = min(nbins, tmax + 1)
@@ -810,9 +1006,9 @@ class Evaluator:
                                            self._local_totals(slab_rel, geo, nbins)]))
         b.scan_bases(tot[:, 0].contiguous(), comm.world, comm.rank, nbins, nq, nq_pad, -1, base0_all, None, found)
         b.scan_bases(tot[:, 1].contiguous(), comm.world, comm.rank, nbins, nq, nq_pad, -1, base0_rel, None, None)
-        # ---- verification: status[1] is raised if some query has fewer than `need` candidates; it is read back
+        # ---- verification: ST_SHORT is raised if some query has fewer than `need` candidates; it is read back
         # together with the results (the finalisation below runs speculatively)
-        b.check_counts(found, nq, need, rec["status"][1:2])
+        b.check_counts(found, nq, need, rec["status"][ST_SHORT:ST_SHORT + 1])
         self.stats["sample"]["key_limit"] = nbins
         b.slab_exscan(slab_all, nstripes, nbins, nq_pad)
         b.slab_exscan(slab_rel, nstripes, nbins, nq_pad)
@@ -842,8 +1038,7 @@ class Evaluator:
         sp0 = Packed()
         sp0.i8 = sp0.nz = sp0.ids = sp0.masks = sp0.info = None
         sp0.n, sp0.nbit = ns0, sp.nbit
-        sp0.bits = b.zeros((b.padded_rows(ns0), sp.bits.shape[1]), torch.int32)
-        sp0.bits[:ns0] = sp.bits[:ns][::sub]
+        _, sp0.bits = b.gather_rows(sp.bits, ns, sp.nbit, sub)
         align = getattr(b, "stripe_align", 256)
         geo0 = (threads, nq_pad, 1, max(align, (ns0 + align - 1) // align * align))
         slab0 = b.zeros((1, nbins, nq_pad), torch.int32)
@@ -853,11 +1048,10 @@ class Evaluator:
         m0 = int(mu0 + 5.0 * mu0 ** 0.5 + 4.0) + 1
         thresh0 = b.empty((nq_pad,), torch.int32)
         base_tmp = b.empty((nbins, nq_pad), torch.int32)
-        b.scan_bases(self._summed_totals(slab0[0].clone()), 1, 0, nbins, nq, nq_pad, m0, base_tmp, thresh0, None)
+        tot0 = slab0[0].clone() if comm.world > 1 else slab0[0]        # (the all-reduce works in place)
+        b.scan_bases(self._summed_totals(tot0), 1, 0, nbins, nq, nq_pad, m0, base_tmp, thresh0, None)
         # list capacities of the sample select: the local mini-sample count <= t0, scaled -- for EVERY stripe (the
         # row order may put all neighbours of a query into one stripe)
-        cap0 = b.empty((1, nq_pad), torch.int32)
-        b.record_caps(0, slab0, thresh0, 1, nbins, nq, nq_pad, False, cap0, sample_stride=sub)
         # the sample select has its own stripes: just enough CTAs to fill the GPU (capacity = the whole-sample bound
         # per slice, because the row order may put all neighbours of a query into one stripe)
         tile = getattr(b, "tc_tile_rows", 1)
@@ -868,7 +1062,9 @@ class Evaluator:
         geo1 = (threads, nq_pad, n1, rps1)
         s_i8 = self._timed("expand_i8", 0, lambda: b.expand_i8(sp.bits, q.nbit))
         after_level0()              # (host-blocking work of the caller, while the GPU runs level 0)
-        cand1, tmax0 = self._alloc_cands(cap0.expand(n1, nq_pad).contiguous(), geo1, nq, thresh0, status)
+        cap0 = b.empty((n1, nq_pad), torch.int32)
+        b.record_caps(0, slab0, thresh0, n1, nbins, nq, nq_pad, False, cap0, sample_stride=sub, replicate=True)
+        cand1, tmax0 = self._alloc_cands(cap0, geo1, nq, thresh0, "s1", nbins)
         nb0 = min(nbins, tmax0 + 1)
         # ---- level 1 ----
         q_i8 = self._query_plane(q, nq_pad, thresh0)
@@ -892,6 +1088,8 @@ class Evaluator:
     def _total_rel_from_classes(self, c, cls):
         """relevant items in the whole gallery per query = class frequency of the query's class (single-label)"""
         b, comm, q, nq = self.b, self.comm, c["q"], c["nq"]
+        if not c["pr_k"]:
+            return None
         total_rel = b.zeros((c["geo"][1],), torch.int32)
         if c["pr_k"]:
             cls_tot = cls.sum(0, dtype=torch.int32)
@@ -967,6 +1165,16 @@ class Evaluator:
         b, comm = self.b, self.comm
         if hasattr(b, "begin"):
             b.begin()
+        self.host_syncs = 0
+        self._hint, self._new_hint = None, dict(sites={}, complete=False)
+        try:
+            return self._retrieve(db_codes, q_codes, R, threshold, remove_first_retrieved, zero_mean)
+        except _TooManySlots as e:
+            raise RuntimeError(f"{int(e.args[0])} candidate slots exceed the 32-bit slot index: retrieve the "
+                               "queries in chunks") from None
+
+    def _retrieve(self, db_codes, q_codes, R, threshold, remove_first_retrieved, zero_mean):
+        b, comm = self.b, self.comm
         q, g, ternary, _, _, _, rows = self._prepare(db_codes, None, q_codes, None, threshold, zero_mean=zero_mean)
         nq, nbit = q.n, q.nbit
         nbins = (2 * nbit if ternary else nbit) + 1
@@ -995,7 +1203,10 @@ class Evaluator:
             b.cand_finalize(cand, mode=2, base0_all=base0_c, base0_rel=None, nq=nq, nq_pad=nq_pad, nstripes=nstripes,
                             nbins=nbins, remove_first=bool(rf), ids=ids, keys=keys, R=R, row_offset=row_offset,
                             key_max=key_max)
-            if self._host_ints(cand["err"])[0] != 0:
+            # (group mode: the verdict is agreed on before anybody raises -- a rank that raised alone would leave
+            # the others waiting in the collectives below)
+            err = comm.all_reduce_max(cand["err"].clone()) if comm.world > 1 else cand["err"]
+            if self._host_ints(err)[0] != 0:
                 raise RuntimeError("internal error: candidate list overflow")
             if comm.world > 1:
                 ids = comm.all_reduce_max(ids)
@@ -1010,7 +1221,9 @@ class Evaluator:
                  sbase_all=slab_all, sbase_rel=None, first_rel=None, partial=None, cols=None, nq=nq, nq_pad=nq_pad,
                  nstripes=nstripes, nbins=nbins, remove_first=bool(rf), r_eff=[], pr_k=[])
         b.scatter_ranked(f, R, row_offset, ids, keys)
-        self._check_records(rec)
+        err = comm.all_reduce_max(rec["err"].clone()) if comm.world > 1 else rec["err"]
+        if self._host_ints(err)[0] != 0:
+            raise RuntimeError("internal error: record buffer overflow")
         if comm.world > 1:
             ids = comm.all_reduce_max(ids)
             keys = comm.all_reduce_max(keys)

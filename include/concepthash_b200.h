@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CH_ABI_VERSION 2
+#define CH_ABI_VERSION 3
 #define CH_MAX_NBIT 256          /* words per code: 1, 2, 4 or 8 x u32 */
 #define CH_MAX_R 8               /* length of an `R` list (test_hashing.py:124-128) */
 #define CH_MAX_PR 32             /* length of `PRs` */
@@ -260,12 +260,36 @@ int ch_scan_bases(ch_ws* ws, const uint32_t* tot_all_dev, int world, int rank, i
  */
 int ch_record_caps(ch_ws* ws, int source, const uint32_t* slab_or_cls, const uint32_t* thresh_or_qids,
                    int nstripes, int nbins_or_nclass, int64_t nq, int64_t nq_pad, int min_with_prev,
-                   int sample_stride, uint32_t* cap_dev, void* stream);
+                   int sample_stride, int src_stripes /* nstripes, or 1 = replicate the one source stripe */,
+                   uint32_t* cap_dev, void* stream);
 /* off[s][q] = start[q] + sum_{s' < s} cap[s'][q]; start = exclusive scan of per-query totals;
- * total_host receives the total number of record slots (the call synchronises the stream). */
+ * total_host receives the total number of record slots (the call synchronises the stream).  Offsets are 32-bit:
+ * a total >= 2^32 - 16 is reported, not an error -- the caller splits the query set (AP is per-query). */
 int ch_record_offsets(ch_ws* ws, const uint32_t* cap_dev, int nstripes, int64_t nq, int64_t nq_pad,
                       uint32_t* off_dev, uint64_t* total_host, const uint32_t* thresh_dev /* or NULL */,
                       uint32_t* thresh_max_host /* max(thresh[0..nq)) rides on the same sync */, void* stream);
+/* The same offsets WITHOUT a host round trip (steady state of a repeated evaluation: the caller allocated
+ * `limit_slots` slots from the total of the previous evaluation of this shape).  info_dev[0] = total slots
+ * (saturated to 2^32 - 1), info_dev[1] = max(thresh[0..nq)) -- read back with the results; status_dev |= 4 when
+ * the total exceeds limit_slots (slices that would leave the arena get capacity 0: cap_dev is updated in place),
+ * |= 8 when a threshold reaches key_limit (the narrowed key range the caller sized its arrays for; 0 = no check).
+ * The caller re-runs the evaluation through ch_record_offsets when either bit comes back set. */
+int ch_record_offsets_async(ch_ws* ws, uint32_t* cap_dev, int nstripes, int64_t nq, int64_t nq_pad,
+                            uint32_t* off_dev, const uint32_t* thresh_dev /* or NULL */, uint64_t limit_slots,
+                            uint32_t key_limit, uint32_t* info_dev /* u32[2] or NULL */, uint32_t* status_dev,
+                            void* stream);
+/* ch_scan_bases for the {all, relevant} totals of the candidate lists in one launch: tot (world, 2, nbins,
+ * nq_pad) -> base0_all, base0_rel (NULL: no labels), key_max[q] = smallest key at which the global list holds
+ * rmax items, total_rel[q] (optional), and the verification of a sampled threshold (torch.topk must see at least
+ * R items): status |= 1 if some query holds fewer than `need` candidates (need <= 0: no check). */
+int ch_scan_bases_pair(ch_ws* ws, const uint32_t* tot_dev, int world, int rank, int nbins, int64_t nq,
+                       int64_t nq_pad, int64_t rmax, int64_t need, uint32_t* base0_all_dev,
+                       uint32_t* base0_rel_dev, uint32_t* key_max_dev, uint32_t* total_rel_dev,
+                       uint32_t* status_dev, void* stream);
+/* every stride-th row of a packed bit plane (the row sample that picks the thresholds): out (rows_out_pad, words),
+ * rows beyond ceil(n_src / stride) are zeroed */
+int ch_gather_rows(ch_ws* ws, const uint32_t* bits_dev, int64_t n_src, int nbit, int64_t stride,
+                   uint32_t* out_dev, int64_t rows_out_pad, void* stream);
 /* per-stripe class histogram of single-label gallery ids: cls (nstripes, nclass), zeroed by caller */
 int ch_class_counts(ch_ws* ws, const uint32_t* g_ids, int64_t ndb, int rows_per_stripe, int nclass,
                     uint32_t* cls_dev, void* stream);
@@ -297,8 +321,8 @@ int ch_first_relevant(ch_ws* ws, const ch_final_args* a, uint32_t* first_rel_dev
 int ch_reduce_means(ch_ws* ws, const double* cols_dev, const uint32_t* total_rel_dev,
                     const uint32_t* first_rel_dev, int64_t nq, int nR, int nPR, const int64_t* pr_k,
                     double* ap_out_dev /* (nR, nq) or NULL */, double* out_host,
-                    const uint32_t* flags_dev /* u32[2] or NULL */, uint32_t* flags_host /* same sync */,
-                    void* stream);
+                    const uint32_t* flags_dev /* u32[nflags] or NULL */, uint32_t* flags_host /* same sync */,
+                    int nflags, void* stream);
 /* flags_dev[0] |= 1 if some total_dev[q] < need  (verification of a sampled threshold) */
 int ch_check_counts(ch_ws* ws, const uint32_t* total_dev, int64_t nq, int64_t need, uint32_t* flags_dev,
                     void* stream);

@@ -350,11 +350,14 @@ class EmuBackend:
         if total is not None:
             _u32(total)[...] = cum_incl[-1].astype(np.uint32)
 
-    def record_caps(self, source, a0, a1, nstripes, nb, nq, nq_pad, min_with_prev, cap, sample_stride=0):
+    def record_caps(self, source, a0, a1, nstripes, nb, nq, nq_pad, min_with_prev, cap, sample_stride=0,
+                    replicate=False):
         self.launches += 1
         c = np.zeros((nstripes, nq_pad), dtype=np.uint32)
         if source in (0, 1):
             s = _u32(a0)
+            if replicate:
+                s = np.broadcast_to(s[:1], (nstripes,) + s.shape[1:])
             for q in range(nq):
                 last = int(_u32(a1)[q]) if source == 0 else nb - 1
                 c[:, q] = s[:, :min(last, nb - 1) + 1, q].sum(1)
@@ -378,6 +381,44 @@ class EmuBackend:
         o = start[None, :] + np.cumsum(c, axis=0) - c
         _u32(off)[...] = o.astype(np.uint32)
         return int(rowtot.sum()), (int(_u32(thresh)[:nq].max()) if thresh is not None else None)
+
+    def record_offsets_async(self, cap, nstripes, nq, nq_pad, off, thresh, limit_slots, key_limit, info, status):
+        self.launches += 1
+        c = _u32(cap)
+        o = _u32(off)
+        run, total = 0, int(c.astype(np.int64).sum())
+        for q in range(nq_pad):
+            for s in range(nstripes):
+                if run + int(c[s, q]) > limit_slots:
+                    c[s, q] = 0
+                    o[s, q] = 0
+                else:
+                    o[s, q] = run
+                    run += int(c[s, q])
+        tmax = int(_u32(thresh)[:nq].max()) if thresh is not None else 0
+        if info is not None:
+            _u32(info)[0], _u32(info)[1] = min(total, 0xFFFFFFFF), tmax
+        if total > limit_slots:
+            _u32(status)[0] |= 4
+        if thresh is not None and key_limit and tmax >= key_limit:
+            _u32(status)[0] |= 8
+
+    def scan_bases_pair(self, tot, world, rank, nbins, nq, nq_pad, rmax, need, base0_all, base0_rel, key_max,
+                        total_rel, status):
+        found = torch.zeros(nq_pad, dtype=torch.int32)
+        self.scan_bases(tot[:, 0].contiguous(), world, rank, nbins, nq, nq_pad, rmax, base0_all, key_max, found)
+        if base0_rel is not None:
+            self.scan_bases(tot[:, 1].contiguous(), world, rank, nbins, nq, nq_pad, -1, base0_rel, None, total_rel)
+        self.launches -= 1 if base0_rel is not None else 0
+        if need > 0 and (_u32(found)[:nq] < need).any():
+            _u32(status)[0] |= 1
+
+    def gather_rows(self, bits, n_src, nbit, stride):
+        self.launches += 1
+        n_out = (n_src + stride - 1) // stride
+        out = torch.zeros((self.padded_rows(n_out), bits.shape[1]), dtype=torch.int32)
+        out[:n_out] = bits[:n_src][::stride]
+        return n_out, out
 
     def check_counts(self, total, nq, need, flags):
         self.launches += 1
@@ -451,7 +492,7 @@ class EmuBackend:
                 tr = tr - _u32(first_rel)[:nq]
             recalls.append(float((hits / np.maximum(tr, 1.0)).mean()))
             precisions.append(float((hits / k).mean()))
-        fl = [int(_u32(flags)[0]), int(_u32(flags)[1])] if flags is not None else [0, 0]
+        fl = [int(v) for v in _u32(flags)] if flags is not None else [0, 0]
         return maps, recalls, precisions, fl
 
     def scatter_ranked(self, f, R, row_offset, ids, keys):

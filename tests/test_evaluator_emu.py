@@ -258,3 +258,95 @@ def test_candidate_path_two_level_sample(seed):
     ev = run_case(dd, torch.arange(1600) % 2, qq, torch.tensor([0, 1, 0]), 80, PRs=[1, 5], rps=64, sampled=True,
                   tc=True, two_level=True)
     assert ev.stats["mode"] == "topR" and ev.stats["sample"]["fallback"]
+
+
+# ------------------------------------------------------------------ speculative re-evaluation + query chunking
+def _spec_ev(tc=True):
+    ev = Evaluator(EmuBackend(rows_per_stripe=64, threads=128, tensor_cores=True) if tc else EmuBackend(rows_per_stripe=64))
+    ev.sample_stride, ev.sample_min_rows, ev.sample_min_ratio = 4, 0, 4
+    ev.sample2_min_rows, ev.sample2_min_work, ev.sample2_sub = 0, 0, 4
+    return ev
+
+
+def _oracle(d, dl, q, ql, R, PRs):
+    om, orec, oprec, oaps = mo.calculate_mAP(d, dl, q, ql, R, PRs=PRs, return_per_query=True)
+    return (om if isinstance(om, list) else [om]), orec, oprec, oaps
+
+
+def _check(out, ora):
+    assert np.allclose(out[0], ora[0], atol=1e-12) and np.allclose(out[1], ora[1], atol=1e-12)
+    assert np.allclose(out[2], ora[2], atol=1e-12) and np.allclose(out[3].numpy(), ora[3], atol=1e-12)
+
+
+@pytest.mark.parametrize("R", [20, -1])
+@pytest.mark.parametrize("tc", [True, False])
+def test_second_evaluation_of_a_shape_is_speculative_and_sync_free(R, tc):
+    """The first evaluation of a shape asks the device (label form, list sizes, largest threshold); the second one
+    assumes them, verifies on the device and needs ONE host round trip -- same numbers."""
+    ev = _spec_ev(tc)
+    d, dl, q, ql, _ = synth.make_random_case(23, 700, 32, 5, p=0.3, seed=1)
+    a = ev.evaluate(d, dl, q, ql, [R], 0.0, [1, 5], False, return_ap=True)
+    first = dict(ev.stats)
+    b = ev.evaluate(d, dl, q, ql, [R], 0.0, [1, 5], False, return_ap=True)
+    assert first["speculation"] == "none" and first["host_syncs"] >= 2
+    assert ev.stats["speculation"] == "hit" and ev.stats["host_syncs"] == 1, ev.stats
+    assert ev.stats["mode"] == first["mode"]
+    ora = _oracle(d, dl, q, ql, R, [1, 5])
+    _check(a, ora)
+    _check(b, ora)
+    # new data of the same shape (another seed): still exact, whether the hint held or the run was repeated
+    d2, dl2, q2, ql2, _ = synth.make_random_case(23, 700, 32, 5, p=0.3, seed=2)
+    c = ev.evaluate(d2, dl2, q2, ql2, [R], 0.0, [1, 5], False, return_ap=True)
+    assert ev.stats["speculation"] in ("hit", "retried")
+    _check(c, _oracle(d2, dl2, q2, ql2, R, [1, 5]))
+
+
+def test_stale_hints_are_detected_and_the_run_repeated():
+    ev = _spec_ev()
+    d, dl, q, ql, _ = synth.make_random_case(23, 700, 32, 5, p=0.05, seed=3)      # tight clusters: short lists
+    ev.evaluate(d, dl, q, ql, [20], 0.0, [1, 5], False)
+    # (a) far more candidates under the same shape: p = 0.5 -> distances concentrate, lists grow, thresholds move
+    d2, dl2, q2, ql2, _ = synth.make_random_case(23, 700, 32, 5, p=0.5, seed=4)
+    out = ev.evaluate(d2, dl2, q2, ql2, [20], 0.0, [1, 5], False, return_ap=True)
+    assert ev.stats["speculation"] == "retried", ev.stats
+    _check(out, _oracle(d2, dl2, q2, ql2, 20, [1, 5]))
+    # (b) exact zeros appear (ternary keys)
+    ev.evaluate(d, dl, q, ql, [20], 0.0, [1, 5], False)
+    dz = d.clone()
+    dz[::9, 2] = 0.0
+    out = ev.evaluate(dz, dl, q, ql, [20], 0.0, [1, 5], False, return_ap=True)
+    assert ev.stats["speculation"] == "retried" and ev.stats["ternary"], ev.stats
+    _check(out, _oracle(dz, dl, q, ql, 20, [1, 5]))
+    # (c) the label form changes under the same shapes: one-hot -> multi-hot
+    oh_d, oh_q = synth.one_hot(dl, 5), synth.one_hot(ql, 5)
+    ev.evaluate(d, oh_d, q, oh_q, [20], 0.0, [1, 5], False)
+    mh_d = oh_d.clone()
+    mh_d[::4, 0] = 1
+    out = ev.evaluate(d, mh_d, q, oh_q, [20], 0.0, [1, 5], False, return_ap=True)
+    assert ev.stats["speculation"] == "retried" and ev.stats["label_mode"] == 2, ev.stats
+    _check(out, _oracle(d, mh_d, q, oh_q, 20, [1, 5]))
+    # (d) NaN under a hint still raises
+    ev.evaluate(d, dl, q, ql, [20], 0.0, [1, 5], False)
+    dn = d.clone()
+    dn[5, 5] = float("nan")
+    with pytest.raises(ValueError, match="NaN"):
+        ev.evaluate(dn, dl, q, ql, [20], 0.0, [1, 5], False)
+
+
+@pytest.mark.parametrize("R", [20, -1])
+def test_query_chunking_when_slots_exceed_the_offset_range(R):
+    """A query set whose slices would not fit the 32-bit slot index is evaluated in query chunks, combined exactly
+    (forced here by a tiny slot limit)."""
+    ev = _spec_ev()
+    d, dl, q, ql, _ = synth.make_random_case(37, 700, 32, 5, p=0.3, seed=6)
+    ref = ev.evaluate(d, dl, q, ql, [R], 0.0, [1, 5], False, return_ap=True)
+    slots = ev.stats["record_slots"]
+    ev2 = _spec_ev()
+    ev2.max_slots = max(64, slots // 3)
+    out = ev2.evaluate(d, dl, q, ql, [R], 0.0, [1, 5], False, return_ap=True)
+    assert ev2.stats.get("query_chunks", 0) >= 2, ev2.stats
+    assert out[3].shape == ref[3].shape
+    _check(out, _oracle(d, dl, q, ql, R, [1, 5]))
+    # and again (the chunks now run speculatively)
+    out = ev2.evaluate(d, dl, q, ql, [R], 0.0, [1, 5], False, return_ap=True)
+    _check(out, _oracle(d, dl, q, ql, R, [1, 5]))

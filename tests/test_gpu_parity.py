@@ -351,17 +351,57 @@ def test_cfg4_full_query_set_vs_oracle(H):
 
 def test_cfg5_shard_geometry_vs_oracle(H):
     """BASELINE configs[4] geometry (64-bit, 1000 classes, top-R = 1000; configs/dataset/inat_birds.yaml:4) at a
-    size the oracle can check: 20,500 queries (41 query groups, a partial last tile) x 2,000,077 rows (KB = 96
-    kernel variant, sparse epilogue, stride-64 sample)."""
+    size the oracle can check: 20,500 queries (41 query groups, a partial last tile) x 5,100,077 rows (KB = 96
+    kernel variant, sparse epilogue, stride-64 sample: candidates are < 0.02 % of the gallery, as in cfg5)."""
     ev = H.get_evaluator()
-    d, dl, q, ql, ncls = synth.make_random_case(20_500, 2_000_077, 64, 1000, p=0.30, seed=0, device="cuda")
+    d, dl, q, ql, ncls = synth.make_random_case(20_500, 5_100_077, 64, 1000, p=0.30, seed=0, device="cuda")
     maps, rec, prec, ap = ev.evaluate(d, dl, q, ql, [1000], 0.0, [1, 10], False, return_ap=True)
     assert ev.stats["mode"] == "topR-sampled" and ev.stats["select_kernel"] == "tcgen05", ev.stats
-    assert not ev.stats.get("select_dense"), ev.stats
+    assert not ev.stats.get("select_dense") and ev.stats["sample"]["stride"] == 2 * ev.sample_stride, ev.stats
     _check_subset_against_packed_oracle(H, d, dl, q, ql, 1000, ap)
-    # the same call through the drop-in surface returns the same numbers
+    # the same call through the drop-in surface: a SPECULATIVE re-evaluation of the shape (one host round trip),
+    # bit-identical numbers
     m, rec2, prec2 = H.calculate_mAP(d, dl, q, ql, 1000, PRs=[1, 10])
+    assert ev.stats["speculation"] == "hit" and ev.stats["host_syncs"] == 1, ev.stats
     assert m == maps[0] and rec2 == rec and prec2 == prec
+
+
+def test_speculative_reevaluation_on_gpu(H):
+    """Second evaluation of a shape: no mid-flight host round trips, same numbers; new data of the same shape is
+    either covered by the hint or detected on the device and repeated -- never wrong.  All modes."""
+    ev = H.get_evaluator()
+    for nq, ndb, nbit, ncls, R in [(3000, 300_000, 64, 50, 100), (700, 9000, 32, 20, -1), (900, 40_000, 128, 30, 500)]:
+        runs = []
+        for seed in (5, 5, 6, 7):
+            d, dl, q, ql, _ = synth.make_random_case(nq, ndb, nbit, ncls, p=0.30 if seed < 7 else 0.45, seed=seed,
+                                                     device="cuda")
+            out = ev.evaluate(d, dl, q, ql, [R], 0.0, [1, 10], False, return_ap=True)
+            runs.append((out, dict(ev.stats)))
+            sub = slice(0, 24)
+            om, orec, oprec, oaps = mo.calculate_mAP(d.cpu(), dl.cpu(), q[sub].cpu(), ql[sub].cpu(), R, PRs=[1, 10],
+                                                     return_per_query=True)
+            assert np.allclose(out[3][0][sub].cpu().numpy(), oaps[0], atol=TOL), (nq, seed, ev.stats)
+        assert runs[1][1]["speculation"] == "hit" and runs[1][1]["host_syncs"] == 1, runs[1][1]
+        assert _same(runs[0][0], runs[1][0])
+        assert runs[2][1]["speculation"] in ("hit", "retried") and runs[3][1]["speculation"] in ("hit", "retried")
+
+
+def test_query_chunking_on_gpu(H):
+    """More slots than the 32-bit slot index allows (forced by a small limit): the query set is evaluated in chunks
+    and the result is that of the one-shot run (to the summation order of the final mean)."""
+    ev = H.get_evaluator()
+    d, dl, q, ql, _ = synth.make_random_case(3000, 300_000, 64, 50, p=0.30, seed=11, device="cuda")
+    ref = ev.evaluate(d, dl, q, ql, [100, 1000], 0.0, [1, 10], False, return_ap=True)
+    saved = ev.max_slots
+    try:
+        ev.max_slots = ev.stats["record_slots"] // 3
+        ev._hints.clear()
+        out = ev.evaluate(d, dl, q, ql, [100, 1000], 0.0, [1, 10], False, return_ap=True)
+        assert ev.stats.get("query_chunks", 0) >= 2, ev.stats
+    finally:
+        ev.max_slots = saved
+        ev._hints.clear()
+    assert _same(out, ref)
 
 
 def test_sampled_one_pass_equals_exact_two_pass(H):

@@ -55,6 +55,22 @@ def _worker(rank, world, port, out):
                 ev2.sample2_min_rows, ev2.sample2_min_work, ev2.sample2_sub = 0, 0, 2
                 results["s2"] = ev2.evaluate(ds, dls, q, ql, [15], thr, PRs, rf) + (ev2.stats["mode"],
                                                                                      "sample2" in ev2.stats)
+                # the same call again: both ranks hold a hint -> speculative run (one agreement round trip at the
+                # idle start + the final read), identical numbers; then a smaller slot limit on ONE rank's shard
+                # only must still make BOTH ranks chunk the query set together
+                again = ev2.evaluate(ds, dls, q, ql, [15], thr, PRs, rf)
+                results["spec"] = (again, ev2.stats["speculation"], ev2.stats["host_syncs"])
+                ev3 = Evaluator(EmuBackend(rows_per_stripe=32, threads=128, tensor_cores=True), DistComm())
+                ev3.sample_stride, ev3.sample_min_rows, ev3.sample_min_ratio = 2, 0, 4
+                ev3.speculate = False
+                ev3.evaluate(ds, dls, q, ql, [15], thr, PRs, rf)
+                mine = torch.tensor([ev3.stats["record_slots"]], dtype=torch.int64)
+                both = [torch.zeros_like(mine) for _ in range(world)]
+                dist.all_gather(both, mine)
+                lo, hi = min(int(t) for t in both), max(int(t) for t in both)
+                assert lo < hi                       # uneven shards: only ONE rank's slices exceed the limit below
+                ev3.max_slots = hi                   # (the same constant on every rank, as in the product)
+                results["chunk"] = (ev3.evaluate(ds, dls, q, ql, [15], thr, PRs, rf), ev3.stats.get("query_chunks", 0))
                 # zero_mean_eval: the column mean is that of the WHOLE gallery (sums all-reduced over the ranks)
                 results["zm"] = ev.evaluate(ds + 0.3, dls, q + 0.3, ql, [15], 0.0, [1, 5], False, zero_mean=True)
         if rank == 0:
@@ -91,6 +107,12 @@ def test_two_ranks_match_oracle(tmp_path):
             s2 = results["s2"]
             assert s2[4] and s2[3] in ("topR-sampled", "topR"), s2
             assert np.allclose(s2[0], om, atol=1e-12) and np.allclose(s2[1], orec, atol=1e-12)
+            again, spec, syncs = results["spec"]
+            assert spec == "hit" and syncs == 2, (spec, syncs)
+            assert np.allclose(again[0], om, atol=1e-12) and np.allclose(again[2], oprec, atol=1e-12)
+            chunked, nchunks = results["chunk"]
+            assert nchunks >= 2, nchunks
+            assert np.allclose(chunked[0], om, atol=1e-12) and np.allclose(chunked[1], orec, atol=1e-12)
             dz, qz = mo.zero_mean(d + 0.3, q + 0.3)
             om, orec, oprec = mo.calculate_mAP(dz, dl, qz, ql, 15, PRs=[1, 5])
             zm = results["zm"]
