@@ -259,7 +259,7 @@ def measure(ctx, name, nbit, steps, warmup, *, main, e2e=True, cpu=True):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    def run(fn, steps, warmup, sample_clocks=False):
+    def run(fn, steps, warmup, sample_clocks=False, detail=False):
         out = None
         for _ in range(warmup):
             out = fn()
@@ -269,6 +269,7 @@ def measure(ctx, name, nbit, steps, warmup, *, main, e2e=True, cpu=True):
             sampler.start()
         ev.events = []
         ev.profile = True
+        ev.profile_all = detail
         l0 = ev.b.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -276,7 +277,7 @@ def measure(ctx, name, nbit, steps, warmup, *, main, e2e=True, cpu=True):
             out = fn()
         e1.record()
         barrier()
-        ev.profile = False
+        ev.profile = ev.profile_all = False
         clocks = sampler.stop() if sampler else None
         ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=device)
         if world > 1:
@@ -384,10 +385,19 @@ def measure(ctx, name, nbit, steps, warmup, *, main, e2e=True, cpu=True):
                          "frac": gbs / peaks["hbm_gbs"], "traffic": ncu_traffic("pack_sign_flat_kernel"),
                          "peak_source": peak_src, "ms_per_launch": pack[0] / pack[2], "bytes_per_launch": pack[1]}
     kernel_ms = {k: v[0] / steps for k, v in kinds.items()}
+    # diagnostic pass (NOT the timed region: a bracket around every entry point costs two event records each):
+    # where the rest of the step goes
+    dsteps = 3
+    _, _, _, _, dev_events = run(step_dev, dsteps, 0, detail=True)
+    detail_ms = {}
+    for kind, units, a, b in dev_events:
+        detail_ms[kind] = detail_ms.get(kind, 0.0) + a.elapsed_time(b) / dsteps
     coll_ms = sum(v for k, v in kernel_ms.items() if k.startswith("comm_"))
-    kern_ms = sum(v for k, v in kernel_ms.items() if not k.startswith("comm_"))
+    kern_ms = sum(v for k, v in detail_ms.items() if not k.startswith("comm_"))
     phase_ms = {"kernels": kern_ms, "collectives": coll_ms, "host_and_launch_gaps": max(0.0, ms - kern_ms - coll_ms),
-                "host_syncs_per_step": stats.get("host_syncs")}
+                "host_syncs_per_step": stats.get("host_syncs"),
+                "note": "kernels = every entry point bracketed in a separate diagnostic pass; collectives = NCCL calls "
+                        "bracketed in the timed region; the rest of ms_per_step is host time / launch gaps"}
 
     # e2e: the public call with HOST tensors; H2D of codes + labels and D2H of the result inside.  Led by what the
     # reference's trainers really hand over -- PAGEABLE tensors (trainers/base.py:291-304) -- with pinned beside it.
@@ -448,8 +458,8 @@ def measure(ctx, name, nbit, steps, warmup, *, main, e2e=True, cpu=True):
             "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None, "dtype": dtype,
             "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e_obj, "gpu_launches": launches,
-            "kernel_ms_per_step": kernel_ms, "phase_ms": phase_ms, "parity_check": pc,
-            "roofline": roofline, "roofline_other_passes": roofline_other, "roofline_pack": roofline_pack,
+            "kernel_ms_per_step": kernel_ms, "kernel_ms_detail": detail_ms, "phase_ms": phase_ms,
+            "parity_check": pc, "roofline": roofline, "roofline_other_passes": roofline_other, "roofline_pack": roofline_pack,
             "cpu_baseline": cpu_obj, "tie_order_delta": tie,
         }, ok
     slim = None
@@ -463,7 +473,7 @@ def measure(ctx, name, nbit, steps, warmup, *, main, e2e=True, cpu=True):
         "steps": steps, "warmup": warmup, "ms_per_step": ms, "value": value, "unit": "64-bit comparisons/s",
         "mAP": config["mAP"], "mode": stats.get("mode"), "ndb_per_gpu": config["ndb_per_gpu"],
         "ndb_total": config["ndb_total"], "gpu_launches": launches, "kernel_ms_per_step": kernel_ms,
-        "phase_ms": phase_ms, "clocks": clocks, "roofline": slim, "parity_check": pc, "tie_order_delta": tie,
+        "kernel_ms_detail": detail_ms, "phase_ms": phase_ms, "clocks": clocks, "roofline": slim, "parity_check": pc, "tie_order_delta": tie,
         "e2e": e2e_obj,
     }, ok
 

@@ -80,6 +80,7 @@ SIGNATURES = {
     "ch_cand_caps": (C.c_int, [P, P, P, P, P, P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, P, P]),
     "ch_slab_totals": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int64, P, P]),
     "ch_slab_exscan": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int64, P]),
+    "ch_slab_scan": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int, C.c_int64, P, P]),
     "ch_scan_bases": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, P, P, P, P]),
     "ch_record_caps": (C.c_int, [P, C.c_int, P, P, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
                                  P, P]),

@@ -304,6 +304,14 @@ class CudaBackend:
         L.check(self.lib.ch_slab_exscan(self.ws, _ptr(slab), nstripes, nbins, nq_pad, self._stream()),
                 "ch_slab_exscan")
 
+    def slab_scan(self, slabs, nstripes, nbins, nq_pad):
+        """``slabs`` (nslabs, nstripes, nbins, nq_pad): in-place exclusive scan over the stripes; returns the totals
+        (nslabs, nbins, nq_pad)"""
+        tot = self.empty((slabs.shape[0], nbins, nq_pad), torch.int32)
+        L.check(self.lib.ch_slab_scan(self.ws, _ptr(slabs), int(slabs.shape[0]), nstripes, nbins, nq_pad, _ptr(tot),
+                                      self._stream()), "ch_slab_scan")
+        return tot
+
     def class_counts(self, g_ids, ndb, rows_per_stripe, nclass, cls):
         L.check(self.lib.ch_class_counts(self.ws, _ptr(g_ids), ndb, rows_per_stripe, nclass, _ptr(cls),
                                          self._stream()), "ch_class_counts")

@@ -353,6 +353,31 @@ __global__ void slab_exscan_kernel(uint32_t* __restrict__ slab, int nstripes, lo
   }
 }
 
+// Both slabs of an evaluation in ONE launch: slab (nslabs, nstripes, plane) -> in-place exclusive scan over the
+// stripes (= the stripe bases) and the per-rank totals tot (nslabs, plane).  One thread per (slab, key, query);
+// the stripe values are loaded in independent batches of 8 (the in-place store after every load had made the
+// one-stripe-at-a-time loop a chain of dependent memory round trips).
+__global__ void slab_scan_kernel(uint32_t* __restrict__ slab, int nslabs, int nstripes, long long plane,
+                                 uint32_t* __restrict__ tot) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= plane * nslabs) return;
+  const long long which = i / plane, e = i - which * plane;
+  uint32_t* base = slab + static_cast<size_t>(which) * nstripes * plane + e;
+  uint32_t run = 0;
+  constexpr int B = 8;
+  for (int k0 = 0; k0 < nstripes; k0 += B) {
+    uint32_t v[B];
+#pragma unroll
+    for (int j = 0; j < B; ++j) v[j] = (k0 + j < nstripes) ? base[static_cast<size_t>(k0 + j) * plane] : 0u;
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+      if (k0 + j < nstripes) base[static_cast<size_t>(k0 + j) * plane] = run;
+      run += v[j];
+    }
+  }
+  tot[i] = run;
+}
+
 // per-stripe class histogram of single-label gallery ids
 __global__ void class_counts_kernel(const uint32_t* __restrict__ ids, long long ndb, int rows_per_stripe,
                                     int nclass, uint32_t* __restrict__ cls) {
@@ -404,22 +429,67 @@ struct Geometry {
   size_t smem, smem_total;
 };
 
+// nq_pad: whole CTAs, and -- unless the query set is tiny -- whole 128-query tiles, so that the tensor-core select
+// pass (128 TMEM lanes = 128 queries) can share the arrays of the POPC passes whatever CTA size those use
+long long padded_queries(long long nq, int threads) {
+  const long long n = nq > 0 ? nq : 1;
+  const int unit = (n > 64 && threads < 128) ? 128 : threads;
+  return ch_round_up(n, unit);
+}
+
+// Modelled time of one full-ranking pass for a candidate (threads, stripes): the pair loop (wave-quantised, scaled
+// by the occupancy the CTA size allows) + the slab traffic every stripe costs (a (nbins x nq_pad) plane per slab
+// that is zeroed, flushed by its CTAs, summed and scanned) + a fixed cost per CTA wave.
+double model_cost(ch_ws* ws, long long ndb, int nw, int nbins, int threads, long long per_sm, long long nq_pad,
+                  long long nstripes, long long rps) {
+  const long long nqtiles = nq_pad / threads;
+  const long long ctas = nstripes * nqtiles;
+  const long long slots = per_sm * ws->sm_count;
+  const long long waves = (ctas + slots - 1) / slots;
+  long long resident = (ctas + static_cast<long long>(ws->sm_count) * waves - 1) / (ws->sm_count * waves);
+  if (resident > per_sm) resident = per_sm;
+  if (resident < 1) resident = 1;
+  double occ = static_cast<double>(resident * threads / 32) / 16.0;       // warps per SM the POPC loop needs: ~16
+  if (occ > 1.0) occ = 1.0;
+  const double rate_sm = 0.87 * 16.0 * (ws->clock_khz > 0 ? ws->clock_khz * 1e3 : 1.9e9) / nw;   // pairs / s / SM
+  const double t_pairs = static_cast<double>(waves) * resident * rps * threads / (rate_sm * occ);
+  const double t_slab = static_cast<double>(nstripes) * nbins * nq_pad * 4.0 * 2.0 * 4.0 / 2.5e12;
+  (void)ndb;
+  return t_pairs + t_slab + 3e-6 * waves;
+}
+
 int make_geometry(ch_ws* ws, long long nq, long long ndb, int nbit, bool tern, int lab, int lw, int forced_threads,
                   int forced_stripes, int forced_rows_per_stripe, Geometry* g) {
   const int nw = ch_code_words(nbit);
   if (nw == 0) CH_FAIL("nbit=%d unsupported (1..%d)", nbit, CH_MAX_NBIT);
   const int nbins = (tern ? 2 * nbit : nbit) + 1;
-  g->threads = forced_threads > 0 ? forced_threads : pick_threads(nbins, nq);
   g->tile = tile_rows_for(nw, tern, lab, lw);
-  const SmemPlan p = smem_plan(nbins, g->threads, nw, tern, lab, lw, g->tile);
-  g->smem = p.total_dynamic;
-  g->smem_total = p.total;
-  if (p.total > static_cast<size_t>(ws->max_smem_optin))
-    CH_FAIL("histogram needs %zu bytes of shared memory per CTA (nbit=%d ternary=%d classes/32=%d), device has %d",
-            p.total, nbit, tern ? 1 : 0, lw, ws->max_smem_optin);
-  g->nq_pad = ch_round_up(nq > 0 ? nq : 1, g->threads);
-  g->nqtiles = static_cast<int>(g->nq_pad / g->threads);
   g->flush_tiles = 65535 / g->tile;
+  auto per_sm_of = [&](int threads, SmemPlan* plan) {
+    *plan = smem_plan(nbins, threads, nw, tern, lab, lw, g->tile);
+    // resident CTAs per SM by shared memory (1 KB reserved per CTA) and threads
+    long long per_sm = (228ll * 1024) / static_cast<long long>(plan->total + 1024);  // static + dynamic
+    if (per_sm > 2048 / threads) per_sm = 2048 / threads;
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 32) per_sm = 32;
+    return per_sm;
+  };
+  auto set_threads = [&](int threads) {
+    SmemPlan p;
+    per_sm_of(threads, &p);
+    g->threads = threads;
+    g->smem = p.total_dynamic;
+    g->smem_total = p.total;
+    g->nq_pad = padded_queries(nq, threads);
+    g->nqtiles = static_cast<int>(g->nq_pad / threads);
+    return p.total;
+  };
+  if (forced_stripes > 0 || forced_threads > 0) {
+    const size_t total = set_threads(forced_threads > 0 ? forced_threads : pick_threads(nbins, nq));
+    if (total > static_cast<size_t>(ws->max_smem_optin))
+      CH_FAIL("histogram needs %zu bytes of shared memory per CTA (nbit=%d ternary=%d classes/32=%d), device has %d",
+              total, nbit, tern ? 1 : 0, lw, ws->max_smem_optin);
+  }
   if (forced_stripes > 0) {
     if (forced_rows_per_stripe <= 0 || forced_rows_per_stripe % 256 != 0 ||
         static_cast<long long>(forced_stripes) * forced_rows_per_stripe < ndb)
@@ -428,48 +498,52 @@ int make_geometry(ch_ws* ws, long long nq, long long ndb, int nbit, bool tern, i
     g->nstripes = forced_stripes;
     g->rows_per_stripe = forced_rows_per_stripe;
     return 0;
-  } else {
-    // resident CTAs per SM by shared memory (1 KB reserved per CTA) and threads
-    long long per_sm = (228ll * 1024) / static_cast<long long>(p.total + 1024);  // static + dynamic
-    if (per_sm > 2048 / g->threads) per_sm = 2048 / g->threads;
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 32) per_sm = 32;
+  }
+  // free choice: the (CTA size, stripe count) with the smallest modelled time.  CTA sizes: the largest the
+  // histogram allows and its halves down to 64 queries (more query tiles = fewer, longer stripes for the same
+  // number of CTAs = smaller slabs and less flush traffic -- what small galleries need).
+  const int t_max = forced_threads > 0 ? forced_threads : pick_threads(nbins, nq);
+  int best_t = t_max;
+  long long best_s = 1, best_rps = 256;
+  double best_cost = 1e300;
+  for (int t = t_max; t >= (forced_threads > 0 ? t_max : (t_max < 64 ? t_max : 64)); t /= 2) {
+    SmemPlan p;
+    const long long per_sm = per_sm_of(t, &p);
+    if (p.total > static_cast<size_t>(ws->max_smem_optin)) continue;
+    const long long nq_pad = padded_queries(nq, t);
+    const long long nqtiles = nq_pad / t;
     const long long slots = per_sm * ws->sm_count;
-    const long long max_stripes = ndb > 0 ? (ndb + g->tile - 1) / g->tile : 1;
-    // smallest stripe count in [lo, hi] with the best wave efficiency (>= 2 waves when the gallery allows)
-    long long lo = (2 * slots + g->nqtiles - 1) / g->nqtiles;
-    if (lo < 1) lo = 1;
-    long long hi = (8 * slots + g->nqtiles - 1) / g->nqtiles;
-    if (lo > max_stripes) lo = max_stripes;
+    long long hi = (8 * slots + nqtiles - 1) / nqtiles;
+    const long long max_stripes = ndb > 0 ? (ndb + 255) / 256 : 1;
     if (hi > max_stripes) hi = max_stripes;
     if (hi > 4096) hi = 4096;
-    if (lo > hi) lo = hi;
-    // every stripe costs a (nbins x nq_pad) slab plane that is zeroed, flushed, summed and scanned: take the
-    // SMALLEST stripe count whose last wave is >= 90 % full, else the best one in range
-    long long best = lo;
-    double best_eff = -1.0;
-    for (long long s = lo; s <= hi; ++s) {
-      const long long ctas = s * g->nqtiles;
-      const long long waves = (ctas + slots - 1) / slots;
-      const double eff = static_cast<double>(ctas) / static_cast<double>(waves * slots);
-      if (eff >= 0.90) {
-        best = s;
-        break;
-      }
-      if (eff > best_eff + 1e-9) {
-        best_eff = eff;
-        best = s;
+    if (hi < 1) hi = 1;
+    long long last_s = 0;
+    for (long long s0 = 1; s0 <= hi; ++s0) {
+      long long rps = ndb > 0 ? (ndb + s0 - 1) / s0 : 256;
+      rps = ch_round_up(rps, 256);
+      const long long s_eff = ndb > 0 ? (ndb + rps - 1) / rps : 1;
+      if (s_eff == last_s) continue;
+      last_s = s_eff;
+      // (the measured 83-88 % of the POPC peak belongs to the largest CTA size: a smaller one must win clearly)
+      const double cost = model_cost(ws, ndb, nw, nbins, t, per_sm, nq_pad, s_eff, rps) * (t == t_max ? 1.0 : 1.1);
+      if (cost < best_cost * (1.0 - 1e-9)) {
+        best_cost = cost;
+        best_t = t;
+        best_s = s_eff;
+        best_rps = rps;
       }
     }
-    g->nstripes = static_cast<int>(best);
   }
+  const size_t total = set_threads(best_t);
+  if (total > static_cast<size_t>(ws->max_smem_optin))
+    CH_FAIL("histogram needs %zu bytes of shared memory per CTA (nbit=%d ternary=%d classes/32=%d), device has %d",
+            total, nbit, tern ? 1 : 0, lw, ws->max_smem_optin);
   // stripe boundaries are multiples of 256 rows (>= every tile size, so every pass of one evaluation --
   // whatever its label mode -- sees the same stripes and every bulk copy starts 16-byte aligned)
-  long long rps = ndb > 0 ? (ndb + g->nstripes - 1) / g->nstripes : 256;
-  rps = ch_round_up(rps, 256);
-  if (rps > 0x7fffff00ll) CH_FAIL("gallery shard too large for one stripe");
-  g->rows_per_stripe = static_cast<int>(rps);
-  g->nstripes = ndb > 0 ? static_cast<int>((ndb + rps - 1) / rps) : 1;
+  if (best_rps > 0x7fffff00ll) CH_FAIL("gallery shard too large for one stripe");
+  g->rows_per_stripe = static_cast<int>(best_rps);
+  g->nstripes = static_cast<int>(best_s);
   return 0;
 }
 
@@ -552,6 +626,18 @@ extern "C" int ch_slab_exscan(ch_ws* ws, uint32_t* slab, int nstripes, int nbins
   const long long plane = static_cast<long long>(nbins) * nq_pad;
   slab_exscan_kernel<<<static_cast<unsigned>((plane + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       slab, nstripes, plane);
+  CH_LAUNCH_CHECK(ws);
+  return 0;
+}
+
+extern "C" int ch_slab_scan(ch_ws* ws, uint32_t* slab, int nslabs, int nstripes, int nbins, int64_t nq_pad,
+                            uint32_t* tot_dev, void* stream) {
+  if (ws == nullptr || slab == nullptr || tot_dev == nullptr) CH_FAIL("null argument to ch_slab_scan");
+  if (nslabs < 1 || nslabs > 2 || nstripes < 1) CH_FAIL("bad arguments to ch_slab_scan");
+  ChDeviceGuard guard(ws->device);
+  const long long plane = static_cast<long long>(nbins) * nq_pad;
+  slab_scan_kernel<<<static_cast<unsigned>((plane * nslabs + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      slab, nslabs, nstripes, plane, tot_dev);
   CH_LAUNCH_CHECK(ws);
   return 0;
 }

@@ -679,7 +679,7 @@ extern "C" int ch_finalize_records(ch_ws* ws, const ch_final_args* a, void* stre
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const FinalDev d = to_dev(a);
   const int ncols = 2 * a->nR + a->nPR;
-  CH_CUDA(cudaMemsetAsync(a->partial, 0, static_cast<size_t>(a->nstripes) * a->nq_pad * ncols * sizeof(double), st));
+  // (no memset of `partial`: finalize_kernel writes every (stripe, query < nq) row, reduce_stripes reads only those)
   finalize_kernel<<<blocks_for(static_cast<long long>(a->nstripes) * a->nq_pad, 128), 128, 0, st>>>(d);
   CH_LAUNCH_CHECK(ws);
   reduce_stripes_kernel<<<blocks_for(a->nq * ncols, 256), 256, 0, st>>>(a->partial, a->nstripes, a->nq, a->nq_pad,

@@ -110,7 +110,7 @@ class _TimedBackend:
     def __getattr__(self, name):
         attr = getattr(self._b, name)
         ev = self._ev
-        if not ev.profile or ev._bracket_open or name in self._PLAIN or not callable(attr):
+        if not (ev.profile and ev.profile_all) or ev._bracket_open or name in self._PLAIN or not callable(attr):
             return attr
         return lambda *a, **k: ev._timed("k_" + name, 0, lambda: attr(*a, **k))
 
@@ -120,7 +120,8 @@ class _TimedBackend:
 
 class Evaluator:
     def __init__(self, backend, comm=None):
-        self.profile = False               # bench: bracket the kernels with CUDA events on the launch stream
+        self.profile = False               # bench: bracket the main kernels with CUDA events on the launch stream
+        self.profile_all = False           # ... and every other entry point too (diagnostic pass: the brackets cost)
         self._bracket_open = False
         self.b = _TimedBackend(self, backend)
         self.comm = comm if comm is not None else LocalComm()
@@ -735,11 +736,8 @@ class Evaluator:
         b, comm, q, g, geo = self.b, self.comm, c["q"], c["g"], c["geo"]
         threads, nq_pad, nstripes, rps = geo
         nbins, nq, label_mode, lw, ternary = c["nbins"], c["nq"], c["label_mode"], c["lw"], c["ternary"]
-        slab_all = b.zeros((nstripes, nbins, nq_pad), torch.int32)
-        slab_rel = b.zeros((nstripes, nbins, nq_pad), torch.int32)
-        base0_all = b.empty((nbins, nq_pad), torch.int32)
-        base0_rel = b.empty((nbins, nq_pad), torch.int32)
-        total_rel = b.zeros((nq_pad,), torch.int32)
+        slabs = b.zeros((2, nstripes, nbins, nq_pad), torch.int32)        # {all, relevant}: one fill, one scan
+        slab_all, slab_rel = slabs[0], slabs[1]
         cap = b.empty((nstripes, nq_pad), torch.int32)
         if label_mode == L.CH_LAB_ID and 0 < c["nclass"] * nstripes <= (1 << 26):
             b.record_caps(2, self._class_counts(c), q.ids, nstripes, c["nclass"], nq, nq_pad, False, cap)
@@ -747,16 +745,15 @@ class Evaluator:
             # capacities from a counting pass (multi-hot labels, or too many classes for the table)
             self._hist(q, g, geo, ternary, label_mode, lw, slab_all, slab_rel)
             b.record_caps(1, slab_rel, None, nstripes, nbins, nq, nq_pad, False, cap)
-            slab_all.zero_()
-            slab_rel.zero_()
+            slabs.zero_()
         rec = self._alloc_records(cap, geo, nq, site="all")
         self._hist(q, g, geo, ternary, label_mode, lw, slab_all, slab_rel, emit=L.CH_EMIT_RELEVANT, rec=rec)
-        tot = comm.all_gather(torch.stack([self._local_totals(slab_all, geo, nbins),
-                                           self._local_totals(slab_rel, geo, nbins)]))
-        b.scan_bases(tot[:, 0].contiguous(), comm.world, comm.rank, nbins, nq, nq_pad, -1, base0_all, None, None)
-        b.scan_bases(tot[:, 1].contiguous(), comm.world, comm.rank, nbins, nq, nq_pad, -1, base0_rel, None, total_rel)
-        b.slab_exscan(slab_all, nstripes, nbins, nq_pad)
-        b.slab_exscan(slab_rel, nstripes, nbins, nq_pad)
+        tot = comm.all_gather(b.slab_scan(slabs, nstripes, nbins, nq_pad))      # (world, 2, nbins, nq_pad)
+        base0_all = b.empty((nbins, nq_pad), torch.int32)
+        base0_rel = b.empty((nbins, nq_pad), torch.int32)
+        total_rel = b.empty((nq_pad,), torch.int32)
+        b.scan_bases_pair(tot, comm.world, comm.rank, nbins, nq, nq_pad, -1, 0, base0_all, base0_rel, None, total_rel,
+                          None)
         return dict(rec=rec, base0_all=base0_all, base0_rel=base0_rel, sbase_all=slab_all, sbase_rel=slab_rel,
                     total_rel=total_rel)
 

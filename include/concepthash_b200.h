@@ -236,6 +236,10 @@ int ch_cand_caps(ch_ws* ws, const uint32_t* cand_off, const uint32_t* cand_cnt, 
 int ch_slab_totals(ch_ws* ws, const uint32_t* slab, int nstripes, int nbins, int64_t nq_pad,
                    uint32_t* tot_dev, void* stream);
 int ch_slab_exscan(ch_ws* ws, uint32_t* slab, int nstripes, int nbins, int64_t nq_pad, void* stream);
+/* both steps for the {all, relevant} slabs of a full-ranking pass in one launch: slab (nslabs, nstripes, nbins,
+ * nq_pad) is scanned in place over the stripes, tot (nslabs, nbins, nq_pad) receives the per-rank totals */
+int ch_slab_scan(ch_ws* ws, uint32_t* slab, int nslabs, int nstripes, int nbins, int64_t nq_pad,
+                 uint32_t* tot_dev, void* stream);
 
 /* ---- K3: exact top-R selection ----------------------------------------------------------------
  * Counting half of `torch.topk` finished: from the per-rank totals (all-gathered over ranks, laid out

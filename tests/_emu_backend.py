@@ -323,6 +323,14 @@ class EmuBackend:
         s[1:] = c[:-1]
         s[0] = 0
 
+    def slab_scan(self, slabs, nstripes, nbins, nq_pad):
+        tot = torch.zeros((slabs.shape[0], nbins, nq_pad), dtype=torch.int32)
+        for i in range(slabs.shape[0]):
+            self.slab_totals(slabs[i], nstripes, nbins, nq_pad, tot[i])
+            self.slab_exscan(slabs[i], nstripes, nbins, nq_pad)
+        self.launches -= 2 * slabs.shape[0] - 1
+        return tot
+
     def class_counts(self, g_ids, ndb, rows_per_stripe, nclass, cls):
         self.launches += 1
         ids, c = _u32(g_ids)[:ndb], _u32(cls)
