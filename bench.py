@@ -285,7 +285,8 @@ def measure(ctx, name, nbit, steps, warmup, *, main, e2e=True, cpu=True):
         return float(ms.item()), out, ev.b.launch_count() - l0, clocks, list(ev.events)
 
     # value: inputs resident in HBM (fp32 codes + int64 ids as torch CUDA tensors)
-    step_dev = lambda: ev.evaluate(d, dl, q, ql, r_list, 0.0, [], False)
+    thr = float(ctx.get("threshold", 0.0)) if main else 0.0
+    step_dev = lambda: ev.evaluate(d, dl, q, ql, r_list, thr, [], False)
     ms, out, launches, clocks, events = run(step_dev, steps, warmup, sample_clocks=True)
     value = total_pairs * unit64 / (ms * 1e-3)
     stats = dict(ev.stats)
@@ -405,7 +406,7 @@ def measure(ctx, name, nbit, steps, warmup, *, main, e2e=True, cpu=True):
     if e2e:
         es, ew = max(2, steps // 2), 2
         pd, pdl, pq, pql = (t.cpu() for t in (d, dl, q, ql))
-        step_page = lambda: hashing.calculate_mAP(pd, pdl, pq, pql, w["R"], group=group)
+        step_page = lambda: hashing.calculate_mAP(pd, pdl, pq, pql, w["R"], threshold=thr, group=group)
         ms_p, out_p, _, _, ev_p = run(step_page, es, ew)
         kinds_p = {}
         for kind, units, a, b in ev_p:
@@ -413,7 +414,7 @@ def measure(ctx, name, nbit, steps, warmup, *, main, e2e=True, cpu=True):
         mode_p = ev.stats.get("mode")
         hd, hdl, hq, hql = (t.pin_memory() for t in (pd, pdl, pq, pql))
         del pd, pdl, pq, pql
-        step_host = lambda: hashing.calculate_mAP(hd, hdl, hq, hql, w["R"], group=group)
+        step_host = lambda: hashing.calculate_mAP(hd, hdl, hq, hql, w["R"], threshold=thr, group=group)
         ms_e, out_e, _, _, _ = run(step_host, es, ew)
         h2d = sum(t.numel() * t.element_size() for t in (hd, hdl, hq, hql))
         del hd, hdl, hq, hql
@@ -424,7 +425,10 @@ def measure(ctx, name, nbit, steps, warmup, *, main, e2e=True, cpu=True):
                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 * len(r_list) + 64,
                    "mAP": out_p[0], "mAP_pinned": out_e[0], "mode": mode_p, "kernel_ms_per_step": kinds_p}
 
-    pc, ok = parity_check(ev, w, d, dl, q, ql, rank, world, device)
+    if thr == 0.0:
+        pc, ok = parity_check(ev, w, d, dl, q, ql, rank, world, device)
+    else:
+        pc, ok = {"skipped": "ternary codes (--threshold): the packed-bit oracle is binary; see tests"}, True
 
     cpu_obj = None
     if cpu and rank == 0 and world == 1:
@@ -439,7 +443,7 @@ def measure(ctx, name, nbit, steps, warmup, *, main, e2e=True, cpu=True):
 
     config = {"workload": w["desc"], "nq": w["nq"], "ndb_per_gpu": int(d.shape[0]),
               "ndb_total": int(ndb_full if w["scaling"] == "strong" else ndb_full * world),
-              "nbit": w["nbit"], "R": w["R"], "nclass": w["nclass"],
+              "nbit": w["nbit"], "R": w["R"], "nclass": w["nclass"], "ternary_threshold": thr,
               "pairs_per_s": total_pairs / (ms * 1e-3),
               "mode": stats.get("mode"), "geometry(threads,nq_pad,stripes,rows/stripe)": stats.get("geometry"),
               "l2_policy": "inputs larger than L2 (fp32 gallery codes >= 512 MB vs 126 MB L2)"
@@ -490,6 +494,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip the other_workloads block")
     ap.add_argument("--sample-stride", type=int, default=0, help="override the evaluator's row-sample stride")
+    ap.add_argument("--threshold", type=float, default=0.0,
+                    help="ternary_threshold (configs/val.yaml:12): |code| < threshold -> 0; the packed-bit oracle of "
+                         "parity_check handles binary codes only, so the check is skipped (tests cover ternary)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3 if args.impl == "ours" else args.warmup
@@ -550,7 +557,7 @@ def main():
     peaks, peak_src = measured_peaks()
     popc_peak, _ = ev.b.popc_peak()
     ctx = dict(rank=rank, world=world, device=device, group=group, ev=ev, peaks=peaks, peak_src=peak_src,
-               popc_peak=popc_peak)
+               popc_peak=popc_peak, threshold=args.threshold)
 
     line, ok_all = measure(ctx, args.workload, args.nbit, args.steps, args.warmup, main=True,
                            e2e=not args.no_e2e, cpu=not args.no_cpu_baseline)

@@ -41,8 +41,8 @@ class SelectArgs(C.Structure):
 
 
 class CandArgs(C.Structure):
-    _fields_ = [(n, P) for n in ("cand_off", "cand_cnt", "cand_rows", "cand_key", "q_bits", "g_bits", "g_plane", "q_lab",
-                                 "g_lab",
+    _fields_ = [(n, P) for n in ("cand_off", "cand_cnt", "cand_rows", "cand_key", "q_bits", "g_bits", "q_nz", "g_nz",
+                                 "g_plane", "q_lab", "g_lab",
                                  "tot_all", "tot_rel", "base0_all", "base0_rel", "first_rel", "first_rel_out", "key_max", "cols",
                                  "ids", "keys", "err_flag")] + \
                [(n, C.c_int64) for n in ("nq", "nq_pad", "R", "row_offset")] + \
@@ -71,7 +71,7 @@ SIGNATURES = {
     "ch_hamming_hist": (C.c_int, [P, C.POINTER(HistArgs), P]),
     "ch_tc_code_bytes": (C.c_int, [C.c_int]),
     "ch_tc_queries_per_cta": (C.c_int, []),
-    "ch_expand_i8": (C.c_int, [P, P, C.c_int64, C.c_int, P, C.c_int64, P, C.c_int64, P]),
+    "ch_expand_i8": (C.c_int, [P, P, P, C.c_int64, C.c_int, C.c_int, P, C.c_int64, P, C.c_int64, P]),
     "ch_hamming_select_tc": (C.c_int, [P, C.POINTER(SelectArgs), P]),
     "ch_cand_hist": (C.c_int, [P, C.POINTER(CandArgs), P]),
     "ch_gather_plane_words": (C.c_int, [C.c_int]),

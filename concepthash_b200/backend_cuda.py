@@ -194,19 +194,20 @@ class CudaBackend:
     def expand_i8_into(self, bits, nbit, out):
         """gallery plane of a row block: ``bits`` (rows, words) -> ``out`` (rows, kb) views of larger arrays"""
         assert bits.shape[0] % 32 == 0 and out.shape[0] >= bits.shape[0]
-        L.check(self.lib.ch_expand_i8(self.ws, _ptr(bits), int(bits.shape[0]), nbit, _ptr(out), int(bits.shape[0]),
-                                      None, 0, self._stream()), "ch_expand_i8")
+        L.check(self.lib.ch_expand_i8(self.ws, _ptr(bits), None, int(bits.shape[0]), nbit, 0, _ptr(out),
+                                      int(bits.shape[0]), None, 0, self._stream()), "ch_expand_i8")
 
-    def expand_i8(self, bits, nbit, min_rows=0, thresh=None, nq=0):
-        """packed sign bits (rows_pad, words) -> +-1 int8 plane in the tiled operand order (rows, kb) int8, with the
-        threshold slots: gallery plane when ``thresh`` is None, else the query plane of ``nq`` queries.
+    def expand_i8(self, bits, nbit, min_rows=0, thresh=None, nq=0, nz=None):
+        """packed sign bits (rows_pad, words) -> {-1, 0, +1} int8 plane in the tiled operand order (rows, kb) int8,
+        with the threshold slots: gallery plane when ``thresh`` is None, else the query plane of ``nq`` queries.
+        ``nz``: the non-zero plane of ternary codes (thresholds are then on the doubled key scale).
         ``min_rows`` over-allocates so that whole 128-query tiles can be read."""
         kb = self.tc_code_bytes(nbit)
         rows_pad = int(bits.shape[0])
         rows = max(rows_pad, (int(min_rows) + 31) // 32 * 32)
         out = self.empty((rows, kb), torch.int8)
-        L.check(self.lib.ch_expand_i8(self.ws, _ptr(bits), rows_pad, nbit, _ptr(out), rows, _ptr(thresh), int(nq),
-                                      self._stream()), "ch_expand_i8")
+        L.check(self.lib.ch_expand_i8(self.ws, _ptr(bits), _ptr(nz), rows_pad, nbit, 0 if nz is None else 1, _ptr(out),
+                                      rows, _ptr(thresh), int(nq), self._stream()), "ch_expand_i8")
         return out
 
     def hamming_select_tc(self, *, q_i8, g_i8, cand, nq, nq_pad, ndb, nbit, nstripes, rows_per_stripe, row_base=0,
@@ -248,10 +249,12 @@ class CudaBackend:
         return out
 
     def cand_hist(self, cand, *, q_bits, g_bits, q_lab, g_lab, label_mode, mask_words, tot_all, tot_rel, nq, nq_pad,
-                  nstripes, nbins, nbit, stripe0=0, g_plane=None):
-        """totals are accumulated; ``stripe0`` / ``nstripes`` select a block of stripes of the list"""
-        a = self._cand_args(cand, nq, nq_pad, nstripes, nbins, stripe0, g_plane=g_plane, q_bits=q_bits, g_bits=g_bits, q_lab=q_lab, g_lab=g_lab,
-                            label_mode=label_mode, mask_words=mask_words, tot_all=tot_all, tot_rel=tot_rel, nbit=nbit)
+                  nstripes, nbins, nbit, stripe0=0, g_plane=None, q_nz=None, g_nz=None):
+        """totals are accumulated; ``stripe0`` / ``nstripes`` select a block of stripes of the list; ``q_nz`` /
+        ``g_nz``: non-zero planes of ternary codes (keys = 2 x distance)"""
+        a = self._cand_args(cand, nq, nq_pad, nstripes, nbins, stripe0, g_plane=g_plane, q_bits=q_bits,
+                            g_bits=g_bits, q_nz=q_nz, g_nz=g_nz, q_lab=q_lab, g_lab=g_lab, label_mode=label_mode,
+                            mask_words=mask_words, tot_all=tot_all, tot_rel=tot_rel, nbit=nbit)
         L.check(self.lib.ch_cand_hist(self.ws, C.byref(a), self._stream()), "ch_cand_hist")
 
     def cand_finalize(self, cand, *, mode, base0_all, base0_rel, nq, nq_pad, nstripes, nbins, remove_first=False,

@@ -18,8 +18,9 @@ namespace {
 
 struct CandDev {
   const uint32_t* cand_off; const uint32_t* cand_cnt;
-  uint32_t* cand_rows; uint8_t* cand_key;
+  uint32_t* cand_rows; uint16_t* cand_key;
   const uint32_t* q_bits; const uint32_t* g_bits;
+  const uint32_t* q_nz; const uint32_t* g_nz;   // non-zero planes (ternary codes: keys on the doubled scale) or NULL
   const uint32_t* g_plane;   // (rows, PW) [code words | class id | pad]: one sector per candidate; or NULL
   const uint32_t* q_lab; const uint32_t* g_lab;
   uint32_t* tot_all; uint32_t* tot_rel;
@@ -29,7 +30,7 @@ struct CandDev {
   double* cols; long long* ids; int* keys;
   uint32_t* err_flag;
   long long nq, nq_pad, R, row_offset;
-  int nstripes, nbins, label_mode, lw, remove_first, nR, nPR, mode;
+  int nstripes, nbins, nbit, label_mode, lw, remove_first, nR, nPR, mode;
   long long r_eff[CH_MAX_R];
   long long pr_k[CH_MAX_PR];
 };
@@ -53,6 +54,23 @@ __device__ __forceinline__ uint32_t key_of(const uint32_t (&qw)[W], const uint32
 #pragma unroll
   for (int w = 0; w < W; ++w) key += __popc(qw[w] ^ gw[w]);
   return key;
+}
+
+// ternary codes: key = 2 x distance = nbit - #(both non-zero) + 2 #(both non-zero and signs differ)
+template <int W>
+__device__ __forceinline__ uint32_t key_of_ternary(const uint32_t (&qw)[W], const uint32_t (&qz)[W],
+                                                   const uint32_t* __restrict__ g_bits,
+                                                   const uint32_t* __restrict__ g_nz, uint32_t row, int nbit) {
+  uint32_t both = 0, dis = 0;
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    const uint32_t gb = __ldg(g_bits + static_cast<size_t>(row) * W + w);
+    const uint32_t gz = __ldg(g_nz + static_cast<size_t>(row) * W + w);
+    const uint32_t m = qz[w] & gz;
+    both += __popc(m);
+    dis += __popc((qw[w] ^ gb) & m);
+  }
+  return static_cast<uint32_t>(nbit) - both + 2u * dis;
 }
 
 // words per row of the gather plane: the code words + the class id, rounded up to a power of two (8 .. 64 bytes)
@@ -99,9 +117,13 @@ __global__ void __launch_bounds__(kCandWarps * 32) cand_hist_kernel(const CandDe
   uint32_t* h_all = sh + static_cast<size_t>(wip) * 2 * a.nbins;
   uint32_t* h_rel = h_all + a.nbins;
   for (int b = lane; b < 2 * a.nbins; b += 32) h_all[b] = 0u;
-  uint32_t qw[W];
+  uint32_t qw[W], qz[W];
+  const bool tern = a.q_nz != nullptr;
 #pragma unroll
-  for (int w = 0; w < W; ++w) qw[w] = a.q_bits[q * W + w];
+  for (int w = 0; w < W; ++w) {
+    qw[w] = a.q_bits[q * W + w];
+    qz[w] = tern ? a.q_nz[q * W + w] : 0xffffffffu;
+  }
   const uint32_t qid = a.label_mode == CH_LAB_ID ? a.q_lab[q] : 0u;
   const uint32_t* qm = a.label_mode == CH_LAB_MASK ? a.q_lab + q * a.lw : nullptr;
   bool bad = false;
@@ -128,7 +150,8 @@ __global__ void __launch_bounds__(kCandWarps * 32) cand_hist_kernel(const CandDe
           rel[u] = ok[u] && id == qid;
           continue;
         }
-        key[u] = ok[u] ? key_of<W>(qw, a.g_bits, row[u]) : 0u;
+        if (tern) key[u] = ok[u] ? key_of_ternary<W>(qw, qz, a.g_bits, a.g_nz, row[u], a.nbit) : 0u;
+        else key[u] = ok[u] ? key_of<W>(qw, a.g_bits, row[u]) : 0u;
         if (ok[u]) {
           if (a.label_mode == CH_LAB_ID) {
             rel[u] = __ldg(a.g_lab + row[u]) == qid;
@@ -149,7 +172,7 @@ __global__ void __launch_bounds__(kCandWarps * 32) cand_hist_kernel(const CandDe
         } else {
           bad = true;
         }
-        a.cand_key[off + i] = static_cast<uint8_t>(key[u]);
+        a.cand_key[off + i] = static_cast<uint16_t>(key[u]);
         if (rel[u]) a.cand_rows[off + i] = row[u] | 0x80000000u;
       }
     }
@@ -299,7 +322,7 @@ __global__ void __launch_bounds__(kCandWarps * 32) cand_final_kernel(const CandD
 // record_caps_kernel.  One warp per query, per-stripe counters in shared memory.
 __global__ void __launch_bounds__(kCandWarps * 32) cand_caps_kernel(
     const uint32_t* __restrict__ off, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ rows,
-    const uint8_t* __restrict__ key, const uint32_t* __restrict__ thresh, int list_stripes, int rows_per_stripe,
+    const uint16_t* __restrict__ key, const uint32_t* __restrict__ thresh, int list_stripes, int rows_per_stripe,
     int nstripes, long long nq, long long nq_pad, int stride, uint32_t* __restrict__ cap) {
   extern __shared__ uint32_t sh[];                       // per warp: nstripes counters
   const int wip = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -337,11 +360,15 @@ int to_dev(const ch_cand_args* a, CandDev* d) {
   if (a->cand_off == nullptr || a->cand_cnt == nullptr || a->cand_rows == nullptr || a->cand_key == nullptr)
     CH_FAIL("null candidate arrays");
   if (a->nR < 0 || a->nR > CH_MAX_R || a->nPR < 0 || a->nPR > CH_MAX_PR) CH_FAIL("too many R / PRs entries");
-  if (a->nbins <= 0 || a->nbins > 257) CH_FAIL("bad nbins %d", a->nbins);
+  if (a->nbins <= 0 || a->nbins > 2 * CH_MAX_NBIT + 1) CH_FAIL("bad nbins %d", a->nbins);
   if (a->nq <= 0 || a->nq_pad < a->nq || a->nstripes <= 0) CH_FAIL("bad candidate geometry");
   d->cand_off = a->cand_off; d->cand_cnt = a->cand_cnt; d->cand_rows = a->cand_rows; d->cand_key = a->cand_key;
   d->q_bits = a->q_bits; d->g_bits = a->g_bits; d->q_lab = a->q_lab; d->g_lab = a->g_lab;
-  d->g_plane = a->label_mode == CH_LAB_ID ? a->g_plane : nullptr;
+  d->q_nz = a->q_nz; d->g_nz = a->q_nz != nullptr ? a->g_nz : nullptr;
+  if (a->q_nz != nullptr && a->g_nz == nullptr) CH_FAIL("ternary keys need both non-zero planes");
+  d->nbit = a->nbit;
+  // the gather plane holds [code | class id]: binary single-label shards only
+  d->g_plane = (a->label_mode == CH_LAB_ID && a->q_nz == nullptr) ? a->g_plane : nullptr;
   d->tot_all = a->tot_all; d->tot_rel = a->tot_rel; d->base0_all = a->base0_all; d->base0_rel = a->base0_rel;
   d->first_rel = a->first_rel; d->first_rel_out = a->first_rel_out; d->cols = a->cols;
   d->key_max = a->key_max;
@@ -403,7 +430,7 @@ extern "C" int ch_cand_hist(ch_ws* ws, const ch_cand_args* a, void* stream) {
 }
 
 extern "C" int ch_cand_caps(ch_ws* ws, const uint32_t* cand_off, const uint32_t* cand_cnt, const uint32_t* cand_rows,
-                            const uint8_t* cand_key, const uint32_t* thresh, int list_stripes, int rows_per_stripe,
+                            const uint16_t* cand_key, const uint32_t* thresh, int list_stripes, int rows_per_stripe,
                             int nstripes, int64_t nq, int64_t nq_pad, int sample_stride, uint32_t* cap_dev,
                             void* stream) {
   if (ws == nullptr || cand_off == nullptr || cand_cnt == nullptr || cand_rows == nullptr || cand_key == nullptr ||

@@ -35,7 +35,9 @@ namespace {
 constexpr int kTileN = 128;   // gallery rows per MMA tile (TMEM columns per accumulator, rows per shared-memory stage)
 constexpr int kTileM = 128;   // queries per query tile
 constexpr int kQT = 4;        // query tiles per CTA (4 accumulators x 128 columns = all 512 TMEM columns)
-constexpr int kStages = 4;    // gallery-tile ring
+// gallery-tile ring: as deep as the 227 KB of shared memory allow beside the four resident query tiles
+// (KB <= 192: 4 stages; KB = 224: 3; KB = 256 / 288, i.e. 225 ... 256-bit codes: 2)
+__host__ __device__ constexpr int stages_for(int kb) { return kb <= 192 ? 4 : (kb <= 224 ? 3 : 2); }
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -105,7 +107,7 @@ struct SelSmem {
   static constexpr int kB = kTileN * KB;   // one gallery tile
   static constexpr int offA = 0;
   static constexpr int offB = offA + kQT * kA;
-  static constexpr int total = offB + kStages * kB;
+  static constexpr int total = offB + stages_for(KB) * kB;
 };
 
 // Column c of a 32-column block holds gallery row kRowOfColumn(c) of the 32-row block: with the PRMT / LOP3
@@ -182,6 +184,7 @@ __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
 template <int KB, bool DENSE>
 __global__ void __launch_bounds__(128 + 128 * kQT, 1) hamming_select_tc_kernel(const SelDev a) {
   typedef SelSmem<KB> S;
+  constexpr int kStages = stages_for(KB);
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar_a, bar_full[kStages], bar_empty[kStages], bar_tfull[kQT], bar_tempty[kQT];
   __shared__ uint32_t tmem_base_s;
@@ -386,11 +389,15 @@ __global__ void __launch_bounds__(128 + 128 * kQT, 1) hamming_select_tc_kernel(c
   }
 }
 
-// packed sign bits -> +-1 int8 in the tiled core-matrix order; one thread per (row, 16-byte K chunk).
-// Bytes nbit and nbit + 1 of a row are the threshold slots: (1, 1) on the gallery side; on the query side
-// (thresh != NULL) a + b = -(nbit - 2 * thresh[row]) for row < nq and (-128, -128) for the padding queries.
-__global__ void expand_i8_tiled_kernel(const uint32_t* __restrict__ bits, long long rows_bits, long long rows_out,
-                                       int words, int nbit, int kb, const uint32_t* __restrict__ thresh, long long nq,
+// packed sign bits -> {-1, 0, +1} int8 in the tiled core-matrix order; one thread per (row, 16-byte K chunk).
+// A clear bit of the non-zero plane `nz` (ternary codes: sign(0) = 0) gives 0 -- the contraction then is the
+// ternary inner product and key = 2 x distance = nbit - <q, g> (oracle/map_oracle.py hamming_distance_matrix).
+// Bytes nbit .. nbit + slots - 1 of a row are the threshold slots: all 1 on the gallery side; on the query side
+// (thresh != NULL) they sum to -tau, tau = nbit - 2 thresh[row] (binary keys) or nbit - thresh[row] (ternary, keys on
+// the doubled scale), so that D = <q, g> - tau >= 0 <=> key <= thresh; padding queries get the most negative sum.
+__global__ void expand_i8_tiled_kernel(const uint32_t* __restrict__ bits, const uint32_t* __restrict__ nz,
+                                       long long rows_bits, long long rows_out, int words, int nbit, int kb, int slots,
+                                       int ternary, const uint32_t* __restrict__ thresh, long long nq,
                                        int8_t* __restrict__ out) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int chunks = kb / 16;
@@ -403,17 +410,17 @@ __global__ void expand_i8_tiled_kernel(const uint32_t* __restrict__ bits, long l
   // gallery planes: column c of a 32-row block holds row kRowOfColumn(c) of that block (see sign_mask32p)
   const long long src = thresh != nullptr ? row : (row & ~31ll) + kRowOfColumn(static_cast<int>(row & 31));
   const int k0 = chunk * 16;
-  uint32_t w = 0;
+  uint32_t w = 0, z = 0xffffffffu;
   const bool has_bits = src < rows_bits;
-  if (has_bits && k0 < words * 32) w = bits[src * words + (k0 >> 5)] >> (k0 & 31);
-  int s0 = 1, s1 = 1;
+  if (has_bits && k0 < words * 32) {
+    w = bits[src * words + (k0 >> 5)] >> (k0 & 31);
+    if (nz != nullptr) z = nz[src * words + (k0 >> 5)] >> (k0 & 31);
+  }
+  int rest = 0;                                 // what the remaining threshold slots still have to sum to
+  bool query_pad = false;
   if (thresh != nullptr) {
-    s0 = s1 = -128;
-    if (row < nq) {
-      const int neg_tau = 2 * static_cast<int>(thresh[row]) - nbit;     // in [-nbit, nbit]
-      s0 = neg_tau < -128 ? -128 : (neg_tau > 127 ? 127 : neg_tau);
-      s1 = neg_tau - s0;
-    }
+    if (row < nq) rest = (ternary ? 1 : 2) * static_cast<int>(thresh[row]) - nbit;     // -tau, in [-nbit, nbit]
+    else query_pad = true;
   }
   uint32_t o[4];
 #pragma unroll
@@ -423,9 +430,18 @@ __global__ void expand_i8_tiled_kernel(const uint32_t* __restrict__ bits, long l
     for (int j = 0; j < 4; ++j) {
       const int k = k0 + v * 4 + j;
       uint32_t byte = 0u;
-      if (k < nbit) byte = has_bits ? ((((w >> (v * 4 + j)) & 1u) != 0u) ? 0x01u : 0xffu) : 0u;
-      else if (k == nbit) byte = static_cast<uint32_t>(s0) & 0xffu;
-      else if (k == nbit + 1) byte = static_cast<uint32_t>(s1) & 0xffu;
+      if (k < nbit) {
+        if (has_bits && ((z >> (v * 4 + j)) & 1u) != 0u) byte = (((w >> (v * 4 + j)) & 1u) != 0u) ? 0x01u : 0xffu;
+      } else if (k < nbit + slots) {
+        int sv = 1;
+        if (thresh != nullptr) {
+          // slot k - nbit takes as much of -tau as an int8 holds; the slots before it took theirs
+          int r = rest;
+          for (int t = 0; t < k - nbit; ++t) r -= (r < -128 ? -128 : (r > 127 ? 127 : r));
+          sv = query_pad ? -128 : (r < -128 ? -128 : (r > 127 ? 127 : r));
+        }
+        byte = static_cast<uint32_t>(sv) & 0xffu;
+      }
       x |= byte << (8 * j);
     }
     o[v] = x;
@@ -445,31 +461,41 @@ sel_fn_t pick_sel(int kb, int dense, size_t* smem) {
     case 64: return pick_dense<64>(dense, smem);
     case 96: return pick_dense<96>(dense, smem);
     case 128: return pick_dense<128>(dense, smem);
-    default: return pick_dense<160>(dense, smem);
+    case 160: return pick_dense<160>(dense, smem);
+    case 192: return pick_dense<192>(dense, smem);
+    case 224: return pick_dense<224>(dense, smem);
+    case 256: return pick_dense<256>(dense, smem);
+    default: return pick_dense<288>(dense, smem);
   }
 }
+
+// threshold slots: |tau| <= nbit must be a sum of int8 values
+int thresh_slots(int nbit) { return nbit <= 254 ? 2 : 4; }
 
 }  // namespace
 
 extern "C" int ch_tc_queries_per_cta(void) { return kQT * kTileM; }
 
 extern "C" int ch_tc_code_bytes(int nbit) {
-  if (nbit <= 0 || nbit > 128) return 0;
-  return (nbit + 2 + 31) / 32 * 32;   // the codes + the two threshold slots, in whole 32-byte K blocks
+  if (nbit <= 0 || nbit > CH_MAX_NBIT) return 0;
+  return (nbit + thresh_slots(nbit) + 31) / 32 * 32;   // the codes + the threshold slots, in whole 32-byte K blocks
 }
 
-extern "C" int ch_expand_i8(ch_ws* ws, const uint32_t* bits_dev, int64_t rows_bits, int nbit, int8_t* out_dev,
-                            int64_t rows_out, const uint32_t* thresh_dev, int64_t nq, void* stream) {
+extern "C" int ch_expand_i8(ch_ws* ws, const uint32_t* bits_dev, const uint32_t* nz_dev, int64_t rows_bits, int nbit,
+                            int ternary, int8_t* out_dev, int64_t rows_out, const uint32_t* thresh_dev, int64_t nq,
+                            void* stream) {
   if (ws == nullptr || bits_dev == nullptr || out_dev == nullptr) CH_FAIL("null argument to ch_expand_i8");
+  if (ternary && nz_dev == nullptr) CH_FAIL("ternary codes need the non-zero plane");
   const int kb = ch_tc_code_bytes(nbit);
-  if (kb == 0) CH_FAIL("nbit=%d unsupported by the tensor-core path (1..128)", nbit);
+  if (kb == 0) CH_FAIL("nbit=%d unsupported by the tensor-core path (1..%d)", nbit, CH_MAX_NBIT);
   if (rows_out % 32 || rows_bits < 0 || rows_out < rows_bits)
     CH_FAIL("rows_out must be a multiple of 32 (whole permuted row blocks) and >= rows_bits");
   if (rows_out == 0) return 0;
   ChDeviceGuard guard(ws->device);
   const long long n = rows_out * (kb / 16);
   expand_i8_tiled_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      bits_dev, rows_bits, rows_out, ch_code_words(nbit), nbit, kb, thresh_dev, nq, out_dev);
+      bits_dev, ternary ? nz_dev : nullptr, rows_bits, rows_out, ch_code_words(nbit), nbit, kb, thresh_slots(nbit),
+      ternary ? 1 : 0, thresh_dev, nq, out_dev);
   CH_LAUNCH_CHECK(ws);
   return 0;
 }
@@ -480,7 +506,7 @@ extern "C" int ch_hamming_select_tc(ch_ws* ws, const ch_select_args* a, void* st
       a->cand_cnt == nullptr || a->cand_rows == nullptr || a->err_flag == nullptr)
     CH_FAIL("null array in ch_select_args");
   const int kb = ch_tc_code_bytes(a->nbit);
-  if (kb == 0) CH_FAIL("nbit=%d unsupported by the tensor-core path (1..128)", a->nbit);
+  if (kb == 0) CH_FAIL("nbit=%d unsupported by the tensor-core path (1..%d)", a->nbit, CH_MAX_NBIT);
   if (a->nq <= 0 || a->ndb < 0) CH_FAIL("bad arguments");
   if (a->nq_pad % kTileM || a->nq_pad < a->nq) CH_FAIL("nq_pad must be a multiple of %d and >= nq", kTileM);
   if (a->nstripes <= 0 || a->rows_per_stripe <= 0 || a->rows_per_stripe % kTileN ||

@@ -372,8 +372,9 @@ class Evaluator:
 
     # ------------------------------------------------------------------ tensor-core select pass -> candidate lists
     def _tc_ok(self, q, ternary, nq_pad):
-        """the select pass can run on tcgen05: binary codes of <= 128 bits, whole 128-query tiles"""
-        return (self.use_tensor_cores and not ternary and hasattr(self.b, "hamming_select_tc") and
+        """the select pass can run on tcgen05: binary or ternary codes of <= 256 bits (int8 operands hold -1, 0, +1
+        exactly), whole 128-query tiles"""
+        return (self.use_tensor_cores and hasattr(self.b, "hamming_select_tc") and
                 nq_pad % 128 == 0 and self.b.tc_code_bytes(q.nbit) > 0)
 
     def _alloc_cands(self, cap, geo, nq, thresh=None, site=None, nbins_full=0):
@@ -384,7 +385,7 @@ class Evaluator:
         off, total, tmax = self._offsets(cap, geo, nq, thresh, site, nbins_full)
         status = self._status
         cand = dict(off=off, cap=cap, cnt=self.b.empty((nstripes, nq_pad), torch.int32),
-                    rows=self.b.empty((total,), torch.int32), key=self.b.empty((total,), torch.uint8),
+                    rows=self.b.empty((total,), torch.int32), key=self.b.empty((total,), torch.int16),
                     err=status[ST_PASS:ST_PASS + 1], status=status)
         return (cand, tmax) if thresh is not None else cand
 
@@ -396,13 +397,18 @@ class Evaluator:
 
     def _query_plane(self, q, nq_pad, thresh):
         """int8 query plane with the thresholds in its threshold slots (made per select pass)"""
-        return self._timed("expand_i8", 0, lambda: self.b.expand_i8(q.bits, q.nbit, nq_pad, thresh=thresh, nq=q.n))
+        kw = {} if q.nz is None else dict(nz=q.nz)
+        return self._timed("expand_i8", 0, lambda: self.b.expand_i8(q.bits, q.nbit, nq_pad, thresh=thresh, nq=q.n, **kw))
+
+    def _gallery_plane(self, p):
+        kw = {} if p.nz is None else dict(nz=p.nz)
+        return self._timed("expand_i8", 0, lambda: self.b.expand_i8(p.bits, p.nbit, **kw))
 
     def _select_tc(self, q, g, geo, thresh, cand, dense):
         threads, nq_pad, nstripes, rps = geo
         q_i8 = self._query_plane(q, nq_pad, thresh)
         if g.i8 is None:
-            g.i8 = self._timed("expand_i8", 0, lambda: self.b.expand_i8(g.bits, g.nbit))
+            g.i8 = self._gallery_plane(g)
         self._timed("hist_select_tc", q.n * g.n, lambda: self.b.hamming_select_tc(
             q_i8=q_i8, g_i8=g.i8, cand=cand, nq=q.n, nq_pad=nq_pad, ndb=g.n, nbit=q.nbit, nstripes=nstripes,
             rows_per_stripe=rps, dense=dense))
@@ -416,7 +422,9 @@ class Evaluator:
         label_mode, lw = c["label_mode"], c["lw"]
         lab = lambda p: None if label_mode == L.CH_LAB_NONE else (p.ids if label_mode == L.CH_LAB_ID else p.masks)
         kw = {}
-        if label_mode == L.CH_LAB_ID and hasattr(b, "gather_plane"):
+        if q.nz is not None:
+            kw = dict(q_nz=q.nz, g_nz=g.nz)            # ternary keys (doubled scale) from both planes
+        elif label_mode == L.CH_LAB_ID and hasattr(b, "gather_plane"):
             # single-label gallery: [code | class id] rows, one memory sector per candidate instead of two gathers
             if nstripes is None:
                 if g.plane is None:
@@ -944,7 +952,7 @@ class Evaluator:
         # block 0 of a streamed gallery travels while the GPU works on the sample: its (host-blocking) copy is
         # issued right after the first sample kernels have been queued
         first_load = streamer.load_first if streamer is not None else (lambda: None)
-        if (tc_pass and self.sample_two_level and not ternary and min(ns_ranks) >= self.sample2_min_rows and
+        if (tc_pass and self.sample_two_level and min(ns_ranks) >= self.sample2_min_rows and
                 float(nq) * min(ns_ranks) * int(q.bits.shape[1]) >=
                 self.sample2_min_work * (1.0 if comm.world > 1 else 0.2)):   # one GPU: no extra collective to pay
             thresh, cap = self._sample_thresholds_tc(c, sp, ns_ranks, m, status, first_load)
@@ -1036,10 +1044,13 @@ class Evaluator:
         sp0.i8 = sp0.nz = sp0.ids = sp0.masks = sp0.info = None
         sp0.n, sp0.nbit = ns0, sp.nbit
         _, sp0.bits = b.gather_rows(sp.bits, ns, sp.nbit, sub)
+        ternary = sp.nz is not None
+        if ternary:
+            _, sp0.nz = b.gather_rows(sp.nz, ns, sp.nbit, sub)
         align = getattr(b, "stripe_align", 256)
         geo0 = (threads, nq_pad, 1, max(align, (ns0 + align - 1) // align * align))
         slab0 = b.zeros((1, nbins, nq_pad), torch.int32)
-        self._hist(q, sp0, geo0, False, L.CH_LAB_NONE, 0, slab0, None)
+        self._hist(q, sp0, geo0, ternary, L.CH_LAB_NONE, 0, slab0, None)
         ns0_total = sum((r + sub - 1) // sub for r in ns_ranks)
         mu0 = need * ns0_total / max(c["ndb_total"], 1)
         m0 = int(mu0 + 5.0 * mu0 ** 0.5 + 4.0) + 1
@@ -1057,7 +1068,7 @@ class Evaluator:
         rps1 = (-(-ns // n1) + tile - 1) // tile * tile
         n1 = max(1, -(-ns // rps1))
         geo1 = (threads, nq_pad, n1, rps1)
-        s_i8 = self._timed("expand_i8", 0, lambda: b.expand_i8(sp.bits, q.nbit))
+        s_i8 = self._gallery_plane(sp)
         after_level0()              # (host-blocking work of the caller, while the GPU runs level 0)
         cap0 = b.empty((n1, nq_pad), torch.int32)
         b.record_caps(0, slab0, thresh0, n1, nbins, nq, nq_pad, False, cap0, sample_stride=sub, replicate=True)
@@ -1070,9 +1081,10 @@ class Evaluator:
             q_i8=q_i8, g_i8=s_i8, cand=cand1, nq=nq, nq_pad=nq_pad, ndb=ns, nbit=q.nbit, nstripes=n1,
             rows_per_stripe=rps1, dense=dense))
         tot1 = b.zeros((nb0, nq_pad), torch.int32)
+        kwz = dict(q_nz=q.nz, g_nz=sp.nz) if ternary else {}
         self._timed("cand_hist", 0, lambda: b.cand_hist(
             cand1, q_bits=q.bits, g_bits=sp.bits, q_lab=None, g_lab=None, label_mode=L.CH_LAB_NONE, mask_words=0,
-            tot_all=tot1, tot_rel=None, nq=nq, nq_pad=nq_pad, nstripes=n1, nbins=nb0, nbit=q.nbit))
+            tot_all=tot1, tot_rel=None, nq=nq, nq_pad=nq_pad, nstripes=n1, nbins=nb0, nbit=q.nbit, **kwz))
         thresh1 = b.empty((nq_pad,), torch.int32)
         base1 = b.empty((nb0, nq_pad), torch.int32)
         b.scan_bases(self._summed_totals(tot1), 1, 0, nb0, nq, nq_pad, m, base1, thresh1, None)

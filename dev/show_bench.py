@@ -19,7 +19,7 @@ def brief(x, main=False):
               f"  issue-frac {r.get('frac_of_measured_mma_issue_peak')}")
     pc = x.get("parity_check")
     if pc:
-        print("   parity", {k: pc[k] for k in ("queries", "gallery_rows", "max_abs_ap_delta", "ids_equal", "ok")})
+        print("   parity", {k: pc.get(k) for k in ("queries", "gallery_rows", "max_abs_ap_delta", "ids_equal", "ok")})
     e = x.get("e2e")
     if e:
         print(f"   e2e pageable {e['ms_per_step']:.2f} ms  pinned {e['ms_per_step_pinned_host_tensors']:.2f} ms")

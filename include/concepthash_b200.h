@@ -147,11 +147,14 @@ int ch_hamming_hist(ch_ws* ws, const ch_hist_args* a, void* stream);
 /* ---- K2, tensor-core form of the select pass -------------------------------------------------------
  * Same question as ch_hamming_hist with `thresh` set -- which pairs have key <= thresh[q]? -- answered by
  * tcgen05.mma kind::i8 (UTCIMMA) with the accumulators in TMEM: for +-1 codes held as int8,
- * <q, g> = nbit - 2 * hamming.  Binary codes only, nbit <= 128.  The int8 planes are made from the packed bits
+ * <q, g> = nbit - 2 * hamming; for ternary codes ({-1, 0, +1}: `threshold` of configs/val.yaml:12 /
+ * experiments/test_hashing.py:109, or an exact zero) the same contraction gives key = 2 * distance = nbit - <q, g>.
+ * nbit <= 256.  The int8 planes are made from the packed bits (and the non-zero plane of ternary codes)
  * by ch_expand_i8 in the shared-memory operand order (8-row x 16-byte core matrices), so the kernel streams
- * them with plain 1-D bulk copies.  ch_tc_code_bytes(nbit) = bytes per plane row: the codes plus two
- * "threshold slots" (bytes nbit, nbit + 1), rounded up to whole 32-byte K blocks; 0 if nbit is unsupported.
- * The slots hold (1, 1) on the gallery side and (a, b), a + b = -(nbit - 2 * thresh[q]), on the query side, so
+ * them with plain 1-D bulk copies.  ch_tc_code_bytes(nbit) = bytes per plane row: the codes plus the
+ * "threshold slots" (2 bytes from nbit on; 4 for nbit > 254), rounded up to whole 32-byte K blocks; 0 if nbit is
+ * unsupported.  The slots hold 1 on the gallery side and int8 values that sum to -tau on the query side
+ * (tau = nbit - 2 * thresh[q], or nbit - thresh[q] on the doubled key scale of ternary codes), so
  * that the accumulator is  <q, g> - (nbit - 2 * thresh[q])  and  key <= thresh  <=>  accumulator >= 0: the
  * epilogue only looks at sign bits.
  *   ch_expand_i8: bits (rows_bits, words) -> out (rows_out, kb) int8, rows_out >= rows_bits, rows_out % 32 == 0
@@ -178,8 +181,9 @@ typedef struct ch_select_args {
 int ch_tc_code_bytes(int nbit);
 /* queries one CTA of the select kernel owns (its grid is ceil(nq_pad / this) x nstripes, one CTA per SM) */
 int ch_tc_queries_per_cta(void);
-int ch_expand_i8(ch_ws* ws, const uint32_t* bits_dev, int64_t rows_bits, int nbit, int8_t* out_dev,
-                 int64_t rows_out, const uint32_t* thresh_dev /* or NULL */, int64_t nq, void* stream);
+int ch_expand_i8(ch_ws* ws, const uint32_t* bits_dev, const uint32_t* nz_dev /* ternary codes, else NULL */,
+                 int64_t rows_bits, int nbit, int ternary, int8_t* out_dev, int64_t rows_out,
+                 const uint32_t* thresh_dev /* or NULL */, int64_t nq, void* stream);
 int ch_hamming_select_tc(ch_ws* ws, const ch_select_args* a, void* stream);
 
 /* ---- K3/K4 on candidate lists ---------------------------------------------------------------------
@@ -198,8 +202,10 @@ int ch_hamming_select_tc(ch_ws* ws, const ch_select_args* a, void* stream);
  *                    mode 2: ids (nq, R) int64 = row_offset + row at its rank, keys (nq, R) int32 (pre-filled -1). */
 typedef struct ch_cand_args {
   const uint32_t* cand_off;  const uint32_t* cand_cnt;    /* (nstripes, nq_pad) */
-  uint32_t* cand_rows;       uint8_t* cand_key;           /* per candidate slot */
+  uint32_t* cand_rows;       uint16_t* cand_key;          /* per candidate slot */
   const uint32_t* q_bits;    const uint32_t* g_bits;      /* packed codes (hist only) */
+  const uint32_t* q_nz;      const uint32_t* g_nz;        /* non-zero planes of ternary codes (keys = 2 x distance,
+                                                             0 .. 2 nbit), else NULL */
   const uint32_t* g_plane;   /* optional (CH_LAB_ID): ch_gather_plane output -- code + class id in ONE sector */
   const uint32_t* q_lab;     const uint32_t* g_lab;       /* ids or masks; NULL if CH_LAB_NONE (hist only) */
   uint32_t* tot_all;         uint32_t* tot_rel;           /* (nbins, nq_pad) out of ch_cand_hist */
@@ -229,7 +235,7 @@ int ch_cand_finalize(ch_ws* ws, const ch_cand_args* a, void* stream);
  * whose sample row lies in [s * rows_per_stripe, (s + 1) * rows_per_stripe): the capacity of slice (s, q) of the
  * full pass (same bound as ch_record_caps with sample_stride).  cap_dev: (nstripes, nq_pad). */
 int ch_cand_caps(ch_ws* ws, const uint32_t* cand_off, const uint32_t* cand_cnt, const uint32_t* cand_rows,
-                 const uint8_t* cand_key, const uint32_t* thresh, int list_stripes, int rows_per_stripe,
+                 const uint16_t* cand_key, const uint32_t* thresh, int list_stripes, int rows_per_stripe,
                  int nstripes, int64_t nq, int64_t nq_pad, int sample_stride, uint32_t* cap_dev, void* stream);
 
 /* slab reductions: totals over stripes -> tot (nbins, nq_pad); exclusive scan over stripes in place */

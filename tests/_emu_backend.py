@@ -191,18 +191,19 @@ class EmuBackend:
 
     # K2, tensor-core form (candidate lists).  The emulation keeps the packed bits + thresholds instead of int8 planes.
     def tc_code_bytes(self, nbit):
-        if not self.tensor_cores or nbit <= 0 or nbit > 128:
+        if not self.tensor_cores or nbit <= 0 or nbit > 256:
             return 0
-        return (nbit + 2 + 31) // 32 * 32
+        return (nbit + (2 if nbit <= 254 else 4) + 31) // 32 * 32
 
-    def expand_i8(self, bits, nbit, min_rows=0, thresh=None, nq=0):
+    def expand_i8(self, bits, nbit, min_rows=0, thresh=None, nq=0, nz=None):
         self.launches += 1
-        return dict(bits=bits, nbit=nbit, nq=nq, thresh=None if thresh is None else thresh.clone())
+        return dict(bits=bits, nz=nz, nbit=nbit, nq=nq, thresh=None if thresh is None else thresh.clone())
 
     def hamming_select_tc(self, *, q_i8, g_i8, cand, nq, nq_pad, ndb, nbit, nstripes, rows_per_stripe, row_base=0,
                           dense=False, stripe0=0):
         self.launches += 1
-        keys = self._keys(q_i8["bits"], None, g_i8["bits"], None, nq, ndb, nbit, False)
+        assert (q_i8["nz"] is None) == (g_i8["nz"] is None)
+        keys = self._keys(q_i8["bits"], q_i8["nz"], g_i8["bits"], g_i8["nz"], nq, ndb, nbit, q_i8["nz"] is not None)
         th = _u32(q_i8["thresh"])
         off, cap, cnt, rows = _u32(cand["off"]), _u32(cand["cap"]), _u32(cand["cnt"]), _u32(cand["rows"])
         for s in range(nstripes):
@@ -218,10 +219,13 @@ class EmuBackend:
 
     # K3/K4 on candidate lists
     def cand_hist(self, cand, *, q_bits, g_bits, q_lab, g_lab, label_mode, mask_words, tot_all, tot_rel, nq, nq_pad,
-                  nstripes, nbins, nbit, stripe0=0, g_plane=None):
+                  nstripes, nbins, nbit, stripe0=0, g_plane=None, q_nz=None, g_nz=None):
         self.launches += 1
         off, cnt, rows, key = _u32(cand["off"]), _u32(cand["cnt"]), _u32(cand["rows"]), cand["key"].numpy()
         qs, gs = _unpack(_u32(q_bits)[:nq], nbit), _unpack(_u32(g_bits), nbit)
+        tern = q_nz is not None
+        if tern:
+            qz, gz = _unpack(_u32(q_nz)[:nq], nbit), _unpack(_u32(g_nz), nbit)
         ta = _u32(tot_all)
         tr = _u32(tot_rel) if tot_rel is not None else None
         for q in range(nq):
@@ -229,7 +233,11 @@ class EmuBackend:
                 o = int(off[s, q])
                 for i in range(int(cnt[s, q])):
                     row = int(rows[o + i] & 0x7FFFFFFF)
-                    k = int((qs[q] != gs[row]).sum())
+                    if tern:
+                        both = qz[q] & gz[row]
+                        k = int(nbit - both.sum() + 2 * ((qs[q] != gs[row]) & (both == 1)).sum())
+                    else:
+                        k = int((qs[q] != gs[row]).sum())
                     if label_mode == CH_LAB_ID:
                         r = _u32(q_lab)[q] == _u32(g_lab)[row]
                     elif label_mode == CH_LAB_MASK:

@@ -51,7 +51,7 @@ def test_struct_layout_matches_c(lib):
     assert ctypes.sizeof(_lib.HistArgs) == 14 * 8 + 3 * 8 + 8 * 4 + 8 + 4 + 4     # ..., int64 row_base, int32 + padding
     assert ctypes.sizeof(_lib.FinalArgs) == 10 * 8 + 2 * 8 + 5 * 4 + 4 + 8 * 8 + 32 * 8
     assert ctypes.sizeof(_lib.SelectArgs) == 7 * 8 + 4 * 8 + 4 * 4
-    assert ctypes.sizeof(_lib.CandArgs) == 20 * 8 + 4 * 8 + 9 * 4 + 4 + 8 * 8 + 32 * 8
+    assert ctypes.sizeof(_lib.CandArgs) == 22 * 8 + 4 * 8 + 9 * 4 + 4 + 8 * 8 + 32 * 8
 
 
 def test_sass_is_blackwell_native():

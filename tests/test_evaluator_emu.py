@@ -350,3 +350,18 @@ def test_query_chunking_when_slots_exceed_the_offset_range(R):
     # and again (the chunks now run speculatively)
     out = ev2.evaluate(d, dl, q, ql, [R], 0.0, [1, 5], False, return_ap=True)
     _check(out, _oracle(d, dl, q, ql, R, [1, 5]))
+
+
+@pytest.mark.parametrize("mode", ["exact", "sampled", "two_level"])
+def test_candidate_path_ternary_codes(mode):
+    """ternary codes (threshold / exact zeros) through the candidate-list path: keys on the doubled scale"""
+    d, dl, q, ql, _ = synth.make_random_case(21, 500, 24, 4, p=0.3, seed=31)
+    d[::5, 3] = 0.0
+    for thr in (0.0, 0.4):
+        ev = run_case(d, dl, q, ql, [7, 60], PRs=[1, 5], thr=thr, tc=True, sampled=mode != "exact",
+                      two_level=mode == "two_level")
+        assert ev.stats["ternary"] and ev.stats.get("select_kernel") == "tcgen05", ev.stats
+    ev = Evaluator(EmuBackend(rows_per_stripe=64, threads=128, tensor_cores=True))
+    ids, keys, tern = ev.retrieve(d, q, 40, 0.4)
+    oids, odist = mo.topk_ids(q, d, 40, threshold=0.4)
+    assert tern and torch.equal(ids, oids) and torch.equal(keys.float() * 0.5, odist)

@@ -466,21 +466,29 @@ def test_pack_sign_flat_fast_path(H, nbit, dtype):
         assert int(f1.cpu()[0]) == 1
 
 
-@pytest.mark.parametrize("nbit", [16, 31, 32, 48, 64, 96, 100, 127, 128])
-def test_tensor_core_select_equals_popc_select(H, nbit):
-    """The tcgen05 (int8 +-1, UTCIMMA) select pass + candidate-list ranking must give the results of the XOR+POPC
-    select pass + record ranking: same AP per query (to fp64 summation order), bit-identical ranked ids -- and
-    both match the oracle on a query subset."""
+@pytest.mark.parametrize("nbit,thr", [(16, 0.0), (31, 0.0), (32, 0.0), (48, 0.0), (64, 0.0), (96, 0.0), (100, 0.0),
+                                      (127, 0.0), (128, 0.0), (129, 0.0), (160, 0.0), (192, 0.0), (200, 0.0),
+                                      (224, 0.0), (255, 0.0), (256, 0.0),
+                                      (32, 0.3), (64, 0.3), (100, 0.3), (128, 0.3), (256, 0.3)])
+def test_tensor_core_select_equals_popc_select(H, nbit, thr):
+    """The tcgen05 (int8 {-1, 0, +1}, UTCIMMA) select pass + candidate-list ranking must give the results of the
+    XOR+POPC select pass + record ranking: same AP per query (to fp64 summation order), bit-identical ranked ids --
+    and both match the oracle on a query subset.  nbit up to 256 (KB up to 288: 2-stage ring, four threshold
+    slots); ``thr`` = configs/val.yaml:12 ``ternary_threshold`` (experiments/test_hashing.py:109): ~16 % of the
+    signs become 0, keys are 2 x distance."""
     ev = H.get_evaluator()
     nq, ndb = 700, 260_000 + nbit          # tail tile, several stripes, inactive query lanes in the last tile
+    if nbit > 128 or thr:
+        ndb = 150_000 + nbit               # (the POPC reference pass of wide / ternary codes is slow)
     d, dl, q, ql, ncls = synth.make_random_case(nq, ndb, nbit, 30, p=0.30, seed=nbit, device="cuda")
     out = {}
     for tc, dense in ((True, False), (True, True), (False, None)):
         ev.use_tensor_cores, ev.select_dense_override = tc, dense
         try:
-            res = ev.evaluate(d, dl, q, ql, [50, 500], 0.0, [1, 5, 10], False, return_ap=True)
+            res = ev.evaluate(d, dl, q, ql, [50, 500], thr, [1, 5, 10], False, return_ap=True)
             kern = ev.stats["select_kernel"]
-            ids, keys, _ = ev.retrieve(d, q, 300)
+            assert ev.stats["ternary"] == bool(thr)
+            ids, keys, _ = ev.retrieve(d, q, 300, thr)
             out[(tc, dense)] = (res, ids, keys)
         finally:
             ev.use_tensor_cores, ev.select_dense_override = True, None
@@ -491,9 +499,13 @@ def test_tensor_core_select_equals_popc_select(H, nbit):
         assert _same(ra, rb)
         assert torch.equal(ia, ib) and torch.equal(ka, kb)
     sub = slice(0, 40)
-    om, orec, oprec = mo.calculate_mAP(d.cpu(), dl.cpu(), q[sub].cpu(), ql[sub].cpu(), [50, 500], PRs=[1, 5, 10])
-    m, rec, prec = H.calculate_mAP(d, dl, q[sub], ql[sub], [50, 500], PRs=[1, 5, 10])
+    om, orec, oprec = mo.calculate_mAP(d.cpu(), dl.cpu(), q[sub].cpu(), ql[sub].cpu(), [50, 500], threshold=thr,
+                                       PRs=[1, 5, 10])
+    m, rec, prec = H.calculate_mAP(d, dl, q[sub], ql[sub], [50, 500], threshold=thr, PRs=[1, 5, 10])
     assert np.allclose(m, om, atol=TOL) and np.allclose(rec, orec, atol=TOL) and np.allclose(prec, oprec, atol=TOL)
+    oids, odist = mo.topk_ids(q[sub].cpu(), d.cpu(), 300, threshold=thr)
+    assert torch.equal(out[(True, False)][1][sub].cpu(), oids)
+    assert torch.equal(out[(True, False)][2][sub].cpu().float() * (0.5 if thr else 1.0), odist)
 
 
 def test_streamed_host_gallery_equals_resident(H):
