@@ -79,9 +79,9 @@ ST_CODES = 2    # ch_pack_sign flags: bit 0 some sign is exactly 0 (ternary keys
 ST_PACKED = 3   # group mode: 1 if this rank packed its gallery up front (then nobody streams)
 # (total slots, max threshold) of the list / record allocations (ch_record_offsets_async): the sample-level list, and
 # the one full-size allocation an evaluation makes (sampled pass, exact pass or full ranking)
-ST_SITE = {"s1": 4, "full": 6, "exact": 6, "all": 6}
-ST_QINFO, ST_GINFO = 8, 12       # ch_pack_labels statistics [max positives per row, max id + 1, rows w/o label, -]
-ST_ROWS = 16    # gallery rows of every rank (group mode)
+ST_SITE = {"s1": 4, "full": 6, "exact": 8, "all": 8}
+ST_QINFO, ST_GINFO = 10, 14      # ch_pack_labels statistics [max positives per row, max id + 1, rows w/o label, -]
+ST_ROWS = 18    # gallery rows of every rank (group mode)
 _RETRY = object()
 
 
@@ -1056,12 +1056,9 @@ class Evaluator:
         m0 = int(mu0 + 5.0 * mu0 ** 0.5 + 4.0) + 1
         thresh0 = b.empty((nq_pad,), torch.int32)
         base_tmp = b.empty((nbins, nq_pad), torch.int32)
-        tot0 = slab0[0].clone() if comm.world > 1 else slab0[0]        # (the all-reduce works in place)
-        b.scan_bases(self._summed_totals(tot0), 1, 0, nbins, nq, nq_pad, m0, base_tmp, thresh0, None)
-        # list capacities of the sample select: the local mini-sample count <= t0, scaled -- for EVERY stripe (the
-        # row order may put all neighbours of a query into one stripe)
-        # the sample select has its own stripes: just enough CTAs to fill the GPU (capacity = the whole-sample bound
-        # per slice, because the row order may put all neighbours of a query into one stripe)
+        tot0 = self._summed_totals(slab0[0])                           # (1, nbins, nq_pad), summed over the ranks
+        b.scan_bases(tot0, 1, 0, nbins, nq, nq_pad, m0, base_tmp, thresh0, None)
+        # the sample select has its own stripes: just enough CTAs to fill the GPU
         tile = getattr(b, "tc_tile_rows", 1)
         groups = -(-nq_pad // getattr(b, "tc_queries_per_cta", 512))
         n1 = max(1, min(-(-getattr(b, "sm_count", 148) // groups), max(1, ns // 4096)))
@@ -1070,8 +1067,12 @@ class Evaluator:
         geo1 = (threads, nq_pad, n1, rps1)
         s_i8 = self._gallery_plane(sp)
         after_level0()              # (host-blocking work of the caller, while the GPU runs level 0)
+        # list capacities of the sample select from the GLOBAL mini-sample count c >= m0 under t0 (a rank's own count
+        # is a thin Poisson split of it: with c_local = 0 the bound would admit a mean of 11 only, and among 10^5
+        # queries some rank-local mean of ~c / world does exceed that) -- for EVERY stripe and rank, because the row
+        # order may put all neighbours of a query into one stripe of one rank
         cap0 = b.empty((n1, nq_pad), torch.int32)
-        b.record_caps(0, slab0, thresh0, n1, nbins, nq, nq_pad, False, cap0, sample_stride=sub, replicate=True)
+        b.record_caps(0, tot0, thresh0, n1, nbins, nq, nq_pad, False, cap0, sample_stride=sub, replicate=True)
         cand1, tmax0 = self._alloc_cands(cap0, geo1, nq, thresh0, "s1", nbins)
         nb0 = min(nbins, tmax0 + 1)
         # ---- level 1 ----
