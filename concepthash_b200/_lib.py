@@ -62,6 +62,7 @@ SIGNATURES = {
     "ch_code_words": (C.c_int, [C.c_int]),
     "ch_pack_sign": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_double,
                                P, P, P, P, P]),
+    "ch_host_pack_sign": (C.c_int, [P, C.c_int64, C.c_int, C.c_int64, P, P, C.c_int]),
     "ch_column_sums": (C.c_int, [P, P, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int64, P, P]),
     "ch_pack_labels": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_uint32,
                                  P, P, P, P]),

@@ -69,6 +69,11 @@ extern "C" int ch_workspace_create(int device, ch_ws** out) {
       const int v = atoi(e);
       if (v >= 1 && v <= 64) ws->host_threads = v;
     }
+    ws->pack_threads = hc >= 2 ? static_cast<int>(hc > 32 ? 32 : hc) : 1;   // read-only pass: every core helps
+    if (const char* e = getenv("CH_PACK_THREADS")) {          // 0 = keep the bounce-copy + GPU pack path
+      const int v = atoi(e);
+      if (v >= 0 && v <= 128) ws->pack_threads = v;
+    }
   }
   for (int i = 0; i < 2; ++i) {
     ws->stage[i] = nullptr;

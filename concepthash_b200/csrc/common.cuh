@@ -23,8 +23,12 @@ struct ch_ws {
   // copies single-threaded, ~9 GB/s)
   void* bounce[2];
   int host_threads;
+  int pack_threads;   // host threads of the pageable fp32 sign/bit-pack (host_pack.cpp)
   int64_t launches;
 };
+
+// host_pack.cpp: sign/bit-pack of pageable fp32 rows on the host's cores -> flag bits (1: a zero, 2: NaN)
+uint32_t ch_host_pack_f32(const float* src, int64_t n, int ncols, int64_t rs, int words, uint32_t* out, int nthreads);
 
 // thread-local last error ---------------------------------------------------------------------------
 void ch_set_error(const char* fmt, ...);

@@ -1,0 +1,190 @@
+// Host side of K1 for PAGEABLE fp32 codes: what `inference_one_epoch` hands over is a `torch.cat` of `.cpu()`
+// batches (trainers/base.py:291-304) -- ordinary pageable memory.  The GPU cannot DMA from it: the bytes have to
+// pass through the host's cores once anyway (into a pinned bounce buffer).  Doing the sign test in that one pass
+// turns a 4-byte-per-code copy into a 1-bit-per-code write: the cores read the codes once (the floor for pageable
+// memory), and 1/32 of the bytes cross PCIe.  Bit-identical to the CUDA kernel by construction and by test
+// (tests/test_gpu_parity.py::test_host_pack_equals_device_pack): bit = (x > 0), zeros and NaNs reported in the
+// same flag bits.  CUDA tensors and pinned host tensors never come here (pack.cu: DMA + pack_sign_flat_kernel).
+#include <immintrin.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace {
+
+// ---- a small persistent pool (a std::thread per call would cost ~20 us each, a streamed gallery makes dozens
+// of calls per evaluation) -----------------------------------------------------------------------------------
+class Pool {
+ public:
+  static Pool& get() {
+    static Pool p;
+    return p;
+  }
+  // runs fn(t) for t in [0, n) on n threads (the caller is thread 0)
+  void run(int n, const std::function<void(int)>& fn) {
+    if (n <= 1) {
+      fn(0);
+      return;
+    }
+    std::lock_guard<std::mutex> serial(call_mu_);
+    ensure(n - 1);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      fn_ = &fn;
+      want_ = n - 1;
+      pending_ = n - 1;
+      ++epoch_;
+    }
+    cv_.notify_all();
+    fn(0);
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [&] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  Pool() = default;
+  ~Pool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+      ++epoch_;
+    }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  void ensure(int n) {
+    while (static_cast<int>(workers_.size()) < n) {
+      const int id = static_cast<int>(workers_.size()) + 1;
+      workers_.emplace_back([this, id] {
+        uint64_t seen = 0;
+        for (;;) {
+          const std::function<void(int)>* fn = nullptr;
+          {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&] { return epoch_ != seen; });
+            seen = epoch_;
+            if (stop_) return;
+            if (id <= want_) fn = fn_;
+          }
+          if (fn != nullptr) {
+            (*fn)(id);
+            std::lock_guard<std::mutex> lk(mu_);
+            if (--pending_ == 0) done_.notify_one();
+          }
+        }
+      });
+    }
+  }
+  std::mutex call_mu_, mu_;
+  std::condition_variable cv_, done_;
+  std::vector<std::thread> workers_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int want_ = 0, pending_ = 0;
+  uint64_t epoch_ = 0;
+  bool stop_ = false;
+};
+
+// one row: ncols floats -> words u32 (bit k % 32 of word k / 32 = x[k] > 0); returns flag bits (1 zero, 2 NaN)
+inline uint32_t pack_row_scalar(const float* x, int k0, int ncols, uint32_t* out, int words) {
+  uint32_t fl = 0;
+  for (int w = k0 / 32; w < words; ++w) {
+    uint32_t v = 0;
+    for (int j = 0; j < 32; ++j) {
+      const int k = w * 32 + j;
+      if (k >= ncols) break;
+      const float f = x[k];
+      if (f > 0.0f) v |= 1u << j;
+      if (f != f) fl |= 2u;
+      else if (f == 0.0f) fl |= 1u;
+    }
+    out[w] = v;
+  }
+  return fl;
+}
+
+__attribute__((target("avx512f"))) uint32_t pack_rows_avx512(const float* src, int64_t r0, int64_t r1, int ncols,
+                                                            int64_t rs, int words, uint32_t* out) {
+  const __m512 zero = _mm512_setzero_ps();
+  __mmask16 anyz = 0, anyn = 0;
+  uint32_t fl = 0;
+  const int full = ncols / 32;                       // words made of two whole 16-float vectors
+  for (int64_t r = r0; r < r1; ++r) {
+    const float* x = src + r * rs;
+    uint32_t* o = out + r * words;
+    for (int w = 0; w < full; ++w) {
+      const __m512 a = _mm512_loadu_ps(x + 32 * w), b = _mm512_loadu_ps(x + 32 * w + 16);
+      const __mmask16 pa = _mm512_cmp_ps_mask(a, zero, _CMP_GT_OQ), pb = _mm512_cmp_ps_mask(b, zero, _CMP_GT_OQ);
+      anyz |= _mm512_cmp_ps_mask(a, zero, _CMP_EQ_OQ) | _mm512_cmp_ps_mask(b, zero, _CMP_EQ_OQ);
+      anyn |= _mm512_cmp_ps_mask(a, a, _CMP_UNORD_Q) | _mm512_cmp_ps_mask(b, b, _CMP_UNORD_Q);
+      o[w] = static_cast<uint32_t>(pa) | (static_cast<uint32_t>(pb) << 16);
+    }
+    if (full < words) fl |= pack_row_scalar(x, full * 32, ncols, o, words);
+  }
+  if (anyz) fl |= 1u;
+  if (anyn) fl |= 2u;
+  return fl;
+}
+
+__attribute__((target("avx2"))) uint32_t pack_rows_avx2(const float* src, int64_t r0, int64_t r1, int ncols, int64_t rs,
+                                                        int words, uint32_t* out) {
+  const __m256 zero = _mm256_setzero_ps();
+  int anyz = 0, anyn = 0;
+  uint32_t fl = 0;
+  const int full = ncols / 32;
+  for (int64_t r = r0; r < r1; ++r) {
+    const float* x = src + r * rs;
+    uint32_t* o = out + r * words;
+    for (int w = 0; w < full; ++w) {
+      uint32_t v = 0;
+      for (int j = 0; j < 4; ++j) {
+        const __m256 a = _mm256_loadu_ps(x + 32 * w + 8 * j);
+        v |= static_cast<uint32_t>(_mm256_movemask_ps(_mm256_cmp_ps(a, zero, _CMP_GT_OQ))) << (8 * j);
+        anyz |= _mm256_movemask_ps(_mm256_cmp_ps(a, zero, _CMP_EQ_OQ));
+        anyn |= _mm256_movemask_ps(_mm256_cmp_ps(a, a, _CMP_UNORD_Q));
+      }
+      o[w] = v;
+    }
+    if (full < words) fl |= pack_row_scalar(x, full * 32, ncols, o, words);
+  }
+  if (anyz) fl |= 1u;
+  if (anyn) fl |= 2u;
+  return fl;
+}
+
+uint32_t pack_rows_plain(const float* src, int64_t r0, int64_t r1, int ncols, int64_t rs, int words, uint32_t* out) {
+  uint32_t fl = 0;
+  for (int64_t r = r0; r < r1; ++r) fl |= pack_row_scalar(src + r * rs, 0, ncols, out + r * words, words);
+  return fl;
+}
+
+}  // namespace
+
+// rows [0, n) of `src` (row stride rs floats, unit column stride) -> out (n, words) u32; returns the flag bits
+// (bit 0: some value is exactly 0, bit 1: NaN) exactly as the pack kernels raise them.
+uint32_t ch_host_pack_f32(const float* src, int64_t n, int ncols, int64_t rs, int words, uint32_t* out, int nthreads) {
+  if (n <= 0) return 0;
+  typedef uint32_t (*fn_t)(const float*, int64_t, int64_t, int, int64_t, int, uint32_t*);
+  fn_t fn = pack_rows_plain;
+  __builtin_cpu_init();
+  if (__builtin_cpu_supports("avx512f")) fn = pack_rows_avx512;
+  else if (__builtin_cpu_supports("avx2")) fn = pack_rows_avx2;
+  // small inputs are not worth waking threads for (>= 1 MB of codes per thread)
+  const int64_t bytes = n * static_cast<int64_t>(ncols) * 4;
+  int nt = nthreads;
+  if (nt > bytes / (1 << 20)) nt = static_cast<int>(bytes / (1 << 20));
+  if (nt < 1) nt = 1;
+  std::vector<uint32_t> flags(static_cast<size_t>(nt), 0u);
+  Pool::get().run(nt, [&](int t) {
+    const int64_t a = n * t / nt, b = n * (t + 1) / nt;
+    flags[static_cast<size_t>(t)] = fn(src, a, b, ncols, rs, words, out);
+  });
+  uint32_t fl = 0;
+  for (uint32_t f : flags) fl |= f;
+  return fl;
+}

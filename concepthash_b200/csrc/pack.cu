@@ -269,6 +269,8 @@ __global__ void column_reduce_kernel(const double* __restrict__ part, int64_t nw
   sums[col] = acc;
 }
 
+__global__ void or_flags_kernel(uint32_t* __restrict__ flags, uint32_t bits) { atomicOr(flags, bits); }
+
 size_t elem_size(int dtype) {
   switch (dtype) {
     case CH_F32: return 4;
@@ -345,6 +347,32 @@ int pack_from_host(ch_ws* ws, const void* src, int dtype, int64_t n, int ncols, 
       cudaGetLastError();   // older drivers report unregistered host pointers as an error
   }
   if (pageable && ch_ws_ensure_bounce(ws)) return 1;
+  // Pageable fp32 codes, plain sign test: the host's cores have to touch every byte anyway (nothing can DMA from
+  // pageable memory), so they do the sign test in that one pass and only the BITS travel (host_pack.cpp).
+  if (pageable && dtype == CH_F32 && thr == 0.0 && sub == nullptr && out_nz == nullptr &&
+      ws->pack_threads > 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+    const size_t out_row = static_cast<size_t>(words) * 4;
+    const int64_t rows_per_buf = static_cast<int64_t>(ws->stage_bytes / out_row);
+    int c = 0;
+    uint32_t fl = 0;
+    for (int64_t r0 = 0; r0 < n; r0 += rows_per_buf, ++c) {
+      const int b = c & 1;
+      const int64_t r1 = (r0 + rows_per_buf < n) ? r0 + rows_per_buf : n;
+      CH_CUDA(cudaEventSynchronize(ws->ev_copied[b]));          // the DMA that last read this bounce buffer is done
+      uint32_t* dst = static_cast<uint32_t*>(ws->bounce[b]);
+      fl |= ch_host_pack_f32(static_cast<const float*>(src) + static_cast<size_t>(r0) * rs, r1 - r0, ncols, rs, words,
+                             dst, ws->pack_threads);
+      CH_CUDA(cudaMemcpyAsync(out_pos + static_cast<size_t>(r0) * words, dst, static_cast<size_t>(r1 - r0) * out_row,
+                              cudaMemcpyHostToDevice, st));
+      CH_CUDA(cudaEventRecord(ws->ev_copied[b], st));
+    }
+    CH_CUDA(cudaMemsetAsync(out_pos + static_cast<size_t>(n) * words, 0, static_cast<size_t>(rows_pad - n) * out_row, st));
+    if (fl != 0u && flags != nullptr) {
+      or_flags_kernel<<<1, 1, 0, st>>>(flags, fl);
+      CH_LAUNCH_CHECK(ws);
+    }
+    return 0;
+  }
   int c = 0;
   for (int64_t r0 = 0; r0 < n; r0 += chunk_rows, ++c) {
     const int b = c & 1;
@@ -398,6 +426,17 @@ int pack_from_host(ch_ws* ws, const void* src, int dtype, int64_t n, int ncols, 
 }
 
 }  // namespace
+
+extern "C" int ch_host_pack_sign(const float* codes_host, int64_t n, int nbit, int64_t row_stride,
+                                 uint32_t* out_bits_host, uint32_t* flags_host, int threads) {
+  const int words = ch_code_words(nbit);
+  if (words == 0) CH_FAIL("nbit=%d unsupported (1..%d)", nbit, CH_MAX_NBIT);
+  if (n < 0 || (n > 0 && (codes_host == nullptr || out_bits_host == nullptr)) || row_stride < nbit)
+    CH_FAIL("bad arguments to ch_host_pack_sign");
+  const uint32_t fl = ch_host_pack_f32(codes_host, n, nbit, row_stride, words, out_bits_host, threads < 1 ? 1 : threads);
+  if (flags_host != nullptr) *flags_host |= fl;
+  return 0;
+}
 
 extern "C" int64_t ch_padded_rows(int64_t n) { return ch_round_up(n < 0 ? 0 : n, 64) + 64; }
 

@@ -85,6 +85,15 @@ int     ch_code_words(int nbit);
 int ch_pack_sign(ch_ws* ws, const void* codes, int mem, int dtype, int64_t n, int nbit,
                  int64_t row_stride, int64_t col_stride, double threshold, const double* col_sub_dev,
                  uint32_t* out_bits_dev, uint32_t* out_nz_dev, uint32_t* flags_dev, void* stream);
+/* The host half of ch_pack_sign for PAGEABLE fp32 codes -- what `inference_one_epoch` returns, a torch.cat of
+ * `.cpu()` batches (trainers/base.py:291-304).  Nothing can DMA from pageable memory, the host's cores have to
+ * touch every byte once anyway; they apply the sign test in that pass (AVX-512 / AVX2, `threads` threads) and only
+ * the bits cross PCIe.  ch_pack_sign does this internally for CH_MEM_HOST + unregistered memory + CH_F32 +
+ * threshold 0 + no col_sub + no non-zero plane; this entry point exposes the same routine with host output
+ * (unit tests; callers that pack while the loader is still producing batches).  out_bits_host: (n, words) u32,
+ * same bit order as ch_pack_sign; *flags_host |= 1 (a zero) / 2 (NaN).  Bit-identical to the kernels. */
+int ch_host_pack_sign(const float* codes_host, int64_t n, int nbit, int64_t row_stride,
+                      uint32_t* out_bits_host, uint32_t* flags_host, int threads);
 /* column sums (fp64, deterministic) of DEVICE codes (n, ncols): the numerator of `db_codes.mean(dim=0)`
  * (zero_mean_eval); with a row-sharded gallery the caller all-reduces the sums over ranks. */
 int ch_column_sums(ch_ws* ws, const void* codes_dev, int dtype, int64_t n, int ncols, int64_t row_stride,

@@ -76,3 +76,46 @@ def lib_call_fails(ws):
     lib = _lib.load()
     rc = lib.ch_workspace_create(0, ctypes.byref(ws))
     return rc != 0 and len(lib.ch_last_error()) > 0
+
+
+@pytest.mark.parametrize("nbit", [1, 8, 31, 32, 33, 64, 100, 128, 200, 256])
+def test_host_pack_sign_bit_exact(lib, nbit):
+    """ch_host_pack_sign (the host half of K1 for pageable fp32 codes; runs without a GPU): bit = (x > 0) exactly --
+    +-0.0, denormals, infinities, NaN flag, zero flag, strided rows, every thread count."""
+    import numpy as np
+    rng = np.random.RandomState(nbit)
+    n, stride = 1037, nbit + 5
+    buf = rng.randn(n, stride).astype(np.float32)
+    x = buf[:, :nbit]
+    x[3, 0] = 0.0
+    x[5, nbit - 1] = -0.0
+    x[7, nbit // 2] = np.float32(1e-45)       # denormal > 0
+    x[9, 0] = -np.inf
+    x[11, nbit - 1] = np.inf
+    words = lib.ch_code_words(nbit)
+    want = np.zeros((n, words * 32), dtype=np.uint8)
+    want[:, :nbit] = x > 0
+    want = np.packbits(want, axis=1, bitorder="little").view(np.uint32)
+    for threads in (1, 3, 8):
+        out = np.full((n, words), 0xDEADBEEF, dtype=np.uint32)
+        flags = ctypes.c_uint32(0)
+        rc = lib.ch_host_pack_sign(buf.ctypes.data, n, nbit, stride, out.ctypes.data, ctypes.byref(flags), threads)
+        assert rc == 0 and np.array_equal(out, want) and flags.value == 1
+    x[100, 1 % nbit] = np.nan
+    flags = ctypes.c_uint32(0)
+    lib.ch_host_pack_sign(buf.ctypes.data, n, nbit, stride, out.ctypes.data, ctypes.byref(flags), 2)
+    assert flags.value == 3
+    clean = np.abs(rng.randn(64, nbit)).astype(np.float32) + 0.5
+    flags = ctypes.c_uint32(0)
+    out = np.zeros((64, words), dtype=np.uint32)
+    lib.ch_host_pack_sign(clean.ctypes.data, 64, nbit, nbit, out.ctypes.data, ctypes.byref(flags), 4)
+    assert flags.value == 0 and int(np.unpackbits(out.view(np.uint8)).sum()) == 64 * nbit
+    # big enough for the thread pool to really split the rows (>= 1 MB per thread)
+    big = rng.randn(40000, nbit).astype(np.float32) if nbit >= 64 else None
+    if big is not None:
+        w2 = np.zeros((40000, words * 32), dtype=np.uint8)
+        w2[:, :nbit] = big > 0
+        w2 = np.packbits(w2, axis=1, bitorder="little").view(np.uint32)
+        out = np.zeros((40000, words), dtype=np.uint32)
+        lib.ch_host_pack_sign(big.ctypes.data, 40000, nbit, nbit, out.ctypes.data, None, 8)
+        assert np.array_equal(out, w2)

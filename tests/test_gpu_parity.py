@@ -89,6 +89,33 @@ def test_pack_sign_large_host_chunks(H):
     assert np.array_equal(_unpack(bits[:300_001], 64), (x.numpy() > 0).astype(np.uint8))
 
 
+@pytest.mark.parametrize("nbit", [16, 48, 64, 100, 128, 256])
+def test_host_pack_equals_device_pack(H, nbit):
+    """PAGEABLE fp32 codes (what trainers/base.py:291-304 hands over) are sign-packed by the host's cores on their
+    way into the pinned bounce buffer (host_pack.cpp) -- the bits, the pad rows and the zero / NaN flags must be
+    those of the CUDA kernel; more rows than one bounce buffer holds; strided row views (the streamed sample)."""
+    ev = H.get_evaluator()
+    g = torch.Generator().manual_seed(nbit)
+    n = 70_001
+    x = torch.randn(n, nbit, generator=g)
+    assert not x.is_pinned()
+    for poke in (None, "zero", "nan"):
+        if poke == "zero":
+            x[n // 2, nbit - 1] = 0.0
+        if poke == "nan":
+            x[n // 3, 0] = float("nan")
+        f_host, f_dev = ev.b.zeros((1,), torch.int32), ev.b.zeros((1,), torch.int32)
+        host, _ = ev.b.pack_sign(x, 0.0, f_host, want_nz=False)
+        dev, _ = ev.b.pack_sign(x.cuda(), 0.0, f_dev, want_nz=False)
+        assert torch.equal(host, dev) and int(f_host.cpu()[0]) == int(f_dev.cpu()[0]) == {None: 0, "zero": 1, "nan": 3}[poke]
+    y = torch.randn(4000, 4 * nbit, generator=g)
+    view = y[:, nbit:2 * nbit]                          # row stride 4 * nbit
+    f1, f2 = ev.b.zeros((1,), torch.int32), ev.b.zeros((1,), torch.int32)
+    a, _ = ev.b.pack_sign(view, 0.0, f1, want_nz=False)
+    b, _ = ev.b.pack_sign(view.cuda(), 0.0, f2, want_nz=False)
+    assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("ncls", [1, 5, 32, 33, 200, 555])
 def test_pack_labels(H, ncls):
     ev = H.get_evaluator()
