@@ -116,6 +116,20 @@ def test_host_pack_equals_device_pack(H, nbit):
     assert torch.equal(a, b)
 
 
+def test_host_pack_more_rows_than_one_bounce_buffer(H):
+    """17 M rows of 16-bit codes = 68 MB of packed words: two passes through the (double-buffered) 64 MB pinned
+    bounce buffers, the second host pass overlapping the DMA of the first"""
+    ev = H.get_evaluator()
+    n = 17_000_000
+    x = torch.empty(n, 16).uniform_(-1, 1, generator=torch.Generator().manual_seed(3))
+    f1, f2 = ev.b.zeros((1,), torch.int32), ev.b.zeros((1,), torch.int32)
+    a, _ = ev.b.pack_sign(x, 0.0, f1, want_nz=False)
+    dev = x.cuda()
+    del x
+    b, _ = ev.b.pack_sign(dev, 0.0, f2, want_nz=False)
+    assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("ncls", [1, 5, 32, 33, 200, 555])
 def test_pack_labels(H, ncls):
     ev = H.get_evaluator()
