@@ -28,8 +28,6 @@
 // Operands live in shared memory in the canonical NO-SWIZZLE K-major core-matrix layout (8 rows x 16 bytes =
 // 128 contiguous bytes; next 16-byte K chunk at +128 B (LBO); next 8-row group at +8*KB (SBO)).  The int8 planes
 // are stored in HBM already in that order (expand_i8_tiled_kernel), so a tile is one contiguous bulk copy.
-#include <stdlib.h>
-
 #include "common.cuh"
 
 namespace {
@@ -391,177 +389,6 @@ __global__ void __launch_bounds__(128 + 128 * kQT, 1) hamming_select_tc_kernel(c
   }
 }
 
-// ---- variant 2: the epilogue warpgroup issues the MMAs of its OWN accumulator ------------------------------
-// Same data flow as above, different hand-over: in the kernel above an accumulator goes round
-//   MMA batch -> commit -> tfull seen by the epilogue warps -> TMEM loads -> tempty (mbarrier) seen by a separate
-//   issuer warp -> shared-memory lock -> next batch,
-// and the last two steps cost 150-280 + 200-340 clk per (tile, accumulator) (profiles/r1g_select_timeline_*).
-// Here the four epilogue warps of a query tile meet at a 128-thread named barrier once their TMEM loads have
-// landed, and the first of them issues the next batch right there (no issuer warp, no tempty barrier, no lock)
-// before it examines its own registers.  Warp 0 only feeds the gallery-tile ring.
-template <int KB, bool DENSE>
-__global__ void __launch_bounds__(128 + 128 * kQT, 1) hamming_select_tc2_kernel(const SelDev a) {
-  typedef SelSmem<KB> S;
-  constexpr int kStages = stages_for(KB);
-  extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t bar_a, bar_full[kStages], bar_empty[kStages], bar_tfull[kQT];
-  __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  const int qgroup = blockIdx.x % a.nqgroups;
-  const int stripe = blockIdx.x / a.nqgroups;
-  const int qtile0 = qgroup * kQT;
-  int nvalid = a.nqtiles128 - qtile0;
-  if (nvalid > kQT) nvalid = kQT;
-  const long long row_begin = static_cast<long long>(stripe) * a.rows_per_stripe;
-  long long row_end = row_begin + a.rows_per_stripe;
-  if (row_end > a.ndb) row_end = a.ndb;
-  const int ntiles = row_end > row_begin ? static_cast<int>((row_end - row_begin + kTileN - 1) / kTileN) : 0;
-
-  if (tid == 0) {
-    mbar_init(&bar_a, 1);
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&bar_full[s], 1);
-      mbar_init(&bar_empty[s], 4 * nvalid);   // every epilogue warp, once it has seen its accumulator complete
-    }
-    for (int i = 0; i < kQT; ++i) mbar_init(&bar_tfull[i], 1);
-    fence_mbar_init();
-  }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
-                 "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;
-
-  if (warp == 0) {
-    // ===================== producer: query tiles once, then the gallery-tile ring =====================
-    if (ntiles > 0) {
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&bar_a, nvalid * S::kA);
-        bulk_g2s(smem + S::offA, a.q_i8 + static_cast<size_t>(qtile0) * kTileM * KB, nvalid * S::kA, &bar_a);
-      }
-      for (int t = 0; t < ntiles; ++t) {
-        const int st = t % kStages;
-        if (t >= kStages) mbar_wait(&bar_empty[st], static_cast<uint32_t>(((t / kStages) & 1) ^ 1));
-        const long long r0 = row_begin + static_cast<long long>(t) * kTileN;
-        long long rows = row_end - r0;
-        if (rows > kTileN) rows = kTileN;
-        const uint32_t rows32 = static_cast<uint32_t>((rows + 31) & ~31ll);
-        const uint32_t bytes_b = rows32 * KB;
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&bar_full[st], bytes_b);
-          bulk_g2s(smem + S::offB + st * S::kB, a.g_i8 + static_cast<size_t>(r0) * KB, bytes_b, &bar_full[st]);
-        }
-        __syncwarp();
-      }
-    }
-  } else if (warp >= 4 && ((warp - 4) >> 2) < nvalid) {
-    // ===================== epilogue + MMA issue: thread = TMEM lane = query =====================
-    const int qt = (warp - 4) >> 2;                // query tile = accumulator of this warpgroup
-    const int e = (tid - 128) & 127;               // 0..127 within the query tile
-    const int ewarp = warp & 3;                    // TMEM lanes 32 * ewarp ..
-    const long long q = static_cast<long long>(qtile0 + qt) * kTileM + e;
-    const bool active = q < a.nq;
-    const size_t sq = static_cast<size_t>(stripe) * a.nq_pad + q;
-    uint32_t n = 0, cap = 0;
-    uint32_t* out = a.cand_rows;
-    if (active) {
-      out += a.cand_off[sq];
-      cap = a.cand_cap[sq];
-    }
-    const uint32_t row_lim = active ? static_cast<uint32_t>(a.row_base + row_end) : 0u;
-    const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ewarp * 32) << 16) + static_cast<uint32_t>(qt) * kTileN;
-    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kTileN >> 3) << 17) |
-                           (static_cast<uint32_t>(kTileM >> 4) << 24);
-    const uint64_t da = umma_desc(smem_u32(smem + S::offA + qt * S::kA), 128, 8 * KB);
-    const uint64_t db0 = umma_desc(smem_u32(smem + S::offB), 128, 8 * KB);
-    const uint32_t d_addr = tmem_base + static_cast<uint32_t>(qt * kTileN);
-
-    // the MMAs of gallery tile t into this warpgroup's accumulator (called by its first warp, converged)
-    auto issue_tile = [&](int t) {
-      const int s = t % kStages;
-      mbar_wait_spin(&bar_full[s], static_cast<uint32_t>((t / kStages) & 1));
-      tc_fence_after();
-      const uint64_t db = db0 + static_cast<uint64_t>((s * S::kB) >> 4);
-      if (elect_one()) {
-        umma_i8_imm<false>(d_addr, da, db, idesc);
-#pragma unroll
-        for (int kk = 1; kk < KB / 32; ++kk)
-          umma_i8_imm<true>(d_addr, da + static_cast<uint64_t>((kk * 256) >> 4),
-                            db + static_cast<uint64_t>((kk * 256) >> 4), idesc);
-        umma_commit(&bar_tfull[qt]);
-      }
-      __syncwarp();
-    };
-    auto emit = [&](uint32_t cand, uint32_t row0) {
-      while (cand != 0u) {
-        const uint32_t z = static_cast<uint32_t>(__clz(static_cast<int>(cand)));
-        cand &= ~(0x80000000u >> z);
-        const uint32_t row = row0 + z;
-        if (row < row_lim) {
-          if (n < cap) out[n] = row;
-          ++n;
-        }
-      }
-    };
-
-    if (ntiles > 0 && ewarp == 0) {
-      mbar_wait_spin(&bar_a, 0);
-      issue_tile(0);
-    }
-    uint32_t ra[32], rb[32];
-    for (int k = 0; k < ntiles; ++k) {
-      const uint32_t row0 = static_cast<uint32_t>(a.row_base + row_begin) + static_cast<uint32_t>(k) * kTileN;
-      mbar_wait(&bar_tfull[qt], static_cast<uint32_t>(k & 1));
-      tc_fence_after();
-      if (lane == 0) mbar_arrive(&bar_empty[k % kStages]);   // this query tile's MMAs are done with the stage
-      tmem_ld64p_issue(taddr0, ra);
-      tmem_ld64p_issue(taddr0 + 64, rb);
-      tmem_wait(ra);
-      tmem_wait(rb);
-      // the whole accumulator is in registers: hand it back to the tensor core -- all four warps of the tile meet
-      // (named barrier 1 + qt), then the first one issues the next batch before it looks at its own registers
-      tc_fence_before();
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + qt) : "memory");
-      if (ewarp == ((k + 1) & 3) && k + 1 < ntiles) issue_tile(k + 1);   // (the issue delay rotates over the warps)
-      uint32_t m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
-      if (DENSE) {
-        m0 = ~sign_mask32p(ra);
-        m1 = ~sign_mask32p(ra + 16);
-        m2 = ~sign_mask32p(rb);
-        m3 = ~sign_mask32p(rb + 16);
-      } else {
-        const bool h0 = any_candidate32p(ra), h1 = any_candidate32p(ra + 16);
-        const bool h2 = any_candidate32p(rb), h3 = any_candidate32p(rb + 16);
-        if (h0) m0 = ~sign_mask32p(ra);
-        if (h1) m1 = ~sign_mask32p(ra + 16);
-        if (h2) m2 = ~sign_mask32p(rb);
-        if (h3) m3 = ~sign_mask32p(rb + 16);
-      }
-      emit(m0, row0);
-      emit(m1, row0 + 32);
-      emit(m2, row0 + 64);
-      emit(m3, row0 + 96);
-    }
-    if (active) {
-      a.cand_cnt[sq] = n < cap ? n : cap;
-      if (n > cap) atomicOr(a.err_flag, 1u);
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-  }
-}
-
 // packed sign bits -> {-1, 0, +1} int8 in the tiled core-matrix order; one thread per (row, 16-byte K chunk).
 // A clear bit of the non-zero plane `nz` (ternary codes: sign(0) = 0) gives 0 -- the contraction then is the
 // ternary inner product and key = 2 x distance = nbit - <q, g> (oracle/map_oracle.py hamming_distance_matrix).
@@ -623,19 +450,9 @@ __global__ void expand_i8_tiled_kernel(const uint32_t* __restrict__ bits, const 
 }
 
 typedef void (*sel_fn_t)(const SelDev);
-int select_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("CH_SELECT_VARIANT");
-    v = (e != nullptr && e[0] == '1') ? 1 : ((e != nullptr && e[0] == '2') ? 2 : 0);
-  }
-  return v;
-}
 template <int KB>
 sel_fn_t pick_dense(int dense, size_t* smem) {
   *smem = SelSmem<KB>::total;
-  if (select_variant() == 2)
-    return dense ? hamming_select_tc2_kernel<KB, true> : hamming_select_tc2_kernel<KB, false>;
   return dense ? hamming_select_tc_kernel<KB, true> : hamming_select_tc_kernel<KB, false>;
 }
 sel_fn_t pick_sel(int kb, int dense, size_t* smem) {
