@@ -35,9 +35,9 @@ class FinalArgs(C.Structure):
 
 
 class SelectArgs(C.Structure):
-    _fields_ = [(n, P) for n in ("q_i8", "g_i8", "cand_off", "cand_cap", "cand_cnt", "cand_rows", "err_flag")] + \
+    _fields_ = [(n, P) for n in ("q_i8", "g_i8", "cand_off", "cand_cap", "cand_cnt", "cand_rows", "err_flag", "thresh")] + \
                [(n, C.c_int64) for n in ("nq", "nq_pad", "ndb", "row_base")] + \
-               [(n, C.c_int32) for n in ("nbit", "nstripes", "rows_per_stripe", "dense")]
+               [(n, C.c_int32) for n in ("nbit", "nstripes", "rows_per_stripe", "dense", "ternary")]
 
 
 class CandArgs(C.Structure):
@@ -72,7 +72,8 @@ SIGNATURES = {
     "ch_hamming_hist": (C.c_int, [P, C.POINTER(HistArgs), P]),
     "ch_tc_code_bytes": (C.c_int, [C.c_int]),
     "ch_tc_queries_per_cta": (C.c_int, []),
-    "ch_expand_i8": (C.c_int, [P, P, P, C.c_int64, C.c_int, C.c_int, P, C.c_int64, P, C.c_int64, P]),
+    "ch_tc_code_bytes_bare": (C.c_int, [C.c_int]),
+    "ch_expand_i8": (C.c_int, [P, P, P, C.c_int64, C.c_int, C.c_int, C.c_int, P, C.c_int64, P, C.c_int64, P]),
     "ch_hamming_select_tc": (C.c_int, [P, C.POINTER(SelectArgs), P]),
     "ch_cand_hist": (C.c_int, [P, C.POINTER(CandArgs), P]),
     "ch_gather_plane_words": (C.c_int, [C.c_int]),

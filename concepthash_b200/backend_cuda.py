@@ -188,33 +188,38 @@ class CudaBackend:
         return th.value, nqp.value, st.value, rps.value
 
     # ---- tensor-core select pass ----
-    def tc_code_bytes(self, nbit):
-        return int(self.lib.ch_tc_code_bytes(int(nbit)))
+    def tc_code_bytes(self, nbit, bare=False):
+        """bytes per row of an int8 operand plane; ``bare``: without threshold slots (comparison in the epilogue)"""
+        return int((self.lib.ch_tc_code_bytes_bare if bare else self.lib.ch_tc_code_bytes)(int(nbit)))
 
-    def expand_i8_into(self, bits, nbit, out):
+    def expand_i8_into(self, bits, nbit, out, bare=False):
         """gallery plane of a row block: ``bits`` (rows, words) -> ``out`` (rows, kb) views of larger arrays"""
         assert bits.shape[0] % 32 == 0 and out.shape[0] >= bits.shape[0]
-        L.check(self.lib.ch_expand_i8(self.ws, _ptr(bits), None, int(bits.shape[0]), nbit, 0, _ptr(out),
+        L.check(self.lib.ch_expand_i8(self.ws, _ptr(bits), None, int(bits.shape[0]), nbit, 0, int(bool(bare)), _ptr(out),
                                       int(bits.shape[0]), None, 0, self._stream()), "ch_expand_i8")
 
-    def expand_i8(self, bits, nbit, min_rows=0, thresh=None, nq=0, nz=None):
+    def expand_i8(self, bits, nbit, min_rows=0, thresh=None, nq=0, nz=None, bare=False, query=False):
         """packed sign bits (rows_pad, words) -> {-1, 0, +1} int8 plane in the tiled operand order (rows, kb) int8,
         with the threshold slots: gallery plane when ``thresh`` is None, else the query plane of ``nq`` queries.
         ``nz``: the non-zero plane of ternary codes (thresholds are then on the doubled key scale).
         ``min_rows`` over-allocates so that whole 128-query tiles can be read."""
-        kb = self.tc_code_bytes(nbit)
+        kb = self.tc_code_bytes(nbit, bare)
         rows_pad = int(bits.shape[0])
         rows = max(rows_pad, (int(min_rows) + 31) // 32 * 32)
         out = self.empty((rows, kb), torch.int8)
-        L.check(self.lib.ch_expand_i8(self.ws, _ptr(bits), _ptr(nz), rows_pad, nbit, 0 if nz is None else 1, _ptr(out),
-                                      rows, _ptr(thresh), int(nq), self._stream()), "ch_expand_i8")
+        L.check(self.lib.ch_expand_i8(self.ws, _ptr(bits), _ptr(nz), rows_pad, nbit, 0 if nz is None else 1,
+                                      (2 if query else 1) if bare else 0, _ptr(out), rows,
+                                      None if bare else _ptr(thresh), int(nq), self._stream()), "ch_expand_i8")
         return out
 
     def hamming_select_tc(self, *, q_i8, g_i8, cand, nq, nq_pad, ndb, nbit, nstripes, rows_per_stripe, row_base=0,
-                          dense=False, stripe0=0):
+                          dense=False, stripe0=0, thresh=None, ternary=False):
         """``cand``: dict(off, cap, cnt (nstripes_total, nq_pad) u32, rows u32[], err u32[1]); ``stripe0`` = first
-        stripe of this call's row block (streamed galleries)."""
+        stripe of this call's row block (streamed galleries).  ``thresh``: the per-query thresholds when both planes
+        are ``bare`` (comparison in the sparse epilogue instead of a threshold block in the contraction)."""
         a = L.SelectArgs()
+        a.thresh = thresh.data_ptr() if thresh is not None else None
+        a.ternary = int(bool(ternary))
         a.q_i8, a.g_i8 = q_i8.data_ptr(), g_i8.data_ptr()
         a.cand_off, a.cand_cap, a.cand_cnt = (cand[k][stripe0:].data_ptr() for k in ("off", "cap", "cnt"))
         a.cand_rows, a.err_flag = cand["rows"].data_ptr(), cand["err"].data_ptr()

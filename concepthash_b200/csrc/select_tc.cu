@@ -95,6 +95,8 @@ struct SelDev {
   uint32_t* cand_cnt;          // (nstripes, nq_pad)
   uint32_t* cand_rows;         // shard-local row index of every candidate
   uint32_t* err_flag;
+  const uint32_t* thresh;      // per-query threshold keys when the comparison happens in the epilogue, else NULL
+  int nbit, ternary;
   long long nq, nq_pad, ndb, row_base;
   int rows_per_stripe;
   int nqtiles128;              // 128-query tiles in total
@@ -132,6 +134,30 @@ __device__ __forceinline__ bool any_candidate32p(const uint32_t* r) {
   const uint32_t a3 = r[9] & r[10] & r[11], a4 = r[12] & r[13] & r[14];
   const uint32_t x = (a0 & a1 & a2) & (a3 & a4 & r[15]);
   return (x & 0x80008000u) != 0x80008000u;
+}
+
+// ---- the comparison in the epilogue (sparse passes: the threshold block of the contraction is dropped) ----------
+// The accumulator then is the plain inner product <q, g>, and key <= thresh <=> <q, g> >= tau, tau = nbit - 2 thresh
+// (binary) or nbit - thresh (ternary, doubled key scale).  t2 = tau in both 16-bit halves.  Whether a 32-column chunk
+// holds a candidate is a packed 16-bit MAX tree (VIMNMX3.S16x2: 8 instructions for 16 registers, as many as the AND
+// tree of sign bits above) and one packed subtraction; only chunks that do hold one pay for the 16 packed
+// subtractions that turn their registers into the D >= 0 form sign_mask32p expects.
+__device__ __forceinline__ bool any_candidate32p_tau(const uint32_t* r, uint32_t t2) {
+  uint32_t m = __vmaxs2(__vmaxs2(r[0], r[1]), r[2]);
+#pragma unroll
+  for (int j = 3; j + 1 < 16; j += 2) m = __vmaxs2(__vmaxs2(m, r[j]), r[j + 1]);
+  m = __vmaxs2(m, r[15]);
+  return (__vsub2(m, t2) & 0x80008000u) != 0x80008000u;
+}
+__device__ __forceinline__ uint32_t sign_mask32p_tau(const uint32_t* r, uint32_t t2) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    uint32_t p;
+    asm("prmt.b32 %0, %1, %2, 0xfdb9;" : "=r"(p) : "r"(__vsub2(r[2 * k], t2)), "r"(__vsub2(r[2 * k + 1], t2)));
+    m |= p & (0x01010101u << k);
+  }
+  return m;
 }
 
 // the MMA with a compile-time accumulate flag (no predicate set-up on the single issuing thread)
@@ -181,7 +207,8 @@ __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
 }
 
 // One CTA = kQT consecutive 128-query tiles x one gallery stripe.
-template <int KB, bool DENSE>
+// TAU: the threshold comparison happens in the epilogue (planes without threshold slots, KB = the code bytes only)
+template <int KB, bool DENSE, bool TAU>
 __global__ void __launch_bounds__(128 + 128 * kQT, 1) hamming_select_tc_kernel(const SelDev a) {
   typedef SelSmem<KB> S;
   constexpr int kStages = stages_for(KB);
@@ -327,6 +354,11 @@ __global__ void __launch_bounds__(128 + 128 * kQT, 1) hamming_select_tc_kernel(c
     // an inactive lane (query padding) accepts nothing
     const uint32_t row_lim = active ? static_cast<uint32_t>(a.row_base + row_end) : 0u;
     const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ewarp * 32) << 16) + static_cast<uint32_t>(qt) * kTileN;
+    uint32_t t2 = 0x7fff7fffu;                     // (inactive lanes: nothing reaches the threshold)
+    if (TAU && active) {
+      const int tau = a.nbit - (a.ternary ? 1 : 2) * static_cast<int>(a.thresh[q]);
+      t2 = (static_cast<uint32_t>(tau) & 0xffffu) * 0x10001u;
+    }
 
     // candidates of one 32-row block (bit 31 - t = row row0 + t), appended in ascending row order
     auto emit = [&](uint32_t cand, uint32_t row0) {
@@ -362,6 +394,13 @@ __global__ void __launch_bounds__(128 + 128 * kQT, 1) hamming_select_tc_kernel(c
         m1 = ~sign_mask32p(ra + 16);
         m2 = ~sign_mask32p(rb);
         m3 = ~sign_mask32p(rb + 16);
+      } else if (TAU) {
+        const bool h0 = any_candidate32p_tau(ra, t2), h1 = any_candidate32p_tau(ra + 16, t2);
+        const bool h2 = any_candidate32p_tau(rb, t2), h3 = any_candidate32p_tau(rb + 16, t2);
+        if (h0) m0 = ~sign_mask32p_tau(ra, t2);
+        if (h1) m1 = ~sign_mask32p_tau(ra + 16, t2);
+        if (h2) m2 = ~sign_mask32p_tau(rb, t2);
+        if (h3) m3 = ~sign_mask32p_tau(rb + 16, t2);
       } else {
         const bool h0 = any_candidate32p(ra), h1 = any_candidate32p(ra + 16);
         const bool h2 = any_candidate32p(rb), h3 = any_candidate32p(rb + 16);
@@ -397,7 +436,7 @@ __global__ void __launch_bounds__(128 + 128 * kQT, 1) hamming_select_tc_kernel(c
 // the doubled scale), so that D = <q, g> - tau >= 0 <=> key <= thresh; padding queries get the most negative sum.
 __global__ void expand_i8_tiled_kernel(const uint32_t* __restrict__ bits, const uint32_t* __restrict__ nz,
                                        long long rows_bits, long long rows_out, int words, int nbit, int kb, int slots,
-                                       int ternary, const uint32_t* __restrict__ thresh, long long nq,
+                                       int ternary, int query, const uint32_t* __restrict__ thresh, long long nq,
                                        int8_t* __restrict__ out) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int chunks = kb / 16;
@@ -408,7 +447,7 @@ __global__ void expand_i8_tiled_kernel(const uint32_t* __restrict__ bits, const 
   const int chunk = within / 8, r8 = within % 8;
   const long long row = group * 8 + r8;        // row of the PLANE = TMEM lane (queries) / TMEM column (gallery)
   // gallery planes: column c of a 32-row block holds row kRowOfColumn(c) of that block (see sign_mask32p)
-  const long long src = thresh != nullptr ? row : (row & ~31ll) + kRowOfColumn(static_cast<int>(row & 31));
+  const long long src = query ? row : (row & ~31ll) + kRowOfColumn(static_cast<int>(row & 31));
   const int k0 = chunk * 16;
   uint32_t w = 0, z = 0xffffffffu;
   const bool has_bits = src < rows_bits;
@@ -451,21 +490,22 @@ __global__ void expand_i8_tiled_kernel(const uint32_t* __restrict__ bits, const 
 
 typedef void (*sel_fn_t)(const SelDev);
 template <int KB>
-sel_fn_t pick_dense(int dense, size_t* smem) {
+sel_fn_t pick_dense(int dense, int tau, size_t* smem) {
   *smem = SelSmem<KB>::total;
-  return dense ? hamming_select_tc_kernel<KB, true> : hamming_select_tc_kernel<KB, false>;
+  if (tau) return hamming_select_tc_kernel<KB, false, true>;
+  return dense ? hamming_select_tc_kernel<KB, true, false> : hamming_select_tc_kernel<KB, false, false>;
 }
-sel_fn_t pick_sel(int kb, int dense, size_t* smem) {
+sel_fn_t pick_sel(int kb, int dense, int tau, size_t* smem) {
   switch (kb) {
-    case 32: return pick_dense<32>(dense, smem);
-    case 64: return pick_dense<64>(dense, smem);
-    case 96: return pick_dense<96>(dense, smem);
-    case 128: return pick_dense<128>(dense, smem);
-    case 160: return pick_dense<160>(dense, smem);
-    case 192: return pick_dense<192>(dense, smem);
-    case 224: return pick_dense<224>(dense, smem);
-    case 256: return pick_dense<256>(dense, smem);
-    default: return pick_dense<288>(dense, smem);
+    case 32: return pick_dense<32>(dense, tau, smem);
+    case 64: return pick_dense<64>(dense, tau, smem);
+    case 96: return pick_dense<96>(dense, tau, smem);
+    case 128: return pick_dense<128>(dense, tau, smem);
+    case 160: return pick_dense<160>(dense, tau, smem);
+    case 192: return pick_dense<192>(dense, tau, smem);
+    case 224: return pick_dense<224>(dense, tau, smem);
+    case 256: return pick_dense<256>(dense, tau, smem);
+    default: return pick_dense<288>(dense, tau, smem);
   }
 }
 
@@ -481,12 +521,19 @@ extern "C" int ch_tc_code_bytes(int nbit) {
   return (nbit + thresh_slots(nbit) + 31) / 32 * 32;   // the codes + the threshold slots, in whole 32-byte K blocks
 }
 
+extern "C" int ch_tc_code_bytes_bare(int nbit) {
+  if (nbit <= 0 || nbit > CH_MAX_NBIT) return 0;
+  return (nbit + 31) / 32 * 32;                        // no threshold slots: the comparison happens in the epilogue
+}
+
 extern "C" int ch_expand_i8(ch_ws* ws, const uint32_t* bits_dev, const uint32_t* nz_dev, int64_t rows_bits, int nbit,
-                            int ternary, int8_t* out_dev, int64_t rows_out, const uint32_t* thresh_dev, int64_t nq,
-                            void* stream) {
+                            int ternary, int bare, int8_t* out_dev, int64_t rows_out, const uint32_t* thresh_dev,
+                            int64_t nq, void* stream) {
   if (ws == nullptr || bits_dev == nullptr || out_dev == nullptr) CH_FAIL("null argument to ch_expand_i8");
   if (ternary && nz_dev == nullptr) CH_FAIL("ternary codes need the non-zero plane");
-  const int kb = ch_tc_code_bytes(nbit);
+  if (bare && thresh_dev != nullptr) CH_FAIL("a plane without threshold slots takes no thresholds");
+  if (bare < 0 || bare > 2) CH_FAIL("bare: 0 = threshold slots, 1 = bare gallery plane, 2 = bare query plane");
+  const int kb = bare ? ch_tc_code_bytes_bare(nbit) : ch_tc_code_bytes(nbit);
   if (kb == 0) CH_FAIL("nbit=%d unsupported by the tensor-core path (1..%d)", nbit, CH_MAX_NBIT);
   if (rows_out % 32 || rows_bits < 0 || rows_out < rows_bits)
     CH_FAIL("rows_out must be a multiple of 32 (whole permuted row blocks) and >= rows_bits");
@@ -494,8 +541,9 @@ extern "C" int ch_expand_i8(ch_ws* ws, const uint32_t* bits_dev, const uint32_t*
   ChDeviceGuard guard(ws->device);
   const long long n = rows_out * (kb / 16);
   expand_i8_tiled_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      bits_dev, ternary ? nz_dev : nullptr, rows_bits, rows_out, ch_code_words(nbit), nbit, kb, thresh_slots(nbit),
-      ternary ? 1 : 0, thresh_dev, nq, out_dev);
+      bits_dev, ternary ? nz_dev : nullptr, rows_bits, rows_out, ch_code_words(nbit), nbit, kb,
+      bare ? 0 : thresh_slots(nbit), ternary ? 1 : 0, (thresh_dev != nullptr || bare == 2) ? 1 : 0, thresh_dev, nq,
+      out_dev);
   CH_LAUNCH_CHECK(ws);
   return 0;
 }
@@ -505,8 +553,10 @@ extern "C" int ch_hamming_select_tc(ch_ws* ws, const ch_select_args* a, void* st
   if (a->q_i8 == nullptr || a->g_i8 == nullptr || a->cand_off == nullptr || a->cand_cap == nullptr ||
       a->cand_cnt == nullptr || a->cand_rows == nullptr || a->err_flag == nullptr)
     CH_FAIL("null array in ch_select_args");
-  const int kb = ch_tc_code_bytes(a->nbit);
+  const int tau = a->thresh != nullptr ? 1 : 0;       // comparison in the epilogue: planes without threshold slots
+  const int kb = tau ? ch_tc_code_bytes_bare(a->nbit) : ch_tc_code_bytes(a->nbit);
   if (kb == 0) CH_FAIL("nbit=%d unsupported by the tensor-core path (1..%d)", a->nbit, CH_MAX_NBIT);
+  if (tau && a->dense) CH_FAIL("the epilogue-side comparison exists for the sparse epilogue only");
   if (a->nq <= 0 || a->ndb < 0) CH_FAIL("bad arguments");
   if (a->nq_pad % kTileM || a->nq_pad < a->nq) CH_FAIL("nq_pad must be a multiple of %d and >= nq", kTileM);
   if (a->nstripes <= 0 || a->rows_per_stripe <= 0 || a->rows_per_stripe % kTileN ||
@@ -520,12 +570,13 @@ extern "C" int ch_hamming_select_tc(ch_ws* ws, const ch_select_args* a, void* st
   d.q_i8 = a->q_i8; d.g_i8 = a->g_i8;
   d.cand_off = a->cand_off; d.cand_cap = a->cand_cap; d.cand_cnt = a->cand_cnt; d.cand_rows = a->cand_rows;
   d.err_flag = a->err_flag;
+  d.thresh = a->thresh; d.nbit = a->nbit; d.ternary = a->ternary;
   d.nq = a->nq; d.nq_pad = a->nq_pad; d.ndb = a->ndb; d.row_base = a->row_base;
   d.rows_per_stripe = a->rows_per_stripe;
   d.nqtiles128 = static_cast<int>(a->nq_pad / kTileM);
   d.nqgroups = (d.nqtiles128 + kQT - 1) / kQT;
   size_t smem = 0;
-  sel_fn_t fn = pick_sel(kb, a->dense != 0, &smem);
+  sel_fn_t fn = pick_sel(kb, a->dense != 0, tau, &smem);
   if (smem > static_cast<size_t>(ws->max_smem_optin)) CH_FAIL("tensor-core kernel needs %zu bytes of shared memory", smem);
   if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: each CTA owns all 512 TMEM columns
   CH_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));

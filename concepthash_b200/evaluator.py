@@ -91,10 +91,11 @@ class _TooManySlots(Exception):
 
 class Packed:
     """Packed codes + labels of one side (query or gallery shard)."""
-    __slots__ = ("n", "nbit", "bits", "nz", "ids", "masks", "info", "ncls", "i8", "plane")
+    __slots__ = ("n", "nbit", "bits", "nz", "ids", "masks", "info", "ncls", "i8", "i8b", "plane")
 
     def __init__(self):
         self.plane = None
+        self.i8b = None          # int8 plane without threshold slots (comparison in the select kernel's epilogue)
 
 
 class _TimedBackend:
@@ -145,14 +146,15 @@ class Evaluator:
         self.sample_two_level = True       # thresholds from the sample by a tensor-core select pass (see below)
         self.sample2_sub = 16              # ... whose own thresholds come from every 16th sample row
         self.sample2_min_rows = 2_048      # ... when every rank's sample has at least this many rows
-        self.sample2_min_work = 1.0e9      # ... and histogramming it would cost >= ~0.2 ms (nq x rows x words); the
-        #                                      two-level route adds a host sync and a collective
+        self.sample2_min_work = 2.0e8      # ... and histogramming it would cost >= ~0.05 ms (nq x rows x words); the
+        #                                      two-level route adds one small all-reduce in group mode
         self.sample_min_rows = 200_000     # below this the two-pass path is cheap anyway
         self.sample_min_ratio = 64         # ... and the sample must still hold ~R/stride*... rows: need ndb >= ratio * R
         self.stream_host_gallery = True    # host-resident gallery: overlap its H2D copy with the select pass
         self.stream_min_rows = 200_000
         self.stream_chunks = 4
         self.use_tensor_cores = True       # select pass on tcgen05 (int8 +-1 codes) when the shape allows it
+        self.epilogue_thresholds = True    # sparse select passes: threshold comparison in the epilogue (see _bare)
         self.select_dense_override = None  # tests: force the dense / sparse epilogue of the tensor-core kernel
         self.col_sub = None                # zero_mean_eval: f64[nbit] column offset of the current evaluation
         self.events = []                   # (kind, work units, start event, end event)
@@ -395,25 +397,49 @@ class Evaluator:
             return bool(self.select_dense_override)
         return expected_per_query * 1024.0 > 0.78 * max(ndb_total, 1)
 
-    def _query_plane(self, q, nq_pad, thresh):
-        """int8 query plane with the thresholds in its threshold slots (made per select pass)"""
+    def _bare(self, dense):
+        """sparse select passes drop the threshold block of the contraction (one K block of 2-5: 64-bit codes contract
+        K = 64 instead of 96) and compare in the epilogue -- a packed 16-bit max tree per 32-column chunk, the same
+        instruction count as the sign-bit AND tree it replaces.  Dense passes keep the block: there every chunk
+        would pay 16 packed subtractions, and the ALU pipe is their second bottleneck."""
+        return bool(self.epilogue_thresholds and not dense and hasattr(self.b, "tc_code_bytes") and
+                    self.b.tc_code_bytes(8, True) > 0)
+
+    def _query_plane(self, q, nq_pad, thresh, bare=False):
+        """int8 query plane: with the thresholds in its threshold slots (made per select pass), or bare"""
         kw = {} if q.nz is None else dict(nz=q.nz)
+        if bare:
+            if q.i8b is None:
+                q.i8b = self._timed("expand_i8", 0, lambda: self.b.expand_i8(q.bits, q.nbit, nq_pad, bare=True,
+                                                                              query=True, **kw))
+            return q.i8b
         return self._timed("expand_i8", 0, lambda: self.b.expand_i8(q.bits, q.nbit, nq_pad, thresh=thresh, nq=q.n, **kw))
 
-    def _gallery_plane(self, p):
+    def _gallery_plane(self, p, bare=False):
         kw = {} if p.nz is None else dict(nz=p.nz)
-        return self._timed("expand_i8", 0, lambda: self.b.expand_i8(p.bits, p.nbit, **kw))
+        if bare:
+            if p.i8b is None:
+                p.i8b = self._timed("expand_i8", 0, lambda: self.b.expand_i8(p.bits, p.nbit, bare=True, **kw))
+            return p.i8b
+        if p.i8 is None:
+            p.i8 = self._timed("expand_i8", 0, lambda: self.b.expand_i8(p.bits, p.nbit, **kw))
+        return p.i8
 
-    def _select_tc(self, q, g, geo, thresh, cand, dense):
-        threads, nq_pad, nstripes, rps = geo
-        q_i8 = self._query_plane(q, nq_pad, thresh)
-        if g.i8 is None:
-            g.i8 = self._gallery_plane(g)
-        self._timed("hist_select_tc", q.n * g.n, lambda: self.b.hamming_select_tc(
-            q_i8=q_i8, g_i8=g.i8, cand=cand, nq=q.n, nq_pad=nq_pad, ndb=g.n, nbit=q.nbit, nstripes=nstripes,
-            rows_per_stripe=rps, dense=dense))
-        self.stats["select_kernel"] = "tcgen05"
-        self.stats["select_dense"] = bool(dense)
+    def _select_tc(self, q, g, geo, thresh, cand, dense, kind="hist_select_tc", ndb=None, nstripes=None, rps=None):
+        """the select pass on the tensor cores over the packed shard ``g`` (or a row sample of it)"""
+        threads, nq_pad, nstripes_g, rps_g = geo
+        bare = self._bare(dense)
+        q_i8 = self._query_plane(q, nq_pad, thresh, bare)
+        g_i8 = self._gallery_plane(g, bare)
+        kw = dict(thresh=thresh, ternary=q.nz is not None) if bare else {}
+        self._timed(kind, q.n * g.n, lambda: self.b.hamming_select_tc(
+            q_i8=q_i8, g_i8=g_i8, cand=cand, nq=q.n, nq_pad=nq_pad, ndb=g.n, nbit=q.nbit,
+            nstripes=nstripes_g if nstripes is None else nstripes, rows_per_stripe=rps_g if rps is None else rps,
+            dense=dense, **kw))
+        if kind == "hist_select_tc":
+            self.stats["select_kernel"] = "tcgen05"
+            self.stats["select_dense"] = bool(dense)
+            self.stats["select_threshold"] = "epilogue" if bare else "contraction"
 
     def _cand_hist(self, c, cand, nbins, tot, stripe0=0, nstripes=None):
         """keys + label matches of the candidates of a block of stripes, accumulated into ``tot`` (2, nbins, nq_pad)"""
@@ -518,7 +544,7 @@ class Evaluator:
         knobs = (self.sample_stride, self.sample_two_level, self.sample2_sub, self.sample2_min_rows,
                  self.sample2_min_work, self.sample_min_rows, self.sample_min_ratio, self.stream_host_gallery,
                  self.stream_min_rows, self.stream_chunks, self.use_tensor_cores, self.select_dense_override,
-                 self.stripe_rows_override)
+                 self.stripe_rows_override, self.epilogue_thresholds, self.max_slots)
         return (sig(db_codes), sig(db_labels), sig(q_codes), sig(q_labels), tuple(r_list), float(threshold),
                 tuple(pr_k), bool(rf), bool(zero_mean), self.comm.world, knobs)
 
@@ -843,13 +869,18 @@ class Evaluator:
         on block i.  Outputs are exactly those of one whole-shard launch (slabs per stripe, records with shard
         row ids)."""
 
-        def __init__(self, ev, c, flags):
-            self.ev, self.c, self.flags = ev, c, flags
+        def __init__(self, ev, c, flags, bare=False):
+            self.ev, self.c, self.flags, self.bare = ev, c, flags, bare
             b, q, g = ev.b, c["q"], c["g"]
             threads, nq_pad, nstripes, rps = c["geo"]
             self.rows_pad = b.padded_rows(g.n)
             g.bits = b.empty((self.rows_pad, q.bits.shape[1]), torch.int32)
-            g.i8 = b.empty((self.rows_pad, b.tc_code_bytes(q.nbit)), torch.int8)
+            kb = b.tc_code_bytes(q.nbit, True) if bare else b.tc_code_bytes(q.nbit)
+            self.plane8 = b.empty((self.rows_pad, kb), torch.int8)
+            if bare:
+                g.i8b = self.plane8
+            else:
+                g.i8 = self.plane8
             per = ev._stream_per(nq_pad)
             # loads run on a side stream so that they are not queued behind the (long) select kernels
             # one side stream per evaluator, reused by every evaluation: the caching allocator pools blocks per
@@ -885,7 +916,8 @@ class Evaluator:
                 else:
                     ev._timed("pack_host", (r1 - r0) * q.nbit * db_codes.element_size(),
                               lambda: b.pack_sign(blk, 0.0, self.flags, False, out=g.bits[r0:]))
-                ev._timed("expand_i8", 0, lambda: b.expand_i8_into(g.bits[r0:r0 + nrow8], q.nbit, g.i8[r0:]))
+                ev._timed("expand_i8", 0, lambda: b.expand_i8_into(g.bits[r0:r0 + nrow8], q.nbit, self.plane8[r0:],
+                                                                    **(dict(bare=True) if self.bare else {})))
                 done = torch.cuda.Event()
                 done.record(self.side)
             self.loaded[i] = done
@@ -895,14 +927,15 @@ class Evaluator:
             for i in range(len(self.blocks) if self.pinned else 1):
                 self.load(i)
 
-        def select(self, i, cand, q_i8, dense):
+        def select(self, i, cand, q_i8, dense, thresh):
             ev, b, q, g = self.ev, self.ev.b, self.c["q"], self.c["g"]
             threads, nq_pad, nstripes, rps = self.c["geo"]
             s0, s1, r0, r1 = self.blocks[i]
             torch.cuda.current_stream().wait_event(self.loaded[i])
+            kw = dict(thresh=thresh, ternary=False) if self.bare else {}
             ev._timed("hist_select_tc", self.c["nq"] * (r1 - r0), lambda: b.hamming_select_tc(
-                q_i8=q_i8, g_i8=g.i8[r0:], cand=cand, nq=self.c["nq"], nq_pad=nq_pad, ndb=r1 - r0, nbit=q.nbit,
-                nstripes=s1 - s0, rows_per_stripe=rps, row_base=r0, dense=dense, stripe0=s0))
+                q_i8=q_i8, g_i8=self.plane8[r0:], cand=cand, nq=self.c["nq"], nq_pad=nq_pad, ndb=r1 - r0, nbit=q.nbit,
+                nstripes=s1 - s0, rows_per_stripe=rps, row_base=r0, dense=dense, stripe0=s0, **kw))
 
     def _pass_topr_sampled(self, c, streamed=False):
         """Top-R in ONE full pass.  A 1-in-``sample_stride`` row sample of the gallery is histogrammed first; from
@@ -917,6 +950,11 @@ class Evaluator:
         stride = c["stride"]
         # ---- the sample: every stride-th row of the local shard, same stripes (rps is a multiple of stride) ----
         status = self._status            # [ST_PASS] overflow bits, [ST_SHORT] verification / zeros in a streamed sample
+        # (host-known: the sample size and the safety margin decide how dense the candidates of the full pass are)
+        ns_host = (sum(self._host_sample_rows(r, stride, max(1, 256 // g.nbit) if g.nbit in (32, 64, 128, 256) else 1)
+                       for r in c["rows"]) if streamed else sum((r + stride - 1) // stride for r in c["rows"]))
+        mu_host = need * ns_host / max(c["ndb_total"], 1)
+        dense = self._dense(1.25 * stride * (int(mu_host + 5.0 * mu_host ** 0.5 + 4.0) + 1), c["ndb_total"])
         sp = Packed()
         sp.i8 = None
         sp.nbit = g.nbit
@@ -931,7 +969,7 @@ class Evaluator:
             packed, _ = self._timed("pack_host", ns * g.nbit * view.element_size(),
                                     lambda: b.pack_sign(view, 0.0, zflag, False))
             sp.bits = packed.view(-1, q.bits.shape[1])         # (super rows, run * words) -> (rows, words)
-            streamer = self._Streamer(self, c, zflag)
+            streamer = self._Streamer(self, c, zflag, self._bare(dense))
             streamer.side.wait_stream(torch.cuda.current_stream())
         else:
             ns, sp.bits = b.gather_rows(g.bits, g.n, g.nbit, stride)
@@ -953,8 +991,7 @@ class Evaluator:
         # issued right after the first sample kernels have been queued
         first_load = streamer.load_first if streamer is not None else (lambda: None)
         if (tc_pass and self.sample_two_level and min(ns_ranks) >= self.sample2_min_rows and
-                float(nq) * min(ns_ranks) * int(q.bits.shape[1]) >=
-                self.sample2_min_work * (1.0 if comm.world > 1 else 0.2)):   # one GPU: no extra collective to pay
+                float(nq) * min(ns_ranks) * int(q.bits.shape[1]) >= self.sample2_min_work):
             thresh, cap = self._sample_thresholds_tc(c, sp, ns_ranks, m, status, first_load)
         else:
             slab_s = b.zeros((nstripes, nbins, nq_pad), torch.int32)
@@ -976,13 +1013,12 @@ class Evaluator:
             del slab_s, base_tmp
             nbins = min(nbins, tmax + 1)
             self.stats["sample"]["key_limit"] = nbins
-            dense = self._dense(1.25 * stride * m, c["ndb_total"])
             tot = None
             if streamed:
-                q_i8 = self._query_plane(q, nq_pad, thresh)
+                q_i8 = self._query_plane(q, nq_pad, thresh, streamer.bare)
                 tot = b.zeros((2, nbins, nq_pad), torch.int32)
                 for i in range(len(streamer.blocks)):
-                    streamer.select(i, cand, q_i8, dense)
+                    streamer.select(i, cand, q_i8, dense, thresh)
                     if i + 1 < len(streamer.blocks) and (i + 1) not in streamer.loaded:
                         streamer.load(i + 1)     # host waits for this copy while the GPU runs select(i)
                     # keys / label matches of this block's candidates while the next block is still travelling
@@ -990,6 +1026,7 @@ class Evaluator:
                     self._cand_hist(c, cand, nbins, tot, s0, s1 - s0)
                 self.stats["select_kernel"] = "tcgen05"
                 self.stats["select_dense"] = bool(dense)
+                self.stats["select_threshold"] = "epilogue" if streamer.bare else "contraction"
             else:
                 self._select_tc(q, g, geo, thresh, cand, dense)
             base0_all, base0_rel, key_max = self._cand_bases(c, cand, nbins, need, tot, rmax=c["rmax"] + c["rf"])
@@ -1065,22 +1102,14 @@ class Evaluator:
         rps1 = (-(-ns // n1) + tile - 1) // tile * tile
         n1 = max(1, -(-ns // rps1))
         geo1 = (threads, nq_pad, n1, rps1)
-        s_i8 = self._gallery_plane(sp)
         after_level0()              # (host-blocking work of the caller, while the GPU runs level 0)
-        # list capacities of the sample select from the GLOBAL mini-sample count c >= m0 under t0 (a rank's own count
-        # is a thin Poisson split of it: with c_local = 0 the bound would admit a mean of 11 only, and among 10^5
-        # queries some rank-local mean of ~c / world does exceed that) -- for EVERY stripe and rank, because the row
-        # order may put all neighbours of a query into one stripe of one rank
         cap0 = b.empty((n1, nq_pad), torch.int32)
         b.record_caps(0, tot0, thresh0, n1, nbins, nq, nq_pad, False, cap0, sample_stride=sub, replicate=True)
         cand1, tmax0 = self._alloc_cands(cap0, geo1, nq, thresh0, "s1", nbins)
         nb0 = min(nbins, tmax0 + 1)
         # ---- level 1 ----
-        q_i8 = self._query_plane(q, nq_pad, thresh0)
         dense = self._dense(1.25 * sub * m0, sum(ns_ranks))
-        self._timed("sample_select_tc", q.n * ns, lambda: b.hamming_select_tc(
-            q_i8=q_i8, g_i8=s_i8, cand=cand1, nq=nq, nq_pad=nq_pad, ndb=ns, nbit=q.nbit, nstripes=n1,
-            rows_per_stripe=rps1, dense=dense))
+        self._select_tc(q, sp, geo1, thresh0, cand1, dense, kind="sample_select_tc")
         tot1 = b.zeros((nb0, nq_pad), torch.int32)
         kwz = dict(q_nz=q.nz, g_nz=sp.nz) if ternary else {}
         self._timed("cand_hist", 0, lambda: b.cand_hist(

@@ -183,16 +183,25 @@ typedef struct ch_select_args {
   uint32_t* cand_cnt;         /* (nstripes, nq_pad) */
   uint32_t* cand_rows;        /* u32[] */
   uint32_t* err_flag;
+  const uint32_t* thresh;     /* NULL: the thresholds ride in the contraction (planes with threshold slots,
+                                 ch_tc_code_bytes).  Else (nq_pad) keys: the planes carry NO slots
+                                 (ch_tc_code_bytes_bare: one K block less at nbit = 64 / 128 / ...), the accumulator
+                                 is the plain <q, g> and the epilogue compares it with tau = nbit - 2 thresh[q]
+                                 (ternary: nbit - thresh[q]) by packed 16-bit max / subtract; sparse epilogue only */
   int64_t nq, nq_pad, ndb, row_base;   /* nq_pad % 128 == 0; ndb = rows of this call's row block */
   int32_t nbit, nstripes, rows_per_stripe;   /* rows_per_stripe % 128 == 0 */
   int32_t dense;              /* != 0: most 32-row chunks of a warp hold a candidate -> skip the max-tree filter */
+  int32_t ternary;            /* keys on the doubled scale (only read when thresh != NULL) */
 } ch_select_args;
 int ch_tc_code_bytes(int nbit);
 /* queries one CTA of the select kernel owns (its grid is ceil(nq_pad / this) x nstripes, one CTA per SM) */
 int ch_tc_queries_per_cta(void);
+int ch_tc_code_bytes_bare(int nbit);   /* bytes per plane row without threshold slots (see ch_select_args.thresh) */
 int ch_expand_i8(ch_ws* ws, const uint32_t* bits_dev, const uint32_t* nz_dev /* ternary codes, else NULL */,
-                 int64_t rows_bits, int nbit, int ternary, int8_t* out_dev, int64_t rows_out,
-                 const uint32_t* thresh_dev /* or NULL */, int64_t nq, void* stream);
+                 int64_t rows_bits, int nbit, int ternary,
+                 int bare /* 0: threshold slots; 1: gallery plane without; 2: query plane without */,
+                 int8_t* out_dev, int64_t rows_out, const uint32_t* thresh_dev /* or NULL */, int64_t nq,
+                 void* stream);
 int ch_hamming_select_tc(ch_ws* ws, const ch_select_args* a, void* stream);
 
 /* ---- K3/K4 on candidate lists ---------------------------------------------------------------------

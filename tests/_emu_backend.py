@@ -190,18 +190,24 @@ class EmuBackend:
                     cnt[s, q] = min(n_rec, cap[s, q])
 
     # K2, tensor-core form (candidate lists).  The emulation keeps the packed bits + thresholds instead of int8 planes.
-    def tc_code_bytes(self, nbit):
+    def tc_code_bytes(self, nbit, bare=False):
         if not self.tensor_cores or nbit <= 0 or nbit > 256:
             return 0
-        return (nbit + (2 if nbit <= 254 else 4) + 31) // 32 * 32
+        return (nbit + (0 if bare else 2 if nbit <= 254 else 4) + 31) // 32 * 32
 
-    def expand_i8(self, bits, nbit, min_rows=0, thresh=None, nq=0, nz=None):
+    def expand_i8(self, bits, nbit, min_rows=0, thresh=None, nq=0, nz=None, bare=False, query=False):
         self.launches += 1
-        return dict(bits=bits, nz=nz, nbit=nbit, nq=nq, thresh=None if thresh is None else thresh.clone())
+        assert not (bare and thresh is not None)
+        return dict(bits=bits, nz=nz, nbit=nbit, nq=nq, bare=bare, thresh=None if thresh is None else thresh.clone())
 
     def hamming_select_tc(self, *, q_i8, g_i8, cand, nq, nq_pad, ndb, nbit, nstripes, rows_per_stripe, row_base=0,
-                          dense=False, stripe0=0):
+                          dense=False, stripe0=0, thresh=None, ternary=False):
         self.launches += 1
+        # both planes with threshold slots (thresholds inside the query plane), or both bare + explicit thresholds
+        assert q_i8["bare"] == g_i8["bare"] == (thresh is not None) and not (dense and thresh is not None)
+        assert ternary == (q_i8["nz"] is not None) or thresh is None
+        if thresh is not None:
+            q_i8 = dict(q_i8, thresh=thresh)
         assert (q_i8["nz"] is None) == (g_i8["nz"] is None)
         keys = self._keys(q_i8["bits"], q_i8["nz"], g_i8["bits"], g_i8["nz"], nq, ndb, nbit, q_i8["nz"] is not None)
         th = _u32(q_i8["thresh"])
