@@ -201,15 +201,33 @@ __global__ void __launch_bounds__(256, (NW <= 2 && !TERN) ? 3 : 1) hamming_hist_
 
   uint32_t epoch = 0;  // number of flushes so far (uniform over the CTA)
   auto flush = [&]() {
-    for (int b = 0; b < a.nbins; ++b) {
-      uint32_t* h = reinterpret_cast<uint32_t*>(hist_b + b * T4);
-      const uint32_t v = *h;
-      if (v != 0u) {
+    if (epoch == 0u) {
+      // first (for stripes of <= 65535 rows: only) flush: nobody else ever writes this (stripe, key, query) entry
+      // and the caller handed the slabs over zeroed, so plain stores do -- the read-modify-write form below is a
+      // chain of dependent global round trips (one per occupied key), which made the flush of a short stripe
+      // cost as much as its pair loop
+#pragma unroll 4
+      for (int b = 0; b < a.nbins; ++b) {
+        uint32_t* h = reinterpret_cast<uint32_t*>(hist_b + b * T4);
+        const uint32_t v = *h;
         *h = 0u;
-        if (active) {
+        if (active && v != 0u) {
           const size_t o = (static_cast<size_t>(stripe) * a.nbins + b) * a.nq_pad + q;
-          a.slab_all[o] += v & 0xffffu;
-          if (LAB != CH_LAB_NONE) a.slab_rel[o] += v >> 16;
+          a.slab_all[o] = v & 0xffffu;
+          if (LAB != CH_LAB_NONE) a.slab_rel[o] = v >> 16;
+        }
+      }
+    } else {
+      for (int b = 0; b < a.nbins; ++b) {
+        uint32_t* h = reinterpret_cast<uint32_t*>(hist_b + b * T4);
+        const uint32_t v = *h;
+        if (v != 0u) {
+          *h = 0u;
+          if (active) {
+            const size_t o = (static_cast<size_t>(stripe) * a.nbins + b) * a.nq_pad + q;
+            a.slab_all[o] += v & 0xffffu;
+            if (LAB != CH_LAB_NONE) a.slab_rel[o] += v >> 16;
+          }
         }
       }
     }

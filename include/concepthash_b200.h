@@ -126,7 +126,8 @@ typedef struct ch_hist_args {
   const uint32_t* q_bits;  const uint32_t* q_nz;   /* (nq_pad', words); q_nz NULL unless ternary */
   const uint32_t* g_bits;  const uint32_t* g_nz;   /* (rows_pad, words) local gallery shard       */
   const uint32_t* q_lab;   const uint32_t* g_lab;  /* ids (n) or masks (n, mask_words); NULL if CH_LAB_NONE */
-  /* outputs: stripe slabs, zero-initialised by the caller */
+  /* outputs: stripe slabs, zero-initialised by the caller; ONE call writes every (stripe, key, query) entry it
+   * owns (a call does not accumulate into the counts of an earlier call) */
   uint32_t* slab_all;      /* (nstripes, nbins, nq_pad) */
   uint32_t* slab_rel;      /* same; NULL if label_mode == CH_LAB_NONE */
   /* thresholded ("select") mode: only pairs with key <= thresh[q] are counted / recorded */
