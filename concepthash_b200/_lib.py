@@ -37,7 +37,8 @@ class FinalArgs(C.Structure):
 class SelectArgs(C.Structure):
     _fields_ = [(n, P) for n in ("q_i8", "g_i8", "cand_off", "cand_cap", "cand_cnt", "cand_rows", "err_flag", "thresh")] + \
                [(n, C.c_int64) for n in ("nq", "nq_pad", "ndb", "row_base")] + \
-               [(n, C.c_int32) for n in ("nbit", "nstripes", "rows_per_stripe", "dense", "ternary")]
+               [(n, C.c_int32) for n in ("nbit", "nstripes", "rows_per_stripe", "dense", "ternary")] + \
+               [("_pad", C.c_int32), ("bad", P)]
 
 
 class CandArgs(C.Structure):
@@ -88,7 +89,7 @@ SIGNATURES = {
                                  P, P]),
     "ch_record_offsets_async": (C.c_int, [P, P, C.c_int, C.c_int64, C.c_int64, P, P, C.c_uint64, C.c_uint32, P, P, P]),
     "ch_scan_bases_pair": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
-                                     P, P, P, P, P, P]),
+                                     P, P, P, P, P, P, P]),
     "ch_gather_rows": (C.c_int, [P, P, C.c_int64, C.c_int, C.c_int64, P, C.c_int64, P]),
     "ch_record_offsets": (C.c_int, [P, P, C.c_int, C.c_int64, C.c_int64, P, C.POINTER(C.c_uint64), P,
                                     C.POINTER(C.c_uint32), P]),

@@ -213,13 +213,14 @@ class CudaBackend:
         return out
 
     def hamming_select_tc(self, *, q_i8, g_i8, cand, nq, nq_pad, ndb, nbit, nstripes, rows_per_stripe, row_base=0,
-                          dense=False, stripe0=0, thresh=None, ternary=False):
+                          dense=False, stripe0=0, thresh=None, ternary=False, bad=None):
         """``cand``: dict(off, cap, cnt (nstripes_total, nq_pad) u32, rows u32[], err u32[1]); ``stripe0`` = first
         stripe of this call's row block (streamed galleries).  ``thresh``: the per-query thresholds when both planes
         are ``bare`` (comparison in the sparse epilogue instead of a threshold block in the contraction)."""
         a = L.SelectArgs()
         a.thresh = thresh.data_ptr() if thresh is not None else None
         a.ternary = int(bool(ternary))
+        a.bad = bad.data_ptr() if bad is not None else None
         a.q_i8, a.g_i8 = q_i8.data_ptr(), g_i8.data_ptr()
         a.cand_off, a.cand_cap, a.cand_cnt = (cand[k][stripe0:].data_ptr() for k in ("off", "cap", "cnt"))
         a.cand_rows, a.err_flag = cand["rows"].data_ptr(), cand["err"].data_ptr()
@@ -343,11 +344,11 @@ class CudaBackend:
                                                  self._stream()), "ch_record_offsets_async")
 
     def scan_bases_pair(self, tot, world, rank, nbins, nq, nq_pad, rmax, need, base0_all, base0_rel, key_max,
-                        total_rel, status):
-        """``tot`` (world, 2, nbins, nq_pad) contiguous"""
+                        total_rel, status, bad=None):
+        """``tot`` (world, 2, nbins, nq_pad) contiguous; ``bad`` (nq_pad): 1 for every query with < ``need`` items"""
         L.check(self.lib.ch_scan_bases_pair(self.ws, _ptr(tot), world, rank, nbins, nq, nq_pad, int(rmax), int(need),
                                             _ptr(base0_all), _ptr(base0_rel), _ptr(key_max), _ptr(total_rel),
-                                            _ptr(status), self._stream()), "ch_scan_bases_pair")
+                                            _ptr(status), _ptr(bad), self._stream()), "ch_scan_bases_pair")
 
     def gather_rows(self, bits, n_src, nbit, stride):
         """every ``stride``-th of the first ``n_src`` rows of a packed plane -> (rows, packed plane with zero pad rows)"""

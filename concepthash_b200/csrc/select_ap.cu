@@ -154,7 +154,7 @@ __global__ void scan_bases_pair_kernel(const uint32_t* __restrict__ tot, int wor
                                        long long nq_pad, long long rmax, long long need,
                                        uint32_t* __restrict__ base0_all, uint32_t* __restrict__ base0_rel,
                                        uint32_t* __restrict__ key_max, uint32_t* __restrict__ total_rel,
-                                       uint32_t* __restrict__ status) {
+                                       uint32_t* __restrict__ status, uint32_t* __restrict__ bad) {
   const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   bool short_list = false;
   if (q < nq_pad) {
@@ -200,6 +200,7 @@ __global__ void scan_bases_pair_kernel(const uint32_t* __restrict__ tot, int wor
     if (key_max != nullptr) key_max[q] = t;
     if (total_rel != nullptr) total_rel[q] = static_cast<uint32_t>(cum_r);
     short_list = need > 0 && q < nq && cum_a < static_cast<unsigned long long>(need);
+    if (short_list && bad != nullptr) bad[q] = 1u;
   }
   if (status != nullptr && __ballot_sync(0xffffffffu, short_list) != 0u && (threadIdx.x & 31) == 0)
     atomicOr(status, 1u);
@@ -644,14 +645,14 @@ extern "C" int ch_record_offsets_async(ch_ws* ws, uint32_t* cap_dev, int nstripe
 extern "C" int ch_scan_bases_pair(ch_ws* ws, const uint32_t* tot_dev, int world, int rank, int nbins, int64_t nq,
                                   int64_t nq_pad, int64_t rmax, int64_t need, uint32_t* base0_all_dev,
                                   uint32_t* base0_rel_dev, uint32_t* key_max_dev, uint32_t* total_rel_dev,
-                                  uint32_t* status_dev, void* stream) {
+                                  uint32_t* status_dev, uint32_t* bad_dev, void* stream) {
   if (ws == nullptr || tot_dev == nullptr || base0_all_dev == nullptr) CH_FAIL("null argument to ch_scan_bases_pair");
   if (world < 1 || rank < 0 || rank >= world) CH_FAIL("bad world/rank %d/%d", world, rank);
   if (need > 0 && status_dev == nullptr) CH_FAIL("verification needs a status word");
   ChDeviceGuard guard(ws->device);
   scan_bases_pair_kernel<<<blocks_for(nq_pad, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       tot_dev, world, rank, nbins, nq, nq_pad, rmax, need, base0_all_dev, base0_rel_dev, key_max_dev, total_rel_dev,
-      status_dev);
+      status_dev, bad_dev);
   CH_LAUNCH_CHECK(ws);
   return 0;
 }

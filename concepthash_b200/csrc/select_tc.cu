@@ -95,6 +95,7 @@ struct SelDev {
   uint32_t* cand_cnt;          // (nstripes, nq_pad)
   uint32_t* cand_rows;         // shard-local row index of every candidate
   uint32_t* err_flag;
+  uint32_t* bad;               // (nq_pad) or NULL: set to 1 for a query whose slice overflowed
   const uint32_t* thresh;      // per-query threshold keys when the comparison happens in the epilogue, else NULL
   int nbit, ternary;
   long long nq, nq_pad, ndb, row_base;
@@ -416,7 +417,10 @@ __global__ void __launch_bounds__(128 + 128 * kQT, 1) hamming_select_tc_kernel(c
     }
     if (active) {
       a.cand_cnt[sq] = n < cap ? n : cap;
-      if (n > cap) atomicOr(a.err_flag, 1u);
+      if (n > cap) {
+        atomicOr(a.err_flag, 1u);
+        if (a.bad != nullptr) a.bad[q] = 1u;     // (the caller re-ranks just these queries by the exact path)
+      }
     }
   }
 
@@ -570,7 +574,7 @@ extern "C" int ch_hamming_select_tc(ch_ws* ws, const ch_select_args* a, void* st
   d.q_i8 = a->q_i8; d.g_i8 = a->g_i8;
   d.cand_off = a->cand_off; d.cand_cap = a->cand_cap; d.cand_cnt = a->cand_cnt; d.cand_rows = a->cand_rows;
   d.err_flag = a->err_flag;
-  d.thresh = a->thresh; d.nbit = a->nbit; d.ternary = a->ternary;
+  d.thresh = a->thresh; d.nbit = a->nbit; d.ternary = a->ternary; d.bad = a->bad;
   d.nq = a->nq; d.nq_pad = a->nq_pad; d.ndb = a->ndb; d.row_base = a->row_base;
   d.rows_per_stripe = a->rows_per_stripe;
   d.nqtiles128 = static_cast<int>(a->nq_pad / kTileM);

@@ -425,13 +425,17 @@ class Evaluator:
             p.i8 = self._timed("expand_i8", 0, lambda: self.b.expand_i8(p.bits, p.nbit, **kw))
         return p.i8
 
-    def _select_tc(self, q, g, geo, thresh, cand, dense, kind="hist_select_tc", ndb=None, nstripes=None, rps=None):
-        """the select pass on the tensor cores over the packed shard ``g`` (or a row sample of it)"""
+    def _select_tc(self, q, g, geo, thresh, cand, dense, kind="hist_select_tc", ndb=None, nstripes=None, rps=None,
+                   bad=None):
+        """the select pass on the tensor cores over the packed shard ``g`` (or a row sample of it); ``bad`` (nq_pad):
+        marked for every query one of whose slices overflows"""
         threads, nq_pad, nstripes_g, rps_g = geo
         bare = self._bare(dense)
         q_i8 = self._query_plane(q, nq_pad, thresh, bare)
         g_i8 = self._gallery_plane(g, bare)
         kw = dict(thresh=thresh, ternary=q.nz is not None) if bare else {}
+        if bad is not None:
+            kw["bad"] = bad
         self._timed(kind, q.n * g.n, lambda: self.b.hamming_select_tc(
             q_i8=q_i8, g_i8=g_i8, cand=cand, nq=q.n, nq_pad=nq_pad, ndb=g.n, nbit=q.nbit,
             nstripes=nstripes_g if nstripes is None else nstripes, rows_per_stripe=rps_g if rps is None else rps,
@@ -467,7 +471,7 @@ class Evaluator:
             tot_all=tot[0], tot_rel=tot[1] if label_mode != L.CH_LAB_NONE else None, nq=c["nq"], nq_pad=nq_pad,
             nstripes=nstripes_all if nstripes is None else nstripes, nbins=nbins, nbit=q.nbit, stripe0=stripe0, **kw))
 
-    def _cand_bases(self, c, cand, nbins, need=None, tot=None, rmax=None):
+    def _cand_bases(self, c, cand, nbins, need=None, tot=None, rmax=None, bad=None):
         """keys + label matches of the candidates -> per-rank key totals -> all-gather -> bases (+ verification
         that every query has >= ``need`` candidates: ST_SHORT).  ``tot``: totals already accumulated per block."""
         b, comm = self.b, self.comm
@@ -484,12 +488,12 @@ class Evaluator:
         key_max = b.empty((nq_pad,), torch.int32) if rmax is not None else None
         b.scan_bases_pair(tot, comm.world, comm.rank, nbins, nq, nq_pad, -1 if rmax is None else rmax,
                           0 if need is None else need, base0_all, base0_rel, key_max, None,
-                          self._status[ST_SHORT:ST_SHORT + 1])
+                          self._status[ST_SHORT:ST_SHORT + 1], **({} if bad is None else dict(bad=bad)))
         return base0_all, base0_rel, key_max
 
     # ------------------------------------------------------------------ the evaluation
     def evaluate(self, db_codes, db_labels, q_codes, q_labels, R, threshold=0.0, PRs=(),
-                 remove_first_retrieved=False, return_ap=False, zero_mean=False):
+                 remove_first_retrieved=False, return_ap=False, zero_mean=False, _raw=False):
         """Returns ``(mAPs list, recalls list, precisions list[, ap (nR, nq) tensor])``.
 
         ``db_codes`` / ``db_labels`` are THIS rank's contiguous gallery row block; queries are replicated.
@@ -501,6 +505,7 @@ class Evaluator:
         if hasattr(b, "begin"):
             b.begin()
         self.host_syncs = 0
+        self._want_raw = bool(_raw)        # internal (repair runs): return the per-query sums instead of the means
         r_list = [int(r) for r in R]
         pr_k = [int(k) for k in PRs]
         if len(r_list) == 0 and len(pr_k) == 0:
@@ -622,7 +627,7 @@ class Evaluator:
                                ndb_total=ndb_total, world=comm.world))
         ctx = dict(q=q, g=g, geo=geo, ternary=ternary, label_mode=label_mode, lw=lw, nclass=nclass, nq=nq,
                    nbins=nbins, rmax=rmax, rf=rf, pr_k=pr_k, ndb_total=ndb_total, stride=stride, rows=rows)
-        ctx.update(r_eff=r_eff, return_ap=return_ap, db_codes=db_codes, threshold=threshold)
+        ctx.update(r_eff=r_eff, r_list=r_list, return_ap=return_ap, db_codes=db_codes, threshold=threshold)
         streamed = streamed and nstripes >= 2
         res = None
         if streamed:
@@ -631,8 +636,10 @@ class Evaluator:
             if hint is not None and self._stale(res[4]):
                 return _RETRY
             if res[4][ST_PASS] or res[4][ST_SHORT]:
-                self.stats["sample"].update(fallback=True, overflow=res[4][ST_PASS], short=res[4][ST_SHORT])
-                res, sampled = None, False          # the same sample would fail again: go exact
+                res = self._repair(ctx, res, q_codes, q_labels, db_labels) if res[4][ST_CODES] == 0 else None
+            if res is None:
+                self.stats["sample"].update(fallback=True)
+                sampled = False                     # the same sample would fail again: go exact
                 self._status[:ST_CODES].zero_()
         if g.bits is None or res is None and streamed:
             # gallery codes were deferred but the streamed path is not applicable (or gave up): pack them now
@@ -661,23 +668,71 @@ class Evaluator:
                 if hint is not None and self._stale(res[4]):
                     return _RETRY
                 if res[4][ST_PASS] or res[4][ST_SHORT]:
-                    # a record slice overflowed or some query has fewer than R candidates under the sampled
-                    # threshold: redo the evaluation by the exact two-pass path
-                    self.stats["sample"].update(fallback=True, overflow=res[4][ST_PASS], short=res[4][ST_SHORT])
-                    res = None
-                    self._status[:ST_CODES].zero_()
+                    # a slice overflowed or some query has fewer than R candidates under the sampled threshold:
+                    # re-rank those queries by the exact path, or -- if they are many -- the whole evaluation
+                    res = self._repair(ctx, res, q_codes, q_labels, db_labels)
+                    if res is None:
+                        self.stats["sample"].update(fallback=True)
+                        self._status[:ST_CODES].zero_()
             if res is None:
                 self.stats["mode"] = "topR"
                 res = self._finish(ctx, self._pass_topr_exact(ctx))
-        maps, recalls, precisions, ap, flags = res
+        maps, recalls, precisions, ap, flags, raw = res
         if hint is not None and self._stale(flags):
             return _RETRY
         if flags[ST_PASS]:
             raise RuntimeError("internal error: record buffer overflow")
         self._close_hint(flags)
+        if self._want_raw:
+            return raw
         if return_ap:
             return maps, recalls, precisions, ap
         return maps, recalls, precisions
+
+    def _repair(self, c, res, q_codes, q_labels, db_labels):
+        """The sampled pass failed for SOME queries (marked in ``bad``: a list slice overflowed its Poisson bound, or
+        the list is shorter than R).  Failures are per query -- every other query's list is complete and ranked --
+        so only the marked queries are re-ranked, by the exact two-pass path of a child evaluator over the already
+        packed codes, and their rows of the per-query sums are replaced before the means are taken again.  Returns
+        the repaired result tuple, or None when too many queries failed (then the whole evaluation is redone)."""
+        maps, recalls, precisions, ap, flags, raw = res
+        b, comm = self.b, self.comm
+        bad = raw.get("bad") if raw is not None else None
+        q, g, nq = c["q"], c["g"], c["nq"]
+        if bad is None or g.bits is None or isinstance(q_labels, PackedCodes):
+            return None
+        if comm.world > 1:
+            bad = comm.all_reduce_max(bad)
+        idx = torch.nonzero(bad[:nq]).flatten()
+        self.host_syncs += 1
+        n_bad = int(idx.numel())
+        self.stats["sample"].update(overflow=flags[ST_PASS], short=flags[ST_SHORT], repaired_queries=n_bad)
+        if n_bad == 0 or n_bad > max(64, nq // 50):
+            return None
+        # inputs of the repair run: the packed planes (binary codes: bits are final -- threshold and column mean are
+        # already applied), the labels of the marked queries
+        if c["ternary"]:
+            return None
+        dbc = PackedCodes(g.bits[:g.n], g.nbit)
+        qc = PackedCodes(q.bits[idx].contiguous(), q.nbit)
+        sel = idx.to(q_labels.device) if isinstance(q_labels, torch.Tensor) else idx.cpu().numpy()
+        child = Evaluator(b._b if isinstance(b, _TimedBackend) else b, comm)
+        child.speculate, child.sample_stride = False, 0           # exact two-pass path, no hints
+        child.use_tensor_cores, child.stripe_rows_override = self.use_tensor_cores, self.stripe_rows_override
+        sub = child.evaluate(dbc, db_labels, qc, q_labels[sel], [r for r in c["r_list"]], 0.0, c["pr_k"], bool(c["rf"]),
+                             _raw=True)
+        self.host_syncs += child.host_syncs
+        raw["cols"][idx] = sub["cols"]
+        if raw["total_rel"] is not None and sub["total_rel"] is not None:
+            raw["total_rel"][idx] = sub["total_rel"][:n_bad]
+        if raw["first_rel"] is not None and sub["first_rel"] is not None:
+            raw["first_rel"][idx] = sub["first_rel"][:n_bad]
+        status = raw["status"]
+        status[:ST_CODES].zero_()                                  # the failure is repaired: clear its flags
+        self.host_syncs += 1
+        maps, recalls, precisions, flags = b.reduce_means(raw["cols"], raw["total_rel"], raw["first_rel"], nq,
+                                                          len(c["r_eff"]), c["pr_k"], ap, status)
+        return maps, recalls, precisions, ap, flags, raw
 
     def _stale(self, flags):
         """did the status block of a speculative run contradict its hint?  (flags = the block, MAX over ranks)"""
@@ -734,7 +789,9 @@ class Evaluator:
             self.host_syncs += 1
             maps, recalls, precisions, flags = b.reduce_means(cols, st["total_rel"] if pr_k else None, first_rel, nq,
                                                               len(r_eff), pr_k, ap, status)
-            return maps, recalls, precisions, ap, flags
+            raw = dict(cols=cols, total_rel=st["total_rel"] if pr_k else None, first_rel=first_rel, bad=st.get("bad"),
+                       status=status)
+            return maps, recalls, precisions, ap, flags, raw
         rec = st["rec"]
         f = dict(recs=rec["recs"], rec_off=rec["off"], rec_cnt=rec["cnt"], base0_all=st["base0_all"],
                  base0_rel=st["base0_rel"], sbase_all=st["sbase_all"], sbase_rel=st["sbase_rel"], first_rel=None,
@@ -756,7 +813,8 @@ class Evaluator:
         self.host_syncs += 1
         maps, recalls, precisions, flags = b.reduce_means(cols, st["total_rel"] if pr_k else None, first_rel, nq,
                                                           len(r_eff), pr_k, ap, status)
-        return maps, recalls, precisions, ap, flags
+        raw = dict(cols=cols, total_rel=st["total_rel"] if pr_k else None, first_rel=first_rel, bad=None, status=status)
+        return maps, recalls, precisions, ap, flags, raw
 
     def _class_counts(self, ctx):
         """(nstripes, nclass) per-stripe class histogram of the single-label gallery shard."""
@@ -927,12 +985,14 @@ class Evaluator:
             for i in range(len(self.blocks) if self.pinned else 1):
                 self.load(i)
 
-        def select(self, i, cand, q_i8, dense, thresh):
+        def select(self, i, cand, q_i8, dense, thresh, bad=None):
             ev, b, q, g = self.ev, self.ev.b, self.c["q"], self.c["g"]
             threads, nq_pad, nstripes, rps = self.c["geo"]
             s0, s1, r0, r1 = self.blocks[i]
             torch.cuda.current_stream().wait_event(self.loaded[i])
             kw = dict(thresh=thresh, ternary=False) if self.bare else {}
+            if bad is not None:
+                kw["bad"] = bad
             ev._timed("hist_select_tc", self.c["nq"] * (r1 - r0), lambda: b.hamming_select_tc(
                 q_i8=q_i8, g_i8=self.plane8[r0:], cand=cand, nq=self.c["nq"], nq_pad=nq_pad, ndb=r1 - r0, nbit=q.nbit,
                 nstripes=s1 - s0, rows_per_stripe=rps, row_base=r0, dense=dense, stripe0=s0, **kw))
@@ -990,9 +1050,12 @@ class Evaluator:
         # block 0 of a streamed gallery travels while the GPU works on the sample: its (host-blocking) copy is
         # issued right after the first sample kernels have been queued
         first_load = streamer.load_first if streamer is not None else (lambda: None)
+        # per-query failure marks of the candidate-list path (a slice overflowed / fewer than R candidates): the
+        # evaluation then re-ranks just those queries by the exact path instead of starting over
+        bad = b.zeros((nq_pad,), torch.int32) if tc_pass else None
         if (tc_pass and self.sample_two_level and min(ns_ranks) >= self.sample2_min_rows and
                 float(nq) * min(ns_ranks) * int(q.bits.shape[1]) >= self.sample2_min_work):
-            thresh, cap = self._sample_thresholds_tc(c, sp, ns_ranks, m, status, first_load)
+            thresh, cap = self._sample_thresholds_tc(c, sp, ns_ranks, m, status, first_load, bad)
         else:
             slab_s = b.zeros((nstripes, nbins, nq_pad), torch.int32)
             self._hist(q, sp, geo_s, ternary, L.CH_LAB_NONE, 0, slab_s, None)
@@ -1018,7 +1081,7 @@ class Evaluator:
                 q_i8 = self._query_plane(q, nq_pad, thresh, streamer.bare)
                 tot = b.zeros((2, nbins, nq_pad), torch.int32)
                 for i in range(len(streamer.blocks)):
-                    streamer.select(i, cand, q_i8, dense, thresh)
+                    streamer.select(i, cand, q_i8, dense, thresh, bad)
                     if i + 1 < len(streamer.blocks) and (i + 1) not in streamer.loaded:
                         streamer.load(i + 1)     # host waits for this copy while the GPU runs select(i)
                     # keys / label matches of this block's candidates while the next block is still travelling
@@ -1028,10 +1091,11 @@ class Evaluator:
                 self.stats["select_dense"] = bool(dense)
                 self.stats["select_threshold"] = "epilogue" if streamer.bare else "contraction"
             else:
-                self._select_tc(q, g, geo, thresh, cand, dense)
-            base0_all, base0_rel, key_max = self._cand_bases(c, cand, nbins, need, tot, rmax=c["rmax"] + c["rf"])
+                self._select_tc(q, g, geo, thresh, cand, dense, bad=bad)
+            base0_all, base0_rel, key_max = self._cand_bases(c, cand, nbins, need, tot, rmax=c["rmax"] + c["rf"],
+                                                             bad=bad)
             return dict(cand=cand, base0_all=base0_all, base0_rel=base0_rel, nbins=nbins, key_max=key_max,
-                        total_rel=self._total_rel_from_classes(c, cls))
+                        total_rel=self._total_rel_from_classes(c, cls), bad=bad)
         b.record_caps(2, cls, q.ids, nstripes, c["nclass"], nq, nq_pad, True, cap)
         rec, tmax = self._alloc_records(cap, geo, nq, thresh, "full", nbins)   # (a host sync unless hinted)
         del slab_s, base_tmp
@@ -1057,7 +1121,7 @@ class Evaluator:
         return dict(rec=rec, base0_all=base0_all, base0_rel=base0_rel, sbase_all=slab_all, sbase_rel=slab_rel,
                     total_rel=self._total_rel_from_classes(c, cls), nbins=nbins)
 
-    def _sample_thresholds_tc(self, c, sp, ns_ranks, m, status, after_level0=lambda: None):
+    def _sample_thresholds_tc(self, c, sp, ns_ranks, m, status, after_level0=lambda: None, bad=None):
         """Per-query thresholds t^ (and the capacities of the full pass) from the row sample WITHOUT histogramming
         every (query, sample row) pair on the integer pipe:
 
@@ -1109,7 +1173,7 @@ class Evaluator:
         nb0 = min(nbins, tmax0 + 1)
         # ---- level 1 ----
         dense = self._dense(1.25 * sub * m0, sum(ns_ranks))
-        self._select_tc(q, sp, geo1, thresh0, cand1, dense, kind="sample_select_tc")
+        self._select_tc(q, sp, geo1, thresh0, cand1, dense, kind="sample_select_tc", bad=bad)
         tot1 = b.zeros((nb0, nq_pad), torch.int32)
         kwz = dict(q_nz=q.nz, g_nz=sp.nz) if ternary else {}
         self._timed("cand_hist", 0, lambda: b.cand_hist(

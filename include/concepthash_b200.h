@@ -193,6 +193,8 @@ typedef struct ch_select_args {
   int32_t nbit, nstripes, rows_per_stripe;   /* rows_per_stripe % 128 == 0 */
   int32_t dense;              /* != 0: most 32-row chunks of a warp hold a candidate -> skip the max-tree filter */
   int32_t ternary;            /* keys on the doubled scale (only read when thresh != NULL) */
+  uint32_t* bad;              /* (nq_pad) or NULL: bad[q] = 1 for every query one of whose slices overflowed, so that
+                                 the caller can re-rank just those queries by the exact path */
 } ch_select_args;
 int ch_tc_code_bytes(int nbit);
 /* queries one CTA of the select kernel owns (its grid is ceil(nq_pad / this) x nstripes, one CTA per SM) */
@@ -314,7 +316,8 @@ int ch_record_offsets_async(ch_ws* ws, uint32_t* cap_dev, int nstripes, int64_t 
 int ch_scan_bases_pair(ch_ws* ws, const uint32_t* tot_dev, int world, int rank, int nbins, int64_t nq,
                        int64_t nq_pad, int64_t rmax, int64_t need, uint32_t* base0_all_dev,
                        uint32_t* base0_rel_dev, uint32_t* key_max_dev, uint32_t* total_rel_dev,
-                       uint32_t* status_dev, void* stream);
+                       uint32_t* status_dev, uint32_t* bad_dev /* (nq_pad) or NULL: 1 for every short query */,
+                       void* stream);
 /* every stride-th row of a packed bit plane (the row sample that picks the thresholds): out (rows_out_pad, words),
  * rows beyond ceil(n_src / stride) are zeroed */
 int ch_gather_rows(ch_ws* ws, const uint32_t* bits_dev, int64_t n_src, int nbit, int64_t stride,

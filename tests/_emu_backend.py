@@ -201,7 +201,7 @@ class EmuBackend:
         return dict(bits=bits, nz=nz, nbit=nbit, nq=nq, bare=bare, thresh=None if thresh is None else thresh.clone())
 
     def hamming_select_tc(self, *, q_i8, g_i8, cand, nq, nq_pad, ndb, nbit, nstripes, rows_per_stripe, row_base=0,
-                          dense=False, stripe0=0, thresh=None, ternary=False):
+                          dense=False, stripe0=0, thresh=None, ternary=False, bad=None):
         self.launches += 1
         # both planes with threshold slots (thresholds inside the query plane), or both bare + explicit thresholds
         assert q_i8["bare"] == g_i8["bare"] == (thresh is not None) and not (dense and thresh is not None)
@@ -222,6 +222,8 @@ class EmuBackend:
                 cnt[s + stripe0, q] = w
                 if len(js) > w:
                     _u32(cand["err"])[0] |= 1
+                    if bad is not None:
+                        _u32(bad)[q] = 1
 
     # K3/K4 on candidate lists
     def cand_hist(self, cand, *, q_bits, g_bits, q_lab, g_lab, label_mode, mask_words, tot_all, tot_rel, nq, nq_pad,
@@ -426,7 +428,7 @@ class EmuBackend:
             _u32(status)[0] |= 8
 
     def scan_bases_pair(self, tot, world, rank, nbins, nq, nq_pad, rmax, need, base0_all, base0_rel, key_max,
-                        total_rel, status):
+                        total_rel, status, bad=None):
         found = torch.zeros(nq_pad, dtype=torch.int32)
         self.scan_bases(tot[:, 0].contiguous(), world, rank, nbins, nq, nq_pad, rmax, base0_all, key_max, found)
         if base0_rel is not None:
@@ -434,6 +436,8 @@ class EmuBackend:
         self.launches -= 1 if base0_rel is not None else 0
         if need > 0 and (_u32(found)[:nq] < need).any():
             _u32(status)[0] |= 1
+            if bad is not None:
+                _u32(bad)[:nq][_u32(found)[:nq] < need] = 1
 
     def gather_rows(self, bits, n_src, nbit, stride):
         self.launches += 1

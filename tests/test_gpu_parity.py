@@ -482,7 +482,9 @@ def test_sampled_one_pass_equals_exact_two_pass(H):
     ll = torch.arange(n, device="cuda") % 7
     ql2 = torch.arange(64, device="cuda") % 7
     m, rec, prec = H.calculate_mAP(dd, ll, qq, ql2, 1000, PRs=[1, 10])
-    assert ev.stats["mode"] == "topR" and ev.stats["sample"]["fallback"]
+    # every query fails the sampled pass: re-ranked by the exact path (per-query repair for few queries, else the
+    # whole evaluation)
+    assert ev.stats["sample"].get("repaired_queries") == 64 or ev.stats["sample"].get("fallback"), ev.stats
     rel = (ql2[:, None] == ll[None, :]).cpu().numpy()
     order = np.concatenate([np.arange(0, st * 900, st), np.setdiff1d(np.arange(n), np.arange(0, st * 900, st))])[:1000]
     aps = [mo._ap_from_rel(rel[i, order]) for i in range(64)]

@@ -71,6 +71,21 @@ def _worker(rank, world, port, out):
                 assert lo < hi                       # uneven shards: only ONE rank's slices exceed the limit below
                 ev3.max_slots = hi                   # (the same constant on every rank, as in the product)
                 results["chunk"] = (ev3.evaluate(ds, dls, q, ql, [15], thr, PRs, rf), ev3.stats.get("query_chunks", 0))
+                # a list slice overflows on ONE rank only (rank 1, two queries): both ranks must agree on the marked
+                # queries and re-rank exactly those together
+                ev4 = Evaluator(EmuBackend(rows_per_stripe=32, threads=128, tensor_cores=True), DistComm())
+                ev4.sample_stride, ev4.sample_min_rows, ev4.sample_min_ratio, ev4.sample_two_level = 2, 0, 4, False
+                if rank == 1:
+                    orig = ev4.b._b.record_caps
+
+                    def starved(source, a0, a1, nstripes, nb, nq, nq_pad, mwp, cap, sample_stride=0, replicate=False):
+                        orig(source, a0, a1, nstripes, nb, nq, nq_pad, mwp, cap, sample_stride=sample_stride,
+                             replicate=replicate)
+                        if sample_stride > 1:
+                            cap[:, [2, 9]] = 0
+                    ev4.b._b.record_caps = starved
+                results["repair"] = (ev4.evaluate(ds, dls, q, ql, [15], thr, PRs, rf), ev4.stats["mode"],
+                                     ev4.stats["sample"].get("repaired_queries"))
                 # zero_mean_eval: the column mean is that of the WHOLE gallery (sums all-reduced over the ranks)
                 results["zm"] = ev.evaluate(ds + 0.3, dls, q + 0.3, ql, [15], 0.0, [1, 5], False, zero_mean=True)
         if rank == 0:
@@ -113,6 +128,9 @@ def test_two_ranks_match_oracle(tmp_path):
             chunked, nchunks = results["chunk"]
             assert nchunks >= 2, nchunks
             assert np.allclose(chunked[0], om, atol=1e-12) and np.allclose(chunked[1], orec, atol=1e-12)
+            rep, mode, nrep = results["repair"]
+            assert mode == "topR-sampled" and nrep == 2, (mode, nrep)
+            assert np.allclose(rep[0], om, atol=1e-12) and np.allclose(rep[1], orec, atol=1e-12)
             dz, qz = mo.zero_mean(d + 0.3, q + 0.3)
             om, orec, oprec = mo.calculate_mAP(dz, dl, qz, ql, 15, PRs=[1, 5])
             zm = results["zm"]
