@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(kCandWarps * 32) cand_final_kernel(const CandD
 }
 
 // capacities of the full pass from a candidate list of the ROW SAMPLE (rows = sample row indices):
-// cap[s][q] = stride * (k + 5 sqrt(k + 1) + 6), k = #sample candidates of query q with key <= thresh[q] whose row
+// cap[s][q] = stride * (k + 6 sqrt(k + 1) + 9), k = #sample candidates of query q with key <= thresh[q] whose row
 // lies in stripe s of the full pass (sample rows [s * rows_per_stripe, (s + 1) * rows_per_stripe)) -- the bound of
 // record_caps_kernel.  One warp per query, per-stripe counters in shared memory.
 __global__ void __launch_bounds__(kCandWarps * 32) cand_caps_kernel(
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(kCandWarps * 32) cand_caps_kernel(
     uint32_t v = 0u;
     if (q < nq) {
       const float kf = static_cast<float>(c[s]);
-      v = static_cast<uint32_t>((kf + 5.0f * sqrtf(kf + 1.0f) + 6.0f) * static_cast<float>(stride));
+      v = static_cast<uint32_t>((kf + 6.0f * sqrtf(kf + 1.0f) + 9.0f) * static_cast<float>(stride));
     }
     cap[static_cast<size_t>(s) * nq_pad + q] = v;
   }

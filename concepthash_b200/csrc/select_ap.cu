@@ -71,7 +71,7 @@ __global__ void record_caps_kernel(int source, const uint32_t* __restrict__ a0, 
     // c candidates seen in a 1-in-stride row sample -> bound on the real count (Poisson tail, checked later:
     // an overflowing slice raises the error flag and the caller redoes the evaluation exactly)
     const float k = static_cast<float>(c);
-    c = static_cast<uint32_t>((k + 5.0f * sqrtf(k + 1.0f) + 6.0f) * static_cast<float>(sample_stride));
+    c = static_cast<uint32_t>((k + 6.0f * sqrtf(k + 1.0f) + 9.0f) * static_cast<float>(sample_stride));
   }
   if (min_with_prev) {
     const uint32_t p = cap[i];

@@ -252,7 +252,7 @@ int ch_gather_plane(ch_ws* ws, const uint32_t* bits_dev, const uint32_t* ids_dev
 int ch_cand_finalize(ch_ws* ws, const ch_cand_args* a, void* stream);
 /* Two-level threshold sampling: the candidate list (list_stripes slices per query, rows = SAMPLE row indices, keys
  * already written by ch_cand_hist) came from a select pass over a 1-in-`sample_stride` row sample.
- * cap[s][q] = sample_stride * (k + 5 sqrt(k + 1) + 6), k = #sample candidates of query q with key <= thresh[q]
+ * cap[s][q] = sample_stride * (k + 6 sqrt(k + 1) + 9), k = #sample candidates of query q with key <= thresh[q]
  * whose sample row lies in [s * rows_per_stripe, (s + 1) * rows_per_stripe): the capacity of slice (s, q) of the
  * full pass (same bound as ch_record_caps with sample_stride).  cap_dev: (nstripes, nq_pad). */
 int ch_cand_caps(ch_ws* ws, const uint32_t* cand_off, const uint32_t* cand_cnt, const uint32_t* cand_rows,
@@ -287,7 +287,7 @@ int ch_scan_bases(ch_ws* ws, const uint32_t* tot_all_dev, int world, int rank, i
  *   source 2: class count = cls_cnt[s][q_ids[q]]                          (single-label fast path)
  *   min_with_prev != 0 keeps min(existing cap, new cap).
  *   sample_stride > 1: the counts come from a 1-in-stride row sample; they are scaled to a high-probability
- *   bound stride * (k + 5 sqrt(k + 1) + 6) (an overflow is detected by the pass and reported in err_flag).
+ *   bound stride * (k + 6 sqrt(k + 1) + 9) (an overflow is detected by the pass and reported in err_flag).
  */
 int ch_record_caps(ch_ws* ws, int source, const uint32_t* slab_or_cls, const uint32_t* thresh_or_qids,
                    int nstripes, int nbins_or_nclass, int64_t nq, int64_t nq_pad, int min_with_prev,

@@ -273,7 +273,7 @@ class EmuBackend:
                 for j in range(int(cnt[ls, q])):
                     if key[o + j] <= th[q]:
                         raw[min(int(rows[o + j] & 0x7FFFFFFF) // rows_per_stripe, nstripes - 1), q] += 1
-        bound = (raw + np.float32(5.0) * np.sqrt(raw + np.float32(1.0)) + np.float32(6.0)) * np.float32(sample_stride)
+        bound = (raw + np.float32(6.0) * np.sqrt(raw + np.float32(1.0)) + np.float32(9.0)) * np.float32(sample_stride)
         c[:, :nq] = bound[:, :nq].astype(np.uint32)
 
     def cand_finalize(self, cand, *, mode, base0_all, base0_rel, nq, nq_pad, nstripes, nbins, remove_first=False,
@@ -392,7 +392,7 @@ class EmuBackend:
                     c[:, q] = cls[:, ids[q]]
         if sample_stride > 1:
             k = c.astype(np.float32)
-            c = ((k + np.float32(5.0) * np.sqrt(k + np.float32(1.0)) + np.float32(6.0)) * np.float32(sample_stride)).astype(np.uint32)
+            c = ((k + np.float32(6.0) * np.sqrt(k + np.float32(1.0)) + np.float32(9.0)) * np.float32(sample_stride)).astype(np.uint32)
         if min_with_prev:
             c = np.minimum(c, _u32(cap))
         _u32(cap)[...] = c
