@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kCandWarps * 32) cand_hist_kernel(const CandDe
   const uint32_t* qm = a.label_mode == CH_LAB_MASK ? a.q_lab + q * a.lw : nullptr;
   bool bad = false;
   __syncwarp();
-  constexpr int U = 4;                         // candidates per lane in flight (independent gathers)
+  constexpr int U = 8;                         // candidates per lane in flight (independent gathers)
   for (int s = 0; s < a.nstripes; ++s) {
     const size_t sq = static_cast<size_t>(s) * a.nq_pad + q;
     const uint32_t off = a.cand_off[sq], n = a.cand_cnt[sq];
@@ -270,12 +270,22 @@ __global__ void __launch_bounds__(kCandWarps * 32) cand_final_kernel(const CandD
   for (int s = 0; s < a.nstripes; ++s) {
     const size_t sq = static_cast<size_t>(s) * a.nq_pad + q;
     const uint32_t off = a.cand_off[sq], n = a.cand_cnt[sq];
+    // (the loads of the next 32 candidates are issued before the current 32 are ranked: the walk is a serial chain
+    // of ballots / match_any / shared-memory counters and would otherwise expose one global round trip per step)
+    uint32_t nrow = 0u, nkey = 0xffffffffu;
+    if (lane < n) {
+      nrow = a.cand_rows[off + lane];
+      nkey = a.cand_key[off + lane];
+    }
     for (uint32_t i0 = 0; i0 < n; i0 += 32) {
       const uint32_t i = i0 + lane;
-      uint32_t rowv = 0u, key = 0xffffffffu;
-      if (i < n) {
-        rowv = a.cand_rows[off + i];
-        key = a.cand_key[off + i];
+      const uint32_t rowv = nrow, key = nkey;
+      if (i + 32 < n) {
+        nrow = a.cand_rows[off + i + 32];
+        nkey = a.cand_key[off + i + 32];
+      } else {
+        nrow = 0u;
+        nkey = 0xffffffffu;
       }
       // keys >= nbins were flagged by ch_cand_hist; keys > kmax cannot rank below rmax
       const bool keep = i < n && key < static_cast<uint32_t>(a.nbins) && key <= kmax;
