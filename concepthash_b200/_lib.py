@@ -38,7 +38,7 @@ class SelectArgs(C.Structure):
     _fields_ = [(n, P) for n in ("q_i8", "g_i8", "cand_off", "cand_cap", "cand_cnt", "cand_rows", "err_flag", "thresh")] + \
                [(n, C.c_int64) for n in ("nq", "nq_pad", "ndb", "row_base")] + \
                [(n, C.c_int32) for n in ("nbit", "nstripes", "rows_per_stripe", "dense", "ternary")] + \
-               [("_pad", C.c_int32), ("bad", P)]
+               [("pair", C.c_int32), ("bad", P)]
 
 
 class CandArgs(C.Structure):
@@ -74,6 +74,8 @@ SIGNATURES = {
     "ch_tc_code_bytes": (C.c_int, [C.c_int]),
     "ch_tc_queries_per_cta": (C.c_int, []),
     "ch_tc_code_bytes_bare": (C.c_int, [C.c_int]),
+    "ch_tc_code_bytes_pair": (C.c_int, [C.c_int, C.c_int]),
+    "ch_tc_tile_rows": (C.c_int, [C.c_int]),
     "ch_expand_i8": (C.c_int, [P, P, P, C.c_int64, C.c_int, C.c_int, C.c_int, P, C.c_int64, P, C.c_int64, P]),
     "ch_hamming_select_tc": (C.c_int, [P, C.POINTER(SelectArgs), P]),
     "ch_cand_hist": (C.c_int, [P, C.POINTER(CandArgs), P]),
@@ -134,7 +136,7 @@ def load():
             raise NativeLibraryError(f"{LIB_PATH} does not export {name}") from e
         fn.restype = res
         fn.argtypes = args
-    if lib.ch_abi_version() != 3:
+    if lib.ch_abi_version() != 4:
         raise NativeLibraryError("ABI version mismatch: rebuild the library")
     _lib = lib
     return lib

@@ -27,7 +27,7 @@ class CudaBackend:
 
     name = "cuda"
     stripe_align = 256     # stripe boundaries must be multiples of 256 gallery rows
-    tc_tile_rows = 128     # rows per tile of the tensor-core select kernel (its stripes are whole tiles)
+    tc_tile_rows = 256     # rows per tile of the tensor-core select kernel, paired form (its stripes are whole tiles)
 
     def __init__(self, device=None):
         if not torch.cuda.is_available():
@@ -192,19 +192,36 @@ class CudaBackend:
         """bytes per row of an int8 operand plane; ``bare``: without threshold slots (comparison in the epilogue)"""
         return int((self.lib.ch_tc_code_bytes_bare if bare else self.lib.ch_tc_code_bytes)(int(nbit)))
 
-    def expand_i8_into(self, bits, nbit, out, bare=False):
-        """gallery plane of a row block: ``bits`` (rows, words) -> ``out`` (rows, kb) views of larger arrays"""
-        assert bits.shape[0] % 32 == 0 and out.shape[0] >= bits.shape[0]
-        L.check(self.lib.ch_expand_i8(self.ws, _ptr(bits), None, int(bits.shape[0]), nbit, 0, int(bool(bare)), _ptr(out),
-                                      int(bits.shape[0]), None, 0, self._stream()), "ch_expand_i8")
+    def tc_code_bytes_pair(self, nbit, ternary=False):
+        """bytes per row of the PAIRED planes (two gallery rows per plane row); 0: this nbit has no paired form"""
+        return int(self.lib.ch_tc_code_bytes_pair(int(nbit), int(bool(ternary))))
 
-    def expand_i8(self, bits, nbit, min_rows=0, thresh=None, nq=0, nz=None, bare=False, query=False):
+    def expand_i8_into(self, bits, nbit, out, bare=False, pair=False):
+        """gallery plane of a row block: ``bits`` (rows, words) -> ``out`` (rows, kb) views of larger arrays
+        (``pair``: rows / 2 plane rows; the block starts on a multiple of 64 rows)"""
+        n = int(bits.shape[0])
+        assert n % (64 if pair else 32) == 0 and out.shape[0] >= (n // 2 if pair else n)
+        L.check(self.lib.ch_expand_i8(self.ws, _ptr(bits), None, n, nbit, 0, 3 if pair else int(bool(bare)), _ptr(out),
+                                      n // 2 if pair else n, None, 0, self._stream()), "ch_expand_i8")
+
+    def expand_i8(self, bits, nbit, min_rows=0, thresh=None, nq=0, nz=None, bare=False, query=False, pair=False):
         """packed sign bits (rows_pad, words) -> {-1, 0, +1} int8 plane in the tiled operand order (rows, kb) int8,
         with the threshold slots: gallery plane when ``thresh`` is None, else the query plane of ``nq`` queries.
         ``nz``: the non-zero plane of ternary codes (thresholds are then on the doubled key scale).
-        ``min_rows`` over-allocates so that whole 128-query tiles can be read."""
-        kb = self.tc_code_bytes(nbit, bare)
+        ``min_rows`` over-allocates so that whole 128-query tiles can be read.  ``pair``: the paired forms
+        (``ch_tc_code_bytes_pair``): a gallery plane of rows_pad / 2 plane rows, or -- with ``thresh`` -- its query plane."""
         rows_pad = int(bits.shape[0])
+        if pair:
+            kb = self.tc_code_bytes_pair(nbit, nz is not None)
+            gallery = thresh is None
+            assert kb > 0 and (not gallery or rows_pad % 64 == 0)
+            rows = rows_pad // 2 if gallery else max(rows_pad, (int(min_rows) + 31) // 32 * 32)
+            out = self.empty((rows, kb), torch.int8)
+            L.check(self.lib.ch_expand_i8(self.ws, _ptr(bits), _ptr(nz), rows_pad, nbit, 0 if nz is None else 1,
+                                          3 if gallery else 4, _ptr(out), rows, _ptr(thresh), int(nq), self._stream()),
+                    "ch_expand_i8")
+            return out
+        kb = self.tc_code_bytes(nbit, bare)
         rows = max(rows_pad, (int(min_rows) + 31) // 32 * 32)
         out = self.empty((rows, kb), torch.int8)
         L.check(self.lib.ch_expand_i8(self.ws, _ptr(bits), _ptr(nz), rows_pad, nbit, 0 if nz is None else 1,
@@ -213,13 +230,15 @@ class CudaBackend:
         return out
 
     def hamming_select_tc(self, *, q_i8, g_i8, cand, nq, nq_pad, ndb, nbit, nstripes, rows_per_stripe, row_base=0,
-                          dense=False, stripe0=0, thresh=None, ternary=False, bad=None):
+                          dense=False, stripe0=0, thresh=None, ternary=False, bad=None, pair=False):
         """``cand``: dict(off, cap, cnt (nstripes_total, nq_pad) u32, rows u32[], err u32[1]); ``stripe0`` = first
         stripe of this call's row block (streamed galleries).  ``thresh``: the per-query thresholds when both planes
-        are ``bare`` (comparison in the sparse epilogue instead of a threshold block in the contraction)."""
+        are ``bare`` (comparison in the sparse epilogue instead of a threshold block in the contraction).
+        ``pair``: both planes are the paired forms (tiles of 256 gallery rows)."""
         a = L.SelectArgs()
         a.thresh = thresh.data_ptr() if thresh is not None else None
         a.ternary = int(bool(ternary))
+        a.pair = int(bool(pair))
         a.bad = bad.data_ptr() if bad is not None else None
         a.q_i8, a.g_i8 = q_i8.data_ptr(), g_i8.data_ptr()
         a.cand_off, a.cand_cap, a.cand_cnt = (cand[k][stripe0:].data_ptr() for k in ("off", "cap", "cnt"))

@@ -161,6 +161,39 @@ __device__ __forceinline__ uint32_t sign_mask32p_tau(const uint32_t* r, uint32_t
   return m;
 }
 
+// ---- two gallery rows per accumulator cell (PAIR; binary codes of <= 128 bits, ternary codes of <= 64) ----------
+// A 16-bit accumulator value has room for TWO comparisons.  With f = thresh - key in [-128, 127] (key <= 128), the
+// paired planes (expand_i8_pair_kernel) make the contraction produce
+//     E = (f_a + 128) + 256 * (-f_b - 1)            in [-32768, 32767]
+// for the two gallery rows a, b that share a plane row: the query side holds [q, 64 q, slots], the gallery side
+// [a, -4 b, slot constants]; for binary codes the gallery side is the {0, 1} form of the code, so that
+// <q, g01> = (#ones of q) - hamming(q, g) -- a difference of DISTANCES, not of inner products, which is what makes
+// 129 values fit a byte.  Bit 7 of E is "row a is a candidate", bit 15 "row b is a candidate": every byte of a packed
+// register pair carries one sign bit, twice as many as in the one-row form, at the same PRMT + LOP3 per register --
+// and a 128-column accumulator covers 256 gallery rows, so there are half as many accumulator hand-overs, TMEM
+// loads and barrier round trips per pair.  (What bounds the one-row kernel is that chain, not the MMA: DESIGN.md 5.)
+// Column c of a 32-column block holds rows kPairRow(c, 0) and kPairRow(c, 1) of the 64-row block: with the folding
+// below, bit 31 - t of mask h (registers 8 h .. 8 h + 7) is row 32 h + t.
+__host__ __device__ constexpr int kPairRow(int c, int f) {
+  return 32 * (c >> 4) + 31 - 8 * (2 * (c & 1) + f) - ((c >> 1) & 7);
+}
+constexpr int kPairSlots = 5;   // query side (x0, x1, y1, y2, y3) . gallery side (2, 1, -128, -128, -128)
+// 8 packed registers = 16 columns x 2 rows -> mask, bit 31 - t = 1 iff row t of the 32 is a candidate
+__device__ __forceinline__ uint32_t pair_mask32(const uint32_t* r) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    uint32_t p;
+    asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(p) : "r"(r[k]));
+    m |= p & (0x01010101u << k);
+  }
+  return m;
+}
+__device__ __forceinline__ bool pair_any32(const uint32_t* r) {
+  const uint32_t x = (r[0] | r[1] | r[2]) | (r[3] | r[4] | r[5]) | (r[6] | r[7]);
+  return (x & 0x80808080u) != 0u;
+}
+
 // the MMA with a compile-time accumulate flag (no predicate set-up on the single issuing thread)
 template <bool ACC>
 __device__ __forceinline__ void umma_i8_imm(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc) {
@@ -209,10 +242,13 @@ __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
 
 // One CTA = kQT consecutive 128-query tiles x one gallery stripe.
 // TAU: the threshold comparison happens in the epilogue (planes without threshold slots, KB = the code bytes only)
-template <int KB, bool DENSE, bool TAU>
+// PAIR: two gallery rows per accumulator cell (planes of expand_i8_pair_kernel): a tile is 256 rows
+template <int KB, bool DENSE, bool TAU, bool PAIR>
 __global__ void __launch_bounds__(128 + 128 * kQT, 1) hamming_select_tc_kernel(const SelDev a) {
   typedef SelSmem<KB> S;
   constexpr int kStages = stages_for(KB);
+  constexpr int kTileRows = PAIR ? 2 * kTileN : kTileN;   // gallery rows per tile
+  static_assert(!(PAIR && TAU), "the paired form carries its thresholds in the contraction");
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar_a, bar_full[kStages], bar_empty[kStages], bar_tfull[kQT], bar_tempty[kQT];
   __shared__ uint32_t tmem_base_s;
@@ -227,7 +263,7 @@ __global__ void __launch_bounds__(128 + 128 * kQT, 1) hamming_select_tc_kernel(c
   const long long row_begin = static_cast<long long>(stripe) * a.rows_per_stripe;
   long long row_end = row_begin + a.rows_per_stripe;
   if (row_end > a.ndb) row_end = a.ndb;
-  const int ntiles = row_end > row_begin ? static_cast<int>((row_end - row_begin + kTileN - 1) / kTileN) : 0;
+  const int ntiles = row_end > row_begin ? static_cast<int>((row_end - row_begin + kTileRows - 1) / kTileRows) : 0;
 
   if (tid == 0) {
     mma_lock = 0u;
@@ -276,14 +312,18 @@ __global__ void __launch_bounds__(128 + 128 * kQT, 1) hamming_select_tc_kernel(c
       int next_load = 0;                                      // producer state (warp 0 only)
       auto load_tile = [&](int t) {
         const int st = t % kStages;
-        const long long r0 = row_begin + static_cast<long long>(t) * kTileN;
+        const long long r0 = row_begin + static_cast<long long>(t) * kTileRows;
         long long rows = row_end - r0;
-        if (rows > kTileN) rows = kTileN;
-        const uint32_t rows32 = static_cast<uint32_t>((rows + 31) & ~31ll);   // whole (permuted) 32-row blocks; pad
-        const uint32_t bytes_b = rows32 * KB;                                  // rows exist (ch_padded_rows)
+        if (rows > kTileRows) rows = kTileRows;
+        // whole (permuted) blocks of 32 plane rows (= 32 gallery rows, or 64 in the paired form); pad rows exist
+        // (ch_padded_rows)
+        const uint32_t prows = PAIR ? static_cast<uint32_t>((rows + 63) >> 6) * 32u
+                                    : static_cast<uint32_t>((rows + 31) & ~31ll);
+        const uint32_t bytes_b = prows * KB;
+        const size_t prow0 = static_cast<size_t>(PAIR ? (r0 >> 1) : r0);
         if (elect_one()) {
           mbar_arrive_expect_tx(&bar_full[st], bytes_b);
-          bulk_g2s(smem + S::offB + st * S::kB, a.g_i8 + static_cast<size_t>(r0) * KB, bytes_b, &bar_full[st]);
+          bulk_g2s(smem + S::offB + st * S::kB, a.g_i8 + prow0 * KB, bytes_b, &bar_full[st]);
         }
       };
       if (warp == 0) {
@@ -376,7 +416,7 @@ __global__ void __launch_bounds__(128 + 128 * kQT, 1) hamming_select_tc_kernel(c
 
     uint32_t ra[32], rb[32];
     for (int k = 0; k < ntiles; ++k) {
-      const uint32_t row0 = static_cast<uint32_t>(a.row_base + row_begin) + static_cast<uint32_t>(k) * kTileN;
+      const uint32_t row0 = static_cast<uint32_t>(a.row_base + row_begin) + static_cast<uint32_t>(k) * kTileRows;
       mbar_wait(&bar_tfull[qt], static_cast<uint32_t>(k & 1));
       tc_fence_after();
       if (lane == 0) mbar_arrive(&bar_empty[k % kStages]);   // this query tile's MMAs are done with the stage
@@ -388,6 +428,18 @@ __global__ void __launch_bounds__(128 + 128 * kQT, 1) hamming_select_tc_kernel(c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_tempty[qt]);
+      if (PAIR) {
+        // eight masks of 32 rows each (bit set = candidate), then the candidate loops
+        uint32_t m[8];
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+          const uint32_t* r = (h < 4 ? ra : rb) + 8 * (h & 3);
+          m[h] = (DENSE || pair_any32(r)) ? pair_mask32(r) : 0u;
+        }
+#pragma unroll
+        for (int h = 0; h < 8; ++h) emit(m[h], row0 + 32u * h);
+        continue;
+      }
       // all four masks first (independent instruction chains), then the (rare, divergent) candidate loops
       uint32_t m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
       if (DENSE) {
@@ -492,24 +544,116 @@ __global__ void expand_i8_tiled_kernel(const uint32_t* __restrict__ bits, const 
   reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+// The paired planes (see kPairRow): one thread per (plane row, 16-byte K chunk); bytes 0 .. nbit - 1 = field a,
+// nbit .. 2 nbit - 1 = field b, then kPairSlots threshold slots.
+//   gallery (query == 0): plane row p of the 32-row block p / 32 holds gallery rows 64 (p / 32) + kPairRow(p % 32, f);
+//     field a = the code as {0, 1} (binary) or {-1, 0, +1} (ternary), field b = -4 x that; slots (2, 1, -128, -128, -128)
+//   query: plane row = query; field a = the code as {-1, 0, +1}, field b = 64 x that; slots (x0, x1, y1, y2, y3) with
+//     2 x0 + x1 = c0 = thresh - P + 128 and -128 (y1 + y2 + y3) = 256 c1, c1 = P - thresh - 1, where P = the number of
+//     one bits of the query (binary: <q, g01> = P - hamming) or nbit (ternary: <q, g> = nbit - key).  Then
+//     E = <row_q, row_g> = (thresh - key_a + 128) + 256 (key_b - thresh - 1).  thresh >= 128 (only possible when it is
+//     the largest key there is: every row is a candidate) is encoded as a zero code with c0 = 128, c1 = -1.
+__global__ void expand_i8_pair_kernel(const uint32_t* __restrict__ bits, const uint32_t* __restrict__ nz,
+                                      long long rows_bits, long long rows_out, int words, int nbit, int kb,
+                                      int ternary, int query, const uint32_t* __restrict__ thresh, long long nq,
+                                      int8_t* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int chunks = kb / 16;
+  if (i >= rows_out * chunks) return;
+  const long long group = i / (8ll * chunks);
+  const int within = static_cast<int>(i - group * 8ll * chunks);
+  const int chunk = within / 8, r8 = within % 8;
+  const long long prow = group * 8 + r8;       // row of the PLANE = TMEM lane (queries) / TMEM column (gallery)
+  long long src0 = prow, src1 = prow;
+  if (!query) {
+    const long long base = (prow >> 5) * 64;
+    const int c = static_cast<int>(prow & 31);
+    src0 = base + kPairRow(c, 0);
+    src1 = base + kPairRow(c, 1);
+  }
+  const int k0 = chunk * 16;
+  // slot values of this row (only the thread(s) whose chunk reaches the slots need them)
+  int slot[kPairSlots] = {2, 1, -128, -128, -128};
+  bool zero_code = false;
+  if (query) {
+    int c0 = 0, c1 = 0;                          // padding queries: E = 0, nothing is a candidate
+    zero_code = true;
+    if (prow < nq && prow < rows_bits) {
+      const uint32_t t = thresh[prow];
+      if (t > 127u) {                            // every row is a candidate: E = 128 - 256 whatever the row
+        c0 = 128;
+        c1 = -1;
+      } else {
+        zero_code = false;
+        int P = nbit;
+        if (!ternary) {
+          P = 0;
+          for (int w = 0; w < words; ++w) P += __popc(bits[prow * words + w]);
+        }
+        c0 = static_cast<int>(t) - P + 128;
+        c1 = P - static_cast<int>(t) - 1;
+      }
+    }
+    slot[0] = c0 >> 1;
+    slot[1] = c0 & 1;
+    int v = -2 * c1;
+    for (int s = 2; s < kPairSlots; ++s) {
+      const int y = v < -128 ? -128 : (v > 127 ? 127 : v);
+      slot[s] = y;
+      v -= y;
+    }
+  }
+  uint32_t o[4];
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    uint32_t x = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + v * 4 + j;
+      int val = 0;
+      if (k < 2 * nbit) {
+        const int f = k < nbit ? 0 : 1;
+        const int bit = k - f * nbit;
+        const long long r = f ? src1 : src0;
+        if (r < rows_bits && !zero_code) {
+          const uint32_t w = bits[r * words + (bit >> 5)] >> (bit & 31);
+          const bool nonzero = nz == nullptr || ((nz[r * words + (bit >> 5)] >> (bit & 31)) & 1u) != 0u;
+          int code;                              // the code value of this operand form
+          if (query || ternary) code = nonzero ? ((w & 1u) ? 1 : -1) : 0;
+          else code = static_cast<int>(w & 1u);  // binary gallery: {0, 1}
+          val = code * (query ? (f ? 64 : 1) : (f ? -4 : 1));
+        }
+      } else if (k < 2 * nbit + kPairSlots) {
+        const int sidx = k - 2 * nbit;           // (selects, not an indexed load: slot[] stays in registers)
+        val = sidx == 0 ? slot[0] : sidx == 1 ? slot[1] : sidx == 2 ? slot[2] : sidx == 3 ? slot[3] : slot[4];
+      }
+      x |= (static_cast<uint32_t>(val) & 0xffu) << (8 * j);
+    }
+    o[v] = x;
+  }
+  reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 typedef void (*sel_fn_t)(const SelDev);
 template <int KB>
-sel_fn_t pick_dense(int dense, int tau, size_t* smem) {
+sel_fn_t pick_dense(int dense, int tau, int pair, size_t* smem) {
   *smem = SelSmem<KB>::total;
-  if (tau) return hamming_select_tc_kernel<KB, false, true>;
-  return dense ? hamming_select_tc_kernel<KB, true, false> : hamming_select_tc_kernel<KB, false, false>;
+  if (pair)
+    return dense ? hamming_select_tc_kernel<KB, true, false, true> : hamming_select_tc_kernel<KB, false, false, true>;
+  if (tau) return hamming_select_tc_kernel<KB, false, true, false>;
+  return dense ? hamming_select_tc_kernel<KB, true, false, false> : hamming_select_tc_kernel<KB, false, false, false>;
 }
-sel_fn_t pick_sel(int kb, int dense, int tau, size_t* smem) {
+sel_fn_t pick_sel(int kb, int dense, int tau, int pair, size_t* smem) {
   switch (kb) {
-    case 32: return pick_dense<32>(dense, tau, smem);
-    case 64: return pick_dense<64>(dense, tau, smem);
-    case 96: return pick_dense<96>(dense, tau, smem);
-    case 128: return pick_dense<128>(dense, tau, smem);
-    case 160: return pick_dense<160>(dense, tau, smem);
-    case 192: return pick_dense<192>(dense, tau, smem);
-    case 224: return pick_dense<224>(dense, tau, smem);
-    case 256: return pick_dense<256>(dense, tau, smem);
-    default: return pick_dense<288>(dense, tau, smem);
+    case 32: return pick_dense<32>(dense, tau, pair, smem);
+    case 64: return pick_dense<64>(dense, tau, pair, smem);
+    case 96: return pick_dense<96>(dense, tau, pair, smem);
+    case 128: return pick_dense<128>(dense, tau, pair, smem);
+    case 160: return pick_dense<160>(dense, tau, pair, smem);
+    case 192: return pick_dense<192>(dense, tau, pair, smem);
+    case 224: return pick_dense<224>(dense, tau, pair, smem);
+    case 256: return pick_dense<256>(dense, tau, pair, smem);
+    default: return pick_dense<288>(dense, tau, pair, smem);
   }
 }
 
@@ -530,13 +674,39 @@ extern "C" int ch_tc_code_bytes_bare(int nbit) {
   return (nbit + 31) / 32 * 32;                        // no threshold slots: the comparison happens in the epilogue
 }
 
+extern "C" int ch_tc_code_bytes_pair(int nbit, int ternary) {
+  // thresh - key must fit a signed byte: keys 0 .. 128
+  if (nbit <= 0 || nbit > (ternary ? 64 : 128)) return 0;
+  return (2 * nbit + kPairSlots + 31) / 32 * 32;       // both fields + the threshold slots, in whole 32-byte K blocks
+}
+
+extern "C" int ch_tc_tile_rows(int pair) { return pair ? 2 * kTileN : kTileN; }
+
 extern "C" int ch_expand_i8(ch_ws* ws, const uint32_t* bits_dev, const uint32_t* nz_dev, int64_t rows_bits, int nbit,
                             int ternary, int bare, int8_t* out_dev, int64_t rows_out, const uint32_t* thresh_dev,
                             int64_t nq, void* stream) {
   if (ws == nullptr || bits_dev == nullptr || out_dev == nullptr) CH_FAIL("null argument to ch_expand_i8");
   if (ternary && nz_dev == nullptr) CH_FAIL("ternary codes need the non-zero plane");
+  if (bare == 3 || bare == 4) {
+    // paired planes: two gallery rows per plane row (3), or the query plane that goes with them (4)
+    const int kbp = ch_tc_code_bytes_pair(nbit, ternary);
+    if (kbp == 0) CH_FAIL("nbit=%d ternary=%d has no paired form (binary <= 128 bits, ternary <= 64)", nbit, ternary);
+    if (bare == 4 && thresh_dev == nullptr) CH_FAIL("the paired query plane needs the thresholds");
+    if (bare == 3 && thresh_dev != nullptr) CH_FAIL("a gallery plane takes no thresholds");
+    if (rows_out % 32 || rows_bits < 0 || (bare == 3 ? 2 * rows_out < rows_bits : rows_out < rows_bits))
+      CH_FAIL("rows_out must be a multiple of 32 and cover rows_bits (gallery: two rows per plane row)");
+    if (rows_out == 0) return 0;
+    ChDeviceGuard guard(ws->device);
+    const long long n = rows_out * (kbp / 16);
+    expand_i8_pair_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        bits_dev, ternary ? nz_dev : nullptr, rows_bits, rows_out, ch_code_words(nbit), nbit, kbp, ternary ? 1 : 0,
+        bare == 4 ? 1 : 0, thresh_dev, nq, out_dev);
+    CH_LAUNCH_CHECK(ws);
+    return 0;
+  }
   if (bare && thresh_dev != nullptr) CH_FAIL("a plane without threshold slots takes no thresholds");
-  if (bare < 0 || bare > 2) CH_FAIL("bare: 0 = threshold slots, 1 = bare gallery plane, 2 = bare query plane");
+  if (bare < 0 || bare > 2)
+    CH_FAIL("bare: 0 = threshold slots, 1 = bare gallery plane, 2 = bare query plane, 3 / 4 = paired gallery / query");
   const int kb = bare ? ch_tc_code_bytes_bare(nbit) : ch_tc_code_bytes(nbit);
   if (kb == 0) CH_FAIL("nbit=%d unsupported by the tensor-core path (1..%d)", nbit, CH_MAX_NBIT);
   if (rows_out % 32 || rows_bits < 0 || rows_out < rows_bits)
@@ -558,12 +728,16 @@ extern "C" int ch_hamming_select_tc(ch_ws* ws, const ch_select_args* a, void* st
       a->cand_cnt == nullptr || a->cand_rows == nullptr || a->err_flag == nullptr)
     CH_FAIL("null array in ch_select_args");
   const int tau = a->thresh != nullptr ? 1 : 0;       // comparison in the epilogue: planes without threshold slots
-  const int kb = tau ? ch_tc_code_bytes_bare(a->nbit) : ch_tc_code_bytes(a->nbit);
-  if (kb == 0) CH_FAIL("nbit=%d unsupported by the tensor-core path (1..%d)", a->nbit, CH_MAX_NBIT);
+  const int pair = a->pair != 0 ? 1 : 0;              // two gallery rows per plane row (ch_expand_i8 forms 3 / 4)
+  if (pair && tau) CH_FAIL("the paired form carries its thresholds in the contraction (thresh must be NULL)");
+  const int kb = pair ? ch_tc_code_bytes_pair(a->nbit, a->ternary)
+                      : (tau ? ch_tc_code_bytes_bare(a->nbit) : ch_tc_code_bytes(a->nbit));
+  if (kb == 0) CH_FAIL("nbit=%d unsupported by the tensor-core path (1..%d; paired: binary <= 128, ternary <= 64)",
+                       a->nbit, CH_MAX_NBIT);
   if (tau && a->dense) CH_FAIL("the epilogue-side comparison exists for the sparse epilogue only");
   if (a->nq <= 0 || a->ndb < 0) CH_FAIL("bad arguments");
   if (a->nq_pad % kTileM || a->nq_pad < a->nq) CH_FAIL("nq_pad must be a multiple of %d and >= nq", kTileM);
-  if (a->nstripes <= 0 || a->rows_per_stripe <= 0 || a->rows_per_stripe % kTileN ||
+  if (a->nstripes <= 0 || a->rows_per_stripe <= 0 || a->rows_per_stripe % (pair ? 2 * kTileN : kTileN) ||
       static_cast<long long>(a->nstripes) * a->rows_per_stripe < a->ndb)
     CH_FAIL("bad stripe geometry");
   if (a->row_base < 0 || a->row_base + a->ndb > 0x7fffffffll) CH_FAIL("shard-local row indices must fit 31 bits");
@@ -580,7 +754,7 @@ extern "C" int ch_hamming_select_tc(ch_ws* ws, const ch_select_args* a, void* st
   d.nqtiles128 = static_cast<int>(a->nq_pad / kTileM);
   d.nqgroups = (d.nqtiles128 + kQT - 1) / kQT;
   size_t smem = 0;
-  sel_fn_t fn = pick_sel(kb, a->dense != 0, tau, &smem);
+  sel_fn_t fn = pick_sel(kb, a->dense != 0, tau, pair, &smem);
   if (smem > static_cast<size_t>(ws->max_smem_optin)) CH_FAIL("tensor-core kernel needs %zu bytes of shared memory", smem);
   if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: each CTA owns all 512 TMEM columns
   CH_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));

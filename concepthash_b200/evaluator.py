@@ -91,17 +91,19 @@ class _TooManySlots(Exception):
 
 class Packed:
     """Packed codes + labels of one side (query or gallery shard)."""
-    __slots__ = ("n", "nbit", "bits", "nz", "ids", "masks", "info", "ncls", "i8", "i8b", "plane")
+    __slots__ = ("n", "nbit", "bits", "nz", "ids", "masks", "info", "ncls", "i8", "i8b", "i8p", "plane")
 
     def __init__(self):
         self.plane = None
         self.i8b = None          # int8 plane without threshold slots (comparison in the select kernel's epilogue)
+        self.i8p = None          # paired int8 plane: two gallery rows per plane row
 
 
 class _TimedBackend:
     """Pass-through to the backend; while the evaluator profiles (bench), every entry point that is not already
     inside an explicit bracket gets its own CUDA-event bracket (kind = "k_<entry point>")."""
-    _PLAIN = frozenset(("empty", "padded_rows", "code_words", "geometry", "tc_code_bytes", "launch_count", "begin",
+    _PLAIN = frozenset(("empty", "padded_rows", "code_words", "geometry", "tc_code_bytes", "tc_code_bytes_pair",
+                        "launch_count", "begin",
                         "on_stream", "to_host", "gather_plane_words", "popc_peak"))
 
     def __init__(self, ev, backend):
@@ -155,6 +157,7 @@ class Evaluator:
         self.stream_chunks = 4
         self.use_tensor_cores = True       # select pass on tcgen05 (int8 +-1 codes) when the shape allows it
         self.epilogue_thresholds = True    # sparse select passes: threshold comparison in the epilogue (see _bare)
+        self.paired_rows = True            # select pass: two gallery rows per accumulator cell where keys fit (see _pair)
         self.select_dense_override = None  # tests: force the dense / sparse epilogue of the tensor-core kernel
         self.col_sub = None                # zero_mean_eval: f64[nbit] column offset of the current evaluation
         self.events = []                   # (kind, work units, start event, end event)
@@ -405,9 +408,20 @@ class Evaluator:
         return bool(self.epilogue_thresholds and not dense and hasattr(self.b, "tc_code_bytes") and
                     self.b.tc_code_bytes(8, True) > 0)
 
-    def _query_plane(self, q, nq_pad, thresh, bare=False):
+    def _pair(self, q):
+        """Keys up to 128 (binary codes of <= 128 bits, ternary codes of <= 64): ``thresh - key`` fits a signed byte, so
+        one 16-bit accumulator value carries the comparisons of TWO gallery rows (bit 7 / bit 15) -- an accumulator
+        covers 256 rows and the select kernel has half as many accumulator hand-overs, TMEM loads and barrier round
+        trips per pair (``ch_tc_code_bytes_pair`` in the header).  The thresholds always ride in the contraction."""
+        return bool(self.paired_rows and hasattr(self.b, "tc_code_bytes_pair") and
+                    self.b.tc_code_bytes_pair(q.nbit, q.nz is not None) > 0)
+
+    def _query_plane(self, q, nq_pad, thresh, bare=False, pair=False):
         """int8 query plane: with the thresholds in its threshold slots (made per select pass), or bare"""
         kw = {} if q.nz is None else dict(nz=q.nz)
+        if pair:
+            return self._timed("expand_i8", 0, lambda: self.b.expand_i8(q.bits, q.nbit, nq_pad, thresh=thresh, nq=q.n,
+                                                                        pair=True, **kw))
         if bare:
             if q.i8b is None:
                 q.i8b = self._timed("expand_i8", 0, lambda: self.b.expand_i8(q.bits, q.nbit, nq_pad, bare=True,
@@ -415,8 +429,12 @@ class Evaluator:
             return q.i8b
         return self._timed("expand_i8", 0, lambda: self.b.expand_i8(q.bits, q.nbit, nq_pad, thresh=thresh, nq=q.n, **kw))
 
-    def _gallery_plane(self, p, bare=False):
+    def _gallery_plane(self, p, bare=False, pair=False):
         kw = {} if p.nz is None else dict(nz=p.nz)
+        if pair:
+            if p.i8p is None:
+                p.i8p = self._timed("expand_i8", 0, lambda: self.b.expand_i8(p.bits, p.nbit, pair=True, **kw))
+            return p.i8p
         if bare:
             if p.i8b is None:
                 p.i8b = self._timed("expand_i8", 0, lambda: self.b.expand_i8(p.bits, p.nbit, bare=True, **kw))
@@ -430,10 +448,13 @@ class Evaluator:
         """the select pass on the tensor cores over the packed shard ``g`` (or a row sample of it); ``bad`` (nq_pad):
         marked for every query one of whose slices overflows"""
         threads, nq_pad, nstripes_g, rps_g = geo
-        bare = self._bare(dense)
-        q_i8 = self._query_plane(q, nq_pad, thresh, bare)
-        g_i8 = self._gallery_plane(g, bare)
+        pair = self._pair(q)
+        bare = not pair and self._bare(dense)
+        q_i8 = self._query_plane(q, nq_pad, thresh, bare, pair)
+        g_i8 = self._gallery_plane(g, bare, pair)
         kw = dict(thresh=thresh, ternary=q.nz is not None) if bare else {}
+        if pair:
+            kw = dict(pair=True, ternary=q.nz is not None)
         if bad is not None:
             kw["bad"] = bad
         self._timed(kind, q.n * g.n, lambda: self.b.hamming_select_tc(
@@ -444,6 +465,7 @@ class Evaluator:
             self.stats["select_kernel"] = "tcgen05"
             self.stats["select_dense"] = bool(dense)
             self.stats["select_threshold"] = "epilogue" if bare else "contraction"
+            self.stats["select_rows_per_cell"] = 2 if pair else 1
 
     def _cand_hist(self, c, cand, nbins, tot, stripe0=0, nstripes=None):
         """keys + label matches of the candidates of a block of stripes, accumulated into ``tot`` (2, nbins, nq_pad)"""
@@ -927,18 +949,23 @@ class Evaluator:
         on block i.  Outputs are exactly those of one whole-shard launch (slabs per stripe, records with shard
         row ids)."""
 
-        def __init__(self, ev, c, flags, bare=False):
-            self.ev, self.c, self.flags, self.bare = ev, c, flags, bare
+        def __init__(self, ev, c, flags, bare=False, pair=False):
+            self.ev, self.c, self.flags, self.bare, self.pair = ev, c, flags, bare and not pair, pair
             b, q, g = ev.b, c["q"], c["g"]
             threads, nq_pad, nstripes, rps = c["geo"]
             self.rows_pad = b.padded_rows(g.n)
             g.bits = b.empty((self.rows_pad, q.bits.shape[1]), torch.int32)
-            kb = b.tc_code_bytes(q.nbit, True) if bare else b.tc_code_bytes(q.nbit)
-            self.plane8 = b.empty((self.rows_pad, kb), torch.int8)
-            if bare:
-                g.i8b = self.plane8
+            if pair:
+                # two gallery rows per plane row: row r of the shard lives in plane row block r // 64
+                self.plane8 = b.empty((self.rows_pad // 2, b.tc_code_bytes_pair(q.nbit, False)), torch.int8)
+                g.i8p = self.plane8
             else:
-                g.i8 = self.plane8
+                kb = b.tc_code_bytes(q.nbit, True) if self.bare else b.tc_code_bytes(q.nbit)
+                self.plane8 = b.empty((self.rows_pad, kb), torch.int8)
+                if self.bare:
+                    g.i8b = self.plane8
+                else:
+                    g.i8 = self.plane8
             per = ev._stream_per(nq_pad)
             # loads run on a side stream so that they are not queued behind the (long) select kernels
             # one side stream per evaluator, reused by every evaluation: the caching allocator pools blocks per
@@ -974,8 +1001,12 @@ class Evaluator:
                 else:
                     ev._timed("pack_host", (r1 - r0) * q.nbit * db_codes.element_size(),
                               lambda: b.pack_sign(blk, 0.0, self.flags, False, out=g.bits[r0:]))
-                ev._timed("expand_i8", 0, lambda: b.expand_i8_into(g.bits[r0:r0 + nrow8], q.nbit, self.plane8[r0:],
-                                                                    **(dict(bare=True) if self.bare else {})))
+                if self.pair:
+                    ev._timed("expand_i8", 0, lambda: b.expand_i8_into(g.bits[r0:r0 + nrow8], q.nbit,
+                                                                        self.plane8[r0 // 2:], pair=True))
+                else:
+                    ev._timed("expand_i8", 0, lambda: b.expand_i8_into(g.bits[r0:r0 + nrow8], q.nbit, self.plane8[r0:],
+                                                                        **(dict(bare=True) if self.bare else {})))
                 done = torch.cuda.Event()
                 done.record(self.side)
             self.loaded[i] = done
@@ -991,10 +1022,13 @@ class Evaluator:
             s0, s1, r0, r1 = self.blocks[i]
             torch.cuda.current_stream().wait_event(self.loaded[i])
             kw = dict(thresh=thresh, ternary=False) if self.bare else {}
+            if self.pair:
+                kw = dict(pair=True)
             if bad is not None:
                 kw["bad"] = bad
             ev._timed("hist_select_tc", self.c["nq"] * (r1 - r0), lambda: b.hamming_select_tc(
-                q_i8=q_i8, g_i8=self.plane8[r0:], cand=cand, nq=self.c["nq"], nq_pad=nq_pad, ndb=r1 - r0, nbit=q.nbit,
+                q_i8=q_i8, g_i8=self.plane8[r0 // 2 if self.pair else r0:], cand=cand, nq=self.c["nq"], nq_pad=nq_pad,
+                ndb=r1 - r0, nbit=q.nbit,
                 nstripes=s1 - s0, rows_per_stripe=rps, row_base=r0, dense=dense, stripe0=s0, **kw))
 
     def _pass_topr_sampled(self, c, streamed=False):
@@ -1029,7 +1063,7 @@ class Evaluator:
             packed, _ = self._timed("pack_host", ns * g.nbit * view.element_size(),
                                     lambda: b.pack_sign(view, 0.0, zflag, False))
             sp.bits = packed.view(-1, q.bits.shape[1])         # (super rows, run * words) -> (rows, words)
-            streamer = self._Streamer(self, c, zflag, self._bare(dense))
+            streamer = self._Streamer(self, c, zflag, self._bare(dense), self._pair(q))
             streamer.side.wait_stream(torch.cuda.current_stream())
         else:
             ns, sp.bits = b.gather_rows(g.bits, g.n, g.nbit, stride)
@@ -1078,7 +1112,7 @@ class Evaluator:
             self.stats["sample"]["key_limit"] = nbins
             tot = None
             if streamed:
-                q_i8 = self._query_plane(q, nq_pad, thresh, streamer.bare)
+                q_i8 = self._query_plane(q, nq_pad, thresh, streamer.bare, streamer.pair)
                 tot = b.zeros((2, nbins, nq_pad), torch.int32)
                 for i in range(len(streamer.blocks)):
                     streamer.select(i, cand, q_i8, dense, thresh, bad)
@@ -1090,6 +1124,7 @@ class Evaluator:
                 self.stats["select_kernel"] = "tcgen05"
                 self.stats["select_dense"] = bool(dense)
                 self.stats["select_threshold"] = "epilogue" if streamer.bare else "contraction"
+                self.stats["select_rows_per_cell"] = 2 if streamer.pair else 1
             else:
                 self._select_tc(q, g, geo, thresh, cand, dense, bad=bad)
             base0_all, base0_rel, key_max = self._cand_bases(c, cand, nbins, need, tot, rmax=c["rmax"] + c["rf"],

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CH_ABI_VERSION 3
+#define CH_ABI_VERSION 4
 #define CH_MAX_NBIT 256          /* words per code: 1, 2, 4 or 8 x u32 */
 #define CH_MAX_R 8               /* length of an `R` list (test_hashing.py:124-128) */
 #define CH_MAX_PR 32             /* length of `PRs` */
@@ -192,7 +192,10 @@ typedef struct ch_select_args {
   int64_t nq, nq_pad, ndb, row_base;   /* nq_pad % 128 == 0; ndb = rows of this call's row block */
   int32_t nbit, nstripes, rows_per_stripe;   /* rows_per_stripe % 128 == 0 */
   int32_t dense;              /* != 0: most 32-row chunks of a warp hold a candidate -> skip the max-tree filter */
-  int32_t ternary;            /* keys on the doubled scale (only read when thresh != NULL) */
+  int32_t ternary;            /* keys on the doubled scale (read when thresh != NULL or pair != 0) */
+  int32_t pair;               /* != 0: the planes are the PAIRED forms of ch_expand_i8 (3 / 4): a plane row of the gallery
+                                 holds two gallery rows, a 16-bit accumulator value both comparisons (bit 7 / bit 15),
+                                 a tile is 256 rows; rows_per_stripe % 256 == 0, thresh must be NULL */
   uint32_t* bad;              /* (nq_pad) or NULL: bad[q] = 1 for every query one of whose slices overflowed, so that
                                  the caller can re-rank just those queries by the exact path */
 } ch_select_args;
@@ -200,9 +203,21 @@ int ch_tc_code_bytes(int nbit);
 /* queries one CTA of the select kernel owns (its grid is ceil(nq_pad / this) x nstripes, one CTA per SM) */
 int ch_tc_queries_per_cta(void);
 int ch_tc_code_bytes_bare(int nbit);   /* bytes per plane row without threshold slots (see ch_select_args.thresh) */
+/* Paired planes: TWO gallery rows per plane row, so an accumulator (128 TMEM columns) covers 256 gallery rows and the
+ * select kernel has half as many accumulator hand-overs, TMEM loads and barrier round trips per pair.  With
+ * f = thresh - key in [-128, 127] (keys <= 128: binary codes of <= 128 bits, ternary codes of <= 64) the contraction
+ * yields E = (f_a + 128) + 256 (-f_b - 1) in int16 range for the rows a, b of a plane row: bit 7 of the packed 16-bit
+ * accumulator says "a is a candidate", bit 15 "b is".  Query plane row = [q, 64 q, 5 slots], gallery plane row =
+ * [a, -4 b, (2, 1, -128, -128, -128)], a / b as {0, 1} for binary codes (<q, g01> = ones(q) - hamming) and {-1, 0, +1}
+ * for ternary ones; plane row c of a 32-row block holds gallery rows 64 (block) + 32 (c >> 4) + 31 - 8 (2 (c & 1) + f)
+ * - ((c >> 1) & 7), f = 0 / 1.  ch_tc_code_bytes_pair = bytes per plane row (0: no paired form for this nbit). */
+int ch_tc_code_bytes_pair(int nbit, int ternary);
+int ch_tc_tile_rows(int pair);         /* gallery rows per tile of the select kernel: 128, paired 256 */
 int ch_expand_i8(ch_ws* ws, const uint32_t* bits_dev, const uint32_t* nz_dev /* ternary codes, else NULL */,
                  int64_t rows_bits, int nbit, int ternary,
-                 int bare /* 0: threshold slots; 1: gallery plane without; 2: query plane without */,
+                 int bare /* 0: threshold slots; 1: gallery plane without; 2: query plane without;
+                             3: paired gallery plane (rows_out = PLANE rows >= rows_bits / 2);
+                             4: paired query plane (thresh_dev required) */,
                  int8_t* out_dev, int64_t rows_out, const uint32_t* thresh_dev /* or NULL */, int64_t nq,
                  void* stream);
 int ch_hamming_select_tc(ch_ws* ws, const ch_select_args* a, void* stream);

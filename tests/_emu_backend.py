@@ -32,6 +32,7 @@ class EmuBackend:
         self.threads = threads
         self.launches = 0
         self.tensor_cores = tensor_cores     # emulate the candidate-list path (needs threads % 128 == 0)
+        self.paired = True                   # offer the paired plane forms (two gallery rows per plane row)
 
     # plumbing
     def zeros(self, shape, dtype):
@@ -195,16 +196,25 @@ class EmuBackend:
             return 0
         return (nbit + (0 if bare else 2 if nbit <= 254 else 4) + 31) // 32 * 32
 
-    def expand_i8(self, bits, nbit, min_rows=0, thresh=None, nq=0, nz=None, bare=False, query=False):
+    def tc_code_bytes_pair(self, nbit, ternary=False):
+        # two gallery rows per plane row: thresh - key must fit a signed byte (keys <= 128)
+        if not self.tensor_cores or not self.paired or nbit <= 0 or nbit > (64 if ternary else 128):
+            return 0
+        return (2 * nbit + 5 + 31) // 32 * 32
+
+    def expand_i8(self, bits, nbit, min_rows=0, thresh=None, nq=0, nz=None, bare=False, query=False, pair=False):
         self.launches += 1
-        assert not (bare and thresh is not None)
-        return dict(bits=bits, nz=nz, nbit=nbit, nq=nq, bare=bare, thresh=None if thresh is None else thresh.clone())
+        assert not (bare and thresh is not None) and not (bare and pair)
+        assert not pair or self.tc_code_bytes_pair(nbit, nz is not None) > 0
+        return dict(bits=bits, nz=nz, nbit=nbit, nq=nq, bare=bare, pair=pair,
+                    thresh=None if thresh is None else thresh.clone())
 
     def hamming_select_tc(self, *, q_i8, g_i8, cand, nq, nq_pad, ndb, nbit, nstripes, rows_per_stripe, row_base=0,
-                          dense=False, stripe0=0, thresh=None, ternary=False, bad=None):
+                          dense=False, stripe0=0, thresh=None, ternary=False, bad=None, pair=False):
         self.launches += 1
         # both planes with threshold slots (thresholds inside the query plane), or both bare + explicit thresholds
         assert q_i8["bare"] == g_i8["bare"] == (thresh is not None) and not (dense and thresh is not None)
+        assert q_i8["pair"] == g_i8["pair"] == bool(pair) and (not pair or rows_per_stripe % self.stripe_align == 0)
         assert ternary == (q_i8["nz"] is not None) or thresh is None
         if thresh is not None:
             q_i8 = dict(q_i8, thresh=thresh)

@@ -525,30 +525,35 @@ def test_tensor_core_select_equals_popc_select(H, nbit, thr):
         ndb = 150_000 + nbit               # (the POPC reference pass of wide / ternary codes is slow)
     d, dl, q, ql, ncls = synth.make_random_case(nq, ndb, nbit, 30, p=0.30, seed=nbit, device="cuda")
     out = {}
-    for tc, dense in ((True, False), (True, True), (False, None)):
-        ev.use_tensor_cores, ev.select_dense_override = tc, dense
+    has_pair = ev.b.tc_code_bytes_pair(nbit, bool(thr)) > 0      # two gallery rows per accumulator cell (keys <= 128)
+    variants = [(True, False, False), (True, True, False), (False, None, False)]
+    if has_pair:
+        variants += [(True, False, True), (True, True, True)]
+    for tc, dense, pair in variants:
+        ev.use_tensor_cores, ev.select_dense_override, ev.paired_rows = tc, dense, pair
         try:
             res = ev.evaluate(d, dl, q, ql, [50, 500], thr, [1, 5, 10], False, return_ap=True)
             kern = ev.stats["select_kernel"]
             assert ev.stats["ternary"] == bool(thr)
+            assert not tc or ev.stats["select_rows_per_cell"] == (2 if pair else 1), ev.stats
             ids, keys, _ = ev.retrieve(d, q, 300, thr)
-            out[(tc, dense)] = (res, ids, keys)
+            out[(tc, dense, pair)] = (res, ids, keys)
         finally:
-            ev.use_tensor_cores, ev.select_dense_override = True, None
+            ev.use_tensor_cores, ev.select_dense_override, ev.paired_rows = True, None, True
         assert kern == ("tcgen05" if tc else "popc")
-    rb, ib, kb = out[(False, None)]
-    for dense in (False, True):                 # both epilogue variants of the tensor-core kernel
-        ra, ia, ka = out[(True, dense)]
-        assert _same(ra, rb)
-        assert torch.equal(ia, ib) and torch.equal(ka, kb)
+    rb, ib, kb = out[(False, None, False)]
+    for key in variants[:2] + variants[3:]:     # both epilogue variants of the tensor-core kernel, one / two rows per cell
+        ra, ia, ka = out[key]
+        assert _same(ra, rb), key
+        assert torch.equal(ia, ib) and torch.equal(ka, kb), key
     sub = slice(0, 40)
     om, orec, oprec = mo.calculate_mAP(d.cpu(), dl.cpu(), q[sub].cpu(), ql[sub].cpu(), [50, 500], threshold=thr,
                                        PRs=[1, 5, 10])
     m, rec, prec = H.calculate_mAP(d, dl, q[sub], ql[sub], [50, 500], threshold=thr, PRs=[1, 5, 10])
     assert np.allclose(m, om, atol=TOL) and np.allclose(rec, orec, atol=TOL) and np.allclose(prec, oprec, atol=TOL)
     oids, odist = mo.topk_ids(q[sub].cpu(), d.cpu(), 300, threshold=thr)
-    assert torch.equal(out[(True, False)][1][sub].cpu(), oids)
-    assert torch.equal(out[(True, False)][2][sub].cpu().float() * (0.5 if thr else 1.0), odist)
+    assert torch.equal(out[(True, False, False)][1][sub].cpu(), oids)
+    assert torch.equal(out[(True, False, False)][2][sub].cpu().float() * (0.5 if thr else 1.0), odist)
 
 
 def test_streamed_host_gallery_equals_resident(H):
