@@ -572,19 +572,45 @@ __global__ void expand_i8_pair_kernel(const uint32_t* __restrict__ bits, const u
     src1 = base + kPairRow(c, 1);
   }
   const int k0 = chunk * 16;
-  // slot values of this row (only the thread(s) whose chunk reaches the slots need them)
-  int slot[kPairSlots] = {2, 1, -128, -128, -128};
+  // a query row whose code is written as zeros: padding, or thresh >= 128 (every row is a candidate)
+  uint32_t t = 0u;
   bool zero_code = false;
   if (query) {
+    zero_code = !(prow < nq && prow < rows_bits);
+    if (!zero_code) {
+      t = thresh[prow];
+      zero_code = t > 127u;
+    }
+  }
+  uint32_t o[4];
+  if (nz == nullptr && (nbit & 15) == 0 && k0 + 16 <= 2 * nbit) {
+    // binary codes, the usual widths: the 16 bytes are 16 consecutive bits of ONE field of one source row
+    const int f = k0 >= nbit ? 1 : 0;
+    const int bit0 = k0 - f * nbit;
+    const long long r = f ? src1 : src0;
+    const bool live = r < rows_bits && !zero_code;
+    uint32_t b16 = 0u;
+    if (live) b16 = (bits[r * words + (bit0 >> 5)] >> (bit0 & 31)) & 0xffffu;
+    // byte = base ^ (bit * mul): query +-1 / +-64, gallery {0, 1} / {0, -4}
+    const uint32_t mul = query ? (f ? 0x80u : 0xfeu) : (f ? 0xfcu : 0x01u);
+    const uint32_t base = (query && live) ? (f ? 0xc0c0c0c0u : 0xffffffffu) : 0u;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const uint32_t x = (((b16 >> (4 * v)) & 0xfu) * 0x00204081u) & 0x01010101u;   // bit j -> byte j
+      o[v] = live ? (base ^ (x * mul)) : 0u;
+    }
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    return;
+  }
+  // slot values of this row (only the chunks that reach the slots need them)
+  int slot[kPairSlots] = {2, 1, -128, -128, -128};
+  if (query) {
     int c0 = 0, c1 = 0;                          // padding queries: E = 0, nothing is a candidate
-    zero_code = true;
-    if (prow < nq && prow < rows_bits) {
-      const uint32_t t = thresh[prow];
+    if (prow < nq && prow < rows_bits && k0 + 16 > 2 * nbit) {
       if (t > 127u) {                            // every row is a candidate: E = 128 - 256 whatever the row
         c0 = 128;
         c1 = -1;
       } else {
-        zero_code = false;
         int P = nbit;
         if (!ternary) {
           P = 0;
@@ -603,7 +629,6 @@ __global__ void expand_i8_pair_kernel(const uint32_t* __restrict__ bits, const u
       v -= y;
     }
   }
-  uint32_t o[4];
 #pragma unroll
   for (int v = 0; v < 4; ++v) {
     uint32_t x = 0;

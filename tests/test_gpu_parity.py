@@ -556,6 +556,63 @@ def test_tensor_core_select_equals_popc_select(H, nbit, thr):
     assert torch.equal(out[(True, False, False)][2][sub].cpu().float() * (0.5 if thr else 1.0), odist)
 
 
+@pytest.mark.parametrize("nbit,tern", [(128, False), (64, False), (100, False), (16, False), (7, False), (64, True),
+                                       (40, True)])
+def test_paired_select_kernel_threshold_edges(H, nbit, tern):
+    """The select kernel alone, paired form (two gallery rows per accumulator cell) against brute force, on the
+    thresholds where ``thresh - key`` touches the ends of a signed byte: 0, 127, 128 (= every row), beyond the
+    largest key; queries of all ones / all minus ones (P = nbit / 0 in the slot constants); gallery rows equal to a
+    query and to its complement (keys 0 and the maximum); a partial last tile; padding queries."""
+    from concepthash_b200.evaluator import Packed
+    ev = H.get_evaluator()
+    b = ev.b
+    assert b.tc_code_bytes_pair(nbit, tern) > 0
+    g = torch.Generator().manual_seed(nbit + tern)
+    nq, ndb, rps = 200, 3000, 2048
+    qx = torch.randn(nq, nbit, generator=g)
+    gx = torch.randn(ndb, nbit, generator=g)
+    qx[0], qx[1] = 1.0, -1.0
+    gx[5], gx[6], gx[2999], gx[2047], gx[2048] = qx[3], -qx[3], qx[4], -qx[4], qx[0]
+    thr = 0.4 if tern else 0.0
+    ip = mo.sign_codes(qx, thr) @ mo.sign_codes(gx, thr).T
+    keys = (nbit - ip) if tern else (nbit - ip) / 2           # ternary: 2 x distance
+    kmax = 2 * nbit if tern else nbit
+    th = torch.randint(0, kmax + 2, (nq,), generator=g)
+    th[:8] = torch.tensor([0, kmax, 127, 128, 200, 1, kmax - 1, kmax + 1]).clamp(max=1000)
+    fl = b.zeros((1,), torch.int32)
+    packs = []
+    for x in (qx, gx):
+        p = Packed()
+        p.n, p.nbit = x.shape[0], nbit
+        p.bits, p.nz = b.pack_sign(x.cuda(), thr, fl, want_nz=tern)
+        p.i8 = None
+        packs.append(p)
+    qp, gp = packs
+    nq_pad, nstripes = 256, 2
+    thresh = b.zeros((nq_pad,), torch.int32)
+    thresh[:nq] = th.to(torch.int32).cuda()
+    off = (torch.arange(nstripes * nq_pad, dtype=torch.int64) * rps).to(torch.int32).view(nstripes, nq_pad).cuda()
+    cap = torch.full((nstripes, nq_pad), rps, dtype=torch.int32, device="cuda")
+    want = keys <= th[:, None].float()
+    try:
+        for pair in (True, False):
+            for dense in (False, True):
+                ev.paired_rows = pair
+                gp.i8 = gp.i8b = gp.i8p = qp.i8b = None
+                cand = dict(off=off, cap=cap, cnt=b.zeros((nstripes, nq_pad), torch.int32),
+                            rows=torch.full((nstripes * nq_pad * rps,), -1, dtype=torch.int32, device="cuda"),
+                            err=b.zeros((1,), torch.int32))
+                ev._select_tc(qp, gp, (128, nq_pad, nstripes, rps), thresh, cand, dense)
+                cnt, rows = cand["cnt"].cpu(), cand["rows"].cpu().view(nstripes, nq_pad, rps)
+                assert int(cand["err"].cpu()[0]) == 0
+                for qi in range(nq):
+                    got = torch.cat([rows[s, qi, :cnt[s, qi]] for s in range(nstripes)])
+                    exp = torch.nonzero(want[qi]).flatten().to(torch.int32)
+                    assert torch.equal(got, exp), (pair, dense, qi, int(th[qi]), got[:8], exp[:8])
+    finally:
+        ev.paired_rows = True
+
+
 def test_streamed_host_gallery_equals_resident(H):
     """A large gallery passed as a HOST tensor is streamed in row blocks behind the select pass; the answer must
     be bit-identical to the device-resident run, and a gallery with exact zeros must fall back cleanly."""
