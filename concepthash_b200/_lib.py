@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libconcepthash_b200.so")
+# (CONCEPTHASH_B200_LIB: another build of the same library -- kernel experiments under dev/; never a fallback)
+LIB_PATH = os.environ.get("CONCEPTHASH_B200_LIB") or os.path.join(HERE, "libconcepthash_b200.so")
 
 CH_F32, CH_F16, CH_BF16, CH_F64, CH_I64, CH_I32, CH_U8, CH_I16, CH_I8 = range(9)
 CH_MEM_DEVICE, CH_MEM_HOST = 0, 1

@@ -252,7 +252,6 @@ __global__ void __launch_bounds__(128 + 128 * kQT, 1) hamming_select_tc_kernel(c
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar_a, bar_full[kStages], bar_empty[kStages], bar_tfull[kQT], bar_tempty[kQT];
   __shared__ uint32_t tmem_base_s;
-  __shared__ uint32_t mma_lock;                // held while one warp issues the MMAs of one (tile, accumulator)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   const int qgroup = blockIdx.x % a.nqgroups;
@@ -266,7 +265,6 @@ __global__ void __launch_bounds__(128 + 128 * kQT, 1) hamming_select_tc_kernel(c
   const int ntiles = row_end > row_begin ? static_cast<int>((row_end - row_begin + kTileRows - 1) / kTileRows) : 0;
 
   if (tid == 0) {
-    mma_lock = 0u;
     mbar_init(&bar_a, 1);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&bar_full[s], 1);
@@ -342,21 +340,35 @@ __global__ void __launch_bounds__(128 + 128 * kQT, 1) hamming_select_tc_kernel(c
           mbar_wait_spin(&bar_tempty[i], static_cast<uint32_t>((k & 1) ^ 1));   // read out by its epilogue warps
           tc_fence_after();
           const uint64_t db = db0 + static_cast<uint64_t>((s * S::kB) >> 4);
+          // Long batches (>= 4 MMAs) are issued one at a time, not interleaved: interleaved, all four accumulators
+          // complete together and the tensor core idles through all four hand-overs at once.  (Measured: -7 % at
+          // KB = 160, +12 % at KB = 96 -- short batches are issued by whoever is ready.)
+          // The turn is a token that goes round the issuing warps through NAMED BARRIERS (ids 1 + accumulator): no
+          // shared-memory traffic -- a shared-memory CAS takes 200-300 clk while the MMA's operand fetch owns the
+          // port -- and it is handed on BEFORE the last MMA of the batch is issued, so the next warp's first MMA
+          // is queued right behind this batch instead of after a round trip (2-3 % against the CAS lock of round 1).
+          constexpr bool kOrdered = KB >= 128;
+          constexpr int kMmas = KB / 32;
+          constexpr int kHead = kMmas > 1 ? kMmas - 1 : 1;
+          const bool tok = kOrdered && nvalid > 1;
+          if (tok && !(k == 0 && i == 0))
+            asm volatile("barrier.sync.aligned %0, 64;" ::"r"(1 + i) : "memory");
           if (elect_one()) {
-            // Long batches (>= 4 MMAs) are issued one at a time (whoever is ready first), not interleaved:
-            // interleaved, all four accumulators complete together and the tensor core idles through all four
-            // hand-overs at once.  (Measured: -7 % at KB = 160, +12 % at KB = 96 -- short batches stay unlocked.)
-            constexpr bool kLock = KB >= 128;
-            if (kLock) {
-              while (atomicCAS(&mma_lock, 0u, 1u) != 0u) {
-              }
-            }
             umma_i8_imm<false>(d_addr, da, db, idesc);
 #pragma unroll
-            for (int kk = 1; kk < KB / 32; ++kk)
+            for (int kk = 1; kk < kHead; ++kk)
               umma_i8_imm<true>(d_addr, da + static_cast<uint64_t>((kk * 256) >> 4),
                                 db + static_cast<uint64_t>((kk * 256) >> 4), idesc);
-            if (kLock) atomicExch(&mma_lock, 0u);
+          }
+          __syncwarp();
+          // (the last arrival of the kernel would find nobody waiting: it is skipped)
+          if (tok && !(k == ntiles - 1 && i == nvalid - 1))
+            asm volatile("barrier.arrive.aligned %0, 64;" ::"r"(1 + (i + 1 == nvalid ? 0 : i + 1)) : "memory");
+          if (elect_one()) {    // (elect.sync picks the same lane for the same mask: the commit covers both blocks)
+#pragma unroll
+            for (int kk = kHead; kk < kMmas; ++kk)
+              umma_i8_imm<true>(d_addr, da + static_cast<uint64_t>((kk * 256) >> 4),
+                                db + static_cast<uint64_t>((kk * 256) >> 4), idesc);
             umma_commit(&bar_tfull[i]);           // accumulator i holds tile k (and is done reading stage s)
           }
           __syncwarp();
