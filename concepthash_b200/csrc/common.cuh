@@ -29,6 +29,7 @@ struct ch_ws {
 
 // host_pack.cpp: sign/bit-pack of pageable fp32 rows on the host's cores -> flag bits (1: a zero, 2: NaN)
 uint32_t ch_host_pack_f32(const float* src, int64_t n, int ncols, int64_t rs, int words, uint32_t* out, int nthreads);
+void ch_host_parallel_copy(void* dst, const void* src, size_t bytes, int nthreads);   // host_pack.cpp
 
 // thread-local last error ---------------------------------------------------------------------------
 void ch_set_error(const char* fmt, ...);

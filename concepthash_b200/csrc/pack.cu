@@ -576,9 +576,22 @@ extern "C" int ch_pack_labels(ch_ws* ws, const void* labels, int mem, int dtype,
     const void* src = labels;
     if (mem == CH_MEM_HOST) {
       const size_t bytes = r1 > r0 ? (static_cast<size_t>(r1 - r0 - 1) * row_stride + 1) * es : 0;
-      if (bytes)
-        CH_CUDA(cudaMemcpyAsync(ws->stage[0], static_cast<const char*>(labels) + static_cast<size_t>(r0) * row_stride * es,
-                                bytes, cudaMemcpyHostToDevice, st));
+      const char* hsrc = static_cast<const char*>(labels) + static_cast<size_t>(r0) * row_stride * es;
+      if (bytes >= (static_cast<size_t>(1) << 20) && ws->pack_threads > 1) {
+        // large pageable label arrays: the pool copies them into the pinned bounce buffer, the DMA runs from there
+        cudaPointerAttributes attr;
+        bool pageable = true;
+        if (cudaPointerGetAttributes(&attr, hsrc) == cudaSuccess) pageable = attr.type == cudaMemoryTypeUnregistered;
+        else cudaGetLastError();
+        if (pageable) {
+          if (ch_ws_ensure_bounce(ws)) return 1;
+          CH_CUDA(cudaEventSynchronize(ws->ev_copied[0]));   // the DMA that last read this bounce buffer is done
+          ch_host_parallel_copy(ws->bounce[0], hsrc, bytes, ws->pack_threads);
+          hsrc = static_cast<const char*>(ws->bounce[0]);
+        }
+      }
+      if (bytes) CH_CUDA(cudaMemcpyAsync(ws->stage[0], hsrc, bytes, cudaMemcpyHostToDevice, st));
+      if (hsrc == static_cast<const char*>(ws->bounce[0])) CH_CUDA(cudaEventRecord(ws->ev_copied[0], st));
       src = ws->stage[0];
     } else {
       src = static_cast<const char*>(labels);

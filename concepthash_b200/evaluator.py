@@ -154,7 +154,7 @@ class Evaluator:
         self.sample_min_ratio = 64         # ... and the sample must still hold ~R/stride*... rows: need ndb >= ratio * R
         self.stream_host_gallery = True    # host-resident gallery: overlap its H2D copy with the select pass
         self.stream_min_rows = 200_000
-        self.stream_chunks = 4
+        self.stream_chunks = 2             # blocks per wave-filling stripe group x 2 (fewer, larger blocks: ~0.15 ms of host work per block)
         self.use_tensor_cores = True       # select pass on tcgen05 (int8 +-1 codes) when the shape allows it
         self.epilogue_thresholds = True    # sparse select passes: threshold comparison in the epilogue (see _bare)
         self.paired_rows = True            # select pass: two gallery rows per accumulator cell where keys fit (see _pair)
