@@ -39,7 +39,7 @@ class SelectArgs(C.Structure):
     _fields_ = [(n, P) for n in ("q_i8", "g_i8", "cand_off", "cand_cap", "cand_cnt", "cand_rows", "err_flag", "thresh")] + \
                [(n, C.c_int64) for n in ("nq", "nq_pad", "ndb", "row_base")] + \
                [(n, C.c_int32) for n in ("nbit", "nstripes", "rows_per_stripe", "dense", "ternary")] + \
-               [("pair", C.c_int32), ("bad", P)]
+               [("pair", C.c_int32), ("bad", P), ("q_stripe_bytes", C.c_int64)]
 
 
 class CandArgs(C.Structure):
@@ -79,11 +79,14 @@ SIGNATURES = {
     "ch_tc_tile_rows": (C.c_int, [C.c_int]),
     "ch_expand_i8": (C.c_int, [P, P, P, C.c_int64, C.c_int, C.c_int, C.c_int, P, C.c_int64, P, C.c_int64, P]),
     "ch_hamming_select_tc": (C.c_int, [P, C.POINTER(SelectArgs), P]),
+    "ch_expand_i8_query_stripes": (C.c_int, [P, P, P, C.c_int64, C.c_int, C.c_int, P, C.c_int64, P, P, C.c_int, C.c_int,
+                                             C.c_int64, P]),
     "ch_cand_hist": (C.c_int, [P, C.POINTER(CandArgs), P]),
     "ch_gather_plane_words": (C.c_int, [C.c_int]),
     "ch_gather_plane": (C.c_int, [P, P, P, C.c_int64, C.c_int, P, P]),
     "ch_cand_finalize": (C.c_int, [P, C.POINTER(CandArgs), P]),
-    "ch_cand_caps": (C.c_int, [P, P, P, P, P, P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, P, P]),
+    "ch_cand_caps": (C.c_int, [P, P, P, P, P, P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, P, C.c_int, P,
+                               P]),
     "ch_slab_totals": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int64, P, P]),
     "ch_slab_exscan": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int64, P]),
     "ch_slab_scan": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int, C.c_int64, P, P]),

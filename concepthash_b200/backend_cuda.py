@@ -241,6 +241,9 @@ class CudaBackend:
         a.pair = int(bool(pair))
         a.bad = bad.data_ptr() if bad is not None else None
         a.q_i8, a.g_i8 = q_i8.data_ptr(), g_i8.data_ptr()
+        if q_i8.dim() == 3:                   # one query plane per stripe (expand_i8_query_stripes)
+            a.q_i8 = q_i8[stripe0:].data_ptr()
+            a.q_stripe_bytes = q_i8.stride(0) * q_i8.element_size()
         a.cand_off, a.cand_cap, a.cand_cnt = (cand[k][stripe0:].data_ptr() for k in ("off", "cap", "cnt"))
         a.cand_rows, a.err_flag = cand["rows"].data_ptr(), cand["err"].data_ptr()
         a.nq, a.nq_pad, a.ndb, a.row_base = nq, nq_pad, ndb, int(row_base)
@@ -299,11 +302,27 @@ class CudaBackend:
             a.pr_k[i] = int(v)
         L.check(self.lib.ch_cand_finalize(self.ws, C.byref(a), self._stream()), "ch_cand_finalize")
 
-    def cand_caps(self, cand, thresh, list_stripes, rows_per_stripe, nstripes, nq, nq_pad, sample_stride, cap):
+    def cand_caps(self, cand, thresh, list_stripes, rows_per_stripe, nstripes, nq, nq_pad, sample_stride, cap,
+                  m=0, scut=None):
+        """``scut`` (nq_pad) out: the (key, stripe) refinement of the thresholds -- stripes >= scut[q] are selected with
+        thresh[q] - 1 (``expand_i8_query_stripes``); ``m`` = the sample count the candidate prefix has to reach"""
         L.check(self.lib.ch_cand_caps(self.ws, _ptr(cand["off"]), _ptr(cand["cnt"]), _ptr(cand["rows"]),
                                       _ptr(cand["key"]), _ptr(thresh), int(list_stripes), int(rows_per_stripe),
-                                      int(nstripes), nq, nq_pad, int(sample_stride), _ptr(cap), self._stream()),
+                                      int(nstripes), nq, nq_pad, int(sample_stride), _ptr(cap), int(m), _ptr(scut),
+                                      self._stream()),
                 "ch_cand_caps")
+
+    def expand_i8_query_stripes(self, bits, nbit, min_rows, thresh, scut, nstripes, nq, nz=None, stripe0=0):
+        """paired query planes, one per stripe: (nstripes, rows, kb) int8 (thresh[q] - 1 for stripes >= scut[q])"""
+        kb = self.tc_code_bytes_pair(nbit, nz is not None)
+        rows_pad = int(bits.shape[0])
+        rows = max(rows_pad, (int(min_rows) + 31) // 32 * 32)
+        out = self.empty((int(nstripes), rows, kb), torch.int8)
+        L.check(self.lib.ch_expand_i8_query_stripes(self.ws, _ptr(bits), _ptr(nz), rows_pad, nbit, 0 if nz is None else 1,
+                                                    _ptr(out), rows, _ptr(thresh), _ptr(scut), int(stripe0),
+                                                    int(nstripes), int(nq), self._stream()),
+                "ch_expand_i8_query_stripes")
+        return out
 
     def hamming_hist(self, **kw):
         a = self._hist_args(**kw)

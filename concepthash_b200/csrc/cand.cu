@@ -85,11 +85,19 @@ __device__ __forceinline__ uint32_t key_id_of(const uint32_t (&qw)[W], const uin
   if constexpr (PW == 2) {
     const uint2 v = __ldg(reinterpret_cast<const uint2*>(plane) + row);
     g[0] = v.x; g[1] = v.y;
+  } else if constexpr (PW == 4) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(plane) + row);
+    g[0] = v.x; g[1] = v.y; g[2] = v.z; g[3] = v.w;
   } else {
+    // 32-byte rows: ONE 256-bit load (LDG.E.256, sm_100) instead of two 128-bit ones (a random gather costs the L1
+    // one wavefront per lane and instruction: -4 % on cfg4)
 #pragma unroll
-    for (int v4 = 0; v4 < PW / 4; ++v4) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(plane) + static_cast<size_t>(row) * (PW / 4) + v4);
-      g[4 * v4] = v.x; g[4 * v4 + 1] = v.y; g[4 * v4 + 2] = v.z; g[4 * v4 + 3] = v.w;
+    for (int v8 = 0; v8 < PW / 8; ++v8) {
+      const uint32_t* src = plane + static_cast<size_t>(row) * PW + 8 * v8;
+      asm("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+          : "=r"(g[8 * v8]), "=r"(g[8 * v8 + 1]), "=r"(g[8 * v8 + 2]), "=r"(g[8 * v8 + 3]), "=r"(g[8 * v8 + 4]),
+            "=r"(g[8 * v8 + 5]), "=r"(g[8 * v8 + 6]), "=r"(g[8 * v8 + 7])
+          : "l"(src));
     }
   }
   uint32_t key = 0;
@@ -330,16 +338,23 @@ __global__ void __launch_bounds__(kCandWarps * 32) cand_final_kernel(const CandD
 // cap[s][q] = stride * (k + 6 sqrt(k + 1) + 9), k = #sample candidates of query q with key <= thresh[q] whose row
 // lies in stripe s of the full pass (sample rows [s * rows_per_stripe, (s + 1) * rows_per_stripe)) -- the bound of
 // record_caps_kernel.  One warp per query, per-stripe counters in shared memory.
+// scut != NULL: the threshold of a query is refined to a (key, stripe) pair.  Candidates are a PREFIX of the canonical
+// (key, row) order, and stripes are row blocks, so "key < t, or key == t in a stripe below scut" is a prefix too:
+// scut[q] = the smallest stripe count at which the sample holds >= m items of that prefix (nstripes: all of them are
+// needed).  Stripes >= scut[q] then run with the threshold t - 1 -- the items with key == t are a large part of a
+// key-level candidate list, and only those of the first few stripes can reach the top R.
 __global__ void __launch_bounds__(kCandWarps * 32) cand_caps_kernel(
     const uint32_t* __restrict__ off, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ rows,
     const uint16_t* __restrict__ key, const uint32_t* __restrict__ thresh, int list_stripes, int rows_per_stripe,
-    int nstripes, long long nq, long long nq_pad, int stride, uint32_t* __restrict__ cap) {
-  extern __shared__ uint32_t sh[];                       // per warp: nstripes counters
+    int nstripes, long long nq, long long nq_pad, int stride, uint32_t* __restrict__ cap, int m,
+    uint32_t* __restrict__ scut) {
+  extern __shared__ uint32_t sh[];                       // per warp: nstripes counters (key < t), nstripes (key == t)
   const int wip = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long q = static_cast<long long>(blockIdx.x) * kCandWarps + wip;
   if (q >= nq_pad) return;                               // whole warps leave; only __syncwarp below
-  uint32_t* c = sh + static_cast<size_t>(wip) * nstripes;
-  for (int s = lane; s < nstripes; s += 32) c[s] = 0u;
+  uint32_t* c = sh + static_cast<size_t>(wip) * 2 * nstripes;
+  uint32_t* ce = c + nstripes;
+  for (int s = lane; s < 2 * nstripes; s += 32) c[s] = 0u;
   __syncwarp();
   if (q < nq) {
     const uint32_t t = thresh[q];
@@ -347,18 +362,31 @@ __global__ void __launch_bounds__(kCandWarps * 32) cand_caps_kernel(
       const size_t i = static_cast<size_t>(ls) * nq_pad + q;
       const uint32_t o = off[i], n = cnt[i];
       for (uint32_t j = lane; j < n; j += 32) {
-        if (key[o + j] > t) continue;
+        const uint32_t k = key[o + j];
+        if (k > t) continue;
         int s = static_cast<int>((rows[o + j] & 0x7fffffffu) / static_cast<uint32_t>(rows_per_stripe));
         if (s >= nstripes) s = nstripes - 1;
-        atomicAdd(&c[s], 1u);
+        atomicAdd(k == t ? &ce[s] : &c[s], 1u);
       }
     }
   }
   __syncwarp();
+  int cut = nstripes;
+  if (scut != nullptr) {
+    if (q < nq) {
+      // (every lane walks the few stripes itself: no divergence, no shuffles)
+      uint32_t have = 0u;
+      for (int s = 0; s < nstripes; ++s) have += c[s];
+      cut = 0;
+      while (cut < nstripes && have < static_cast<uint32_t>(m)) have += ce[cut++];
+      if (have < static_cast<uint32_t>(m)) cut = nstripes;
+    }
+    if (lane == 0) scut[q] = static_cast<uint32_t>(cut);
+  }
   for (int s = lane; s < nstripes; s += 32) {
     uint32_t v = 0u;
     if (q < nq) {
-      const float kf = static_cast<float>(c[s]);
+      const float kf = static_cast<float>(c[s] + (s < cut ? ce[s] : 0u));
       v = static_cast<uint32_t>((kf + 6.0f * sqrtf(kf + 1.0f) + 9.0f) * static_cast<float>(stride));
     }
     cap[static_cast<size_t>(s) * nq_pad + q] = v;
@@ -442,7 +470,7 @@ extern "C" int ch_cand_hist(ch_ws* ws, const ch_cand_args* a, void* stream) {
 extern "C" int ch_cand_caps(ch_ws* ws, const uint32_t* cand_off, const uint32_t* cand_cnt, const uint32_t* cand_rows,
                             const uint16_t* cand_key, const uint32_t* thresh, int list_stripes, int rows_per_stripe,
                             int nstripes, int64_t nq, int64_t nq_pad, int sample_stride, uint32_t* cap_dev,
-                            void* stream) {
+                            int m, uint32_t* scut_dev, void* stream) {
   if (ws == nullptr || cand_off == nullptr || cand_cnt == nullptr || cand_rows == nullptr || cand_key == nullptr ||
       thresh == nullptr || cap_dev == nullptr)
     CH_FAIL("null argument to ch_cand_caps");
@@ -450,9 +478,10 @@ extern "C" int ch_cand_caps(ch_ws* ws, const uint32_t* cand_off, const uint32_t*
     CH_FAIL("bad arguments to ch_cand_caps");
   ChDeviceGuard guard(ws->device);
   cand_caps_kernel<<<static_cast<unsigned>((nq_pad + kCandWarps - 1) / kCandWarps), kCandWarps * 32,
-                     static_cast<size_t>(kCandWarps) * nstripes * sizeof(uint32_t), static_cast<cudaStream_t>(stream)>>>(
+                     static_cast<size_t>(kCandWarps) * 2 * nstripes * sizeof(uint32_t),
+                     static_cast<cudaStream_t>(stream)>>>(
       cand_off, cand_cnt, cand_rows, cand_key, thresh, list_stripes, rows_per_stripe, nstripes, nq, nq_pad,
-      sample_stride, cap_dev);
+      sample_stride, cap_dev, m, scut_dev);
   CH_LAUNCH_CHECK(ws);
   return 0;
 }

@@ -100,6 +100,7 @@ struct SelDev {
   int nbit, ternary;
   long long nq, nq_pad, ndb, row_base;
   int rows_per_stripe;
+  long long q_stripe_bytes;    // distance of the per-stripe query planes (0: one plane)
   int nqtiles128;              // 128-query tiles in total
   int nqgroups;                // CTAs along the query axis (each owns kQT consecutive query tiles)
 };
@@ -327,7 +328,9 @@ __global__ void __launch_bounds__(128 + 128 * kQT, 1) hamming_select_tc_kernel(c
       if (warp == 0) {
         if (elect_one()) {
           mbar_arrive_expect_tx(&bar_a, nvalid * S::kA);
-          bulk_g2s(smem + S::offA, a.q_i8 + static_cast<size_t>(qtile0) * kTileM * KB, nvalid * S::kA, &bar_a);
+          bulk_g2s(smem + S::offA,
+                   a.q_i8 + static_cast<size_t>(stripe) * a.q_stripe_bytes + static_cast<size_t>(qtile0) * kTileM * KB,
+                   nvalid * S::kA, &bar_a);
         }
         for (; next_load < kStages && next_load < ntiles; ++next_load) load_tile(next_load);
       }
@@ -568,10 +571,11 @@ __global__ void expand_i8_tiled_kernel(const uint32_t* __restrict__ bits, const 
 __global__ void expand_i8_pair_kernel(const uint32_t* __restrict__ bits, const uint32_t* __restrict__ nz,
                                       long long rows_bits, long long rows_out, int words, int nbit, int kb,
                                       int ternary, int query, const uint32_t* __restrict__ thresh, long long nq,
-                                      int8_t* __restrict__ out) {
+                                      int8_t* __restrict__ out, const uint32_t* __restrict__ scut, int stripe0) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int chunks = kb / 16;
   if (i >= rows_out * chunks) return;
+  out += static_cast<size_t>(blockIdx.y) * rows_out * kb;      // one query plane per stripe (blockIdx.y)
   const long long group = i / (8ll * chunks);
   const int within = static_cast<int>(i - group * 8ll * chunks);
   const int chunk = within / 8, r8 = within % 8;
@@ -586,12 +590,17 @@ __global__ void expand_i8_pair_kernel(const uint32_t* __restrict__ bits, const u
   const int k0 = chunk * 16;
   // a query row whose code is written as zeros: padding, or thresh >= 128 (every row is a candidate)
   uint32_t t = 0u;
-  bool zero_code = false;
+  bool zero_code = false, none = false;
   if (query) {
     zero_code = !(prow < nq && prow < rows_bits);
     if (!zero_code) {
       t = thresh[prow];
-      zero_code = t > 127u;
+      if (scut != nullptr && static_cast<uint32_t>(stripe0) + blockIdx.y >= scut[prow]) {
+        // this stripe lies beyond the query's cut: threshold t - 1 (below 0: no candidates, like a padding query)
+        if (t == 0u) none = true;
+        else if (t <= 128u) --t;           // (t > 128: every row qualifies with t - 1 as well)
+      }
+      zero_code = none || t > 127u;
     }
   }
   uint32_t o[4];
@@ -618,7 +627,7 @@ __global__ void expand_i8_pair_kernel(const uint32_t* __restrict__ bits, const u
   int slot[kPairSlots] = {2, 1, -128, -128, -128};
   if (query) {
     int c0 = 0, c1 = 0;                          // padding queries: E = 0, nothing is a candidate
-    if (prow < nq && prow < rows_bits && k0 + 16 > 2 * nbit) {
+    if (prow < nq && prow < rows_bits && !none && k0 + 16 > 2 * nbit) {
       if (t > 127u) {                            // every row is a candidate: E = 128 - 256 whatever the row
         c0 = 128;
         c1 = -1;
@@ -737,7 +746,7 @@ extern "C" int ch_expand_i8(ch_ws* ws, const uint32_t* bits_dev, const uint32_t*
     const long long n = rows_out * (kbp / 16);
     expand_i8_pair_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         bits_dev, ternary ? nz_dev : nullptr, rows_bits, rows_out, ch_code_words(nbit), nbit, kbp, ternary ? 1 : 0,
-        bare == 4 ? 1 : 0, thresh_dev, nq, out_dev);
+        bare == 4 ? 1 : 0, thresh_dev, nq, out_dev, nullptr, 0);
     CH_LAUNCH_CHECK(ws);
     return 0;
   }
@@ -755,6 +764,28 @@ extern "C" int ch_expand_i8(ch_ws* ws, const uint32_t* bits_dev, const uint32_t*
       bits_dev, ternary ? nz_dev : nullptr, rows_bits, rows_out, ch_code_words(nbit), nbit, kb,
       bare ? 0 : thresh_slots(nbit), ternary ? 1 : 0, (thresh_dev != nullptr || bare == 2) ? 1 : 0, thresh_dev, nq,
       out_dev);
+  CH_LAUNCH_CHECK(ws);
+  return 0;
+}
+
+extern "C" int ch_expand_i8_query_stripes(ch_ws* ws, const uint32_t* bits_dev, const uint32_t* nz_dev, int64_t rows_bits,
+                                          int nbit, int ternary, int8_t* out_dev, int64_t rows_out,
+                                          const uint32_t* thresh_dev, const uint32_t* scut_dev, int stripe0, int nstripes,
+                                          int64_t nq, void* stream) {
+  if (ws == nullptr || bits_dev == nullptr || out_dev == nullptr || thresh_dev == nullptr || scut_dev == nullptr)
+    CH_FAIL("null argument to ch_expand_i8_query_stripes");
+  if (ternary && nz_dev == nullptr) CH_FAIL("ternary codes need the non-zero plane");
+  const int kbp = ch_tc_code_bytes_pair(nbit, ternary);
+  if (kbp == 0) CH_FAIL("nbit=%d ternary=%d has no paired form (binary <= 128 bits, ternary <= 64)", nbit, ternary);
+  if (rows_out % 32 || rows_bits < 0 || rows_out < rows_bits || rows_out == 0)
+    CH_FAIL("rows_out must be a positive multiple of 32 and >= rows_bits");
+  if (nstripes <= 0 || nstripes > 65535 || stripe0 < 0) CH_FAIL("bad stripe range");
+  ChDeviceGuard guard(ws->device);
+  const long long n = rows_out * (kbp / 16);
+  const dim3 grid(static_cast<unsigned>((n + 255) / 256), static_cast<unsigned>(nstripes));
+  expand_i8_pair_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      bits_dev, ternary ? nz_dev : nullptr, rows_bits, rows_out, ch_code_words(nbit), nbit, kbp, ternary ? 1 : 0, 1,
+      thresh_dev, nq, out_dev, scut_dev, stripe0);
   CH_LAUNCH_CHECK(ws);
   return 0;
 }
@@ -788,6 +819,8 @@ extern "C" int ch_hamming_select_tc(ch_ws* ws, const ch_select_args* a, void* st
   d.thresh = a->thresh; d.nbit = a->nbit; d.ternary = a->ternary; d.bad = a->bad;
   d.nq = a->nq; d.nq_pad = a->nq_pad; d.ndb = a->ndb; d.row_base = a->row_base;
   d.rows_per_stripe = a->rows_per_stripe;
+  d.q_stripe_bytes = a->q_stripe_bytes;
+  if (a->q_stripe_bytes < 0 || (a->q_stripe_bytes & 15)) CH_FAIL("bad q_stripe_bytes");
   d.nqtiles128 = static_cast<int>(a->nq_pad / kTileM);
   d.nqgroups = (d.nqtiles128 + kQT - 1) / kQT;
   size_t smem = 0;

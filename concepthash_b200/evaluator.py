@@ -158,6 +158,8 @@ class Evaluator:
         self.use_tensor_cores = True       # select pass on tcgen05 (int8 +-1 codes) when the shape allows it
         self.epilogue_thresholds = True    # sparse select passes: threshold comparison in the epilogue (see _bare)
         self.paired_rows = True            # select pass: two gallery rows per accumulator cell where keys fit (see _pair)
+        self.debug_counts = False          # dev tools: stats["candidates"] = length of all candidate lists (costs a sync)
+        self.stripe_cut = True             # sampled thresholds refined to (key, stripe) pairs (see _sample_thresholds_tc)
         self.select_dense_override = None  # tests: force the dense / sparse epilogue of the tensor-core kernel
         self.col_sub = None                # zero_mean_eval: f64[nbit] column offset of the current evaluation
         self.events = []                   # (kind, work units, start event, end event)
@@ -416,9 +418,13 @@ class Evaluator:
         return bool(self.paired_rows and hasattr(self.b, "tc_code_bytes_pair") and
                     self.b.tc_code_bytes_pair(q.nbit, q.nz is not None) > 0)
 
-    def _query_plane(self, q, nq_pad, thresh, bare=False, pair=False):
-        """int8 query plane: with the thresholds in its threshold slots (made per select pass), or bare"""
+    def _query_plane(self, q, nq_pad, thresh, bare=False, pair=False, scut=None, nstripes=0):
+        """int8 query plane: with the thresholds in its threshold slots (made per select pass), or bare; ``scut``: one
+        paired plane per stripe (threshold - 1 in the stripes beyond a query's cut)"""
         kw = {} if q.nz is None else dict(nz=q.nz)
+        if pair and scut is not None:
+            return self._timed("expand_i8", 0, lambda: self.b.expand_i8_query_stripes(q.bits, q.nbit, nq_pad, thresh, scut,
+                                                                                      nstripes, q.n, **kw))
         if pair:
             return self._timed("expand_i8", 0, lambda: self.b.expand_i8(q.bits, q.nbit, nq_pad, thresh=thresh, nq=q.n,
                                                                         pair=True, **kw))
@@ -444,13 +450,14 @@ class Evaluator:
         return p.i8
 
     def _select_tc(self, q, g, geo, thresh, cand, dense, kind="hist_select_tc", ndb=None, nstripes=None, rps=None,
-                   bad=None):
+                   bad=None, scut=None):
         """the select pass on the tensor cores over the packed shard ``g`` (or a row sample of it); ``bad`` (nq_pad):
         marked for every query one of whose slices overflows"""
         threads, nq_pad, nstripes_g, rps_g = geo
         pair = self._pair(q)
         bare = not pair and self._bare(dense)
-        q_i8 = self._query_plane(q, nq_pad, thresh, bare, pair)
+        q_i8 = self._query_plane(q, nq_pad, thresh, bare, pair, scut if pair else None,
+                                 nstripes_g if nstripes is None else nstripes)
         g_i8 = self._gallery_plane(g, bare, pair)
         kw = dict(thresh=thresh, ternary=q.nz is not None) if bare else {}
         if pair:
@@ -503,6 +510,8 @@ class Evaluator:
         if tot is None:
             tot = b.zeros((2, nbins, nq_pad), torch.int32)
             self._cand_hist(c, cand, nbins, tot)
+        if self.debug_counts:                                        # (dev tools only: a host round trip)
+            self.stats["candidates"] = int(cand["cnt"][:, :nq].sum(dtype=torch.int64))
         tot = comm.all_gather(tot)                                   # (world, 2, nbins, nq_pad)
         base0_all = b.empty((nbins, nq_pad), torch.int32)
         base0_rel = b.empty((nbins, nq_pad), torch.int32) if labelled else None
@@ -1089,8 +1098,9 @@ class Evaluator:
         bad = b.zeros((nq_pad,), torch.int32) if tc_pass else None
         if (tc_pass and self.sample_two_level and min(ns_ranks) >= self.sample2_min_rows and
                 float(nq) * min(ns_ranks) * int(q.bits.shape[1]) >= self.sample2_min_work):
-            thresh, cap = self._sample_thresholds_tc(c, sp, ns_ranks, m, status, first_load, bad)
+            thresh, cap, scut = self._sample_thresholds_tc(c, sp, ns_ranks, m, status, first_load, bad)
         else:
+            scut = None
             slab_s = b.zeros((nstripes, nbins, nq_pad), torch.int32)
             self._hist(q, sp, geo_s, ternary, L.CH_LAB_NONE, 0, slab_s, None)
             thresh = b.empty((nq_pad,), torch.int32)
@@ -1112,7 +1122,8 @@ class Evaluator:
             self.stats["sample"]["key_limit"] = nbins
             tot = None
             if streamed:
-                q_i8 = self._query_plane(q, nq_pad, thresh, streamer.bare, streamer.pair)
+                q_i8 = self._query_plane(q, nq_pad, thresh, streamer.bare, streamer.pair,
+                                         scut if streamer.pair else None, nstripes)
                 tot = b.zeros((2, nbins, nq_pad), torch.int32)
                 for i in range(len(streamer.blocks)):
                     streamer.select(i, cand, q_i8, dense, thresh, bad)
@@ -1126,7 +1137,8 @@ class Evaluator:
                 self.stats["select_threshold"] = "epilogue" if streamer.bare else "contraction"
                 self.stats["select_rows_per_cell"] = 2 if streamer.pair else 1
             else:
-                self._select_tc(q, g, geo, thresh, cand, dense, bad=bad)
+                self._select_tc(q, g, geo, thresh, cand, dense, bad=bad, scut=scut)
+            self.stats["sample"]["stripe_cut"] = scut is not None
             base0_all, base0_rel, key_max = self._cand_bases(c, cand, nbins, need, tot, rmax=c["rmax"] + c["rf"],
                                                              bad=bad)
             return dict(cand=cand, base0_all=base0_all, base0_rel=base0_rel, nbins=nbins, key_max=key_max,
@@ -1219,9 +1231,15 @@ class Evaluator:
         b.scan_bases(self._summed_totals(tot1), 1, 0, nb0, nq, nq_pad, m, base1, thresh1, None)
         thresh = torch.minimum(thresh1, thresh0)
         cap = b.empty((nstripes, nq_pad), torch.int32)
-        b.cand_caps(cand1, thresh, n1, rps // stride, nstripes, nq, nq_pad, stride, cap)
+        # (key, stripe) refinement of the thresholds: the items with key == t^ are more than half of a key-level
+        # candidate list, yet only those of the first few stripes can reach the top R (ties rank by row).  One rank:
+        # the cut over (rank, stripe) would need the per-stripe counts of every rank.
+        scut = None
+        if self.stripe_cut and comm.world == 1 and nstripes > 1 and self._pair(q) and hasattr(b, "expand_i8_query_stripes"):
+            scut = b.empty((nq_pad,), torch.int32)
+        b.cand_caps(cand1, thresh, n1, rps // stride, nstripes, nq, nq_pad, stride, cap, m=m, scut=scut)
         self.stats["sample2"] = dict(sub=sub, m0=m0, key_limit0=nb0, slots=self.stats.get("record_slots"))
-        return thresh, cap
+        return thresh, cap, scut
 
     def _total_rel_from_classes(self, c, cls):
         """relevant items in the whole gallery per query = class frequency of the query's class (single-label)"""

@@ -198,6 +198,8 @@ typedef struct ch_select_args {
                                  a tile is 256 rows; rows_per_stripe % 256 == 0, thresh must be NULL */
   uint32_t* bad;              /* (nq_pad) or NULL: bad[q] = 1 for every query one of whose slices overflowed, so that
                                  the caller can re-rank just those queries by the exact path */
+  int64_t q_stripe_bytes;     /* 0: one query plane for all stripes; else q_i8 holds one plane per stripe of this launch
+                                 (ch_expand_i8_query_stripes), this many bytes apart */
 } ch_select_args;
 int ch_tc_code_bytes(int nbit);
 /* queries one CTA of the select kernel owns (its grid is ceil(nq_pad / this) x nstripes, one CTA per SM) */
@@ -220,6 +222,12 @@ int ch_expand_i8(ch_ws* ws, const uint32_t* bits_dev, const uint32_t* nz_dev /* 
                              4: paired query plane (thresh_dev required) */,
                  int8_t* out_dev, int64_t rows_out, const uint32_t* thresh_dev /* or NULL */, int64_t nq,
                  void* stream);
+/* the paired query plane (form 4) once per stripe: out (nstripes, rows_out, kb); plane s carries thresh[q] for the
+ * stripes stripe0 + s < scut[q] and thresh[q] - 1 (below 0: nothing is a candidate) for the others.  The select
+ * kernel reads plane `stripe` of a launch when ch_select_args.q_stripe_bytes = rows_out * kb is set. */
+int ch_expand_i8_query_stripes(ch_ws* ws, const uint32_t* bits_dev, const uint32_t* nz_dev, int64_t rows_bits, int nbit,
+                               int ternary, int8_t* out_dev, int64_t rows_out, const uint32_t* thresh_dev,
+                               const uint32_t* scut_dev, int stripe0, int nstripes, int64_t nq, void* stream);
 int ch_hamming_select_tc(ch_ws* ws, const ch_select_args* a, void* stream);
 
 /* ---- K3/K4 on candidate lists ---------------------------------------------------------------------
@@ -269,10 +277,16 @@ int ch_cand_finalize(ch_ws* ws, const ch_cand_args* a, void* stream);
  * already written by ch_cand_hist) came from a select pass over a 1-in-`sample_stride` row sample.
  * cap[s][q] = sample_stride * (k + 6 sqrt(k + 1) + 9), k = #sample candidates of query q with key <= thresh[q]
  * whose sample row lies in [s * rows_per_stripe, (s + 1) * rows_per_stripe): the capacity of slice (s, q) of the
- * full pass (same bound as ch_record_caps with sample_stride).  cap_dev: (nstripes, nq_pad). */
+ * full pass (same bound as ch_record_caps with sample_stride).  cap_dev: (nstripes, nq_pad).
+ * scut_dev != NULL (nq_pad): the threshold is refined to a (key, stripe) pair -- candidates are a prefix of the
+ * canonical (key, row) order and stripes are row blocks, so "key < thresh, or key == thresh in a stripe < scut" is a
+ * prefix as well: scut[q] = the smallest stripe count at which the sample holds >= m items of that prefix (nstripes
+ * if it never does); stripes >= scut[q] are to be selected with thresh[q] - 1 (ch_expand_i8_query_stripes) and their
+ * capacities count keys < thresh only. */
 int ch_cand_caps(ch_ws* ws, const uint32_t* cand_off, const uint32_t* cand_cnt, const uint32_t* cand_rows,
                  const uint16_t* cand_key, const uint32_t* thresh, int list_stripes, int rows_per_stripe,
-                 int nstripes, int64_t nq, int64_t nq_pad, int sample_stride, uint32_t* cap_dev, void* stream);
+                 int nstripes, int64_t nq, int64_t nq_pad, int sample_stride, uint32_t* cap_dev,
+                 int m, uint32_t* scut_dev, void* stream);
 
 /* slab reductions: totals over stripes -> tot (nbins, nq_pad); exclusive scan over stripes in place */
 int ch_slab_totals(ch_ws* ws, const uint32_t* slab, int nstripes, int nbins, int64_t nq_pad,

@@ -209,6 +209,12 @@ class EmuBackend:
         return dict(bits=bits, nz=nz, nbit=nbit, nq=nq, bare=bare, pair=pair,
                     thresh=None if thresh is None else thresh.clone())
 
+    def expand_i8_query_stripes(self, bits, nbit, min_rows, thresh, scut, nstripes, nq, nz=None, stripe0=0):
+        self.launches += 1
+        assert self.tc_code_bytes_pair(nbit, nz is not None) > 0 and stripe0 == 0
+        return dict(bits=bits, nz=nz, nbit=nbit, nq=nq, bare=False, pair=True, thresh=thresh.clone(),
+                    scut=scut.clone(), nstripes=nstripes)
+
     def hamming_select_tc(self, *, q_i8, g_i8, cand, nq, nq_pad, ndb, nbit, nstripes, rows_per_stripe, row_base=0,
                           dense=False, stripe0=0, thresh=None, ternary=False, bad=None, pair=False):
         self.launches += 1
@@ -225,7 +231,10 @@ class EmuBackend:
         for s in range(nstripes):
             r0, r1 = s * rows_per_stripe, min(ndb, (s + 1) * rows_per_stripe)
             for q in range(nq):
-                js = [j + row_base for j in range(r0, r1) if keys[q, j] <= th[q]]
+                tq = int(th[q])
+                if q_i8.get("scut") is not None and s + stripe0 >= int(_u32(q_i8["scut"])[q]):
+                    tq -= 1                  # beyond the query's stripe cut: one key less
+                js = [j + row_base for j in range(r0, r1) if keys[q, j] <= tq]
                 w = min(len(js), int(cap[s + stripe0, q]))
                 o = int(off[s + stripe0, q])
                 rows[o:o + w] = js[:w]
@@ -271,18 +280,35 @@ class EmuBackend:
                     key[o + i] = k
                     rows[o + i] = row | (0x80000000 if r else 0)
 
-    def cand_caps(self, cand, thresh, list_stripes, rows_per_stripe, nstripes, nq, nq_pad, sample_stride, cap):
+    def cand_caps(self, cand, thresh, list_stripes, rows_per_stripe, nstripes, nq, nq_pad, sample_stride, cap,
+                  m=0, scut=None):
         self.launches += 1
         off, cnt, rows, key = _u32(cand["off"]), _u32(cand["cnt"]), _u32(cand["rows"]), cand["key"].numpy()
         th, c = _u32(thresh), _u32(cap)
         c[...] = 0
         raw = np.zeros((nstripes, nq_pad), dtype=np.float32)
+        eq = np.zeros((nstripes, nq_pad), dtype=np.float32)
         for ls in range(list_stripes):
             for q in range(nq):
                 o = int(off[ls, q])
                 for j in range(int(cnt[ls, q])):
                     if key[o + j] <= th[q]:
-                        raw[min(int(rows[o + j] & 0x7FFFFFFF) // rows_per_stripe, nstripes - 1), q] += 1
+                        s = min(int(rows[o + j] & 0x7FFFFFFF) // rows_per_stripe, nstripes - 1)
+                        (eq if key[o + j] == th[q] else raw)[s, q] += 1
+        if scut is not None:
+            sc = _u32(scut)
+            for q in range(nq_pad):
+                cut = nstripes
+                if q < nq:
+                    have, cut = raw[:, q].sum(), 0
+                    while cut < nstripes and have < m:
+                        have += eq[cut, q]
+                        cut += 1
+                    if have < m:
+                        cut = nstripes
+                sc[q] = cut
+                eq[cut:, q] = 0
+        raw += eq
         bound = (raw + np.float32(6.0) * np.sqrt(raw + np.float32(1.0)) + np.float32(9.0)) * np.float32(sample_stride)
         c[:, :nq] = bound[:, :nq].astype(np.uint32)
 

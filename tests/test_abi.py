@@ -50,7 +50,7 @@ def test_struct_layout_matches_c(lib):
     # sizes as the C compiler lays them out (pointers 8, int64 8, int32 4, natural alignment)
     assert ctypes.sizeof(_lib.HistArgs) == 14 * 8 + 3 * 8 + 8 * 4 + 8 + 4 + 4     # ..., int64 row_base, int32 + padding
     assert ctypes.sizeof(_lib.FinalArgs) == 10 * 8 + 2 * 8 + 5 * 4 + 4 + 8 * 8 + 32 * 8
-    assert ctypes.sizeof(_lib.SelectArgs) == 8 * 8 + 4 * 8 + 5 * 4 + 4 + 8
+    assert ctypes.sizeof(_lib.SelectArgs) == 8 * 8 + 4 * 8 + 6 * 4 + 8 + 8      # ..., int32 pair, bad, int64 q_stripe_bytes
     assert ctypes.sizeof(_lib.CandArgs) == 22 * 8 + 4 * 8 + 9 * 4 + 4 + 8 * 8 + 32 * 8
 
 
