@@ -76,12 +76,11 @@ __device__ __forceinline__ uint32_t key_of_ternary(const uint32_t (&qw)[W], cons
 // words per row of the gather plane: the code words + the class id, rounded up to a power of two (8 .. 64 bytes)
 __host__ __device__ constexpr int plane_words(int W) { return W == 1 ? 2 : W == 2 ? 4 : W == 4 ? 8 : 16; }
 
-// key and class id of one candidate from the gather plane: ONE 32-byte sector for codes of <= 128 bits
+// one row of the gather plane ([code words | class id | pad]): ONE 32-byte sector for codes of <= 128 bits
 template <int W>
-__device__ __forceinline__ uint32_t key_id_of(const uint32_t (&qw)[W], const uint32_t* __restrict__ plane, uint32_t row,
-                                              uint32_t* id) {
+__device__ __forceinline__ void load_plane_row(const uint32_t* __restrict__ plane, uint32_t row,
+                                               uint32_t (&g)[plane_words(W)]) {
   constexpr int PW = plane_words(W);
-  uint32_t g[PW];
   if constexpr (PW == 2) {
     const uint2 v = __ldg(reinterpret_cast<const uint2*>(plane) + row);
     g[0] = v.x; g[1] = v.y;
@@ -90,7 +89,7 @@ __device__ __forceinline__ uint32_t key_id_of(const uint32_t (&qw)[W], const uin
     g[0] = v.x; g[1] = v.y; g[2] = v.z; g[3] = v.w;
   } else {
     // 32-byte rows: ONE 256-bit load (LDG.E.256, sm_100) instead of two 128-bit ones (a random gather costs the L1
-    // one wavefront per lane and instruction: -4 % on cfg4)
+    // one wavefront per lane and instruction)
 #pragma unroll
     for (int v8 = 0; v8 < PW / 8; ++v8) {
       const uint32_t* src = plane + static_cast<size_t>(row) * PW + 8 * v8;
@@ -100,11 +99,6 @@ __device__ __forceinline__ uint32_t key_id_of(const uint32_t (&qw)[W], const uin
           : "l"(src));
     }
   }
-  uint32_t key = 0;
-#pragma unroll
-  for (int w = 0; w < W; ++w) key += __popc(qw[w] ^ g[w]);
-  *id = g[W];
-  return key;
 }
 
 __global__ void gather_plane_kernel(const uint32_t* __restrict__ bits, const uint32_t* __restrict__ ids, long long rows,
@@ -136,7 +130,11 @@ __global__ void __launch_bounds__(kCandWarps * 32) cand_hist_kernel(const CandDe
   const uint32_t* qm = a.label_mode == CH_LAB_MASK ? a.q_lab + q * a.lw : nullptr;
   bool bad = false;
   __syncwarp();
-  constexpr int U = 8;                         // candidates per lane in flight (independent gathers)
+  // candidates per lane in flight.  The gathers of all U candidates are issued back to back, UNCONDITIONALLY (lanes
+  // past the end of the slice read row 0), before the first one is used: with the load inside a predicated block per
+  // candidate the compiler serialised them, and the kernel sat in long-scoreboard stalls (63 % of its samples) with
+  // one random sector in flight per lane.
+  constexpr int U = plane_words(W) <= 4 ? 8 : 4;
   for (int s = 0; s < a.nstripes; ++s) {
     const size_t sq = static_cast<size_t>(s) * a.nq_pad + q;
     const uint32_t off = a.cand_off[sq], n = a.cand_cnt[sq];
@@ -149,24 +147,32 @@ __global__ void __launch_bounds__(kCandWarps * 32) cand_hist_kernel(const CandDe
         ok[u] = i < n;
         row[u] = ok[u] ? (a.cand_rows[off + i] & 0x7fffffffu) : 0u;
       }
+      if (a.g_plane != nullptr) {              // single-label: code and class id come in one sector
+        uint32_t g[U][plane_words(W)];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        rel[u] = false;
-        if (a.g_plane != nullptr) {            // single-label: code and class id come in one sector
-          uint32_t id = 0u;
-          key[u] = ok[u] ? key_id_of<W>(qw, a.g_plane, row[u], &id) : 0u;
-          rel[u] = ok[u] && id == qid;
-          continue;
+        for (int u = 0; u < U; ++u) load_plane_row<W>(a.g_plane, row[u], g[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          uint32_t k = 0;
+#pragma unroll
+          for (int w = 0; w < W; ++w) k += __popc(qw[w] ^ g[u][w]);
+          key[u] = k;
+          rel[u] = ok[u] && g[u][W] == qid;
         }
-        if (tern) key[u] = ok[u] ? key_of_ternary<W>(qw, qz, a.g_bits, a.g_nz, row[u], a.nbit) : 0u;
-        else key[u] = ok[u] ? key_of<W>(qw, a.g_bits, row[u]) : 0u;
-        if (ok[u]) {
-          if (a.label_mode == CH_LAB_ID) {
-            rel[u] = __ldg(a.g_lab + row[u]) == qid;
-          } else if (a.label_mode == CH_LAB_MASK) {
-            uint32_t any = 0;
-            for (int w = 0; w < a.lw; ++w) any |= qm[w] & __ldg(a.g_lab + static_cast<size_t>(row[u]) * a.lw + w);
-            rel[u] = any != 0u;
+      } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          rel[u] = false;
+          if (tern) key[u] = ok[u] ? key_of_ternary<W>(qw, qz, a.g_bits, a.g_nz, row[u], a.nbit) : 0u;
+          else key[u] = ok[u] ? key_of<W>(qw, a.g_bits, row[u]) : 0u;
+          if (ok[u]) {
+            if (a.label_mode == CH_LAB_ID) {
+              rel[u] = __ldg(a.g_lab + row[u]) == qid;
+            } else if (a.label_mode == CH_LAB_MASK) {
+              uint32_t any = 0;
+              for (int w = 0; w < a.lw; ++w) any |= qm[w] & __ldg(a.g_lab + static_cast<size_t>(row[u]) * a.lw + w);
+              rel[u] = any != 0u;
+            }
           }
         }
       }
