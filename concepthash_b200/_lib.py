@@ -85,6 +85,7 @@ SIGNATURES = {
     "ch_gather_plane_words": (C.c_int, [C.c_int]),
     "ch_gather_plane": (C.c_int, [P, P, P, C.c_int64, C.c_int, P, P]),
     "ch_cand_finalize": (C.c_int, [P, C.POINTER(CandArgs), P]),
+    "ch_cand_rank": (C.c_int, [P, C.POINTER(CandArgs), C.c_int64, C.c_int64, P, P, P]),
     "ch_cand_caps": (C.c_int, [P, P, P, P, P, P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, P, C.c_int, P,
                                P]),
     "ch_slab_totals": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int64, P, P]),

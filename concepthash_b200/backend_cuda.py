@@ -285,6 +285,22 @@ class CudaBackend:
                             mask_words=mask_words, tot_all=tot_all, tot_rel=tot_rel, nbit=nbit)
         L.check(self.lib.ch_cand_hist(self.ws, C.byref(a), self._stream()), "ch_cand_hist")
 
+    def cand_rank(self, cand, *, q_bits, g_bits, q_lab, g_lab, label_mode, mask_words, nq, nq_pad, nstripes, nbins, nbit,
+                  cols, r_eff=(), pr_k=(), rmax=-1, need=0, status=None, bad=None, g_plane=None, q_nz=None, g_nz=None):
+        """``cand_hist`` + ``scan_bases_pair`` + ``cand_finalize`` (mode 0) of a single rank in ONE kernel"""
+        r_eff, pr_k = list(r_eff), list(pr_k)
+        if len(r_eff) > L.CH_MAX_R or len(pr_k) > L.CH_MAX_PR:
+            raise ValueError(f"at most {L.CH_MAX_R} R values and {L.CH_MAX_PR} PRs cut-offs are supported")
+        a = self._cand_args(cand, nq, nq_pad, nstripes, nbins, 0, g_plane=g_plane, q_bits=q_bits, g_bits=g_bits,
+                            q_nz=q_nz, g_nz=g_nz, q_lab=q_lab, g_lab=g_lab, label_mode=label_mode,
+                            mask_words=mask_words, nbit=nbit, mode=0, cols=cols, nR=len(r_eff), nPR=len(pr_k))
+        for i, v in enumerate(r_eff):
+            a.r_eff[i] = int(v)
+        for i, v in enumerate(pr_k):
+            a.pr_k[i] = int(v)
+        L.check(self.lib.ch_cand_rank(self.ws, C.byref(a), int(rmax), int(need), _ptr(status), _ptr(bad),
+                                      self._stream()), "ch_cand_rank")
+
     def cand_finalize(self, cand, *, mode, base0_all, base0_rel, nq, nq_pad, nstripes, nbins, remove_first=False,
                       first_rel=None, first_rel_out=None, cols=None, r_eff=(), pr_k=(), ids=None, keys=None, R=0,
                       row_offset=0, key_max=None):

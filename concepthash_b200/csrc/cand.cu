@@ -110,13 +110,10 @@ __global__ void gather_plane_kernel(const uint32_t* __restrict__ bits, const uin
   out[i] = w < W ? bits[r * W + w] : (w == W ? ids[r] : 0u);
 }
 
+// keys + label matches of the candidates of query q (one warp): cand_key / the relevance bit of cand_rows are written,
+// the key histograms {all, relevant} are left in shared memory (h_rel = h_all + nbins).  Returns "some key >= nbins".
 template <int W>
-__global__ void __launch_bounds__(kCandWarps * 32) cand_hist_kernel(const CandDev a) {
-  extern __shared__ uint32_t sh[];
-  const int wip = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long q = static_cast<long long>(blockIdx.x) * kCandWarps + wip;
-  if (q >= a.nq) return;                       // whole warps leave; only __syncwarp below
-  uint32_t* h_all = sh + static_cast<size_t>(wip) * 2 * a.nbins;
+__device__ __forceinline__ bool cand_hist_body(const CandDev& a, long long q, int lane, uint32_t* h_all) {
   uint32_t* h_rel = h_all + a.nbins;
   for (int b = lane; b < 2 * a.nbins; b += 32) h_all[b] = 0u;
   uint32_t qw[W], qz[W];
@@ -192,6 +189,18 @@ __global__ void __launch_bounds__(kCandWarps * 32) cand_hist_kernel(const CandDe
     }
   }
   __syncwarp();
+  return bad;
+}
+
+template <int W>
+__global__ void __launch_bounds__(kCandWarps * 32) cand_hist_kernel(const CandDev a) {
+  extern __shared__ uint32_t sh[];
+  const int wip = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long q = static_cast<long long>(blockIdx.x) * kCandWarps + wip;
+  if (q >= a.nq) return;                       // whole warps leave; only __syncwarp below
+  uint32_t* h_all = sh + static_cast<size_t>(wip) * 2 * a.nbins;
+  uint32_t* h_rel = h_all + a.nbins;
+  const bool bad = cand_hist_body<W>(a, q, lane, h_all);
   // accumulated: the caller zero-initialises the totals and may histogram a list in several calls (row blocks of
   // a streamed gallery); one warp owns a query, calls are stream-ordered -> no atomics
   for (int b = lane; b < a.nbins; b += 32) {
@@ -200,6 +209,7 @@ __global__ void __launch_bounds__(kCandWarps * 32) cand_hist_kernel(const CandDe
   }
   if (bad) atomicOr(a.err_flag, 2u);
 }
+
 
 // 1 / x for x = 1 .. 2^32: MUFU.RCP64H seed + two Newton steps (relative error < 2^-52; the AP sums only need
 // ~1e-12, a correctly rounded division costs ~40 instructions per relevant candidate)
@@ -211,17 +221,11 @@ __device__ __forceinline__ double fast_rcp(double x) {
   return r;
 }
 
-__global__ void __launch_bounds__(kCandWarps * 32) cand_final_kernel(const CandDev a) {
-  extern __shared__ uint32_t sh[];
-  const int wip = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long q = static_cast<long long>(blockIdx.x) * kCandWarps + wip;
-  if (q >= a.nq) return;
-  uint32_t* run_all = sh + static_cast<size_t>(wip) * 2 * a.nbins;
+// the in-order walk of query q's candidate list (one warp): run_all / run_rel (shared memory, run_rel = run_all + nbins)
+// hold the bases on entry; qrow = 128 words of shared memory for the compaction queue
+__device__ __forceinline__ void cand_final_body(const CandDev& a, long long q, int lane, uint32_t* run_all,
+                                                uint32_t* qrow, uint32_t kmax) {
   uint32_t* run_rel = run_all + a.nbins;
-  for (int b = lane; b < a.nbins; b += 32) {
-    run_all[b] = a.base0_all[static_cast<size_t>(b) * a.nq_pad + q];
-    run_rel[b] = a.base0_rel != nullptr ? a.base0_rel[static_cast<size_t>(b) * a.nq_pad + q] : 0u;
-  }
   const int ncols = 2 * a.nR + a.nPR;
   double acc[2 * CH_MAX_R + CH_MAX_PR];
   if (a.mode == 0)
@@ -232,8 +236,6 @@ __global__ void __launch_bounds__(kCandWarps * 32) cand_final_kernel(const CandD
   // Only candidates with key <= kmax[q] (the smallest key at which the list holds rmax items) can rank below rmax:
   // the others are dropped while the list is read, the survivors are compacted (in order) through a small
   // shared-memory queue and ranked 32 at a time.
-  const uint32_t kmax = a.key_max != nullptr ? a.key_max[q] : 0xfffffffeu;
-  uint32_t* qrow = sh + static_cast<size_t>(kCandWarps) * 2 * a.nbins + static_cast<size_t>(wip) * 128;
   uint32_t* qkey = qrow + 64;
   uint32_t queued = 0;                                            // warp-uniform
   // ranks the candidates held by the lanes (key == 0xffffffff: none) -- one step of the in-order walk
@@ -338,6 +340,76 @@ __global__ void __launch_bounds__(kCandWarps * 32) cand_final_kernel(const CandD
       if (lane == 0) a.cols[q * ncols + c] = v;
     }
   }
+}
+
+__global__ void __launch_bounds__(kCandWarps * 32) cand_final_kernel(const CandDev a) {
+  extern __shared__ uint32_t sh[];
+  const int wip = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long q = static_cast<long long>(blockIdx.x) * kCandWarps + wip;
+  if (q >= a.nq) return;
+  uint32_t* run_all = sh + static_cast<size_t>(wip) * 2 * a.nbins;
+  uint32_t* run_rel = run_all + a.nbins;
+  for (int b = lane; b < a.nbins; b += 32) {
+    run_all[b] = a.base0_all[static_cast<size_t>(b) * a.nq_pad + q];
+    run_rel[b] = a.base0_rel != nullptr ? a.base0_rel[static_cast<size_t>(b) * a.nq_pad + q] : 0u;
+  }
+  const uint32_t kmax = a.key_max != nullptr ? a.key_max[q] : 0xfffffffeu;
+  cand_final_body(a, q, lane, run_all, sh + static_cast<size_t>(kCandWarps) * 2 * a.nbins + static_cast<size_t>(wip) * 128,
+                  kmax);
+}
+
+// ch_cand_hist + ch_scan_bases_pair + ch_cand_finalize (mode 0) of ONE rank in one kernel: a warp histograms the keys
+// of its query's candidates, turns the histogram into the bases by a shared-memory scan (the totals of a single rank
+// need no exchange), verifies the list (>= need candidates, else bad[q] / status) and walks it.  The two phases have
+// complementary bounds -- random L2 gathers vs. a serial, issue-bound walk -- and the warps of an SM are in
+// different phases at any moment, so the kernel takes about as long as the slower phase alone.
+template <int W>
+__global__ void __launch_bounds__(kCandWarps * 32) cand_rank_kernel(const CandDev a, long long rmax, long long need,
+                                                                    uint32_t* __restrict__ status,
+                                                                    uint32_t* __restrict__ bad_q) {
+  extern __shared__ uint32_t sh[];
+  const int wip = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long q = static_cast<long long>(blockIdx.x) * kCandWarps + wip;
+  if (q >= a.nq) return;
+  uint32_t* h_all = sh + static_cast<size_t>(wip) * 2 * a.nbins;
+  uint32_t* h_rel = h_all + a.nbins;
+  if (cand_hist_body<W>(a, q, lane, h_all)) atomicOr(a.err_flag, 2u);
+  // histogram -> exclusive bases, 32 keys at a time; kmax = the smallest key at which the list holds rmax items
+  uint32_t carry_a = 0u, carry_r = 0u, kmax = static_cast<uint32_t>(a.nbins - 1);
+  bool found = false;
+  for (int b0 = 0; b0 < a.nbins; b0 += 32) {
+    const int b = b0 + lane;
+    const uint32_t va = b < a.nbins ? h_all[b] : 0u, vr = b < a.nbins ? h_rel[b] : 0u;
+    uint32_t ia = va, ir = vr;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t ta = __shfl_up_sync(0xffffffffu, ia, o), tr = __shfl_up_sync(0xffffffffu, ir, o);
+      if (lane >= o) {
+        ia += ta;
+        ir += tr;
+      }
+    }
+    __syncwarp();
+    if (b < a.nbins) {
+      h_all[b] = carry_a + ia - va;
+      h_rel[b] = carry_r + ir - vr;
+    }
+    const uint32_t hit = __ballot_sync(0xffffffffu, b < a.nbins && rmax >= 0 &&
+                                                         static_cast<long long>(carry_a + ia) >= rmax);
+    if (!found && hit != 0u) {
+      kmax = static_cast<uint32_t>(b0 + __ffs(static_cast<int>(hit)) - 1);
+      found = true;
+    }
+    carry_a += __shfl_sync(0xffffffffu, ia, 31);
+    carry_r += __shfl_sync(0xffffffffu, ir, 31);
+  }
+  __syncwarp();
+  if (need > 0 && static_cast<long long>(carry_a) < need && lane == 0) {
+    if (bad_q != nullptr) bad_q[q] = 1u;
+    if (status != nullptr) atomicOr(status, 1u);
+  }
+  cand_final_body(a, q, lane, h_all, sh + static_cast<size_t>(kCandWarps) * 2 * a.nbins + static_cast<size_t>(wip) * 128,
+                  kmax);
 }
 
 // capacities of the full pass from a candidate list of the ROW SAMPLE (rows = sample row indices):
@@ -468,6 +540,35 @@ extern "C" int ch_cand_hist(ch_ws* ws, const ch_cand_args* a, void* stream) {
     case 2: cand_hist_kernel<2><<<blocks, kCandWarps * 32, smem, st>>>(d); break;
     case 4: cand_hist_kernel<4><<<blocks, kCandWarps * 32, smem, st>>>(d); break;
     default: cand_hist_kernel<8><<<blocks, kCandWarps * 32, smem, st>>>(d); break;
+  }
+  CH_LAUNCH_CHECK(ws);
+  return 0;
+}
+
+extern "C" int ch_cand_rank(ch_ws* ws, const ch_cand_args* a, int64_t rmax, int64_t need, uint32_t* status_dev,
+                            uint32_t* bad_dev, void* stream) {
+  if (ws == nullptr) CH_FAIL("null workspace");
+  CandDev d;
+  if (to_dev(a, &d)) return 1;
+  if (a->q_bits == nullptr || a->g_bits == nullptr || a->err_flag == nullptr || a->cols == nullptr)
+    CH_FAIL("null argument to ch_cand_rank");
+  if (a->label_mode != CH_LAB_NONE && (a->q_lab == nullptr || a->g_lab == nullptr)) CH_FAIL("labels missing");
+  if (a->mode != 0 || a->remove_first) CH_FAIL("ch_cand_rank computes the AP sums (mode 0) without remove_first");
+  if (need > 0 && status_dev == nullptr) CH_FAIL("verification needs a status word");
+  const int words = ch_code_words(a->nbit);
+  if (words == 0) CH_FAIL("nbit=%d unsupported", a->nbit);
+  ChDeviceGuard guard(ws->device);
+  d.tot_all = d.tot_rel = nullptr;
+  d.base0_all = d.base0_rel = nullptr;
+  d.key_max = nullptr;
+  const unsigned blocks = static_cast<unsigned>((a->nq + kCandWarps - 1) / kCandWarps);
+  const size_t smem = static_cast<size_t>(kCandWarps) * (2 * a->nbins + 128) * sizeof(uint32_t);   // counters + queue
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (words) {
+    case 1: cand_rank_kernel<1><<<blocks, kCandWarps * 32, smem, st>>>(d, rmax, need, status_dev, bad_dev); break;
+    case 2: cand_rank_kernel<2><<<blocks, kCandWarps * 32, smem, st>>>(d, rmax, need, status_dev, bad_dev); break;
+    case 4: cand_rank_kernel<4><<<blocks, kCandWarps * 32, smem, st>>>(d, rmax, need, status_dev, bad_dev); break;
+    default: cand_rank_kernel<8><<<blocks, kCandWarps * 32, smem, st>>>(d, rmax, need, status_dev, bad_dev); break;
   }
   CH_LAUNCH_CHECK(ws);
   return 0;

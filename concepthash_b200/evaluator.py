@@ -159,6 +159,7 @@ class Evaluator:
         self.epilogue_thresholds = True    # sparse select passes: threshold comparison in the epilogue (see _bare)
         self.paired_rows = True            # select pass: two gallery rows per accumulator cell where keys fit (see _pair)
         self.debug_counts = False          # dev tools: stats["candidates"] = length of all candidate lists (costs a sync)
+        self.fused_rank = True             # one rank: candidate histogram + bases + walk in one kernel (ch_cand_rank)
         self.stripe_cut = True             # sampled thresholds refined to (key, stripe) pairs (see _sample_thresholds_tc)
         self.select_dense_override = None  # tests: force the dense / sparse epilogue of the tensor-core kernel
         self.col_sub = None                # zero_mean_eval: f64[nbit] column offset of the current evaluation
@@ -474,8 +475,10 @@ class Evaluator:
             self.stats["select_threshold"] = "epilogue" if bare else "contraction"
             self.stats["select_rows_per_cell"] = 2 if pair else 1
 
-    def _cand_hist(self, c, cand, nbins, tot, stripe0=0, nstripes=None):
-        """keys + label matches of the candidates of a block of stripes, accumulated into ``tot`` (2, nbins, nq_pad)"""
+    def _cand_hist(self, c, cand, nbins, tot, stripe0=0, nstripes=None, rank=None):
+        """keys + label matches of the candidates of a block of stripes, accumulated into ``tot`` (2, nbins, nq_pad);
+        ``rank`` (single rank, whole list): the fused kernel instead -- histogram, bases, verification and the walk
+        in one launch (``ch_cand_rank``), ``rank`` = its cols / r_eff / pr_k / rmax / need / status / bad"""
         b, q, g = self.b, c["q"], c["g"]
         threads, nq_pad, nstripes_all, rps = c["geo"]
         label_mode, lw = c["label_mode"], c["lw"]
@@ -495,6 +498,11 @@ class Evaluator:
                 r1 = min(g.bits.shape[0], (stripe0 + nstripes) * rps)
                 b.gather_plane(g.bits[r0:r1], g.ids[r0:r1], g.nbit, out=g.plane[r0:r1])
             kw = dict(g_plane=g.plane)
+        if rank is not None:
+            self._timed("cand_rank", 0, lambda: b.cand_rank(
+                cand, q_bits=q.bits, g_bits=g.bits, q_lab=lab(q), g_lab=lab(g), label_mode=label_mode, mask_words=lw,
+                nq=c["nq"], nq_pad=nq_pad, nstripes=nstripes_all, nbins=nbins, nbit=q.nbit, **rank, **kw))
+            return
         self._timed("cand_hist", 0, lambda: b.cand_hist(
             cand, q_bits=q.bits, g_bits=g.bits, q_lab=lab(q), g_lab=lab(g), label_mode=label_mode, mask_words=lw,
             tot_all=tot[0], tot_rel=tot[1] if label_mode != L.CH_LAB_NONE else None, nq=c["nq"], nq_pad=nq_pad,
@@ -803,15 +811,21 @@ class Evaluator:
         if "cand" in st:
             # candidate lists (tensor-core select pass): ranks straight from the lists
             cand, nbins = st["cand"], st["nbins"]
-            kw = dict(base0_all=st["base0_all"], base0_rel=st["base0_rel"], nq=nq, nq_pad=nq_pad, nstripes=nstripes,
-                      nbins=nbins, remove_first=bool(rf), key_max=st.get("key_max"))
             first_rel = None
-            if rf:
-                first_rel = b.zeros((nq_pad,), torch.int32)
-                b.cand_finalize(cand, mode=1, first_rel_out=first_rel, **kw)
-                first_rel = comm.all_reduce_max(first_rel)
-            self._timed("cand_finalize", 0, lambda: b.cand_finalize(cand, mode=0, first_rel=first_rel, cols=cols,
-                                                                    r_eff=r_eff, pr_k=pr_k, **kw))
+            if st.get("fused"):
+                f = st["fused"]
+                self._cand_hist(c, cand, nbins, None, rank=dict(
+                    cols=cols, r_eff=r_eff, pr_k=pr_k, rmax=f["rmax"], need=f["need"],
+                    status=self._status[ST_SHORT:ST_SHORT + 1], bad=f["bad"]))
+            else:
+                kw = dict(base0_all=st["base0_all"], base0_rel=st["base0_rel"], nq=nq, nq_pad=nq_pad, nstripes=nstripes,
+                          nbins=nbins, remove_first=bool(rf), key_max=st.get("key_max"))
+                if rf:
+                    first_rel = b.zeros((nq_pad,), torch.int32)
+                    b.cand_finalize(cand, mode=1, first_rel_out=first_rel, **kw)
+                    first_rel = comm.all_reduce_max(first_rel)
+                self._timed("cand_finalize", 0, lambda: b.cand_finalize(cand, mode=0, first_rel=first_rel, cols=cols,
+                                                                        r_eff=r_eff, pr_k=pr_k, **kw))
             cols = comm.all_reduce_sum(cols)
             status = cand["status"]
             if comm.world > 1:
@@ -1139,6 +1153,11 @@ class Evaluator:
             else:
                 self._select_tc(q, g, geo, thresh, cand, dense, bad=bad, scut=scut)
             self.stats["sample"]["stripe_cut"] = scut is not None
+            if (self.fused_rank and comm.world == 1 and not streamed and not c["rf"] and hasattr(b, "cand_rank")):
+                # a single rank needs no exchange of the key totals: keys, bases, verification and the in-order
+                # walk of every list happen in ONE kernel, launched by _finish (which owns the result columns)
+                return dict(cand=cand, fused=dict(rmax=c["rmax"] + c["rf"], need=need, bad=bad), nbins=nbins,
+                            total_rel=self._total_rel_from_classes(c, cls), bad=bad)
             base0_all, base0_rel, key_max = self._cand_bases(c, cand, nbins, need, tot, rmax=c["rmax"] + c["rf"],
                                                              bad=bad)
             return dict(cand=cand, base0_all=base0_all, base0_rel=base0_rel, nbins=nbins, key_max=key_max,

@@ -273,6 +273,13 @@ int ch_gather_plane_words(int nbit);
 int ch_gather_plane(ch_ws* ws, const uint32_t* bits_dev, const uint32_t* ids_dev, int64_t rows, int nbit,
                     uint32_t* out_dev, void* stream);
 int ch_cand_finalize(ch_ws* ws, const ch_cand_args* a, void* stream);
+/* ch_cand_hist + ch_scan_bases_pair + ch_cand_finalize (mode 0, no remove_first) of a SINGLE rank in one kernel: a warp
+ * histograms the keys of its query's candidates (cand_key and the relevance bits are written as by ch_cand_hist), scans
+ * the histogram into the bases in shared memory, verifies the list -- fewer than `need` candidates: bad[q] = 1,
+ * status |= 1 -- and walks it (candidates beyond the key at which the list holds `rmax` items are skipped).
+ * tot_*, base0_*, key_max of the arguments are not used; cols (nq, 2 nR + nPR) as in ch_cand_finalize. */
+int ch_cand_rank(ch_ws* ws, const ch_cand_args* a, int64_t rmax, int64_t need, uint32_t* status_dev, uint32_t* bad_dev,
+                 void* stream);
 /* Two-level threshold sampling: the candidate list (list_stripes slices per query, rows = SAMPLE row indices, keys
  * already written by ch_cand_hist) came from a select pass over a 1-in-`sample_stride` row sample.
  * cap[s][q] = sample_stride * (k + 6 sqrt(k + 1) + 9), k = #sample candidates of query q with key <= thresh[q]

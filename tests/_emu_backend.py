@@ -312,6 +312,23 @@ class EmuBackend:
         bound = (raw + np.float32(6.0) * np.sqrt(raw + np.float32(1.0)) + np.float32(9.0)) * np.float32(sample_stride)
         c[:, :nq] = bound[:, :nq].astype(np.uint32)
 
+    def cand_rank(self, cand, *, q_bits, g_bits, q_lab, g_lab, label_mode, mask_words, nq, nq_pad, nstripes, nbins, nbit,
+                  cols, r_eff=(), pr_k=(), rmax=-1, need=0, status=None, bad=None, g_plane=None, q_nz=None, g_nz=None):
+        """the fused kernel = the three steps it replaces, on one rank"""
+        tot = torch.zeros((1, 2, nbins, nq_pad), dtype=torch.int32)
+        self.cand_hist(cand, q_bits=q_bits, g_bits=g_bits, q_lab=q_lab, g_lab=g_lab, label_mode=label_mode,
+                       mask_words=mask_words, tot_all=tot[0, 0], tot_rel=tot[0, 1] if label_mode != CH_LAB_NONE else None,
+                       nq=nq, nq_pad=nq_pad, nstripes=nstripes, nbins=nbins, nbit=nbit, g_plane=g_plane, q_nz=q_nz,
+                       g_nz=g_nz)
+        base_all = torch.zeros((nbins, nq_pad), dtype=torch.int32)
+        base_rel = torch.zeros((nbins, nq_pad), dtype=torch.int32)
+        key_max = torch.zeros((nq_pad,), dtype=torch.int32)
+        self.scan_bases_pair(tot, 1, 0, nbins, nq, nq_pad, rmax, need, base_all, base_rel, key_max, None, status,
+                             **({} if bad is None else dict(bad=bad)))
+        self.cand_finalize(cand, mode=0, base0_all=base_all, base0_rel=base_rel, nq=nq, nq_pad=nq_pad,
+                           nstripes=nstripes, nbins=nbins, cols=cols, r_eff=r_eff, pr_k=pr_k, key_max=key_max)
+        self.launches -= 2
+
     def cand_finalize(self, cand, *, mode, base0_all, base0_rel, nq, nq_pad, nstripes, nbins, remove_first=False,
                       first_rel=None, first_rel_out=None, cols=None, r_eff=(), pr_k=(), ids=None, keys=None, R=0,
                       row_offset=0, key_max=None):
