@@ -106,6 +106,8 @@ SIGNATURES = {
     "ch_first_relevant": (C.c_int, [P, C.POINTER(FinalArgs), P, P]),
     "ch_reduce_means": (C.c_int, [P, P, P, P, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), P,
                                   C.POINTER(C.c_double), P, C.POINTER(C.c_uint32), C.c_int, P]),
+    "ch_reduce_means_enqueue": (C.c_int, [P, P, P, P, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), P, P, C.c_int, P]),
+    "ch_reduce_means_fetch": (C.c_int, [P, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_uint32), C.c_int, P]),
     "ch_scatter_ranked": (C.c_int, [P, C.POINTER(FinalArgs), C.c_int64, C.c_int64, P, P, P]),
     "ch_ap_from_ranked": (C.c_int, [P, P, C.c_int64, C.c_int64, P, P, C.c_int, C.c_int, C.c_int,
                                     C.POINTER(C.c_int64), P, P]),

@@ -42,6 +42,9 @@ class CudaBackend:
         L.check(self.lib.ch_device_info(self.ws, C.byref(sm), C.byref(smem), C.byref(l2), C.byref(khz)))
         self.sm_count, self.max_smem, self.l2_bytes, self.clock_khz = sm.value, smem.value, l2.value, khz.value
         self.tc_queries_per_cta = int(self.lib.ch_tc_queries_per_cta())
+        self.capture_results = None      # set while an evaluation is captured into a CUDA graph (see reduce_means)
+        self.last_results = None
+        self.last_result_shape = (0, 0, 0)
 
     def __del__(self):
         try:
@@ -452,14 +455,28 @@ class CudaBackend:
 
     def reduce_means(self, cols, total_rel, first_rel, nq, n_r, pr_k, ap_out=None, flags=None):
         """-> (mAPs, recalls, precisions, status words); ``flags`` (the u32 status block on the device) rides on
-        the same host sync."""
+        the same host sync.  While an evaluation is being CAPTURED into a CUDA graph (``capture_results`` set) the
+        reduction and its copies are only enqueued, and the values of the evaluation that ran just before on the same
+        inputs are returned -- the replayed graph's own values are read by ``fetch_results``."""
         n_pr = len(pr_k)
-        out = (C.c_double * max(1, n_r + 2 * n_pr))()
         nfl = int(flags.numel()) if flags is not None else 0
-        fl = (C.c_uint32 * max(2, nfl))()
         prk = (C.c_int64 * max(1, n_pr))(*[int(k) for k in pr_k])
-        L.check(self.lib.ch_reduce_means(self.ws, _ptr(cols), _ptr(total_rel), _ptr(first_rel), nq, n_r, n_pr, prk,
-                                         _ptr(ap_out), out, _ptr(flags), fl, nfl, self._stream()), "ch_reduce_means")
+        L.check(self.lib.ch_reduce_means_enqueue(self.ws, _ptr(cols), _ptr(total_rel), _ptr(first_rel), nq, n_r, n_pr,
+                                                 prk, _ptr(ap_out), _ptr(flags), nfl, self._stream()),
+                "ch_reduce_means")
+        self.last_result_shape = (n_r, n_pr, nfl)
+        if self.capture_results is not None:
+            return self.capture_results
+        self.last_results = self.fetch_results()
+        return self.last_results
+
+    def fetch_results(self):
+        """waits for the stream and reads the result words of the last ``reduce_means`` (or graph replay)"""
+        n_r, n_pr, nfl = self.last_result_shape
+        out = (C.c_double * max(1, n_r + 2 * n_pr))()
+        fl = (C.c_uint32 * max(2, nfl))()
+        L.check(self.lib.ch_reduce_means_fetch(self.ws, out, n_r + 2 * n_pr, fl, nfl, self._stream()),
+                "ch_reduce_means_fetch")
         vals = [float(out[i]) for i in range(n_r + 2 * n_pr)]
         return vals[:n_r], vals[n_r:n_r + n_pr], vals[n_r + n_pr:], [int(fl[i]) for i in range(max(2, nfl))]
 

@@ -6,6 +6,8 @@
 
 #include "common.cuh"
 
+#include <vector>
+
 static thread_local char g_err[1024] = "";
 
 void ch_set_error(const char* fmt, ...) {
@@ -19,13 +21,16 @@ struct ch_ws_priv {
   ch_ws pub;
   void* scratch;
   size_t scratch_bytes;
+  std::vector<void*> retired;   // outgrown scratch buffers: kept until destroy (a captured CUDA graph may still name them)
+  void* res_dev;                // results of ch_reduce_means_enqueue: device words and their pinned host mirror
+  void* res_host;
 };
 
 // grow-only device scratch shared by the small helper kernels (all calls are stream-ordered by the caller)
 int ch_ws_scratch(ch_ws* ws, size_t bytes, void** out) {
   ch_ws_priv* p = reinterpret_cast<ch_ws_priv*>(ws);
   if (bytes > p->scratch_bytes) {
-    if (p->scratch) CH_CUDA(cudaFree(p->scratch));  // cudaFree waits for outstanding work
+    if (p->scratch) p->retired.push_back(p->scratch);
     p->scratch = nullptr;
     p->scratch_bytes = 0;
     const size_t want = ch_round_up(static_cast<int64_t>(bytes), 1 << 20);
@@ -33,6 +38,16 @@ int ch_ws_scratch(ch_ws* ws, size_t bytes, void** out) {
     p->scratch_bytes = want;
   }
   *out = p->scratch;
+  return 0;
+}
+
+// 1 KB of device words + a pinned host mirror for the results of an evaluation (allocated on first use)
+int ch_ws_results(ch_ws* ws, void** dev, void** host) {
+  ch_ws_priv* p = reinterpret_cast<ch_ws_priv*>(ws);
+  if (p->res_dev == nullptr) CH_CUDA(cudaMalloc(&p->res_dev, 1024));
+  if (p->res_host == nullptr) CH_CUDA(cudaHostAlloc(&p->res_host, 1024, cudaHostAllocDefault));
+  *dev = p->res_dev;
+  *host = p->res_host;
   return 0;
 }
 
@@ -51,8 +66,7 @@ extern "C" int ch_workspace_create(int device, ch_ws** out) {
     CH_FAIL("concepthash_b200 is built for sm_100a only; device %d is sm_%d%d (%s)", device, prop.major, prop.minor,
             prop.name);
   ChDeviceGuard guard(device);
-  ch_ws_priv* p = new ch_ws_priv();
-  memset(p, 0, sizeof(*p));
+  ch_ws_priv* p = new ch_ws_priv();   // value-initialised: every plain member is zero
   ch_ws* ws = &p->pub;
   ws->device = device;
   ws->sm_count = prop.multiProcessorCount;
@@ -112,6 +126,9 @@ extern "C" int ch_workspace_destroy(ch_ws* ws) {
   }
   cudaStreamDestroy(ws->copy_stream);
   if (p->scratch) cudaFree(p->scratch);
+  for (void* r : p->retired) cudaFree(r);
+  if (p->res_dev) cudaFree(p->res_dev);
+  if (p->res_host) cudaFreeHost(p->res_host);
   delete p;
   return 0;
 }

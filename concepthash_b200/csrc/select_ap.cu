@@ -416,11 +416,15 @@ __device__ double block_sum_1024(double v, double* sh) {
   return r;
 }
 
+struct PrK {
+  long long k[CH_MAX_PR];   // by value in the kernel parameters: nothing to copy, nothing a captured graph could lose
+};
+
 // out[0..nR) = mAP_i, out[nR..nR+nPR) = recall@k, out[nR+nPR..nR+2nPR) = precision@k
 __global__ void __launch_bounds__(1024) reduce_means_kernel(const double* __restrict__ cols,
                                                             const uint32_t* __restrict__ total_rel,
                                                             const uint32_t* __restrict__ first_rel, long long nq,
-                                                            int nR, int nPR, const long long* __restrict__ pr_k,
+                                                            int nR, int nPR, const PrK pr_k,
                                                             double* __restrict__ ap_out, double* __restrict__ out) {
   __shared__ double sh[1024];
   const int ncols = 2 * nR + nPR;
@@ -439,7 +443,7 @@ __global__ void __launch_bounds__(1024) reduce_means_kernel(const double* __rest
       v = c[2 * nR + j] / (tr > 1.0 ? tr : 1.0);
     } else {
       const int j = which - nR - nPR;
-      v = c[2 * nR + j] / static_cast<double>(pr_k[j]);
+      v = c[2 * nR + j] / static_cast<double>(pr_k.k[j]);
     }
     s += v;
   }
@@ -711,36 +715,61 @@ extern "C" int ch_check_counts(ch_ws* ws, const uint32_t* total_dev, int64_t nq,
   return 0;
 }
 
+int ch_ws_results(ch_ws* ws, void** dev, void** host);  // api.cu
+
+// The means and the status block are written to the workspace's result words and copied to their pinned host mirror,
+// all on `stream` and without waiting: the sequence can be captured in a CUDA graph.  ch_reduce_means_fetch waits for
+// the stream and hands the values out.  Result layout: doubles [0, nR + 2 nPR), then u32 flags from byte 512.
+extern "C" int ch_reduce_means_enqueue(ch_ws* ws, const double* cols_dev, const uint32_t* total_rel_dev,
+                                       const uint32_t* first_rel_dev, int64_t nq, int nR, int nPR, const int64_t* pr_k,
+                                       double* ap_out_dev, const uint32_t* flags_dev, int nflags, void* stream) {
+  if (ws == nullptr || cols_dev == nullptr) CH_FAIL("null argument to ch_reduce_means");
+  if (nR < 0 || nR > CH_MAX_R || nPR < 0 || nPR > CH_MAX_PR) CH_FAIL("too many R / PRs entries");
+  if (nflags < 0 || nflags > 128) CH_FAIL("at most 128 status words");
+  const int nout = nR + 2 * nPR;
+  ChDeviceGuard guard(ws->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  void *dev = nullptr, *host = nullptr;
+  if (ch_ws_results(ws, &dev, &host)) return 1;
+  // the caller's status block (overflow / verification flags, packing statistics, slot totals) rides on the same
+  // host sync
+  if (flags_dev != nullptr && nflags > 0)
+    CH_CUDA(cudaMemcpyAsync(static_cast<char*>(host) + 512, flags_dev, static_cast<size_t>(nflags) * 4,
+                            cudaMemcpyDeviceToHost, st));
+  if (nout == 0) return 0;
+  PrK prk;
+  for (int i = 0; i < CH_MAX_PR; ++i) prk.k[i] = i < nPR ? pr_k[i] : 1;
+  double* out_dev = static_cast<double*>(dev);
+  reduce_means_kernel<<<nout, 1024, 0, st>>>(cols_dev, total_rel_dev, first_rel_dev, nq, nR, nPR, prk, ap_out_dev,
+                                             out_dev);
+  CH_LAUNCH_CHECK(ws);
+  CH_CUDA(cudaMemcpyAsync(host, out_dev, static_cast<size_t>(nout) * 8, cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+extern "C" int ch_reduce_means_fetch(ch_ws* ws, double* out_host, int nout, uint32_t* flags_host, int nflags,
+                                     void* stream) {
+  if (ws == nullptr) CH_FAIL("null workspace");
+  if (nout < 0 || nout > CH_MAX_R + 2 * CH_MAX_PR || nflags < 0 || nflags > 128) CH_FAIL("bad result counts");
+  ChDeviceGuard guard(ws->device);
+  void *dev = nullptr, *host = nullptr;
+  if (ch_ws_results(ws, &dev, &host)) return 1;
+  CH_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  if (out_host != nullptr && nout > 0) memcpy(out_host, host, static_cast<size_t>(nout) * 8);
+  if (flags_host != nullptr && nflags > 0) memcpy(flags_host, static_cast<char*>(host) + 512, static_cast<size_t>(nflags) * 4);
+  return 0;
+}
+
 extern "C" int ch_reduce_means(ch_ws* ws, const double* cols_dev, const uint32_t* total_rel_dev,
                                const uint32_t* first_rel_dev, int64_t nq, int nR, int nPR, const int64_t* pr_k,
                                double* ap_out_dev, double* out_host, const uint32_t* flags_dev, uint32_t* flags_host,
                                int nflags, void* stream) {
-  if (ws == nullptr || cols_dev == nullptr || out_host == nullptr) CH_FAIL("null argument to ch_reduce_means");
-  if (nR < 0 || nR > CH_MAX_R || nPR < 0 || nPR > CH_MAX_PR) CH_FAIL("too many R / PRs entries");
-  const int nout = nR + 2 * nPR;
-  ChDeviceGuard guard(ws->device);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // the caller's status block (overflow / verification flags, packing statistics, slot totals) rides on the same
-  // host sync
-  if (flags_dev != nullptr && flags_host != nullptr && nflags > 0)
-    CH_CUDA(cudaMemcpyAsync(flags_host, flags_dev, static_cast<size_t>(nflags) * 4, cudaMemcpyDeviceToHost, st));
-  if (nout == 0) {
-    CH_CUDA(cudaStreamSynchronize(st));
-    return 0;
-  }
-  void* scratch = nullptr;
-  if (ch_ws_scratch(ws, (CH_MAX_PR + CH_MAX_R + 2 * CH_MAX_PR) * 8, &scratch)) return 1;
-  long long* prk_dev = static_cast<long long*>(scratch);
-  double* out_dev = reinterpret_cast<double*>(prk_dev + CH_MAX_PR);
-  long long prk_host[CH_MAX_PR];
-  for (int i = 0; i < CH_MAX_PR; ++i) prk_host[i] = i < nPR ? pr_k[i] : 1;
-  CH_CUDA(cudaMemcpyAsync(prk_dev, prk_host, sizeof(prk_host), cudaMemcpyHostToDevice, st));
-  reduce_means_kernel<<<nout, 1024, 0, st>>>(cols_dev, total_rel_dev, first_rel_dev, nq, nR, nPR, prk_dev, ap_out_dev,
-                                             out_dev);
-  CH_LAUNCH_CHECK(ws);
-  CH_CUDA(cudaMemcpyAsync(out_host, out_dev, static_cast<size_t>(nout) * 8, cudaMemcpyDeviceToHost, st));
-  CH_CUDA(cudaStreamSynchronize(st));
-  return 0;
+  if (out_host == nullptr) CH_FAIL("null argument to ch_reduce_means");
+  if (ch_reduce_means_enqueue(ws, cols_dev, total_rel_dev, first_rel_dev, nq, nR, nPR, pr_k, ap_out_dev, flags_dev,
+                              flags_host != nullptr ? nflags : 0, stream))
+    return 1;
+  return ch_reduce_means_fetch(ws, out_host, nR + 2 * nPR, flags_host, flags_host != nullptr && flags_dev != nullptr ? nflags : 0,
+                               stream);
 }
 
 extern "C" int ch_scatter_ranked(ch_ws* ws, const ch_final_args* a, int64_t R, int64_t row_offset, int64_t* ids_dev,

@@ -159,6 +159,15 @@ class Evaluator:
         self.epilogue_thresholds = True    # sparse select passes: threshold comparison in the epilogue (see _bare)
         self.paired_rows = True            # select pass: two gallery rows per accumulator cell where keys fit (see _pair)
         self.debug_counts = False          # dev tools: stats["candidates"] = length of all candidate lists (costs a sync)
+        # Small evaluations are bound by the host (15-30 launches of 3-50 us kernels behind ~0.4 ms of Python): the
+        # speculative launch sequence of a shape -- fixed once its hint exists -- is captured into a CUDA graph and
+        # replayed with ONE launch.  Inputs are copied into the graph's own buffers first (that is why only small
+        # inputs qualify), the status block is checked after the replay exactly as after a speculative run, and any
+        # contradiction falls back to the ordinary path.
+        self.use_graphs = True
+        self.graph_max_bytes = 96 << 20
+        self._graphs = {}
+        self.graph_launches = 0            # kernels launched through graph replays (they bypass the C-side counter)
         self.fused_rank = True             # one rank: candidate histogram + bases + walk in one kernel (ch_cand_rank)
         self.stripe_cut = True             # sampled thresholds refined to (key, stripe) pairs (see _sample_thresholds_tc)
         self.select_dense_override = None  # tests: force the dense / sparse epilogue of the tensor-core kernel
@@ -561,6 +570,14 @@ class Evaluator:
             have = b.full((1,), 0 if hint is None else 1, torch.int32)
             if self._host_ints(comm.all_reduce_max(-have))[0] != -1:
                 hint = None
+        graphable = self._graphable(args, hint, _raw)
+        if graphable:
+            ge = self._graphs.get(key)
+            if ge is not None and ge.get("graph") is not None:
+                out = self._replay(ge, args)
+                if out is not None:
+                    return out
+                ge["graph"] = None           # contradicted: the ordinary path decides (and may re-capture)
         try:
             out = self._evaluate(*args, hint=hint)
             if out is _RETRY:
@@ -576,7 +593,79 @@ class Evaluator:
         if self.speculate and self._new_hint is not None and self._new_hint.get("complete"):
             self._hints[key] = self._new_hint
         self.stats["host_syncs"] = self.host_syncs
+        if graphable and self.stats.get("speculation") == "hit":
+            self._capture(key, args)
         return out
+
+    # ------------------------------------------------------------------ CUDA graphs of small evaluations
+    def _graphable(self, args, hint, raw):
+        db_codes, db_labels, q_codes, q_labels, r_list, threshold, pr_k, rf, return_ap, zero_mean = args
+        if not (self.use_graphs and self.speculate and hint is not None and self.comm.world == 1 and not raw
+                and not return_ap and not zero_mean and not self.profile and hasattr(self.b, "capture_results")):
+            return False
+        total = 0
+        for t in (db_codes, db_labels, q_codes, q_labels):
+            if not (isinstance(t, torch.Tensor) and t.is_cuda and t.is_contiguous()):
+                return False
+            total += t.numel() * t.element_size()
+        return total <= self.graph_max_bytes
+
+    def _capture(self, key, args):
+        """Right after a successful speculative evaluation: the same evaluation once more, on copies of the inputs,
+        recorded instead of executed.  The host-side decisions of the recording run are made on the results of the
+        evaluation that has just finished -- same data, same hint: the same road."""
+        ge = self._graphs.setdefault(key, dict(graph=None, tries=0))
+        st = self.stats
+        if ge["tries"] >= 2 or st.get("query_chunks") or (st.get("sample") or {}).get("fallback") or \
+                (st.get("sample") or {}).get("repaired_queries"):
+            return
+        ge["tries"] += 1
+        b = self.b
+        db_codes, db_labels, q_codes, q_labels, r_list, threshold, pr_k, rf, return_ap, zero_mean = args
+        static = [t.clone() for t in (db_codes, db_labels, q_codes, q_labels)]
+        saved = (dict(self.stats), self.host_syncs, self._hint, self._new_hint)
+        graph = torch.cuda.CUDAGraph()
+        ok = False
+        l0 = b.launch_count()
+        try:
+            torch.cuda.synchronize()
+            b.capture_results = b.last_results
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                b.begin()
+                out = self._evaluate(static[0], static[1], static[2], static[3], r_list, threshold, pr_k, rf,
+                                     return_ap, zero_mean, hint=self._hints.get(key))
+            ok = out is not _RETRY and out is not None
+        except Exception as e:                  # (a host round trip inside the sequence, an allocation the capture
+            self.stats_graph_error = repr(e)    #  cannot hold, ...: this shape simply keeps the ordinary path)
+            ge["tries"] = 99
+        finally:
+            b.capture_results = None
+            b.begin()
+        launches = b.launch_count() - l0
+        stats = dict(self.stats)
+        self.stats, self.host_syncs, self._hint, self._new_hint = saved
+        if ok:
+            ge.update(graph=graph, static=static, shape=b.last_result_shape, stats=stats, launches=launches,
+                      hint=self._hints.get(key))
+        else:
+            torch.cuda.synchronize()
+
+    def _replay(self, ge, args):
+        b = self.b
+        for s, t in zip(ge["static"], args[:4]):
+            s.copy_(t)
+        ge["graph"].replay()
+        b.last_result_shape = ge["shape"]
+        maps, recalls, precisions, flags = b.fetch_results()
+        self.host_syncs = 1
+        self._hint = ge["hint"]
+        # what a speculative run checks after its one round trip: a contradicted hint, an overflow, a short list
+        if self._hint is None or self._stale(flags) or flags[ST_PASS] or flags[ST_SHORT]:
+            return None
+        self.graph_launches += ge["launches"]
+        self.stats = dict(ge["stats"])
+        self.stats.update(speculation="graph", host_syncs=1)
+        return maps, recalls, precisions
 
     def _hint_key(self, db_codes, db_labels, q_codes, q_labels, r_list, threshold, pr_k, rf, return_ap, zero_mean):
         def sig(t):
@@ -588,7 +677,8 @@ class Evaluator:
         knobs = (self.sample_stride, self.sample_two_level, self.sample2_sub, self.sample2_min_rows,
                  self.sample2_min_work, self.sample_min_rows, self.sample_min_ratio, self.stream_host_gallery,
                  self.stream_min_rows, self.stream_chunks, self.use_tensor_cores, self.select_dense_override,
-                 self.stripe_rows_override, self.epilogue_thresholds, self.max_slots)
+                 self.stripe_rows_override, self.epilogue_thresholds, self.max_slots, self.paired_rows,
+                 self.stripe_cut, self.fused_rank)
         return (sig(db_codes), sig(db_labels), sig(q_codes), sig(q_labels), tuple(r_list), float(threshold),
                 tuple(pr_k), bool(rf), bool(zero_mean), self.comm.world, knobs)
 

@@ -391,6 +391,13 @@ int ch_reduce_means(ch_ws* ws, const double* cols_dev, const uint32_t* total_rel
                     double* ap_out_dev /* (nR, nq) or NULL */, double* out_host,
                     const uint32_t* flags_dev /* u32[nflags] or NULL */, uint32_t* flags_host /* same sync */,
                     int nflags, void* stream);
+/* the same in two halves: _enqueue launches the reduction and the copies into the workspace's pinned result words on
+ * `stream` without waiting (capturable in a CUDA graph; at most 128 status words), _fetch waits for the stream and hands
+ * the values out */
+int ch_reduce_means_enqueue(ch_ws* ws, const double* cols_dev, const uint32_t* total_rel_dev,
+                            const uint32_t* first_rel_dev, int64_t nq, int nR, int nPR, const int64_t* pr_k,
+                            double* ap_out_dev, const uint32_t* flags_dev, int nflags, void* stream);
+int ch_reduce_means_fetch(ch_ws* ws, double* out_host, int nout, uint32_t* flags_host, int nflags, void* stream);
 /* flags_dev[0] |= 1 if some total_dev[q] < need  (verification of a sampled threshold) */
 int ch_check_counts(ch_ws* ws, const uint32_t* total_dev, int64_t nq, int64_t need, uint32_t* flags_dev,
                     void* stream);

@@ -424,7 +424,44 @@ def test_speculative_reevaluation_on_gpu(H):
             assert np.allclose(out[3][0][sub].cpu().numpy(), oaps[0], atol=TOL), (nq, seed, ev.stats)
         assert runs[1][1]["speculation"] == "hit" and runs[1][1]["host_syncs"] == 1, runs[1][1]
         assert _same(runs[0][0], runs[1][0])
-        assert runs[2][1]["speculation"] in ("hit", "retried") and runs[3][1]["speculation"] in ("hit", "retried")
+        assert all(r[1]["speculation"] in ("hit", "retried", "graph") for r in runs[2:])
+
+
+def test_cuda_graph_replay_of_small_evaluations(H):
+    """Third and later evaluations of a small shape are ONE graph launch: same numbers as the eager path on new data
+    of the same shape, in every mode; data that contradicts what the graph assumed (an exact zero -> ternary keys; a
+    gallery whose order defeats the sample) is noticed on the device and re-evaluated by the ordinary path."""
+    ev = H.get_evaluator()
+    assert ev.use_graphs
+    for nq, ndb, nbit, ncls, R in [(700, 9000, 32, 20, -1), (3000, 200_000, 64, 50, 100), (900, 40_000, 128, 30, 500),
+                                   (5794, 5994, 64, 200, -1)]:
+        ev._hints.clear()
+        ev._graphs.clear()
+        seen = []
+        for seed in (1, 2, 3, 4, 5):
+            d, dl, q, ql, _ = synth.make_random_case(nq, ndb, nbit, ncls, p=0.30, seed=seed, device="cuda")
+            out = ev.evaluate(d, dl, q, ql, [R], 0.0, [1, 10], False)
+            seen.append(ev.stats["speculation"])
+            ev.use_graphs = False
+            try:
+                ref = ev.evaluate(d, dl, q, ql, [R], 0.0, [1, 10], False)
+                assert ev.stats["speculation"] != "graph"
+            finally:
+                ev.use_graphs = True
+            assert out == ref, (nq, seed, out, ref)
+        assert seen[0] == "none" and "graph" in seen[2:], seen
+        sub = slice(0, 24)
+        om, orec, oprec = mo.calculate_mAP(d.cpu(), dl.cpu(), q[sub].cpu(), ql[sub].cpu(), R, PRs=[1, 10])
+        m, rec, prec = H.calculate_mAP(d, dl, q[sub], ql[sub], R, PRs=[1, 10])
+        assert abs(m - om) < TOL and np.allclose(rec, orec, atol=TOL) and np.allclose(prec, oprec, atol=TOL)
+        # an exact zero in the codes: the graph's status block says "ternary keys" -> ordinary path, right answer
+        dz = d.clone()
+        dz[7, 3] = 0.0
+        out = ev.evaluate(dz, dl, q, ql, [R], 0.0, [1, 10], False)
+        assert ev.stats["ternary"] and ev.stats["speculation"] != "graph", ev.stats
+        om, orec, oprec = mo.calculate_mAP(dz.cpu(), dl.cpu(), q[sub].cpu(), ql[sub].cpu(), R, PRs=[1, 10])
+        m, rec, prec = H.calculate_mAP(dz, dl, q[sub], ql[sub], R, PRs=[1, 10])
+        assert abs(m - om) < TOL
 
 
 def test_query_chunking_on_gpu(H):
