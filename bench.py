@@ -294,7 +294,7 @@ def measure(ctx, name, nbit, steps, warmup, *, main, e2e=True, cpu=True):
     # brackets its kernels with events, as it does in the loop above.  For them the timed region is run a second time
     # without the brackets: that loop gives ms_per_step, the bracketed one the per-kernel times.
     graph_info = None
-    if getattr(ev, "use_graphs", False) and world == 1:
+    if getattr(ev, "use_graphs", False) and (world == 1 or getattr(ev, "graph_multi_gpu", False)):
         ms_g, out_g, launches_g, clocks_g, _ = run(step_dev, steps, warmup, sample_clocks=True, profile=False)
         if ev.stats.get("speculation") == "graph":
             assert out_g[0] == out[0], (out_g, out)

@@ -166,6 +166,7 @@ class Evaluator:
         # contradiction falls back to the ordinary path.
         self.use_graphs = True
         self.graph_max_bytes = 96 << 20
+        self.graph_multi_gpu = True        # NCCL collectives are captured with the kernels (every rank replays or none)
         self._graphs = {}
         self.graph_launches = 0            # kernels launched through graph replays (they bypass the C-side counter)
         self.fused_rank = True             # one rank: candidate histogram + bases + walk in one kernel (ch_cand_rank)
@@ -564,20 +565,24 @@ class Evaluator:
                 zero_mean)
         key = self._hint_key(*args)
         hint = self._hints.get(key) if self.speculate else None
-        if comm.world > 1 and self.speculate:
-            # every rank must take the same road (the collectives differ): speculate only if ALL ranks hold a hint.
-            # (The stream is idle here -- the previous evaluation ended with a sync -- so this round trip is cheap.)
-            have = b.full((1,), 0 if hint is None else 1, torch.int32)
-            if self._host_ints(comm.all_reduce_max(-have))[0] != -1:
-                hint = None
         graphable = self._graphable(args, hint, _raw)
-        if graphable:
-            ge = self._graphs.get(key)
-            if ge is not None and ge.get("graph") is not None:
-                out = self._replay(ge, args)
-                if out is not None:
-                    return out
-                ge["graph"] = None           # contradicted: the ordinary path decides (and may re-capture)
+        ge = self._graphs.get(key) if graphable else None
+        replay = ge is not None and ge.get("graph") is not None
+        if comm.world > 1 and self.speculate:
+            # every rank must take the same road (the collectives differ): speculate only if ALL ranks hold a hint,
+            # replay a captured graph only if ALL ranks hold one.  (The stream is idle here -- the previous evaluation
+            # ended with a sync -- so this round trip is cheap.)
+            have = b.full((1,), 2 if replay else (0 if hint is None else 1), torch.int32)
+            level = -self._host_ints(comm.all_reduce_max(-have))[0]
+            if level < 1:
+                hint = None
+            replay = replay and level == 2
+            graphable = graphable and hint is not None
+        if replay:
+            out = self._replay(ge, args)
+            if out is not None:
+                return out
+            ge["graph"] = None               # contradicted: the ordinary path decides (and may re-capture)
         try:
             out = self._evaluate(*args, hint=hint)
             if out is _RETRY:
@@ -600,7 +605,8 @@ class Evaluator:
     # ------------------------------------------------------------------ CUDA graphs of small evaluations
     def _graphable(self, args, hint, raw):
         db_codes, db_labels, q_codes, q_labels, r_list, threshold, pr_k, rf, return_ap, zero_mean = args
-        if not (self.use_graphs and self.speculate and hint is not None and self.comm.world == 1 and not raw
+        if not (self.use_graphs and self.speculate and hint is not None and not raw
+                and (self.comm.world == 1 or self.graph_multi_gpu)
                 and not return_ap and not zero_mean and not self.profile and hasattr(self.b, "capture_results")):
             return False
         total = 0
@@ -657,14 +663,14 @@ class Evaluator:
         ge["graph"].replay()
         b.last_result_shape = ge["shape"]
         maps, recalls, precisions, flags = b.fetch_results()
-        self.host_syncs = 1
+        self.host_syncs = 1 if self.comm.world == 1 else 2
         self._hint = ge["hint"]
         # what a speculative run checks after its one round trip: a contradicted hint, an overflow, a short list
         if self._hint is None or self._stale(flags) or flags[ST_PASS] or flags[ST_SHORT]:
             return None
         self.graph_launches += ge["launches"]
         self.stats = dict(ge["stats"])
-        self.stats.update(speculation="graph", host_syncs=1)
+        self.stats.update(speculation="graph", host_syncs=self.host_syncs)
         return maps, recalls, precisions
 
     def _hint_key(self, db_codes, db_labels, q_codes, q_labels, r_list, threshold, pr_k, rf, return_ap, zero_mean):
