@@ -582,11 +582,24 @@ def main():
     ev = hashing.get_evaluator(device, group)
     if args.sample_stride:
         ev.sample_stride = args.sample_stride
+    if world > 1 and os.environ.get("CH_GRAPH_MULTI_GPU", "1") == "1":
+        # small per-rank problems (cfg4 over 8 GPUs): the launch sequence incl. its NCCL collectives is replayed from a
+        # CUDA graph; the graphs are released before the process group goes away (evaluator.release_graphs)
+        ev.graph_multi_gpu = True
     peaks, peak_src = measured_peaks()
     popc_peak, _ = ev.b.popc_peak()
     ctx = dict(rank=rank, world=world, device=device, group=group, ev=ev, peaks=peaks, peak_src=peak_src,
                popc_peak=popc_peak, threshold=args.threshold)
 
+    try:
+        return _measure_all(args, ctx, ev, rank, world, wl)
+    finally:
+        ev.release_graphs()
+        if world > 1:
+            torch.distributed.destroy_process_group()
+
+
+def _measure_all(args, ctx, ev, rank, world, wl):
     line, ok_all = measure(ctx, args.workload, args.nbit, args.steps, args.warmup, main=True,
                            e2e=not args.no_e2e, cpu=not args.no_cpu_baseline)
     others = []
@@ -605,8 +618,6 @@ def main():
         line["other_workloads"] = others
         line["parity_ok"] = ok_all
         print(json.dumps(line))
-    if world > 1:
-        torch.distributed.destroy_process_group()
     if not ok_all:
         if rank == 0:
             print("PARITY CHECK FAILED (see parity_check in the JSON line)", file=sys.stderr)

@@ -16,6 +16,8 @@ calls.  ``tests/`` substitute a numpy emulation of the backend to exercise this 
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib as L
@@ -166,7 +168,10 @@ class Evaluator:
         # contradiction falls back to the ordinary path.
         self.use_graphs = True
         self.graph_max_bytes = 96 << 20
-        self.graph_multi_gpu = True        # NCCL collectives are captured with the kernels (every rank replays or none)
+        # Group mode: the NCCL collectives are captured with the kernels (every rank replays or none does -- agreed in
+        # the hint round trip).  Opt-in: a process group must not be destroyed while a graph that holds its collectives
+        # is alive (the teardown hung when tried) -- call release_graphs() first, as bench.py does.
+        self.graph_multi_gpu = os.environ.get("CH_GRAPH_MULTI_GPU", "0") == "1"
         self._graphs = {}
         self.graph_launches = 0            # kernels launched through graph replays (they bypass the C-side counter)
         self.fused_rank = True             # one rank: candidate histogram + bases + walk in one kernel (ch_cand_rank)
@@ -279,9 +284,11 @@ class Evaluator:
                             info=st[ST_GINFO:ST_GINFO + 4], defer_codes=defer)
         if self.comm.world > 1:
             # ranks must agree: everything by MAX (each rank fills only its own slot of the row counts)
-            st[ST_ROWS + self.comm.rank] = g.n
+            # (fill_: the value travels as a kernel argument -- an indexed assignment of a Python int is a pageable
+            # host-to-device copy, which a CUDA graph cannot record)
+            st[ST_ROWS + self.comm.rank:ST_ROWS + self.comm.rank + 1].fill_(g.n)
             if g.bits is not None:
-                st[ST_PACKED] = 1
+                st[ST_PACKED:ST_PACKED + 1].fill_(1)
         if self._hint is not None:
             mm, rows, any_packed = self._hint["mm"], self._hint["rows"], self._hint["any_packed"]
         else:
@@ -603,6 +610,12 @@ class Evaluator:
         return out
 
     # ------------------------------------------------------------------ CUDA graphs of small evaluations
+    def release_graphs(self):
+        """drops every captured graph (and its buffers); required before ``destroy_process_group`` in group mode"""
+        self._graphs.clear()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+
     def _graphable(self, args, hint, raw):
         db_codes, db_labels, q_codes, q_labels, r_list, threshold, pr_k, rf, return_ap, zero_mean = args
         if not (self.use_graphs and self.speculate and hint is not None and not raw
