@@ -483,6 +483,8 @@ def measure(ctx, name, nbit, steps, warmup, *, main, e2e=True, cpu=True):
     if rank == 0:
         print(f"[{name}/{w['nbit']}] evaluator stats:", stats, file=sys.stderr)
     del d, dl, q, ql
+    if hasattr(ev, "release_graphs"):
+        ev.release_graphs()                  # (a captured graph owns its arenas: give them back before the next workload)
     torch.cuda.empty_cache()
     if main:
         return {

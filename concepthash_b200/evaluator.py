@@ -167,7 +167,8 @@ class Evaluator:
         # inputs qualify), the status block is checked after the replay exactly as after a speculative run, and any
         # contradiction falls back to the ordinary path.
         self.use_graphs = True
-        self.graph_max_bytes = 96 << 20
+        self.graph_max_bytes = 96 << 20      # inputs up to this size are copied into graph-owned buffers
+        self.graph_in_place = True           # larger ones: captured in place, replayed for the same addresses only
         # Group mode: the NCCL collectives are captured with the kernels (every rank replays or none does -- agreed in
         # the hint round trip).  Opt-in: a process group must not be destroyed while a graph that holds its collectives
         # is alive (the teardown hung when tried) -- call release_graphs() first, as bench.py does.
@@ -575,6 +576,8 @@ class Evaluator:
         graphable = self._graphable(args, hint, _raw)
         ge = self._graphs.get(key) if graphable else None
         replay = ge is not None and ge.get("graph") is not None
+        if replay and ge.get("ptrs") is not None and ge["ptrs"] != tuple(t.data_ptr() for t in args[:4]):
+            replay, ge = False, None         # captured in place, for other buffers: ordinary path, graph kept
         if comm.world > 1 and self.speculate:
             # every rank must take the same road (the collectives differ): speculate only if ALL ranks hold a hint,
             # replay a captured graph only if ALL ranks hold one.  (The stream is idle here -- the previous evaluation
@@ -622,12 +625,16 @@ class Evaluator:
                 and (self.comm.world == 1 or self.graph_multi_gpu)
                 and not return_ap and not zero_mean and not self.profile and hasattr(self.b, "capture_results")):
             return False
-        total = 0
         for t in (db_codes, db_labels, q_codes, q_labels):
             if not (isinstance(t, torch.Tensor) and t.is_cuda and t.is_contiguous()):
                 return False
-            total += t.numel() * t.element_size()
-        return total <= self.graph_max_bytes
+        return True
+
+    def _graph_in_place(self, args):
+        """inputs too large to copy into graph-owned buffers are captured IN PLACE: such a graph is replayed only for
+        calls that pass tensors at the very same addresses (a re-evaluation of the same buffers, or buffers the
+        caching allocator handed out again) -- the memory read is always that of the current call's tensors"""
+        return sum(t.numel() * t.element_size() for t in args[:4]) > self.graph_max_bytes
 
     def _capture(self, key, args):
         """Right after a successful speculative evaluation: the same evaluation once more, on copies of the inputs,
@@ -641,7 +648,12 @@ class Evaluator:
         ge["tries"] += 1
         b = self.b
         db_codes, db_labels, q_codes, q_labels, r_list, threshold, pr_k, rf, return_ap, zero_mean = args
-        static = [t.clone() for t in (db_codes, db_labels, q_codes, q_labels)]
+        in_place = self._graph_in_place(args)
+        if in_place and not self.graph_in_place:
+            return
+        if ge.get("graph") is not None:
+            return                           # (an in-place graph of other buffers exists: keep it)
+        static = list(args[:4]) if in_place else [t.clone() for t in (db_codes, db_labels, q_codes, q_labels)]
         saved = (dict(self.stats), self.host_syncs, self._hint, self._new_hint)
         graph = torch.cuda.CUDAGraph()
         ok = False
@@ -664,15 +676,17 @@ class Evaluator:
         stats = dict(self.stats)
         self.stats, self.host_syncs, self._hint, self._new_hint = saved
         if ok:
-            ge.update(graph=graph, static=static, shape=b.last_result_shape, stats=stats, launches=launches,
-                      hint=self._hints.get(key))
+            ge.update(graph=graph, static=None if in_place else static, shape=b.last_result_shape, stats=stats,
+                      launches=launches, hint=self._hints.get(key),
+                      ptrs=tuple(t.data_ptr() for t in args[:4]) if in_place else None)
         else:
             torch.cuda.synchronize()
 
     def _replay(self, ge, args):
         b = self.b
-        for s, t in zip(ge["static"], args[:4]):
-            s.copy_(t)
+        if ge["static"] is not None:
+            for s, t in zip(ge["static"], args[:4]):
+                s.copy_(t)
         ge["graph"].replay()
         b.last_result_shape = ge["shape"]
         maps, recalls, precisions, flags = b.fetch_results()
