@@ -54,8 +54,13 @@ def _as_tensor(x):
 
 def calculate_mAP(db_codes, db_labels, test_codes, test_labels, R, threshold=0., dist_metric="hamming",
                   PRs=None, multiclass=False, landmark_gt=None, db_id=None, test_id=None,
-                  remove_first_retrieved=False, group=None, zero_mean_eval=False, **_ignored):
+                  remove_first_retrieved=False, group=None, zero_mean_eval=False, empty_queries="zero", **_ignored):
     """mAP@R (+ R@k, P@k for ``PRs``) of a Hamming ranking on sign-binarised codes.
+
+    ``empty_queries`` (not in the reference signature) names the convention for a query whose list holds NO relevant
+    item: ``"zero"`` (default; the OrthoHash-lineage ``APx.append(0)``) scores it AP = 0 and keeps it in the mean,
+    ``"skip"`` (DeepHash-lineage ``if rel != 0: APx.append(...)``) leaves it out of the mean (mAP = 0 if every query is
+    empty).  The upstream function is not in the reference tree, so the choice is the caller's.
 
     ``zero_mean_eval=True`` (not in the reference signature) fuses the callers' preprocessing
     ``db_mean = db.mean(0); db -= db_mean; test -= db_mean`` (experiments/train_helper.py:223-226,
@@ -68,6 +73,9 @@ def calculate_mAP(db_codes, db_labels, test_codes, test_labels, R, threshold=0.,
     With ``group`` (a torch.distributed process group) ``db_*`` is this rank's contiguous gallery block.
     """
     _check_common(dist_metric, landmark_gt, db_id, test_id)
+    if empty_queries not in ("zero", "skip"):
+        raise ValueError(f"empty_queries={empty_queries!r}: 'zero' or 'skip'")
+    skip = empty_queries == "skip"
     db_codes, db_labels, test_codes, test_labels = map(_as_tensor, (db_codes, db_labels, test_codes, test_labels))
     r_is_list = isinstance(R, (list, tuple)) or (hasattr(R, "__iter__") and not isinstance(R, (str, bytes)))
     r_list = [int(r) for r in R] if r_is_list else [int(R)]
@@ -81,8 +89,15 @@ def calculate_mAP(db_codes, db_labels, test_codes, test_labels, R, threshold=0.,
         ks = pr_list[i * _lib.CH_MAX_PR:(i + 1) * _lib.CH_MAX_PR]
         if not rs and not ks:
             continue
-        m, r, p = ev.evaluate(db_codes, db_labels, test_codes, test_labels, rs, threshold, ks,
-                              bool(remove_first_retrieved), zero_mean=bool(zero_mean_eval))
+        if skip and rs:
+            # per-query AP (device, fp64) -> mean over the queries whose list holds a relevant item (AP > 0 <=> it does)
+            m, r, p, ap = ev.evaluate(db_codes, db_labels, test_codes, test_labels, rs, threshold, ks,
+                                      bool(remove_first_retrieved), return_ap=True, zero_mean=bool(zero_mean_eval))
+            hit = (ap > 0).sum(dim=1)
+            m = (ap.sum(dim=1) / hit.clamp(min=1)).tolist()
+        else:
+            m, r, p = ev.evaluate(db_codes, db_labels, test_codes, test_labels, rs, threshold, ks,
+                                  bool(remove_first_retrieved), zero_mean=bool(zero_mean_eval))
         maps += m
         recalls += r
         precisions += p

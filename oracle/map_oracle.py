@@ -150,8 +150,11 @@ def _ap_from_rel(rel_row):
 def calculate_mAP(db_codes, db_labels, test_codes, test_labels, R, threshold=0.0,
                   dist_metric="hamming", PRs=None, multiclass=False, landmark_gt=None,
                   db_id=None, test_id=None, remove_first_retrieved=False, tie="stable",
-                  return_per_query=False, **_ignored):
+                  return_per_query=False, empty_queries="zero", **_ignored):
     """Oracle for the hot path.  Gallery first, query second.
+
+    ``empty_queries``: "zero" (normative here: AP = 0, kept in the mean) or "skip" (queries without a relevant item in
+    their list are left out of the mean -- the other convention found among upstream lineages).
 
     Definition (normative):
       1. ternary zeroing iff threshold != 0, then sign;
@@ -191,7 +194,12 @@ def calculate_mAP(db_codes, db_labels, test_codes, test_labels, R, threshold=0.0
         r_eff = L if r == -1 else min(r, L)
         for i in range(nq):
             aps[ri, i] = _ap_from_rel(rel_ranked[i, :r_eff])
-    maps = [float(a.mean()) if nq else 0.0 for a in aps]
+    if empty_queries == "skip":
+        maps = [float(a[a > 0].mean()) if (a > 0).any() else 0.0 for a in aps]
+    elif empty_queries == "zero":
+        maps = [float(a.mean()) if nq else 0.0 for a in aps]
+    else:
+        raise ValueError(f"empty_queries={empty_queries!r}")
 
     cum = np.cumsum(rel_ranked.astype(np.float64), axis=1) if L else np.zeros((nq, 0))
     recalls, precisions = [], []

@@ -732,3 +732,20 @@ def test_pr_curve_matches_oracle(H):
     orec, oprec, _ = mo.calculate_pr_curve(d, dl, q, ql, Rs=cuts)
     rec, prec, rs = H.calculate_pr_curve(d.cuda(), dl.cuda(), q.cuda(), ql.cuda(), Rs=cuts)
     assert rs == cuts and np.allclose(rec, orec, atol=TOL) and np.allclose(prec, oprec, atol=TOL)
+
+
+def test_empty_queries_convention(H):
+    """`empty_queries="skip"`: queries whose list holds no relevant item are left out of the mean (the other upstream
+    lineage's convention); "zero" is the default.  Sparse labels + small R make such queries common."""
+    d, dl, q, ql, _ = synth.make_random_case(300, 4000, 32, 400, p=0.45, seed=5)
+    for R in (5, [3, 20], -1):
+        z = H.calculate_mAP(d.cuda(), dl.cuda(), q.cuda(), ql.cuda(), R, PRs=[1, 5])
+        s = H.calculate_mAP(d.cuda(), dl.cuda(), q.cuda(), ql.cuda(), R, PRs=[1, 5], empty_queries="skip")
+        oz = mo.calculate_mAP(d, dl, q, ql, R, PRs=[1, 5])
+        os_ = mo.calculate_mAP(d, dl, q, ql, R, PRs=[1, 5], empty_queries="skip")
+        assert np.allclose(z[0], oz[0], atol=TOL) and np.allclose(s[0], os_[0], atol=TOL)
+        assert np.allclose(s[1], os_[1], atol=TOL) and np.allclose(s[2], os_[2], atol=TOL)
+        if R == 5:
+            assert s[0] > z[0] + 1e-3            # (the case does hold empty lists)
+    with pytest.raises(ValueError):
+        H.calculate_mAP(d.cuda(), dl.cuda(), q.cuda(), ql.cuda(), 5, empty_queries="drop")
