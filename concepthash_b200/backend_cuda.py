@@ -130,7 +130,7 @@ class CudaBackend:
                                         t.stride(1) if nbit > 1 else 1, _ptr(out), self._stream()), "ch_column_sums")
         return out
 
-    def pack_sign(self, codes, threshold, flags, want_nz=True, out=None, col_sub=None):
+    def pack_sign(self, codes, threshold, flags, want_nz=True, out=None, col_sub=None, stream=None):
         """codes (n, nbit) real -> (bits, nz) u32 (rows_pad, words); ``flags`` u32[1] is OR-ed.
         ``want_nz=False`` skips the non-zero plane (zeros are still detected in ``flags``) and lets
         contiguous inputs take the flat fast path."""
@@ -154,7 +154,8 @@ class CudaBackend:
         rs = t.stride(0) if n > 1 else nbit
         L.check(self.lib.ch_pack_sign(self.ws, _ptr(t), mem, _DTYPES[t.dtype], n, nbit, rs,
                                       t.stride(1) if nbit > 1 else 1, thr, _ptr(col_sub), _ptr(bits), _ptr(nz),
-                                      _ptr(flags), self._stream()), "ch_pack_sign")
+                                      _ptr(flags), self._stream() if stream is None else C.c_void_p(stream.cuda_stream)),
+                "ch_pack_sign")
         return bits, nz
 
     def pack_labels(self, labels, nolabel, info=None):
@@ -199,13 +200,14 @@ class CudaBackend:
         """bytes per row of the PAIRED planes (two gallery rows per plane row); 0: this nbit has no paired form"""
         return int(self.lib.ch_tc_code_bytes_pair(int(nbit), int(bool(ternary))))
 
-    def expand_i8_into(self, bits, nbit, out, bare=False, pair=False):
+    def expand_i8_into(self, bits, nbit, out, bare=False, pair=False, stream=None):
         """gallery plane of a row block: ``bits`` (rows, words) -> ``out`` (rows, kb) views of larger arrays
         (``pair``: rows / 2 plane rows; the block starts on a multiple of 64 rows)"""
         n = int(bits.shape[0])
         assert n % (64 if pair else 32) == 0 and out.shape[0] >= (n // 2 if pair else n)
         L.check(self.lib.ch_expand_i8(self.ws, _ptr(bits), None, n, nbit, 0, 3 if pair else int(bool(bare)), _ptr(out),
-                                      n // 2 if pair else n, None, 0, self._stream()), "ch_expand_i8")
+                                      n // 2 if pair else n, None, 0,
+                                      self._stream() if stream is None else C.c_void_p(stream.cuda_stream)), "ch_expand_i8")
 
     def expand_i8(self, bits, nbit, min_rows=0, thresh=None, nq=0, nz=None, bare=False, query=False, pair=False):
         """packed sign bits (rows_pad, words) -> {-1, 0, +1} int8 plane in the tiled operand order (rows, kb) int8,

@@ -56,7 +56,7 @@ void ch_set_error(const char* fmt, ...);
       ch_set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
       return 1;                                                                            \
     }                                                                                      \
-    (ws)->launches++;                                                                      \
+    __atomic_fetch_add(&(ws)->launches, 1, __ATOMIC_RELAXED); /* (a loader thread may launch too) */                                                                     \
   } while (0)
 
 struct ChDeviceGuard {

@@ -570,6 +570,7 @@ extern "C" int ch_pack_labels(ch_ws* ws, const void* labels, int mem, int dtype,
     if (chunk_rows < 64) CH_FAIL("label row stride too large for the staging buffer");
     if (ch_ws_ensure_stage(ws)) return 1;
   }
+  bool user_buffer_in_flight = false;   // a DMA may still be reading the CALLER's memory when the loop ends
   for (int64_t r0 = 0; r0 == 0 || r0 < n; r0 += chunk_rows) {
     const int64_t r1 = (r0 + chunk_rows < n) ? r0 + chunk_rows : n;
     const bool last = r1 >= n;
@@ -590,8 +591,11 @@ extern "C" int ch_pack_labels(ch_ws* ws, const void* labels, int mem, int dtype,
           hsrc = static_cast<const char*>(ws->bounce[0]);
         }
       }
+      // (the staging buffer may still be read by a kernel of an earlier call on another stream: pack_from_host's protocol)
+      CH_CUDA(cudaStreamWaitEvent(st, ws->ev_consumed[0], 0));
       if (bytes) CH_CUDA(cudaMemcpyAsync(ws->stage[0], hsrc, bytes, cudaMemcpyHostToDevice, st));
       if (hsrc == static_cast<const char*>(ws->bounce[0])) CH_CUDA(cudaEventRecord(ws->ev_copied[0], st));
+      else if (bytes) user_buffer_in_flight = true;
       src = ws->stage[0];
     } else {
       src = static_cast<const char*>(labels);
@@ -615,9 +619,14 @@ extern "C" int ch_pack_labels(ch_ws* ws, const void* labels, int mem, int dtype,
         CH_FAIL("unsupported dtype %d for 1-D labels", dtype);
     }
     CH_LAUNCH_CHECK(ws);
+    if (mem == CH_MEM_HOST) CH_CUDA(cudaEventRecord(ws->ev_consumed[0], st));
     if (last) break;
   }
 #undef CH_ID_CASE
-  if (mem == CH_MEM_HOST) CH_CUDA(cudaStreamSynchronize(st));  // staging buffer reusable, host buffer released
+  // The caller's host buffer must be released on return.  A pageable array that went through the bounce buffer is
+  // (the pool copied it; the bounce buffer is guarded by its event, the staging buffer is reused in stream order):
+  // no wait -- the 8 MB of int64 ids of a 1M-row gallery cost 1.5 ms of host time here, a sixth of the whole
+  // evaluation.  Anything still being read by a DMA is waited for.
+  if (user_buffer_in_flight) CH_CUDA(cudaStreamSynchronize(st));
   return 0;
 }

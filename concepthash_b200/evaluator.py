@@ -157,6 +157,7 @@ class Evaluator:
         self.stream_host_gallery = True    # host-resident gallery: overlap its H2D copy with the select pass
         self.stream_min_rows = 200_000
         self.stream_chunks = 2             # blocks per wave-filling stripe group x 2 (fewer, larger blocks: ~0.15 ms of host work per block)
+        self.stream_loader_thread = True   # pageable gallery: a loader thread packs / copies the blocks back to back
         self.use_tensor_cores = True       # select pass on tcgen05 (int8 +-1 codes) when the shape allows it
         self.epilogue_thresholds = True    # sparse select passes: threshold comparison in the epilogue (see _bare)
         self.paired_rows = True            # select pass: two gallery rows per accumulator cell where keys fit (see _pair)
@@ -794,7 +795,12 @@ class Evaluator:
         res = None
         if streamed:
             self.stats["mode"] = "topR-sampled-streamed"
-            res = self._finish(ctx, self._pass_topr_sampled(ctx, streamed=True))
+            try:
+                res = self._finish(ctx, self._pass_topr_sampled(ctx, streamed=True))
+            finally:
+                streamer = ctx.pop("streamer", None)
+                if streamer is not None:
+                    streamer.join()
             if hint is not None and self._stale(res[4]):
                 return _RETRY
             if res[4][ST_PASS] or res[4][ST_SHORT]:
@@ -1120,6 +1126,12 @@ class Evaluator:
                 ev._side_stream = torch.cuda.Stream(device=g.bits.device)
             self.side = ev._side_stream
             self.pinned = bool(c["db_codes"].is_contiguous() and c["db_codes"].is_pinned())
+            # Pageable memory: every block costs ~1 ms of (GIL-free) host packing.  A loader thread runs the blocks back
+            # to back from the moment the sample has been packed, while this thread queues the sample-level passes, the
+            # select launches and the list kernels (~0.3 ms of host time per block that used to sit between two packs).
+            # (Not while the bench brackets entry points with events: the brackets are not thread-safe.)
+            self.threaded = bool(ev.stream_loader_thread and not self.pinned and not ev.profile)
+            self.thread, self.ready, self.error = None, [], None
             self.loaded = {}
             self.blocks = []
             for s0 in range(0, nstripes, per):
@@ -1138,6 +1150,15 @@ class Evaluator:
             db_codes = self.c["db_codes"]
             nrow8 = (self.rows_pad - r0) if r1 == g.n else (r1 - r0)
             blk = db_codes[r0:r1]
+            if self.thread is not None:
+                # the loader thread: explicit stream handles (the backend's cached stream belongs to the other thread)
+                b.pack_sign(blk, 0.0, self.flags, False, out=g.bits[r0:], stream=self.side)
+                b.expand_i8_into(g.bits[r0:r0 + nrow8], q.nbit, self.plane8[r0 // 2 if self.pair else r0:],
+                                 stream=self.side, **(dict(pair=True) if self.pair else dict(bare=self.bare)))
+                done = torch.cuda.Event()
+                done.record(self.side)
+                self.loaded[i] = done
+                return
             with b.on_stream(self.side):
                 if self.pinned:
                     def copy_and_pack():
@@ -1159,13 +1180,51 @@ class Evaluator:
 
         def load_first(self):
             """block 0 -- or, from pinned memory, every block -- is queued while the GPU works on the sample"""
+            if self.threaded:
+                return
             for i in range(len(self.blocks) if self.pinned else 1):
                 self.load(i)
+
+        def start(self):
+            """starts the loader thread (pageable galleries): all blocks, back to back"""
+            if not self.threaded or self.thread is not None:
+                return
+            import threading
+            self.ready = [threading.Event() for _ in self.blocks]
+            dev = self.ev.b.device
+
+            def run():
+                try:
+                    torch.cuda.set_device(dev)
+                    for i in range(len(self.blocks)):
+                        self.load(i)
+                        self.ready[i].set()
+                except BaseException as e:      # handed to the evaluating thread (select / join)
+                    self.error = e
+                finally:
+                    for r in self.ready:
+                        r.set()
+            self.thread = threading.Thread(target=run, name="ch-gallery-loader", daemon=True)
+            self.thread.start()
+
+        def join(self):
+            """the loader thread has finished (it writes into the shard's packed arrays: nothing may outlive it)"""
+            t, self.thread = self.thread, None
+            if t is not None:
+                t.join()
+            self.threaded = False
+
+        def wait_block(self, i):
+            if self.thread is not None or self.ready:
+                self.ready[i].wait()
+                if self.error is not None:
+                    raise self.error
 
         def select(self, i, cand, q_i8, dense, thresh, bad=None):
             ev, b, q, g = self.ev, self.ev.b, self.c["q"], self.c["g"]
             threads, nq_pad, nstripes, rps = self.c["geo"]
             s0, s1, r0, r1 = self.blocks[i]
+            self.wait_block(i)
             torch.cuda.current_stream().wait_event(self.loaded[i])
             kw = dict(thresh=thresh, ternary=False) if self.bare else {}
             if self.pair:
@@ -1211,6 +1270,8 @@ class Evaluator:
             sp.bits = packed.view(-1, q.bits.shape[1])         # (super rows, run * words) -> (rows, words)
             streamer = self._Streamer(self, c, zflag, self._bare(dense), self._pair(q))
             streamer.side.wait_stream(torch.cuda.current_stream())
+            c["streamer"] = streamer       # (the caller joins its loader thread whatever happens below)
+            streamer.start()
         else:
             ns, sp.bits = b.gather_rows(g.bits, g.n, g.nbit, stride)
         sp.n = ns
@@ -1230,6 +1291,15 @@ class Evaluator:
         # block 0 of a streamed gallery travels while the GPU works on the sample: its (host-blocking) copy is
         # issued right after the first sample kernels have been queued
         first_load = streamer.load_first if streamer is not None else (lambda: None)
+        # With hints for the list allocations (sites "s1" / "full") nothing below waits for the device: the (host-blocking) copy of block 0
+        # is then issued LAST, after every sample-level launch and the set-up of the full pass have been queued -- the
+        # GPU works through them while the host's cores pack the block (0.7 ms of a cfg4 evaluation).
+        late_load = False
+        if streamer is not None and self._hint is not None and hasattr(b, "record_offsets_async"):
+            sites = self._hint["sites"]
+            late_load = sites.get("full") is not None and sites.get("s1", True) is not None
+        if late_load:
+            first_load, deferred_load = (lambda: None), streamer.load_first      # (no-ops with a loader thread)
         # per-query failure marks of the candidate-list path (a slice overflowed / fewer than R candidates): the
         # evaluation then re-ranks just those queries by the exact path instead of starting over
         bad = b.zeros((nq_pad,), torch.int32) if tc_pass else None
@@ -1262,9 +1332,11 @@ class Evaluator:
                 q_i8 = self._query_plane(q, nq_pad, thresh, streamer.bare, streamer.pair,
                                          scut if streamer.pair else None, nstripes)
                 tot = b.zeros((2, nbins, nq_pad), torch.int32)
+                if late_load:
+                    deferred_load()
                 for i in range(len(streamer.blocks)):
                     streamer.select(i, cand, q_i8, dense, thresh, bad)
-                    if i + 1 < len(streamer.blocks) and (i + 1) not in streamer.loaded:
+                    if not streamer.threaded and i + 1 < len(streamer.blocks) and (i + 1) not in streamer.loaded:
                         streamer.load(i + 1)     # host waits for this copy while the GPU runs select(i)
                     # keys / label matches of this block's candidates while the next block is still travelling
                     s0, s1 = streamer.blocks[i][0], streamer.blocks[i][1]
