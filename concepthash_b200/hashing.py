@@ -187,3 +187,26 @@ def get_hamm_dist(codes, centroids, margin=0., normalize=False):
     d = keys.to(torch.float32) * (0.5 if ternary else 1.0)
     d = d / codes.shape[1] if normalize else d
     return d.to(codes.device) if isinstance(codes, torch.Tensor) and d.device != codes.device else d
+
+
+# ---- training-loss helpers of the same missing module -------------------------------------------------------------
+# Not part of the retrieval hot path: two small autograd-visible torch helpers that the reference's pairwise losses
+# import from ``utils.hashing`` (models/loss/dpsh.py:4, models/loss/hashnet.py:5, models/loss/adsh.py:5).  A drop-in
+# ``utils/hashing.py`` has to export them or those modules stop importing.  Their behaviour is pinned by the call sites.
+def get_sim(label_a, label_b, onehot=True):
+    """Boolean pairwise similarity ``(N, M)``: ``s_ij = 1`` iff samples i and j share a class.
+
+    ``onehot=True``: one-/multi-hot ``(N, C)`` / ``(M, C)`` label matrices -> ``label_a @ label_b.T >= 1`` (the
+    "share >= 1 positive class" relevance of ``calculate_mAP``); ``onehot=False``: class ids -> equality.  Callers:
+    ``get_sim(y1, y2).float()`` (models/loss/dpsh.py:58, models/loss/hashnet.py:73),
+    ``get_sim(Y.cpu(), Y_train.cpu(), onehot).float() * 2. - 1.`` (models/loss/adsh.py:26,41,65)."""
+    label_a, label_b = torch.as_tensor(label_a), torch.as_tensor(label_b)
+    if onehot:
+        return torch.matmul(label_a.float(), label_b.float().t()) >= 1
+    return label_a.reshape(-1, 1) == label_b.reshape(1, -1)
+
+
+def log_trick(dot_product):
+    """``log(1 + exp(x))`` without overflow: ``log(1 + exp(-|x|)) + max(x, 0)`` -- the expression the callers keep
+    beside the call as a comment (models/loss/dpsh.py:64, models/loss/hashnet.py:79).  Differentiable."""
+    return torch.log(1 + torch.exp(-torch.abs(dot_product))) + dot_product.clamp(min=0)

@@ -1,5 +1,7 @@
 """``utils.hashing`` -- the module the reference imports its retrieval evaluation from
-(``experiments/test_hashing.py:15``, ``experiments/train_helper.py:18``) and does not ship
+(``experiments/test_hashing.py:15``, ``experiments/train_helper.py:18``; also ``get_hamm_dist`` in
+``trainers/orthohash.py:16`` / ``trainers/dpn.py:4`` and the loss helpers ``get_sim`` / ``log_trick`` in
+``models/loss/{dpsh,hashnet,adsh}.py``) and does not ship
 (``README.md:11`` points at another repository).  This file is the binding a maintainer drops into the
 reference's ``utils/`` directory: it forwards to the B200-native implementation.
 
@@ -12,10 +14,12 @@ from concepthash_b200.hashing import (  # noqa: F401
     calculate_mAP,
     calculate_pr_curve,
     get_hamm_dist,
+    get_sim,
+    log_trick,
     map_at_r,
     pack_codes,
     retrieve_topk,
 )
 
-__all__ = ["calculate_mAP", "calculate_pr_curve", "get_hamm_dist", "map_at_r", "retrieve_topk",
+__all__ = ["calculate_mAP", "calculate_pr_curve", "get_hamm_dist", "get_sim", "log_trick", "map_at_r", "retrieve_topk",
            "PackedCodes", "evaluate_dumps", "load_packed", "save_packed", "pack_codes"]
