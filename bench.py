@@ -41,6 +41,12 @@ WORKLOADS = {
     "cfg5": dict(nq=100_000, ndb=12_500_000, nbit=64, nclass=1000, R=1000, p=0.30, scaling="weak",
                  desc="BASELINE configs[4] per-GPU shard: 64-bit, 100,000 queries x 12.5M gallery rows per GPU "
                       "(8 GPUs = the 100M gallery), top-R=1000, 1000 classes"),
+    # BASELINE.json configs[4] AS NAMED, strong-scaled: the whole 100M-row gallery (= the 8 shards of "cfg5" concatenated,
+    # so the mAP must equal the 8-GPU weak-scaled run's to the last bit) split over however many GPUs there are; on few
+    # GPUs the candidate slices exceed the 32-bit slot range and calculate_mAP chunks the queries internally
+    "cfg5full": dict(nq=100_000, ndb=12_500_000, shards=8, nbit=64, nclass=1000, R=1000, p=0.30, scaling="strong",
+                     desc="BASELINE configs[4] as named: 64-bit, 100,000 queries x 100M gallery (strong-scaled: 100M / N "
+                          "rows per GPU), top-R=1000, 1000 classes"),
     # development-size stand-in for cfg5 (same code path, 1/12.5 of the per-GPU shard)
     "cfg5s": dict(nq=100_000, ndb=1_000_000, nbit=64, nclass=1000, R=1000, p=0.30, scaling="strong",
                   desc="cfg5 stand-in: 64-bit, 100,000 queries x 1,000,000 gallery, top-R=1000, 1000 classes"),
@@ -64,6 +70,17 @@ def make_workload(name, device, nbit_override=None, shard=0):
     if "dataset" in w:
         d, dl, q, ql, ncls = synth.make_dataset_case(w["dataset"], nbit=w["nbit"], p=w["p"], seed=0, device=device)
         w.update(nq=q.shape[0], ndb=d.shape[0], nclass=ncls)
+    elif "shards" in w:
+        # the concatenation of the weak-scaled run's per-rank blocks (generated block by block into one allocation)
+        ns, per = int(w["shards"]), int(w["ndb"])
+        d = torch.empty(ns * per, w["nbit"], dtype=torch.float32, device=device)
+        dl = torch.empty(ns * per, dtype=torch.int64, device=device)
+        for sh in range(ns):
+            db, dlb, q, ql, ncls = synth.make_random_case(w["nq"], per, w["nbit"], w["nclass"], p=w["p"], seed=0,
+                                                          device=device, shard=sh)
+            d[sh * per:(sh + 1) * per], dl[sh * per:(sh + 1) * per] = db, dlb
+            del db, dlb
+        w["ndb"] = ns * per
     else:
         d, dl, q, ql, ncls = synth.make_random_case(w["nq"], w["ndb"], w["nbit"], w["nclass"], p=w["p"], seed=0,
                                                     device=device, shard=shard)
@@ -627,6 +644,8 @@ def _measure_all(args, ctx, ev, rank, world, wl):
         plan = []
         if args.workload != "cfg5":
             plan.append(("cfg5", 0, 5, 3))              # configs[4]: weak-scaled shard, at every N
+        if args.workload != "cfg5full":
+            plan.append(("cfg5full", 0, 3, 3))          # configs[4] as named: the whole 100M gallery, strong-scaled
         if world == 1:
             plan += [(n, b, 10, 3) for n, b in (("cub200", 64), ("cars196", 16), ("cars196", 32), ("cars196", 64),
                                                 ("nabirds", 64)) if not (n == args.workload and b == wl["nbit"])]
