@@ -84,6 +84,13 @@ extern "C" int ch_workspace_create(int device, ch_ws** out) {
       if (v >= 1 && v <= 64) ws->host_threads = v;
     }
     ws->pack_threads = hc >= 2 ? static_cast<int>(hc > 32 ? 32 : hc) : 1;   // read-only pass: every core helps
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) {         // one process per GPU (torchrun): the ranks share the cores
+      const int lw = atoi(e);
+      if (lw > 1 && hc >= 2) {
+        int v = static_cast<int>(hc) / lw;
+        ws->pack_threads = v < 2 ? 2 : (v > 32 ? 32 : v);
+      }
+    }
     if (const char* e = getenv("CH_PACK_THREADS")) {          // 0 = keep the bounce-copy + GPU pack path
       const int v = atoi(e);
       if (v >= 0 && v <= 128) ws->pack_threads = v;
