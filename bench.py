@@ -480,12 +480,20 @@ def measure(ctx, name, nbit, steps, warmup, *, main, e2e=True, cpu=True):
         step_host = lambda: hashing.calculate_mAP(hd, hdl, hq, hql, w["R"], threshold=thr, group=group)
         ms_e, out_e, _, _, _ = run(step_host, es, ew, profile=False)
         h2d = sum(t.numel() * t.element_size() for t in (hd, hdl, hq, hql))
+        # what crosses PCIe: fp32 codes in host memory are sign/bit-packed by the host's cores (csrc/loader.cu,
+        # host_pack.cpp) -- 1 bit per code travels, plus the row sample's bits; labels travel as they are
+        sample_rows = (ev.stats.get("sample") or {}).get("rows", 0)
+        wire = (sum(t.shape[0] for t in (hd, hq)) + sample_rows) * ((w["nbit"] + 31) // 32 * 4) + \
+            sum(t.numel() * t.element_size() for t in (hdl, hql))
         del hd, hdl, hq, hql
         e2e_obj = {"value": total_pairs * unit64 / (ms_p * 1e-3), "unit": "64-bit comparisons/s",
                    "ms_per_step": ms_p, "host_memory": "pageable (what trainers/base.py:291-304 hands over)",
                    "ms_per_step_pinned_host_tensors": ms_e,
                    "value_pinned_host_tensors": total_pairs * unit64 / (ms_e * 1e-3),
-                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8 * len(r_list) + 64,
+                   "h2d_bytes_per_step": wire, "host_input_bytes_per_step": h2d,
+                   "h2d_note": "fp32 codes are read once by the host's cores (host_input_bytes_per_step) and cross "
+                               "PCIe as packed sign bits (h2d_bytes_per_step); pageable and pinned alike",
+                   "d2h_bytes_per_step": 8 * len(r_list) + 64,
                    "mAP": out_p[0], "mAP_pinned": out_e[0], "mode": mode_p, "kernel_ms_per_step": kinds_p}
 
     if thr == 0.0:

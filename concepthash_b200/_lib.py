@@ -65,6 +65,10 @@ SIGNATURES = {
     "ch_pack_sign": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_double,
                                P, P, P, P, P]),
     "ch_host_pack_sign": (C.c_int, [P, C.c_int64, C.c_int, C.c_int64, P, P, C.c_int]),
+    "ch_host_pack_threads": (C.c_int, [P]),
+    "ch_host_loader_start": (C.c_int, [P, P, C.c_int64, C.c_int, C.c_int64, P, P, P, C.POINTER(C.c_void_p)]),
+    "ch_host_loader_wait": (C.c_int, [P, C.c_int64, P]),
+    "ch_host_loader_join": (C.c_int, [P, C.POINTER(C.c_uint32)]),
     "ch_column_sums": (C.c_int, [P, P, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int64, P, P]),
     "ch_pack_labels": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_uint32,
                                  P, P, P, P]),
@@ -143,7 +147,7 @@ def load():
             raise NativeLibraryError(f"{LIB_PATH} does not export {name}") from e
         fn.restype = res
         fn.argtypes = args
-    if lib.ch_abi_version() != 4:
+    if lib.ch_abi_version() != 5:
         raise NativeLibraryError("ABI version mismatch: rebuild the library")
     _lib = lib
     return lib

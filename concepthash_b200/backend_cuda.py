@@ -22,6 +22,37 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+class _HostLoader:
+    """Handle of a running native gallery loader (``CudaBackend.host_loader_start``).  Keeps the source tensor and the
+    destination alive until ``join``."""
+
+    def __init__(self, lib, handle, codes, bits):
+        self.lib, self.h, self.codes, self.bits = lib, handle, codes, bits
+        self.flags = None
+
+    def wait(self, rows, stream):
+        """blocks until rows [0, rows) are on their way to the device, then makes ``stream`` wait for their copy"""
+        assert self.h is not None, "loader already joined"
+        L.check(self.lib.ch_host_loader_wait(self.h, int(rows), C.c_void_p(stream.cuda_stream)), "ch_host_loader_wait")
+
+    def join(self):
+        """waits for the loader thread; returns the flag bits it found (1: a zero sign, 2: NaN).  Idempotent."""
+        if self.h is not None:
+            h, self.h = self.h, None
+            fl = C.c_uint32(0)
+            rc = self.lib.ch_host_loader_join(h, C.byref(fl))
+            self.flags = int(fl.value)
+            self.codes = None
+            L.check(rc, "ch_host_loader_join")
+        return self.flags
+
+    def __del__(self):
+        try:
+            self.join()
+        except Exception:
+            pass
+
+
 class CudaBackend:
     """One instance per process / GPU (owns a ``ch_ws`` workspace)."""
 
@@ -157,6 +188,26 @@ class CudaBackend:
                                       _ptr(flags), self._stream() if stream is None else C.c_void_p(stream.cuda_stream)),
                 "ch_pack_sign")
         return bits, nz
+
+    def host_loader_ok(self, codes):
+        """can ``host_loader_start`` take this gallery?  (a contiguous-row fp32 CPU tensor, host packing enabled)"""
+        return (isinstance(codes, torch.Tensor) and not codes.is_cuda and codes.dtype == torch.float32 and
+                codes.dim() == 2 and codes.shape[0] > 0 and self.code_words(int(codes.shape[1])) > 0 and
+                (codes.shape[1] == 1 or codes.stride(1) == 1) and
+                (codes.shape[0] == 1 or codes.stride(0) >= codes.shape[1]) and codes.data_ptr() % 4 == 0 and
+                int(self.lib.ch_host_pack_threads(self.ws)) > 0)
+
+    def host_loader_start(self, codes, bits, flags, stream):
+        """Starts the native gallery loader (csrc/loader.cu): ``codes`` (n, nbit) fp32 on the HOST are sign/bit-packed
+        by the host's cores on a thread of their own and copied chunk by chunk into ``bits`` (rows_pad, words) on
+        ``stream``.  Returns a handle: ``wait(rows, stream)`` / ``join() -> flag bits``."""
+        n, nbit = int(codes.shape[0]), int(codes.shape[1])
+        assert bits.shape[0] >= self.padded_rows(n) and bits.shape[1] == self.code_words(nbit) and bits.is_contiguous()
+        h = C.c_void_p()
+        L.check(self.lib.ch_host_loader_start(self.ws, _ptr(codes), n, nbit, codes.stride(0) if n > 1 else nbit,
+                                              _ptr(bits), _ptr(flags), C.c_void_p(stream.cuda_stream), C.byref(h)),
+                "ch_host_loader_start")
+        return _HostLoader(self.lib, h, codes, bits)
 
     def pack_labels(self, labels, nolabel, info=None):
         """labels (n, C) one-/multi-hot or (n,) ids -> (ids u32 (rows_pad), masks (rows_pad, lw) | None, info u32[4]).

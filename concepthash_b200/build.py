@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libconcepthash_b200.so")
 STAMP = LIB + ".stamp"
-SOURCES = ["api.cu", "pack.cu", "hist.cu", "select_tc.cu", "cand.cu", "select_ap.cu", "host_pack.cpp"]
+SOURCES = ["api.cu", "pack.cu", "hist.cu", "select_tc.cu", "cand.cu", "select_ap.cu", "loader.cu", "host_pack.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

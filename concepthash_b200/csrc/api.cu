@@ -24,6 +24,10 @@ struct ch_ws_priv {
   std::vector<void*> retired;   // outgrown scratch buffers: kept until destroy (a captured CUDA graph may still name them)
   void* res_dev;                // results of ch_reduce_means_enqueue: device words and their pinned host mirror
   void* res_host;
+  void* ring;                   // pinned chunk ring of the gallery loader (loader.cu) + the event behind its last copy
+  size_t ring_bytes;
+  cudaEvent_t ring_last;
+  bool ring_event;
 };
 
 // grow-only device scratch shared by the small helper kernels (all calls are stream-ordered by the caller)
@@ -48,6 +52,31 @@ int ch_ws_results(ch_ws* ws, void** dev, void** host) {
   if (p->res_host == nullptr) CH_CUDA(cudaHostAlloc(&p->res_host, 1024, cudaHostAllocDefault));
   *dev = p->res_dev;
   *host = p->res_host;
+  return 0;
+}
+
+// pinned ring of the gallery loader: grow-only, at least `bytes`; *last = the event recorded behind the last copy that
+// read the ring (never recorded at first: synchronising on it returns at once)
+int ch_ws_loader_ring(ch_ws* ws, size_t bytes, void** ring, size_t* ring_bytes, cudaEvent_t** last) {
+  ch_ws_priv* p = reinterpret_cast<ch_ws_priv*>(ws);
+  if (!p->ring_event) {
+    CH_CUDA(cudaEventCreateWithFlags(&p->ring_last, cudaEventDisableTiming));
+    p->ring_event = true;
+  }
+  if (bytes > p->ring_bytes) {
+    if (p->ring != nullptr) {
+      CH_CUDA(cudaEventSynchronize(p->ring_last));
+      CH_CUDA(cudaFreeHost(p->ring));
+      p->ring = nullptr;
+      p->ring_bytes = 0;
+    }
+    const size_t want = ch_round_up(static_cast<int64_t>(bytes), 1 << 20);
+    CH_CUDA(cudaHostAlloc(&p->ring, want, cudaHostAllocDefault));
+    p->ring_bytes = want;
+  }
+  *ring = p->ring;
+  *ring_bytes = p->ring_bytes;
+  *last = &p->ring_last;
   return 0;
 }
 
@@ -136,6 +165,8 @@ extern "C" int ch_workspace_destroy(ch_ws* ws) {
   for (void* r : p->retired) cudaFree(r);
   if (p->res_dev) cudaFree(p->res_dev);
   if (p->res_host) cudaFreeHost(p->res_host);
+  if (p->ring) cudaFreeHost(p->ring);
+  if (p->ring_event) cudaEventDestroy(p->ring_last);
   delete p;
   return 0;
 }

@@ -7,6 +7,7 @@
 // same flag bits.  CUDA tensors and pinned host tensors never come here (pack.cu: DMA + pack_sign_flat_kernel).
 #include <immintrin.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -16,15 +17,19 @@
 #include <thread>
 #include <vector>
 
+void ch_host_pool_run(int which, int n, const std::function<void(int)>& fn);
+
 namespace {
 
 // ---- a small persistent pool (a std::thread per call would cost ~20 us each, a streamed gallery makes dozens
 // of calls per evaluation) -----------------------------------------------------------------------------------
 class Pool {
  public:
-  static Pool& get() {
-    static Pool p;
-    return p;
+  // pool 0: the evaluating thread's calls; pool 1: the gallery loader (loader.cu), whose ONE run lasts for the whole
+  // gallery -- the short packs of the evaluating thread (queries, labels, the row sample) must not queue behind it
+  static Pool& get(int which = 0) {
+    static Pool p[2];
+    return p[which != 0];
   }
   // runs fn(t) for t in [0, n) on n threads (the caller is thread 0)
   void run(int n, const std::function<void(int)>& fn) {
@@ -109,6 +114,16 @@ inline uint32_t pack_row_scalar(const float* x, int k0, int ncols, uint32_t* out
   return fl;
 }
 
+// software prefetch distance (bytes ahead of the row being packed; 0 = none) and hint (0 NTA, 1 T0, 2 T2): one core's
+// read bandwidth is bounded by its outstanding misses, and the hardware prefetcher stops at 4 KB page boundaries
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+// (16 threads on the B200 host, 512 MB of codes: 151 GB/s without, 122 with NTA @ 2 KB, 190 with T0 @ 8 KB, 198 with T2 @ 8 KB)
+static const int g_pf_bytes = env_int("CH_PACK_PREFETCH", 8192);
+static const int g_pf_hint = env_int("CH_PACK_PREFETCH_HINT", 2);
+
 __attribute__((target("avx512f"))) uint32_t pack_rows_avx512(const float* src, int64_t r0, int64_t r1, int ncols,
                                                             int64_t rs, int words, uint32_t* out) {
   const __m512 zero = _mm512_setzero_ps();
@@ -118,6 +133,14 @@ __attribute__((target("avx512f"))) uint32_t pack_rows_avx512(const float* src, i
   for (int64_t r = r0; r < r1; ++r) {
     const float* x = src + r * rs;
     uint32_t* o = out + r * words;
+    if (g_pf_bytes > 0) {
+      const char* p = reinterpret_cast<const char*>(x) + g_pf_bytes;
+      for (int l = 0; l < ncols * 4; l += 64) {
+        if (g_pf_hint == 0) _mm_prefetch(p + l, _MM_HINT_NTA);
+        else if (g_pf_hint == 1) _mm_prefetch(p + l, _MM_HINT_T0);
+        else _mm_prefetch(p + l, _MM_HINT_T2);
+      }
+    }
     for (int w = 0; w < full; ++w) {
       const __m512 a = _mm512_loadu_ps(x + 32 * w), b = _mm512_loadu_ps(x + 32 * w + 16);
       const __mmask16 pa = _mm512_cmp_ps_mask(a, zero, _CMP_GT_OQ), pb = _mm512_cmp_ps_mask(b, zero, _CMP_GT_OQ);
@@ -186,7 +209,7 @@ uint32_t ch_host_pack_f32(const float* src, int64_t n, int ncols, int64_t rs, in
   int64_t piece = (256 * 1024) / (static_cast<int64_t>(ncols) * 4);
   if (piece < 16) piece = 16;
   std::atomic<int64_t> next(0);
-  Pool::get().run(nt, [&](int t) {
+  ch_host_pool_run(0, nt, [&](int t) {
     uint32_t f = 0;
     for (;;) {
       const int64_t a = next.fetch_add(piece, std::memory_order_relaxed);
@@ -198,6 +221,61 @@ uint32_t ch_host_pack_f32(const float* src, int64_t n, int ncols, int64_t rs, in
   uint32_t fl = 0;
   for (uint32_t f : flags) fl |= f;
   return fl;
+}
+
+// Calls of the evaluating thread (pool 0) are short and on the critical path of the GPU's first work; the loader's run
+// (pool 1, loader.cu) is long and holds every core.  Two pools oversubscribe the cores, and the scheduler does not
+// hand a freshly woken worker a core for milliseconds when 16 busy threads hold them (measured: a 0.18 ms query pack
+// took 3.7 ms); pausing the loader meanwhile leaves cores idle (0.4 ms of a 5.5 ms evaluation).  So while a loader
+// runs, a call of the evaluating thread is published as a JOB that the loader's threads help with between two of
+// their own pieces (<= ~30 us away): each helper takes a ticket t < nt and runs fn(t).  Every fn draws pieces from a
+// shared counter until none is left, so the caller's own fn(0) completes the job even if nobody helps.
+struct HelpJob {
+  const std::function<void(int)>* fn;
+  int nt;
+  std::atomic<int> ticket{1};
+};
+static std::atomic<HelpJob*> g_job{nullptr};
+static std::atomic<int> g_inside{0};          // helpers that may hold a pointer to the job
+static std::atomic<int> g_loaders{0};         // running loaders (they call ch_host_help between pieces)
+
+void ch_host_loader_running(int delta) { g_loaders.fetch_add(delta); }
+
+void ch_host_help() {
+  if (g_job.load(std::memory_order_acquire) == nullptr) return;
+  g_inside.fetch_add(1);
+  HelpJob* j = g_job.load();
+  if (j != nullptr) {
+    const int t = j->ticket.fetch_add(1);
+    if (t < j->nt) (*j->fn)(t);
+  }
+  g_inside.fetch_sub(1);
+}
+
+void ch_host_pool_run(int which, int n, const std::function<void(int)>& fn) {
+  if (which == 0 && n > 1 && g_loaders.load() > 0) {
+    static std::mutex one_job;
+    std::lock_guard<std::mutex> serial(one_job);
+    HelpJob job{&fn, n};
+    g_job.store(&job);
+    fn(0);
+    g_job.store(nullptr);
+    while (g_inside.load() > 0) std::this_thread::yield();    // helpers still inside fn (or about to look at the job)
+    return;
+  }
+  Pool::get(which).run(n, fn);
+}
+
+// rows [r0, r1) of `src` -> dst (r1 - r0, words) u32 on the calling thread; returns the flag bits (loader.cu)
+uint32_t ch_host_pack_rows(const float* src, int64_t r0, int64_t r1, int ncols, int64_t rs, int words, uint32_t* dst) {
+  typedef uint32_t (*fn_t)(const float*, int64_t, int64_t, int, int64_t, int, uint32_t*);
+  static const fn_t fn = [] {
+    __builtin_cpu_init();
+    if (__builtin_cpu_supports("avx512f")) return static_cast<fn_t>(pack_rows_avx512);
+    if (__builtin_cpu_supports("avx2")) return static_cast<fn_t>(pack_rows_avx2);
+    return static_cast<fn_t>(pack_rows_plain);
+  }();
+  return fn(src + r0 * rs, 0, r1 - r0, ncols, rs, words, dst);
 }
 
 // memcpy of a large pageable block into a pinned bounce buffer by the same pool (~256 KB pieces): a pageable
@@ -235,7 +313,7 @@ void ch_host_parallel_copy(void* dst, const void* src, size_t bytes, int nthread
     return;
   }
   std::atomic<size_t> next(0);
-  Pool::get().run(nt, [&](int) {
+  ch_host_pool_run(0, nt, [&](int) {
     for (;;) {
       const size_t a = next.fetch_add(piece, std::memory_order_relaxed);
       if (a >= bytes) break;

@@ -93,10 +93,12 @@ class _TooManySlots(Exception):
 
 class Packed:
     """Packed codes + labels of one side (query or gallery shard)."""
-    __slots__ = ("n", "nbit", "bits", "nz", "ids", "masks", "info", "ncls", "i8", "i8b", "i8p", "plane")
+    __slots__ = ("n", "nbit", "bits", "nz", "ids", "masks", "info", "ncls", "i8", "i8b", "i8p", "plane", "loader", "pending")
 
     def __init__(self):
         self.plane = None
+        self.pending = None      # labels not packed yet: (labels, nolabel, info) -- see Evaluator._ensure_labels
+        self.loader = None       # native gallery loader filling ``loader.bits`` (host gallery; see Evaluator._prepare)
         self.i8b = None          # int8 plane without threshold slots (comparison in the select kernel's epilogue)
         self.i8p = None          # paired int8 plane: two gallery rows per plane row
 
@@ -158,6 +160,15 @@ class Evaluator:
         self.stream_min_rows = 200_000
         self.stream_chunks = 2             # blocks per wave-filling stripe group x 2 (fewer, larger blocks: ~0.15 ms of host work per block)
         self.stream_loader_thread = True   # pageable gallery: a loader thread packs / copies the blocks back to back
+        self.stream_native_loader = True   # fp32 host gallery: packed from the first moment of the evaluation by a native
+        #                                    thread (csrc/loader.cu); the blocks of the select pass only wait for their rows
+        self.stream_chunks_native = 2      # ... blocks per wave-filling stripe group x 2 on that path (3 / 4 measured: no gain)
+        self.stream_late_labels = False    # ... labels packed behind the first select launch (measured: no gain either)
+        self.stream_cand_overlap = False   # ... list kernels beside the next block's select kernel (measured: no gain --
+        #                                    they slow the select kernel by what they save)
+        self._loader = None
+        self._side_stream = None
+        self._cand_stream = None
         self.use_tensor_cores = True       # select pass on tcgen05 (int8 +-1 codes) when the shape allows it
         self.epilogue_thresholds = True    # sparse select passes: threshold comparison in the epilogue (see _bare)
         self.paired_rows = True            # select pass: two gallery rows per accumulator cell where keys fit (see _pair)
@@ -216,7 +227,15 @@ class Evaluator:
         kw = {} if self.col_sub is None else dict(col_sub=self.col_sub)
         p.bits, p.nz = self._timed(kind, pack_bytes, lambda: self.b.pack_sign(codes, threshold, flags, want_nz, **kw))
 
-    def _pack_side(self, codes, labels, threshold, flags, nolabel, want_nz=False, info=None, defer_codes=False):
+    def _ensure_labels(self, *sides):
+        """packs the labels whose packing ``_pack_side`` put off (``defer_labels``)"""
+        for p in sides:
+            if p.pending is not None:
+                (labels, nolabel, info), p.pending = p.pending, None
+                p.ids, p.masks, p.info = self.b.pack_labels(labels, nolabel, info)
+
+    def _pack_side(self, codes, labels, threshold, flags, nolabel, want_nz=False, info=None, defer_codes=False,
+                   defer_labels=False):
         p = Packed()
         p.i8 = None
         p.n, p.nbit = int(codes.shape[0]), int(codes.shape[1])
@@ -229,7 +248,10 @@ class Evaluator:
         if labels is not None:
             if labels.shape[0] != p.n:
                 raise ValueError(f"{labels.shape[0]} label rows for {p.n} code rows")
-            p.ids, p.masks, p.info = self.b.pack_labels(labels, nolabel, info)
+            if defer_labels:
+                p.pending = (labels, nolabel, info)
+            else:
+                p.ids, p.masks, p.info = self.b.pack_labels(labels, nolabel, info)
             p.ncls = int(labels.shape[1]) if labels.dim() == 2 else 0
         return p
 
@@ -276,14 +298,37 @@ class Evaluator:
         # the rows of the other ranks are taken from the hint and verified against the block after the final sync.
         st = self._status = self.b.zeros((ST_ROWS + self.comm.world,), torch.int32)
         flags = st[ST_CODES:ST_CODES + 1]
-        q = self._pack_side(q_codes, q_labels, threshold, flags, L.CH_QUERY_NOLABEL, info=st[ST_QINFO:ST_QINFO + 4])
         # a large HOST gallery is not copied yet: the top-R path streams it in row blocks behind the select pass
         defer = (allow_defer and self.stream_host_gallery and not isinstance(db_codes, PackedCodes) and
                  not db_codes.is_cuda and threshold == 0 and
                  db_labels is not None and db_codes.shape[0] >= self.stream_min_rows and
                  hasattr(self.b, "hamming_select_tc") and self.b.tc_code_bytes(int(db_codes.shape[1])) > 0)
+        loader = None
+        if (defer and self.stream_native_loader and hasattr(self.b, "host_loader_start") and
+                self.b.host_loader_ok(db_codes)):
+            # fp32 rows in host memory (pageable or pinned): the host's cores are the bottleneck of this evaluation
+            # (they read every code once), so they start NOW, on a native thread of their own -- before the queries,
+            # the labels and the row sample are packed -- and run without a pause to the last row (csrc/loader.cu).
+            # Zeros / NaNs raise ST_SHORT (the streamed pass then falls back) and come back from join().
+            bits = self.b.empty((self.b.padded_rows(int(db_codes.shape[0])), self.b.code_words(int(db_codes.shape[1]))),
+                                torch.int32)
+            if getattr(self, "_side_stream", None) is None:
+                # (high priority: the small expansion kernels behind the copies must not queue behind the thousands of
+                # blocks of a list kernel -- measured 0.02 -> 0.34 ms each, and the next select waits for them)
+                self._side_stream = torch.cuda.Stream(device=bits.device, priority=-1)
+            self._side_stream.wait_stream(torch.cuda.current_stream())      # (the status block is zeroed on this stream)
+            loader = self._loader = self.b.host_loader_start(db_codes, bits, st[ST_SHORT:ST_SHORT + 1],
+                                                             self._side_stream)
+        # With the loader running and a hint for the label form, the labels are not on the way to the thresholds (the
+        # sample passes rank by keys alone): they are packed after those passes have been queued (0.4 ms of a 5 ms
+        # evaluation sat between the query pack and the row sample otherwise) -- _ensure_labels.
+        late = (self.stream_late_labels and loader is not None and self._hint is not None and self.comm.world == 1 and
+                max(self._hint["mm"][ST_QINFO], self._hint["mm"][ST_GINFO]) <= 1)         # (single-label form)
+        q = self._pack_side(q_codes, q_labels, threshold, flags, L.CH_QUERY_NOLABEL, info=st[ST_QINFO:ST_QINFO + 4],
+                            defer_labels=late)
         g = self._pack_side(db_codes, db_labels, threshold, flags, L.CH_GALLERY_NOLABEL,
-                            info=st[ST_GINFO:ST_GINFO + 4], defer_codes=defer)
+                            info=st[ST_GINFO:ST_GINFO + 4], defer_codes=defer, defer_labels=late)
+        g.loader = loader
         if self.comm.world > 1:
             # ranks must agree: everything by MAX (each rank fills only its own slot of the row counts)
             # (fill_: the value travels as a kernel argument -- an indexed assignment of a Python int is a pageable
@@ -302,7 +347,13 @@ class Evaluator:
             mm = mm[:ST_ROWS]
         self._new_hint.update(mm=list(mm), rows=list(rows), any_packed=any_packed)
         if self.comm.world > 1 and any_packed and g.bits is None:
-            self._pack_codes(g, db_codes, threshold, flags)      # (zeros / NaN are re-checked by the caller)
+            if g.loader is not None:
+                fl = self._loader_bits(g)
+                if fl:
+                    flags.bitwise_or_(fl)
+                    st[ST_SHORT:ST_SHORT + 1].zero_()
+            else:
+                self._pack_codes(g, db_codes, threshold, flags)      # (zeros / NaN are re-checked by the caller)
         mm = [mm[ST_CODES], 0, 0, 0] + list(mm[ST_QINFO:ST_QINFO + 4]) + list(mm[ST_GINFO:ST_GINFO + 4])
         m = [mm[0] & 1, max(mm[4], mm[8]), max(mm[5], mm[9]), (mm[0] >> 1) & 1]
         if m[3]:
@@ -712,7 +763,8 @@ class Evaluator:
                  self.sample2_min_work, self.sample_min_rows, self.sample_min_ratio, self.stream_host_gallery,
                  self.stream_min_rows, self.stream_chunks, self.use_tensor_cores, self.select_dense_override,
                  self.stripe_rows_override, self.epilogue_thresholds, self.max_slots, self.paired_rows,
-                 self.stripe_cut, self.fused_rank)
+                 self.stripe_cut, self.fused_rank, self.stream_native_loader, self.stream_chunks_native,
+                 self.stream_cand_overlap, self.stream_late_labels)
         return (sig(db_codes), sig(db_labels), sig(q_codes), sig(q_labels), tuple(r_list), float(threshold),
                 tuple(pr_k), bool(rf), bool(zero_mean), self.comm.world, knobs)
 
@@ -745,8 +797,26 @@ class Evaluator:
             return maps, recalls, precisions, torch.cat(aps, dim=1)
         return maps, recalls, precisions
 
-    def _evaluate(self, db_codes, db_labels, q_codes, q_labels, r_list, threshold, pr_k, remove_first_retrieved,
-                  return_ap, zero_mean, hint=None):
+    def _loader_bits(self, g):
+        """The gallery is not streamed after all: waits for the native loader, hands its bits to ``g`` (the current
+        stream waits for the copies) and returns the flag bits (1: a zero sign, 2: NaN)."""
+        loader, g.loader = g.loader, None
+        fl = loader.join()
+        torch.cuda.current_stream().wait_stream(self._side_stream)
+        g.bits, g.nz = loader.bits, None
+        return fl
+
+    def _evaluate(self, *args, **kw):
+        try:
+            return self._evaluate_body(*args, **kw)
+        finally:
+            # the loader thread reads the caller's memory and writes into the shard's arrays: nothing may outlive it
+            loader, self._loader = self._loader, None
+            if loader is not None:
+                loader.join()
+
+    def _evaluate_body(self, db_codes, db_labels, q_codes, q_labels, r_list, threshold, pr_k, remove_first_retrieved,
+                       return_ap, zero_mean, hint=None):
         b, comm = self.b, self.comm
         self._hint = hint
         self._new_hint = dict(sites={}, complete=False)
@@ -778,7 +848,8 @@ class Evaluator:
                     and self.use_tensor_cores)
         min_stripes = 0
         if streamed:
-            min_stripes = self._stream_per(geo[1]) * 2 * self.stream_chunks
+            min_stripes = self._stream_per(geo[1]) * 2 * (self.stream_chunks_native if g.loader is not None
+                                                          else self.stream_chunks)
         geo = self._agree_geometry(geo, g.n, stride if sampled else 1, min_stripes)
         if (not streamed and not full_ranking and not self.stripe_rows_override and hasattr(b, "sm_count")
                 and self._tc_ok(q, ternary, geo[1])):
@@ -792,6 +863,8 @@ class Evaluator:
                    nbins=nbins, rmax=rmax, rf=rf, pr_k=pr_k, ndb_total=ndb_total, stride=stride, rows=rows)
         ctx.update(r_eff=r_eff, r_list=r_list, return_ap=return_ap, db_codes=db_codes, threshold=threshold)
         streamed = streamed and nstripes >= 2
+        if not streamed:
+            self._ensure_labels(q, g)
         res = None
         if streamed:
             self.stats["mode"] = "topR-sampled-streamed"
@@ -804,16 +877,27 @@ class Evaluator:
             if hint is not None and self._stale(res[4]):
                 return _RETRY
             if res[4][ST_PASS] or res[4][ST_SHORT]:
-                res = self._repair(ctx, res, q_codes, q_labels, db_labels) if res[4][ST_CODES] == 0 else None
+                # (a zero / NaN found by the native loader is not a per-query failure: no repair, the whole evaluation
+                # is redone with ternary keys -- or raises)
+                odd = comm.world == 1 and g.loader is not None and g.loader.join() != 0
+                res = self._repair(ctx, res, q_codes, q_labels, db_labels) if res[4][ST_CODES] == 0 and not odd else None
             if res is None:
                 self.stats["sample"].update(fallback=True)
                 sampled = False                     # the same sample would fail again: go exact
                 self._status[:ST_CODES].zero_()
         if g.bits is None or res is None and streamed:
             # gallery codes were deferred but the streamed path is not applicable (or gave up): pack them now
-            fl = b.zeros((1,), torch.int32)
-            self._pack_codes(g, db_codes, threshold, fl)
-            fl = self._host_ints(comm.all_reduce_max(fl) if comm.world > 1 else fl)[0]
+            if g.loader is not None:
+                # (the native loader has packed -- or is packing -- every row: its bits are the shard's bits)
+                fl = self._loader_bits(g)
+                if comm.world > 1:
+                    flt = b.zeros((1,), torch.int32)
+                    flt.fill_(fl)
+                    fl = self._host_ints(comm.all_reduce_max(flt))[0]
+            else:
+                fl = b.zeros((1,), torch.int32)
+                self._pack_codes(g, db_codes, threshold, fl)
+                fl = self._host_ints(comm.all_reduce_max(fl) if comm.world > 1 else fl)[0]
             if fl & 2:
                 raise ValueError("codes contain NaN")
             if fl & 1:
@@ -1106,7 +1190,8 @@ class Evaluator:
             b, q, g = ev.b, c["q"], c["g"]
             threads, nq_pad, nstripes, rps = c["geo"]
             self.rows_pad = b.padded_rows(g.n)
-            g.bits = b.empty((self.rows_pad, q.bits.shape[1]), torch.int32)
+            self.native = g.loader           # native loader (started by _prepare): the rows arrive on their own
+            g.bits = self.native.bits if self.native is not None else b.empty((self.rows_pad, q.bits.shape[1]), torch.int32)
             if pair:
                 # two gallery rows per plane row: row r of the shard lives in plane row block r // 64
                 self.plane8 = b.empty((self.rows_pad // 2, b.tc_code_bytes_pair(q.nbit, False)), torch.int8)
@@ -1130,7 +1215,7 @@ class Evaluator:
             # to back from the moment the sample has been packed, while this thread queues the sample-level passes, the
             # select launches and the list kernels (~0.3 ms of host time per block that used to sit between two packs).
             # (Not while the bench brackets entry points with events: the brackets are not thread-safe.)
-            self.threaded = bool(ev.stream_loader_thread and not self.pinned and not ev.profile)
+            self.threaded = bool(ev.stream_loader_thread and not self.pinned and not ev.profile and self.native is None)
             self.thread, self.ready, self.error = None, [], None
             self.loaded = {}
             self.blocks = []
@@ -1149,6 +1234,21 @@ class Evaluator:
             s0, s1, r0, r1 = self.blocks[i]
             db_codes = self.c["db_codes"]
             nrow8 = (self.rows_pad - r0) if r1 == g.n else (r1 - r0)
+            if self.native is not None:
+                # the rows of this block are (being) packed by the native loader: wait for them on the host, make the
+                # evaluation's stream wait for their copy, expand them there
+                # (the int8 expansion runs on the loader's stream, behind the copy: beside the select kernel of the
+                # previous block, not between two selects)
+                self.native.wait(r1, self.side)
+                with b.on_stream(self.side):
+                    ev._timed("expand_i8", 0, lambda: b.expand_i8_into(
+                        g.bits[r0:r0 + nrow8], q.nbit, self.plane8[r0 // 2 if self.pair else r0:],
+                        **(dict(pair=True) if self.pair else dict(bare=self.bare))))
+                    done = torch.cuda.Event()
+                    done.record(self.side)
+                torch.cuda.current_stream().wait_event(done)
+                self.loaded[i] = done
+                return
             blk = db_codes[r0:r1]
             if self.thread is not None:
                 # the loader thread: explicit stream handles (the backend's cached stream belongs to the other thread)
@@ -1180,7 +1280,7 @@ class Evaluator:
 
         def load_first(self):
             """block 0 -- or, from pinned memory, every block -- is queued while the GPU works on the sample"""
-            if self.threaded:
+            if self.threaded or self.native is not None:
                 return
             for i in range(len(self.blocks) if self.pinned else 1):
                 self.load(i)
@@ -1224,8 +1324,11 @@ class Evaluator:
             ev, b, q, g = self.ev, self.ev.b, self.c["q"], self.c["g"]
             threads, nq_pad, nstripes, rps = self.c["geo"]
             s0, s1, r0, r1 = self.blocks[i]
-            self.wait_block(i)
-            torch.cuda.current_stream().wait_event(self.loaded[i])
+            if self.native is not None:
+                self.load(i)
+            else:
+                self.wait_block(i)
+                torch.cuda.current_stream().wait_event(self.loaded[i])
             kw = dict(thresh=thresh, ternary=False) if self.bare else {}
             if self.pair:
                 kw = dict(pair=True)
@@ -1318,6 +1421,8 @@ class Evaluator:
             cap = b.empty((nstripes, nq_pad), torch.int32)
             b.record_caps(0, slab_s, thresh, nstripes, nbins, nq, nq_pad, False, cap, sample_stride=stride)
             first_load()
+        if not (tc_pass and streamed and not c["pr_k"]):
+            self._ensure_labels(q, g)      # (put off by _prepare: the thresholds above did not need them)
         # per-stripe class counts: record capacities of the POPC path; whole-gallery relevant counts for R@k
         cls = self._class_counts(c) if (not tc_pass or c["pr_k"]) else None
         self.stats["sample"] = dict(stride=stride, rows=ns_total, m=m)
@@ -1334,13 +1439,32 @@ class Evaluator:
                 tot = b.zeros((2, nbins, nq_pad), torch.int32)
                 if late_load:
                     deferred_load()
+                # list kernels of block i (random L2 gathers, ~0.09 ms) on a stream of their own: they run beside the
+                # select kernel of block i + 1 (tensor pipe) instead of between two selects
+                side2 = None
+                if self.stream_cand_overlap and streamer.native is not None and hasattr(b, "on_stream"):
+                    if getattr(self, "_cand_stream", None) is None:
+                        self._cand_stream = torch.cuda.Stream(device=q.bits.device)
+                    side2, main = self._cand_stream, torch.cuda.current_stream()
+                    if g.plane is None and q.nz is None and label_mode == L.CH_LAB_ID and hasattr(b, "gather_plane"):
+                        g.plane = b.empty((streamer.rows_pad, b.gather_plane_words(g.nbit)), torch.int32)
                 for i in range(len(streamer.blocks)):
                     streamer.select(i, cand, q_i8, dense, thresh, bad)
-                    if not streamer.threaded and i + 1 < len(streamer.blocks) and (i + 1) not in streamer.loaded:
+                    self._ensure_labels(q, g)      # (first needed by the list kernels: packed behind the first select)
+                    if side2 is not None:
+                        side2.wait_stream(main)
+                        with b.on_stream(side2):
+                            self._cand_hist(c, cand, nbins, tot, streamer.blocks[i][0],
+                                            streamer.blocks[i][1] - streamer.blocks[i][0])
+                        continue
+                    if (not streamer.threaded and streamer.native is None and i + 1 < len(streamer.blocks)
+                            and (i + 1) not in streamer.loaded):
                         streamer.load(i + 1)     # host waits for this copy while the GPU runs select(i)
                     # keys / label matches of this block's candidates while the next block is still travelling
                     s0, s1 = streamer.blocks[i][0], streamer.blocks[i][1]
                     self._cand_hist(c, cand, nbins, tot, s0, s1 - s0)
+                if side2 is not None:
+                    main.wait_stream(side2)
                 self.stats["select_kernel"] = "tcgen05"
                 self.stats["select_dense"] = bool(dense)
                 self.stats["select_threshold"] = "epilogue" if streamer.bare else "contraction"

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CH_ABI_VERSION 4
+#define CH_ABI_VERSION 5
 #define CH_MAX_NBIT 256          /* words per code: 1, 2, 4 or 8 x u32 */
 #define CH_MAX_R 8               /* length of an `R` list (test_hashing.py:124-128) */
 #define CH_MAX_PR 32             /* length of `PRs` */
@@ -94,6 +94,21 @@ int ch_pack_sign(ch_ws* ws, const void* codes, int mem, int dtype, int64_t n, in
  * same bit order as ch_pack_sign; *flags_host |= 1 (a zero) / 2 (NaN).  Bit-identical to the kernels. */
 int ch_host_pack_sign(const float* codes_host, int64_t n, int nbit, int64_t row_stride,
                       uint32_t* out_bits_host, uint32_t* flags_host, int threads);
+/* Gallery loader: ch_host_pack_sign for a whole HOST-resident fp32 gallery on a thread of its own, started before
+ * anything else of the evaluation (the host's cores are the bottleneck of an evaluation whose codes arrive as the
+ * `torch.cat` of `.cpu()` batches of trainers/base.py:291-304: they read 4 bytes per code, the GPU is done in less).
+ * The rows are packed in ~256 KB pieces by `ch_host_pack_threads(ws)` threads into a ring of pinned chunks; every
+ * complete chunk is copied to out_bits_dev (rows_pad x words u32, the layout of ch_pack_sign; pad rows zeroed) on
+ * `stream`, in order.  Zeros / NaNs are OR-ed into *flags_dev (bits as in ch_pack_sign) on `stream` before the
+ * last chunk's copy.  `codes_host` (pageable or pinned) must stay valid until ch_host_loader_join.
+ *   ch_host_loader_wait : blocks until rows [0, rows) are on their way, then makes `stream` wait for their copy
+ *   ch_host_loader_join : waits for the thread, frees the handle; *flags_host = the flag bits found (host side) */
+typedef struct ch_loader ch_loader;
+int ch_host_pack_threads(ch_ws* ws);
+int ch_host_loader_start(ch_ws* ws, const float* codes_host, int64_t n, int nbit, int64_t row_stride,
+                         uint32_t* out_bits_dev, uint32_t* flags_dev, void* stream, ch_loader** out);
+int ch_host_loader_wait(ch_loader* loader, int64_t rows, void* stream);
+int ch_host_loader_join(ch_loader* loader, uint32_t* flags_host);
 /* column sums (fp64, deterministic) of DEVICE codes (n, ncols): the numerator of `db_codes.mean(dim=0)`
  * (zero_mean_eval); with a row-sharded gallery the caller all-reduces the sums over ranks. */
 int ch_column_sums(ch_ws* ws, const void* codes_dev, int dtype, int64_t n, int ncols, int64_t row_stride,

@@ -40,7 +40,7 @@ def test_exported_symbols_match_header(lib):
 
 
 def test_pure_host_entry_points(lib):
-    assert lib.ch_abi_version() == 4
+    assert lib.ch_abi_version() == 5
     assert lib.ch_padded_rows(0) == 64 and lib.ch_padded_rows(1) == 128 and lib.ch_padded_rows(64) == 128
     assert [lib.ch_code_words(n) for n in (1, 16, 32, 33, 64, 65, 128, 129, 256, 257, 0)] == \
            [1, 1, 1, 2, 2, 4, 4, 8, 8, 0, 0]

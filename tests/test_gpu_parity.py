@@ -673,6 +673,77 @@ def test_streamed_host_gallery_equals_resident(H):
     assert abs(m2 - om) < TOL and np.allclose(rec2, orec, atol=TOL) and np.allclose(prec2, oprec, atol=TOL)
 
 
+def test_native_gallery_loader(H):
+    """csrc/loader.cu: the whole host gallery packed by a native thread into a ring of pinned chunks and copied chunk by
+    chunk -- bits, pad rows and flags equal to the pack kernel's; a ring smaller than the gallery (slots are
+    refilled); strided rows; waits for row prefixes; and the evaluation paths around it: Python loader (native off),
+    column-slice views, a host gallery that is not streamed after all (R = all), NaN."""
+    import os
+    ev = H.get_evaluator()
+    b = ev.b
+    side = torch.cuda.Stream()
+    g = torch.Generator().manual_seed(5)
+    for n, nbit, ring in [(300_123, 128, None), (1_000_003, 64, 1 << 20), (70_001, 48, None), (5, 32, None)]:
+        x = torch.randn(n, nbit, generator=g)
+        wide = torch.randn(n, nbit + 24, generator=g)
+        x[x == 0], wide[wide == 0] = 1.0, 1.0      # (the CPU generator does produce exact zeros, ~6e-8 of its samples)
+        for src, poke in ((x, None), (wide[:, 8:8 + nbit], None), (x.pin_memory(), None), (x.clone(), "zero"),
+                          (x.clone(), "nan")):
+            if poke == "zero":
+                src[n // 2, 1] = 0.0
+            elif poke == "nan":
+                src[n - 1, nbit - 1] = float("nan")
+            assert b.host_loader_ok(src)
+            bits = torch.full((b.padded_rows(n), b.code_words(nbit)), -1, dtype=torch.int32, device="cuda")
+            flags = torch.zeros(1, dtype=torch.int32, device="cuda")
+            torch.cuda.synchronize()
+            if ring is not None:
+                os.environ["CH_LOADER_RING_BYTES"] = str(ring)
+            try:
+                ld = b.host_loader_start(src, bits, flags, side)
+            finally:
+                os.environ.pop("CH_LOADER_RING_BYTES", None)
+            cur = torch.cuda.current_stream()
+            ld.wait(min(n, 1000), cur)
+            head = bits[:min(n, 1000)].clone()
+            ld.wait(n, cur)
+            fl = ld.join()
+            assert ld.join() == fl                                   # idempotent
+            f_dev = torch.zeros(1, dtype=torch.int32, device="cuda")
+            ref, _ = b.pack_sign(src.cuda(), 0.0, f_dev, False)
+            assert torch.equal(bits, ref) and torch.equal(head, ref[:min(n, 1000)])
+            assert fl == int(f_dev.cpu()[0]) == int(flags.cpu()[0]) == {None: 0, "zero": 1, "nan": 2}[poke], (n, poke)
+    assert not b.host_loader_ok(x.double()) and not b.host_loader_ok(x.cuda()) and not b.host_loader_ok(x.t())
+    # ---- the evaluation around it
+    d, dl, q, ql, ncls = synth.make_random_case(1200, 330_000, 64, 40, p=0.30, seed=77, device="cuda")
+    ref = ev.evaluate(d, dl, q, ql, [100, 1000], 0.0, [1, 5, 10], False, return_ap=True)
+    hd, hdl, hq, hql = d.cpu(), dl.cpu(), q.cpu(), ql.cpu()
+    wide = torch.randn(330_000, 96)
+    wide[:, 16:80] = hd
+    for native in (True, False):
+        ev.stream_native_loader = native
+        try:
+            for host in (hd, wide[:, 16:80]):
+                out = ev.evaluate(host, hdl, hq, hql, [100, 1000], 0.0, [1, 5, 10], False, return_ap=True)
+                assert ev.stats["mode"] == "topR-sampled-streamed", ev.stats
+                assert _same(out, ref)
+        finally:
+            ev.stream_native_loader = True
+    # not streamed after all: the loader's bits are the shard's bits
+    ref_all = ev.evaluate(d, dl, q[:200], ql[:200], [-1], 0.0, [1, 10], False)
+    out_all = ev.evaluate(hd, hdl, hq[:200], hql[:200], [-1], 0.0, [1, 10], False)
+    assert ev.stats["mode"] == "all" and all(np.allclose(a, r, rtol=0, atol=EPS) for a, r in zip(out_all, ref_all))
+    hn = hd.clone()
+    hn[123_456, 7] = float("nan")
+    with pytest.raises(ValueError, match="NaN"):
+        ev.evaluate(hn, hdl, hq, hql, [100], 0.0, [], False)
+    with pytest.raises(ValueError, match="NaN"):
+        ev.evaluate(hn, hdl, hq[:50], hql[:50], [-1], 0.0, [], False)
+    assert ev._loader is None
+    out = ev.evaluate(hd, hdl, hq, hql, [100, 1000], 0.0, [1, 5, 10], False, return_ap=True)     # and it still works
+    assert _same(out, ref)
+
+
 # ------------------------------------------------------------------ zero_mean_eval fused into K1 (SURVEY f2)
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64, torch.float16])
 def test_zero_mean_eval_fused(H, dtype):
