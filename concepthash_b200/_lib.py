@@ -53,6 +53,14 @@ class CandArgs(C.Structure):
                [("r_eff", C.c_int64 * CH_MAX_R), ("pr_k", C.c_int64 * CH_MAX_PR)]
 
 
+CH_LOADER_MAX_JOBS = 4
+
+
+class LoaderJob(C.Structure):
+    _fields_ = [("codes_host", P), ("n", C.c_int64), ("nbit", C.c_int32), ("reserved", C.c_int32),
+                ("row_stride", C.c_int64), ("out_bits_dev", P), ("flags_dev", P)]
+
+
 # name -> (restype, argtypes); the authoritative list of exported symbols (tests check it against the header)
 SIGNATURES = {
     "ch_abi_version": (C.c_int, []),
@@ -66,8 +74,8 @@ SIGNATURES = {
                                P, P, P, P, P]),
     "ch_host_pack_sign": (C.c_int, [P, C.c_int64, C.c_int, C.c_int64, P, P, C.c_int]),
     "ch_host_pack_threads": (C.c_int, [P]),
-    "ch_host_loader_start": (C.c_int, [P, P, C.c_int64, C.c_int, C.c_int64, P, P, P, C.POINTER(C.c_void_p)]),
-    "ch_host_loader_wait": (C.c_int, [P, C.c_int64, P]),
+    "ch_host_loader_start": (C.c_int, [P, C.POINTER(LoaderJob), C.c_int, P, C.POINTER(C.c_void_p)]),
+    "ch_host_loader_wait": (C.c_int, [P, C.c_int, C.c_int64, P, C.c_int]),
     "ch_host_loader_join": (C.c_int, [P, C.POINTER(C.c_uint32)]),
     "ch_column_sums": (C.c_int, [P, P, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int64, P, P]),
     "ch_pack_labels": (C.c_int, [P, P, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_uint32,

@@ -23,26 +23,28 @@ def _ptr(t):
 
 
 class _HostLoader:
-    """Handle of a running native gallery loader (``CudaBackend.host_loader_start``).  Keeps the source tensor and the
-    destination alive until ``join``."""
+    """Handle of a running native host loader (``CudaBackend.host_loader_start``).  Keeps the source tensors and the
+    destinations alive until ``join``.  ``bits[j]`` = the packed array of job j."""
 
-    def __init__(self, lib, handle, codes, bits):
-        self.lib, self.h, self.codes, self.bits = lib, handle, codes, bits
+    def __init__(self, lib, handle, sources, bits):
+        self.lib, self.h, self.sources, self.bits = lib, handle, sources, list(bits)
         self.flags = None
 
-    def wait(self, rows, stream):
-        """blocks until rows [0, rows) are on their way to the device, then makes ``stream`` wait for their copy"""
+    def wait(self, job, rows, stream, block=False):
+        """makes ``stream`` -- any stream but the loader's own -- wait until rows [0, rows) of ``job`` have landed on
+        the device; blocks the calling thread (GIL released) until their copy has been queued."""
         assert self.h is not None, "loader already joined"
-        L.check(self.lib.ch_host_loader_wait(self.h, int(rows), C.c_void_p(stream.cuda_stream)), "ch_host_loader_wait")
+        L.check(self.lib.ch_host_loader_wait(self.h, int(job), int(rows), C.c_void_p(stream.cuda_stream), int(block)),
+                "ch_host_loader_wait")
 
     def join(self):
-        """waits for the loader thread; returns the flag bits it found (1: a zero sign, 2: NaN).  Idempotent."""
+        """waits for the loader thread; returns the flag bits per job (1: a zero sign, 2: NaN).  Idempotent."""
         if self.h is not None:
             h, self.h = self.h, None
-            fl = C.c_uint32(0)
-            rc = self.lib.ch_host_loader_join(h, C.byref(fl))
-            self.flags = int(fl.value)
-            self.codes = None
+            fl = (C.c_uint32 * L.CH_LOADER_MAX_JOBS)()
+            rc = self.lib.ch_host_loader_join(h, fl)
+            self.flags = [int(fl[j]) for j in range(len(self.bits))]
+            self.sources = None
             L.check(rc, "ch_host_loader_join")
         return self.flags
 
@@ -197,17 +199,23 @@ class CudaBackend:
                 (codes.shape[0] == 1 or codes.stride(0) >= codes.shape[1]) and codes.data_ptr() % 4 == 0 and
                 int(self.lib.ch_host_pack_threads(self.ws)) > 0)
 
-    def host_loader_start(self, codes, bits, flags, stream):
-        """Starts the native gallery loader (csrc/loader.cu): ``codes`` (n, nbit) fp32 on the HOST are sign/bit-packed
-        by the host's cores on a thread of their own and copied chunk by chunk into ``bits`` (rows_pad, words) on
-        ``stream``.  Returns a handle: ``wait(rows, stream)`` / ``join() -> flag bits``."""
-        n, nbit = int(codes.shape[0]), int(codes.shape[1])
-        assert bits.shape[0] >= self.padded_rows(n) and bits.shape[1] == self.code_words(nbit) and bits.is_contiguous()
+    def host_loader_start(self, jobs, stream):
+        """Starts the native host loader (csrc/loader.cu).  ``jobs`` = [(codes, bits, flags), ...] in the order they are
+        needed: ``codes`` (n, nbit) fp32 on the HOST are sign/bit-packed by the host's cores on a thread of their own
+        and copied chunk by chunk into ``bits`` (rows_pad, words) on ``stream`` (which must carry nothing else until
+        ``join``); ``flags`` u32[1] gets the zero / NaN bits.  Returns a handle: ``wait(job, rows, stream)`` /
+        ``join() -> flag bits per job``."""
+        arr = (L.LoaderJob * len(jobs))()
+        for k, (codes, bits, flags) in enumerate(jobs):
+            n, nbit = int(codes.shape[0]), int(codes.shape[1])
+            assert bits.shape[0] >= self.padded_rows(n) and bits.shape[1] == self.code_words(nbit) and bits.is_contiguous()
+            arr[k].codes_host, arr[k].n, arr[k].nbit = codes.data_ptr(), n, nbit
+            arr[k].row_stride = codes.stride(0) if n > 1 else nbit
+            arr[k].out_bits_dev, arr[k].flags_dev = bits.data_ptr(), (flags.data_ptr() if flags is not None else None)
         h = C.c_void_p()
-        L.check(self.lib.ch_host_loader_start(self.ws, _ptr(codes), n, nbit, codes.stride(0) if n > 1 else nbit,
-                                              _ptr(bits), _ptr(flags), C.c_void_p(stream.cuda_stream), C.byref(h)),
+        L.check(self.lib.ch_host_loader_start(self.ws, arr, len(jobs), C.c_void_p(stream.cuda_stream), C.byref(h)),
                 "ch_host_loader_start")
-        return _HostLoader(self.lib, h, codes, bits)
+        return _HostLoader(self.lib, h, [j[0] for j in jobs], [j[1] for j in jobs])
 
     def pack_labels(self, labels, nolabel, info=None):
         """labels (n, C) one-/multi-hot or (n,) ids -> (ids u32 (rows_pad), masks (rows_pad, lw) | None, info u32[4]).

@@ -28,6 +28,8 @@ struct ch_ws_priv {
   size_t ring_bytes;
   cudaEvent_t ring_last;
   bool ring_event;
+  uint32_t* progress_dev;       // progress words of the loader's jobs (stream-ordered writes / waits) + their sequence
+  uint32_t progress_seq;
 };
 
 // grow-only device scratch shared by the small helper kernels (all calls are stream-ordered by the caller)
@@ -57,12 +59,20 @@ int ch_ws_results(ch_ws* ws, void** dev, void** host) {
 
 // pinned ring of the gallery loader: grow-only, at least `bytes`; *last = the event recorded behind the last copy that
 // read the ring (never recorded at first: synchronising on it returns at once)
-int ch_ws_loader_ring(ch_ws* ws, size_t bytes, void** ring, size_t* ring_bytes, cudaEvent_t** last) {
+int ch_ws_loader_ring(ch_ws* ws, size_t bytes, void** ring, size_t* ring_bytes, cudaEvent_t** last,
+                      uint32_t** progress_dev, uint32_t** seq) {
   ch_ws_priv* p = reinterpret_cast<ch_ws_priv*>(ws);
   if (!p->ring_event) {
     CH_CUDA(cudaEventCreateWithFlags(&p->ring_last, cudaEventDisableTiming));
     p->ring_event = true;
   }
+  if (p->progress_dev == nullptr) {
+    CH_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->progress_dev), 64));
+    CH_CUDA(cudaMemset(p->progress_dev, 0, 64));
+    CH_CUDA(cudaDeviceSynchronize());
+  }
+  *progress_dev = p->progress_dev;
+  *seq = &p->progress_seq;
   if (bytes > p->ring_bytes) {
     if (p->ring != nullptr) {
       CH_CUDA(cudaEventSynchronize(p->ring_last));
@@ -167,6 +177,7 @@ extern "C" int ch_workspace_destroy(ch_ws* ws) {
   if (p->res_host) cudaFreeHost(p->res_host);
   if (p->ring) cudaFreeHost(p->ring);
   if (p->ring_event) cudaEventDestroy(p->ring_last);
+  if (p->progress_dev) cudaFree(p->progress_dev);
   delete p;
   return 0;
 }

@@ -162,12 +162,13 @@ class Evaluator:
         self.stream_loader_thread = True   # pageable gallery: a loader thread packs / copies the blocks back to back
         self.stream_native_loader = True   # fp32 host gallery: packed from the first moment of the evaluation by a native
         #                                    thread (csrc/loader.cu); the blocks of the select pass only wait for their rows
-        self.stream_chunks_native = 2      # ... blocks per wave-filling stripe group x 2 on that path (3 / 4 measured: no gain)
+        self.stream_chunks_native = 3      # ... blocks per wave-filling stripe group x 2 on that path (2: 4.97, 3: 4.65, 4: 5.0 ms on cfg4)
         self.stream_late_labels = False    # ... labels packed behind the first select launch (measured: no gain either)
         self.stream_cand_overlap = False   # ... list kernels beside the next block's select kernel (measured: no gain --
         #                                    they slow the select kernel by what they save)
         self._loader = None
         self._side_stream = None
+        self._expand_stream = None
         self._cand_stream = None
         self.use_tensor_cores = True       # select pass on tcgen05 (int8 +-1 codes) when the shape allows it
         self.epilogue_thresholds = True    # sparse select passes: threshold comparison in the epilogue (see _bare)
@@ -270,7 +271,8 @@ class Evaluator:
         dt = db_codes.dtype if db_codes.dtype.is_floating_point else torch.float32
         return mean.to(dt).to(torch.float64).contiguous()
 
-    def _prepare(self, db_codes, db_labels, q_codes, q_labels, threshold, allow_defer=False, zero_mean=False):
+    def _prepare(self, db_codes, db_labels, q_codes, q_labels, threshold, allow_defer=False, zero_mean=False,
+                 sample_stride=0):
         if q_codes.dim() != 2 or db_codes.dim() != 2:
             raise ValueError("codes must be 2-D (N, nbit)")
         if q_codes.shape[1] != db_codes.shape[1]:
@@ -307,25 +309,53 @@ class Evaluator:
         if (defer and self.stream_native_loader and hasattr(self.b, "host_loader_start") and
                 self.b.host_loader_ok(db_codes)):
             # fp32 rows in host memory (pageable or pinned): the host's cores are the bottleneck of this evaluation
-            # (they read every code once), so they start NOW, on a native thread of their own -- before the queries,
-            # the labels and the row sample are packed -- and run without a pause to the last row (csrc/loader.cu).
-            # Zeros / NaNs raise ST_SHORT (the streamed pass then falls back) and come back from join().
-            bits = self.b.empty((self.b.padded_rows(int(db_codes.shape[0])), self.b.code_words(int(db_codes.shape[1]))),
-                                torch.int32)
+            # (they read every code once), so they start NOW, on a native thread of their own, and run without a
+            # pause to the last row (csrc/loader.cu): first the queries, then the row sample (both feed the
+            # thresholds the GPU needs before it can touch the gallery), then the gallery.  This thread waits
+            # ~0.3 ms for the first two (less than packing them itself took) and queues the GPU's work meanwhile.
+            # Zeros / NaNs of the gallery and the sample raise ST_SHORT (the streamed pass then falls back) and come
+            # back from join(); those of the queries go to ST_CODES like those of any query pack.
+            b = self.b
+            nbit = int(db_codes.shape[1])
+            jobs, idx = [], {}
+            if self.col_sub is None and b.host_loader_ok(q_codes):
+                idx["q"] = len(jobs)
+                jobs.append((q_codes, b.empty((b.padded_rows(int(q_codes.shape[0])), b.code_words(nbit)), torch.int32),
+                             flags))
+            if sample_stride > 1:
+                run = max(1, 256 // nbit) if nbit in (32, 64, 128, 256) else 1
+                ns, view = self._host_sample_view(db_codes, sample_stride, run)
+                if ns > 0 and b.host_loader_ok(view):
+                    idx["s"] = len(jobs)
+                    jobs.append((view, b.empty((b.padded_rows(ns // run), b.code_words(run * nbit)), torch.int32),
+                                 st[ST_SHORT:ST_SHORT + 1]))
+                    idx["sample"] = (sample_stride, run, ns)
+            idx["g"] = len(jobs)
+            jobs.append((db_codes, b.empty((b.padded_rows(int(db_codes.shape[0])), b.code_words(nbit)), torch.int32),
+                         st[ST_SHORT:ST_SHORT + 1]))
             if getattr(self, "_side_stream", None) is None:
-                # (high priority: the small expansion kernels behind the copies must not queue behind the thousands of
-                # blocks of a list kernel -- measured 0.02 -> 0.34 ms each, and the next select waits for them)
-                self._side_stream = torch.cuda.Stream(device=bits.device, priority=-1)
+                # the loader's copy stream carries NOTHING else while a loader runs (a wait queued on it would sit in
+                # front of the copies it waits for); the expansion kernels behind the copies have a stream of their
+                # own (high priority: they must not queue behind the thousands of blocks of a list kernel --
+                # measured 0.02 -> 0.34 ms each, and the next select waits for them)
+                self._side_stream = torch.cuda.Stream(device=b.device, priority=-1)
+                self._expand_stream = torch.cuda.Stream(device=b.device, priority=-1)
             self._side_stream.wait_stream(torch.cuda.current_stream())      # (the status block is zeroed on this stream)
-            loader = self._loader = self.b.host_loader_start(db_codes, bits, st[ST_SHORT:ST_SHORT + 1],
-                                                             self._side_stream)
+            loader = self._loader = b.host_loader_start(jobs, self._side_stream)
+            loader.idx = idx
         # With the loader running and a hint for the label form, the labels are not on the way to the thresholds (the
         # sample passes rank by keys alone): they are packed after those passes have been queued (0.4 ms of a 5 ms
         # evaluation sat between the query pack and the row sample otherwise) -- _ensure_labels.
         late = (self.stream_late_labels and loader is not None and self._hint is not None and self.comm.world == 1 and
                 max(self._hint["mm"][ST_QINFO], self._hint["mm"][ST_GINFO]) <= 1)         # (single-label form)
+        q_bits = None
+        if loader is not None and "q" in loader.idx:
+            q_bits = loader.bits[loader.idx["q"]]
+            loader.wait(loader.idx["q"], int(q_codes.shape[0]), torch.cuda.current_stream())
         q = self._pack_side(q_codes, q_labels, threshold, flags, L.CH_QUERY_NOLABEL, info=st[ST_QINFO:ST_QINFO + 4],
-                            defer_labels=late)
+                            defer_labels=late, defer_codes=q_bits is not None)
+        if q_bits is not None:
+            q.bits = q_bits
         g = self._pack_side(db_codes, db_labels, threshold, flags, L.CH_GALLERY_NOLABEL,
                             info=st[ST_GINFO:ST_GINFO + 4], defer_codes=defer, defer_labels=late)
         g.loader = loader
@@ -801,9 +831,9 @@ class Evaluator:
         """The gallery is not streamed after all: waits for the native loader, hands its bits to ``g`` (the current
         stream waits for the copies) and returns the flag bits (1: a zero sign, 2: NaN)."""
         loader, g.loader = g.loader, None
-        fl = loader.join()
+        fl = loader.join()[loader.idx["g"]]
         torch.cuda.current_stream().wait_stream(self._side_stream)
-        g.bits, g.nz = loader.bits, None
+        g.bits, g.nz = loader.bits[loader.idx["g"]], None
         return fl
 
     def _evaluate(self, *args, **kw):
@@ -821,8 +851,19 @@ class Evaluator:
         self._hint = hint
         self._new_hint = dict(sites={}, complete=False)
         self.stats.pop("query_chunks", None)
+        # (one rank, host gallery: the row sample the top-R path will want is host-known up front -- the native loader
+        # packs it right behind the queries; _pass_topr_sampled checks that it is the sample it needs)
+        pre_stride = 0
+        if comm.world == 1 and isinstance(db_codes, torch.Tensor) and db_codes.dim() == 2 and not db_codes.is_cuda:
+            n0, rf0 = int(db_codes.shape[0]), (1 if remove_first_retrieved else 0)
+            ll = max(n0 - rf0, 0)
+            rmax0 = max([ll if r == -1 else min(r, ll) for r in r_list] + [min(k, ll) for k in pr_k] + [0])
+            if (rmax0 * 4 < ll and self.sample_stride > 1 and n0 >= self.sample_min_rows and
+                    rmax0 * self.sample_min_ratio <= n0):
+                pre_stride = self.sample_stride * (2 if (rmax0 + rf0) * 5000 <= n0 else 1)
         q, g, ternary, label_mode, lw, nclass, rows = self._prepare(db_codes, db_labels, q_codes, q_labels, threshold,
-                                                                    allow_defer=True, zero_mean=zero_mean)
+                                                                    allow_defer=True, zero_mean=zero_mean,
+                                                                    sample_stride=pre_stride)
         db_codes = self._db_codes_eff           # (the device copy when zero_mean moved a host gallery)
         if label_mode == L.CH_LAB_NONE:
             raise ValueError("labels are required")
@@ -879,7 +920,7 @@ class Evaluator:
             if res[4][ST_PASS] or res[4][ST_SHORT]:
                 # (a zero / NaN found by the native loader is not a per-query failure: no repair, the whole evaluation
                 # is redone with ternary keys -- or raises)
-                odd = comm.world == 1 and g.loader is not None and g.loader.join() != 0
+                odd = comm.world == 1 and g.loader is not None and any(g.loader.join())
                 res = self._repair(ctx, res, q_codes, q_labels, db_labels) if res[4][ST_CODES] == 0 and not odd else None
             if res is None:
                 self.stats["sample"].update(fallback=True)
@@ -1191,7 +1232,8 @@ class Evaluator:
             threads, nq_pad, nstripes, rps = c["geo"]
             self.rows_pad = b.padded_rows(g.n)
             self.native = g.loader           # native loader (started by _prepare): the rows arrive on their own
-            g.bits = self.native.bits if self.native is not None else b.empty((self.rows_pad, q.bits.shape[1]), torch.int32)
+            g.bits = (self.native.bits[self.native.idx["g"]] if self.native is not None
+                      else b.empty((self.rows_pad, q.bits.shape[1]), torch.int32))
             if pair:
                 # two gallery rows per plane row: row r of the shard lives in plane row block r // 64
                 self.plane8 = b.empty((self.rows_pad // 2, b.tc_code_bytes_pair(q.nbit, False)), torch.int8)
@@ -1237,15 +1279,16 @@ class Evaluator:
             if self.native is not None:
                 # the rows of this block are (being) packed by the native loader: wait for them on the host, make the
                 # evaluation's stream wait for their copy, expand them there
-                # (the int8 expansion runs on the loader's stream, behind the copy: beside the select kernel of the
+                # (the int8 expansion runs on a stream of its own behind the copy: beside the select kernel of the
                 # previous block, not between two selects)
-                self.native.wait(r1, self.side)
-                with b.on_stream(self.side):
+                xs = ev._expand_stream
+                self.native.wait(self.native.idx["g"], r1, xs)
+                with b.on_stream(xs):
                     ev._timed("expand_i8", 0, lambda: b.expand_i8_into(
                         g.bits[r0:r0 + nrow8], q.nbit, self.plane8[r0 // 2 if self.pair else r0:],
                         **(dict(pair=True) if self.pair else dict(bare=self.bare))))
                     done = torch.cuda.Event()
-                    done.record(self.side)
+                    done.record(xs)
                 torch.cuda.current_stream().wait_event(done)
                 self.loaded[i] = done
                 return
@@ -1368,11 +1411,21 @@ class Evaluator:
             run = max(1, 256 // g.nbit) if g.nbit in (32, 64, 128, 256) else 1
             ns, view = self._host_sample_view(c["db_codes"], stride, run)
             zflag = status[ST_SHORT:ST_SHORT + 1]     # a zero / NaN in the streamed codes sends the run to the exact path
-            packed, _ = self._timed("pack_host", ns * g.nbit * view.element_size(),
-                                    lambda: b.pack_sign(view, 0.0, zflag, False))
+            ld = g.loader
+            if ld is not None and ld.idx.get("sample") == (stride, run, ns):
+                # the native loader packs the sample right behind the queries
+                packed = ld.bits[ld.idx["s"]]
+                ld.wait(ld.idx["s"], ns // run, torch.cuda.current_stream())
+            else:
+                packed, _ = self._timed("pack_host", ns * g.nbit * view.element_size(),
+                                        lambda: b.pack_sign(view, 0.0, zflag, False))
             sp.bits = packed.view(-1, q.bits.shape[1])         # (super rows, run * words) -> (rows, words)
             streamer = self._Streamer(self, c, zflag, self._bare(dense), self._pair(q))
-            streamer.side.wait_stream(torch.cuda.current_stream())
+            if streamer.native is None:
+                streamer.side.wait_stream(torch.cuda.current_stream())
+            else:
+                # (never the loader's copy stream: a wait queued there would sit in front of the copies it waits for)
+                self._expand_stream.wait_stream(torch.cuda.current_stream())
             c["streamer"] = streamer       # (the caller joins its loader thread whatever happens below)
             streamer.start()
         else:

@@ -28,7 +28,7 @@ ts = []
 for i in range(6):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    ld = b.host_loader_start(hd, bits, flags, side)
+    ld = b.host_loader_start([(hd, bits, flags)], side)
     ld.join()
     t1 = time.perf_counter()
     torch.cuda.synchronize()

@@ -94,20 +94,34 @@ int ch_pack_sign(ch_ws* ws, const void* codes, int mem, int dtype, int64_t n, in
  * same bit order as ch_pack_sign; *flags_host |= 1 (a zero) / 2 (NaN).  Bit-identical to the kernels. */
 int ch_host_pack_sign(const float* codes_host, int64_t n, int nbit, int64_t row_stride,
                       uint32_t* out_bits_host, uint32_t* flags_host, int threads);
-/* Gallery loader: ch_host_pack_sign for a whole HOST-resident fp32 gallery on a thread of its own, started before
- * anything else of the evaluation (the host's cores are the bottleneck of an evaluation whose codes arrive as the
- * `torch.cat` of `.cpu()` batches of trainers/base.py:291-304: they read 4 bytes per code, the GPU is done in less).
- * The rows are packed in ~256 KB pieces by `ch_host_pack_threads(ws)` threads into a ring of pinned chunks; every
- * complete chunk is copied to out_bits_dev (rows_pad x words u32, the layout of ch_pack_sign; pad rows zeroed) on
- * `stream`, in order.  Zeros / NaNs are OR-ed into *flags_dev (bits as in ch_pack_sign) on `stream` before the
- * last chunk's copy.  `codes_host` (pageable or pinned) must stay valid until ch_host_loader_join.
- *   ch_host_loader_wait : blocks until rows [0, rows) are on their way, then makes `stream` wait for their copy
- *   ch_host_loader_join : waits for the thread, frees the handle; *flags_host = the flag bits found (host side) */
+/* Host loader: ch_host_pack_sign for whole HOST-resident fp32 arrays on a thread of its own, started before anything
+ * else of the evaluation (the host's cores are the bottleneck of an evaluation whose codes arrive as the `torch.cat`
+ * of `.cpu()` batches of trainers/base.py:291-304: they read 4 bytes per code, the GPU is done in less).  Up to
+ * CH_LOADER_MAX_JOBS arrays are packed in order (the evaluator passes queries, row sample, gallery) in ~256 KB
+ * pieces by `ch_host_pack_threads(ws)` - 1 threads into a ring of pinned chunks; every complete chunk is copied to
+ * its job's out_bits_dev (rows_pad x words u32, the layout of ch_pack_sign; pad rows zeroed) on `stream`, in order,
+ * followed by an event.  Zeros / NaNs of a job are OR-ed into its *flags_dev
+ * (bits as in ch_pack_sign) on `stream` before the job's last chunk.  The arrays (pageable or pinned) must stay
+ * valid until ch_host_loader_join.
+ *   ch_host_loader_wait : makes `stream` (NOT the loader's own stream) wait until rows [0, rows) of `job` have landed:
+ *                         blocks the calling thread until their copy has been queued, then waits for its event.
+ *                         (Only with CH_LOADER_STREAM_OPS=1 and block = 0 it returns at once -- a cuStreamWaitValue32
+ *                         on the job's progress word; off by default, such waits can deadlock, see loader.cu.)
+ *   ch_host_loader_join : waits for the thread, frees the handle; flags_host[j] = the flag bits of job j (host side) */
+#define CH_LOADER_MAX_JOBS 4
 typedef struct ch_loader ch_loader;
+typedef struct ch_loader_job {
+  const float* codes_host;   /* (n, nbit) fp32, unit column stride, 4-byte aligned */
+  int64_t n;
+  int32_t nbit;
+  int32_t reserved;
+  int64_t row_stride;        /* in elements, >= nbit */
+  uint32_t* out_bits_dev;    /* (ch_padded_rows(n), ch_code_words(nbit)) u32 */
+  uint32_t* flags_dev;       /* device u32, OR-ed; may be NULL */
+} ch_loader_job;
 int ch_host_pack_threads(ch_ws* ws);
-int ch_host_loader_start(ch_ws* ws, const float* codes_host, int64_t n, int nbit, int64_t row_stride,
-                         uint32_t* out_bits_dev, uint32_t* flags_dev, void* stream, ch_loader** out);
-int ch_host_loader_wait(ch_loader* loader, int64_t rows, void* stream);
+int ch_host_loader_start(ch_ws* ws, const ch_loader_job* jobs, int njobs, void* stream, ch_loader** out);
+int ch_host_loader_wait(ch_loader* loader, int job, int64_t rows, void* stream, int block);
 int ch_host_loader_join(ch_loader* loader, uint32_t* flags_host);
 /* column sums (fp64, deterministic) of DEVICE codes (n, ncols): the numerator of `db_codes.mean(dim=0)`
  * (zero_mean_eval); with a row-sharded gallery the caller all-reduces the sums over ranks. */

@@ -699,20 +699,29 @@ def test_native_gallery_loader(H):
             torch.cuda.synchronize()
             if ring is not None:
                 os.environ["CH_LOADER_RING_BYTES"] = str(ring)
+            # a second, short job in front (as the evaluator queues the queries in front of the gallery)
+            small = x[:min(n, 3000)]
+            bits0 = torch.full((b.padded_rows(small.shape[0]), b.code_words(nbit)), -1, dtype=torch.int32, device="cuda")
+            flags0 = torch.zeros(1, dtype=torch.int32, device="cuda")
             try:
-                ld = b.host_loader_start(src, bits, flags, side)
+                ld = b.host_loader_start([(small, bits0, flags0), (src, bits, flags)], side)
             finally:
                 os.environ.pop("CH_LOADER_RING_BYTES", None)
             cur = torch.cuda.current_stream()
-            ld.wait(min(n, 1000), cur)
+            ld.wait(1, min(n, 1000), cur)
             head = bits[:min(n, 1000)].clone()
-            ld.wait(n, cur)
+            ld.wait(0, small.shape[0], cur, block=poke is None)
+            first = bits0.clone()
+            ld.wait(1, n, cur)
+            done = bits.clone()
             fl = ld.join()
-            assert ld.join() == fl                                   # idempotent
+            assert ld.join() == fl and fl[0] == 0                    # idempotent
             f_dev = torch.zeros(1, dtype=torch.int32, device="cuda")
             ref, _ = b.pack_sign(src.cuda(), 0.0, f_dev, False)
-            assert torch.equal(bits, ref) and torch.equal(head, ref[:min(n, 1000)])
-            assert fl == int(f_dev.cpu()[0]) == int(flags.cpu()[0]) == {None: 0, "zero": 1, "nan": 2}[poke], (n, poke)
+            ref0, _ = b.pack_sign(small.cuda(), 0.0, f_dev.clone(), False)
+            assert torch.equal(done, ref) and torch.equal(head, ref[:min(n, 1000)]) and torch.equal(first, ref0)
+            assert fl[1] == int(f_dev.cpu()[0]) == int(flags.cpu()[0]) == {None: 0, "zero": 1, "nan": 2}[poke], (n, poke)
+            assert int(flags0.cpu()[0]) == 0
     assert not b.host_loader_ok(x.double()) and not b.host_loader_ok(x.cuda()) and not b.host_loader_ok(x.t())
     # ---- the evaluation around it
     d, dl, q, ql, ncls = synth.make_random_case(1200, 330_000, 64, 40, p=0.30, seed=77, device="cuda")
