@@ -163,6 +163,7 @@ class Evaluator:
         self.stream_native_loader = True   # fp32 host gallery: packed from the first moment of the evaluation by a native
         #                                    thread (csrc/loader.cu); the blocks of the select pass only wait for their rows
         self.stream_chunks_native = 3      # ... blocks per wave-filling stripe group x 2 on that path (2: 4.97, 3: 4.65, 4: 5.0 ms on cfg4)
+        self.stream_fused_rank = False     # ... one fused list kernel behind the last block instead of one per block
         self.stream_late_labels = False    # ... labels packed behind the first select launch (measured: no gain either)
         self.stream_cand_overlap = False   # ... list kernels beside the next block's select kernel (measured: no gain --
         #                                    they slow the select kernel by what they save)
@@ -794,7 +795,7 @@ class Evaluator:
                  self.stream_min_rows, self.stream_chunks, self.use_tensor_cores, self.select_dense_override,
                  self.stripe_rows_override, self.epilogue_thresholds, self.max_slots, self.paired_rows,
                  self.stripe_cut, self.fused_rank, self.stream_native_loader, self.stream_chunks_native,
-                 self.stream_cand_overlap, self.stream_late_labels)
+                 self.stream_cand_overlap, self.stream_late_labels, self.stream_fused_rank)
         return (sig(db_codes), sig(db_labels), sig(q_codes), sig(q_labels), tuple(r_list), float(threshold),
                 tuple(pr_k), bool(rf), bool(zero_mean), self.comm.world, knobs)
 
@@ -1486,6 +1487,11 @@ class Evaluator:
             nbins = min(nbins, tmax + 1)
             self.stats["sample"]["key_limit"] = nbins
             tot = None
+            # a single rank needs no exchange of the key totals: keys, bases, verification and the in-order walk of
+            # every list happen in ONE kernel, launched by _finish (a streamed gallery: when the GPU, not the host, is
+            # the bottleneck of the full pass -- stream_fused_rank -- instead of list kernels per block)
+            fused_late = (self.fused_rank and comm.world == 1 and not c["rf"] and hasattr(b, "cand_rank") and
+                          (not streamed or (self.stream_fused_rank and streamer.native is not None)))
             if streamed:
                 q_i8 = self._query_plane(q, nq_pad, thresh, streamer.bare, streamer.pair,
                                          scut if streamer.pair else None, nstripes)
@@ -1504,6 +1510,8 @@ class Evaluator:
                 for i in range(len(streamer.blocks)):
                     streamer.select(i, cand, q_i8, dense, thresh, bad)
                     self._ensure_labels(q, g)      # (first needed by the list kernels: packed behind the first select)
+                    if fused_late:
+                        continue
                     if side2 is not None:
                         side2.wait_stream(main)
                         with b.on_stream(side2):
@@ -1525,9 +1533,7 @@ class Evaluator:
             else:
                 self._select_tc(q, g, geo, thresh, cand, dense, bad=bad, scut=scut)
             self.stats["sample"]["stripe_cut"] = scut is not None
-            if (self.fused_rank and comm.world == 1 and not streamed and not c["rf"] and hasattr(b, "cand_rank")):
-                # a single rank needs no exchange of the key totals: keys, bases, verification and the in-order
-                # walk of every list happen in ONE kernel, launched by _finish (which owns the result columns)
+            if fused_late:
                 return dict(cand=cand, fused=dict(rmax=c["rmax"] + c["rf"], need=need, bad=bad), nbins=nbins,
                             total_rel=self._total_rel_from_classes(c, cls), bad=bad)
             base0_all, base0_rel, key_max = self._cand_bases(c, cand, nbins, need, tot, rmax=c["rmax"] + c["rf"],

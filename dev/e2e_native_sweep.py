@@ -56,7 +56,6 @@ for native in (True, False):
         run("python loader (before)")
         continue
     for chunks in (2, 3):
-        for overlap in (False,):
-            for late in (True, False):
-                ev.stream_chunks_native, ev.stream_cand_overlap, ev.stream_late_labels = chunks, overlap, late
-                run("native chunks=%d overlap=%d late=%d" % (chunks, overlap, late))
+        for fused in (False, True):
+            ev.stream_chunks_native, ev.stream_fused_rank = chunks, fused
+            run("native chunks=%d fused_rank=%d" % (chunks, fused))
