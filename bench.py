@@ -462,7 +462,7 @@ def measure(ctx, name, nbit, steps, warmup, *, main, e2e=True, cpu=True):
 
     # e2e: the public call with HOST tensors; H2D of codes + labels and D2H of the result inside.  Led by what the
     # reference's trainers really hand over -- PAGEABLE tensors (trainers/base.py:291-304) -- with pinned beside it.
-    e2e_obj = None
+    e2e_obj, e2e_ok = None, True
     if e2e:
         es, ew = max(2, steps // 2), 2
         pd, pdl, pq, pql = (t.cpu() for t in (d, dl, q, ql))
@@ -495,9 +495,15 @@ def measure(ctx, name, nbit, steps, warmup, *, main, e2e=True, cpu=True):
                                "PCIe as packed sign bits (h2d_bytes_per_step); pageable and pinned alike",
                    "d2h_bytes_per_step": 8 * len(r_list) + 64,
                    "mAP": out_p[0], "mAP_pinned": out_e[0], "mode": mode_p, "kernel_ms_per_step": kinds_p}
+        # the host paths (native loader, streamed blocks) must return the device-resident answer to the last bit:
+        # the candidate lists and the in-order walk do not depend on where the codes came from
+        flat = lambda v: [float(x) for x in (v if isinstance(v, (list, tuple)) else [v])]
+        e2e_obj["equals_resident"] = bool(out is not None and flat(out_p[0]) == flat(out[0]) == flat(out_e[0]))
+        e2e_ok = e2e_obj["equals_resident"]
 
     if thr == 0.0:
         pc, ok = parity_check(ev, w, d, dl, q, ql, rank, world, device)
+        ok = ok and e2e_ok
     else:
         pc, ok = {"skipped": "ternary codes (--threshold): the packed-bit oracle is binary; see tests"}, True
 
@@ -658,7 +664,8 @@ def _measure_all(args, ctx, ev, rank, world, wl):
             plan += [(n, b, 10, 3) for n, b in (("cub200", 64), ("cars196", 16), ("cars196", 32), ("cars196", 64),
                                                 ("nabirds", 64)) if not (n == args.workload and b == wl["nbit"])]
         for name, nbit, steps, warm in plan:
-            obj, ok = measure(ctx, name, nbit, steps, warm, main=False, e2e=False, cpu=False)
+            # (the dataset shapes are what the reference's trainers evaluate, from pageable CPU tensors: their e2e too)
+            obj, ok = measure(ctx, name, nbit, steps, warm, main=False, e2e="dataset" in WORKLOADS[name], cpu=False)
             others.append(obj)
             ok_all = ok_all and ok
     if rank == 0:
