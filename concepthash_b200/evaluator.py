@@ -340,6 +340,7 @@ class Evaluator:
                 # own (high priority: they must not queue behind the thousands of blocks of a list kernel --
                 # measured 0.02 -> 0.34 ms each, and the next select waits for them)
                 self._side_stream = torch.cuda.Stream(device=b.device, priority=-1)
+            if getattr(self, "_expand_stream", None) is None:
                 self._expand_stream = torch.cuda.Stream(device=b.device, priority=-1)
             self._side_stream.wait_stream(torch.cuda.current_stream())      # (the status block is zeroed on this stream)
             loader = self._loader = b.host_loader_start(jobs, self._side_stream)

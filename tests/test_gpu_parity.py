@@ -738,6 +738,11 @@ def test_native_gallery_loader(H):
                 assert _same(out, ref)
         finally:
             ev.stream_native_loader = True
+    # other host dtypes keep the staged path (Python loader thread) -- before and after a native evaluation
+    out = ev.evaluate(hd.half(), hdl, hq.half(), hql, [100, 1000], 0.0, [1, 5, 10], False, return_ap=True)
+    assert ev.stats["mode"] == "topR-sampled-streamed" and _same(out, ref)
+    out = ev.evaluate(hd, hdl, hq.double(), hql, [100, 1000], 0.0, [1, 5, 10], False, return_ap=True)
+    assert ev.stats["mode"] == "topR-sampled-streamed" and _same(out, ref)
     # not streamed after all: the loader's bits are the shard's bits
     ref_all = ev.evaluate(d, dl, q[:200], ql[:200], [-1], 0.0, [1, 10], False)
     out_all = ev.evaluate(hd, hdl, hq[:200], hql[:200], [-1], 0.0, [1, 10], False)
