@@ -53,11 +53,12 @@ class CandArgs(C.Structure):
                [("r_eff", C.c_int64 * CH_MAX_R), ("pr_k", C.c_int64 * CH_MAX_PR)]
 
 
-CH_LOADER_MAX_JOBS = 4
+CH_LOADER_MAX_JOBS = 6
+CH_LOADER_PACK, CH_LOADER_COPY = 0, 1
 
 
 class LoaderJob(C.Structure):
-    _fields_ = [("codes_host", P), ("n", C.c_int64), ("nbit", C.c_int32), ("reserved", C.c_int32),
+    _fields_ = [("codes_host", P), ("n", C.c_int64), ("nbit", C.c_int32), ("kind", C.c_int32),
                 ("row_stride", C.c_int64), ("out_bits_dev", P), ("flags_dev", P)]
 
 

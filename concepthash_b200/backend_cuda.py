@@ -206,16 +206,27 @@ class CudaBackend:
         ``join``); ``flags`` u32[1] gets the zero / NaN bits.  Returns a handle: ``wait(job, rows, stream)`` /
         ``join() -> flag bits per job``."""
         arr = (L.LoaderJob * len(jobs))()
-        for k, (codes, bits, flags) in enumerate(jobs):
+        for k, job in enumerate(jobs):
+            if job[0] == "copy":
+                # ("copy", src, dst): a contiguous 1-D host array (int64 / int32 / float32 class ids) travels as it is
+                _, src, dst = job
+                es = src.element_size()
+                assert src.dim() == 1 and src.is_contiguous() and dst.is_contiguous() and es % 4 == 0
+                assert dst.numel() == src.numel() and dst.dtype == src.dtype and src.data_ptr() % 4 == 0
+                arr[k].codes_host, arr[k].n, arr[k].nbit, arr[k].kind = src.data_ptr(), int(src.numel()), es, L.CH_LOADER_COPY
+                arr[k].row_stride, arr[k].out_bits_dev, arr[k].flags_dev = es, dst.data_ptr(), None
+                continue
+            codes, bits, flags = job
             n, nbit = int(codes.shape[0]), int(codes.shape[1])
             assert bits.shape[0] >= self.padded_rows(n) and bits.shape[1] == self.code_words(nbit) and bits.is_contiguous()
-            arr[k].codes_host, arr[k].n, arr[k].nbit = codes.data_ptr(), n, nbit
+            arr[k].codes_host, arr[k].n, arr[k].nbit, arr[k].kind = codes.data_ptr(), n, nbit, L.CH_LOADER_PACK
             arr[k].row_stride = codes.stride(0) if n > 1 else nbit
             arr[k].out_bits_dev, arr[k].flags_dev = bits.data_ptr(), (flags.data_ptr() if flags is not None else None)
         h = C.c_void_p()
         L.check(self.lib.ch_host_loader_start(self.ws, arr, len(jobs), C.c_void_p(stream.cuda_stream), C.byref(h)),
                 "ch_host_loader_start")
-        return _HostLoader(self.lib, h, [j[0] for j in jobs], [j[1] for j in jobs])
+        return _HostLoader(self.lib, h, [j[1] if j[0] == "copy" else j[0] for j in jobs],
+                           [j[2] if j[0] == "copy" else j[1] for j in jobs])
 
     def pack_labels(self, labels, nolabel, info=None):
         """labels (n, C) one-/multi-hot or (n,) ids -> (ids u32 (rows_pad), masks (rows_pad, lw) | None, info u32[4]).

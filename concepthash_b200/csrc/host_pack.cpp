@@ -303,6 +303,11 @@ static void copy_piece(char* d, const char* s, size_t len, bool nt_ok) {
   if (i < len) memcpy(d + i, s + i, len - i);
 }
 
+void ch_host_copy_piece(void* dst, const void* src, size_t bytes) {
+  static const bool nt_ok = __builtin_cpu_supports("avx2");
+  copy_piece(static_cast<char*>(dst), static_cast<const char*>(src), bytes, nt_ok);
+}
+
 void ch_host_parallel_copy(void* dst, const void* src, size_t bytes, int nthreads) {
   const bool nt_ok = __builtin_cpu_supports("avx2");
   const size_t piece = static_cast<size_t>(256) << 10;

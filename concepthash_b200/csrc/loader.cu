@@ -35,6 +35,7 @@ void ch_host_help();                     // host_pack.cpp: lends this thread to 
 void ch_host_loader_running(int delta);  // host_pack.cpp
 uint32_t ch_host_pack_rows(const float* src, int64_t r0, int64_t r1, int ncols, int64_t rs, int words,
                            uint32_t* dst);                                                         // host_pack.cpp
+void ch_host_copy_piece(void* dst, const void* src, size_t bytes);   // host_pack.cpp: non-temporal stores into pinned memory
 int ch_ws_loader_ring(ch_ws* ws, size_t bytes, void** ring, size_t* ring_bytes, cudaEvent_t** last,
                       uint32_t** progress_dev, uint32_t** seq);                                    // api.cu
 
@@ -72,6 +73,7 @@ const StreamOps& stream_ops() {
 }
 
 struct Job {
+  int kind = CH_LOADER_PACK;               // CH_LOADER_COPY: rows of `words` x 4 bytes are copied as they are
   const float* src = nullptr;
   int64_t n = 0, rs = 0, rows_pad = 0;
   int ncols = 0, words = 0;
@@ -204,11 +206,22 @@ struct Loader {
           }
           int64_t b = a + J.piece;
           if (b > J.n) b = J.n;
-          const uint32_t f = ch_host_pack_rows(
-              J.src, a, b, J.ncols, J.rs, J.words,
-              ring + static_cast<size_t>(c % slots) * slot_words +
-                  static_cast<size_t>(a - static_cast<int64_t>(lc) * J.chunk_rows) * J.words);
-          if (f != 0u) J.fl.fetch_or(f, std::memory_order_relaxed);
+          uint32_t* dst = ring + static_cast<size_t>(c % slots) * slot_words +
+                          static_cast<size_t>(a - static_cast<int64_t>(lc) * J.chunk_rows) * J.words;
+          if (J.kind == CH_LOADER_COPY) {
+            const char* srcb = reinterpret_cast<const char*>(J.src);
+            const size_t rowb = static_cast<size_t>(J.words) * 4, pitch = static_cast<size_t>(J.rs);
+            if (pitch == rowb) {
+              ch_host_copy_piece(dst, srcb + static_cast<size_t>(a) * pitch, static_cast<size_t>(b - a) * rowb);
+            } else {
+              for (int64_t r = a; r < b; ++r)
+                memcpy(reinterpret_cast<char*>(dst) + static_cast<size_t>(r - a) * rowb,
+                       srcb + static_cast<size_t>(r) * pitch, rowb);
+            }
+          } else {
+            const uint32_t f = ch_host_pack_rows(J.src, a, b, J.ncols, J.rs, J.words, dst);
+            if (f != 0u) J.fl.fetch_or(f, std::memory_order_relaxed);
+          }
           left[static_cast<size_t>(c)].fetch_sub(1, std::memory_order_release);
         }
       });
@@ -253,16 +266,26 @@ extern "C" int ch_host_loader_start(ch_ws* ws, const ch_loader_job* jobs, int nj
   for (int j = 0; j < njobs; ++j) {
     const ch_loader_job& in = jobs[j];
     Job& J = tmp[j];
-    J.words = ch_code_words(in.nbit);
-    if (J.words == 0) CH_FAIL("nbit=%d unsupported (1..%d)", in.nbit, CH_MAX_NBIT);
+    J.kind = in.kind;
+    if (in.kind != CH_LOADER_PACK && in.kind != CH_LOADER_COPY) CH_FAIL("loader job %d: unknown kind %d", j, in.kind);
+    if (in.kind == CH_LOADER_COPY) {
+      // raw rows of `nbit` BYTES (a multiple of 4; e.g. 8 = int64 class ids), pitch `row_stride` bytes
+      if (in.nbit < 4 || (in.nbit & 3) != 0 || in.nbit > 4096) CH_FAIL("copy job %d: %d bytes per row", j, in.nbit);
+      J.words = in.nbit / 4;
+    } else {
+      J.words = ch_code_words(in.nbit);
+      if (J.words == 0) CH_FAIL("nbit=%d unsupported (1..%d)", in.nbit, CH_MAX_NBIT);
+    }
     if (in.n <= 0 || in.codes_host == nullptr || in.out_bits_dev == nullptr || in.row_stride < in.nbit)
       CH_FAIL("bad loader job %d", j);
-    if ((reinterpret_cast<uintptr_t>(in.codes_host) & 3) != 0) CH_FAIL("codes must be 4-byte aligned");
-    J.src = in.codes_host; J.n = in.n; J.rs = in.row_stride; J.rows_pad = ch_padded_rows(in.n);
+    if ((reinterpret_cast<uintptr_t>(in.codes_host) & 3) != 0) CH_FAIL("loader sources must be 4-byte aligned");
+    J.src = static_cast<const float*>(in.codes_host); J.n = in.n; J.rs = in.row_stride;
+    J.rows_pad = in.kind == CH_LOADER_COPY ? in.n : ch_padded_rows(in.n);
     J.ncols = in.nbit; J.out_dev = in.out_bits_dev; J.flags_dev = in.flags_dev;
     // pieces of ~256 KB of codes; chunks (the unit that travels) of 32 pieces -- 8 for the short jobs in front of the
     // last one, whose rows the GPU is waiting for -- and at most ~256 chunks per job
-    J.piece = (256 * 1024) / (static_cast<int64_t>(in.nbit) * 4);
+    J.piece = (256 * 1024) / (in.kind == CH_LOADER_COPY ? static_cast<int64_t>(in.nbit)
+                                                         : static_cast<int64_t>(in.nbit) * 4);
     if (J.piece < 16) J.piece = 16;
     int64_t per_chunk = (j + 1 < njobs) ? 8 : 32;
     while ((J.n + J.piece * per_chunk - 1) / (J.piece * per_chunk) > 256) per_chunk *= 2;
@@ -303,7 +326,7 @@ extern "C" int ch_host_loader_start(ch_ws* ws, const ch_loader_job* jobs, int nj
   for (int j = 0; j < njobs; ++j) {
     Job& J = L.job[j];
     const Job& T = tmp[j];
-    J.src = T.src; J.n = T.n; J.rs = T.rs; J.rows_pad = T.rows_pad; J.ncols = T.ncols; J.words = T.words;
+    J.kind = T.kind; J.src = T.src; J.n = T.n; J.rs = T.rs; J.rows_pad = T.rows_pad; J.ncols = T.ncols; J.words = T.words;
     J.out_dev = T.out_dev; J.flags_dev = T.flags_dev; J.piece = T.piece; J.chunk_rows = T.chunk_rows;
     J.npieces = T.npieces; J.piece0 = T.piece0; J.nchunks = T.nchunks; J.chunk0 = T.chunk0;
     J.base = *seq;                       // (monotonic over the workspace's life; compared cyclically)
@@ -326,6 +349,7 @@ extern "C" int ch_host_loader_start(ch_ws* ws, const ch_loader_job* jobs, int nj
   // the pad rows [n, rows_pad) are zero, as ch_pack_sign leaves them
   for (int j = 0; j < njobs; ++j) {
     const Job& J = L.job[j];
+    if (J.rows_pad == J.n) continue;
     cudaError_t e = cudaMemsetAsync(J.out_dev + static_cast<size_t>(J.n) * J.words, 0,
                                     static_cast<size_t>(J.rows_pad - J.n) * J.words * 4, st);
     if (e != cudaSuccess) {

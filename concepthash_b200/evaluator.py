@@ -163,6 +163,7 @@ class Evaluator:
         self.stream_native_loader = True   # fp32 host gallery: packed from the first moment of the evaluation by a native
         #                                    thread (csrc/loader.cu); the blocks of the select pass only wait for their rows
         self.stream_chunks_native = 3      # ... blocks per wave-filling stripe group x 2 on that path (2: 4.97, 3: 4.65, 4: 5.0 ms on cfg4)
+        self.stream_loader_labels = False  # ... 1-D label ids in pageable memory as raw-copy loader jobs (measured: no gain)
         self.stream_fused_rank = False     # ... one fused list kernel behind the last block instead of one per block
         self.stream_late_labels = False    # ... labels packed behind the first select launch (measured: no gain either)
         self.stream_cand_overlap = False   # ... list kernels beside the next block's select kernel (measured: no gain --
@@ -331,6 +332,15 @@ class Evaluator:
                     jobs.append((view, b.empty((b.padded_rows(ns // run), b.code_words(run * nbit)), torch.int32),
                                  st[ST_SHORT:ST_SHORT + 1]))
                     idx["sample"] = (sample_stride, run, ns)
+            # 1-D class ids in pageable memory (8 MB for a 1M-row gallery) travel as loader jobs too: packing them cost
+            # this thread ~0.3 ms between the queries and the first sample pass
+            if self.stream_loader_labels:
+                for key, lab in (("ql", q_labels), ("gl", db_labels)):
+                    if (isinstance(lab, torch.Tensor) and not lab.is_cuda and lab.dim() == 1 and lab.is_contiguous()
+                            and lab.dtype in (torch.int64, torch.int32, torch.float32) and lab.numel() >= 4096
+                            and lab.data_ptr() % 4 == 0 and not lab.is_pinned()):
+                        idx[key] = len(jobs)
+                        jobs.append(("copy", lab, b.empty((lab.numel(),), lab.dtype)))
             idx["g"] = len(jobs)
             jobs.append((db_codes, b.empty((b.padded_rows(int(db_codes.shape[0])), b.code_words(nbit)), torch.int32),
                          st[ST_SHORT:ST_SHORT + 1]))
@@ -354,11 +364,17 @@ class Evaluator:
         if loader is not None and "q" in loader.idx:
             q_bits = loader.bits[loader.idx["q"]]
             loader.wait(loader.idx["q"], int(q_codes.shape[0]), torch.cuda.current_stream())
-        q = self._pack_side(q_codes, q_labels, threshold, flags, L.CH_QUERY_NOLABEL, info=st[ST_QINFO:ST_QINFO + 4],
-                            defer_labels=late, defer_codes=q_bits is not None)
+        def landed(key, lab):
+            """the device copy of a label array the loader carries (the current stream waits for it), or the array"""
+            if loader is None or key not in loader.idx:
+                return lab
+            loader.wait(loader.idx[key], int(lab.numel()), torch.cuda.current_stream())
+            return loader.bits[loader.idx[key]]
+        q = self._pack_side(q_codes, landed("ql", q_labels), threshold, flags, L.CH_QUERY_NOLABEL,
+                            info=st[ST_QINFO:ST_QINFO + 4], defer_labels=late, defer_codes=q_bits is not None)
         if q_bits is not None:
             q.bits = q_bits
-        g = self._pack_side(db_codes, db_labels, threshold, flags, L.CH_GALLERY_NOLABEL,
+        g = self._pack_side(db_codes, landed("gl", db_labels), threshold, flags, L.CH_GALLERY_NOLABEL,
                             info=st[ST_GINFO:ST_GINFO + 4], defer_codes=defer, defer_labels=late)
         g.loader = loader
         if self.comm.world > 1:
@@ -796,7 +812,7 @@ class Evaluator:
                  self.stream_min_rows, self.stream_chunks, self.use_tensor_cores, self.select_dense_override,
                  self.stripe_rows_override, self.epilogue_thresholds, self.max_slots, self.paired_rows,
                  self.stripe_cut, self.fused_rank, self.stream_native_loader, self.stream_chunks_native,
-                 self.stream_cand_overlap, self.stream_late_labels, self.stream_fused_rank)
+                 self.stream_cand_overlap, self.stream_late_labels, self.stream_fused_rank, self.stream_loader_labels)
         return (sig(db_codes), sig(db_labels), sig(q_codes), sig(q_labels), tuple(r_list), float(threshold),
                 tuple(pr_k), bool(rf), bool(zero_mean), self.comm.world, knobs)
 

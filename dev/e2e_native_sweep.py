@@ -55,7 +55,6 @@ for native in (True, False):
     if not native:
         run("python loader (before)")
         continue
-    for chunks in (2, 3):
-        for fused in (False, True):
-            ev.stream_chunks_native, ev.stream_fused_rank = chunks, fused
-            run("native chunks=%d fused_rank=%d" % (chunks, fused))
+    for labels in (False, True, False, True):
+        ev.stream_loader_labels = labels
+        run("native loader_labels=%d" % labels)

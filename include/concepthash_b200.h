@@ -108,16 +108,17 @@ int ch_host_pack_sign(const float* codes_host, int64_t n, int nbit, int64_t row_
  *                         (Only with CH_LOADER_STREAM_OPS=1 and block = 0 it returns at once -- a cuStreamWaitValue32
  *                         on the job's progress word; off by default, such waits can deadlock, see loader.cu.)
  *   ch_host_loader_join : waits for the thread, frees the handle; flags_host[j] = the flag bits of job j (host side) */
-#define CH_LOADER_MAX_JOBS 4
+#define CH_LOADER_MAX_JOBS 6
 typedef struct ch_loader ch_loader;
+enum { CH_LOADER_PACK = 0, CH_LOADER_COPY = 1 };
 typedef struct ch_loader_job {
-  const float* codes_host;   /* (n, nbit) fp32, unit column stride, 4-byte aligned */
+  const void* codes_host;    /* PACK: (n, nbit) fp32, unit column stride, 4-byte aligned.  COPY: n rows of raw bytes */
   int64_t n;
-  int32_t nbit;
-  int32_t reserved;
-  int64_t row_stride;        /* in elements, >= nbit */
-  uint32_t* out_bits_dev;    /* (ch_padded_rows(n), ch_code_words(nbit)) u32 */
-  uint32_t* flags_dev;       /* device u32, OR-ed; may be NULL */
+  int32_t nbit;              /* PACK: bits per row.  COPY: BYTES per row (a multiple of 4, e.g. 8 = int64 class ids) */
+  int32_t kind;              /* CH_LOADER_PACK | CH_LOADER_COPY (rows travel as they are: the label ids of a side) */
+  int64_t row_stride;        /* PACK: in elements, >= nbit.  COPY: in bytes, >= nbit */
+  uint32_t* out_bits_dev;    /* PACK: (ch_padded_rows(n), ch_code_words(nbit)) u32.  COPY: n x nbit bytes, dense */
+  uint32_t* flags_dev;       /* PACK: device u32, OR-ed; may be NULL.  COPY: unused */
 } ch_loader_job;
 int ch_host_pack_threads(ch_ws* ws);
 int ch_host_loader_start(ch_ws* ws, const ch_loader_job* jobs, int njobs, void* stream, ch_loader** out);

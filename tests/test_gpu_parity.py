@@ -703,19 +703,24 @@ def test_native_gallery_loader(H):
             small = x[:min(n, 3000)]
             bits0 = torch.full((b.padded_rows(small.shape[0]), b.code_words(nbit)), -1, dtype=torch.int32, device="cuda")
             flags0 = torch.zeros(1, dtype=torch.int32, device="cuda")
+            ids = torch.randint(0, 1 << 40, (max(n // 3, 7),), generator=g)          # raw copy job (label ids)
+            ids_dev = torch.zeros_like(ids, device="cuda")
             try:
-                ld = b.host_loader_start([(small, bits0, flags0), (src, bits, flags)], side)
+                ld = b.host_loader_start([(small, bits0, flags0), ("copy", ids, ids_dev), (src, bits, flags)], side)
             finally:
                 os.environ.pop("CH_LOADER_RING_BYTES", None)
             cur = torch.cuda.current_stream()
-            ld.wait(1, min(n, 1000), cur)
+            ld.wait(2, min(n, 1000), cur)
             head = bits[:min(n, 1000)].clone()
             ld.wait(0, small.shape[0], cur, block=poke is None)
             first = bits0.clone()
-            ld.wait(1, n, cur)
+            ld.wait(1, ids.numel(), cur)
+            assert torch.equal(ids_dev.cpu(), ids)
+            ld.wait(2, n, cur)
             done = bits.clone()
             fl = ld.join()
-            assert ld.join() == fl and fl[0] == 0                    # idempotent
+            assert ld.join() == fl and fl[0] == 0 and fl[1] == 0     # idempotent
+            fl = [fl[0], fl[2]]
             f_dev = torch.zeros(1, dtype=torch.int32, device="cuda")
             ref, _ = b.pack_sign(src.cuda(), 0.0, f_dev, False)
             ref0, _ = b.pack_sign(small.cuda(), 0.0, f_dev.clone(), False)
