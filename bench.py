@@ -495,10 +495,23 @@ def measure(ctx, name, nbit, steps, warmup, *, main, e2e=True, cpu=True):
                                "PCIe as packed sign bits (h2d_bytes_per_step); pageable and pinned alike",
                    "d2h_bytes_per_step": 8 * len(r_list) + 64,
                    "mAP": out_p[0], "mAP_pinned": out_e[0], "mode": mode_p, "kernel_ms_per_step": kinds_p}
+        if "dataset" in wl:
+            # the label form the reference's trainers hand over: one-hot (N, C) float32 rows (trainers/base.py:291-304)
+            from concepthash_b200 import synth as _synth
+            ohd, ohq = _synth.one_hot(dl.cpu(), w["nclass"]), _synth.one_hot(ql.cpu(), w["nclass"])
+            pd2, pq2 = d.cpu(), q.cpu()
+            step_oh = lambda: hashing.calculate_mAP(pd2, ohd, pq2, ohq, w["R"], threshold=thr, group=group)
+            ms_oh, out_oh, _, _, _ = run(step_oh, es, ew, profile=False)
+            e2e_obj["ms_per_step_onehot_labels"] = ms_oh
+            e2e_obj["labels_note"] = ("ms_per_step: 1-D int64 class ids; ms_per_step_onehot_labels: the one-hot (N, C) "
+                                      "float32 label rows of trainers/base.py:291-304, pageable")
+            e2e_obj["mAP_onehot"] = out_oh[0]
+            del ohd, ohq, pd2, pq2
         # the host paths (native loader, streamed blocks) must return the device-resident answer to the last bit:
         # the candidate lists and the in-order walk do not depend on where the codes came from
         flat = lambda v: [float(x) for x in (v if isinstance(v, (list, tuple)) else [v])]
-        e2e_obj["equals_resident"] = bool(out is not None and flat(out_p[0]) == flat(out[0]) == flat(out_e[0]))
+        e2e_obj["equals_resident"] = bool(out is not None and flat(out_p[0]) == flat(out[0]) == flat(out_e[0]) and
+                                          ("mAP_onehot" not in e2e_obj or flat(e2e_obj["mAP_onehot"]) == flat(out[0])))
         e2e_ok = e2e_obj["equals_resident"]
 
     if thr == 0.0:

@@ -384,10 +384,13 @@ int pack_from_host(ch_ws* ws, const void* src, int dtype, int64_t n, int ncols, 
       cudaGetLastError();   // older drivers report unregistered host pointers as an error
   }
   if (pageable && ch_ws_ensure_bounce(ws)) return 1;
-  // Pageable fp32 codes, plain sign test: the host's cores have to touch every byte anyway (nothing can DMA from
-  // pageable memory), so they do the sign test in that one pass and only the BITS travel (host_pack.cpp).
-  if (pageable && dtype == CH_F32 && thr == 0.0 && sub == nullptr && out_nz == nullptr &&
+  // fp32 codes in host memory, plain sign test: for pageable memory the host's cores have to touch every byte anyway
+  // (nothing can DMA from it), so they do the sign test in that one pass and only the BITS travel (host_pack.cpp).
+  // Pinned memory takes the same route: the cores read it at 150-200 GB/s, the DMA engine at ~43 GB/s (NABirds from
+  // pinned tensors: 1.95 ms by DMA + kernel, 1.19 ms from pageable tensors by this path).
+  if (dtype == CH_F32 && thr == 0.0 && sub == nullptr && out_nz == nullptr &&
       ws->pack_threads > 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+    if (ch_ws_ensure_bounce(ws)) return 1;
     const size_t out_row = static_cast<size_t>(words) * 4;
     const int64_t rows_per_buf = static_cast<int64_t>(ws->stage_bytes / out_row);
     int c = 0;

@@ -22,7 +22,8 @@ def brief(x, main=False):
         print("   parity", {k: pc.get(k) for k in ("queries", "gallery_rows", "max_abs_ap_delta", "ids_equal", "ok")})
     e = x.get("e2e")
     if e:
-        print(f"   e2e pageable {e['ms_per_step']:.2f} ms  pinned {e['ms_per_step_pinned_host_tensors']:.2f} ms")
+        print(f"   e2e pageable {e['ms_per_step']:.2f} ms  pinned {e['ms_per_step_pinned_host_tensors']:.2f} ms" +
+              (f"  one-hot labels {e['ms_per_step_onehot_labels']:.2f} ms" if "ms_per_step_onehot_labels" in e else ""))
     if x.get("clocks"):
         print("   clocks", x["clocks"])
     if x.get("cpu_baseline"):

@@ -88,7 +88,7 @@ int ch_pack_sign(ch_ws* ws, const void* codes, int mem, int dtype, int64_t n, in
 /* The host half of ch_pack_sign for PAGEABLE fp32 codes -- what `inference_one_epoch` returns, a torch.cat of
  * `.cpu()` batches (trainers/base.py:291-304).  Nothing can DMA from pageable memory, the host's cores have to
  * touch every byte once anyway; they apply the sign test in that pass (AVX-512 / AVX2, `threads` threads) and only
- * the bits cross PCIe.  ch_pack_sign does this internally for CH_MEM_HOST + unregistered memory + CH_F32 +
+ * the bits cross PCIe.  ch_pack_sign does this internally for CH_MEM_HOST (pageable or pinned) + CH_F32 +
  * threshold 0 + no col_sub + no non-zero plane; this entry point exposes the same routine with host output
  * (unit tests; callers that pack while the loader is still producing batches).  out_bits_host: (n, words) u32,
  * same bit order as ch_pack_sign; *flags_host |= 1 (a zero) / 2 (NaN).  Bit-identical to the kernels. */
