@@ -184,60 +184,105 @@ __global__ void record_offsets_kernel(const uint32_t* __restrict__ cap, const un
 // arrays: key_max[q] = smallest key at which the global list holds rmax items (0xfffffffe-like "no limit" = nbins-1
 // when it never does), optional total_rel[q], and the verification of a sampled threshold -- status |= 1 when some
 // query counted fewer than `need` candidates (replaces a separate ch_check_counts launch).
-__global__ void scan_bases_pair_kernel(const uint32_t* __restrict__ tot, int world, int rank, int nbins, long long nq,
-                                       long long nq_pad, long long rmax, long long need,
-                                       uint32_t* __restrict__ base0_all, uint32_t* __restrict__ base0_rel,
-                                       uint32_t* __restrict__ key_max, uint32_t* __restrict__ total_rel,
-                                       uint32_t* __restrict__ status, uint32_t* __restrict__ bad) {
-  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  bool short_list = false;
-  if (q < nq_pad) {
-    unsigned long long cum_a = 0, cum_r = 0;
-    uint32_t t = static_cast<uint32_t>(nbins - 1);
-    bool found = false;
-    constexpr int B = 4;
-    for (int key0 = 0; key0 < nbins; key0 += B) {
-      unsigned long long la[B], ta[B], lr[B], tr[B];
+// (key groups as in scan_bases_kernel: with 8 ranks a thread of the one-thread-per-query form issued 2 x 8 dependent
+// rounds of loads per key batch -- 82 us of a 1.6 ms step on 8 GPUs)
+__global__ void __launch_bounds__(32 * kScanGroups)
+scan_bases_pair_kernel(const uint32_t* __restrict__ tot, int world, int rank, int nbins, long long nq,
+                       long long nq_pad, long long rmax, long long need, uint32_t* __restrict__ base0_all,
+                       uint32_t* __restrict__ base0_rel, uint32_t* __restrict__ key_max,
+                       uint32_t* __restrict__ total_rel, uint32_t* __restrict__ status, uint32_t* __restrict__ bad) {
+  __shared__ unsigned long long gsum_a[kScanGroups][32], gsum_r[kScanGroups][32];
+  __shared__ uint32_t gfirst[kScanGroups][32];
+  const int lane = threadIdx.x & 31, kg = threadIdx.x >> 5;
+  const long long q = static_cast<long long>(blockIdx.x) * 32 + lane;
+  const bool inside = q < nq_pad, live = q < nq;
+  const bool with_rel = base0_rel != nullptr;
+  const size_t plane = static_cast<size_t>(nbins) * nq_pad;
+  const int chunk = (nbins + kScanGroups - 1) / kScanGroups;
+  const int k0 = kg * chunk, k1 = min(nbins, k0 + chunk);
+  constexpr int B = 4;
+  unsigned long long sum_a = 0, sum_r = 0;
+  if (live) {
+    for (int key0 = k0; key0 < k1; key0 += B) {
+      uint32_t va[B], vr[B];
 #pragma unroll
-      for (int j = 0; j < B; ++j) {
-        la[j] = ta[j] = lr[j] = tr[j] = 0;
-        const int key = key0 + j;
-        if (q < nq && key < nbins) {
+      for (int jj = 0; jj < B; ++jj) {
+        va[jj] = vr[jj] = 0u;
+        if (key0 + jj < k1) {
           for (int g = 0; g < world; ++g) {
-            const size_t o = ((static_cast<size_t>(g) * 2) * nbins + key) * nq_pad + q;
-            const uint32_t va = __ldg(tot + o);
-            const uint32_t vr = base0_rel != nullptr ? __ldg(tot + o + static_cast<size_t>(nbins) * nq_pad) : 0u;
-            if (g < rank) {
-              la[j] += va;
-              lr[j] += vr;
-            }
-            ta[j] += va;
-            tr[j] += vr;
+            const size_t o = ((static_cast<size_t>(g) * 2) * nbins + key0 + jj) * nq_pad + q;
+            va[jj] += __ldg(tot + o);
+            if (with_rel) vr[jj] += __ldg(tot + o + plane);
           }
         }
       }
 #pragma unroll
-      for (int j = 0; j < B; ++j) {
-        const int key = key0 + j;
-        if (key >= nbins) break;
-        const size_t o = static_cast<size_t>(key) * nq_pad + q;
-        base0_all[o] = static_cast<uint32_t>(cum_a + la[j]);
-        if (base0_rel != nullptr) base0_rel[o] = static_cast<uint32_t>(cum_r + lr[j]);
-        cum_a += ta[j];
-        cum_r += tr[j];
-        if (!found && rmax >= 0 && cum_a >= static_cast<unsigned long long>(rmax)) {
-          t = static_cast<uint32_t>(key);
-          found = true;
-        }
+      for (int jj = 0; jj < B; ++jj) {
+        sum_a += va[jj];
+        sum_r += vr[jj];
       }
     }
+  }
+  gsum_a[kg][lane] = sum_a;
+  gsum_r[kg][lane] = sum_r;
+  __syncthreads();
+  unsigned long long cum_a = 0, cum_r = 0;
+  for (int g2 = 0; g2 < kg; ++g2) {
+    cum_a += gsum_a[g2][lane];
+    cum_r += gsum_r[g2][lane];
+  }
+  uint32_t first = 0xffffffffu;
+  if (inside) {
+    for (int key0 = k0; key0 < k1; key0 += B) {
+      unsigned long long la[B], ta[B], lr[B], tr[B];
+#pragma unroll
+      for (int jj = 0; jj < B; ++jj) {
+        la[jj] = ta[jj] = lr[jj] = tr[jj] = 0;
+        if (live && key0 + jj < k1) {
+          for (int g = 0; g < world; ++g) {
+            const size_t o = ((static_cast<size_t>(g) * 2) * nbins + key0 + jj) * nq_pad + q;
+            const uint32_t va = __ldg(tot + o);
+            const uint32_t vr = with_rel ? __ldg(tot + o + plane) : 0u;
+            if (g < rank) {
+              la[jj] += va;
+              lr[jj] += vr;
+            }
+            ta[jj] += va;
+            tr[jj] += vr;
+          }
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < B; ++jj) {
+        const int key = key0 + jj;
+        if (key >= k1) break;
+        const size_t o = static_cast<size_t>(key) * nq_pad + q;
+        base0_all[o] = static_cast<uint32_t>(cum_a + la[jj]);
+        if (with_rel) base0_rel[o] = static_cast<uint32_t>(cum_r + lr[jj]);
+        cum_a += ta[jj];
+        cum_r += tr[jj];
+        if (first == 0xffffffffu && rmax >= 0 && cum_a >= static_cast<unsigned long long>(rmax))
+          first = static_cast<uint32_t>(key);
+      }
+    }
+  }
+  gfirst[kg][lane] = first;
+  __syncthreads();
+  bool short_list = false;
+  if (kg == 0 && inside) {
+    uint32_t t = static_cast<uint32_t>(nbins - 1);
+    unsigned long long all_a = 0, all_r = 0;
+    for (int g2 = kScanGroups - 1; g2 >= 0; --g2) {
+      if (gfirst[g2][lane] != 0xffffffffu) t = gfirst[g2][lane];
+      all_a += gsum_a[g2][lane];
+      all_r += gsum_r[g2][lane];
+    }
     if (key_max != nullptr) key_max[q] = t;
-    if (total_rel != nullptr) total_rel[q] = static_cast<uint32_t>(cum_r);
-    short_list = need > 0 && q < nq && cum_a < static_cast<unsigned long long>(need);
+    if (total_rel != nullptr) total_rel[q] = static_cast<uint32_t>(all_r);
+    short_list = need > 0 && live && all_a < static_cast<unsigned long long>(need);
     if (short_list && bad != nullptr) bad[q] = 1u;
   }
-  if (status != nullptr && __ballot_sync(0xffffffffu, short_list) != 0u && (threadIdx.x & 31) == 0)
-    atomicOr(status, 1u);
+  if (status != nullptr && __ballot_sync(0xffffffffu, short_list) != 0u && lane == 0) atomicOr(status, 1u);
 }
 
 // every stride-th row of a packed bit plane (rows, words) -> (rows_out_pad, words), pad rows zero
@@ -711,7 +756,7 @@ extern "C" int ch_scan_bases_pair(ch_ws* ws, const uint32_t* tot_dev, int world,
   if (world < 1 || rank < 0 || rank >= world) CH_FAIL("bad world/rank %d/%d", world, rank);
   if (need > 0 && status_dev == nullptr) CH_FAIL("verification needs a status word");
   ChDeviceGuard guard(ws->device);
-  scan_bases_pair_kernel<<<blocks_for(nq_pad, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  scan_bases_pair_kernel<<<blocks_for(nq_pad, 32), 32 * kScanGroups, 0, static_cast<cudaStream_t>(stream)>>>(
       tot_dev, world, rank, nbins, nq, nq_pad, rmax, need, base0_all_dev, base0_rel_dev, key_max_dev, total_rel_dev,
       status_dev, bad_dev);
   CH_LAUNCH_CHECK(ws);
