@@ -192,7 +192,17 @@ struct Loader {
           if (failed.load(std::memory_order_relaxed)) break;
           ch_host_help();                     // the evaluating thread's short packs go first (they feed the GPU's first work)
           const int64_t p = next.fetch_add(1, std::memory_order_relaxed);
-          if (p >= npieces) break;
+          if (p >= npieces) {
+            // no piece left for this thread -- but thread 0 is the one that sends chunks and frees ring slots: it
+            // stays until the last chunk is on its way.  (It used to leave here; a thread still waiting for a ring
+            // slot then waited for ever, and the pool run with it: a rare hang with a ring of 4 slots.)
+            while (t == 0 && sent_local < nchunks && !failed.load(std::memory_order_relaxed)) {
+              drain(sent_local);
+              ch_host_help();
+              if (sent_local < nchunks) std::this_thread::yield();
+            }
+            break;
+          }
           int j = 0;
           while (j + 1 < njobs && p >= job[j + 1].piece0) ++j;
           Job& J = job[j];

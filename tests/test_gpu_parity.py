@@ -728,6 +728,23 @@ def test_native_gallery_loader(H):
             assert fl[1] == int(f_dev.cpu()[0]) == int(flags.cpu()[0]) == {None: 0, "zero": 1, "nan": 2}[poke], (n, poke)
             assert int(flags0.cpu()[0]) == 0
     assert not b.host_loader_ok(x.double()) and not b.host_loader_ok(x.cuda()) and not b.host_loader_ok(x.t())
+    # a ring of 4 slots, many times: threads wait for slots all the time and depend on thread 0 sending chunks to the
+    # very end (it used to leave with the last piece: a rare hang)
+    big = torch.randn(400_000, 64, generator=g)
+    big[big == 0] = 1.0
+    bits = torch.empty((b.padded_rows(big.shape[0]), 2), dtype=torch.int32, device="cuda")
+    ref, _ = b.pack_sign(big.cuda(), 0.0, torch.zeros(1, dtype=torch.int32, device="cuda"), False)
+    os.environ["CH_LOADER_RING_BYTES"] = str(1 << 20)
+    try:
+        for rep in range(100):
+            ld = b.host_loader_start([(big[:2000], torch.empty((b.padded_rows(2000), 2), dtype=torch.int32, device="cuda"),
+                                       None), (big, bits, None)], side)
+            ld.wait(1, big.shape[0], torch.cuda.current_stream())
+            if rep % 25 == 0:
+                assert torch.equal(bits, ref)
+            assert ld.join() == [0, 0]
+    finally:
+        os.environ.pop("CH_LOADER_RING_BYTES", None)
     # ---- the evaluation around it
     d, dl, q, ql, ncls = synth.make_random_case(1200, 330_000, 64, 40, p=0.30, seed=77, device="cuda")
     ref = ev.evaluate(d, dl, q, ql, [100, 1000], 0.0, [1, 5, 10], False, return_ap=True)
