@@ -363,10 +363,17 @@ __global__ void __launch_bounds__(1024) exscan_check_kernel(unsigned long long* 
   }
   __syncthreads();
   unsigned long long run = part[t];
-  for (long long i = b; i < e; ++i) {
-    const unsigned long long x = v[i];
-    v[i] = run;
-    run += x;
+  // (batches of 8: a load of v[i + 1] may not pass the store to v[i] otherwise, and 25 dependent round trips of one
+  // thread were half of this single-CTA kernel's time)
+  for (long long i = b; i < e; i += 8) {
+    unsigned long long x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = i + j < e ? v[i + j] : 0ull;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (i + j < e) v[i + j] = run;
+      run += x[j];
+    }
   }
 }
 
