@@ -760,6 +760,17 @@ def test_native_gallery_loader(H):
                 assert _same(out, ref)
         finally:
             ev.stream_native_loader = True
+    # the knobs of the native path that were measured and left off still give the same answer
+    for knob, val in (("stream_cand_overlap", True), ("stream_late_labels", True), ("stream_fused_rank", True),
+                      ("stream_loader_labels", True), ("stream_chunks_native", 2), ("stream_chunks_native", 5)):
+        saved = getattr(ev, knob)
+        setattr(ev, knob, val)
+        try:
+            for rep in range(2):                    # without and with a hint
+                out = ev.evaluate(hd, hdl, hq, hql, [100, 1000], 0.0, [1, 5, 10], False, return_ap=True)
+                assert ev.stats["mode"] == "topR-sampled-streamed" and _same(out, ref), (knob, rep)
+        finally:
+            setattr(ev, knob, saved)
     # other host dtypes keep the staged path (Python loader thread) -- before and after a native evaluation
     out = ev.evaluate(hd.half(), hdl, hq.half(), hql, [100, 1000], 0.0, [1, 5, 10], False, return_ap=True)
     assert ev.stats["mode"] == "topR-sampled-streamed" and _same(out, ref)
