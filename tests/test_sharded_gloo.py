@@ -1,4 +1,4 @@
-"""world_size-2 (gloo, CPU) run of the REAL multi-rank orchestration (evaluator + DistComm) over the numpy
+"""world_size-2 and -3 (gloo, CPU) runs of the REAL multi-rank orchestration (evaluator + DistComm) over the numpy
 backend emulation: a row-sharded gallery must give the 1-rank / oracle answers exactly."""
 import os
 import socket
@@ -21,7 +21,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, extras=True):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -48,7 +48,7 @@ def _worker(rank, world, port, out):
             maps, rec, prec = ev.evaluate(ds, dls, q, ql, r_list, thr, PRs, rf)
             ids, keys, tern = ev.retrieve(ds, q, 20, thr, rf)
             results[case] = (maps, rec, prec, ids.clone(), keys.clone(), tern)
-            if case == 1:
+            if case == 1 and extras:
                 # sampled top-R with two-level thresholds across ranks
                 ev2 = Evaluator(EmuBackend(rows_per_stripe=32, threads=128, tensor_cores=True), DistComm())
                 ev2.sample_stride, ev2.sample_min_rows, ev2.sample_min_ratio = 2, 0, 4
@@ -94,11 +94,7 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.timeout(300)
-def test_two_ranks_match_oracle(tmp_path):
-    out = str(tmp_path / "res.pt")
-    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
-    results = torch.load(out)
+def _check_base_cases(results, extras):
     for case, (R, PRs, rf, thr, zero) in enumerate([(-1, [1, 5, 10], False, 0.0, False),
                                                      (15, [1, 5], False, 0.0, False),
                                                      ([4, 30, -1], [3], False, 0.0, True),
@@ -118,7 +114,7 @@ def test_two_ranks_match_oracle(tmp_path):
         oids, odist = mo.topk_ids(q, d, 20, threshold=thr, remove_first_retrieved=rf)
         assert torch.equal(ids, oids), case
         assert torch.equal(keys.float() * (0.5 if tern else 1.0), odist), case
-        if case == 1:
+        if case == 1 and extras:
             s2 = results["s2"]
             assert s2[4] and s2[3] in ("topR-sampled", "topR"), s2
             assert np.allclose(s2[0], om, atol=1e-12) and np.allclose(s2[1], orec, atol=1e-12)
@@ -136,3 +132,19 @@ def test_two_ranks_match_oracle(tmp_path):
             zm = results["zm"]
             assert np.allclose(zm[0], [om], atol=1e-12) and np.allclose(zm[1], orec, atol=1e-12)
             assert np.allclose(zm[2], oprec, atol=1e-12)
+
+
+@pytest.mark.timeout(300)
+def test_two_ranks_match_oracle(tmp_path):
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    _check_base_cases(torch.load(out), True)
+
+
+@pytest.mark.timeout(300)
+def test_three_ranks_match_oracle(tmp_path):
+    """Three shards: ranks >= 2 add the totals of SEVERAL lower ranks to their stable-tie prefixes (the two-rank run
+    only ever adds one), and the candidate totals are gathered from more than one peer."""
+    out = str(tmp_path / "res3.pt")
+    mp.spawn(_worker, args=(3, _free_port(), out, False), nprocs=3, join=True)
+    _check_base_cases(torch.load(out), False)
