@@ -396,3 +396,34 @@ def test_failed_lists_are_repaired_per_query(R, rf):
     out = ev.evaluate(d, dl, q, ql, [R], 0.0, [1, 5], rf, return_ap=True)
     assert ev.stats["mode"] == "topR" and ev.stats["sample"].get("fallback"), ev.stats
     assert np.allclose(out[3].numpy(), oaps, atol=1e-12)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_sweep_of_paths_and_shapes(seed):
+    """CPU analogue of dev/fuzz_gpu.py: random shapes, code widths, label kinds, R (single / list / all), PRs,
+    remove_first, ternary thresholds, stripe sizes and path knobs (exact / sampled / two-level, POPC records /
+    candidate lists) -- every combination must give the oracle's per-query AP, means and curves."""
+    rng = np.random.default_rng(1000 + seed)
+    nq, ndb = int(rng.integers(1, 40)), int(rng.integers(20, 700))
+    nbit = int(rng.choice([8, 16, 32, 48, 64, 96, 128]))
+    ncls = int(rng.integers(2, 12))
+    d, dl, q, ql, _ = synth.make_random_case(nq, ndb, nbit, ncls, p=float(rng.choice([0.0, 0.3, 0.6])),
+                                             seed=2000 + seed)
+    rf = bool(rng.integers(0, 2)) and nq <= ndb
+    if rf:
+        q, ql = d[:nq].clone(), dl[:nq].clone()
+    if rng.integers(0, 3) == 0:                                   # multi-hot rows
+        dl, ql = synth.one_hot(dl, ncls), synth.one_hot(ql, ncls)
+        dl[rng.integers(0, ndb, ndb // 5), rng.integers(0, ncls)] = 1
+    thr = float(rng.choice([0.0, 0.0, 0.25]))
+    top = max(1, ndb - int(rf))
+    small = lambda: int(rng.integers(1, max(2, top // 6)))        # short lists: the top-R paths proper
+    kind = int(rng.integers(0, 6))
+    R = [-1, small(), small(), int(rng.integers(1, top + 1)), [small(), small()],
+         [small(), -1, int(rng.integers(1, top + 1))]][kind]
+    # P@k / R@k cut-offs lengthen the list a query needs: short ones beside a short R, any beside a long one
+    PRs = sorted({small() if kind in (1, 2, 4) else int(rng.integers(1, top + 1))
+                  for _ in range(int(rng.integers(0, 4)))})
+    sampled = bool(rng.integers(0, 2))
+    run_case(d, dl, q, ql, R, PRs, rf, thr, rps=int(rng.choice([32, 64, 256])), sampled=sampled,
+             tc=bool(rng.integers(0, 2)), two_level=sampled and bool(rng.integers(0, 2)))
