@@ -148,3 +148,16 @@ def test_three_ranks_match_oracle(tmp_path):
     out = str(tmp_path / "res3.pt")
     mp.spawn(_worker, args=(3, _free_port(), out, False), nprocs=3, join=True)
     _check_base_cases(torch.load(out), False)
+
+
+@pytest.mark.timeout(300)
+def test_random_shardings_match_oracle():
+    """A short run of tests/_shard_sweep.py: random cuts over three ranks (empty shards included), random R / PRs /
+    remove_first / thresholds / path knobs, each checked against the oracle over the whole gallery."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tests", "_shard_sweep.py"), "3", "0", "24"], cwd=root,
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "bad 0 of 24" in res.stdout, res.stdout[-2000:]
