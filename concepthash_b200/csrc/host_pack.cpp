@@ -202,17 +202,31 @@ uint32_t pack_rows_plain(const float* src, int64_t r0, int64_t r1, int ncols, in
   return fl;
 }
 
+typedef uint32_t (*pack_fn_t)(const float*, int64_t, int64_t, int, int64_t, int, uint32_t*);
+
+// The widest variant this host runs.  CH_HOST_PACK_ISA = avx2 | plain (read at every call: a few ns beside a piece of
+// >= 256 KB) narrows it, so that the variants a host without AVX-512 would take are tested on one that has it; a
+// variant the host cannot run is never chosen.
+pack_fn_t pick_pack_fn() {
+  static const int widest = [] {
+    __builtin_cpu_init();
+    return __builtin_cpu_supports("avx512f") ? 2 : __builtin_cpu_supports("avx2") ? 1 : 0;
+  }();
+  int level = widest;
+  if (const char* e = getenv("CH_HOST_PACK_ISA")) {
+    const int want = !strcmp(e, "plain") ? 0 : !strcmp(e, "avx2") ? 1 : 2;
+    if (want < level) level = want;
+  }
+  return level == 2 ? pack_rows_avx512 : level == 1 ? pack_rows_avx2 : pack_rows_plain;
+}
+
 }  // namespace
 
 // rows [0, n) of `src` (row stride rs floats, unit column stride) -> out (n, words) u32; returns the flag bits
 // (bit 0: some value is exactly 0, bit 1: NaN) exactly as the pack kernels raise them.
 uint32_t ch_host_pack_f32(const float* src, int64_t n, int ncols, int64_t rs, int words, uint32_t* out, int nthreads) {
   if (n <= 0) return 0;
-  typedef uint32_t (*fn_t)(const float*, int64_t, int64_t, int, int64_t, int, uint32_t*);
-  fn_t fn = pack_rows_plain;
-  __builtin_cpu_init();
-  if (__builtin_cpu_supports("avx512f")) fn = pack_rows_avx512;
-  else if (__builtin_cpu_supports("avx2")) fn = pack_rows_avx2;
+  const pack_fn_t fn = pick_pack_fn();
   // small inputs are not worth waking threads for (>= 1 MB of codes per thread)
   const int64_t bytes = n * static_cast<int64_t>(ncols) * 4;
   int nt = nthreads;
@@ -283,14 +297,7 @@ void ch_host_pool_run(int which, int n, const std::function<void(int)>& fn) {
 
 // rows [r0, r1) of `src` -> dst (r1 - r0, words) u32 on the calling thread; returns the flag bits (loader.cu)
 uint32_t ch_host_pack_rows(const float* src, int64_t r0, int64_t r1, int ncols, int64_t rs, int words, uint32_t* dst) {
-  typedef uint32_t (*fn_t)(const float*, int64_t, int64_t, int, int64_t, int, uint32_t*);
-  static const fn_t fn = [] {
-    __builtin_cpu_init();
-    if (__builtin_cpu_supports("avx512f")) return static_cast<fn_t>(pack_rows_avx512);
-    if (__builtin_cpu_supports("avx2")) return static_cast<fn_t>(pack_rows_avx2);
-    return static_cast<fn_t>(pack_rows_plain);
-  }();
-  return fn(src + r0 * rs, 0, r1 - r0, ncols, rs, words, dst);
+  return pick_pack_fn()(src + r0 * rs, 0, r1 - r0, ncols, rs, words, dst);
 }
 
 // memcpy of a large pageable block into a pinned bounce buffer by the same pool (~256 KB pieces): a pageable

@@ -78,6 +78,42 @@ def lib_call_fails(ws):
     return rc != 0 and len(lib.ch_last_error()) > 0
 
 
+@pytest.mark.parametrize("isa", ["avx2", "plain"])
+def test_host_pack_narrower_isa_variants(lib, isa, monkeypatch):
+    """The packer picks AVX-512 on the B200 hosts; CH_HOST_PACK_ISA narrows it so that the AVX2 and scalar variants
+    (what a host without AVX-512 runs) are held to the same bits and flags: every width around the vector and word
+    boundaries, strided rows, +-0.0, NaN, row counts that are no multiple of anything."""
+    import numpy as np
+    rng = np.random.RandomState(7)
+    for nbit in (1, 7, 8, 9, 15, 16, 17, 31, 32, 33, 48, 63, 64, 65, 100, 128, 129, 200, 255, 256):
+        n, stride = 613, nbit + 3
+        buf = rng.randn(n, stride).astype(np.float32)
+        x = buf[:, :nbit]
+        x[2, 0] = 0.0
+        x[4, nbit - 1] = -0.0
+        x[6, nbit // 2] = np.float32(1e-45)
+        words = lib.ch_code_words(nbit)
+        for nan in (False, True):
+            if nan:
+                x[n - 1, nbit - 1] = np.nan
+            want = np.zeros((n, words * 32), dtype=np.uint8)
+            want[:, :nbit] = x > 0
+            want = np.packbits(want, axis=1, bitorder="little").view(np.uint32)
+            res = {}
+            for which in (None, isa):
+                if which is None:
+                    monkeypatch.delenv("CH_HOST_PACK_ISA", raising=False)
+                else:
+                    monkeypatch.setenv("CH_HOST_PACK_ISA", which)
+                out = np.full((n, words), 0xDEADBEEF, dtype=np.uint32)
+                flags = ctypes.c_uint32(0)
+                assert lib.ch_host_pack_sign(buf.ctypes.data, n, nbit, stride, out.ctypes.data, ctypes.byref(flags), 3) == 0
+                res[which] = (out, flags.value)
+            assert np.array_equal(res[isa][0], want), (isa, nbit)
+            assert np.array_equal(res[None][0], want), nbit
+            assert res[isa][1] == res[None][1] == (3 if nan else 1), (isa, nbit, res[isa][1], res[None][1])
+
+
 @pytest.mark.parametrize("nbit", [1, 8, 31, 32, 33, 64, 100, 128, 200, 256])
 def test_host_pack_sign_bit_exact(lib, nbit):
     """ch_host_pack_sign (the host half of K1 for pageable fp32 codes; runs without a GPU): bit = (x > 0) exactly --
