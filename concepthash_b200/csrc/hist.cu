@@ -155,7 +155,9 @@ __global__ void __launch_bounds__(256, (NW <= 2 && !TERN) ? 3 : 1) hamming_hist_
   if (LAB == CH_LAB_MASK)
     for (int w = 0; w < lw; ++w) qmask[w * T + tid] = active ? a.q_lab[q * lw + w] : 0u;
   uint32_t thr = 0;
-  if (THRESH && active) thr = a.thresh[q];
+  // nbins may have been narrowed from a HINT of the largest threshold (key_limit): a threshold beyond it is flagged
+  // by exscan_check_kernel (status bit 3) and the evaluation is repeated -- this launch must only stay in bounds
+  if (THRESH && active) thr = min(a.thresh[q], static_cast<uint32_t>(a.nbins - 1));
 
   for (int b = 0; b < a.nbins; ++b) *reinterpret_cast<uint32_t*>(hist_b + b * T4) = 0u;
 

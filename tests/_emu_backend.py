@@ -160,6 +160,12 @@ class EmuBackend:
         sa = _u32(slab_all)
         sr = _u32(slab_rel) if slab_rel is not None else None
         th = _u32(thresh) if thresh is not None else None
+        full = (2 * nbit if ternary else nbit) + 1
+        if th is not None and 0 < key_limit < full:
+            # the kernel indexes the slabs with nbins = key_limit
+            assert sa.shape[1] == key_limit, (sa.shape, key_limit)
+            # the kernel clamps a threshold beyond the (hinted) key range: record_offsets_async has flagged it
+            th = np.minimum(th, np.uint32(key_limit - 1))
         if emit_mode != CH_EMIT_NONE:
             off, cap, cnt, rc = _u32(rec_off), _u32(rec_cap), _u32(rec_cnt), _u32(recs)
         for s in range(nstripes):

@@ -427,3 +427,68 @@ def test_random_sweep_of_paths_and_shapes(seed):
     sampled = bool(rng.integers(0, 2))
     run_case(d, dl, q, ql, R, PRs, rf, thr, rps=int(rng.choice([32, 64, 256])), sampled=sampled,
              tc=bool(rng.integers(0, 2)), two_level=sampled and bool(rng.integers(0, 2)))
+
+
+@pytest.mark.parametrize("seed", [1, 3, 19, 30, 174, 183, 5, 8])
+def test_repeated_evaluations_with_changing_data(seed):
+    """Four evaluations of one shape on ONE evaluator while the data change under it (tie density, zeros appear ->
+    ternary keys, labels become multi-hot, one huge tie bucket, everything relevant): buffer sizes and key ranges
+    assumed from the previous evaluation must be verified and the run repeated when they fail -- never an
+    out-of-range key (the hinted key range of the POPC select pass once let a larger threshold write past its
+    histogram: seeds 1, 3, 19, 30, 174, 183 of the sweep this comes from) and never a different number."""
+    rng = np.random.default_rng(seed)
+    nq, ndb = int(rng.integers(1, 40)), int(rng.integers(40, 700))
+    nbit = int(rng.choice([16, 32, 64, 128]))
+    ncls = int(rng.integers(2, 12))
+    tc = bool(rng.integers(0, 2))
+    rps = int(rng.choice([32, 64, 256]))
+    ev = Evaluator(EmuBackend(rows_per_stripe=rps, threads=128, tensor_cores=True) if tc
+                   else EmuBackend(rows_per_stripe=rps))
+    if bool(rng.integers(0, 2)):
+        ev.sample_stride, ev.sample_min_rows, ev.sample_min_ratio = 4, 0, 4
+    else:
+        ev.sample_stride = 0
+    small = lambda: int(rng.integers(1, max(2, ndb // 6)))
+    R = [-1, small(), small(), [small(), small()]][int(rng.integers(0, 4))]
+    PRs = sorted({small() for _ in range(int(rng.integers(0, 3)))})
+    for rep in range(4):
+        p = float(rng.choice([0.0, 0.3, 0.8]))
+        d, dl, q, ql, _ = synth.make_random_case(nq, ndb, nbit, ncls, p=p, seed=seed * 10 + rep)
+        kind = int(rng.integers(0, 5))
+        if kind == 0:
+            d[:: int(rng.integers(2, 9)), int(rng.integers(0, nbit))] = 0
+        if kind == 1:
+            dl, ql = synth.one_hot(dl, ncls), synth.one_hot(ql, ncls)
+            dl[::3, 0] = 1
+        if kind == 2:
+            d[:] = d[0]
+        if kind == 3:
+            dl[:] = dl[0]
+            ql[:] = dl[0]
+        maps, rec, prec, ap = ev.evaluate(d, dl, q, ql, R if isinstance(R, list) else [R], 0.0, PRs, False,
+                                          return_ap=True)
+        om, orec, oprec, oaps = mo.calculate_mAP(d, dl, q, ql, R, PRs=PRs, return_per_query=True)
+        om = om if isinstance(om, list) else [om]
+        assert np.allclose(ap.numpy(), oaps, atol=1e-12), (rep, kind, ev.stats)
+        assert np.allclose(maps, om, atol=1e-12) and np.allclose(rec, orec, atol=1e-12)
+        assert np.allclose(prec, oprec, atol=1e-12)
+
+
+def test_hinted_key_range_outgrown_by_the_next_evaluation():
+    """Tight clusters first (thresholds of 0-2 keys), near-random codes of the same shape next (thresholds ~20): the
+    POPC select pass of the second evaluation runs with slabs as narrow as the FIRST one's largest threshold + 3.  The
+    kernel clamps, the device check flags it, the evaluation is repeated -- and gives the oracle's numbers."""
+    ev = Evaluator(EmuBackend(rows_per_stripe=256))
+    ev.sample_stride, ev.sample_min_rows, ev.sample_min_ratio = 4, 0, 4
+    seen = []
+    for p, seed in ((0.02, 1), (0.02, 1), (0.45, 2)):
+        d, dl, q, ql, _ = synth.make_random_case(24, 1500, 64, 5, p=p, seed=seed)
+        maps, rec, prec, ap = ev.evaluate(d, dl, q, ql, [10], 0.0, [1, 5], False, return_ap=True)
+        om, orec, oprec, oaps = mo.calculate_mAP(d, dl, q, ql, 10, PRs=[1, 5], return_per_query=True)
+        assert np.allclose(ap.numpy(), oaps, atol=1e-12) and abs(maps[0] - om) < 1e-12
+        assert np.allclose(rec, orec, atol=1e-12) and np.allclose(prec, oprec, atol=1e-12)
+        seen.append((ev.stats["mode"], ev.stats["select_kernel"], ev.stats["speculation"],
+                     ev.stats["sample"]["key_limit"]))
+    assert [s[:3] for s in seen] == [("topR-sampled", "popc", "none"), ("topR-sampled", "popc", "hit"),
+                                     ("topR-sampled", "popc", "retried")], seen
+    assert seen[2][3] > seen[1][3] + 3, seen          # the key range really was outgrown

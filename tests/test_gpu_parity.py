@@ -867,3 +867,31 @@ def test_empty_queries_convention(H):
             assert s[0] > z[0] + 1e-3            # (the case does hold empty lists)
     with pytest.raises(ValueError):
         H.calculate_mAP(d.cuda(), dl.cuda(), q.cuda(), ql.cuda(), 5, empty_queries="drop")
+
+
+def test_hinted_key_range_outgrown_on_gpu(H):
+    """POPC select pass (``use_tensor_cores=False``; also what wide ternary codes take) evaluated three times on one
+    shape: tight clusters twice (thresholds of 0-2 keys; the second run sizes its slabs from the first one's largest
+    threshold + 3), then near-random codes (thresholds ~15).  The kernel must clamp the thresholds to the narrowed
+    key range (hist.cu), the device check flags the evaluation and it is repeated: the oracle's numbers every time.
+    CPU twin: tests/test_evaluator_emu.py::test_hinted_key_range_outgrown_by_the_next_evaluation."""
+    ev = H.get_evaluator()
+    nq, ndb, nbit, ncls, R = 1234, 260_000, 64, 20, 50
+    seen = []
+    ev.use_tensor_cores = False
+    try:
+        for p, seed in ((0.02, 1), (0.02, 1), (0.45, 2), (0.45, 2)):
+            d, dl, q, ql, _ = synth.make_random_case(nq, ndb, nbit, ncls, p=p, seed=seed, device="cuda")
+            out = ev.evaluate(d, dl, q, ql, [R], 0.0, [1, 10], False, return_ap=True)
+            sub = slice(0, 24)
+            om, orec, oprec, oaps = mo.calculate_mAP(d.cpu(), dl.cpu(), q[sub].cpu(), ql[sub].cpu(), R, PRs=[1, 10],
+                                                     return_per_query=True)
+            assert np.allclose(out[3][0][sub].cpu().numpy(), oaps[0], atol=TOL), (p, seed, ev.stats)
+            seen.append((ev.stats["mode"], ev.stats["select_kernel"], ev.stats["speculation"],
+                         (ev.stats.get("sample") or {}).get("key_limit", -1)))
+    finally:
+        ev.use_tensor_cores = True
+    assert all(s[0].startswith("topR") and s[1] == "popc" for s in seen), seen
+    assert seen[1][2] == "hit" and seen[2][2] != "hit", seen
+    if all(s[0] == "topR-sampled" for s in seen[:3]):
+        assert seen[2][3] > seen[1][3] + 3, seen      # the key range really was outgrown
